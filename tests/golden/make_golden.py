@@ -1,0 +1,305 @@
+"""Generate the golden fixtures by running the UNMODIFIED reference (/root/reference) on CPU.
+
+Run in the build container only (the GPU box has no /root/reference):
+    python tests/golden/make_golden.py
+Shims are applied before importing reference modules; no reference source is
+copied.  Inputs are regenerated from seeds in the tests; checksums stored here pin them.
+"""
+import os
+import sys
+import tempfile
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+
+# --- shims -----------------------------------------------------------------------------------
+sys.modules["kaldi_io"] = types.ModuleType("kaldi_io")       # plda.py:13, only ReadIvectors uses it
+np.infty = np.inf                                             # removed in NumPy 2
+import torchaudio  # noqa: E402
+
+_librosa = types.ModuleType("librosa")
+_librosa.filters = types.ModuleType("librosa.filters")
+
+
+def _mel(sr, n_fft, n_mels=128, fmin=0.0, fmax=None):
+    fmax = sr / 2 if fmax is None else fmax
+    return torchaudio.functional.melscale_fbanks(n_fft // 2 + 1, float(fmin), float(fmax), n_mels, sr,
+                                                 norm="slaney", mel_scale="slaney").T.numpy()
+
+
+_librosa.filters.mel = _mel
+sys.modules["librosa"] = _librosa
+sys.modules["librosa.filters"] = _librosa.filters
+_orig_stft = torch.stft
+
+
+def _stft(*a, **k):
+    k["return_complex"] = True
+    return torch.view_as_real(_orig_stft(*a, **k))
+
+
+from oracle import sg_oracle as O  # noqa: E402
+
+
+def vec(v):
+    return " [ " + " ".join("%.6f" % x for x in v) + " ]\n"
+
+
+def rows(M):
+    return "".join("  " + " ".join("%.6f" % x for x in r) + (" \n" if i < len(M) - 1 else " ]\n")
+                   for i, r in enumerate(M))
+
+
+def build_reference_xv(p, tmp, threshold=None):
+    from model._xv_plda.xvecTDNN import xvecTDNN
+    from model.xv_plda import xv_plda
+    torch.manual_seed(0)
+    net = xvecTDNN(numSpkrs=100)
+    sd = net.state_dict()
+    for i in range(1, 6):
+        assert torch.equal(sd[f"tdnn{i}.weight"], p[f"tdnn{i}.weight"]), "init order mismatch"
+        assert torch.equal(sd[f"tdnn{i}.bias"], p[f"tdnn{i}.bias"])
+        getattr(net, f"bn_tdnn{i}").running_mean.copy_(p[f"bn{i}.mean"])
+        getattr(net, f"bn_tdnn{i}").running_var.copy_(p[f"bn{i}.var"])
+    assert torch.equal(sd["fc1.weight"], p["fc1.weight"])
+    L = p["plda.mean"].shape[0]
+    with open(f"{tmp}/plda.txt", "w") as f:
+        f.write("<Plda> " + vec(p["plda.mean"].tolist()) + " [\n" + rows(p["plda.transform"].tolist())
+                + vec(p["plda.psi"].tolist()) + "</Plda> \n")
+    with open(f"{tmp}/mean.vec", "w") as f:
+        f.write(vec(p["emb_mean"].tolist()))
+    with open(f"{tmp}/transform.txt", "w") as f:
+        f.write(" [\n" + rows(p["lda"].tolist()))
+    with open(f"{tmp}/speaker_model", "w") as f:
+        for s in range(p["enroll"].shape[0]):
+            path = f"{tmp}/spk{s}.emb"
+            torch.save(p["enroll"][s:s + 1].clone(), path)
+            f.write(f"spk{s} {path} 0.0 1.0\n")
+    model = xv_plda(net, f"{tmp}/plda.txt", f"{tmp}/mean.vec", f"{tmp}/transform.txt",
+                    model_file=f"{tmp}/speaker_model", threshold=threshold)
+    model.eval()
+    assert model.plda.dim == L
+    for k, v in [("plda.mean", model.plda.mean), ("plda.transform", model.plda.transform),
+                 ("plda.psi", model.plda.psi), ("emb_mean", model.emb_mean), ("lda", model.transform_mat),
+                 ("enroll", model.enroll_embs)]:
+        assert torch.equal(v, p[k]), f"parser round trip differs for {k}"
+    return model
+
+
+class RandnTap:
+    """Record every torch.randn draw (the dither of kaldi.py:180)."""
+
+    def __enter__(self):
+        self.draws = []
+        self._orig = torch.randn
+
+        def tap(*a, **k):
+            t = self._orig(*a, **k)
+            self.draws.append(t.clone())
+            return t
+        torch.randn = tap
+        return self
+
+    def __exit__(self, *exc):
+        torch.randn = self._orig
+
+
+def make_inputs(seed, B, N, S=10):
+    torch.manual_seed(seed)
+    x = (torch.rand(B, 1, N) * 2 - 1) * 0.5
+    y = torch.randint(0, S, (B,))
+    return x, y
+
+
+def cks(t):
+    return np.float64(t.double().abs().sum().item())
+
+
+def forward_case(model, p, tag, seed, B, N, out):
+    from attack.utils import SEC4SR_CrossEntropy
+    x, y = make_inputs(seed, B, N)
+    xr = x.clone().requires_grad_(True)
+    hooks, acts = [], {}
+    net = model.extractor.extractor
+    for i in range(1, 6):
+        hooks.append(getattr(net, f"bn_tdnn{i}").register_forward_hook(
+            lambda m, a, o, i=i: acts.setdefault(i, []).append(o.detach().clone())))
+    torch.manual_seed(seed + 1)
+    with RandnTap() as tap:
+        raw = model.compute_feat(xr, flag=1)
+    dither = torch.stack(tap.draws)
+    torch.manual_seed(seed + 1)
+    regen = torch.stack([torch.randn((O.num_frames(N), 400)) for _ in range(B)])
+    assert torch.equal(dither, regen)
+    feat = model.comput_feat_from_feat(raw, 1, 2)
+    emb = model.embedding(feat, flag=2)
+    scores = model.scoring_trials(model.enroll_embs, emb)
+    for h in hooks:
+        h.remove()
+    dec = torch.argmax(scores, 1)
+    loss = SEC4SR_CrossEntropy(reduction="none", task="CSI")(scores, y)
+    loss.backward(torch.ones_like(loss))
+    grad = xr.grad.detach()
+    out.update({
+        f"{tag}.seed": seed, f"{tag}.B": B, f"{tag}.N": N,
+        f"{tag}.x_cks": cks(x), f"{tag}.dither_cks": cks(dither), f"{tag}.y": y.numpy(),
+        f"{tag}.raw": raw.detach().numpy(), f"{tag}.feat": feat.detach().numpy(),
+        f"{tag}.emb": emb.detach().numpy(), f"{tag}.scores": scores.detach().numpy(),
+        f"{tag}.dec": dec.numpy(), f"{tag}.loss": loss.detach().numpy(), f"{tag}.grad": grad[:, 0].numpy(),
+    })
+    for i in range(1, 6):
+        a = torch.cat(acts[i], 0)           # [B,C,T_l]; keep utterance 0, first 48 channels
+        out[f"{tag}.act{i}"] = a[0, :48].numpy()
+        out[f"{tag}.act{i}_abs_sum"] = np.float64(a.double().abs().sum().item())
+    # oracle vs reference, reported at generation time
+    o = O.xv_forward(x[:, 0], p, dither, return_all=True)
+    print(f"[{tag}] oracle-vs-ref max|d| raw {float((o['raw'] - raw).abs().max()):.3e} "
+          f"feat {float((o['feat'] - feat).abs().max()):.3e} emb {float((o['emb'] - emb).abs().max()):.3e} "
+          f"scores {float((o['scores'] - scores).abs().max()):.3e}")
+
+
+def attack_case(model, p, tag, seed, B, N, out, kind, **kw):
+    from attack.FGSM import FGSM
+    from attack.PGD import PGD
+    from attack.CWinf import CWinf
+    cls = {"FGSM": FGSM, "PGD": PGD, "CWinf": CWinf}[kind]
+    x, y = make_inputs(seed, B, N)
+    att = cls(model, batch_size=B, verbose=0, **kw)
+    torch.manual_seed(seed + 1)
+    with RandnTap() as tap:
+        adv, success = att.attack(x, y)
+    n_pass = att.max_iter + 1
+    m = O.num_frames(N)
+    assert len(tap.draws) == n_pass * B
+    dither = torch.stack(tap.draws).view(n_pass, B, m, 400)
+    torch.manual_seed(seed + 1)
+    regen = torch.stack([torch.randn((m, 400)) for _ in range(n_pass * B)]).view(n_pass, B, m, 400)
+    assert torch.equal(dither, regen)
+    with torch.no_grad():
+        dec, scores = model.make_decision(adv.detach())   # fresh dither: informational only
+    out.update({f"{tag}.seed": seed, f"{tag}.B": B, f"{tag}.N": N, f"{tag}.n_pass": n_pass,
+                f"{tag}.x_cks": cks(x), f"{tag}.dither_cks": cks(dither), f"{tag}.y": y.numpy(),
+                f"{tag}.adv": adv.detach()[:, 0].numpy(), f"{tag}.success": np.array(success)})
+    xa, suc, info = O.pgd_attack(x[:, 0], y, p, dither=dither, fgsm=(kind == "FGSM"),
+                                 loss_name="Margin" if kind == "CWinf" else kw.get("loss", "Entropy"),
+                                 targeted=kw.get("targeted", False),
+                                 **{k: v for k, v in kw.items() if k in ("epsilon", "step_size", "max_iter")})
+    mism = float((xa != adv.detach()[:, 0]).float().mean())
+    print(f"[{tag}] success {sum(success)}/{B}; oracle iterate mismatch fraction {mism:.2e}; "
+          f"oracle success equal: {suc == success}")
+
+
+def audionet_case(out):
+    torch.stft = _stft
+    try:
+        from model.audionet_csine import audionet_csine
+        p = O.make_audionet_params(seed=0, num_class=251)
+        torch.manual_seed(0)
+        model = audionet_csine(num_class=251)
+        sd = model.state_dict()
+        assert torch.equal(sd["conv2.0.weight"], p["conv2.weight"]), "audionet init order mismatch"
+        assert torch.equal(sd["fc.weight"], p["fc.weight"])
+        mods = {"conv1": model.conv1[1], **{n: getattr(model, n)[1] for n, *_ in O.AN_CONVS}}
+        for n, bn in mods.items():
+            bn.running_mean.copy_(p[f"{n}.bn_mean"])
+            bn.running_var.copy_(p[f"{n}.bn_var"])
+            bn.weight.data.copy_(p[f"{n}.bn_gamma"])
+            bn.bias.data.copy_(p[f"{n}.bn_beta"])
+        model.eval()
+        for N, tag in [(16000, "an1s"), (48000, "an3s")]:
+            B = 4
+            x, _ = make_inputs(4321, B, N)
+            torch.manual_seed(5)
+            y = torch.randint(0, 251, (B,))
+            xr = x.clone().requires_grad_(True)
+            feat = model.compute_feat(xr, flag=1)
+            logits = model(feat, flag=1)
+            from attack.utils import SEC4SR_MarginLoss
+            loss = SEC4SR_MarginLoss(targeted=True, task="CSI", clip_max=True)(logits, y)
+            loss.backward(torch.ones_like(loss))
+            out.update({f"{tag}.B": B, f"{tag}.N": N, f"{tag}.x_cks": cks(x), f"{tag}.y": y.numpy(),
+                        f"{tag}.feat": feat.detach().numpy(), f"{tag}.logits": logits.detach().numpy(),
+                        f"{tag}.loss": loss.detach().numpy(), f"{tag}.grad": xr.grad[:, 0].numpy()})
+            o = O.audionet_forward(x[:, 0], p, return_all=True)
+            print(f"[{tag}] oracle-vs-ref max|d| feat {float((o['feat'].transpose(1, 2) - feat).abs().max()):.3e} "
+                  f"logits {float((o['logits'] - logits).abs().max()):.3e}")
+        # CW2, tiny budget (2 search steps x 20 iterations)
+        from attack.CW2 import CW2
+        B, N = 4, 16000
+        x, _ = make_inputs(777, B, N)
+        with torch.no_grad():
+            pred = model(x).argmax(1)
+        y = (pred + 1) % 251
+        att = CW2(model, targeted=True, initial_const=1e3, binary_search_steps=2, max_iter=20,
+                  stop_early=True, stop_early_iter=10, lr=1e-2, batch_size=B, verbose=0)
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):
+            adv, success = att.attack(x, y)
+        out.update({"cw2.B": B, "cw2.N": N, "cw2.x_cks": cks(x), "cw2.y": y.numpy(),
+                    "cw2.adv": adv.detach()[:, 0].numpy(), "cw2.success": np.array(success)})
+        xa, suc, _ = O.cw2_attack(x[:, 0], y, lambda z: O.audionet_forward(z, p), targeted=True,
+                                  initial_const=1e3, binary_search_steps=2, max_iter=20, stop_early=True,
+                                  stop_early_iter=10, lr=1e-2)
+        print(f"[cw2] success {success}; oracle max|d adv| {float((xa - adv.detach()[:, 0]).abs().max()):.3e} "
+              f"success equal: {suc == success}")
+    finally:
+        torch.stft = _orig_stft
+
+
+def feco_case(out):
+    """Conditional FeCo golden: the reference's own mean-by-cluster code driven with fixed ids."""
+    km = types.ModuleType("kmeans_pytorch")
+    ids_box = {}
+    km.kmeans = lambda X, num_clusters, distance, device: (ids_box["ids"], None)
+    sys.modules["kmeans_pytorch"] = km
+    from defense.feature_level import FeCo
+    g = torch.Generator().manual_seed(99)
+    feat = torch.randn(1, 120, 30, generator=g, requires_grad=True)
+    k = 60
+    ids = torch.randint(0, k, (120,), generator=g)
+    ids[ids == 7] = 8                                      # force an empty cluster
+    ids_box["ids"] = ids
+    y = FeCo(torch.cat([feat, feat]), "kmeans", 0.5, "L2")   # batch 2 => force=True
+    w = torch.randn(y.shape, generator=g)
+    (y * w).sum().backward()
+    out.update({"feco.feat": feat.detach().numpy()[0], "feco.ids": ids.numpy(), "feco.k": k,
+                "feco.out": y.detach().numpy()[0], "feco.w": w.numpy(), "feco.grad": feat.grad.numpy()[0]})
+
+
+def main():
+    torch.set_num_threads(8)
+    out = {}
+    p = O.make_xv_params(seed=0)
+    out["params_cks"] = np.float64(O.params_checksum(p))
+    with tempfile.TemporaryDirectory() as tmp:
+        model = build_reference_xv(p, tmp)
+        forward_case(model, p, "fwd2s", 1234, 4, 32000, out)
+        forward_case(model, p, "fwd5s", 4242, 2, 80000, out)
+        forward_case(model, p, "fwd1p1s", 99, 2, 17777, out)      # ragged length, m = 111
+        attack_case(model, p, "fgsm", 1234, 8, 32000, out, "FGSM", epsilon=0.002)
+        attack_case(model, p, "pgd3", 2024, 4, 48000, out, "PGD", epsilon=0.002, step_size=0.0004, max_iter=3)
+        attack_case(model, p, "pgd3t", 2025, 4, 32000, out, "PGD", epsilon=0.002, step_size=0.0004, max_iter=3,
+                    targeted=True)
+        attack_case(model, p, "cwinf3", 2026, 4, 32000, out, "CWinf", epsilon=0.002, step_size=0.0004, max_iter=3)
+    audionet_case(out)
+    feco_case(out)
+    xv = {k: v for k, v in out.items() if not k.startswith(("an", "cw2", "feco"))}
+    np.savez_compressed(os.path.join(HERE, "xv_golden.npz"), **xv)
+    np.savez_compressed(os.path.join(HERE, "audionet_golden.npz"),
+                        **{k: v for k, v in out.items() if k.startswith(("an", "cw2"))})
+    np.savez_compressed(os.path.join(HERE, "feco_golden.npz"),
+                        **{k: v for k, v in out.items() if k.startswith("feco")})
+    for f in ("xv_golden.npz", "audionet_golden.npz", "feco_golden.npz"):
+        print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,122 @@
+"""Pins oracle/sg_oracle.py against fixtures produced by the unmodified reference
+(tests/golden/make_golden.py).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sg_oracle as O
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def xv():
+    return np.load(os.path.join(G, "xv_golden.npz"))
+
+
+@pytest.fixture(scope="module")
+def params():
+    return O.make_xv_params(seed=0)
+
+
+def regen(g, tag, n_pass=None):
+    seed, B, N = int(g[f"{tag}.seed"]), int(g[f"{tag}.B"]), int(g[f"{tag}.N"])
+    torch.manual_seed(seed)
+    x = (torch.rand(B, 1, N) * 2 - 1) * 0.5
+    y = torch.randint(0, 10, (B,))
+    m = O.num_frames(N)
+    torch.manual_seed(seed + 1)
+    n = B if n_pass is None else n_pass * B
+    d = torch.stack([torch.randn((m, 400)) for _ in range(n)])
+    d = d if n_pass is None else d.view(n_pass, B, m, 400)
+    assert abs(float(x.double().abs().sum()) - float(g[f"{tag}.x_cks"])) < 1e-9, "input regeneration drifted"
+    assert abs(float(d.double().abs().sum()) - float(g[f"{tag}.dither_cks"])) < 1e-6, "dither regeneration drifted"
+    assert np.array_equal(y.numpy(), g[f"{tag}.y"])
+    return x[:, 0], y, d
+
+
+def test_params_regenerate(xv, params):
+    assert abs(O.params_checksum(params) - float(xv["params_cks"])) < 1e-6
+
+
+@pytest.mark.parametrize("tag", ["fwd2s", "fwd5s", "fwd1p1s"])
+def test_forward_stages(xv, params, tag):
+    x, y, d = regen(xv, tag)
+    o = O.xv_forward(x, params, d, return_all=True)
+    assert np.array_equal(o["raw"].numpy(), xv[f"{tag}.raw"])            # same torch ops: bit-exact
+    np.testing.assert_allclose(o["feat"].numpy(), xv[f"{tag}.feat"], atol=5e-5, rtol=0)
+    np.testing.assert_allclose(o["emb"].numpy(), xv[f"{tag}.emb"], atol=5e-6, rtol=1e-5)
+    np.testing.assert_allclose(o["scores"].numpy(), xv[f"{tag}.scores"], atol=2e-4, rtol=0)
+    assert np.array_equal(O.decide(o["scores"]).numpy(), xv[f"{tag}.dec"])
+    acts = O.tdnn_layers(O.cmvn(O.mfcc(x, d)), params)
+    for i in range(1, 6):
+        np.testing.assert_allclose(acts[i - 1][0, :48].numpy(), xv[f"{tag}.act{i}"], atol=2e-4, rtol=1e-4)
+
+
+@pytest.mark.parametrize("tag", ["fwd2s", "fwd1p1s"])
+def test_input_gradient(xv, params, tag):
+    x, y, d = regen(xv, tag)
+    scores, loss, grad, dec = O.xv_loss_and_grad(x, y, params, O.loss_ce, d)
+    np.testing.assert_allclose(loss.numpy(), xv[f"{tag}.loss"], atol=2e-4, rtol=1e-4)
+    ref = xv[f"{tag}.grad"]
+    err = np.abs(grad.numpy() - ref).max(axis=1) / np.abs(ref).max(axis=1)
+    assert err.max() < 1e-4, err
+
+
+def test_cmvn_closed_form_equals_loop():
+    g = torch.Generator().manual_seed(3)
+    for T in (1, 7, 299, 300, 301, 450, 700):
+        f = torch.randn(1, T, 5, generator=g) * 10
+        np.testing.assert_allclose(O.cmvn(f).numpy(), O.cmvn_loop(f).numpy(), atol=2e-5, rtol=0)
+
+
+@pytest.mark.parametrize("tag,kw", [
+    ("fgsm", dict(fgsm=True, epsilon=0.002)),
+    ("pgd3", dict(epsilon=0.002, step_size=0.0004, max_iter=3)),
+    ("pgd3t", dict(epsilon=0.002, step_size=0.0004, max_iter=3, targeted=True)),
+    ("cwinf3", dict(epsilon=0.002, step_size=0.0004, max_iter=3, loss_name="Margin")),
+])
+def test_attack_iterates(xv, params, tag, kw):
+    x, y, d = regen(xv, tag, int(xv[f"{tag}.n_pass"]))
+    adv, success, info = O.pgd_attack(x, y, params, dither=d, **kw)
+    ref = xv[f"{tag}.adv"]
+    mism = float((adv.numpy() != ref).mean())
+    assert mism < 1e-3, mism          # sign flips only where |grad| ~ 0
+    assert success == xv[f"{tag}.success"].tolist()
+
+
+def test_audionet(params):
+    g = np.load(os.path.join(G, "audionet_golden.npz"))
+    p = O.make_audionet_params(seed=0, num_class=251)
+    for tag in ("an1s", "an3s"):
+        B, N = int(g[f"{tag}.B"]), int(g[f"{tag}.N"])
+        torch.manual_seed(4321)
+        x = ((torch.rand(B, 1, N) * 2 - 1) * 0.5)[:, 0]
+        assert abs(float(x.double().abs().sum()) - float(g[f"{tag}.x_cks"])) < 1e-9
+        y = torch.tensor(g[f"{tag}.y"])
+        xr = x.clone().requires_grad_(True)
+        o = O.audionet_forward(xr, p, return_all=True)
+        np.testing.assert_allclose(o["feat"].transpose(1, 2).detach().numpy(), g[f"{tag}.feat"], atol=2e-4, rtol=0)
+        np.testing.assert_allclose(o["logits"].detach().numpy(), g[f"{tag}.logits"], atol=1e-5, rtol=1e-5)
+        loss = O.loss_margin(o["logits"], y, targeted=True, clip_max=True)
+        loss.backward(torch.ones_like(loss))
+        np.testing.assert_allclose(loss.detach().numpy(), g[f"{tag}.loss"], atol=1e-5, rtol=1e-5)
+        ref = g[f"{tag}.grad"]
+        err = np.abs(xr.grad.numpy() - ref).max(axis=1) / np.abs(ref).max(axis=1)
+        assert err.max() < 1e-4, err
+
+
+def test_feco_conditional():
+    g = np.load(os.path.join(G, "feco_golden.npz"))
+    feat = torch.tensor(g["feco.feat"], requires_grad=True)
+    out = O.feco_means(feat, g["feco.ids"], int(g["feco.k"]), force=True)
+    np.testing.assert_allclose(out.detach().numpy(), g["feco.out"], atol=1e-6, rtol=1e-6)
+    (out * torch.tensor(g["feco.w"][0])).sum().backward()
+    # the reference fixture fed the same feat twice (batch 2): its grad sums both batch rows
+    w = torch.tensor(g["feco.w"])
+    feat2 = torch.tensor(g["feco.feat"], requires_grad=True)
+    tot = sum((O.feco_means(feat2, g["feco.ids"], int(g["feco.k"])) * w[i]).sum() for i in range(2))
+    tot.backward()
+    np.testing.assert_allclose(feat2.grad.numpy(), g["feco.grad"], atol=1e-6, rtol=1e-5)
