@@ -1,0 +1,169 @@
+/* libsgb200 -- C-ABI of the B200-native engine for SpeakerGuard's attack-iteration hot path.
+ *
+ * Every entry point replaces a piece of the reference's Python/PyTorch path (citations are
+ * relative to the SpeakerGuard repository; "kaldi.py" = torchaudio/compliance/kaldi.py).
+ * Conventions:
+ *   - plain C types only; all tensor arguments are raw DEVICE pointers to fp32 / int64 data
+ *     owned by the caller (PyTorch's caching allocator), except sg_load_* which take HOST pointers;
+ *   - every function returns 0 (SG_OK) or a negative SG_E* code; the message is read with
+ *     sg_last_error() (thread-local); no C++ exception crosses the boundary;
+ *   - functions enqueue work on `stream` (a cudaStream_t passed as void*) and do not synchronise;
+ *   - a handle is bound to one device, holds the packed weights/tables, is not re-entrant;
+ *   - the library never allocates per-call memory: workspaces are sized by sg_*_ws_bytes() and
+ *     passed in by the caller.
+ * There is no CPU fallback: without a CUDA device every compute entry point fails with SG_ECUDA.
+ */
+#ifndef SGB200_H_
+#define SGB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGB200_VERSION 100
+
+typedef struct sg_handle sg_handle;
+typedef void* sg_stream; /* cudaStream_t */
+
+enum { SG_OK = 0, SG_EINVAL = -1, SG_ECUDA = -2, SG_ESTATE = -3, SG_EUNSUPPORTED = -4 };
+
+/* arithmetic of the TDNN contractions (everything else is always fp32) */
+enum { SG_PREC_FP32 = 0 /* FFMA, parity mode */, SG_PREC_TF32 = 1 /* tcgen05 kind::tf32 */,
+       SG_PREC_BF16 = 2 /* tcgen05 kind::f16, bf16 operands, fp32 accumulate */ };
+/* dither of kaldi.py:179-181 (dither = 1.0 hard-coded at model/xv_plda.py:119) */
+enum { SG_DITHER_OFF = 0, SG_DITHER_TENSOR = 1 /* caller supplies N(0,1) [B,m,400] */,
+       SG_DITHER_PHILOX = 2 /* counter-based, regenerated identically in the adjoint */ };
+enum { SG_LOSS_CE = 0, SG_LOSS_MARGIN = 1 };       /* attack/utils.py:7-29, :31-102 */
+enum { SG_TASK_CSI = 0, SG_TASK_SV = 1, SG_TASK_OSI = 2 };
+
+/* ---- lifecycle / diagnostics ---------------------------------------------------------------- */
+int sg_version(void);
+const char* sg_last_error(void);
+int sg_create(sg_handle** out, int device);
+void sg_destroy(sg_handle* h);
+int sg_set_precision(sg_handle* h, int precision);
+int sg_get_precision(const sg_handle* h);
+
+/* ---- x-vector / PLDA system: weights ---------------------------------------------------------
+ * Replaces the state built by model/xv_plda.py:17-48 (xvectorExtractor, PLDA, parse_mean_file,
+ * parse_transform_mat_file, parse_enroll_model_file).  HOST pointers, fp32, PyTorch layouts:
+ * conv weight [C_out][C_in][k] (model/_xv_plda/xvecTDNN.py:16-34), fc1 [512][3000],
+ * lda [L][513] (offset in the last column, model/iv_plda.py:423-435), plda_transform [L][L]
+ * (model/_xv_plda/plda.py:27-51), enroll [S][L].  BatchNorm running stats are folded into the
+ * next layer (eval mode, affine=False). */
+typedef struct {
+  const float* tdnn_w[5];
+  const float* tdnn_b[5];
+  const float* bn_mean[5];
+  const float* bn_var[5];
+  const float* fc1_w;
+  const float* fc1_b;
+  const float* emb_mean;
+  const float* lda;
+  const float* plda_mean;
+  const float* plda_transform;
+  const float* plda_psi;
+  const float* enroll;
+  int L;
+  int S;
+  float bn_eps;
+} sg_xv_weights;
+int sg_load_xv(sg_handle* h, const sg_xv_weights* w);
+
+/* ---- feature extraction ----------------------------------------------------------------------
+ * sg_num_frames: kaldi.py:70 (snip_edges=False).
+ * sg_mfcc_fwd: xv_plda.raw (model/xv_plda.py:107-156) = check_input_range x 2^15
+ *   (model/utils.py:7-19) + torchaudio kaldi.mfcc (kaldi.py:669-813).  x [B,N] in [-1,1];
+ *   raw [B,m,ld] (ld >= 30; columns 30..ld-1 are written as zero).
+ * sg_mfcc_bwd: its adjoint (what autograd computes in adaptive_attack/EOT.py:35);
+ *   grad [B,N] = (accumulate ? grad : 0) + scale * d(raw)/dx^T draw.
+ * sg_dither_fill: materialises the SG_DITHER_PHILOX noise as [B,m,400] (tests / oracle). */
+int sg_num_frames(int N);
+int sg_mfcc_fwd(sg_handle* h, const float* x, int B, int N, int dither_mode, const float* dither,
+                uint64_t seed, uint64_t pass, float* raw, int ld, sg_stream stream);
+int sg_mfcc_bwd(sg_handle* h, const float* x, int B, int N, int dither_mode, const float* dither,
+                uint64_t seed, uint64_t pass, const float* draw, int ld, float* grad, float scale,
+                int accumulate, sg_stream stream);
+int sg_dither_fill(sg_handle* h, int B, int N, uint64_t seed, uint64_t pass, float* out,
+                   sg_stream stream);
+/* iv_plda.cmvn (model/iv_plda.py:296-377): sliding mean-only CMVN, window 300, centred. */
+int sg_cmvn_fwd(sg_handle* h, const float* raw, int ld_in, float* out, int ld_out, int B, int T,
+                sg_stream stream);
+int sg_cmvn_bwd(sg_handle* h, const float* dout, int ld_in, float* draw, int ld_out, int B, int T,
+                sg_stream stream);
+
+/* ---- TDNN + embedding head -------------------------------------------------------------------
+ * sg_xv_embed_fwd: xv_plda.extract_emb (model/xv_plda.py:159-174) = xvecTDNN.embedding
+ *   (xvecTDNN.py:46-64) + iv_plda.process_emb (model/iv_plda.py:411-443; length-norm with the
+ *   norm detached, xvector_extract.py:33; PLDA transform plda.py:73-97).
+ *   feat [B,T,32] (CMVN features, row stride 32) -> emb [B,L].  Activations stay in `ws`.
+ * sg_xv_embed_bwd: demb [B,L] -> dfeat [B,T,32], using the activations left in `ws`. */
+size_t sg_xv_ws_bytes(const sg_handle* h, int B, int T);
+int sg_xv_embed_fwd(sg_handle* h, const float* feat, int B, int T, void* ws, float* emb,
+                    sg_stream stream);
+int sg_xv_embed_bwd(sg_handle* h, const float* demb, int B, int T, void* ws, float* dfeat,
+                    sg_stream stream);
+
+/* ---- scoring, decision, loss -----------------------------------------------------------------
+ * sg_plda_score_fwd: iv_plda.scoring_trials -> PLDA.ComputeScores (model/iv_plda.py:399-408,
+ *   plda.py:140-190) and the decision rule of model/defended_model.py:167-170.
+ *   enroll == NULL uses the handle's enrolled set.  decisions may be NULL.
+ * sg_loss_fwd_bwd: SEC4SR_CrossEntropy / SEC4SR_MarginLoss (attack/utils.py:7-102) and the
+ *   gradient of sum(loss) wrt scores (loss.backward(ones), adaptive_attack/EOT.py:35). */
+int sg_plda_score_fwd(sg_handle* h, const float* emb, int B, const float* enroll, int S,
+                      float threshold, float* scores, int64_t* decisions, sg_stream stream);
+int sg_plda_score_bwd(sg_handle* h, const float* emb, const float* dscores, int B,
+                      const float* enroll, int S, float* demb, sg_stream stream);
+typedef struct {
+  int loss;         /* SG_LOSS_* */
+  int task;         /* SG_TASK_* */
+  int targeted;
+  int clip_max;     /* SEC4SR_MarginLoss(clip_max) */
+  float confidence;
+  float threshold;  /* SV / OSI */
+} sg_loss_params;
+int sg_loss_fwd_bwd(sg_handle* h, const float* scores, const int64_t* y, int B, int S,
+                    const sg_loss_params* lp, float* loss, float* dscores, sg_stream stream);
+
+/* ---- the attack step and whole-attack loops --------------------------------------------------
+ * sg_step_linf: attack/FGSM.py:62-68 with the bounds of attack/PGD.py:48-49 recomputed from
+ *   x0: x <- min(max(x + step*sign(grad)*grad_sign, max(x0-eps,-1)), min(x0+eps,1)).
+ *   eps = +inf gives FGSM's [-1,1] box (attack/FGSM.py:74-81).
+ * sg_pgd_run: FGSM.attack_batch (attack/FGSM.py:38-70) with EOT.forward
+ *   (adaptive_attack/EOT.py:16-54) inlined: max_iter gradient passes + the final evaluation
+ *   pass, entirely on the device.  x_adv is in/out (caller initialises it with x0 or a random
+ *   start, attack/PGD.py:58-61).  dither (SG_DITHER_TENSOR) is [(passes), B, m, 400] with
+ *   passes = max_iter*eot_size + 1.  loss_hist (nullable) is [max_iter+1, B]. */
+int sg_step_linf(sg_handle* h, float* x, const float* x0, const float* grad, size_t n, float step,
+                 float grad_sign, float eps, sg_stream stream);
+typedef struct {
+  int max_iter;
+  float epsilon;      /* bounds; +inf for FGSM */
+  float step_size;
+  int eot_size;       /* >= 1 gradient samples averaged per iteration */
+  int dither_mode;
+  uint64_t seed;
+  sg_loss_params loss;
+  float decision_threshold; /* model.threshold; -inf for CSI */
+} sg_pgd_params;
+size_t sg_pgd_ws_bytes(const sg_handle* h, int B, int N);
+int sg_pgd_run(sg_handle* h, float* x_adv, const float* x0, const int64_t* y, const float* dither,
+               int B, int N, const sg_pgd_params* p, void* ws, int64_t* decisions, float* scores,
+               float* loss_hist, sg_stream stream);
+/* one forward pass wav -> scores/decisions through the same fused path (model.make_decision) */
+int sg_xv_forward(sg_handle* h, const float* x, int B, int N, int dither_mode, const float* dither,
+                  uint64_t seed, uint64_t pass, float decision_threshold, void* ws, float* scores,
+                  int64_t* decisions, float* emb, sg_stream stream);
+
+/* kernel-launch counter (bench.py's gpu_launches): kernels launched by this library since the
+ * last sg_reset_launch_count() on the calling thread's handle. */
+long long sg_launch_count(const sg_handle* h);
+void sg_reset_launch_count(sg_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGB200_H_ */

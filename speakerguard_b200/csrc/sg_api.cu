@@ -1,0 +1,539 @@
+// C-ABI of libsgb200 (include/sgb200.h): handle, weight packing, workspace layout, and the
+// orchestration of the per-pass kernel sequence and of the whole-attack loops.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <vector>
+
+#include "sg_common.cuh"
+#include "sg_head.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// error string
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void sg_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* sg_last_error(void) { return g_err; }
+extern "C" int sg_version(void) { return SGB200_VERSION; }
+
+// ---------------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------------
+static const int kTaps[5] = {5, 5, 7, 1, 1};
+static const int kDil[5] = {1, 2, 3, 1, 1};
+static const int kCin[5] = {30, 512, 512, 512, 512};
+static const int kCinP[5] = {32, 512, 512, 512, 512};
+static const int kCout[5] = {512, 512, 512, 512, 1500};
+static const int kCoutP[5] = {512, 512, 512, 512, SG_C5P};
+
+struct sg_handle {
+  int device = 0;
+  int precision = SG_PREC_FP32;
+  long long launches = 0;
+  SgFeatTables* d_tables = nullptr;
+  bool xv_loaded = false;
+  int L = 0, Lp = 0, S = 0;
+  // packed TDNN weights
+  float* Wf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // [taps*cinP, coutP]
+  float* Wb[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // [taps*coutP, cinP]
+  float* bias[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; // [coutP] (BN of the previous layer folded)
+  float* bn5_mean = nullptr; float* bn5_istd = nullptr;           // [C5P]
+  float* Wfc = nullptr; float* Wfc_b = nullptr; float* bfc = nullptr;     // fc1: [3072,512], [512,3072], [512]
+  float* Wlda = nullptr; float* Wlda_b = nullptr; float* blda = nullptr;  // LDA: [512,Lp], [Lp,512], [Lp]
+  float* plda_mean = nullptr; float* plda_T = nullptr; float* plda_Tt = nullptr;
+  float* inv_psi1 = nullptr; float* psi_ratio = nullptr; float* inv_var_given = nullptr;
+  float* enroll = nullptr;
+  SgHeadConst H;
+  std::vector<void*> allocs;
+};
+
+static int dev_upload(sg_handle* h, float** dst, const std::vector<float>& src) {
+  SG_CUDA_CHECK(cudaMalloc((void**)dst, src.size() * sizeof(float)));
+  h->allocs.push_back(*dst);
+  SG_CUDA_CHECK(cudaMemcpy(*dst, src.data(), src.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return SG_OK;
+}
+#define SG_TRY(expr) do { int _r = (expr); if (_r != SG_OK) return _r; } while (0)
+
+extern "C" int sg_create(sg_handle** out, int device) {
+  if (!out) { sg_set_error("sg_create: out is NULL"); return SG_EINVAL; }
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    sg_set_error("sg_create: no CUDA device (%s); libsgb200 has no CPU fallback", cudaGetErrorString(e));
+    return SG_ECUDA;
+  }
+  if (device < 0 || device >= n) { sg_set_error("sg_create: device %d out of range [0,%d)", device, n); return SG_EINVAL; }
+  SG_CUDA_CHECK(cudaSetDevice(device));
+  sg_handle* h = new sg_handle();
+  h->device = device;
+  SgFeatTables* host = new SgFeatTables();
+  int r = sg_feat_tables_build(host);
+  if (r != SG_OK) { delete host; delete h; sg_set_error("sg_create: feature table construction failed"); return r; }
+  cudaError_t ce = cudaMalloc((void**)&h->d_tables, sizeof(SgFeatTables));
+  if (ce == cudaSuccess) ce = cudaMemcpy(h->d_tables, host, sizeof(SgFeatTables), cudaMemcpyHostToDevice);
+  delete host;
+  if (ce != cudaSuccess) { sg_set_error("sg_create: table upload failed: %s", cudaGetErrorString(ce)); delete h; return SG_ECUDA; }
+  h->allocs.push_back(h->d_tables);
+  r = sg_feat_init();
+  if (r != SG_OK) { sg_destroy(h); return r; }
+  *out = h;
+  return SG_OK;
+}
+
+extern "C" void sg_destroy(sg_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  for (void* p : h->allocs) cudaFree(p);
+  delete h;
+}
+
+extern "C" int sg_set_precision(sg_handle* h, int precision) {
+  if (!h) { sg_set_error("null handle"); return SG_EINVAL; }
+  if (precision < SG_PREC_FP32 || precision > SG_PREC_BF16) { sg_set_error("unknown precision %d", precision); return SG_EINVAL; }
+  h->precision = precision;
+  return SG_OK;
+}
+extern "C" int sg_get_precision(const sg_handle* h) { return h ? h->precision : SG_EINVAL; }
+extern "C" long long sg_launch_count(const sg_handle* h) { return h ? h->launches : 0; }
+extern "C" void sg_reset_launch_count(sg_handle* h) { if (h) h->launches = 0; }
+
+// ---------------------------------------------------------------------------------------------
+// weights: fold eval-mode BatchNorm (affine=False) of layer l into layer l+1 (exact: valid
+// convolutions), pack [taps*cin, cout] for the forward and [taps*cout, cin] for dgrad
+// ---------------------------------------------------------------------------------------------
+extern "C" int sg_load_xv(sg_handle* h, const sg_xv_weights* w) {
+  if (!h || !w) { sg_set_error("sg_load_xv: null argument"); return SG_EINVAL; }
+  if (h->xv_loaded) { sg_set_error("sg_load_xv: weights already loaded for this handle"); return SG_ESTATE; }
+  if (w->L < 1 || w->L > 512 || w->S < 1) { sg_set_error("sg_load_xv: need 1 <= L <= 512, S >= 1 (L=%d S=%d)", w->L, w->S); return SG_EINVAL; }
+  for (int l = 0; l < 5; ++l)
+    if (!w->tdnn_w[l] || !w->tdnn_b[l] || !w->bn_mean[l] || !w->bn_var[l]) { sg_set_error("sg_load_xv: null TDNN pointer (layer %d)", l + 1); return SG_EINVAL; }
+  if (!w->fc1_w || !w->fc1_b || !w->emb_mean || !w->lda || !w->plda_mean || !w->plda_transform || !w->plda_psi || !w->enroll) {
+    sg_set_error("sg_load_xv: null head pointer"); return SG_EINVAL;
+  }
+  SG_CUDA_CHECK(cudaSetDevice(h->device));
+  const float eps = w->bn_eps > 0.f ? w->bn_eps : 1e-5f;
+  const int L = w->L, Lp = (L + 15) / 16 * 16, S = w->S;
+  h->L = L; h->Lp = Lp; h->S = S;
+  for (int l = 0; l < 5; ++l) {
+    const int K = kTaps[l], ci = kCin[l], cip = kCinP[l], co = kCout[l], cop = kCoutP[l];
+    std::vector<float> Wf((size_t)K * cip * cop, 0.f), Wb((size_t)K * cop * cip, 0.f), bias(cop, 0.f);
+    std::vector<double> istd(ci, 1.0), mu(ci, 0.0);
+    if (l > 0)
+      for (int c = 0; c < ci; ++c) {
+        istd[c] = 1.0 / sqrt((double)w->bn_var[l - 1][c] + (double)eps);
+        mu[c] = w->bn_mean[l - 1][c];
+      }
+    for (int o = 0; o < co; ++o) {
+      double bacc = w->tdnn_b[l][o];
+      for (int c = 0; c < ci; ++c)
+        for (int k = 0; k < K; ++k) {
+          const double wv = (double)w->tdnn_w[l][((size_t)o * ci + c) * K + k] * istd[c];
+          bacc -= wv * mu[c];
+          Wf[((size_t)k * cip + c) * cop + o] = (float)wv;
+          Wb[((size_t)k * cop + o) * cip + c] = (float)wv;
+        }
+      bias[o] = (float)bacc;
+    }
+    SG_TRY(dev_upload(h, &h->Wf[l], Wf));
+    SG_TRY(dev_upload(h, &h->Wb[l], Wb));
+    SG_TRY(dev_upload(h, &h->bias[l], bias));
+  }
+  {
+    std::vector<float> m5(SG_C5P, 0.f), i5(SG_C5P, 0.f);
+    for (int c = 0; c < SG_C5; ++c) { m5[c] = w->bn_mean[4][c]; i5[c] = (float)(1.0 / sqrt((double)w->bn_var[4][c] + (double)eps)); }
+    SG_TRY(dev_upload(h, &h->bn5_mean, m5));
+    SG_TRY(dev_upload(h, &h->bn5_istd, i5));
+  }
+  {  // fc1 (xvecTDNN.py:36, :63) with emb_mean folded into the bias (xvector_extract.py:41-43)
+    std::vector<float> Wfc((size_t)SG_STATS * SG_EMB, 0.f), Wfcb((size_t)SG_EMB * SG_STATS, 0.f), b(SG_EMB);
+    for (int o = 0; o < SG_EMB; ++o) {
+      for (int j = 0; j < 2 * SG_C5; ++j) {
+        const int jp = j < SG_C5 ? j : SG_C5P + (j - SG_C5);
+        const float v = w->fc1_w[(size_t)o * (2 * SG_C5) + j];
+        Wfc[(size_t)jp * SG_EMB + o] = v;
+        Wfcb[(size_t)o * SG_STATS + jp] = v;
+      }
+      b[o] = w->fc1_b[o] - w->emb_mean[o];
+    }
+    SG_TRY(dev_upload(h, &h->Wfc, Wfc));
+    SG_TRY(dev_upload(h, &h->Wfc_b, Wfcb));
+    SG_TRY(dev_upload(h, &h->bfc, b));
+  }
+  {  // LDA (model/iv_plda.py:423-435): [L, 513], offset in the last column
+    std::vector<float> Wl((size_t)SG_EMB * Lp, 0.f), Wlb((size_t)Lp * SG_EMB, 0.f), b(Lp, 0.f);
+    for (int i = 0; i < L; ++i) {
+      for (int c = 0; c < SG_EMB; ++c) {
+        const float v = w->lda[(size_t)i * (SG_EMB + 1) + c];
+        Wl[(size_t)c * Lp + i] = v;
+        Wlb[(size_t)i * SG_EMB + c] = v;
+      }
+      b[i] = w->lda[(size_t)i * (SG_EMB + 1) + SG_EMB];
+    }
+    SG_TRY(dev_upload(h, &h->Wlda, Wl));
+    SG_TRY(dev_upload(h, &h->Wlda_b, Wlb));
+    SG_TRY(dev_upload(h, &h->blda, b));
+  }
+  {  // PLDA (plda.py:27-51, :140-190)
+    std::vector<float> mean(w->plda_mean, w->plda_mean + L), T(w->plda_transform, w->plda_transform + (size_t)L * L);
+    std::vector<float> Tt((size_t)L * L), ip(L), pr(L), ivg(L);
+    for (int i = 0; i < L; ++i)
+      for (int j = 0; j < L; ++j) Tt[(size_t)j * L + i] = T[(size_t)i * L + j];
+    float ld_given = 0.f, ld_without = 0.f;
+    for (int i = 0; i < L; ++i) {
+      const float psi = w->plda_psi[i];
+      ip[i] = 1.0f / (psi + 1.0f);
+      pr[i] = psi / (psi + 1.0f);
+      const float vg = 1.0f + psi / (psi + 1.0f);
+      ivg[i] = 1.0f / vg;
+      ld_given += logf(vg);
+      ld_without += logf(psi + 1.0f);
+    }
+    SG_TRY(dev_upload(h, &h->plda_mean, mean));
+    SG_TRY(dev_upload(h, &h->plda_T, T));
+    SG_TRY(dev_upload(h, &h->plda_Tt, Tt));
+    SG_TRY(dev_upload(h, &h->inv_psi1, ip));
+    SG_TRY(dev_upload(h, &h->psi_ratio, pr));
+    SG_TRY(dev_upload(h, &h->inv_var_given, ivg));
+    std::vector<float> en(w->enroll, w->enroll + (size_t)S * L);
+    SG_TRY(dev_upload(h, &h->enroll, en));
+    h->H.L = L; h->H.Lp = Lp;
+    h->H.plda_mean = h->plda_mean; h->H.plda_T = h->plda_T; h->H.plda_Tt = h->plda_Tt;
+    h->H.inv_psi1 = h->inv_psi1; h->H.psi_ratio = h->psi_ratio; h->H.inv_var_given = h->inv_var_given;
+    h->H.logdet_given = ld_given; h->H.logdet_without = ld_without;
+    h->H.log2pi_L = logf(2.0f * 3.1415926f) * (float)L;            // plda.py:179
+  }
+  h->xv_loaded = true;
+  return SG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// workspace layout
+// ---------------------------------------------------------------------------------------------
+struct XvWs {
+  float *r[5], *G0, *G1, *G2, *stats, *dstats, *save_mean, *save_std, *e1, *de1, *e2, *de2, *tsave, *scal;
+  // attack-loop extras
+  float *raw, *draw, *feat, *dfeat, *emb, *demb, *scores, *dscores, *loss, *xbuf, *grad;
+  long long* dec;
+  size_t bytes;
+};
+
+static XvWs xv_ws_layout(void* base, int B, int T, int Lp, int L, int S, bool attack, int N) {
+  XvWs w;
+  char* p = (char*)base;
+  size_t off = 0;
+  auto take = [&](size_t nfloat) { float* q = (float*)(p + off); off += (nfloat * sizeof(float) + 255) / 256 * 256; return q; };
+  const size_t R = (size_t)B * T;
+  for (int l = 0; l < 4; ++l) w.r[l] = take(R * SG_C1);
+  w.r[4] = take(R * SG_C5P);
+  w.G0 = take(R * SG_C5P); w.G1 = take(R * SG_C1); w.G2 = take(R * SG_C1);
+  w.stats = take((size_t)B * SG_STATS); w.dstats = take((size_t)B * SG_STATS);
+  w.save_mean = take((size_t)B * SG_C5P); w.save_std = take((size_t)B * SG_C5P);
+  w.e1 = take((size_t)B * SG_EMB); w.de1 = take((size_t)B * SG_EMB);
+  w.e2 = take((size_t)B * Lp); w.de2 = take((size_t)B * Lp); w.tsave = take((size_t)B * Lp);
+  w.scal = take((size_t)B * 4);
+  w.raw = w.draw = w.feat = w.dfeat = w.emb = w.demb = w.scores = w.dscores = w.loss = w.xbuf = w.grad = nullptr;
+  w.dec = nullptr;
+  if (attack) {
+    w.raw = take(R * SG_FLD); w.draw = take(R * SG_FLD); w.feat = take(R * SG_FLD); w.dfeat = take(R * SG_FLD);
+    w.emb = take((size_t)B * L); w.demb = take((size_t)B * L);
+    w.scores = take((size_t)B * S); w.dscores = take((size_t)B * S); w.loss = take(B);
+    w.dec = (long long*)take((size_t)B * 2);
+    w.xbuf = take((size_t)B * N); w.grad = take((size_t)B * N);
+  }
+  w.bytes = off;
+  return w;
+}
+
+extern "C" size_t sg_xv_ws_bytes(const sg_handle* h, int B, int T) {
+  if (!h || !h->xv_loaded || B < 1 || T < 1) return 0;
+  return xv_ws_layout(nullptr, B, T, h->Lp, h->L, h->S, false, 0).bytes;
+}
+extern "C" size_t sg_pgd_ws_bytes(const sg_handle* h, int B, int N) {
+  if (!h || !h->xv_loaded || B < 1 || N < SG_WIN) return 0;
+  return xv_ws_layout(nullptr, B, sg_num_frames(N), h->Lp, h->L, h->S, true, N).bytes;
+}
+
+// ---------------------------------------------------------------------------------------------
+// argument checks
+// ---------------------------------------------------------------------------------------------
+static int check_handle(sg_handle* h, bool need_xv) {
+  if (!h) { sg_set_error("null handle"); return SG_EINVAL; }
+  if (need_xv && !h->xv_loaded) { sg_set_error("x-vector weights not loaded (call sg_load_xv first)"); return SG_ESTATE; }
+  return SG_OK;
+}
+static int check_wave(int B, int N) {
+  if (B < 1) { sg_set_error("batch must be >= 1 (B=%d)", B); return SG_EINVAL; }
+  if (N < SG_WIN) { sg_set_error("waveform shorter than one 25 ms window (N=%d < %d), kaldi.py:141", N, SG_WIN); return SG_EINVAL; }
+  return SG_OK;
+}
+static int check_dither(int mode, const float* dither) {
+  if (mode < SG_DITHER_OFF || mode > SG_DITHER_PHILOX) { sg_set_error("unknown dither mode %d", mode); return SG_EINVAL; }
+  if (mode == SG_DITHER_TENSOR && !dither) { sg_set_error("SG_DITHER_TENSOR needs a dither tensor"); return SG_EINVAL; }
+  return SG_OK;
+}
+
+extern "C" int sg_num_frames(int N) { return (N + SG_SHIFT / 2) / SG_SHIFT; }
+
+// ---------------------------------------------------------------------------------------------
+// stage entry points
+// ---------------------------------------------------------------------------------------------
+extern "C" int sg_mfcc_fwd(sg_handle* h, const float* x, int B, int N, int dither_mode, const float* dither,
+                           uint64_t seed, uint64_t pass, float* raw, int ld, sg_stream stream) {
+  SG_TRY(check_handle(h, false)); SG_TRY(check_wave(B, N)); SG_TRY(check_dither(dither_mode, dither));
+  if (!x || !raw || ld < SG_NCEP || ld > 32) { sg_set_error("sg_mfcc_fwd: bad pointer or ld (%d not in [30,32])", ld); return SG_EINVAL; }
+  h->launches += 1;
+  return sg_feat_fwd_launch(h->d_tables, x, B, N, sg_num_frames(N), dither_mode, dither, seed, pass, raw, ld, (cudaStream_t)stream);
+}
+
+extern "C" int sg_mfcc_bwd(sg_handle* h, const float* x, int B, int N, int dither_mode, const float* dither,
+                           uint64_t seed, uint64_t pass, const float* draw, int ld, float* grad, float scale,
+                           int accumulate, sg_stream stream) {
+  SG_TRY(check_handle(h, false)); SG_TRY(check_wave(B, N)); SG_TRY(check_dither(dither_mode, dither));
+  if (!x || !draw || !grad || ld < SG_NCEP || ld > 32) { sg_set_error("sg_mfcc_bwd: bad pointer or ld (%d)", ld); return SG_EINVAL; }
+  h->launches += 1;
+  return sg_feat_bwd_launch(h->d_tables, x, B, N, sg_num_frames(N), dither_mode, dither, seed, pass, draw, ld, grad,
+                            scale, accumulate, (cudaStream_t)stream);
+}
+
+extern "C" int sg_dither_fill(sg_handle* h, int B, int N, uint64_t seed, uint64_t pass, float* out, sg_stream stream) {
+  SG_TRY(check_handle(h, false)); SG_TRY(check_wave(B, N));
+  if (!out) { sg_set_error("sg_dither_fill: null output"); return SG_EINVAL; }
+  h->launches += 1;
+  return sg_dither_fill_launch(B, sg_num_frames(N), seed, pass, out, (cudaStream_t)stream);
+}
+
+extern "C" int sg_cmvn_fwd(sg_handle* h, const float* raw, int ld_in, float* out, int ld_out, int B, int T, sg_stream stream) {
+  SG_TRY(check_handle(h, false));
+  if (!raw || !out || B < 1 || T < 1 || ld_in < SG_NCEP || ld_out < SG_NCEP || ld_in > 32 || ld_out > 32) { sg_set_error("sg_cmvn_fwd: bad argument"); return SG_EINVAL; }
+  h->launches += 1;
+  return sg_cmvn_launch(raw, ld_in, out, ld_out, B, T, 0, (cudaStream_t)stream);
+}
+extern "C" int sg_cmvn_bwd(sg_handle* h, const float* dout, int ld_in, float* draw, int ld_out, int B, int T, sg_stream stream) {
+  SG_TRY(check_handle(h, false));
+  if (!dout || !draw || B < 1 || T < 1 || ld_in < SG_NCEP || ld_out < SG_NCEP || ld_in > 32 || ld_out > 32) { sg_set_error("sg_cmvn_bwd: bad argument"); return SG_EINVAL; }
+  h->launches += 1;
+  return sg_cmvn_launch(dout, ld_in, draw, ld_out, B, T, 1, (cudaStream_t)stream);
+}
+
+// ---- TDNN -------------------------------------------------------------------------------------
+static int run_conv(sg_handle* h, const SgConvArgs& a, bool tensor_ok, cudaStream_t st) {
+  h->launches += 1;
+  if (h->precision != SG_PREC_FP32 && tensor_ok) return sg_conv_tc(a, h->precision, st);
+  return sg_conv_simt(a, st);
+}
+
+static void tdnn_valid(int T, int tv[5]) {
+  int t = T;
+  for (int l = 0; l < 5; ++l) { t -= (kTaps[l] - 1) * kDil[l]; tv[l] = t; }
+}
+
+static int embed_fwd(sg_handle* h, const float* feat, int B, int T, const XvWs& w, float* emb, cudaStream_t st) {
+  int tv[5];
+  tdnn_valid(T, tv);
+  if (tv[4] < 2) { sg_set_error("need at least 32 frames for the TDNN + unbiased std (T=%d)", T); return SG_EINVAL; }
+  const int R = B * T;
+  const float* in = feat;
+  int lda = SG_FLD;
+  for (int l = 0; l < 5; ++l) {
+    SgConvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.A = in; a.lda = lda; a.W = h->Wf[l]; a.bias = h->bias[l]; a.out = w.r[l]; a.ldo = kCoutP[l];
+    a.rows = R; a.N = kCoutP[l]; a.cin = kCinP[l]; a.taps = kTaps[l]; a.tap_step = kDil[l];
+    a.epilogue = SG_EPI_BIAS_RELU; a.T = T; a.t_valid = tv[l];
+    SG_TRY(run_conv(h, a, true, st));
+    in = w.r[l]; lda = kCoutP[l];
+  }
+  h->launches += 1;
+  SG_TRY(sg_pool_fwd_launch(w.r[4], B, T, tv[4], h->bn5_mean, h->bn5_istd, w.stats, w.save_mean, w.save_std, st));
+  {
+    SgConvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.A = w.stats; a.lda = SG_STATS; a.W = h->Wfc; a.bias = h->bfc; a.out = w.e1; a.ldo = SG_EMB;
+    a.rows = B; a.N = SG_EMB; a.cin = SG_STATS; a.taps = 1; a.tap_step = 0; a.epilogue = SG_EPI_BIAS; a.T = 1;
+    SG_TRY(run_conv(h, a, false, st));
+    a.A = w.e1; a.lda = SG_EMB; a.W = h->Wlda; a.bias = h->blda; a.out = w.e2; a.ldo = h->Lp;
+    a.N = h->Lp; a.cin = SG_EMB;
+    SG_TRY(run_conv(h, a, false, st));
+  }
+  h->launches += 1;
+  return sg_head_fwd_launch(h->H, w.e2, B, w.tsave, w.scal, emb, st);
+}
+
+static int embed_bwd(sg_handle* h, const float* demb, int B, int T, const XvWs& w, float* dfeat, cudaStream_t st) {
+  int tv[5];
+  tdnn_valid(T, tv);
+  const int R = B * T;
+  h->launches += 1;
+  SG_TRY(sg_head_bwd_launch(h->H, demb, B, w.tsave, w.scal, w.de2, st));
+  {
+    SgConvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.A = w.de2; a.lda = h->Lp; a.W = h->Wlda_b; a.out = w.de1; a.ldo = SG_EMB;
+    a.rows = B; a.N = SG_EMB; a.cin = h->Lp; a.taps = 1; a.epilogue = SG_EPI_NONE; a.T = 1;
+    SG_TRY(run_conv(h, a, false, st));
+    a.A = w.de1; a.lda = SG_EMB; a.W = h->Wfc_b; a.out = w.dstats; a.ldo = SG_STATS; a.N = SG_STATS; a.cin = SG_EMB;
+    SG_TRY(run_conv(h, a, false, st));
+  }
+  h->launches += 1;
+  SG_TRY(sg_pool_bwd_launch(w.r[4], B, T, tv[4], h->bn5_istd, w.dstats, w.save_mean, w.save_std, w.G0, st));
+  // dgrad chain: dA_l (pre-ReLU grad of layer l) -> dA_{l-1}
+  const float* gin = w.G0;
+  float* bufs[2] = {w.G1, w.G2};
+  for (int l = 4; l >= 0; --l) {
+    SgConvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.A = gin; a.lda = kCoutP[l]; a.W = h->Wb[l]; a.rows = R; a.cin = kCoutP[l]; a.taps = kTaps[l];
+    a.tap_step = -kDil[l]; a.T = T;
+    if (l > 0) {
+      float* out = bufs[(4 - l) & 1];
+      a.out = out; a.ldo = kCinP[l]; a.N = kCinP[l];
+      a.epilogue = SG_EPI_MASK; a.mask = w.r[l - 1]; a.ldmask = kCoutP[l - 1]; a.t_valid = tv[l - 1];
+      SG_TRY(run_conv(h, a, true, st));
+      gin = out;
+    } else {
+      a.out = dfeat; a.ldo = SG_FLD; a.N = SG_FLD; a.epilogue = SG_EPI_NONE;
+      SG_TRY(run_conv(h, a, true, st));
+    }
+  }
+  return SG_OK;
+}
+
+extern "C" int sg_xv_embed_fwd(sg_handle* h, const float* feat, int B, int T, void* ws, float* emb, sg_stream stream) {
+  SG_TRY(check_handle(h, true));
+  if (!feat || !ws || !emb || B < 1) { sg_set_error("sg_xv_embed_fwd: bad argument"); return SG_EINVAL; }
+  XvWs w = xv_ws_layout(ws, B, T, h->Lp, h->L, h->S, false, 0);
+  return embed_fwd(h, feat, B, T, w, emb, (cudaStream_t)stream);
+}
+extern "C" int sg_xv_embed_bwd(sg_handle* h, const float* demb, int B, int T, void* ws, float* dfeat, sg_stream stream) {
+  SG_TRY(check_handle(h, true));
+  if (!demb || !ws || !dfeat || B < 1) { sg_set_error("sg_xv_embed_bwd: bad argument"); return SG_EINVAL; }
+  XvWs w = xv_ws_layout(ws, B, T, h->Lp, h->L, h->S, false, 0);
+  return embed_bwd(h, demb, B, T, w, dfeat, (cudaStream_t)stream);
+}
+
+// ---- scoring / loss ----------------------------------------------------------------------------
+extern "C" int sg_plda_score_fwd(sg_handle* h, const float* emb, int B, const float* enroll, int S, float threshold,
+                                 float* scores, int64_t* decisions, sg_stream stream) {
+  SG_TRY(check_handle(h, true));
+  if (!emb || !scores || B < 1) { sg_set_error("sg_plda_score_fwd: bad argument"); return SG_EINVAL; }
+  if (!enroll) { enroll = h->enroll; S = h->S; }
+  if (S < 1) { sg_set_error("sg_plda_score_fwd: S must be >= 1"); return SG_EINVAL; }
+  h->launches += 1;
+  return sg_score_fwd_launch(h->H, emb, B, enroll, S, threshold, scores, (long long*)decisions, (cudaStream_t)stream);
+}
+extern "C" int sg_plda_score_bwd(sg_handle* h, const float* emb, const float* dscores, int B, const float* enroll, int S,
+                                 float* demb, sg_stream stream) {
+  SG_TRY(check_handle(h, true));
+  if (!emb || !dscores || !demb || B < 1) { sg_set_error("sg_plda_score_bwd: bad argument"); return SG_EINVAL; }
+  if (!enroll) { enroll = h->enroll; S = h->S; }
+  h->launches += 1;
+  return sg_score_bwd_launch(h->H, emb, dscores, B, enroll, S, demb, (cudaStream_t)stream);
+}
+static int check_loss(const sg_loss_params* lp, int S) {
+  if (!lp) { sg_set_error("null loss params"); return SG_EINVAL; }
+  if (lp->loss == SG_LOSS_CE && lp->task != SG_TASK_CSI) { sg_set_error("CrossEntropy only supports the CSI task (attack/utils.py:12)"); return SG_EINVAL; }
+  if (lp->task == SG_TASK_SV && S != 1) { sg_set_error("SV task needs exactly one enrolled speaker (S=%d)", S); return SG_EINVAL; }
+  return SG_OK;
+}
+extern "C" int sg_loss_fwd_bwd(sg_handle* h, const float* scores, const int64_t* y, int B, int S, const sg_loss_params* lp,
+                               float* loss, float* dscores, sg_stream stream) {
+  SG_TRY(check_handle(h, false)); SG_TRY(check_loss(lp, S));
+  if (!scores || !y || !loss || B < 1 || S < 1) { sg_set_error("sg_loss_fwd_bwd: bad argument"); return SG_EINVAL; }
+  h->launches += 1;
+  return sg_loss_launch(scores, (const long long*)y, B, S, *lp, loss, dscores, (cudaStream_t)stream);
+}
+
+extern "C" int sg_step_linf(sg_handle* h, float* x, const float* x0, const float* grad, size_t n, float step,
+                            float grad_sign, float eps, sg_stream stream) {
+  SG_TRY(check_handle(h, false));
+  if (!x || !x0 || !grad) { sg_set_error("sg_step_linf: null pointer"); return SG_EINVAL; }
+  h->launches += 1;
+  return sg_step_linf_launch(x, x0, grad, n, step * grad_sign, eps, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused passes
+// ---------------------------------------------------------------------------------------------
+static int forward_pass(sg_handle* h, const float* x, int B, int N, int m, int mode, const float* dither, uint64_t seed,
+                        uint64_t pass, float thr, const XvWs& w, float* emb, float* scores, long long* dec, cudaStream_t st) {
+  h->launches += 3;
+  SG_TRY(sg_feat_fwd_launch(h->d_tables, x, B, N, m, mode, dither, seed, pass, w.raw, SG_FLD, st));
+  SG_TRY(sg_cmvn_launch(w.raw, SG_FLD, w.feat, SG_FLD, B, m, 0, st));
+  SG_TRY(embed_fwd(h, w.feat, B, m, w, emb, st));
+  return sg_score_fwd_launch(h->H, emb, B, h->enroll, h->S, thr, scores, dec, st);
+}
+
+extern "C" int sg_xv_forward(sg_handle* h, const float* x, int B, int N, int dither_mode, const float* dither,
+                             uint64_t seed, uint64_t pass, float decision_threshold, void* ws, float* scores,
+                             int64_t* decisions, float* emb, sg_stream stream) {
+  SG_TRY(check_handle(h, true)); SG_TRY(check_wave(B, N)); SG_TRY(check_dither(dither_mode, dither));
+  if (!x || !ws || !scores) { sg_set_error("sg_xv_forward: bad argument"); return SG_EINVAL; }
+  const int m = sg_num_frames(N);
+  XvWs w = xv_ws_layout(ws, B, m, h->Lp, h->L, h->S, true, N);
+  return forward_pass(h, x, B, N, m, dither_mode, dither, seed, pass, decision_threshold, w, emb ? emb : w.emb, scores,
+                      (long long*)decisions, (cudaStream_t)stream);
+}
+
+extern "C" int sg_pgd_run(sg_handle* h, float* x_adv, const float* x0, const int64_t* y, const float* dither, int B, int N,
+                          const sg_pgd_params* p, void* ws, int64_t* decisions, float* scores, float* loss_hist,
+                          sg_stream stream) {
+  SG_TRY(check_handle(h, true)); SG_TRY(check_wave(B, N));
+  if (!x_adv || !x0 || !y || !p || !ws) { sg_set_error("sg_pgd_run: null argument"); return SG_EINVAL; }
+  SG_TRY(check_dither(p->dither_mode, dither)); SG_TRY(check_loss(&p->loss, h->S));
+  if (p->max_iter < 0 || p->eot_size < 1) { sg_set_error("sg_pgd_run: max_iter >= 0 and eot_size >= 1 required"); return SG_EINVAL; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int m = sg_num_frames(N), E = p->eot_size;
+  XvWs w = xv_ws_layout(ws, B, m, h->Lp, h->L, h->S, true, N);
+  const size_t dstride = (size_t)B * m * SG_WIN;
+  // grad_sign of attack/utils.py:114
+  const float grad_sign = (p->loss.loss == SG_LOSS_CE) ? (p->loss.targeted ? -1.f : 1.f) : -1.f;
+  float* cur = x_adv;
+  float* other = w.xbuf;
+  float* sc = scores ? scores : w.scores;
+  long long* dec = decisions ? (long long*)decisions : w.dec;
+  for (int it = 0; it < p->max_iter; ++it) {
+    for (int e = 0; e < E; ++e) {
+      const uint64_t pass = (uint64_t)it * E + e;
+      const float* dth = dither ? dither + pass * dstride : nullptr;
+      SG_TRY(forward_pass(h, cur, B, N, m, p->dither_mode, dth, p->seed, pass, p->decision_threshold, w, w.emb, sc, dec, st));
+      float* lossp = (loss_hist && e == 0) ? loss_hist + (size_t)it * B : w.loss;
+      h->launches += 3;
+      SG_TRY(sg_loss_launch(sc, (const long long*)y, B, h->S, p->loss, lossp, w.dscores, st));
+      SG_TRY(sg_score_bwd_launch(h->H, w.emb, w.dscores, B, h->enroll, h->S, w.demb, st));
+      SG_TRY(embed_bwd(h, w.demb, B, m, w, w.dfeat, st));
+      SG_TRY(sg_cmvn_launch(w.dfeat, SG_FLD, w.draw, SG_FLD, B, m, 1, st));
+      h->launches += 1;
+      if (E == 1) {
+        SG_TRY(sg_feat_bwd_step_launch(h->d_tables, cur, B, N, m, p->dither_mode, dth, p->seed, pass, w.draw, SG_FLD, x0,
+                                       other, p->step_size * grad_sign, p->epsilon, st));
+        float* t = cur; cur = other; other = t;
+      } else {
+        SG_TRY(sg_feat_bwd_launch(h->d_tables, cur, B, N, m, p->dither_mode, dth, p->seed, pass, w.draw, SG_FLD, w.grad,
+                                  1.0f / (float)E, e > 0, st));
+      }
+    }
+    if (E > 1) {
+      h->launches += 1;
+      SG_TRY(sg_step_linf_launch(cur, x0, w.grad, (size_t)B * N, p->step_size * grad_sign, p->epsilon, st));
+    }
+  }
+  // final evaluation pass (attack/FGSM.py:44-57 with iter == max_iter)
+  {
+    const uint64_t pass = (uint64_t)p->max_iter * E;
+    const float* dth = dither ? dither + pass * dstride : nullptr;
+    SG_TRY(forward_pass(h, cur, B, N, m, p->dither_mode, dth, p->seed, pass, p->decision_threshold, w, w.emb, sc, dec, st));
+    float* lossp = loss_hist ? loss_hist + (size_t)p->max_iter * B : w.loss;
+    h->launches += 1;
+    SG_TRY(sg_loss_launch(sc, (const long long*)y, B, h->S, p->loss, lossp, nullptr, st));
+  }
+  if (cur != x_adv) SG_CUDA_CHECK(cudaMemcpyAsync(x_adv, cur, (size_t)B * N * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return SG_OK;
+}

@@ -1,0 +1,98 @@
+// Shared declarations for libsgb200 (internal; the public C-ABI is include/sgb200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/sgb200.h"
+
+#define SG_WIN 400      // 25 ms @ 16 kHz          (kaldi.py:125-151)
+#define SG_SHIFT 160    // 10 ms
+#define SG_NFFT 512     // round_to_power_of_two
+#define SG_HALO 120     // WIN/2 - SHIFT/2: left reflect pad (kaldi.py:71)
+#define SG_NMEL 30
+#define SG_NCEP 30
+#define SG_FLD 32       // internal feature row stride (30 cepstra + 2 zero pads)
+#define SG_EPS 1.1920928955078125e-07f
+
+#define SG_C1 512
+#define SG_C5 1500
+#define SG_C5P 1536     // layer-5 channels padded to a multiple of 128
+#define SG_STATS (2 * SG_C5P)
+#define SG_EMB 512
+
+void sg_set_error(const char* fmt, ...);
+
+#define SG_CUDA_CHECK(expr)                                                          \
+  do {                                                                               \
+    cudaError_t _e = (expr);                                                         \
+    if (_e != cudaSuccess) {                                                         \
+      sg_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                   __LINE__);                                                        \
+      return SG_ECUDA;                                                               \
+    }                                                                                \
+  } while (0)
+
+#define SG_LAUNCH_CHECK()                                                            \
+  do {                                                                               \
+    cudaError_t _e = cudaGetLastError();                                             \
+    if (_e != cudaSuccess) {                                                         \
+      sg_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),       \
+                   __FILE__, __LINE__);                                              \
+      return SG_ECUDA;                                                               \
+    }                                                                                \
+  } while (0)
+
+// ---- feature tables (device resident, built once per handle by sg_feat_tables_build) --------
+struct alignas(16) SgFeatTables {
+  float window[SG_WIN];          // Povey window
+  float2 tw[24][32];             // per-lane FFT twiddles: [0..7] pass A, [8..15] pass B, [16..23] untangle
+  int mel_lo[32];                // first FFT bin of filter c
+  int mel_len[32];               // number of bins
+  int mel_off[32];               // offset into mel_w
+  float mel_w[512];              // packed non-zero weights
+  int bin_c0[256], bin_c1[256];  // per FFT bin: the (<=2) filters it feeds (31 = none)
+  float bin_w0[256], bin_w1[256];
+  float dct[SG_NMEL][32];        // dct[n][k] * lifter[k]   (forward: lane k, loop n)
+  float dct_t[32][32];           // dct_t[k][n] = dct[n][k] (backward: lane n, loop k)
+  int mel_maxlen;
+};
+
+int sg_feat_tables_build(SgFeatTables* host_out);
+
+// ---- GEMM-as-convolution (SIMT fp32 path) ----------------------------------------------------
+enum SgEpilogue {
+  SG_EPI_BIAS = 0,        // out = acc + bias
+  SG_EPI_BIAS_RELU = 1,   // out = relu(acc + bias)
+  SG_EPI_MASK = 2,        // out = acc * (mask > 0) * (t < t_valid)      (dgrad through ReLU)
+  SG_EPI_NONE = 3         // out = acc
+};
+
+struct SgConvArgs {
+  const float* A; int lda;          // activations [rows, lda], K (channels) contiguous
+  const float* W;                   // packed weights [taps*cin, N] row-major
+  const float* bias;                // [N] or null
+  float* out; int ldo;              // [rows, ldo]
+  int rows;                         // M
+  int N;                            // output columns (<= ldo)
+  int cin;                          // K per tap (multiple of 16)
+  int taps; int tap_step;           // source row of tap k = p + k*tap_step (may be negative)
+  int epilogue;
+  const float* mask; int ldmask;    // SG_EPI_MASK: post-ReLU activation of the producing layer
+  int T; int t_valid;               // rows per utterance / valid rows (SG_EPI_MASK)
+};
+
+int sg_conv_simt(const SgConvArgs& a, cudaStream_t st);
+int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st);   // tcgen05 path (sg_tdnn_tc.cu)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}

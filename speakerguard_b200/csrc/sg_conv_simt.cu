@@ -1,0 +1,134 @@
+// fp32 (FFMA) GEMM-as-dilated-convolution: the parity-mode path for the TDNN layers
+// (reference model/_xv_plda/xvecTDNN.py:16-53, forward; autograd dgrad in the backward) and for
+// the dense projections of the head (fc1 :63, LDA model/iv_plda.py:423-435).
+//
+//   out[p, n] = epi( sum_{tap, c} A[p + tap*tap_step, c] * W[tap*cin + c, n] )
+//
+// Activations are channels-last [rows, lda] with every utterance occupying T consecutive rows,
+// so a dilated tap is just a row offset (no im2col); rows outside [0, rows) read as zero.
+// 128 x 128 x 16 tiles, 256 threads, 8 x 8 register micro-tiles, register-staged double buffering.
+#include "sg_common.cuh"
+
+#define BM 128
+#define BN 128
+#define BK 16
+
+__global__ void __launch_bounds__(256, 2)
+conv_simt_kernel(SgConvArgs a) {
+  __shared__ __align__(16) float As[2][BK][BM];
+  __shared__ __align__(16) float Bs[2][BK][BN];
+  const int tid = threadIdx.x;
+  const int n0 = blockIdx.x * BN;
+  const int p0 = blockIdx.y * BM;
+  const int ty = tid >> 4, tx = tid & 15;
+  // loaders
+  const int a_row = tid & 127, a_k = (tid >> 7) * 8;
+  const int b_k = tid >> 4, b_col = (tid & 15) * 8;
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  const int kchunks = a.cin / BK;
+  const int nk = a.taps * kchunks;
+
+  float4 ra[2], rb[2];
+  auto gload = [&](int kt) {
+    const int tap = kt / kchunks, c0 = (kt - tap * kchunks) * BK;
+    const long long sr = (long long)p0 + a_row + (long long)tap * a.tap_step;
+    if (sr >= 0 && sr < a.rows) {
+      const float4* src = reinterpret_cast<const float4*>(a.A + sr * a.lda + c0 + a_k);
+      ra[0] = __ldg(src); ra[1] = __ldg(src + 1);
+    } else {
+      ra[0] = ra[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float* wrow = a.W + (size_t)(tap * a.cin + c0 + b_k) * a.N + n0 + b_col;
+    rb[0] = (n0 + b_col + 3 < a.N) ? __ldg(reinterpret_cast<const float4*>(wrow)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    rb[1] = (n0 + b_col + 7 < a.N) ? __ldg(reinterpret_cast<const float4*>(wrow + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  auto sstore = [&](int buf) {
+    As[buf][a_k + 0][a_row] = ra[0].x; As[buf][a_k + 1][a_row] = ra[0].y;
+    As[buf][a_k + 2][a_row] = ra[0].z; As[buf][a_k + 3][a_row] = ra[0].w;
+    As[buf][a_k + 4][a_row] = ra[1].x; As[buf][a_k + 5][a_row] = ra[1].y;
+    As[buf][a_k + 6][a_row] = ra[1].z; As[buf][a_k + 7][a_row] = ra[1].w;
+    *reinterpret_cast<float4*>(&Bs[buf][b_k][b_col]) = rb[0];
+    *reinterpret_cast<float4*>(&Bs[buf][b_k][b_col + 4]) = rb[1];
+  };
+
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) gload(kt + 1);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+      float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) {
+      sstore(buf ^ 1);
+      __syncthreads();
+    }
+  }
+
+  // epilogue
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = p0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (row >= a.rows) continue;
+    bool row_ok = true;
+    if (a.epilogue == SG_EPI_MASK) row_ok = (row % a.T) < a.t_valid;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int col = n0 + (h == 0 ? tx * 4 : 64 + tx * 4);
+      if (col >= a.N) continue;
+      float v[4] = {acc[i][h * 4 + 0], acc[i][h * 4 + 1], acc[i][h * 4 + 2], acc[i][h * 4 + 3]};
+      if (a.epilogue == SG_EPI_BIAS || a.epilogue == SG_EPI_BIAS_RELU) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (col + j < a.N) v[j] += a.bias ? __ldg(a.bias + col + j) : 0.f;
+      }
+      if (a.epilogue == SG_EPI_BIAS_RELU) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
+      } else if (a.epilogue == SG_EPI_MASK) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool on = row_ok && (col + j < a.N) && (__ldg(a.mask + (size_t)row * a.ldmask + col + j) > 0.f);
+          v[j] = on ? v[j] : 0.f;
+        }
+      }
+      float* o = a.out + (size_t)row * a.ldo + col;
+      if (col + 3 < a.N) {
+        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (col + j < a.N) o[j] = v[j];
+      }
+    }
+  }
+}
+
+int sg_conv_simt(const SgConvArgs& a, cudaStream_t st) {
+  if (a.cin % BK != 0 || a.N % 4 != 0 || a.lda % 4 != 0 || a.ldo % 4 != 0) {
+    sg_set_error("sg_conv_simt: cin %% 16, N %% 4, lda %% 4, ldo %% 4 required (cin=%d N=%d lda=%d ldo=%d)",
+                 a.cin, a.N, a.lda, a.ldo);
+    return SG_EINVAL;
+  }
+  dim3 grid((a.N + BN - 1) / BN, (a.rows + BM - 1) / BM);
+  conv_simt_kernel<<<grid, 256, 0, st>>>(a);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}

@@ -1,0 +1,721 @@
+// F1 / F2: Kaldi-compatible MFCC forward and its adjoint (+ fused L-inf sign step), sliding CMVN.
+//
+// Restates xv_plda.raw (reference model/xv_plda.py:107-156) = torchaudio kaldi.mfcc
+// (kaldi.py:669-813 -> fbank :514-645 -> _get_window :154-217 -> _get_strided :44-83) and
+// iv_plda.cmvn (model/iv_plda.py:296-377) as hand-written sm_100a kernels.  One warp owns one
+// 25 ms frame: reflect-padded gather, dither, DC removal, raw log-energy, pre-emphasis, Povey
+// window, a 512-point real FFT done as a 256-point complex FFT in registers + shared memory
+// (8 x 8 x 4 radix passes), sparse triangular mel filterbank, log, DCT + lifter.
+// The adjoint recomputes the forward per frame (bytes are scarce, flops are free), walks the
+// chain backwards, and overlap-adds the frame gradients in shared memory in a fixed order
+// (deterministic), so the waveform gradient / the updated iterate is written exactly once.
+#include <math.h>
+#include <string.h>
+
+#include "sg_common.cuh"
+
+// =============================================================================================
+// host: constant tables
+// =============================================================================================
+int sg_feat_tables_build(SgFeatTables* t) {
+  memset(t, 0, sizeof(*t));
+  const double PI = 3.14159265358979323846;
+  for (int j = 0; j < SG_WIN; ++j) {
+    double h = 0.5 - 0.5 * cos(2.0 * PI * j / (SG_WIN - 1));     // kaldi.py:98-100 (povey)
+    t->window[j] = (float)pow(h, 0.85);
+  }
+  for (int lane = 0; lane < 32; ++lane) {
+    for (int k0 = 0; k0 < 8; ++k0) {                              // pass A: W_64^(n1*k0)
+      int n1 = lane >> 2;
+      double a = -2.0 * PI * (n1 * k0) / 64.0;
+      t->tw[k0][lane] = make_float2((float)cos(a), (float)sin(a));
+    }
+    for (int k1 = 0; k1 < 8; ++k1) {                              // pass B: W_256^(n2*(k0+8*k1))
+      int k0 = lane >> 2, n2 = lane & 3;
+      double a = -2.0 * PI * (n2 * (k0 + 8 * k1)) / 256.0;
+      t->tw[8 + k1][lane] = make_float2((float)cos(a), (float)sin(a));
+    }
+    for (int i = 0; i < 8; ++i) {                                 // untangle: (cos, sin)(2 pi k / 512)
+      int k = lane + 32 * i;
+      double a = 2.0 * PI * k / 512.0;
+      t->tw[16 + i][lane] = make_float2((float)cos(a), (float)sin(a));
+    }
+  }
+  // mel filterbank, kaldi.py:436-511 with low 20 Hz, high 7600 Hz, 30 bins, vtln_warp 1
+  auto mel = [](double f) { return 1127.0 * log(1.0 + f / 700.0); };
+  const double ml = mel(20.0), mh = mel(7600.0);
+  const double delta = (mh - ml) / (SG_NMEL + 1);
+  static double w[SG_NMEL][256];
+  for (int c = 0; c < SG_NMEL; ++c) {
+    double left = ml + c * delta, center = ml + (c + 1.0) * delta, right = ml + (c + 2.0) * delta;
+    for (int b = 0; b < 256; ++b) {
+      double mf = mel((16000.0 / SG_NFFT) * b);
+      double up = (mf - left) / (center - left), down = (right - mf) / (right - center);
+      double v = up < down ? up : down;
+      w[c][b] = v > 0.0 ? v : 0.0;
+    }
+  }
+  int off = 0, maxlen = 0;
+  for (int b = 0; b < 256; ++b) { t->bin_c0[b] = t->bin_c1[b] = 31; }
+  for (int c = 0; c < 32; ++c) {
+    int lo = 0, hi = -1;
+    if (c < SG_NMEL) {
+      lo = 256;
+      for (int b = 0; b < 256; ++b)
+        if (w[c][b] > 0.0) { if (b < lo) lo = b; hi = b; }
+      if (hi < 0) lo = 0;
+    }
+    int len = hi - lo + 1;
+    if (len < 0) len = 0;
+    t->mel_lo[c] = lo; t->mel_len[c] = len; t->mel_off[c] = off;
+    if (off + len > 512) return SG_EINVAL;
+    for (int i = 0; i < len; ++i) {
+      int b = lo + i;
+      t->mel_w[off + i] = (float)w[c][b];
+      if (w[c][b] > 0.0) {
+        if (t->bin_c0[b] == 31) { t->bin_c0[b] = c; t->bin_w0[b] = (float)w[c][b]; }
+        else if (t->bin_c1[b] == 31) { t->bin_c1[b] = c; t->bin_w1[b] = (float)w[c][b]; }
+        else return SG_EINVAL;   // triangles overlap at most pairwise
+      }
+    }
+    off += len;
+    if (len > maxlen) maxlen = len;
+  }
+  t->mel_maxlen = maxlen;
+  // DCT-II (ortho) with kaldi's first column and the lifter folded in: kaldi.py:648-666, :788-796
+  for (int n = 0; n < SG_NMEL; ++n)
+    for (int k = 0; k < SG_NCEP; ++k) {
+      double d = (k == 0) ? sqrt(1.0 / SG_NMEL) : sqrt(2.0 / SG_NMEL) * cos(PI / SG_NMEL * (n + 0.5) * k);
+      double lift = 1.0 + 0.5 * 22.0 * sin(PI * k / 22.0);
+      t->dct[n][k] = (float)(d * lift);
+      t->dct_t[k][n] = (float)(d * lift);
+    }
+  return SG_OK;
+}
+
+// =============================================================================================
+// device helpers
+// =============================================================================================
+#define FEAT_THREADS 256
+#define FEAT_WARPS 8
+#define WARP_SCRATCH 832                  // floats per warp: re[288] + im[288] + P[256]
+#define ACC_LEN 1520                      // 7*160 + 400: padded span of 8 consecutive frames
+#define ACC_FIN 1280                      // 8*160: positions no later group touches
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+__device__ __forceinline__ void fft4(float2& a0, float2& a1, float2& a2, float2& a3) {
+  float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = csub(a1, a3);
+  a0 = cadd(t0, t2);
+  a2 = csub(t0, t2);
+  a1 = make_float2(t1.x + t3.y, t1.y - t3.x);   // t1 - i*t3
+  a3 = make_float2(t1.x - t3.y, t1.y + t3.x);   // t1 + i*t3
+}
+
+// natural-order in, natural-order out: v[k] = sum_n v[n] W_8^(nk)
+__device__ __forceinline__ void fft8(float2 (&v)[8]) {
+  fft4(v[0], v[2], v[4], v[6]);
+  fft4(v[1], v[3], v[5], v[7]);
+  const float h = 0.70710678118654752440f;
+  float2 o1 = make_float2(h * (v[3].x + v[3].y), h * (v[3].y - v[3].x));     // * W_8^1
+  float2 o2 = make_float2(v[5].y, -v[5].x);                                   // * W_8^2 = -i
+  float2 o3 = make_float2(h * (v[7].y - v[7].x), -h * (v[7].x + v[7].y));    // * W_8^3
+  float2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6], o0 = v[1];
+  v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
+  v[1] = cadd(e1, o1); v[5] = csub(e1, o1);
+  v[2] = cadd(e2, o2); v[6] = csub(e2, o2);
+  v[3] = cadd(e3, o3); v[7] = csub(e3, o3);
+}
+
+// 256-point complex FFT across one warp.  In: z[r] = element 32*r + lane.  Out: z[4*j + k2] =
+// Z[k0 + 8*(c + 4*j) + 64*k2] with lane = k0 + 8*c.  sre/sim: >= 288 floats each, warp private.
+// (index maps prototyped and checked in tools/fft_proto.py)
+__device__ __forceinline__ void warp_fft256(float2 (&z)[8], const float2 (*tw)[32], float* sre,
+                                            float* sim, int lane) {
+  fft8(z);
+#pragma unroll
+  for (int k0 = 1; k0 < 8; ++k0) z[k0] = cmul(z[k0], tw[k0][lane]);
+#pragma unroll
+  for (int k0 = 0; k0 < 8; ++k0) { sre[k0 * 36 + lane] = z[k0].x; sim[k0 * 36 + lane] = z[k0].y; }
+  __syncwarp();
+  {
+    const int base = (lane >> 2) * 36 + (lane & 3);
+#pragma unroll
+    for (int n1 = 0; n1 < 8; ++n1) z[n1] = make_float2(sre[base + n1 * 4], sim[base + n1 * 4]);
+  }
+  __syncwarp();
+  fft8(z);
+#pragma unroll
+  for (int k1 = 0; k1 < 8; ++k1) z[k1] = cmul(z[k1], tw[8 + k1][lane]);
+#pragma unroll
+  for (int k1 = 0; k1 < 8; ++k1) { sre[k1 * 33 + lane] = z[k1].x; sim[k1 * 33 + lane] = z[k1].y; }
+  __syncwarp();
+  {
+    const int k0 = lane & 7, c = lane >> 3;
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int n2 = 0; n2 < 4; ++n2) {
+        int a = (c + 4 * j) * 33 + k0 * 4 + n2;
+        z[4 * j + n2] = make_float2(sre[a], sim[a]);
+      }
+  }
+  __syncwarp();
+  fft4(z[0], z[1], z[2], z[3]);
+  fft4(z[4], z[5], z[6], z[7]);
+}
+
+// scatter the FFT output to natural order in shared memory: s[k] for k in [0,256)
+__device__ __forceinline__ void fft_out_to_smem(const float2 (&z)[8], float* sre, float* sim, int lane) {
+  const int k0 = lane & 7, c = lane >> 3;
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int k2 = 0; k2 < 4; ++k2) {
+      int k = k0 + 8 * (c + 4 * j) + 64 * k2;
+      sre[k] = z[4 * j + k2].x;
+      sim[k] = z[4 * j + k2].y;
+    }
+}
+
+// ---- Philox4x32-10 (counter-based dither) -----------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
+  float u1 = __uint2float_rn(a) * 2.3283064365386963e-10f + 1.1641532182693481e-10f;
+  float u2 = __uint2float_rn(b) * 2.3283064365386963e-10f + 1.1641532182693481e-10f;
+  float r = sqrtf(-2.0f * logf(u1));
+  float s, c;
+  sincospif(2.0f * u2, &s, &c);
+  return make_float2(r * c, r * s);
+}
+
+struct DitherSpec {
+  int mode;              // SG_DITHER_*
+  const float* tensor;   // [B, m, 400] for this pass
+  uint32_t seed_lo, seed_hi;
+  uint32_t pass;
+};
+
+// Per-lane ownership of a frame: sample j = 64*n0 + 2*lane + e, n0 in [0,7), e in {0,1};
+// valid iff j < 400 (n0 == 6 only for lane < 8).  The FFT packs z[n] = g[2n] + i g[2n+1], so
+// the lane's pair (n0) is exactly FFT input element n = 32*n0 + lane.
+struct Frame {
+  float fe[7], fo[7];    // DC-removed samples (even / odd of each pair)
+  float sumsq;           // raw energy sum (kaldi.py:116-122)
+  float2 X[8];           // spectrum bins k = lane + 32*i
+};
+
+__device__ __forceinline__ void load_frame(Frame& F, const float* __restrict__ xb, int N, int b, int m,
+                                           int fr, const DitherSpec& D, int lane) {
+  const int p0 = fr * SG_SHIFT - SG_HALO + 2 * lane;
+  float nz[14];
+#pragma unroll
+  for (int i = 0; i < 14; ++i) nz[i] = 0.f;
+  if (D.mode == SG_DITHER_TENSOR) {
+    const float* dp = D.tensor + ((size_t)b * m + fr) * SG_WIN + 2 * lane;
+#pragma unroll
+    for (int n0 = 0; n0 < 7; ++n0)
+      if (n0 < 6 || lane < 8) {
+        float2 d = *reinterpret_cast<const float2*>(dp + 64 * n0);
+        nz[2 * n0] = d.x; nz[2 * n0 + 1] = d.y;
+      }
+  } else if (D.mode == SG_DITHER_PHILOX) {
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      uint4 r = philox4x32_10(make_uint4(h * 32 + lane, (uint32_t)fr, (uint32_t)b, D.pass),
+                              make_uint2(D.seed_lo, D.seed_hi));
+      float2 a = box_muller(r.x, r.y), c = box_muller(r.z, r.w);
+      nz[4 * h] = a.x; nz[4 * h + 1] = a.y;
+      if (h < 3) { nz[4 * h + 2] = c.x; nz[4 * h + 3] = c.y; }
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int n0 = 0; n0 < 7; ++n0) {
+    const bool valid = (n0 < 6) || (lane < 8);
+    float ve = 0.f, vo = 0.f;
+    if (valid) {
+      int pe = p0 + 64 * n0, po = pe + 1;
+      pe = pe < 0 ? -pe - 1 : (pe >= N ? 2 * N - 1 - pe : pe);     // kaldi.py:69-77 reflect pad
+      po = po < 0 ? -po - 1 : (po >= N ? 2 * N - 1 - po : po);
+      ve = __ldg(xb + pe) * 32768.0f + nz[2 * n0];                 // model/utils.py:14, kaldi.py:181
+      vo = __ldg(xb + po) * 32768.0f + nz[2 * n0 + 1];
+    }
+    F.fe[n0] = ve; F.fo[n0] = vo;
+    s += ve + vo;
+  }
+  const float mean = warp_sum(s) * (1.0f / SG_WIN);                // kaldi.py:183-186
+  float q = 0.f;
+#pragma unroll
+  for (int n0 = 0; n0 < 7; ++n0) {
+    const bool valid = (n0 < 6) || (lane < 8);
+    F.fe[n0] = valid ? F.fe[n0] - mean : 0.f;
+    F.fo[n0] = valid ? F.fo[n0] - mean : 0.f;
+    q += F.fe[n0] * F.fe[n0] + F.fo[n0] * F.fo[n0];
+  }
+  F.sumsq = warp_sum(q);
+}
+
+// pre-emphasis + window + real FFT; leaves the spectrum in F.X and |X|^2 in P[0..255] (smem)
+__device__ __forceinline__ void frame_spectrum(Frame& F, const SgFeatTables* T, float* sre, float* sim,
+                                               float* P, int lane) {
+  float2 z[8];
+#pragma unroll
+  for (int n0 = 0; n0 < 7; ++n0) {
+    // previous sample of the even element: odd element of lane-1 (same pair row), or of lane 31
+    // in the previous row; j == 0 replicates itself (kaldi.py:193-198)
+    float up = __shfl_up_sync(0xffffffffu, F.fo[n0], 1);
+    float wrap = __shfl_sync(0xffffffffu, n0 > 0 ? F.fo[n0 > 0 ? n0 - 1 : 0] : F.fe[0], 31);
+    float prev = lane > 0 ? up : (n0 > 0 ? wrap : F.fe[0]);
+    const bool valid = (n0 < 6) || (lane < 8);
+    float2 w2 = valid ? *reinterpret_cast<const float2*>(&T->window[64 * n0 + 2 * lane]) : make_float2(0.f, 0.f);
+    z[n0] = make_float2((F.fe[n0] - 0.97f * prev) * w2.x, (F.fo[n0] - 0.97f * F.fe[n0]) * w2.y);
+  }
+  z[7] = make_float2(0.f, 0.f);
+  warp_fft256(z, T->tw, sre, sim, lane);
+  fft_out_to_smem(z, sre, sim, lane);
+  __syncwarp();
+  // untangle: X[k] = a_k Z[k] + b_k conj(Z[256-k]),  a_k = ((1-s) - i c)/2, b_k = ((1+s) + i c)/2
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int k = lane + 32 * i;
+    const int km = (256 - k) & 255;
+    float2 zk = make_float2(sre[k], sim[k]);
+    float2 zm = make_float2(sre[km], -sim[km]);
+    float2 cs = T->tw[16 + i][lane];
+    float2 a = make_float2(0.5f * (1.f - cs.y), -0.5f * cs.x);
+    float2 bq = make_float2(0.5f * (1.f + cs.y), 0.5f * cs.x);
+    float2 X = cadd(cmul(a, zk), cmul(bq, zm));
+    F.X[i] = X;
+    P[k] = X.x * X.x + X.y * X.y;                                   // kaldi.py:616-618
+  }
+  __syncwarp();
+}
+
+// lane c (< 30): mel energy (before the log); kaldi.py:621-630
+__device__ __forceinline__ float mel_energy(const SgFeatTables* T, const float* P, int lane) {
+  const int lo = T->mel_lo[lane], len = T->mel_len[lane], off = T->mel_off[lane];
+  float acc = 0.f;
+  for (int i = 0; i < T->mel_maxlen; ++i)
+    if (i < len) acc = fmaf(T->mel_w[off + i], P[lo + i], acc);
+  return acc;
+}
+
+__device__ __forceinline__ void copy_tables(SgFeatTables* dst, const SgFeatTables* __restrict__ src) {
+  const int4* s = reinterpret_cast<const int4*>(src);
+  int4* d = reinterpret_cast<int4*>(dst);
+  for (int i = threadIdx.x; i < (int)(sizeof(SgFeatTables) / 16); i += blockDim.x) d[i] = s[i];
+}
+static_assert(sizeof(SgFeatTables) % 16 == 0, "SgFeatTables must be int4-copyable");
+
+// =============================================================================================
+// F1: waveform -> raw MFCC
+// =============================================================================================
+__global__ void __launch_bounds__(FEAT_THREADS)
+mfcc_fwd_kernel(const float* __restrict__ x, int N, int m, int frames_per_cta, DitherSpec D,
+                float* __restrict__ raw, int ld, const SgFeatTables* __restrict__ gT) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SgFeatTables* T = reinterpret_cast<SgFeatTables*>(smem_raw);
+  copy_tables(T, gT);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* scratch = reinterpret_cast<float*>(smem_raw + sizeof(SgFeatTables)) + warp * WARP_SCRATCH;
+  float *sre = scratch, *sim = scratch + 288, *P = scratch + 576;
+  const int b = blockIdx.y;
+  const float* xb = x + (size_t)b * N;
+  const int f0 = blockIdx.x * frames_per_cta;
+  const int f1 = min(f0 + frames_per_cta, m);
+  for (int fr = f0 + warp; fr < f1; fr += FEAT_WARPS) {
+    Frame F;
+    load_frame(F, xb, N, b, m, fr, D, lane);
+    const float logE = logf(fmaxf(F.sumsq, SG_EPS));               // kaldi.py:119
+    frame_spectrum(F, T, sre, sim, P, lane);
+    float me = mel_energy(T, P, lane);
+    float lm = logf(fmaxf(me, SG_EPS));                            // kaldi.py:631-633
+    float c = 0.f;
+#pragma unroll
+    for (int n = 0; n < SG_NMEL; ++n) c = fmaf(__shfl_sync(0xffffffffu, lm, n), T->dct[n][lane], c);
+    if (lane == 0) c = logE;                                       // kaldi.py:799-800
+    if (lane >= SG_NCEP) c = 0.f;
+    if (lane < ld) raw[((size_t)b * m + fr) * ld + lane] = c;
+    __syncwarp();
+  }
+}
+
+// =============================================================================================
+// F2: d(raw MFCC) -> d(waveform), optionally fused with the L-inf sign step
+// =============================================================================================
+struct BwdOut {
+  int mode;               // 0: write gradient, 1: fused sign step
+  float* grad;            // mode 0: [B,N]
+  float scale;            // mode 0
+  int accumulate;         // mode 0
+  const float* x0;        // mode 1: clean waveform (bounds)
+  float* x_out;           // mode 1: updated iterate (must not alias the input waveform)
+  float step;             // mode 1: step_size * grad_sign
+  float eps;              // mode 1
+};
+
+__global__ void __launch_bounds__(FEAT_THREADS)
+mfcc_bwd_kernel(const float* __restrict__ x, int N, int m, int own_frames, DitherSpec D,
+                const float* __restrict__ draw, int ld, BwdOut O, const SgFeatTables* __restrict__ gT) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SgFeatTables* T = reinterpret_cast<SgFeatTables*>(smem_raw);
+  float* fbase = reinterpret_cast<float*>(smem_raw + sizeof(SgFeatTables));
+  float* framebuf = fbase + FEAT_WARPS * WARP_SCRATCH;             // [8][400]
+  float* acc = framebuf + FEAT_WARPS * SG_WIN;                     // [ACC_LEN]
+  copy_tables(T, gT);
+  for (int i = threadIdx.x; i < ACC_LEN; i += FEAT_THREADS) acc[i] = 0.f;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* scratch = fbase + warp * WARP_SCRATCH;
+  float *sre = scratch, *sim = scratch + 288, *P = scratch + 576;
+  float* mybuf = framebuf + warp * SG_WIN;
+  const int b = blockIdx.y;
+  const float* xb = x + (size_t)b * N;
+  const int f0 = blockIdx.x * own_frames;
+  const int f1 = min(f0 + own_frames, m);
+  const int fs = max(f0 - 2, 0);                                   // 2 halo frames on the left
+  const int pmax = SG_SHIFT * (m - 1) + (SG_WIN - SG_HALO) - 1;    // last padded position touched
+  const int own_lo = SG_SHIFT * f0 - SG_HALO;
+  const int own_hi = (f1 == m) ? pmax + 1 : SG_SHIFT * f1 - SG_HALO;
+
+  for (int gf = fs; gf < f1; gf += FEAT_WARPS) {
+    const int fr = gf + warp;
+    if (fr < f1) {
+      // ---- recompute the forward for this frame ------------------------------------------
+      Frame F;
+      load_frame(F, xb, N, b, m, fr, D, lane);
+      frame_spectrum(F, T, sre, sim, P, lane);
+      const float me = mel_energy(T, P, lane);
+      // ---- backward: cepstra -> log-mel -> mel -> power -> spectrum -----------------------
+      const float dC = (lane < SG_NCEP) ? __ldg(draw + ((size_t)b * m + fr) * ld + lane) : 0.f;
+      const float dE = __shfl_sync(0xffffffffu, dC, 0);            // C0 <- log-energy
+      float dM = 0.f;
+#pragma unroll
+      for (int k = 1; k < SG_NCEP; ++k) dM = fmaf(__shfl_sync(0xffffffffu, dC, k), T->dct_t[k][lane], dM);
+      const float dmel = (lane < SG_NMEL && me > SG_EPS) ? dM / me : 0.f;
+      __syncwarp();
+      P[lane] = dmel;                                              // P is free again: reuse as dmel[32]
+      __syncwarp();
+      float2 dX[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int k = lane + 32 * i;
+        float dP = T->bin_w0[k] * P[T->bin_c0[k]] + T->bin_w1[k] * P[T->bin_c1[k]];
+        dX[i] = make_float2(2.f * dP * F.X[i].x, 2.f * dP * F.X[i].y);
+        sre[k] = dX[i].x; sim[k] = dX[i].y;
+      }
+      __syncwarp();
+      // adjoint of the untangle step (derivation + check: tools/fft_proto.py):
+      //   dZ[k] = ((1-s) + i c)/2 * dX[k] + ((1+s) - i c)/2 * conj(dX[256-k]),  dZ[0] = 0
+      float2 z[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int k = lane + 32 * i;
+        const int km = (256 - k) & 255;
+        float2 xm = make_float2(sre[km], -sim[km]);
+        float2 cs = T->tw[16 + i][lane];
+        float2 ca = make_float2(0.5f * (1.f - cs.y), 0.5f * cs.x);
+        float2 cb = make_float2(0.5f * (1.f + cs.y), -0.5f * cs.x);
+        float2 dz = cadd(cmul(ca, dX[i]), cmul(cb, xm));
+        if (k == 0) dz = make_float2(0.f, 0.f);
+        z[i] = make_float2(dz.x, -dz.y);                           // conj -> forward FFT -> conj = inverse
+      }
+      __syncwarp();
+      warp_fft256(z, T->tw, sre, sim, lane);
+      fft_out_to_smem(z, sre, sim, lane);
+      __syncwarp();
+      // back in sample ownership: dg[2n] = Re dz[n], dg[2n+1] = Im dz[n] (conj: -sim)
+      float dge[7], dgo[7];
+#pragma unroll
+      for (int n0 = 0; n0 < 7; ++n0) {
+        const bool valid = (n0 < 6) || (lane < 8);
+        const int n = 32 * n0 + lane;
+        float2 w2 = valid ? *reinterpret_cast<const float2*>(&T->window[64 * n0 + 2 * lane]) : make_float2(0.f, 0.f);
+        dge[n0] = sre[n] * w2.x;
+        dgo[n0] = -sim[n] * w2.y;
+      }
+      // pre-emphasis adjoint: g[j] = f[j] - 0.97 f[max(j-1,0)]
+      float s = 0.f;
+      const float esc = (F.sumsq > SG_EPS) ? 2.f * dE / F.sumsq : 0.f;   // d log(sum f^2)
+      float dfe[7], dfo[7];
+#pragma unroll
+      for (int n0 = 0; n0 < 7; ++n0) {
+        const bool valid = (n0 < 6) || (lane < 8);
+        float dn = __shfl_down_sync(0xffffffffu, dge[n0], 1);      // even sample of lane+1
+        float wrap = __shfl_sync(0xffffffffu, dge[n0 < 6 ? n0 + 1 : 6], 0);
+        float next = lane < 31 ? dn : (n0 < 6 ? wrap : 0.f);       // dg of sample j+1 for the odd element
+        if (n0 == 6 && lane == 7) next = 0.f;                      // j = 399 is the last sample
+        float de = dge[n0] - 0.97f * dgo[n0];
+        float dd = dgo[n0] - 0.97f * next;
+        if (n0 == 0 && lane == 0) de -= 0.97f * dge[0];            // replicate pad at j = 0
+        de = fmaf(esc, F.fe[n0], de);
+        dd = fmaf(esc, F.fo[n0], dd);
+        dfe[n0] = valid ? de : 0.f;
+        dfo[n0] = valid ? dd : 0.f;
+        s += dfe[n0] + dfo[n0];
+      }
+      const float mean = warp_sum(s) * (1.0f / SG_WIN);            // DC-removal adjoint
+#pragma unroll
+      for (int n0 = 0; n0 < 7; ++n0)
+        if ((n0 < 6) || (lane < 8))
+          *reinterpret_cast<float2*>(&mybuf[64 * n0 + 2 * lane]) =
+              make_float2((dfe[n0] - mean) * 32768.0f, (dfo[n0] - mean) * 32768.0f);
+    }
+    __syncthreads();
+    // ---- deterministic overlap-add of this group's frames -----------------------------------
+    const int base = SG_SHIFT * gf - SG_HALO;                      // padded position of acc[0]
+    const int nfr = min(FEAT_WARPS, f1 - gf);
+    for (int q = threadIdx.x; q < ACC_LEN; q += FEAT_THREADS) {
+      float a = acc[q];
+#pragma unroll
+      for (int w = 0; w < FEAT_WARPS; ++w) {
+        const int jj = q - SG_SHIFT * w;
+        if (w < nfr && jj >= 0 && jj < SG_WIN) a += framebuf[w * SG_WIN + jj];
+      }
+      acc[q] = a;
+    }
+    __syncthreads();
+    const bool last = (gf + FEAT_WARPS >= f1);
+    const int fin = last ? ACC_LEN : ACC_FIN;
+    for (int q = threadIdx.x; q < fin; q += FEAT_THREADS) {
+      const int n = base + q;
+      if (n < own_lo || n >= own_hi || n < 0 || n >= N) continue;
+      float g = acc[q];
+      if (n < SG_HALO) {                                           // left reflection: p = -n-1
+        const int qm = (-n - 1) - base;
+        if (qm >= 0 && qm < ACC_LEN) g += acc[qm];
+      }
+      const int pr = 2 * N - 1 - n;                                // right reflection
+      if (pr <= pmax) {
+        const int qm = pr - base;
+        if (qm >= 0 && qm < ACC_LEN) g += acc[qm];
+      }
+      const size_t gi = (size_t)b * N + n;
+      if (O.mode == 0) {
+        float v = O.scale * g;
+        O.grad[gi] = O.accumulate ? O.grad[gi] + v : v;
+      } else {
+        const float xc = xb[n], x0 = O.x0[gi];
+        const float sg = (g > 0.f) ? 1.f : ((g < 0.f) ? -1.f : 0.f);
+        float xn = xc + O.step * sg;                               // attack/FGSM.py:65
+        const float lo = fmaxf(x0 - O.eps, -1.f), hi = fminf(x0 + O.eps, 1.f);   // attack/PGD.py:48-49
+        O.x_out[gi] = fminf(fmaxf(xn, lo), hi);                    // attack/FGSM.py:68
+      }
+    }
+    __syncthreads();
+    if (!last) {
+      // shift the 240-sample overlap to the front, clear the rest
+      float keep = 0.f;
+      if (threadIdx.x < ACC_LEN - ACC_FIN) keep = acc[threadIdx.x + ACC_FIN];
+      __syncthreads();
+      for (int q = threadIdx.x; q < ACC_LEN; q += FEAT_THREADS) acc[q] = (q < ACC_LEN - ACC_FIN) ? keep : 0.f;
+      __syncthreads();
+    }
+  }
+}
+
+// =============================================================================================
+// dither materialisation, sign step
+// =============================================================================================
+__global__ void dither_fill_kernel(int m, DitherSpec D, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int fr = blockIdx.x * (blockDim.x >> 5) + warp, b = blockIdx.y;
+  if (fr >= m) return;
+  float* o = out + ((size_t)b * m + fr) * SG_WIN;
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    uint4 r = philox4x32_10(make_uint4(h * 32 + lane, (uint32_t)fr, (uint32_t)b, D.pass),
+                            make_uint2(D.seed_lo, D.seed_hi));
+    float2 a = box_muller(r.x, r.y), c = box_muller(r.z, r.w);
+    int j0 = 64 * (2 * h) + 2 * lane, j1 = 64 * (2 * h + 1) + 2 * lane;
+    if (j0 < SG_WIN) { o[j0] = a.x; o[j0 + 1] = a.y; }
+    if (h < 3 && j1 < SG_WIN) { o[j1] = c.x; o[j1 + 1] = c.y; }
+  }
+}
+
+__global__ void step_linf_kernel(float* __restrict__ x, const float* __restrict__ x0,
+                                 const float* __restrict__ grad, size_t n, float step, float eps) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float g = grad[i], a = x0[i];
+    const float sg = (g > 0.f) ? 1.f : ((g < 0.f) ? -1.f : 0.f);
+    const float xn = x[i] + step * sg;
+    x[i] = fminf(fmaxf(xn, fmaxf(a - eps, -1.f)), fminf(a + eps, 1.f));
+  }
+}
+
+// =============================================================================================
+// CMVN (model/iv_plda.py:296-377): y[t] = x[t] - mean(x[ws(t):we(t)]), window 300 centred
+// =============================================================================================
+#define CMN_WIN 300
+__device__ __forceinline__ void cmvn_window(int t, int T, int& ws, int& we) {
+  ws = t - CMN_WIN / 2; we = ws + CMN_WIN;
+  if (ws < 0) { we -= ws; ws = 0; }
+  if (we > T) { ws -= (we - T); we = T; if (ws < 0) ws = 0; }
+}
+
+// one CTA per utterance, blockDim = (32 columns, 8 row lanes)
+__global__ void cmvn_kernel(const float* __restrict__ in, int ld_in, float* __restrict__ out, int ld_out,
+                            int T, int ncol, int backward) {
+  __shared__ float part[8][33];
+  __shared__ float tot[32];
+  const int c = threadIdx.x, r = threadIdx.y, b = blockIdx.x;
+  const float* ib = in + (size_t)b * T * ld_in;
+  float* ob = out + (size_t)b * T * ld_out;
+  const bool cin = c < ncol && c < ld_in;
+  if (T <= CMN_WIN) {
+    // every window is [0,T): global mean.  Self-adjoint: dx = dy - mean(dy).
+    float s = 0.f;
+    for (int t = r; t < T; t += 8) s += cin ? ib[(size_t)t * ld_in + c] : 0.f;
+    part[r][c] = s;
+    __syncthreads();
+    if (r == 0) {
+      float a = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a += part[i][c];
+      tot[c] = a / (float)T;
+    }
+    __syncthreads();
+    const float mu = tot[c];
+    for (int t = r; t < T; t += 8)
+      if (c < ld_out) ob[(size_t)t * ld_out + c] = cin ? ib[(size_t)t * ld_in + c] - mu : 0.f;
+    return;
+  }
+  // T > 300: sliding window.  Serial per column (rare path: > 3 s utterances), r == 0 only.
+  if (r != 0) return;
+  if (!backward) {
+    float cur = 0.f;
+    int ls = -1, le = -1;
+    for (int t = 0; t < T; ++t) {
+      int ws, we;
+      cmvn_window(t, T, ws, we);
+      if (ls < 0) { for (int u = ws; u < we; ++u) cur += cin ? ib[(size_t)u * ld_in + c] : 0.f; }
+      else {
+        if (ws > ls) cur -= cin ? ib[(size_t)ls * ld_in + c] : 0.f;
+        if (we > le) cur += cin ? ib[(size_t)le * ld_in + c] : 0.f;
+      }
+      ls = ws; le = we;
+      if (c < ld_out) ob[(size_t)t * ld_out + c] = cin ? ib[(size_t)t * ld_in + c] - cur / (float)(we - ws) : 0.f;
+    }
+  } else {
+    // dx[s] = dy[s] - (1/300) * sum_{t : ws(t) <= s < we(t)} dy[t]
+    // t < 150 -> [0,300);  150 <= t <= T-150 -> [t-150,t+150);  t > T-150 -> [T-300,T)
+    float head = 0.f, tail = 0.f;
+    for (int t = 0; t < CMN_WIN / 2; ++t) head += cin ? ib[(size_t)t * ld_in + c] : 0.f;
+    for (int t = T - CMN_WIN / 2 + 1; t < T; ++t) tail += cin ? ib[(size_t)t * ld_in + c] : 0.f;
+    // middle set for s: t in [max(s-149,150), min(s+150, T-150)]
+    float mid = 0.f;
+    int lo = 150, hi = 149;                                        // current inclusive range (empty)
+    for (int s = 0; s < T; ++s) {
+      const int nlo = max(s - 149, 150), nhi = min(s + 150, T - 150);
+      while (hi < nhi) { ++hi; mid += cin ? ib[(size_t)hi * ld_in + c] : 0.f; }
+      while (lo < nlo) { mid -= cin ? ib[(size_t)lo * ld_in + c] : 0.f; ++lo; }
+      float sum = mid + (s < CMN_WIN ? head : 0.f) + (s >= T - CMN_WIN ? tail : 0.f);
+      if (c < ld_out) ob[(size_t)s * ld_out + c] = cin ? ib[(size_t)s * ld_in + c] - sum * (1.0f / CMN_WIN) : 0.f;
+    }
+  }
+}
+
+// =============================================================================================
+// host launchers (called from sg_api.cu)
+// =============================================================================================
+static size_t feat_fwd_smem() { return sizeof(SgFeatTables) + FEAT_WARPS * WARP_SCRATCH * sizeof(float); }
+static size_t feat_bwd_smem() {
+  return sizeof(SgFeatTables) + (FEAT_WARPS * WARP_SCRATCH + FEAT_WARPS * SG_WIN + ACC_LEN) * sizeof(float);
+}
+
+static DitherSpec make_dither(int mode, const float* tensor, uint64_t seed, uint64_t pass) {
+  DitherSpec D;
+  D.mode = mode; D.tensor = tensor;
+  D.seed_lo = (uint32_t)seed; D.seed_hi = (uint32_t)(seed >> 32); D.pass = (uint32_t)pass;
+  return D;
+}
+
+int sg_feat_init() {
+  SG_CUDA_CHECK(cudaFuncSetAttribute(mfcc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)feat_fwd_smem()));
+  SG_CUDA_CHECK(cudaFuncSetAttribute(mfcc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)feat_bwd_smem()));
+  return SG_OK;
+}
+
+int sg_feat_fwd_launch(const SgFeatTables* dT, const float* x, int B, int N, int m, int mode, const float* dither,
+                       uint64_t seed, uint64_t pass, float* raw, int ld, cudaStream_t st) {
+  int fpc = 64;
+  while (fpc > 8 && (long long)B * ((m + fpc - 1) / fpc) < 592) fpc >>= 1;   // >= 4 CTAs per SM when possible
+  dim3 grid((m + fpc - 1) / fpc, B);
+  mfcc_fwd_kernel<<<grid, FEAT_THREADS, feat_fwd_smem(), st>>>(x, N, m, fpc, make_dither(mode, dither, seed, pass),
+                                                              raw, ld, dT);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+
+static int bwd_own_frames(int B, int m) {
+  int chunks = 1;
+  while (chunks < 16 && (long long)B * chunks < 444 && m / (chunks * 2) >= 16) chunks *= 2;
+  return (m + chunks - 1) / chunks;
+}
+
+int sg_feat_bwd_launch(const SgFeatTables* dT, const float* x, int B, int N, int m, int mode, const float* dither,
+                       uint64_t seed, uint64_t pass, const float* draw, int ld, float* grad, float scale,
+                       int accumulate, cudaStream_t st) {
+  BwdOut O;
+  memset(&O, 0, sizeof(O));
+  O.mode = 0; O.grad = grad; O.scale = scale; O.accumulate = accumulate;
+  int own = bwd_own_frames(B, m);
+  dim3 grid((m + own - 1) / own, B);
+  mfcc_bwd_kernel<<<grid, FEAT_THREADS, feat_bwd_smem(), st>>>(x, N, m, own, make_dither(mode, dither, seed, pass),
+                                                              draw, ld, O, dT);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+
+int sg_feat_bwd_step_launch(const SgFeatTables* dT, const float* x, int B, int N, int m, int mode,
+                            const float* dither, uint64_t seed, uint64_t pass, const float* draw, int ld,
+                            const float* x0, float* x_out, float step, float eps, cudaStream_t st) {
+  BwdOut O;
+  memset(&O, 0, sizeof(O));
+  O.mode = 1; O.x0 = x0; O.x_out = x_out; O.step = step; O.eps = eps;
+  int own = bwd_own_frames(B, m);
+  dim3 grid((m + own - 1) / own, B);
+  mfcc_bwd_kernel<<<grid, FEAT_THREADS, feat_bwd_smem(), st>>>(x, N, m, own, make_dither(mode, dither, seed, pass),
+                                                              draw, ld, O, dT);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+
+int sg_dither_fill_launch(int B, int m, uint64_t seed, uint64_t pass, float* out, cudaStream_t st) {
+  dim3 grid((m + 7) / 8, B);
+  dither_fill_kernel<<<grid, 256, 0, st>>>(m, make_dither(SG_DITHER_PHILOX, nullptr, seed, pass), out);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+
+int sg_step_linf_launch(float* x, const float* x0, const float* grad, size_t n, float step, float eps,
+                        cudaStream_t st) {
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  step_linf_kernel<<<blocks, 256, 0, st>>>(x, x0, grad, n, step, eps);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+
+int sg_cmvn_launch(const float* in, int ld_in, float* out, int ld_out, int B, int T, int backward, cudaStream_t st) {
+  cmvn_kernel<<<B, dim3(32, 8), 0, st>>>(in, ld_in, out, ld_out, T, SG_NCEP, backward);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}

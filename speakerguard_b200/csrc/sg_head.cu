@@ -1,0 +1,358 @@
+// H1: statistics pooling, embedding post-processing, PLDA scoring, decision and attack losses,
+// with their adjoints.  Everything here is per-utterance vector work (<= 3072 floats), fp32.
+//
+// Reference: stats pooling xvecTDNN.py:62; process_emb model/iv_plda.py:411-443 (length-norm
+// with detached norm: xvector_extract.py:31-38; PLDA transform plda.py:73-97); scoring
+// plda.py:140-190; decision model/defended_model.py:167-170; losses attack/utils.py:7-102.
+#include <math.h>
+
+#include "sg_common.cuh"
+#include "sg_head.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// statistics pooling over the valid frames of the last TDNN layer (post-ReLU, BN folded here)
+// grid (C5P/32, B), block (32, 8)
+// ---------------------------------------------------------------------------------------------
+__global__ void pool_fwd_kernel(const float* __restrict__ r5, int T, int Tv, const float* __restrict__ bn_mean,
+                                const float* __restrict__ bn_istd, float* __restrict__ stats,
+                                float* __restrict__ save_mean, float* __restrict__ save_std) {
+  __shared__ float part[8][33];
+  __shared__ float bc[32];
+  const int c = blockIdx.x * 32 + threadIdx.x, r = threadIdx.y, b = blockIdx.y;
+  const float* base = r5 + (size_t)b * T * SG_C5P + c;
+  float s = 0.f;
+  for (int t = r; t < Tv; t += 8) s += base[(size_t)t * SG_C5P];
+  part[r][threadIdx.x] = s;
+  __syncthreads();
+  if (r == 0) {
+    float a = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a += part[i][threadIdx.x];
+    bc[threadIdx.x] = a / (float)Tv;
+  }
+  __syncthreads();
+  const float mean = bc[threadIdx.x];
+  float q = 0.f;
+  for (int t = r; t < Tv; t += 8) { float d = base[(size_t)t * SG_C5P] - mean; q = fmaf(d, d, q); }
+  __syncthreads();
+  part[r][threadIdx.x] = q;
+  __syncthreads();
+  if (r == 0) {
+    float a = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a += part[i][threadIdx.x];
+    const float sd = sqrtf(a / (float)(Tv - 1));                   // unbiased (torch.std default)
+    const bool real = c < SG_C5;
+    const float mu = real ? bn_mean[c] : 0.f, is = real ? bn_istd[c] : 0.f;
+    stats[(size_t)b * SG_STATS + c] = real ? (mean - mu) * is : 0.f;
+    stats[(size_t)b * SG_STATS + SG_C5P + c] = real ? sd * is : 0.f;
+    save_mean[(size_t)b * SG_C5P + c] = mean;
+    save_std[(size_t)b * SG_C5P + c] = sd;
+  }
+}
+
+// d(stats) -> d(pre-ReLU layer-5 activation), ReLU mask and row validity applied
+// grid (C5P/32, B, tsplit), block (32, 8)
+__global__ void pool_bwd_kernel(const float* __restrict__ r5, int T, int Tv, const float* __restrict__ bn_istd,
+                                const float* __restrict__ dstats, const float* __restrict__ save_mean,
+                                const float* __restrict__ save_std, float* __restrict__ dA5) {
+  const int c = blockIdx.x * 32 + threadIdx.x, b = blockIdx.y;
+  const bool real = c < SG_C5;
+  const float is = real ? bn_istd[c] : 0.f;
+  const float mean = save_mean[(size_t)b * SG_C5P + c], sd = save_std[(size_t)b * SG_C5P + c];
+  const float alpha = real ? dstats[(size_t)b * SG_STATS + c] * is / (float)Tv : 0.f;
+  const float beta = (real && sd > 0.f) ? dstats[(size_t)b * SG_STATS + SG_C5P + c] * is / ((float)(Tv - 1) * sd) : 0.f;
+  const size_t off = (size_t)b * T * SG_C5P + c;
+  for (int t = blockIdx.z * 8 + threadIdx.y; t < T; t += 8 * gridDim.z) {
+    const float r = r5[off + (size_t)t * SG_C5P];
+    dA5[off + (size_t)t * SG_C5P] = (t < Tv && r > 0.f) ? fmaf(beta, r - mean, alpha) : 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// block helpers (blockDim.x == 256)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float a = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a += red[i];
+  return a;
+}
+
+// ---------------------------------------------------------------------------------------------
+// head forward: e2 (after LDA) -> length-norm -> PLDA transform -> normalised embedding q
+// one CTA (256 threads) per utterance
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+head_fwd_kernel(SgHeadConst H, const float* __restrict__ e2, float* __restrict__ tsave,
+                float* __restrict__ scal, float* __restrict__ emb) {
+  extern __shared__ float sm[];
+  float* v = sm;                 // [Lp]
+  float* red = sm + H.Lp;        // [8]
+  const int b = blockIdx.x, tid = threadIdx.x, L = H.L;
+  float x = 0.f;
+  for (int j = tid; j < L; j += 256) { float e = e2[(size_t)b * H.Lp + j]; x = fmaf(e, e, x); }
+  const float norm = sqrtf(block_sum(x, red));
+  const float ratio = sqrtf((float)L) / norm;                      // xvector_extract.py:31-38
+  for (int j = tid; j < L; j += 256) v[j] = e2[(size_t)b * H.Lp + j] * ratio - H.plda_mean[j];
+  __syncthreads();
+  float tloc[2] = {0.f, 0.f};                                      // L <= 512
+  float s = 0.f;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int i = tid + 256 * h;
+    if (i < L) {
+      float a = 0.f;
+      for (int j = 0; j < L; ++j) a = fmaf(H.plda_Tt[(size_t)j * L + i], v[j], a);   // plda.py:75
+      tloc[h] = a;
+      s = fmaf(a * a, H.inv_psi1[i], s);
+    }
+  }
+  s = block_sum(s, red);
+  const float factor = sqrtf((float)L / s);                        // plda.py:92-97
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int i = tid + 256 * h;
+    if (i < L) {
+      tsave[(size_t)b * H.Lp + i] = tloc[h];
+      emb[(size_t)b * L + i] = tloc[h] * factor;
+    }
+  }
+  if (tid == 0) { scal[b * 4 + 0] = ratio; scal[b * 4 + 1] = factor; scal[b * 4 + 2] = s; scal[b * 4 + 3] = norm; }
+}
+
+// head backward: dq -> de2 (norm treated as a constant: reference quirk Q2)
+__global__ void __launch_bounds__(256)
+head_bwd_kernel(SgHeadConst H, const float* __restrict__ dq, const float* __restrict__ tsave,
+                const float* __restrict__ scal, float* __restrict__ de2) {
+  extern __shared__ float sm[];
+  float* dt = sm;                // [Lp]
+  float* red = sm + H.Lp;
+  const int b = blockIdx.x, tid = threadIdx.x, L = H.L;
+  const float ratio = scal[b * 4 + 0], factor = scal[b * 4 + 1], s = scal[b * 4 + 2];
+  float dot = 0.f;
+  for (int i = tid; i < L; i += 256) dot = fmaf(dq[(size_t)b * L + i], tsave[(size_t)b * H.Lp + i], dot);
+  dot = block_sum(dot, red);
+  const float k = factor / s * dot;
+  for (int i = tid; i < L; i += 256)
+    dt[i] = factor * dq[(size_t)b * L + i] - k * H.inv_psi1[i] * tsave[(size_t)b * H.Lp + i];
+  __syncthreads();
+  for (int j = tid; j < H.Lp; j += 256) {
+    float a = 0.f;
+    if (j < L)
+      for (int i = 0; i < L; ++i) a = fmaf(H.plda_T[(size_t)i * L + j], dt[i], a);
+    de2[(size_t)b * H.Lp + j] = a * ratio;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// PLDA log-likelihood-ratio scoring + decision (plda.py:140-190, defended_model.py:167-170)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+score_fwd_kernel(SgHeadConst H, const float* __restrict__ emb, const float* __restrict__ enroll, int S,
+                 float threshold, float* __restrict__ scores, long long* __restrict__ decisions) {
+  extern __shared__ float sm[];
+  float* q = sm;                 // [L]
+  float* sc = sm + H.Lp;         // [S]
+  float* red = sc + S;           // [8]
+  const int b = blockIdx.x, tid = threadIdx.x, L = H.L, lane = tid & 31, warp = tid >> 5;
+  float s2 = 0.f;
+  for (int i = tid; i < L; i += 256) {
+    float x = emb[(size_t)b * L + i];
+    q[i] = x;
+    s2 = fmaf(x * x, H.inv_psi1[i], s2);
+  }
+  s2 = block_sum(s2, red);                                         // also orders the q[] writes
+  const float without = -0.5f * (H.logdet_without + H.log2pi_L + s2);
+  for (int n = warp; n < S; n += 8) {
+    float a = 0.f;
+    for (int i = lane; i < L; i += 32) {
+      float d = q[i] - H.psi_ratio[i] * enroll[(size_t)n * L + i];
+      a = fmaf(d * d, H.inv_var_given[i], a);
+    }
+    a = warp_sum(a);
+    if (lane == 0) {
+      float given = -0.5f * (H.logdet_given + H.log2pi_L + a);
+      float v = given - without;
+      sc[n] = v;
+      scores[(size_t)b * S + n] = v;
+    }
+  }
+  __syncthreads();
+  if (decisions != nullptr && warp == 0) {
+    float best = -INFINITY; int bi = 0x7fffffff;
+    for (int n = lane; n < S; n += 32)
+      if (sc[n] > best) { best = sc[n]; bi = n; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) decisions[b] = (best > threshold) ? (long long)bi : -1LL;
+  }
+}
+
+// dscores -> demb
+__global__ void __launch_bounds__(256)
+score_bwd_kernel(SgHeadConst H, const float* __restrict__ emb, const float* __restrict__ dscores,
+                 const float* __restrict__ enroll, int S, float* __restrict__ demb) {
+  extern __shared__ float sm[];
+  float* ds = sm;                // [S]
+  const int b = blockIdx.x, tid = threadIdx.x, L = H.L;
+  for (int n = tid; n < S; n += 256) ds[n] = dscores[(size_t)b * S + n];
+  __syncthreads();
+  for (int i = tid; i < L; i += 256) {
+    const float qi = emb[(size_t)b * L + i], pr = H.psi_ratio[i], iv = H.inv_var_given[i], w = H.inv_psi1[i];
+    float a = 0.f;
+    for (int n = 0; n < S; ++n) a = fmaf(ds[n], -(qi - pr * enroll[(size_t)n * L + i]) * iv + qi * w, a);
+    demb[(size_t)b * L + i] = a;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// losses (attack/utils.py:7-102) and d(sum loss)/d(scores).  One warp per utterance.
+// ---------------------------------------------------------------------------------------------
+struct ArgMax { float v; int i; };
+__device__ __forceinline__ ArgMax warp_argmax(float v, int i) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    int oi = __shfl_xor_sync(0xffffffffu, i, o);
+    if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+  }
+  ArgMax r; r.v = v; r.i = i; return r;
+}
+
+__global__ void loss_kernel(const float* __restrict__ scores, const long long* __restrict__ y, int B, int S,
+                            sg_loss_params lp, float* __restrict__ loss, float* __restrict__ dscores) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const float* sc = scores + (size_t)b * S;
+  float* ds = dscores ? dscores + (size_t)b * S : nullptr;
+  const int lab = (int)y[b];
+  if (ds) for (int n = lane; n < S; n += 32) ds[n] = 0.f;
+  __syncwarp();
+  float L = 0.f;
+  if (lp.loss == SG_LOSS_CE && lp.task == SG_TASK_CSI) {
+    if (lab >= 0) {
+      float mx = -INFINITY;
+      for (int n = lane; n < S; n += 32) mx = fmaxf(mx, sc[n]);
+      mx = warp_max(mx);
+      float se = 0.f;
+      for (int n = lane; n < S; n += 32) se += expf(sc[n] - mx);
+      se = warp_sum(se);
+      L = logf(se) + mx - sc[lab];
+      if (ds) for (int n = lane; n < S; n += 32) ds[n] = expf(sc[n] - mx) / se - (n == lab ? 1.f : 0.f);
+    }
+    if (lane == 0) loss[b] = L;
+    return;
+  }
+  // ---- margin family ----
+  // every branch yields loss = sum_k coef_k * score[idx_k] + const with at most 2 active indices
+  int i0 = -1, i1 = -1; float c0 = 0.f, c1 = 0.f;
+  const float thr = lp.threshold, conf = lp.confidence;
+  if (lp.task == SG_TASK_SV) {
+    const float s = sc[0];
+    const bool plus = (lab == 0) ? !lp.targeted : (lp.targeted != 0);   // loss = s + conf - thr
+    L = plus ? s + conf - thr : thr + conf - s;
+    i0 = 0; c0 = plus ? 1.f : -1.f;
+  } else if (lab >= 0) {
+    ArgMax oth; { float bv = -INFINITY; int bi = 0x7fffffff;
+      for (int n = lane; n < S; n += 32) { float v = (n == lab) ? -10000.f : sc[n]; if (v > bv) { bv = v; bi = n; } }
+      oth = warp_argmax(bv, bi); }
+    const float real = sc[lab];
+    const float gother = (oth.i != lab) ? 1.f : 0.f;               // (1-onehot)*scores: no grad through the label slot
+    if (lp.targeted) {
+      if (lp.task == SG_TASK_CSI) { L = oth.v + conf - real; i0 = oth.i; c0 = gother; }
+      else { L = fmaxf(oth.v, thr) + conf - real; i0 = oth.i; c0 = (oth.v >= thr) ? gother : 0.f; }
+      i1 = lab; c1 = -1.f;
+    } else if (lp.task == SG_TASK_CSI) {
+      L = real + conf - oth.v; i0 = lab; c0 = 1.f; i1 = oth.i; c1 = -gother;
+    } else {
+      ArgMax mx; { float bv = -INFINITY; int bi = 0x7fffffff;
+        for (int n = lane; n < S; n += 32) if (sc[n] > bv) { bv = sc[n]; bi = n; }
+        mx = warp_argmax(bv, bi); }
+      const float f_rej = mx.v + conf - thr;
+      const float f_mis = fmaxf(real, thr) + conf - oth.v;
+      L = fminf(f_rej, f_mis);
+      // torch.minimum: ties split the gradient evenly
+      const float wr = (f_rej < f_mis) ? 1.f : ((f_rej == f_mis) ? 0.5f : 0.f), wm = 1.f - wr;
+      if (ds && lane == 0) {
+        atomicAdd(&ds[mx.i], wr);
+        if (real >= thr) atomicAdd(&ds[lab], wm);
+        atomicAdd(&ds[oth.i], -wm * gother);
+      }
+      i0 = -2;                                                     // handled
+    }
+  } else if (lp.task == SG_TASK_OSI) {                              // imposter, OSI
+    ArgMax mx; { float bv = -INFINITY; int bi = 0x7fffffff;
+      for (int n = lane; n < S; n += 32) if (sc[n] > bv) { bv = sc[n]; bi = n; }
+      mx = warp_argmax(bv, bi); }
+    if (lp.targeted) { L = mx.v + conf - thr; i0 = mx.i; c0 = 1.f; }
+    else { L = thr + conf - mx.v; i0 = mx.i; c0 = -1.f; }
+  }  // CSI imposter: 0 * sum(scores): zero loss, zero gradient (quirk Q7)
+  float g = 1.f;
+  if (lp.clip_max) {                                               // torch.max(0, loss): tie -> half gradient
+    g = (L > 0.f) ? 1.f : ((L == 0.f) ? 0.5f : 0.f);
+    L = fmaxf(L, 0.f);
+  }
+  __syncwarp();
+  if (ds && lane == 0) {
+    if (i0 == -2) { for (int n = 0; n < S; ++n) ds[n] *= g; }
+    else {
+      if (i0 >= 0) ds[i0] += g * c0;
+      if (i1 >= 0) ds[i1] += g * c1;
+    }
+  }
+  if (lane == 0) loss[b] = L;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------------
+int sg_pool_fwd_launch(const float* r5, int B, int T, int Tv, const float* bn_mean, const float* bn_istd,
+                       float* stats, float* save_mean, float* save_std, cudaStream_t st) {
+  pool_fwd_kernel<<<dim3(SG_C5P / 32, B), dim3(32, 8), 0, st>>>(r5, T, Tv, bn_mean, bn_istd, stats, save_mean, save_std);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+int sg_pool_bwd_launch(const float* r5, int B, int T, int Tv, const float* bn_istd, const float* dstats,
+                       const float* save_mean, const float* save_std, float* dA5, cudaStream_t st) {
+  int tsplit = (B >= 64) ? 1 : 4;
+  pool_bwd_kernel<<<dim3(SG_C5P / 32, B, tsplit), dim3(32, 8), 0, st>>>(r5, T, Tv, bn_istd, dstats, save_mean, save_std, dA5);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+int sg_head_fwd_launch(const SgHeadConst& H, const float* e2, int B, float* tsave, float* scal, float* emb, cudaStream_t st) {
+  head_fwd_kernel<<<B, 256, (H.Lp + 8) * sizeof(float), st>>>(H, e2, tsave, scal, emb);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+int sg_head_bwd_launch(const SgHeadConst& H, const float* dq, int B, const float* tsave, const float* scal, float* de2, cudaStream_t st) {
+  head_bwd_kernel<<<B, 256, (H.Lp + 8) * sizeof(float), st>>>(H, dq, tsave, scal, de2);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+int sg_score_fwd_launch(const SgHeadConst& H, const float* emb, int B, const float* enroll, int S, float threshold,
+                        float* scores, long long* decisions, cudaStream_t st) {
+  score_fwd_kernel<<<B, 256, (H.Lp + S + 8) * sizeof(float), st>>>(H, emb, enroll, S, threshold, scores, decisions);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+int sg_score_bwd_launch(const SgHeadConst& H, const float* emb, const float* dscores, int B, const float* enroll, int S,
+                        float* demb, cudaStream_t st) {
+  score_bwd_kernel<<<B, 256, (S + 8) * sizeof(float), st>>>(H, emb, dscores, enroll, S, demb);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+int sg_loss_launch(const float* scores, const long long* y, int B, int S, const sg_loss_params& lp, float* loss,
+                   float* dscores, cudaStream_t st) {
+  loss_kernel<<<(B + 7) / 8, 256, 0, st>>>(scores, y, B, S, lp, loss, dscores);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}

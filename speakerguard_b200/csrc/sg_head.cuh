@@ -1,0 +1,40 @@
+// Internal declarations shared by sg_head.cu / sg_feat.cu / sg_api.cu.
+#pragma once
+#include "sg_common.cuh"
+
+struct SgHeadConst {           // device pointers + scalars describing the PLDA back-end
+  int L, Lp;                   // embedding dim and its padding to a multiple of 16
+  const float* plda_mean;      // [L]
+  const float* plda_T;         // [L][L]   transform (row i = output i)
+  const float* plda_Tt;        // [L][L]   transposed copy (coalesced mat-vec in the forward)
+  const float* inv_psi1;       // 1 / (psi + 1)
+  const float* psi_ratio;      // psi / (psi + 1)
+  const float* inv_var_given;  // 1 / (1 + psi / (psi + 1))
+  float logdet_given, logdet_without, log2pi_L;   // plda.py:176-186 constants (fp32 like the reference)
+};
+
+int sg_feat_init();
+int sg_feat_fwd_launch(const SgFeatTables* dT, const float* x, int B, int N, int m, int mode, const float* dither,
+                       uint64_t seed, uint64_t pass, float* raw, int ld, cudaStream_t st);
+int sg_feat_bwd_launch(const SgFeatTables* dT, const float* x, int B, int N, int m, int mode, const float* dither,
+                       uint64_t seed, uint64_t pass, const float* draw, int ld, float* grad, float scale,
+                       int accumulate, cudaStream_t st);
+int sg_feat_bwd_step_launch(const SgFeatTables* dT, const float* x, int B, int N, int m, int mode,
+                            const float* dither, uint64_t seed, uint64_t pass, const float* draw, int ld,
+                            const float* x0, float* x_out, float step, float eps, cudaStream_t st);
+int sg_dither_fill_launch(int B, int m, uint64_t seed, uint64_t pass, float* out, cudaStream_t st);
+int sg_step_linf_launch(float* x, const float* x0, const float* grad, size_t n, float step, float eps, cudaStream_t st);
+int sg_cmvn_launch(const float* in, int ld_in, float* out, int ld_out, int B, int T, int backward, cudaStream_t st);
+
+int sg_pool_fwd_launch(const float* r5, int B, int T, int Tv, const float* bn_mean, const float* bn_istd,
+                       float* stats, float* save_mean, float* save_std, cudaStream_t st);
+int sg_pool_bwd_launch(const float* r5, int B, int T, int Tv, const float* bn_istd, const float* dstats,
+                       const float* save_mean, const float* save_std, float* dA5, cudaStream_t st);
+int sg_head_fwd_launch(const SgHeadConst& H, const float* e2, int B, float* tsave, float* scal, float* emb, cudaStream_t st);
+int sg_head_bwd_launch(const SgHeadConst& H, const float* dq, int B, const float* tsave, const float* scal, float* de2, cudaStream_t st);
+int sg_score_fwd_launch(const SgHeadConst& H, const float* emb, int B, const float* enroll, int S, float threshold,
+                        float* scores, long long* decisions, cudaStream_t st);
+int sg_score_bwd_launch(const SgHeadConst& H, const float* emb, const float* dscores, int B, const float* enroll, int S,
+                        float* demb, cudaStream_t st);
+int sg_loss_launch(const float* scores, const long long* y, int B, int S, const sg_loss_params& lp, float* loss,
+                   float* dscores, cudaStream_t st);

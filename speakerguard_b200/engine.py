@@ -1,0 +1,242 @@
+"""Thin Python owner of one libsgb200 handle (one per device).
+
+PyTorch is used for device memory and streams only: every method takes contiguous fp32 CUDA
+tensors, passes raw ``data_ptr()``s to the C-ABI on the current stream, and returns tensors
+allocated with the caching allocator.  Nothing here computes on the host.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import LossParams, PgdParams, XvWeights, check
+
+FLD = 32  # internal feature row stride
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _f32c(t: torch.Tensor, dev: torch.device) -> torch.Tensor:
+    if t.device != dev:
+        raise _lib.SgError(f"tensor on {t.device}, engine on {dev}")
+    return t.detach().to(torch.float32).contiguous()
+
+
+def make_loss_params(loss_name: str = "Entropy", targeted: bool = False, task: str = "CSI", confidence: float = 0.0,
+                     threshold: Optional[float] = None, clip_max: bool = False) -> LossParams:
+    """Loss selection rule of the reference's resolve_loss (attack/utils.py:104-116)."""
+    if task not in _lib.TASKS:
+        raise ValueError(f"task must be one of {list(_lib.TASKS)}")
+    if loss_name not in ("Entropy", "Margin"):
+        raise ValueError("loss must be 'Entropy' or 'Margin'")
+    margin = task in ("SV", "OSI") or loss_name == "Margin"
+    thr = 0.0 if threshold is None or not math.isfinite(threshold) else float(threshold)
+    return LossParams(_lib.LOSS_MARGIN if margin else _lib.LOSS_CE, _lib.TASKS[task], int(bool(targeted)),
+                      int(bool(clip_max)), float(confidence), thr)
+
+
+class Engine:
+    def __init__(self, device="cuda:0", precision: str = "fp32"):
+        self.lib = _lib.load()
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise _lib.SgError(f"speakerguard_b200 runs on CUDA devices only (got '{device}'); there is no CPU fallback")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.device = dev
+        self._h = C.c_void_p()
+        with torch.cuda.device(dev):
+            check(self.lib.sg_create(C.byref(self._h), dev.index), "sg_create")
+        self.L = self.S = 0
+        self.set_precision(precision)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            self.lib.sg_destroy(h)
+            self._h = C.c_void_p()
+
+    # ---- configuration -----------------------------------------------------------------------
+    def set_precision(self, precision: str) -> None:
+        check(self.lib.sg_set_precision(self._h, _lib.PRECISIONS[precision]), "sg_set_precision")
+        self.precision = precision
+
+    @property
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def launch_count(self) -> int:
+        return int(self.lib.sg_launch_count(self._h))
+
+    def reset_launch_count(self) -> None:
+        self.lib.sg_reset_launch_count(self._h)
+
+    def load_xv(self, p: Dict[str, torch.Tensor], bn_eps: float = 1e-5) -> None:
+        """p: 'tdnn{1..5}.weight/.bias', 'bn{1..5}.mean/.var', 'fc1.weight/.bias', 'emb_mean',
+        'lda' [L,513], 'plda.mean/.transform/.psi', 'enroll' [S,L] (any device; copied to host)."""
+        keep = []
+
+        def host(name):
+            a = np.ascontiguousarray(p[name].detach().cpu().numpy().astype(np.float32))
+            keep.append(a)
+            return a.ctypes.data
+
+        w = XvWeights()
+        for i in range(5):
+            w.tdnn_w[i] = host(f"tdnn{i + 1}.weight")
+            w.tdnn_b[i] = host(f"tdnn{i + 1}.bias")
+            w.bn_mean[i] = host(f"bn{i + 1}.mean")
+            w.bn_var[i] = host(f"bn{i + 1}.var")
+        w.fc1_w, w.fc1_b = host("fc1.weight"), host("fc1.bias")
+        w.emb_mean, w.lda = host("emb_mean"), host("lda")
+        w.plda_mean, w.plda_transform, w.plda_psi = host("plda.mean"), host("plda.transform"), host("plda.psi")
+        w.enroll = host("enroll")
+        w.L, w.S, w.bn_eps = int(p["plda.mean"].shape[0]), int(p["enroll"].shape[0]), float(bn_eps)
+        if tuple(p["lda"].shape) != (w.L, 513):
+            raise ValueError(f"lda must be [L, 513], got {tuple(p['lda'].shape)}")
+        with torch.cuda.device(self.device):
+            check(self.lib.sg_load_xv(self._h, C.byref(w)), "sg_load_xv")
+        self.L, self.S = w.L, w.S
+
+    # ---- stage ops -----------------------------------------------------------------------------
+    def num_frames(self, N: int) -> int:
+        return int(self.lib.sg_num_frames(N))
+
+    def mfcc_fwd(self, x: torch.Tensor, dither_mode: int = _lib.DITHER_OFF, dither: Optional[torch.Tensor] = None,
+                 seed: int = 0, pass_: int = 0, ld: int = 30) -> torch.Tensor:
+        x = _f32c(x, self.device)
+        B, N = x.shape
+        raw = torch.empty(B, self.num_frames(N), ld, device=self.device, dtype=torch.float32)
+        d = None if dither is None else _f32c(dither, self.device)
+        check(self.lib.sg_mfcc_fwd(self._h, _ptr(x), B, N, dither_mode, _ptr(d), seed, pass_, _ptr(raw), ld, self.stream),
+              "sg_mfcc_fwd")
+        return raw
+
+    def mfcc_bwd(self, x: torch.Tensor, draw: torch.Tensor, dither_mode: int = _lib.DITHER_OFF,
+                 dither: Optional[torch.Tensor] = None, seed: int = 0, pass_: int = 0,
+                 grad: Optional[torch.Tensor] = None, scale: float = 1.0) -> torch.Tensor:
+        x, draw = _f32c(x, self.device), _f32c(draw, self.device)
+        B, N = x.shape
+        acc = grad is not None
+        if grad is None:
+            grad = torch.empty(B, N, device=self.device, dtype=torch.float32)
+        d = None if dither is None else _f32c(dither, self.device)
+        check(self.lib.sg_mfcc_bwd(self._h, _ptr(x), B, N, dither_mode, _ptr(d), seed, pass_, _ptr(draw), draw.shape[2],
+                                   _ptr(grad), scale, int(acc), self.stream), "sg_mfcc_bwd")
+        return grad
+
+    def dither_fill(self, B: int, N: int, seed: int, pass_: int) -> torch.Tensor:
+        out = torch.empty(B, self.num_frames(N), 400, device=self.device, dtype=torch.float32)
+        check(self.lib.sg_dither_fill(self._h, B, N, seed, pass_, _ptr(out), self.stream), "sg_dither_fill")
+        return out
+
+    def cmvn(self, feat: torch.Tensor, ld_out: int = 30, backward: bool = False) -> torch.Tensor:
+        feat = _f32c(feat, self.device)
+        B, T, ld = feat.shape
+        out = torch.empty(B, T, ld_out, device=self.device, dtype=torch.float32)
+        fn = self.lib.sg_cmvn_bwd if backward else self.lib.sg_cmvn_fwd
+        check(fn(self._h, _ptr(feat), ld, _ptr(out), ld_out, B, T, self.stream), "sg_cmvn")
+        return out
+
+    def alloc_ws(self, nbytes: int) -> torch.Tensor:
+        return torch.empty(nbytes, device=self.device, dtype=torch.uint8)
+
+    def embed_fwd(self, feat32: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """feat32 [B,T,32] -> (emb [B,L], workspace holding the activations for embed_bwd)."""
+        feat32 = _f32c(feat32, self.device)
+        B, T, ld = feat32.shape
+        assert ld == FLD
+        ws = self.alloc_ws(self.lib.sg_xv_ws_bytes(self._h, B, T))
+        emb = torch.empty(B, self.L, device=self.device, dtype=torch.float32)
+        check(self.lib.sg_xv_embed_fwd(self._h, _ptr(feat32), B, T, _ptr(ws), _ptr(emb), self.stream), "sg_xv_embed_fwd")
+        return emb, ws
+
+    def embed_bwd(self, demb: torch.Tensor, ws: torch.Tensor, B: int, T: int) -> torch.Tensor:
+        demb = _f32c(demb, self.device)
+        dfeat = torch.empty(B, T, FLD, device=self.device, dtype=torch.float32)
+        check(self.lib.sg_xv_embed_bwd(self._h, _ptr(demb), B, T, _ptr(ws), _ptr(dfeat), self.stream), "sg_xv_embed_bwd")
+        return dfeat
+
+    def score_fwd(self, emb: torch.Tensor, enroll: Optional[torch.Tensor] = None, threshold: float = -math.inf,
+                  want_decisions: bool = True):
+        emb = _f32c(emb, self.device)
+        B = emb.shape[0]
+        en = None if enroll is None else _f32c(enroll, self.device)
+        S = self.S if en is None else en.shape[0]
+        scores = torch.empty(B, S, device=self.device, dtype=torch.float32)
+        dec = torch.empty(B, device=self.device, dtype=torch.int64) if want_decisions else None
+        check(self.lib.sg_plda_score_fwd(self._h, _ptr(emb), B, _ptr(en), S, float(threshold), _ptr(scores), _ptr(dec),
+                                         self.stream), "sg_plda_score_fwd")
+        return scores, dec
+
+    def score_bwd(self, emb: torch.Tensor, dscores: torch.Tensor, enroll: Optional[torch.Tensor] = None) -> torch.Tensor:
+        emb, dscores = _f32c(emb, self.device), _f32c(dscores, self.device)
+        en = None if enroll is None else _f32c(enroll, self.device)
+        B, S = dscores.shape
+        demb = torch.empty_like(emb)
+        check(self.lib.sg_plda_score_bwd(self._h, _ptr(emb), _ptr(dscores), B, _ptr(en), S, _ptr(demb), self.stream),
+              "sg_plda_score_bwd")
+        return demb
+
+    def loss(self, scores: torch.Tensor, y: torch.Tensor, lp: LossParams, want_grad: bool = True):
+        scores = _f32c(scores, self.device)
+        y = y.to(device=self.device, dtype=torch.int64).contiguous()
+        B, S = scores.shape
+        loss = torch.empty(B, device=self.device, dtype=torch.float32)
+        ds = torch.empty_like(scores) if want_grad else None
+        check(self.lib.sg_loss_fwd_bwd(self._h, _ptr(scores), _ptr(y), B, S, C.byref(lp), _ptr(loss), _ptr(ds), self.stream),
+              "sg_loss_fwd_bwd")
+        return loss, ds
+
+    def step_linf(self, x: torch.Tensor, x0: torch.Tensor, grad: torch.Tensor, step: float, grad_sign: float,
+                  eps: float) -> None:
+        """In place on x (must be contiguous fp32)."""
+        assert x.is_contiguous() and x.dtype == torch.float32
+        check(self.lib.sg_step_linf(self._h, _ptr(x), _ptr(_f32c(x0, self.device)), _ptr(_f32c(grad, self.device)),
+                                    x.numel(), step, grad_sign, eps, self.stream), "sg_step_linf")
+
+    # ---- fused paths -------------------------------------------------------------------------
+    def xv_forward(self, x: torch.Tensor, dither_mode: int, dither: Optional[torch.Tensor], seed: int, pass_: int,
+                   threshold: float = -math.inf, ws: Optional[torch.Tensor] = None):
+        x = _f32c(x, self.device)
+        B, N = x.shape
+        if ws is None:
+            ws = self.alloc_ws(self.lib.sg_pgd_ws_bytes(self._h, B, N))
+        scores = torch.empty(B, self.S, device=self.device, dtype=torch.float32)
+        dec = torch.empty(B, device=self.device, dtype=torch.int64)
+        emb = torch.empty(B, self.L, device=self.device, dtype=torch.float32)
+        d = None if dither is None else _f32c(dither, self.device)
+        check(self.lib.sg_xv_forward(self._h, _ptr(x), B, N, dither_mode, _ptr(d), seed, pass_, float(threshold), _ptr(ws),
+                                     _ptr(scores), _ptr(dec), _ptr(emb), self.stream), "sg_xv_forward")
+        return scores, dec, emb
+
+    def pgd_ws(self, B: int, N: int) -> torch.Tensor:
+        return self.alloc_ws(self.lib.sg_pgd_ws_bytes(self._h, B, N))
+
+    def pgd_run(self, x_adv: torch.Tensor, x0: torch.Tensor, y: torch.Tensor, *, max_iter: int, epsilon: float,
+                step_size: float, lp: LossParams, dither_mode: int = _lib.DITHER_PHILOX,
+                dither: Optional[torch.Tensor] = None, seed: int = 0, eot_size: int = 1,
+                decision_threshold: float = -math.inf, ws: Optional[torch.Tensor] = None, want_loss_hist: bool = False):
+        """x_adv [B,N] is updated in place.  Returns (decisions [B] i64, scores [B,S], loss_hist or None)."""
+        assert x_adv.is_contiguous() and x_adv.dtype == torch.float32 and x_adv.device == self.device
+        x0 = _f32c(x0, self.device)
+        y = y.to(device=self.device, dtype=torch.int64).contiguous()
+        B, N = x_adv.shape
+        if ws is None:
+            ws = self.pgd_ws(B, N)
+        scores = torch.empty(B, self.S, device=self.device, dtype=torch.float32)
+        dec = torch.empty(B, device=self.device, dtype=torch.int64)
+        hist = torch.empty(max_iter + 1, B, device=self.device, dtype=torch.float32) if want_loss_hist else None
+        d = None if dither is None else _f32c(dither, self.device)
+        pp = PgdParams(int(max_iter), float(epsilon), float(step_size), int(eot_size), int(dither_mode), int(seed), lp,
+                       float(decision_threshold))
+        check(self.lib.sg_pgd_run(self._h, _ptr(x_adv), _ptr(x0), _ptr(y), _ptr(d), B, N, C.byref(pp), _ptr(ws), _ptr(dec),
+                                  _ptr(scores), _ptr(hist), self.stream), "sg_pgd_run")
+        return dec, scores, hist

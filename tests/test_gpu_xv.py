@@ -1,0 +1,341 @@
+"""GPU parity tests for the x-vector path: libsgb200 (through the C-ABI) vs the CPU oracle and the
+golden fixtures produced by the reference.  Run on a B200 with ``-m gpu``.
+
+Tolerances (BASELINE.json north_star): fp32 mode features / embeddings / scores / input gradients
+within 1e-4 relative (max-norm per row); decisions bit-exact; single-step iterates bit-exact
+wherever |grad| > 1e-6.
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sg_oracle as O
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def relerr(a: torch.Tensor, b: torch.Tensor) -> float:
+    """max over rows of max|a-b| / max|b| (rows = leading dim)."""
+    a, b = a.detach().double().cpu().flatten(1), b.detach().double().cpu().flatten(1)
+    return float(((a - b).abs().max(1)[0] / b.abs().max(1)[0].clamp_min(1e-30)).max())
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from speakerguard_b200.engine import Engine
+    e = Engine("cuda:0", precision="fp32")
+    e.load_xv(O.make_xv_params(seed=0))
+    return e
+
+
+@pytest.fixture(scope="module")
+def params():
+    return O.make_xv_params(seed=0)
+
+
+@pytest.fixture(scope="module")
+def xv():
+    return np.load(os.path.join(G, "xv_golden.npz"))
+
+
+def wave(B, N, seed=1234):
+    torch.manual_seed(seed)
+    return ((torch.rand(B, 1, N) * 2 - 1) * 0.5)[:, 0].contiguous()
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,N", [(3, 32000), (2, 48000), (2, 17777), (1, 400), (2, 80000)])
+def test_mfcc_forward_no_dither(eng, B, N):
+    from speakerguard_b200 import _lib
+    x = wave(B, N)
+    ref = O.mfcc(x)
+    got = eng.mfcc_fwd(x.cuda(), _lib.DITHER_OFF).cpu()
+    assert got.shape == ref.shape
+    e = float((got - ref).abs().max() / ref.abs().max())
+    print(f"mfcc no-dither B={B} N={N}: max abs {float((got - ref).abs().max()):.3e} rel {e:.3e}")
+    assert e < 1e-4
+
+
+def test_mfcc_forward_tensor_dither_and_ld32(eng):
+    from speakerguard_b200 import _lib
+    x = wave(4, 32000)
+    d = torch.randn(4, 200, 400, generator=torch.Generator().manual_seed(5))
+    ref = O.mfcc(x, d)
+    got = eng.mfcc_fwd(x.cuda(), _lib.DITHER_TENSOR, d.cuda(), ld=32).cpu()
+    assert torch.all(got[:, :, 30:] == 0)
+    e = float((got[:, :, :30] - ref).abs().max() / ref.abs().max())
+    print(f"mfcc tensor dither rel {e:.3e}")
+    assert e < 1e-4
+
+
+def test_mfcc_philox_dither_is_reproducible_and_normal(eng):
+    from speakerguard_b200 import _lib
+    x = wave(2, 32000)
+    d = eng.dither_fill(2, 32000, seed=77, pass_=3)
+    d2 = eng.dither_fill(2, 32000, seed=77, pass_=3)
+    d3 = eng.dither_fill(2, 32000, seed=77, pass_=4)
+    assert torch.equal(d, d2) and not torch.equal(d, d3)
+    dc = d.cpu().double()
+    assert abs(float(dc.mean())) < 0.02 and abs(float(dc.std()) - 1.0) < 0.02
+    assert abs(float((dc ** 4).mean()) - 3.0) < 0.15           # kurtosis of N(0,1)
+    a = eng.mfcc_fwd(x.cuda(), _lib.DITHER_PHILOX, None, seed=77, pass_=3).cpu()
+    ref = O.mfcc(x, d.cpu())
+    e = float((a - ref).abs().max() / ref.abs().max())
+    print(f"mfcc philox vs oracle on the materialised noise rel {e:.3e}")
+    assert e < 1e-4
+
+
+@pytest.mark.parametrize("T", [40, 200, 300, 301, 500])
+def test_cmvn_forward_backward(eng, T):
+    g = torch.Generator().manual_seed(T)
+    f = (torch.randn(3, T, 30, generator=g) * 8).requires_grad_(True)
+    ref = O.cmvn(f)
+    w = torch.randn(3, T, 30, generator=g)
+    (ref * w).sum().backward()
+    got = eng.cmvn(f.detach().cuda(), ld_out=32).cpu()
+    assert torch.all(got[:, :, 30:] == 0)
+    assert float((got[:, :, :30] - ref).abs().max()) < 5e-5
+    gb = eng.cmvn(w.cuda(), ld_out=30, backward=True).cpu()
+    assert float((gb - f.grad).abs().max()) < 5e-5
+
+
+@pytest.mark.parametrize("B,N,dith", [(2, 32000, False), (2, 17777, True), (1, 48000, True), (2, 4000, False)])
+def test_mfcc_adjoint(eng, B, N, dith):
+    from speakerguard_b200 import _lib
+    x = wave(B, N, seed=7).requires_grad_(True)
+    m = O.num_frames(N)
+    g = torch.Generator().manual_seed(11)
+    d = torch.randn(B, m, 400, generator=g) if dith else None
+    w = torch.randn(B, m, 30, generator=g)
+    (O.mfcc(x, d) * w).sum().backward()
+    mode = _lib.DITHER_TENSOR if dith else _lib.DITHER_OFF
+    got = eng.mfcc_bwd(x.detach().cuda(), w.cuda(), mode, None if d is None else d.cuda()).cpu()
+    e = relerr(got, x.grad)
+    print(f"mfcc adjoint B={B} N={N} dither={dith}: rel {e:.3e}")
+    assert e < 1e-4
+    # accumulate + scale
+    base = torch.ones(B, N).cuda()
+    acc = eng.mfcc_bwd(x.detach().cuda(), w.cuda(), mode, None if d is None else d.cuda(), grad=base, scale=0.5).cpu()
+    assert relerr(acc - 1.0, 0.5 * x.grad) < 2e-4
+
+
+@pytest.mark.parametrize("B,T", [(3, 200), (2, 300), (1, 64)])
+def test_embedding_forward_backward(eng, params, B, T):
+    g = torch.Generator().manual_seed(T)
+    feat = (torch.randn(B, T, 30, generator=g) * 3).requires_grad_(True)
+    emb_ref = O.process_emb(O.xvector(feat, params), params)
+    w = torch.randn(B, 200, generator=g)
+    (emb_ref * w).sum().backward()
+    f32 = torch.zeros(B, T, 32)
+    f32[:, :, :30] = feat.detach()
+    emb, ws = eng.embed_fwd(f32.cuda())
+    e = relerr(emb.cpu(), emb_ref)
+    print(f"embedding B={B} T={T}: rel {e:.3e}")
+    assert e < 1e-4
+    dfeat = eng.embed_bwd(w.cuda(), ws, B, T).cpu()
+    assert torch.all(dfeat[:, :, 30:] == 0)
+    e2 = relerr(dfeat[:, :, :30], feat.grad)
+    print(f"embedding backward: rel {e2:.3e}")
+    assert e2 < 1e-4
+
+
+def test_scoring_and_decisions(eng, params):
+    g = torch.Generator().manual_seed(3)
+    emb = (torch.randn(16, 200, generator=g)).requires_grad_(True)
+    ref = O.plda_scores(emb, params)
+    w = torch.randn(16, 10, generator=g)
+    (ref * w).sum().backward()
+    scores, dec = eng.score_fwd(emb.detach().cuda())
+    assert float((scores.cpu() - ref).abs().max()) < 2e-4 * float(ref.abs().max())
+    assert torch.equal(dec.cpu(), O.decide(ref.detach()))
+    demb = eng.score_bwd(emb.detach().cuda(), w.cuda()).cpu()
+    assert relerr(demb, emb.grad) < 1e-4
+    # threshold -> reject; custom enrolment set
+    thr = float(ref.max(1)[0].median())
+    _, dec2 = eng.score_fwd(emb.detach().cuda(), threshold=thr)
+    assert torch.equal(dec2.cpu(), O.decide(ref.detach(), thr))
+    en2 = torch.randn(3, 200, generator=g)
+    s3, d3 = eng.score_fwd(emb.detach().cuda(), enroll=en2.cuda())
+    ref3 = O.plda_scores(emb.detach(), params, en2)
+    assert float((s3.cpu() - ref3).abs().max()) < 2e-4 * float(ref3.abs().max())
+
+
+LOSS_CASES = [
+    ("Entropy", False, "CSI", None, False), ("Entropy", True, "CSI", None, False),
+    ("Margin", False, "CSI", None, False), ("Margin", True, "CSI", None, True),
+    ("Margin", False, "OSI", 1.5, False), ("Margin", True, "OSI", 1.5, True),
+]
+
+
+@pytest.mark.parametrize("name,targeted,task,thr,clip", LOSS_CASES)
+def test_losses(eng, name, targeted, task, thr, clip):
+    from speakerguard_b200.engine import make_loss_params
+    g = torch.Generator().manual_seed(9)
+    scores = (torch.randn(32, 10, generator=g) * 4).requires_grad_(True)
+    y = torch.randint(0, 10, (32,), generator=g)
+    y[::7] = -1
+    fn, _ = O.resolve_loss(name, targeted, 0.0, task, thr, clip)
+    ref = fn(scores, y)
+    ref.backward(torch.ones_like(ref))
+    lp = make_loss_params(name, targeted, task, 0.0, thr, clip)
+    loss, ds = eng.loss(scores.detach().cuda(), y.cuda(), lp)
+    assert float((loss.cpu() - ref.detach()).abs().max()) < 1e-5 * max(1.0, float(ref.abs().max()))
+    assert float((ds.cpu() - scores.grad).abs().max()) < 1e-5
+
+
+def test_loss_sv(eng):
+    from speakerguard_b200.engine import make_loss_params
+    g = torch.Generator().manual_seed(10)
+    scores = (torch.randn(12, 1, generator=g) * 4).requires_grad_(True)
+    y = torch.tensor([0, -1] * 6)
+    for targeted in (False, True):
+        scores.grad = None
+        ref = O.loss_margin(scores, y, targeted, 0.5, "SV", 0.7, clip_max=False)
+        ref.backward(torch.ones_like(ref))
+        loss, ds = eng.loss(scores.detach().cuda(), y.cuda(), make_loss_params("Margin", targeted, "SV", 0.5, 0.7, False))
+        assert float((loss.cpu() - ref.detach()).abs().max()) < 1e-5
+        assert float((ds.cpu() - scores.grad).abs().max()) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------
+def regen(g, tag, n_pass=None):
+    seed, B, N = int(g[f"{tag}.seed"]), int(g[f"{tag}.B"]), int(g[f"{tag}.N"])
+    torch.manual_seed(seed)
+    x = (torch.rand(B, 1, N) * 2 - 1) * 0.5
+    y = torch.randint(0, 10, (B,))
+    m = O.num_frames(N)
+    torch.manual_seed(seed + 1)
+    n = B if n_pass is None else n_pass * B
+    d = torch.stack([torch.randn((m, 400)) for _ in range(n)])
+    d = d if n_pass is None else d.view(n_pass, B, m, 400)
+    assert abs(float(d.double().abs().sum()) - float(g[f"{tag}.dither_cks"])) < 1e-6
+    return x[:, 0].contiguous(), y, d
+
+
+@pytest.mark.parametrize("tag", ["fwd2s", "fwd5s", "fwd1p1s"])
+def test_end_to_end_against_reference_golden(eng, xv, tag):
+    """wav -> scores / decisions / loss / input gradient vs tensors dumped from the reference."""
+    from speakerguard_b200 import _lib
+    from speakerguard_b200.engine import make_loss_params
+    x, y, d = regen(xv, tag)
+    xc, dc = x.cuda(), d.cuda()
+    raw = eng.mfcc_fwd(xc, _lib.DITHER_TENSOR, dc, ld=32)
+    assert relerr(raw[:, :, :30].cpu().flatten(0, 1), torch.tensor(xv[f"{tag}.raw"]).flatten(0, 1)) < 1e-4 or \
+        float((raw[:, :, :30].cpu() - torch.tensor(xv[f"{tag}.raw"])).abs().max()) < 1e-4 * float(np.abs(xv[f"{tag}.raw"]).max())
+    feat = eng.cmvn(raw, ld_out=32)
+    ref_feat = torch.tensor(xv[f"{tag}.feat"])
+    assert float((feat[:, :, :30].cpu() - ref_feat).abs().max()) < 1e-4 * float(ref_feat.abs().max())
+    emb, ws = eng.embed_fwd(feat)
+    assert relerr(emb.cpu(), torch.tensor(xv[f"{tag}.emb"])) < 1e-4
+    scores, dec = eng.score_fwd(emb)
+    ref_s = torch.tensor(xv[f"{tag}.scores"])
+    assert relerr(scores.cpu(), ref_s) < 1e-4
+    assert np.array_equal(dec.cpu().numpy(), xv[f"{tag}.dec"])
+    loss, ds = eng.loss(scores, y.cuda(), make_loss_params("Entropy"))
+    np.testing.assert_allclose(loss.cpu().numpy(), xv[f"{tag}.loss"], atol=2e-4, rtol=1e-4)
+    demb = eng.score_bwd(emb, ds)
+    B, T = feat.shape[0], feat.shape[1]
+    dfeat = eng.embed_bwd(demb, ws, B, T)
+    draw = eng.cmvn(dfeat, ld_out=32, backward=True)
+    grad = eng.mfcc_bwd(xc, draw, _lib.DITHER_TENSOR, dc).cpu()
+    e = relerr(grad, torch.tensor(xv[f"{tag}.grad"]))
+    print(f"[{tag}] input-gradient rel err vs reference {e:.3e}")
+    assert e < 1e-4
+
+
+@pytest.mark.parametrize("tag,kw", [
+    ("fgsm", dict(fgsm=True, epsilon=0.002)),
+    ("pgd3", dict(epsilon=0.002, step_size=0.0004, max_iter=3)),
+    ("pgd3t", dict(epsilon=0.002, step_size=0.0004, max_iter=3, targeted=True)),
+    ("cwinf3", dict(epsilon=0.002, step_size=0.0004, max_iter=3, loss_name="Margin")),
+])
+def test_fused_attack_loop_against_reference_golden(eng, xv, params, tag, kw):
+    """sg_pgd_run (whole loop on the device) vs the reference's adversarial examples."""
+    from speakerguard_b200 import _lib
+    from speakerguard_b200.engine import make_loss_params
+    x, y, d = regen(xv, tag, int(xv[f"{tag}.n_pass"]))
+    fgsm = kw.get("fgsm", False)
+    eps = kw["epsilon"]
+    lp = make_loss_params(kw.get("loss_name", "Entropy"), kw.get("targeted", False), "CSI", 0.0, None, False)
+    xa = x.cuda().clone()
+    dec, scores, hist = eng.pgd_run(xa, x.cuda(), y.cuda(), max_iter=1 if fgsm else kw["max_iter"],
+                                    epsilon=math.inf if fgsm else eps, step_size=eps if fgsm else kw["step_size"],
+                                    lp=lp, dither_mode=_lib.DITHER_TENSOR, dither=d.cuda(), want_loss_hist=True)
+    ref = torch.tensor(xv[f"{tag}.adv"])
+    mism = float((xa.cpu() != ref).float().mean())
+    print(f"[{tag}] iterate mismatch fraction vs reference {mism:.3e}")
+    # first step: bit-exact wherever the oracle gradient magnitude exceeds 1e-6
+    fn, gs = O.resolve_loss(kw.get("loss_name", "Entropy"), kw.get("targeted", False), 0.0, "CSI", None, False)
+    _, _, g0, _ = O.xv_loss_and_grad(x, y, params, fn, d[0])
+    if fgsm:
+        big = g0.abs() > 1e-6
+        assert torch.equal(xa.cpu()[big], ref[big])
+    assert mism < 2e-3
+    targeted = kw.get("targeted", False)
+    success = ((dec.cpu() == y) if targeted else (dec.cpu() != y)).tolist()
+    assert success == xv[f"{tag}.success"].tolist()
+    assert float((xa.cpu() - x).abs().max()) <= eps + 1e-7
+    assert hist.shape == ((1 if fgsm else kw["max_iter"]) + 1, x.shape[0])
+
+
+def test_fused_loop_equals_stagewise_loop(eng, params):
+    """Philox mode: the fused loop and a host-driven stage-by-stage loop give identical iterates."""
+    from speakerguard_b200 import _lib
+    from speakerguard_b200.engine import make_loss_params
+    B, N = 3, 32000
+    x = wave(B, N, seed=31).cuda()
+    y = torch.tensor([1, 5, 7]).cuda()
+    lp = make_loss_params("Entropy")
+    xa = x.clone()
+    eng.pgd_run(xa, x, y, max_iter=2, epsilon=0.002, step_size=0.0004, lp=lp, dither_mode=_lib.DITHER_PHILOX, seed=5)
+    xb = x.clone()
+    for it in range(2):
+        raw = eng.mfcc_fwd(xb, _lib.DITHER_PHILOX, None, seed=5, pass_=it, ld=32)
+        feat = eng.cmvn(raw, ld_out=32)
+        emb, ws = eng.embed_fwd(feat)
+        scores, _ = eng.score_fwd(emb)
+        _, ds = eng.loss(scores, y, lp)
+        dfeat = eng.embed_bwd(eng.score_bwd(emb, ds), ws, B, feat.shape[1])
+        grad = eng.mfcc_bwd(xb, eng.cmvn(dfeat, ld_out=32, backward=True), _lib.DITHER_PHILOX, None, seed=5, pass_=it)
+        eng.step_linf(xb, x, grad, 0.0004, 1.0, 0.002)
+    assert torch.equal(xa, xb)
+
+
+def test_eot_gradient_averaging(eng):
+    """eot_size > 1: the fused loop averages E gradient samples (different dither) before the sign."""
+    from speakerguard_b200 import _lib
+    from speakerguard_b200.engine import make_loss_params
+    B, N, E = 2, 32000, 3
+    x = wave(B, N, seed=41).cuda()
+    y = torch.tensor([2, 4]).cuda()
+    lp = make_loss_params("Entropy")
+    xa = x.clone()
+    eng.pgd_run(xa, x, y, max_iter=1, epsilon=0.002, step_size=0.0004, lp=lp, dither_mode=_lib.DITHER_PHILOX, seed=9,
+                eot_size=E)
+    gsum = torch.zeros_like(x)
+    for e in range(E):
+        raw = eng.mfcc_fwd(x, _lib.DITHER_PHILOX, None, seed=9, pass_=e, ld=32)
+        feat = eng.cmvn(raw, ld_out=32)
+        emb, ws = eng.embed_fwd(feat)
+        scores, _ = eng.score_fwd(emb)
+        _, ds = eng.loss(scores, y, lp)
+        dfeat = eng.embed_bwd(eng.score_bwd(emb, ds), ws, B, feat.shape[1])
+        eng.mfcc_bwd(x, eng.cmvn(dfeat, ld_out=32, backward=True), _lib.DITHER_PHILOX, None, seed=9, pass_=e, grad=gsum,
+                     scale=1.0 / E)
+    xb = x.clone()
+    eng.step_linf(xb, x, gsum, 0.0004, 1.0, 0.002)
+    assert torch.equal(xa, xb)
+
+
+def test_error_paths(eng):
+    from speakerguard_b200 import _lib
+    with pytest.raises(_lib.SgError):
+        eng.mfcc_fwd(torch.zeros(1, 100).cuda())            # shorter than one window
+    with pytest.raises(_lib.SgError):
+        eng.mfcc_fwd(torch.zeros(1, 1000).cuda(), _lib.DITHER_TENSOR, None)
+    with pytest.raises(_lib.SgError):
+        eng.mfcc_fwd(torch.zeros(1, 1000))                   # CPU tensor: no fallback
