@@ -217,21 +217,32 @@ def cmvn_loop(feat: torch.Tensor) -> torch.Tensor:
 # ----------------------------------------------------------------------------------------------
 # x-vector TDNN + head (xvecTDNN.py:46-64, iv_plda.py:411-443, plda.py:73-97,140-190)
 # ----------------------------------------------------------------------------------------------
-def tdnn_layers(feat: torch.Tensor, p: Dict[str, torch.Tensor]) -> List[torch.Tensor]:
-    """feat [B,T,30] -> list of the five post-BN activations [B,C,T_l]."""
+def tdnn_layers(feat: torch.Tensor, p: Dict[str, torch.Tensor], flips=None, preacts: Optional[list] = None
+                ) -> List[torch.Tensor]:
+    """feat [B,T,30] -> list of the five post-BN activations [B,C,T_l].
+
+    ``flips`` (test aid): per-layer bool tensors; where True the ReLU gate of that unit is inverted
+    (the gradient of the network is discontinuous where a pre-activation is ~0, and two fp32
+    summation orders can land on different sides; see tests/kink.py).  ``preacts`` collects the
+    pre-activations."""
     x = feat.transpose(1, 2)
     outs = []
     for i, (_, _, _, d) in enumerate(TDNN_SPEC, 1):
         a = F.conv1d(x, p[f"tdnn{i}.weight"].to(x.dtype), p[f"tdnn{i}.bias"].to(x.dtype), dilation=d)
-        r = F.relu(a)                                           # ReLU precedes BN (xvecTDNN.py:49)
+        if preacts is not None:
+            preacts.append(a.detach())
+        if flips is not None and flips[i - 1] is not None:
+            r = a * ((a > 0) ^ flips[i - 1]).to(a.dtype)
+        else:
+            r = F.relu(a)                                       # ReLU precedes BN (xvecTDNN.py:49)
         x = (r - p[f"bn{i}.mean"].to(x.dtype).view(1, -1, 1)) / torch.sqrt(
             p[f"bn{i}.var"].to(x.dtype).view(1, -1, 1) + BN_EPS)
         outs.append(x)
     return outs
 
 
-def xvector(feat: torch.Tensor, p: Dict[str, torch.Tensor]) -> torch.Tensor:
-    x = tdnn_layers(feat, p)[-1]
+def xvector(feat: torch.Tensor, p: Dict[str, torch.Tensor], flips=None, preacts=None) -> torch.Tensor:
+    x = tdnn_layers(feat, p, flips, preacts)[-1]
     stats = torch.cat((x.mean(dim=2), x.std(dim=2)), dim=1)     # xvecTDNN.py:62 (unbiased std)
     return stats @ p["fc1.weight"].to(x.dtype).T + p["fc1.bias"].to(x.dtype)
 
@@ -274,13 +285,13 @@ def decide(scores: torch.Tensor, threshold: float = -math.inf) -> torch.Tensor:
 
 
 def xv_forward(x: torch.Tensor, p: Dict[str, torch.Tensor], dither: Optional[torch.Tensor] = None,
-               return_all: bool = False):
+               return_all: bool = False, flips=None, preacts=None):
     """x [B,N] (or [B,1,N]) -> scores [B,S] (iv_plda.py:155-169 with flag 0)."""
     if x.dim() == 3:
         x = x[:, 0]
     raw = mfcc(x, dither)
     feat = cmvn(raw)
-    emb = process_emb(xvector(feat, p), p)
+    emb = process_emb(xvector(feat, p, flips, preacts), p)
     scores = plda_scores(emb, p)
     if return_all:
         return {"raw": raw, "feat": feat, "emb": emb, "scores": scores}
@@ -347,10 +358,10 @@ def resolve_loss(loss_name="Entropy", targeted=False, confidence=0.0, task="CSI"
 # ----------------------------------------------------------------------------------------------
 # FGSM / PGD (attack/FGSM.py:38-98, attack/PGD.py:40-79, adaptive_attack/EOT.py:16-54, EOT_size 1)
 # ----------------------------------------------------------------------------------------------
-def xv_loss_and_grad(x: torch.Tensor, y: torch.Tensor, p, loss_fn, dither=None):
+def xv_loss_and_grad(x: torch.Tensor, y: torch.Tensor, p, loss_fn, dither=None, flips=None, preacts=None):
     """One EOT pass with E=1: scores, loss, d(sum loss)/dx, decisions."""
     xr = x.detach().clone().requires_grad_(True)
-    scores = xv_forward(xr, p, dither)
+    scores = xv_forward(xr, p, dither, flips=flips, preacts=preacts)
     loss = loss_fn(scores, y)
     loss.backward(torch.ones_like(loss))                          # EOT.py:35
     thr = p.get("threshold", -math.inf)

@@ -240,3 +240,17 @@ class Engine:
         check(self.lib.sg_pgd_run(self._h, _ptr(x_adv), _ptr(x0), _ptr(y), _ptr(d), B, N, C.byref(pp), _ptr(ws), _ptr(dec),
                                   _ptr(scores), _ptr(hist), self.stream), "sg_pgd_run")
         return dec, scores, hist
+
+
+_DEFAULT_ENGINES: Dict[int, "Engine"] = {}
+
+
+def default_engine(device) -> "Engine":
+    """A weight-less engine per device for the stateless entry points (losses, sign step)."""
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise _lib.SgError(f"speakerguard_b200 ops need CUDA tensors (got a tensor on '{dev}'); no CPU fallback")
+    idx = torch.cuda.current_device() if dev.index is None else dev.index
+    if idx not in _DEFAULT_ENGINES:
+        _DEFAULT_ENGINES[idx] = Engine(torch.device("cuda", idx))
+    return _DEFAULT_ENGINES[idx]

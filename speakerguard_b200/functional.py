@@ -1,0 +1,86 @@
+"""torch.autograd bridges over the libsgb200 stage entry points.
+
+They let unchanged host code (``loss.backward()`` in an EOT wrapper, ``torch.optim.Adam`` in CW2,
+feature-level defenses sitting between the stages) differentiate through the CUDA kernels.  Each
+Function's backward calls the hand-written adjoint kernel of its stage; nothing is recomputed or
+approximated in PyTorch.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+from .engine import FLD, Engine
+
+
+class MfccFn(torch.autograd.Function):
+    """x [B,N] -> raw MFCC [B,m,30]  (sg_mfcc_fwd / sg_mfcc_bwd)."""
+
+    @staticmethod
+    def forward(ctx, x, eng: Engine, mode: int, dither: Optional[torch.Tensor], seed: int, pass_: int):
+        x = x.contiguous()
+        ctx.eng, ctx.mode, ctx.dither, ctx.seed, ctx.pass_ = eng, mode, dither, seed, pass_
+        ctx.save_for_backward(x)
+        return eng.mfcc_fwd(x, mode, dither, seed, pass_, ld=30)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        grad = ctx.eng.mfcc_bwd(x, g.contiguous(), ctx.mode, ctx.dither, ctx.seed, ctx.pass_)
+        return grad, None, None, None, None, None
+
+
+class CmvnFn(torch.autograd.Function):
+    """[B,T,30] -> sliding-window mean normalised [B,T,30]  (sg_cmvn_fwd / sg_cmvn_bwd)."""
+
+    @staticmethod
+    def forward(ctx, feat, eng: Engine):
+        ctx.eng = eng
+        return eng.cmvn(feat.contiguous(), ld_out=30)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ctx.eng.cmvn(g.contiguous(), ld_out=30, backward=True), None
+
+
+class EmbedFn(torch.autograd.Function):
+    """CMVN features [B,T,30] -> PLDA-space embedding [B,L]  (sg_xv_embed_fwd / _bwd)."""
+
+    @staticmethod
+    def forward(ctx, feat, eng: Engine):
+        B, T, F = feat.shape
+        f32 = torch.zeros(B, T, FLD, device=feat.device, dtype=torch.float32)
+        f32[:, :, :F] = feat
+        emb, ws = eng.embed_fwd(f32)
+        ctx.eng, ctx.ws, ctx.shape = eng, ws, (B, T, F)
+        return emb
+
+    @staticmethod
+    def backward(ctx, g):
+        B, T, F = ctx.shape
+        dfeat = ctx.eng.embed_bwd(g.contiguous(), ctx.ws, B, T)
+        return dfeat[:, :, :F].contiguous(), None
+
+
+class ScoreFn(torch.autograd.Function):
+    """embedding [B,L] x enrolled [S,L] -> PLDA LLR scores [B,S]  (sg_plda_score_fwd / _bwd)."""
+
+    @staticmethod
+    def forward(ctx, emb, enroll, eng: Engine):
+        emb = emb.contiguous()
+        en = None if enroll is None else enroll.detach().contiguous()
+        scores, _ = eng.score_fwd(emb, en, want_decisions=False)
+        ctx.eng, ctx.en = eng, en
+        ctx.save_for_backward(emb)
+        return scores
+
+    @staticmethod
+    def backward(ctx, g):
+        (emb,) = ctx.saved_tensors
+        return ctx.eng.score_bwd(emb, g.contiguous(), ctx.en), None, None
+
+
+DITHER_MODE = {"off": _lib.DITHER_OFF, "philox": _lib.DITHER_PHILOX, "torch": _lib.DITHER_TENSOR,
+               "tensor": _lib.DITHER_TENSOR}
