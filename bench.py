@@ -1,0 +1,277 @@
+#!/usr/bin/env python
+"""Headline benchmark: PGD utterance-iterations/s against xv_plda (BASELINE.json configs[1]).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision ...]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one full PGD-100 attack (100 gradient passes + the final evaluation pass,
+attack/PGD.py semantics) on one batch of 1024 synthetic 3 s utterances per GPU (weak scaling:
+utterances shard independently, no data-path collective).  Prints ONE JSON line on rank 0.
+
+  value        utterance-iterations/s, whole job, inputs resident in HBM, device-timed (CUDA
+               events, max over ranks), through the C-ABI (sg_pgd_run).
+  e2e          same metric through the public drop-in API ``PGD(model).attack(x, y)`` with HOST
+               buffers: pinned H2D of x/y and D2H of the adversarial batch + success inside the
+               timed region.
+  roofline     the TDNN contraction kernel (forward + dgrad launches of one profiled step):
+               algorithmic FLOPs / CUDA-event time vs the measured tensor peak.
+  cpu_baseline the oracle port of the reference path on the host cores, bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOAD = "PGD-100 Linf eps=0.002 step=0.0004 CE-untargeted vs xv_plda CSI-E (random-init TDNN+PLDA, L=200, S=10), " \
+           "synthetic 3 s 16 kHz utterances, batch 1024 per GPU"
+TDNN = [(30, 512, 5, 1), (512, 512, 5, 2), (512, 512, 7, 3), (512, 512, 1, 1), (512, 1500, 1, 1)]
+
+
+def tdnn_flops_per_utt(m: int) -> float:
+    """Algorithmic FLOPs of the TDNN forward + dgrad for one utterance-iteration:
+    2 * sum_l 2*C_in*k*C_out*T_l (valid frames only, no wgrad, unpadded channels)."""
+    t, tot = m, 0.0
+    for ci, co, k, d in TDNN:
+        t -= (k - 1) * d
+        tot += 2.0 * ci * k * co * t
+    return 2.0 * tot
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "power_w_max": max(pw) if pw else None, "samples": len(self.rows)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+def cpu_reference_throughput(p, N, budget_s=12.0, batch=8, iters=2):
+    """utt-iter/s of the oracle port of the reference path (PGD, CE, B=8) on the host cores."""
+    from oracle import sg_oracle as O
+    from speakerguard_b200.synthetic import synthetic_batch
+    torch.set_num_threads(os.cpu_count() or 1)
+    x, y = synthetic_batch(batch, N, p["enroll"].shape[0])
+    m = O.num_frames(N)
+    done, t0 = 0, time.perf_counter()
+    while True:
+        d = torch.randn(iters + 1, batch, m, 400)
+        O.pgd_attack(x[:, 0], y, p, epsilon=0.002, step_size=0.0004, max_iter=iters, dither=d)
+        done += iters
+        el = time.perf_counter() - t0
+        if el >= budget_s:
+            break
+    return batch * done / el, f"oracle PGD-{done} (incl. {done // iters} evaluation passes), B={batch}, {N / 16000:g} s, " \
+                              f"{el:.1f} s of CPU work", torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from speakerguard_b200.synthetic import make_xv_params
+    p = make_xv_params(0)
+    N = int(args.seconds * 16000)
+    for _ in range(args.warmup):
+        cpu_reference_throughput(p, N, budget_s=0.0, iters=1)
+    t0 = time.perf_counter()
+    vals = []
+    for _ in range(args.steps):
+        v, sample, cores = cpu_reference_throughput(p, N, budget_s=args.ref_budget / max(args.steps, 1), iters=2)
+        vals.append(v)
+    el = time.perf_counter() - t0
+    value = sum(vals) / len(vals)
+    out = {"impl": "reference", "metric": "PGD utterance-iterations/s vs xv_plda", "value": value, "unit": "utt-iter/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * el / args.steps,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": WORKLOAD, "note": "reference arm = CPU path of the reference (oracle port, torch-CPU fp32, "
+                      "all host threads) on a bounded sample of the same workload: B=8 per step"},
+           "cpu_baseline": {"value": value, "unit": "utt-iter/s", "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": "utt-iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("SGB200_PRECISION", "fp32"), choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--batch", type=int, default=1024, help="utterances per GPU")
+    ap.add_argument("--seconds", type=float, default=3.0)
+    ap.add_argument("--iters", type=int, default=100, help="PGD iterations per attack")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--ref-budget", type=float, default=30.0, help="CPU seconds for --impl reference")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    from speakerguard_b200 import _lib, dist
+    from speakerguard_b200.attack.PGD import PGD
+    from speakerguard_b200.engine import make_loss_params
+    from speakerguard_b200.model.xv_plda import xv_plda
+    from speakerguard_b200.synthetic import make_xv_params, state_dict_of, synthetic_batch, write_xv_model_files
+
+    rank, world, local = dist.init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: speakerguard_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    B, N, iters = args.batch, int(args.seconds * 16000), args.iters
+    p = make_xv_params(0)
+    tmp = tempfile.mkdtemp(prefix=f"sgb200_bench_{rank}_")
+    files = write_xv_model_files(p, tmp)
+    model = xv_plda(state_dict_of(p), files["plda.txt"], files["mean.vec"], files["transform.txt"],
+                    model_file=files["speaker_model"], device=dev, precision=args.precision, dither="philox", seed=rank)
+    eng = model.engine
+    m = eng.num_frames(N)
+    x_host, y_host = synthetic_batch(B, N, 10, seed=1234 + rank)
+    x_host, y_host = x_host.pin_memory(), y_host.pin_memory()
+    x_dev, y_dev = x_host.to(dev), y_host.to(dev)
+    lp = make_loss_params("Entropy", False, "CSI")
+    ws = eng.pgd_ws(B, N)
+    xa = torch.empty(B, N, device=dev)
+
+    def step(seed):
+        xa.copy_(x_dev[:, 0])
+        return eng.pgd_run(xa, x_dev[:, 0], y_dev, max_iter=iters, epsilon=0.002, step_size=0.0004, lp=lp,
+                           dither_mode=_lib.DITHER_PHILOX, seed=seed, ws=ws)
+
+    for w in range(args.warmup):
+        step(1000 + w)
+    torch.cuda.synchronize()
+    dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    eng.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for k in range(args.steps):
+        dec, scores, _ = step(2000 + k)
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    launches = eng.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = dist.max_over_ranks(e0.elapsed_time(e1), dev)
+    ms_step = ms_total / args.steps
+    value = world * B * iters / (ms_step / 1000.0)
+
+    # ---- end-to-end through the public API, host buffers -------------------------------------------
+    attacker = PGD(model, task="CSI", epsilon=0.002, step_size=0.0004, max_iter=iters, batch_size=B, verbose=0)
+    adv_host = torch.empty(B, 1, N).pin_memory()
+
+    def e2e_step():
+        xd = x_host.to(dev, non_blocking=True)
+        yd = y_host.to(dev, non_blocking=True)
+        adv, success = attacker.attack(xd, yd)
+        adv_host.copy_(adv, non_blocking=True)
+        torch.cuda.synchronize()
+        return adv, success
+
+    e2e_step()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        adv, success = e2e_step()
+    e2e_s = dist.max_over_ranks(time.perf_counter() - t0, dev) / args.e2e_steps
+    e2e_value = world * B * iters / e2e_s
+    metrics = dist.reduce_metrics(dist.attack_metrics(x_dev, adv, success))     # NCCL: metric scalars only
+
+    # ---- per-kernel device time of one profiled step, roofline of the TDNN contraction -------------
+    eng.profile(True)
+    step(3000)
+    prof = eng.profile_read()
+    eng.profile(False)
+    tot_prof = sum(v[0] for v in prof.values())
+    tdnn_ms = prof["tdnn_fwd"][0] + prof["tdnn_dgrad"][0]
+    tdnn_launches = prof["tdnn_fwd"][1] + prof["tdnn_dgrad"][1]
+    passes = iters + 1
+    flops = tdnn_flops_per_utt(m) * B * iters + 0.5 * tdnn_flops_per_utt(m) * B     # + forward of the evaluation pass
+    achieved = flops / (tdnn_ms / 1000.0) / 1e12
+    peaks, peak_src = measured_peaks()
+    if args.precision == "bf16":
+        peak, peak_note = peaks["bf16_tflops_sustained"], f"bf16 sustained, {peak_src}"
+    elif args.precision == "tf32":
+        peak, peak_note = peaks["bf16_tflops_sustained"] / 2.0, f"tf32 = half of bf16 sustained, {peak_src}"
+    else:
+        peak, peak_note = peaks["bf16_tflops_sustained"] / 2.0, \
+            f"fp32 FFMA parity mode is not on the tensor pipe; quoted against the tf32 tensor peak (half of bf16 sustained, {peak_src})"
+
+    if rank != 0:
+        return
+    out = {
+        "metric": "PGD utterance-iterations/s vs xv_plda", "value": value, "unit": "utt-iter/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[args.precision], "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "samples": N, "frames": m, "pgd_iters": iters,
+                   "passes_per_step": passes, "dither": "philox (in-kernel N(0,1), fresh per pass)",
+                   "cache": "inputs larger than L2 (activations ~7.6 GB per pass)", "precision": args.precision},
+        "clocks": clocks, "gpu_launches": launches,
+        "e2e": {"value": e2e_value, "unit": "utt-iter/s", "h2d_bytes_per_step": B * N * 4 + B * 8,
+                "d2h_bytes_per_step": B * N * 4 + B * 8, "ms_per_step": e2e_s * 1000.0,
+                "api": "speakerguard_b200.attack.PGD(model).attack(x, y) with pinned host buffers"},
+        "roofline": {"bound": "tensor", "kernel": "TDNN conv-as-GEMM (forward + dgrad launches)", "achieved": achieved,
+                     "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_note,
+                     "launches": tdnn_launches, "avg_launch_ms": tdnn_ms / max(tdnn_launches, 1),
+                     "algorithmic_flops_per_utt_iter": tdnn_flops_per_utt(m),
+                     "share_of_step": tdnn_ms / tot_prof if tot_prof else None},
+        "kernel_ms_per_step": {k: round(v[0], 3) for k, v in prof.items()},
+        "attack_metrics": metrics,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        v, sample, cores = cpu_reference_throughput(p, N)
+        out["cpu_baseline"] = {"value": v, "unit": "utt-iter/s", "cores": cores, "kind": "port", "sample": sample}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

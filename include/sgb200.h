@@ -158,6 +158,27 @@ int sg_xv_forward(sg_handle* h, const float* x, int B, int N, int dither_mode, c
                   uint64_t seed, uint64_t pass, float decision_threshold, void* ws, float* scores,
                   int64_t* decisions, float* emb, sg_stream stream);
 
+/* ---- test hook: one conv-as-GEMM launch on either arithmetic path -----------------------------
+ * out[p,n] = epi(sum_{tap,c} A[p + tap*tap_step, c] * W[tap*cin + c, n]); W is [taps*cin, N]
+ * (FFMA path), Wk its K-major copy [N, taps*cin] (tcgen05 path); epilogue 0 bias, 1 bias+ReLU,
+ * 2 ReLU-mask (mask > 0 and row %% T < t_valid), 3 none.  This is the kernel behind the TDNN
+ * layers (xvecTDNN.py:16-53) and their dgrad. */
+int sg_debug_conv(sg_handle* h, int precision, const float* A, int lda, const float* W, const float* Wk,
+                  const float* bias, float* out, int ldo, int rows, int N, int cin, int taps,
+                  int tap_step, int epilogue, const float* mask, int ldmask, int T, int t_valid,
+                  sg_stream stream);
+
+/* ---- device-side timing ------------------------------------------------------------------------
+ * With profiling enabled every kernel launch is bracketed by CUDA events on its stream and
+ * attributed to a category; sg_profile_read() synchronises on the recorded events and returns the
+ * summed duration and the launch count since sg_profile_enable() was last called.  bench.py
+ * uses this for the per-kernel share of a step and for the roofline of the dominant kernel. */
+enum { SG_PROF_MFCC_FWD = 0, SG_PROF_MFCC_BWD, SG_PROF_CMVN, SG_PROF_TDNN_FWD, SG_PROF_TDNN_BWD,
+       SG_PROF_POOL, SG_PROF_HEAD_GEMM, SG_PROF_HEAD, SG_PROF_LOSS, SG_PROF_STEP, SG_PROF_COUNT };
+int sg_profile_enable(sg_handle* h, int enable);
+int sg_profile_read(sg_handle* h, int category, double* total_ms, long long* launches);
+const char* sg_profile_name(int category);
+
 /* kernel-launch counter (bench.py's gpu_launches): kernels launched by this library since the
  * last sg_reset_launch_count() on the calling thread's handle. */
 long long sg_launch_count(const sg_handle* h);

@@ -16,6 +16,7 @@ SG_OK, SG_EINVAL, SG_ECUDA, SG_ESTATE, SG_EUNSUPPORTED = 0, -1, -2, -3, -4
 PREC_FP32, PREC_TF32, PREC_BF16 = 0, 1, 2
 DITHER_OFF, DITHER_TENSOR, DITHER_PHILOX = 0, 1, 2
 LOSS_CE, LOSS_MARGIN = 0, 1
+PROF_COUNT = 10
 TASK_CSI, TASK_SV, TASK_OSI = 0, 1, 2
 TASKS = {"CSI": TASK_CSI, "SV": TASK_SV, "OSI": TASK_OSI}
 PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "bf16": PREC_BF16}
@@ -70,6 +71,11 @@ PROTOTYPES = {
     "sg_pgd_run": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.POINTER(PgdParams), _vp, _vp, _vp, _vp, _vp]),
     "sg_xv_forward": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, C.c_uint64, C.c_uint64, C.c_float, _vp, _vp,
                                 _vp, _vp, _vp]),
+    "sg_debug_conv": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                C.c_int, C.c_int, _vp, C.c_int, C.c_int, C.c_int, _vp]),
+    "sg_profile_enable": (C.c_int, [_vp, C.c_int]),
+    "sg_profile_read": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
+    "sg_profile_name": (C.c_char_p, [C.c_int]),
     "sg_launch_count": (C.c_longlong, [_vp]),
     "sg_reset_launch_count": (None, [_vp]),
 }

@@ -32,7 +32,34 @@ static const int kCinP[5] = {32, 512, 512, 512, 512};
 static const int kCout[5] = {512, 512, 512, 512, 1500};
 static const int kCoutP[5] = {512, 512, 512, 512, SG_C5P};
 
+// per-category device timing (CUDA events on the launching stream); off by default
+static const char* kProfNames[SG_PROF_COUNT] = {
+    "mfcc_fwd", "mfcc_bwd", "cmvn", "tdnn_fwd", "tdnn_dgrad", "pool", "head_gemm", "head", "loss", "step"};
+struct SgProf {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;      // pairs (start, stop)
+  std::vector<int> cat;             // category of pair i
+  size_t used = 0;                  // pairs recorded since the last reset
+  cudaEvent_t* begin(int c, cudaStream_t st) {
+    if (!on) return nullptr;
+    if (used == cat.size()) {
+      cudaEvent_t a, b;
+      if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return nullptr;
+      ev.push_back(a); ev.push_back(b); cat.push_back(c);
+    }
+    cat[used] = c;
+    cudaEventRecord(ev[2 * used], st);
+    return &ev[2 * used + 1];
+  }
+  void end(cudaEvent_t* stop, cudaStream_t st) {
+    if (!stop) return;
+    cudaEventRecord(*stop, st);
+    ++used;
+  }
+};
+
 struct sg_handle {
+  SgProf prof;
   int device = 0;
   int precision = SG_PREC_FP32;
   long long launches = 0;
@@ -42,6 +69,8 @@ struct sg_handle {
   // packed TDNN weights
   float* Wf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // [taps*cinP, coutP]
   float* Wb[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // [taps*coutP, cinP]
+  float* Wfk[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // K-major copies for the tensor-core path: [coutP, taps*cinP]
+  float* Wbk[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [cinP, taps*coutP]
   float* bias[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; // [coutP] (BN of the previous layer folded)
   float* bn5_mean = nullptr; float* bn5_istd = nullptr;           // [C5P]
   float* Wfc = nullptr; float* Wfc_b = nullptr; float* bfc = nullptr;     // fc1: [3072,512], [512,3072], [512]
@@ -91,6 +120,7 @@ extern "C" int sg_create(sg_handle** out, int device) {
 extern "C" void sg_destroy(sg_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  for (cudaEvent_t e : h->prof.ev) cudaEventDestroy(e);
   for (void* p : h->allocs) cudaFree(p);
   delete h;
 }
@@ -102,6 +132,30 @@ extern "C" int sg_set_precision(sg_handle* h, int precision) {
   return SG_OK;
 }
 extern "C" int sg_get_precision(const sg_handle* h) { return h ? h->precision : SG_EINVAL; }
+extern "C" int sg_profile_enable(sg_handle* h, int enable) {
+  if (!h) { sg_set_error("null handle"); return SG_EINVAL; }
+  h->prof.on = enable != 0;
+  h->prof.used = 0;
+  return SG_OK;
+}
+extern "C" int sg_profile_read(sg_handle* h, int category, double* total_ms, long long* launches) {
+  if (!h || category < 0 || category >= SG_PROF_COUNT || !total_ms || !launches) { sg_set_error("sg_profile_read: bad argument"); return SG_EINVAL; }
+  double tot = 0.0; long long n = 0;
+  for (size_t i = 0; i < h->prof.used; ++i) {
+    if (h->prof.cat[i] != category) continue;
+    SG_CUDA_CHECK(cudaEventSynchronize(h->prof.ev[2 * i + 1]));
+    float ms = 0.f;
+    SG_CUDA_CHECK(cudaEventElapsedTime(&ms, h->prof.ev[2 * i], h->prof.ev[2 * i + 1]));
+    tot += ms; ++n;
+  }
+  *total_ms = tot; *launches = n;
+  return SG_OK;
+}
+extern "C" const char* sg_profile_name(int category) {
+  return (category >= 0 && category < SG_PROF_COUNT) ? kProfNames[category] : "";
+}
+#define PROF(h, c, st, call) do { cudaEvent_t* _pe = (h)->prof.begin((c), (st)); int _pr = (call); (h)->prof.end(_pe, (st)); if (_pr != SG_OK) return _pr; } while (0)
+
 extern "C" long long sg_launch_count(const sg_handle* h) { return h ? h->launches : 0; }
 extern "C" void sg_reset_launch_count(sg_handle* h) { if (h) h->launches = 0; }
 
@@ -125,6 +179,7 @@ extern "C" int sg_load_xv(sg_handle* h, const sg_xv_weights* w) {
   for (int l = 0; l < 5; ++l) {
     const int K = kTaps[l], ci = kCin[l], cip = kCinP[l], co = kCout[l], cop = kCoutP[l];
     std::vector<float> Wf((size_t)K * cip * cop, 0.f), Wb((size_t)K * cop * cip, 0.f), bias(cop, 0.f);
+    std::vector<float> Wfk((size_t)cop * K * cip, 0.f), Wbk((size_t)cip * K * cop, 0.f);
     std::vector<double> istd(ci, 1.0), mu(ci, 0.0);
     if (l > 0)
       for (int c = 0; c < ci; ++c) {
@@ -139,11 +194,15 @@ extern "C" int sg_load_xv(sg_handle* h, const sg_xv_weights* w) {
           bacc -= wv * mu[c];
           Wf[((size_t)k * cip + c) * cop + o] = (float)wv;
           Wb[((size_t)k * cop + o) * cip + c] = (float)wv;
+          Wfk[(size_t)o * (K * cip) + (size_t)k * cip + c] = (float)wv;
+          Wbk[(size_t)c * (K * cop) + (size_t)k * cop + o] = (float)wv;
         }
       bias[o] = (float)bacc;
     }
     SG_TRY(dev_upload(h, &h->Wf[l], Wf));
     SG_TRY(dev_upload(h, &h->Wb[l], Wb));
+    SG_TRY(dev_upload(h, &h->Wfk[l], Wfk));
+    SG_TRY(dev_upload(h, &h->Wbk[l], Wbk));
     SG_TRY(dev_upload(h, &h->bias[l], bias));
   }
   {
@@ -290,7 +349,8 @@ extern "C" int sg_mfcc_fwd(sg_handle* h, const float* x, int B, int N, int dithe
   SG_TRY(check_handle(h, false)); SG_TRY(check_wave(B, N)); SG_TRY(check_dither(dither_mode, dither));
   if (!x || !raw || ld < SG_NCEP || ld > 32) { sg_set_error("sg_mfcc_fwd: bad pointer or ld (%d not in [30,32])", ld); return SG_EINVAL; }
   h->launches += 1;
-  return sg_feat_fwd_launch(h->d_tables, x, B, N, sg_num_frames(N), dither_mode, dither, seed, pass, raw, ld, (cudaStream_t)stream);
+  PROF(h, SG_PROF_MFCC_FWD, (cudaStream_t)stream, sg_feat_fwd_launch(h->d_tables, x, B, N, sg_num_frames(N), dither_mode, dither, seed, pass, raw, ld, (cudaStream_t)stream));
+  return SG_OK;
 }
 
 extern "C" int sg_mfcc_bwd(sg_handle* h, const float* x, int B, int N, int dither_mode, const float* dither,
@@ -299,8 +359,9 @@ extern "C" int sg_mfcc_bwd(sg_handle* h, const float* x, int B, int N, int dithe
   SG_TRY(check_handle(h, false)); SG_TRY(check_wave(B, N)); SG_TRY(check_dither(dither_mode, dither));
   if (!x || !draw || !grad || ld < SG_NCEP || ld > 32) { sg_set_error("sg_mfcc_bwd: bad pointer or ld (%d)", ld); return SG_EINVAL; }
   h->launches += 1;
-  return sg_feat_bwd_launch(h->d_tables, x, B, N, sg_num_frames(N), dither_mode, dither, seed, pass, draw, ld, grad,
-                            scale, accumulate, (cudaStream_t)stream);
+  PROF(h, SG_PROF_MFCC_BWD, (cudaStream_t)stream, sg_feat_bwd_launch(h->d_tables, x, B, N, sg_num_frames(N), dither_mode, dither, seed, pass, draw, ld, grad,
+                            scale, accumulate, (cudaStream_t)stream));
+  return SG_OK;
 }
 
 extern "C" int sg_dither_fill(sg_handle* h, int B, int N, uint64_t seed, uint64_t pass, float* out, sg_stream stream) {
@@ -314,20 +375,23 @@ extern "C" int sg_cmvn_fwd(sg_handle* h, const float* raw, int ld_in, float* out
   SG_TRY(check_handle(h, false));
   if (!raw || !out || B < 1 || T < 1 || ld_in < SG_NCEP || ld_out < SG_NCEP || ld_in > 32 || ld_out > 32) { sg_set_error("sg_cmvn_fwd: bad argument"); return SG_EINVAL; }
   h->launches += 1;
-  return sg_cmvn_launch(raw, ld_in, out, ld_out, B, T, 0, (cudaStream_t)stream);
+  PROF(h, SG_PROF_CMVN, (cudaStream_t)stream, sg_cmvn_launch(raw, ld_in, out, ld_out, B, T, 0, (cudaStream_t)stream));
+  return SG_OK;
 }
 extern "C" int sg_cmvn_bwd(sg_handle* h, const float* dout, int ld_in, float* draw, int ld_out, int B, int T, sg_stream stream) {
   SG_TRY(check_handle(h, false));
   if (!dout || !draw || B < 1 || T < 1 || ld_in < SG_NCEP || ld_out < SG_NCEP || ld_in > 32 || ld_out > 32) { sg_set_error("sg_cmvn_bwd: bad argument"); return SG_EINVAL; }
   h->launches += 1;
-  return sg_cmvn_launch(dout, ld_in, draw, ld_out, B, T, 1, (cudaStream_t)stream);
+  PROF(h, SG_PROF_CMVN, (cudaStream_t)stream, sg_cmvn_launch(dout, ld_in, draw, ld_out, B, T, 1, (cudaStream_t)stream));
+  return SG_OK;
 }
 
 // ---- TDNN -------------------------------------------------------------------------------------
-static int run_conv(sg_handle* h, const SgConvArgs& a, bool tensor_ok, cudaStream_t st) {
+static int run_conv(sg_handle* h, const SgConvArgs& a, bool tensor_ok, int cat, cudaStream_t st) {
   h->launches += 1;
-  if (h->precision != SG_PREC_FP32 && tensor_ok) return sg_conv_tc(a, h->precision, st);
-  return sg_conv_simt(a, st);
+  if (h->precision != SG_PREC_FP32 && tensor_ok) { PROF(h, cat, st, sg_conv_tc(a, h->precision, st)); return SG_OK; }
+  PROF(h, cat, st, sg_conv_simt(a, st));
+  return SG_OK;
 }
 
 static void tdnn_valid(int T, int tv[5]) {
@@ -345,26 +409,27 @@ static int embed_fwd(sg_handle* h, const float* feat, int B, int T, const XvWs& 
   for (int l = 0; l < 5; ++l) {
     SgConvArgs a;
     memset(&a, 0, sizeof(a));
-    a.A = in; a.lda = lda; a.W = h->Wf[l]; a.bias = h->bias[l]; a.out = w.r[l]; a.ldo = kCoutP[l];
+    a.A = in; a.lda = lda; a.W = h->Wf[l]; a.Wk = h->Wfk[l]; a.bias = h->bias[l]; a.out = w.r[l]; a.ldo = kCoutP[l];
     a.rows = R; a.N = kCoutP[l]; a.cin = kCinP[l]; a.taps = kTaps[l]; a.tap_step = kDil[l];
     a.epilogue = SG_EPI_BIAS_RELU; a.T = T; a.t_valid = tv[l];
-    SG_TRY(run_conv(h, a, true, st));
+    SG_TRY(run_conv(h, a, true, SG_PROF_TDNN_FWD, st));
     in = w.r[l]; lda = kCoutP[l];
   }
   h->launches += 1;
-  SG_TRY(sg_pool_fwd_launch(w.r[4], B, T, tv[4], h->bn5_mean, h->bn5_istd, w.stats, w.save_mean, w.save_std, st));
+  PROF(h, SG_PROF_POOL, st, sg_pool_fwd_launch(w.r[4], B, T, tv[4], h->bn5_mean, h->bn5_istd, w.stats, w.save_mean, w.save_std, st));
   {
     SgConvArgs a;
     memset(&a, 0, sizeof(a));
     a.A = w.stats; a.lda = SG_STATS; a.W = h->Wfc; a.bias = h->bfc; a.out = w.e1; a.ldo = SG_EMB;
     a.rows = B; a.N = SG_EMB; a.cin = SG_STATS; a.taps = 1; a.tap_step = 0; a.epilogue = SG_EPI_BIAS; a.T = 1;
-    SG_TRY(run_conv(h, a, false, st));
+    SG_TRY(run_conv(h, a, false, SG_PROF_HEAD_GEMM, st));
     a.A = w.e1; a.lda = SG_EMB; a.W = h->Wlda; a.bias = h->blda; a.out = w.e2; a.ldo = h->Lp;
     a.N = h->Lp; a.cin = SG_EMB;
-    SG_TRY(run_conv(h, a, false, st));
+    SG_TRY(run_conv(h, a, false, SG_PROF_HEAD_GEMM, st));
   }
   h->launches += 1;
-  return sg_head_fwd_launch(h->H, w.e2, B, w.tsave, w.scal, emb, st);
+  PROF(h, SG_PROF_HEAD, st, sg_head_fwd_launch(h->H, w.e2, B, w.tsave, w.scal, emb, st));
+  return SG_OK;
 }
 
 static int embed_bwd(sg_handle* h, const float* demb, int B, int T, const XvWs& w, float* dfeat, cudaStream_t st) {
@@ -372,35 +437,35 @@ static int embed_bwd(sg_handle* h, const float* demb, int B, int T, const XvWs& 
   tdnn_valid(T, tv);
   const int R = B * T;
   h->launches += 1;
-  SG_TRY(sg_head_bwd_launch(h->H, demb, B, w.tsave, w.scal, w.de2, st));
+  PROF(h, SG_PROF_HEAD, st, sg_head_bwd_launch(h->H, demb, B, w.tsave, w.scal, w.de2, st));
   {
     SgConvArgs a;
     memset(&a, 0, sizeof(a));
     a.A = w.de2; a.lda = h->Lp; a.W = h->Wlda_b; a.out = w.de1; a.ldo = SG_EMB;
     a.rows = B; a.N = SG_EMB; a.cin = h->Lp; a.taps = 1; a.epilogue = SG_EPI_NONE; a.T = 1;
-    SG_TRY(run_conv(h, a, false, st));
+    SG_TRY(run_conv(h, a, false, SG_PROF_HEAD_GEMM, st));
     a.A = w.de1; a.lda = SG_EMB; a.W = h->Wfc_b; a.out = w.dstats; a.ldo = SG_STATS; a.N = SG_STATS; a.cin = SG_EMB;
-    SG_TRY(run_conv(h, a, false, st));
+    SG_TRY(run_conv(h, a, false, SG_PROF_HEAD_GEMM, st));
   }
   h->launches += 1;
-  SG_TRY(sg_pool_bwd_launch(w.r[4], B, T, tv[4], h->bn5_istd, w.dstats, w.save_mean, w.save_std, w.G0, st));
+  PROF(h, SG_PROF_POOL, st, sg_pool_bwd_launch(w.r[4], B, T, tv[4], h->bn5_istd, w.dstats, w.save_mean, w.save_std, w.G0, st));
   // dgrad chain: dA_l (pre-ReLU grad of layer l) -> dA_{l-1}
   const float* gin = w.G0;
   float* bufs[2] = {w.G1, w.G2};
   for (int l = 4; l >= 0; --l) {
     SgConvArgs a;
     memset(&a, 0, sizeof(a));
-    a.A = gin; a.lda = kCoutP[l]; a.W = h->Wb[l]; a.rows = R; a.cin = kCoutP[l]; a.taps = kTaps[l];
+    a.A = gin; a.lda = kCoutP[l]; a.W = h->Wb[l]; a.Wk = h->Wbk[l]; a.rows = R; a.cin = kCoutP[l]; a.taps = kTaps[l];
     a.tap_step = -kDil[l]; a.T = T;
     if (l > 0) {
       float* out = bufs[(4 - l) & 1];
       a.out = out; a.ldo = kCinP[l]; a.N = kCinP[l];
       a.epilogue = SG_EPI_MASK; a.mask = w.r[l - 1]; a.ldmask = kCoutP[l - 1]; a.t_valid = tv[l - 1];
-      SG_TRY(run_conv(h, a, true, st));
+      SG_TRY(run_conv(h, a, true, SG_PROF_TDNN_BWD, st));
       gin = out;
     } else {
       a.out = dfeat; a.ldo = SG_FLD; a.N = SG_FLD; a.epilogue = SG_EPI_NONE;
-      SG_TRY(run_conv(h, a, true, st));
+      SG_TRY(run_conv(h, a, true, SG_PROF_TDNN_BWD, st));
     }
   }
   return SG_OK;
@@ -419,6 +484,21 @@ extern "C" int sg_xv_embed_bwd(sg_handle* h, const float* demb, int B, int T, vo
   return embed_bwd(h, demb, B, T, w, dfeat, (cudaStream_t)stream);
 }
 
+// generic contraction, either path (tests): W is [taps*cin, N], Wk its K-major copy [N, taps*cin]
+extern "C" int sg_debug_conv(sg_handle* h, int precision, const float* A, int lda, const float* W, const float* Wk,
+                             const float* bias, float* out, int ldo, int rows, int N, int cin, int taps, int tap_step,
+                             int epilogue, const float* mask, int ldmask, int T, int t_valid, sg_stream stream) {
+  SG_TRY(check_handle(h, false));
+  if (!A || !out || rows < 1 || N < 1) { sg_set_error("sg_debug_conv: bad argument"); return SG_EINVAL; }
+  SgConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.A = A; a.lda = lda; a.W = W; a.Wk = Wk; a.bias = bias; a.out = out; a.ldo = ldo; a.rows = rows; a.N = N; a.cin = cin;
+  a.taps = taps; a.tap_step = tap_step; a.epilogue = epilogue; a.mask = mask; a.ldmask = ldmask; a.T = T; a.t_valid = t_valid;
+  h->launches += 1;
+  if (precision == SG_PREC_FP32) return sg_conv_simt(a, (cudaStream_t)stream);
+  return sg_conv_tc(a, precision, (cudaStream_t)stream);
+}
+
 // ---- scoring / loss ----------------------------------------------------------------------------
 extern "C" int sg_plda_score_fwd(sg_handle* h, const float* emb, int B, const float* enroll, int S, float threshold,
                                  float* scores, int64_t* decisions, sg_stream stream) {
@@ -427,7 +507,8 @@ extern "C" int sg_plda_score_fwd(sg_handle* h, const float* emb, int B, const fl
   if (!enroll) { enroll = h->enroll; S = h->S; }
   if (S < 1) { sg_set_error("sg_plda_score_fwd: S must be >= 1"); return SG_EINVAL; }
   h->launches += 1;
-  return sg_score_fwd_launch(h->H, emb, B, enroll, S, threshold, scores, (long long*)decisions, (cudaStream_t)stream);
+  PROF(h, SG_PROF_HEAD, (cudaStream_t)stream, sg_score_fwd_launch(h->H, emb, B, enroll, S, threshold, scores, (long long*)decisions, (cudaStream_t)stream));
+  return SG_OK;
 }
 extern "C" int sg_plda_score_bwd(sg_handle* h, const float* emb, const float* dscores, int B, const float* enroll, int S,
                                  float* demb, sg_stream stream) {
@@ -435,7 +516,8 @@ extern "C" int sg_plda_score_bwd(sg_handle* h, const float* emb, const float* ds
   if (!emb || !dscores || !demb || B < 1) { sg_set_error("sg_plda_score_bwd: bad argument"); return SG_EINVAL; }
   if (!enroll) { enroll = h->enroll; S = h->S; }
   h->launches += 1;
-  return sg_score_bwd_launch(h->H, emb, dscores, B, enroll, S, demb, (cudaStream_t)stream);
+  PROF(h, SG_PROF_HEAD, (cudaStream_t)stream, sg_score_bwd_launch(h->H, emb, dscores, B, enroll, S, demb, (cudaStream_t)stream));
+  return SG_OK;
 }
 static int check_loss(const sg_loss_params* lp, int S) {
   if (!lp) { sg_set_error("null loss params"); return SG_EINVAL; }
@@ -448,7 +530,8 @@ extern "C" int sg_loss_fwd_bwd(sg_handle* h, const float* scores, const int64_t*
   SG_TRY(check_handle(h, false)); SG_TRY(check_loss(lp, S));
   if (!scores || !y || !loss || B < 1 || S < 1) { sg_set_error("sg_loss_fwd_bwd: bad argument"); return SG_EINVAL; }
   h->launches += 1;
-  return sg_loss_launch(scores, (const long long*)y, B, S, *lp, loss, dscores, (cudaStream_t)stream);
+  PROF(h, SG_PROF_LOSS, (cudaStream_t)stream, sg_loss_launch(scores, (const long long*)y, B, S, *lp, loss, dscores, (cudaStream_t)stream));
+  return SG_OK;
 }
 
 extern "C" int sg_step_linf(sg_handle* h, float* x, const float* x0, const float* grad, size_t n, float step,
@@ -456,7 +539,8 @@ extern "C" int sg_step_linf(sg_handle* h, float* x, const float* x0, const float
   SG_TRY(check_handle(h, false));
   if (!x || !x0 || !grad) { sg_set_error("sg_step_linf: null pointer"); return SG_EINVAL; }
   h->launches += 1;
-  return sg_step_linf_launch(x, x0, grad, n, step * grad_sign, eps, (cudaStream_t)stream);
+  PROF(h, SG_PROF_STEP, (cudaStream_t)stream, sg_step_linf_launch(x, x0, grad, n, step * grad_sign, eps, (cudaStream_t)stream));
+  return SG_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -465,10 +549,11 @@ extern "C" int sg_step_linf(sg_handle* h, float* x, const float* x0, const float
 static int forward_pass(sg_handle* h, const float* x, int B, int N, int m, int mode, const float* dither, uint64_t seed,
                         uint64_t pass, float thr, const XvWs& w, float* emb, float* scores, long long* dec, cudaStream_t st) {
   h->launches += 3;
-  SG_TRY(sg_feat_fwd_launch(h->d_tables, x, B, N, m, mode, dither, seed, pass, w.raw, SG_FLD, st));
-  SG_TRY(sg_cmvn_launch(w.raw, SG_FLD, w.feat, SG_FLD, B, m, 0, st));
+  PROF(h, SG_PROF_MFCC_FWD, st, sg_feat_fwd_launch(h->d_tables, x, B, N, m, mode, dither, seed, pass, w.raw, SG_FLD, st));
+  PROF(h, SG_PROF_CMVN, st, sg_cmvn_launch(w.raw, SG_FLD, w.feat, SG_FLD, B, m, 0, st));
   SG_TRY(embed_fwd(h, w.feat, B, m, w, emb, st));
-  return sg_score_fwd_launch(h->H, emb, B, h->enroll, h->S, thr, scores, dec, st);
+  PROF(h, SG_PROF_HEAD, st, sg_score_fwd_launch(h->H, emb, B, h->enroll, h->S, thr, scores, dec, st));
+  return SG_OK;
 }
 
 extern "C" int sg_xv_forward(sg_handle* h, const float* x, int B, int N, int dither_mode, const float* dither,
@@ -506,23 +591,23 @@ extern "C" int sg_pgd_run(sg_handle* h, float* x_adv, const float* x0, const int
       SG_TRY(forward_pass(h, cur, B, N, m, p->dither_mode, dth, p->seed, pass, p->decision_threshold, w, w.emb, sc, dec, st));
       float* lossp = (loss_hist && e == 0) ? loss_hist + (size_t)it * B : w.loss;
       h->launches += 3;
-      SG_TRY(sg_loss_launch(sc, (const long long*)y, B, h->S, p->loss, lossp, w.dscores, st));
-      SG_TRY(sg_score_bwd_launch(h->H, w.emb, w.dscores, B, h->enroll, h->S, w.demb, st));
+      PROF(h, SG_PROF_LOSS, st, sg_loss_launch(sc, (const long long*)y, B, h->S, p->loss, lossp, w.dscores, st));
+      PROF(h, SG_PROF_HEAD, st, sg_score_bwd_launch(h->H, w.emb, w.dscores, B, h->enroll, h->S, w.demb, st));
       SG_TRY(embed_bwd(h, w.demb, B, m, w, w.dfeat, st));
-      SG_TRY(sg_cmvn_launch(w.dfeat, SG_FLD, w.draw, SG_FLD, B, m, 1, st));
+      PROF(h, SG_PROF_CMVN, st, sg_cmvn_launch(w.dfeat, SG_FLD, w.draw, SG_FLD, B, m, 1, st));
       h->launches += 1;
       if (E == 1) {
-        SG_TRY(sg_feat_bwd_step_launch(h->d_tables, cur, B, N, m, p->dither_mode, dth, p->seed, pass, w.draw, SG_FLD, x0,
+        PROF(h, SG_PROF_MFCC_BWD, st, sg_feat_bwd_step_launch(h->d_tables, cur, B, N, m, p->dither_mode, dth, p->seed, pass, w.draw, SG_FLD, x0,
                                        other, p->step_size * grad_sign, p->epsilon, st));
         float* t = cur; cur = other; other = t;
       } else {
-        SG_TRY(sg_feat_bwd_launch(h->d_tables, cur, B, N, m, p->dither_mode, dth, p->seed, pass, w.draw, SG_FLD, w.grad,
+        PROF(h, SG_PROF_MFCC_BWD, st, sg_feat_bwd_launch(h->d_tables, cur, B, N, m, p->dither_mode, dth, p->seed, pass, w.draw, SG_FLD, w.grad,
                                   1.0f / (float)E, e > 0, st));
       }
     }
     if (E > 1) {
       h->launches += 1;
-      SG_TRY(sg_step_linf_launch(cur, x0, w.grad, (size_t)B * N, p->step_size * grad_sign, p->epsilon, st));
+      PROF(h, SG_PROF_STEP, st, sg_step_linf_launch(cur, x0, w.grad, (size_t)B * N, p->step_size * grad_sign, p->epsilon, st));
     }
   }
   // final evaluation pass (attack/FGSM.py:44-57 with iter == max_iter)
@@ -532,7 +617,7 @@ extern "C" int sg_pgd_run(sg_handle* h, float* x_adv, const float* x0, const int
     SG_TRY(forward_pass(h, cur, B, N, m, p->dither_mode, dth, p->seed, pass, p->decision_threshold, w, w.emb, sc, dec, st));
     float* lossp = loss_hist ? loss_hist + (size_t)p->max_iter * B : w.loss;
     h->launches += 1;
-    SG_TRY(sg_loss_launch(sc, (const long long*)y, B, h->S, p->loss, lossp, nullptr, st));
+    PROF(h, SG_PROF_LOSS, st, sg_loss_launch(sc, (const long long*)y, B, h->S, p->loss, lossp, nullptr, st));
   }
   if (cur != x_adv) SG_CUDA_CHECK(cudaMemcpyAsync(x_adv, cur, (size_t)B * N * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return SG_OK;

@@ -71,7 +71,8 @@ enum SgEpilogue {
 
 struct SgConvArgs {
   const float* A; int lda;          // activations [rows, lda], K (channels) contiguous
-  const float* W;                   // packed weights [taps*cin, N] row-major
+  const float* W;                   // packed weights [taps*cin, N] row-major (SIMT path)
+  const float* Wk;                  // K-major copy [N, taps*cin] (tensor-core path); may be null for SIMT-only calls
   const float* bias;                // [N] or null
   float* out; int ldo;              // [rows, ldo]
   int rows;                         // M

@@ -1,8 +1,308 @@
-// tcgen05 / TMEM tensor-core path for the TDNN contractions (placeholder until the kernel lands).
+// T1 / T2: the TDNN contractions on 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a.
+//
+// Same contract as sg_conv_simt.cu: out[p, n] = epi(sum_{tap,c} A[p + tap*step, c] * W[n, tap*cin + c])
+// with channels-last fp32 activations, so a dilated tap is a TMA box shifted by `step` rows (rows
+// outside the tensor are zero-filled by TMA: no im2col, no halo copies).  Both operands are K-major,
+// SWIZZLE_128B: A box = 128 rows x 32 fp32, B box = BN rows x 32 fp32 per pipeline stage.
+//
+// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one elected
+// lane) and TMEM owner, warps 2..5 = epilogue (tcgen05.ld -> bias/ReLU or ReLU-mask -> st.global).
+// The fp32 accumulator (128 lanes x BN columns) is double-buffered in TMEM (2 x 256 columns) so
+// the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cuda.h>
+
 #include "sg_common.cuh"
 
+#define TC_BM 128
+#define TC_BK 32                     // fp32 elements per k-block = one 128-byte swizzle span
+#define TC_STAGES 4
+#define TC_MAX_BN 256
+#define TC_A_BYTES (TC_BM * TC_BK * 4)          // 16 KB
+#define TC_B_BYTES (TC_MAX_BN * TC_BK * 4)      // 32 KB
+#define TC_STAGE_BYTES (TC_A_BYTES + TC_B_BYTES)
+#define TC_SMEM_BYTES (TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/)
+#define TC_THREADS 192
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// bounded spin: a protocol bug traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t it = 0; !done; ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (it > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+template <int KIND_BF16>
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (KIND_BF16) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  } else {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  }
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp):
+// start address >> 4 in [0,14), LBO (unused for swizzled K-major) = 1 in [16,30), SBO = 1024 B
+// (8 rows x 128 B) >> 4 in [32,46), version 1 in [46,48), layout SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+struct TcArgs {
+  const float* bias;
+  float* out; int ldo;
+  const float* mask; int ldmask;
+  int rows, N, bn;                 // bn: N-tile (multiple of 32, <= 256)
+  int kchunks, taps, tap_step;     // kchunks = cin / 32
+  int epilogue, T, t_valid;
+  int m_tiles, n_tiles;
+};
+
+template <int KIND_BF16>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + TC_STAGES * TC_STAGE_BYTES);
+  uint64_t* full = bars;                       // [TC_STAGES]
+  uint64_t* empty = bars + TC_STAGES;          // [TC_STAGES]
+  uint64_t* tfull = bars + 2 * TC_STAGES;      // [2]
+  uint64_t* tempty = bars + 2 * TC_STAGES + 2; // [2]
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TC_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = a.taps * a.kchunks;
+  const int ntiles = a.m_tiles * a.n_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      const uint32_t tx = TC_A_BYTES + (uint32_t)a.bn * TC_BK * 4;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
+        const int p0 = mt * TC_BM, n0 = nt * a.bn;
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int tap = kb / a.kchunks, kc = kb - tap * a.kchunks;
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], tx);
+          uint8_t* sa = smem + stage * TC_STAGE_BYTES;
+          tma_load_2d(sa, &mapA, &full[stage], kc * TC_BK, p0 + tap * a.tap_step);
+          tma_load_2d(sa + TC_A_BYTES, &mapB, &full[stage], kb * TC_BK, n0);
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      // instruction descriptor: D=f32 [4,6)=1, A/B format [7,10)/[10,13) (tf32=2, bf16=1), K-major both,
+      // N>>3 in [17,23), M>>4 in [24,29)
+      const uint32_t fmt = KIND_BF16 ? 1u : 2u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(a.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)acc * TC_MAX_BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * TC_STAGE_BYTES);
+          const uint64_t da = make_desc(sa), db = make_desc(sa + TC_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // 4 x (K = 32 bytes) per 128-byte swizzle span: +2 in 16-byte units
+            tc_mma<KIND_BF16>(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          tc_commit(&empty[stage]);      // frees the smem slot when these MMAs retire
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&tfull[acc]);          // accumulator complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===== epilogue: warps 2..5; a warp may only touch TMEM lanes 32*(warp%4) .. +31 =====
+    const int q = warp & 3;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
+      const int row = mt * TC_BM + q * 32 + lane;
+      const int n0 = nt * a.bn;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const bool row_in = row < a.rows;
+      bool row_ok = row_in;
+      if (a.epilogue == SG_EPI_MASK) row_ok = row_in && ((row % a.T) < a.t_valid);
+      for (int c = 0; c < a.bn; c += 32) {
+        float v[32];
+        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TC_MAX_BN + c), v);
+        const int col = n0 + c;
+        if (a.epilogue == SG_EPI_BIAS || a.epilogue == SG_EPI_BIAS_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += __ldg(a.bias + col + j);
+          if (a.epilogue == SG_EPI_BIAS_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+        } else if (a.epilogue == SG_EPI_MASK) {
+          if (row_ok) {
+            const float4* mp = reinterpret_cast<const float4*>(a.mask + (size_t)row * a.ldmask + col);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 m4 = __ldg(mp + j);
+              v[4 * j + 0] = m4.x > 0.f ? v[4 * j + 0] : 0.f;
+              v[4 * j + 1] = m4.y > 0.f ? v[4 * j + 1] : 0.f;
+              v[4 * j + 2] = m4.z > 0.f ? v[4 * j + 2] : 0.f;
+              v[4 * j + 3] = m4.w > 0.f ? v[4 * j + 3] : 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          }
+        }
+        if (row_in) {
+          float4* op = reinterpret_cast<float4*>(a.out + (size_t)row * a.ldo + col);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+// ---- host ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeFn g_encode = nullptr;
+static int g_num_sms = 0;
+
+static int tc_init() {
+  if (g_encode) return SG_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+    sg_set_error("cuTensorMapEncodeTiled unavailable (%s)", cudaGetErrorString(e));
+    return SG_ECUDA;
+  }
+  int dev = 0;
+  SG_CUDA_CHECK(cudaGetDevice(&dev));
+  SG_CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+  SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+  g_encode = (EncodeFn)fn;
+  return SG_OK;
+}
+
+static int make_map_f32(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * sizeof(float)};
+  cuuint32_t box[2] = {TC_BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { sg_set_error("cuTensorMapEncodeTiled failed (%d): rows=%llu cols=%llu ld=%llu box=%u", (int)r,
+                                        (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows); return SG_ECUDA; }
+  return SG_OK;
+}
+
+// uses a.Wk, the K-major copy of the weights: [N][taps*cin]
 int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
-  (void)a; (void)precision; (void)st;
-  sg_set_error("tensor-core path not built yet: use SG_PREC_FP32");
-  return SG_EUNSUPPORTED;
+  if (precision != SG_PREC_TF32) { sg_set_error("tensor-core path: only SG_PREC_TF32 is built (fp32 storage)"); return SG_EUNSUPPORTED; }
+  int r = tc_init();
+  if (r != SG_OK) return r;
+  if (a.cin % TC_BK != 0 || a.N % 32 != 0 || a.lda % 4 != 0 || a.ldo % 4 != 0 || (a.epilogue == SG_EPI_MASK && a.ldmask % 4 != 0)) {
+    sg_set_error("sg_conv_tc: cin %% 32, N %% 32, lda/ldo %% 4 required (cin=%d N=%d)", a.cin, a.N);
+    return SG_EINVAL;
+  }
+  int bn = a.N >= TC_MAX_BN ? TC_MAX_BN : a.N;
+  if (a.N % bn != 0) { sg_set_error("sg_conv_tc: N=%d is not a multiple of the N-tile %d", a.N, bn); return SG_EINVAL; }
+  CUtensorMap mapA, mapB;
+  r = make_map_f32(&mapA, a.A, (uint64_t)a.rows, (uint64_t)a.cin, (uint64_t)a.lda, TC_BM);
+  if (r != SG_OK) return r;
+  if (!a.Wk) { sg_set_error("sg_conv_tc: K-major weights missing"); return SG_EINVAL; }
+  r = make_map_f32(&mapB, a.Wk, (uint64_t)a.N, (uint64_t)a.taps * a.cin, (uint64_t)a.taps * a.cin, (uint32_t)bn);
+  if (r != SG_OK) return r;
+  TcArgs t;
+  t.bias = a.bias; t.out = a.out; t.ldo = a.ldo; t.mask = a.mask; t.ldmask = a.ldmask;
+  t.rows = a.rows; t.N = a.N; t.bn = bn; t.kchunks = a.cin / TC_BK; t.taps = a.taps; t.tap_step = a.tap_step;
+  t.epilogue = a.epilogue; t.T = a.T > 0 ? a.T : 1; t.t_valid = a.t_valid;
+  t.m_tiles = (a.rows + TC_BM - 1) / TC_BM; t.n_tiles = a.N / bn;
+  if ((a.epilogue == SG_EPI_BIAS || a.epilogue == SG_EPI_BIAS_RELU) && !a.bias) { sg_set_error("sg_conv_tc: bias epilogue without bias"); return SG_EINVAL; }
+  int grid = t.m_tiles * t.n_tiles;
+  if (grid > g_num_sms) grid = g_num_sms;
+  conv_tc_kernel<0><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mapA, mapB, t);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
 }

@@ -1,0 +1,71 @@
+"""Multi-GPU plumbing: one process per GPU, utterances sharded contiguously, no data-path
+collective (every utterance is independent through the whole attack iteration).
+NCCL (via torch.distributed) is used only to reduce a handful of metric scalars at the end of an
+attack: success count, sum of SNR / L2 / Linf and the utterance count (reference
+metric/metric.py:10-42 semantics for SNR / Lp)."""
+from __future__ import annotations
+
+import os
+from typing import Dict, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend: str = None) -> Tuple[int, int, int]:
+    """-> (rank, world, local_rank); initialises the default process group when WORLD_SIZE > 1."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend)
+    return rank, world, local
+
+
+def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous split of n utterances: rank r owns [lo, hi); remainders go to the first ranks."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def attack_metrics(x: torch.Tensor, adv: torch.Tensor, success) -> torch.Tensor:
+    """Local sums [n, n_success, sum SNR(dB), sum L2, sum Linf] as one fp64 vector on x's device."""
+    x2, a2 = x.flatten(1).double(), adv.detach().flatten(1).double()
+    delta = a2 - x2
+    noise = delta.pow(2).sum(1)
+    snr = 10.0 * torch.log10(x2.pow(2).sum(1) / noise.clamp_min(1e-300))
+    snr = torch.where(noise > 0, snr, torch.zeros_like(snr))
+    suc = torch.as_tensor(success, dtype=torch.float64, device=x.device)
+    return torch.stack([torch.tensor(float(x.shape[0]), dtype=torch.float64, device=x.device), suc.sum(), snr.sum(),
+                        noise.sqrt().sum(), delta.abs().max(1)[0].sum()])
+
+
+def reduce_metrics(local: torch.Tensor) -> Dict[str, float]:
+    """All-reduce (sum) of the metric vector over the job; a no-op without a process group."""
+    v = local.clone()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(v, op=dist.ReduceOp.SUM)
+    n = max(float(v[0]), 1.0)
+    return {"n": float(v[0]), "success_rate": float(v[1]) / n, "snr_db": float(v[2]) / n, "l2": float(v[3]) / n,
+            "linf": float(v[4]) / n}
+
+
+def max_over_ranks(value: float, device) -> float:
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0])
+
+
+def barrier() -> None:
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()

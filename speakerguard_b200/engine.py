@@ -78,6 +78,18 @@ class Engine:
     def reset_launch_count(self) -> None:
         self.lib.sg_reset_launch_count(self._h)
 
+    def profile(self, enable: bool) -> None:
+        check(self.lib.sg_profile_enable(self._h, int(enable)), "sg_profile_enable")
+
+    def profile_read(self) -> Dict[str, Tuple[float, int]]:
+        """{category: (total device ms, launches)} since profile(True); synchronises."""
+        out = {}
+        for c in range(_lib.PROF_COUNT):
+            ms, n = C.c_double(), C.c_longlong()
+            check(self.lib.sg_profile_read(self._h, c, C.byref(ms), C.byref(n)), "sg_profile_read")
+            out[self.lib.sg_profile_name(c).decode()] = (ms.value, n.value)
+        return out
+
     def load_xv(self, p: Dict[str, torch.Tensor], bn_eps: float = 1e-5) -> None:
         """p: 'tdnn{1..5}.weight/.bias', 'bn{1..5}.mean/.var', 'fc1.weight/.bias', 'emb_mean',
         'lda' [L,513], 'plda.mean/.transform/.psi', 'enroll' [S,L] (any device; copied to host)."""
@@ -254,3 +266,17 @@ def default_engine(device) -> "Engine":
     if idx not in _DEFAULT_ENGINES:
         _DEFAULT_ENGINES[idx] = Engine(torch.device("cuda", idx))
     return _DEFAULT_ENGINES[idx]
+
+
+def debug_conv(eng: "Engine", precision: str, A: torch.Tensor, W: torch.Tensor, bias, rows: int, N: int, cin: int,
+               taps: int, tap_step: int, epilogue: int, mask=None, T: int = 1, t_valid: int = 0) -> torch.Tensor:
+    """One conv-as-GEMM launch through sg_debug_conv.  A [rows, cin] fp32, W [taps*cin, N] fp32."""
+    A, W = _f32c(A, eng.device), _f32c(W, eng.device)
+    Wk = W.t().contiguous()
+    out = torch.empty(rows, N, device=eng.device, dtype=torch.float32)
+    b = None if bias is None else _f32c(bias, eng.device)
+    mk = None if mask is None else _f32c(mask, eng.device)
+    check(eng.lib.sg_debug_conv(eng._h, _lib.PRECISIONS[precision], _ptr(A), A.shape[1], _ptr(W), _ptr(Wk), _ptr(b),
+                                _ptr(out), N, rows, N, cin, taps, tap_step, epilogue, _ptr(mk),
+                                0 if mk is None else mk.shape[1], T, t_valid, eng.stream), "sg_debug_conv")
+    return out
