@@ -140,7 +140,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("SGB200_PRECISION", "fp32"), choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("SGB200_PRECISION", "tf32"), choices=["fp32", "tf32", "bf16"])
     ap.add_argument("--batch", type=int, default=1024, help="utterances per GPU")
     ap.add_argument("--seconds", type=float, default=3.0)
     ap.add_argument("--iters", type=int, default=100, help="PGD iterations per attack")
@@ -217,12 +217,14 @@ def main():
         torch.cuda.synchronize()
         return adv, success
 
-    e2e_step()
+    adv, success = e2e_step()
     dist.barrier()
     t0 = time.perf_counter()
     for _ in range(args.e2e_steps):
         adv, success = e2e_step()
-    e2e_s = dist.max_over_ranks(time.perf_counter() - t0, dev) / args.e2e_steps
+    e2e_s = dist.max_over_ranks(time.perf_counter() - t0, dev) / max(args.e2e_steps, 1)
+    if args.e2e_steps == 0:
+        e2e_s = float("inf")
     e2e_value = world * B * iters / e2e_s
     metrics = dist.reduce_metrics(dist.attack_metrics(x_dev, adv, success))     # NCCL: metric scalars only
 

@@ -75,6 +75,8 @@ struct sg_handle {
   float* bn5_mean = nullptr; float* bn5_istd = nullptr;           // [C5P]
   float* Wfc = nullptr; float* Wfc_b = nullptr; float* bfc = nullptr;     // fc1: [3072,512], [512,3072], [512]
   float* Wlda = nullptr; float* Wlda_b = nullptr; float* blda = nullptr;  // LDA: [512,Lp], [Lp,512], [Lp]
+  // K-major copies for the tensor-core path ([N, K]): transposes of the four matrices above
+  float* Wfc_k = nullptr; float* Wfc_bk = nullptr; float* Wlda_k = nullptr; float* Wlda_bk = nullptr;
   float* plda_mean = nullptr; float* plda_T = nullptr; float* plda_Tt = nullptr;
   float* inv_psi1 = nullptr; float* psi_ratio = nullptr; float* inv_var_given = nullptr;
   float* enroll = nullptr;
@@ -174,7 +176,7 @@ extern "C" int sg_load_xv(sg_handle* h, const sg_xv_weights* w) {
   }
   SG_CUDA_CHECK(cudaSetDevice(h->device));
   const float eps = w->bn_eps > 0.f ? w->bn_eps : 1e-5f;
-  const int L = w->L, Lp = (L + 15) / 16 * 16, S = w->S;
+  const int L = w->L, Lp = (L + 31) / 32 * 32, S = w->S;
   h->L = L; h->Lp = Lp; h->S = S;
   for (int l = 0; l < 5; ++l) {
     const int K = kTaps[l], ci = kCin[l], cip = kCinP[l], co = kCout[l], cop = kCoutP[l];
@@ -224,6 +226,8 @@ extern "C" int sg_load_xv(sg_handle* h, const sg_xv_weights* w) {
     }
     SG_TRY(dev_upload(h, &h->Wfc, Wfc));
     SG_TRY(dev_upload(h, &h->Wfc_b, Wfcb));
+    h->Wfc_k = h->Wfc_b;    // [512, 3072] is the K-major form of the forward matrix
+    h->Wfc_bk = h->Wfc;     // and vice versa
     SG_TRY(dev_upload(h, &h->bfc, b));
   }
   {  // LDA (model/iv_plda.py:423-435): [L, 513], offset in the last column
@@ -238,6 +242,8 @@ extern "C" int sg_load_xv(sg_handle* h, const sg_xv_weights* w) {
     }
     SG_TRY(dev_upload(h, &h->Wlda, Wl));
     SG_TRY(dev_upload(h, &h->Wlda_b, Wlb));
+    h->Wlda_k = h->Wlda_b;  // [Lp, 512]
+    h->Wlda_bk = h->Wlda;   // [512, Lp]
     SG_TRY(dev_upload(h, &h->blda, b));
   }
   {  // PLDA (plda.py:27-51, :140-190)
@@ -420,12 +426,12 @@ static int embed_fwd(sg_handle* h, const float* feat, int B, int T, const XvWs& 
   {
     SgConvArgs a;
     memset(&a, 0, sizeof(a));
-    a.A = w.stats; a.lda = SG_STATS; a.W = h->Wfc; a.bias = h->bfc; a.out = w.e1; a.ldo = SG_EMB;
+    a.A = w.stats; a.lda = SG_STATS; a.W = h->Wfc; a.Wk = h->Wfc_k; a.bias = h->bfc; a.out = w.e1; a.ldo = SG_EMB;
     a.rows = B; a.N = SG_EMB; a.cin = SG_STATS; a.taps = 1; a.tap_step = 0; a.epilogue = SG_EPI_BIAS; a.T = 1;
-    SG_TRY(run_conv(h, a, false, SG_PROF_HEAD_GEMM, st));
-    a.A = w.e1; a.lda = SG_EMB; a.W = h->Wlda; a.bias = h->blda; a.out = w.e2; a.ldo = h->Lp;
+    SG_TRY(run_conv(h, a, true, SG_PROF_HEAD_GEMM, st));
+    a.A = w.e1; a.lda = SG_EMB; a.W = h->Wlda; a.Wk = h->Wlda_k; a.bias = h->blda; a.out = w.e2; a.ldo = h->Lp;
     a.N = h->Lp; a.cin = SG_EMB;
-    SG_TRY(run_conv(h, a, false, SG_PROF_HEAD_GEMM, st));
+    SG_TRY(run_conv(h, a, true, SG_PROF_HEAD_GEMM, st));
   }
   h->launches += 1;
   PROF(h, SG_PROF_HEAD, st, sg_head_fwd_launch(h->H, w.e2, B, w.tsave, w.scal, emb, st));
@@ -441,11 +447,11 @@ static int embed_bwd(sg_handle* h, const float* demb, int B, int T, const XvWs& 
   {
     SgConvArgs a;
     memset(&a, 0, sizeof(a));
-    a.A = w.de2; a.lda = h->Lp; a.W = h->Wlda_b; a.out = w.de1; a.ldo = SG_EMB;
+    a.A = w.de2; a.lda = h->Lp; a.W = h->Wlda_b; a.Wk = h->Wlda_bk; a.out = w.de1; a.ldo = SG_EMB;
     a.rows = B; a.N = SG_EMB; a.cin = h->Lp; a.taps = 1; a.epilogue = SG_EPI_NONE; a.T = 1;
-    SG_TRY(run_conv(h, a, false, SG_PROF_HEAD_GEMM, st));
-    a.A = w.de1; a.lda = SG_EMB; a.W = h->Wfc_b; a.out = w.dstats; a.ldo = SG_STATS; a.N = SG_STATS; a.cin = SG_EMB;
-    SG_TRY(run_conv(h, a, false, SG_PROF_HEAD_GEMM, st));
+    SG_TRY(run_conv(h, a, true, SG_PROF_HEAD_GEMM, st));
+    a.A = w.de1; a.lda = SG_EMB; a.W = h->Wfc_b; a.Wk = h->Wfc_bk; a.out = w.dstats; a.ldo = SG_STATS; a.N = SG_STATS; a.cin = SG_EMB;
+    SG_TRY(run_conv(h, a, true, SG_PROF_HEAD_GEMM, st));
   }
   h->launches += 1;
   PROF(h, SG_PROF_POOL, st, sg_pool_bwd_launch(w.r[4], B, T, tv[4], h->bn5_istd, w.dstats, w.save_mean, w.save_std, w.G0, st));

@@ -286,8 +286,9 @@ int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
     sg_set_error("sg_conv_tc: cin %% 32, N %% 32, lda/ldo %% 4 required (cin=%d N=%d)", a.cin, a.N);
     return SG_EINVAL;
   }
-  int bn = a.N >= TC_MAX_BN ? TC_MAX_BN : a.N;
-  if (a.N % bn != 0) { sg_set_error("sg_conv_tc: N=%d is not a multiple of the N-tile %d", a.N, bn); return SG_EINVAL; }
+  int bn = TC_MAX_BN;
+  while (bn > 32 && a.N % bn != 0) bn -= 32;     // largest N-tile (multiple of 32, <= 256) dividing N
+  if (a.N % bn != 0) { sg_set_error("sg_conv_tc: N=%d is not a multiple of 32", a.N); return SG_EINVAL; }
   CUtensorMap mapA, mapB;
   r = make_map_f32(&mapA, a.A, (uint64_t)a.rows, (uint64_t)a.cin, (uint64_t)a.lda, TC_BM);
   if (r != SG_OK) return r;

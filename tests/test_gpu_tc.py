@@ -59,3 +59,36 @@ def test_tc_conv_matches_ffma_and_fp64(rows, cin, N, taps, step, epi):
     print(f"rows={rows} cin={cin} N={N} taps={taps} step={step} epi={epi}: ffma err {e_simt:.2e}  tf32 err {e_tc:.2e}")
     assert e_simt < 1e-5
     assert e_tc < 2e-3
+
+
+def test_tf32_network_vs_fp32_network():
+    """Whole x-vector pass in TF32 tensor-core mode vs the fp32 parity mode (same kernels otherwise).
+    Stated tolerances for TF32 mode: embeddings / scores 5e-3 relative (row max), decisions equal on
+    this data, >= 97 % of input-gradient signs equal, gradient cosine >= 0.995."""
+    from oracle import sg_oracle as O
+    from speakerguard_b200 import _lib
+    from speakerguard_b200.engine import Engine, make_loss_params
+    p = O.make_xv_params(seed=0)
+    res = {}
+    torch.manual_seed(77)
+    x = ((torch.rand(6, 1, 32000) * 2 - 1) * 0.5)[:, 0].cuda()
+    y = torch.tensor([0, 1, 2, 3, 4, 5]).cuda()
+    for prec in ("fp32", "tf32"):
+        eng = Engine("cuda:0", precision=prec)
+        eng.load_xv(p)
+        feat = eng.cmvn(eng.mfcc_fwd(x, _lib.DITHER_PHILOX, None, seed=3, pass_=0, ld=32), ld_out=32)
+        emb, ws = eng.embed_fwd(feat)
+        scores, dec = eng.score_fwd(emb)
+        _, ds = eng.loss(scores, y, make_loss_params("Entropy"))
+        dfeat = eng.embed_bwd(eng.score_bwd(emb, ds), ws, 6, feat.shape[1])
+        grad = eng.mfcc_bwd(x, eng.cmvn(dfeat, ld_out=32, backward=True), _lib.DITHER_PHILOX, None, seed=3, pass_=0)
+        res[prec] = (emb.cpu(), scores.cpu(), dec.cpu(), grad.cpu())
+    rel = lambda a, b: float(((a - b).abs().max(1)[0] / b.abs().max(1)[0]).max())
+    e_emb, e_sc = rel(res["tf32"][0], res["fp32"][0]), rel(res["tf32"][1], res["fp32"][1])
+    g1, g0 = res["tf32"][3], res["fp32"][3]
+    sign_agree = float((torch.sign(g1) == torch.sign(g0)).float().mean())
+    cos = float((g1 * g0).sum() / (g1.norm() * g0.norm()))
+    print(f"tf32 vs fp32: emb {e_emb:.2e} scores {e_sc:.2e} grad sign agreement {sign_agree:.4f} cosine {cos:.5f}")
+    assert e_emb < 5e-3 and e_sc < 5e-3
+    assert torch.equal(res["tf32"][2], res["fp32"][2])
+    assert sign_agree > 0.97 and cos > 0.995
