@@ -158,6 +158,61 @@ int sg_xv_forward(sg_handle* h, const float* x, int B, int N, int dither_mode, c
                   uint64_t seed, uint64_t pass, float decision_threshold, void* ws, float* scores,
                   int64_t* decisions, float* emb, sg_stream stream);
 
+/* ---- AudioNet (log-mel CNN, CSI-NE) and CW2 ------------------------------------------------------
+ * sg_load_audionet: weights of audionet_csine (model/audionet_csine.py:58-121), HOST pointers in
+ *   PyTorch layouts: conv1_w [5][5] (Conv2d 1->1), conv_w[l] [C_out][C_in][3] for conv2..conv8,
+ *   BatchNorm (eval, affine) running stats / gamma / beta with index 0 = conv1's BatchNorm2d(1),
+ *   fc_w [num_class][32].  BatchNorm is folded into the convolutions.
+ * sg_audionet_logmel_fwd/bwd: Preprocessor.forward (model/_audionet/Preprocessor.py:85-112) and its
+ *   adjoint; x [B,N] in [-1,1] -> feat [B,T,32], T = sg_audionet_num_frames(N).
+ * sg_audionet_cnn_fwd/bwd: extract_emb + fc (audionet_csine.py:176-224); logits have row stride
+ *   sg_audionet_num_class_padded() (classes padded to a multiple of 16 with zero weights).
+ * sg_argmax_decide: make_decision (audionet_csine.py:243-257).
+ * sg_cw2_audionet_run: CW2.attack_batch (attack/CW2.py:41-132) entirely on the device: tanh-space
+ *   iterate, clipped margin loss, L2 term, Adam (lr, betas 0.9/0.999, eps 1e-8), best-example
+ *   tracking, per-utterance binary search on c; the only host syncs are the early-stop checks every
+ *   stop_early_iter iterations.  best_x [B,N] out, success [B] (0/1) out. */
+typedef struct {
+  const float* conv1_w;
+  const float* conv1_b;
+  const float* conv_w[7];
+  const float* conv_b[7];
+  const float* bn_mean[8];
+  const float* bn_var[8];
+  const float* bn_gamma[8];
+  const float* bn_beta[8];
+  const float* fc_w;
+  const float* fc_b;
+  int num_class;
+  float bn_eps;
+} sg_audionet_weights;
+typedef struct {
+  int binary_search_steps;
+  int max_iter;
+  int stop_early;
+  int stop_early_iter;
+  float lr;
+  float initial_const;
+  sg_loss_params loss;        /* SG_LOSS_MARGIN with clip_max = 1 */
+  float decision_threshold;   /* -inf for CSI */
+} sg_cw2_params;
+int sg_load_audionet(sg_handle* h, const sg_audionet_weights* w);
+int sg_audionet_num_frames(int N);
+int sg_audionet_num_class_padded(const sg_handle* h);
+size_t sg_audionet_ws_bytes(const sg_handle* h, int B, int N, int for_cw2);
+int sg_audionet_logmel_fwd(sg_handle* h, const float* x, int B, int N, float* feat, sg_stream stream);
+int sg_audionet_logmel_bwd(sg_handle* h, const float* x, int B, int N, const float* dfeat, void* ws,
+                           float* dx, float scale, int accumulate, sg_stream stream);
+int sg_audionet_cnn_fwd(sg_handle* h, const float* feat, int B, int N, void* ws, float* logits,
+                        sg_stream stream);
+int sg_audionet_cnn_bwd(sg_handle* h, const float* dlogits, int B, int N, void* ws, float* dfeat,
+                        sg_stream stream);
+int sg_argmax_decide(sg_handle* h, const float* scores, int B, int S, int ld, float threshold,
+                     int64_t* decisions, sg_stream stream);
+int sg_cw2_audionet_run(sg_handle* h, const float* x, const int64_t* y, int B, int N,
+                        const sg_cw2_params* p, void* ws, float* best_x, int64_t* success,
+                        float* final_const, sg_stream stream);
+
 /* ---- test hook: one conv-as-GEMM launch on either arithmetic path -----------------------------
  * out[p,n] = epi(sum_{tap,c} A[p + tap*tap_step, c] * W[tap*cin + c, n]); W is [taps*cin, N]
  * (FFMA path), Wk its K-major copy [N, taps*cin] (tcgen05 path); epilogue 0 bias, 1 bias+ReLU,
@@ -174,7 +229,8 @@ int sg_debug_conv(sg_handle* h, int precision, const float* A, int lda, const fl
  * summed duration and the launch count since sg_profile_enable() was last called.  bench.py
  * uses this for the per-kernel share of a step and for the roofline of the dominant kernel. */
 enum { SG_PROF_MFCC_FWD = 0, SG_PROF_MFCC_BWD, SG_PROF_CMVN, SG_PROF_TDNN_FWD, SG_PROF_TDNN_BWD,
-       SG_PROF_POOL, SG_PROF_HEAD_GEMM, SG_PROF_HEAD, SG_PROF_LOSS, SG_PROF_STEP, SG_PROF_COUNT };
+       SG_PROF_POOL, SG_PROF_HEAD_GEMM, SG_PROF_HEAD, SG_PROF_LOSS, SG_PROF_STEP, SG_PROF_AUDIONET,
+       SG_PROF_CW2, SG_PROF_COUNT };
 int sg_profile_enable(sg_handle* h, int enable);
 int sg_profile_read(sg_handle* h, int category, double* total_ms, long long* launches);
 const char* sg_profile_name(int category);

@@ -16,7 +16,7 @@ SG_OK, SG_EINVAL, SG_ECUDA, SG_ESTATE, SG_EUNSUPPORTED = 0, -1, -2, -3, -4
 PREC_FP32, PREC_TF32, PREC_BF16 = 0, 1, 2
 DITHER_OFF, DITHER_TENSOR, DITHER_PHILOX = 0, 1, 2
 LOSS_CE, LOSS_MARGIN = 0, 1
-PROF_COUNT = 10
+PROF_COUNT = 12
 TASK_CSI, TASK_SV, TASK_OSI = 0, 1, 2
 TASKS = {"CSI": TASK_CSI, "SV": TASK_SV, "OSI": TASK_OSI}
 PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "bf16": PREC_BF16}
@@ -36,6 +36,18 @@ class XvWeights(C.Structure):
 class LossParams(C.Structure):
     _fields_ = [("loss", C.c_int), ("task", C.c_int), ("targeted", C.c_int), ("clip_max", C.c_int),
                 ("confidence", C.c_float), ("threshold", C.c_float)]
+
+
+class AudioNetWeights(C.Structure):
+    _fields_ = [("conv1_w", _vp), ("conv1_b", _vp), ("conv_w", _vp * 7), ("conv_b", _vp * 7), ("bn_mean", _vp * 8),
+                ("bn_var", _vp * 8), ("bn_gamma", _vp * 8), ("bn_beta", _vp * 8), ("fc_w", _vp), ("fc_b", _vp),
+                ("num_class", C.c_int), ("bn_eps", C.c_float)]
+
+
+class Cw2Params(C.Structure):
+    _fields_ = [("binary_search_steps", C.c_int), ("max_iter", C.c_int), ("stop_early", C.c_int),
+                ("stop_early_iter", C.c_int), ("lr", C.c_float), ("initial_const", C.c_float), ("loss", LossParams),
+                ("decision_threshold", C.c_float)]
 
 
 class PgdParams(C.Structure):
@@ -71,6 +83,16 @@ PROTOTYPES = {
     "sg_pgd_run": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.POINTER(PgdParams), _vp, _vp, _vp, _vp, _vp]),
     "sg_xv_forward": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, C.c_uint64, C.c_uint64, C.c_float, _vp, _vp,
                                 _vp, _vp, _vp]),
+    "sg_load_audionet": (C.c_int, [_vp, C.POINTER(AudioNetWeights)]),
+    "sg_audionet_num_frames": (C.c_int, [C.c_int]),
+    "sg_audionet_num_class_padded": (C.c_int, [_vp]),
+    "sg_audionet_ws_bytes": (C.c_size_t, [_vp, C.c_int, C.c_int, C.c_int]),
+    "sg_audionet_logmel_fwd": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp]),
+    "sg_audionet_logmel_bwd": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_float, C.c_int, _vp]),
+    "sg_audionet_cnn_fwd": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "sg_audionet_cnn_bwd": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "sg_argmax_decide": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_float, _vp, _vp]),
+    "sg_cw2_audionet_run": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.POINTER(Cw2Params), _vp, _vp, _vp, _vp, _vp]),
     "sg_debug_conv": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.c_int, C.c_int, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     "sg_profile_enable": (C.c_int, [_vp, C.c_int]),

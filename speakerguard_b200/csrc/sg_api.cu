@@ -6,8 +6,7 @@
 
 #include <vector>
 
-#include "sg_common.cuh"
-#include "sg_head.cuh"
+#include "sg_handle.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // error string
@@ -32,65 +31,15 @@ static const int kCinP[5] = {32, 512, 512, 512, 512};
 static const int kCout[5] = {512, 512, 512, 512, 1500};
 static const int kCoutP[5] = {512, 512, 512, 512, SG_C5P};
 
-// per-category device timing (CUDA events on the launching stream); off by default
 static const char* kProfNames[SG_PROF_COUNT] = {
-    "mfcc_fwd", "mfcc_bwd", "cmvn", "tdnn_fwd", "tdnn_dgrad", "pool", "head_gemm", "head", "loss", "step"};
-struct SgProf {
-  bool on = false;
-  std::vector<cudaEvent_t> ev;      // pairs (start, stop)
-  std::vector<int> cat;             // category of pair i
-  size_t used = 0;                  // pairs recorded since the last reset
-  cudaEvent_t* begin(int c, cudaStream_t st) {
-    if (!on) return nullptr;
-    if (used == cat.size()) {
-      cudaEvent_t a, b;
-      if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return nullptr;
-      ev.push_back(a); ev.push_back(b); cat.push_back(c);
-    }
-    cat[used] = c;
-    cudaEventRecord(ev[2 * used], st);
-    return &ev[2 * used + 1];
-  }
-  void end(cudaEvent_t* stop, cudaStream_t st) {
-    if (!stop) return;
-    cudaEventRecord(*stop, st);
-    ++used;
-  }
-};
+    "mfcc_fwd", "mfcc_bwd", "cmvn", "tdnn_fwd", "tdnn_dgrad", "pool", "head_gemm", "head", "loss", "step", "audionet", "cw2"};
 
-struct sg_handle {
-  SgProf prof;
-  int device = 0;
-  int precision = SG_PREC_FP32;
-  long long launches = 0;
-  SgFeatTables* d_tables = nullptr;
-  bool xv_loaded = false;
-  int L = 0, Lp = 0, S = 0;
-  // packed TDNN weights
-  float* Wf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // [taps*cinP, coutP]
-  float* Wb[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // [taps*coutP, cinP]
-  float* Wfk[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // K-major copies for the tensor-core path: [coutP, taps*cinP]
-  float* Wbk[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [cinP, taps*coutP]
-  float* bias[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; // [coutP] (BN of the previous layer folded)
-  float* bn5_mean = nullptr; float* bn5_istd = nullptr;           // [C5P]
-  float* Wfc = nullptr; float* Wfc_b = nullptr; float* bfc = nullptr;     // fc1: [3072,512], [512,3072], [512]
-  float* Wlda = nullptr; float* Wlda_b = nullptr; float* blda = nullptr;  // LDA: [512,Lp], [Lp,512], [Lp]
-  // K-major copies for the tensor-core path ([N, K]): transposes of the four matrices above
-  float* Wfc_k = nullptr; float* Wfc_bk = nullptr; float* Wlda_k = nullptr; float* Wlda_bk = nullptr;
-  float* plda_mean = nullptr; float* plda_T = nullptr; float* plda_Tt = nullptr;
-  float* inv_psi1 = nullptr; float* psi_ratio = nullptr; float* inv_var_given = nullptr;
-  float* enroll = nullptr;
-  SgHeadConst H;
-  std::vector<void*> allocs;
-};
-
-static int dev_upload(sg_handle* h, float** dst, const std::vector<float>& src) {
+int sg_dev_upload(sg_handle* h, float** dst, const std::vector<float>& src) {
   SG_CUDA_CHECK(cudaMalloc((void**)dst, src.size() * sizeof(float)));
   h->allocs.push_back(*dst);
   SG_CUDA_CHECK(cudaMemcpy(*dst, src.data(), src.size() * sizeof(float), cudaMemcpyHostToDevice));
   return SG_OK;
 }
-#define SG_TRY(expr) do { int _r = (expr); if (_r != SG_OK) return _r; } while (0)
 
 extern "C" int sg_create(sg_handle** out, int device) {
   if (!out) { sg_set_error("sg_create: out is NULL"); return SG_EINVAL; }
@@ -123,6 +72,7 @@ extern "C" void sg_destroy(sg_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   for (cudaEvent_t e : h->prof.ev) cudaEventDestroy(e);
+  sg_audionet_free(h);
   for (void* p : h->allocs) cudaFree(p);
   delete h;
 }
@@ -156,7 +106,6 @@ extern "C" int sg_profile_read(sg_handle* h, int category, double* total_ms, lon
 extern "C" const char* sg_profile_name(int category) {
   return (category >= 0 && category < SG_PROF_COUNT) ? kProfNames[category] : "";
 }
-#define PROF(h, c, st, call) do { cudaEvent_t* _pe = (h)->prof.begin((c), (st)); int _pr = (call); (h)->prof.end(_pe, (st)); if (_pr != SG_OK) return _pr; } while (0)
 
 extern "C" long long sg_launch_count(const sg_handle* h) { return h ? h->launches : 0; }
 extern "C" void sg_reset_launch_count(sg_handle* h) { if (h) h->launches = 0; }
@@ -201,17 +150,17 @@ extern "C" int sg_load_xv(sg_handle* h, const sg_xv_weights* w) {
         }
       bias[o] = (float)bacc;
     }
-    SG_TRY(dev_upload(h, &h->Wf[l], Wf));
-    SG_TRY(dev_upload(h, &h->Wb[l], Wb));
-    SG_TRY(dev_upload(h, &h->Wfk[l], Wfk));
-    SG_TRY(dev_upload(h, &h->Wbk[l], Wbk));
-    SG_TRY(dev_upload(h, &h->bias[l], bias));
+    SG_TRY(sg_dev_upload(h, &h->Wf[l], Wf));
+    SG_TRY(sg_dev_upload(h, &h->Wb[l], Wb));
+    SG_TRY(sg_dev_upload(h, &h->Wfk[l], Wfk));
+    SG_TRY(sg_dev_upload(h, &h->Wbk[l], Wbk));
+    SG_TRY(sg_dev_upload(h, &h->bias[l], bias));
   }
   {
     std::vector<float> m5(SG_C5P, 0.f), i5(SG_C5P, 0.f);
     for (int c = 0; c < SG_C5; ++c) { m5[c] = w->bn_mean[4][c]; i5[c] = (float)(1.0 / sqrt((double)w->bn_var[4][c] + (double)eps)); }
-    SG_TRY(dev_upload(h, &h->bn5_mean, m5));
-    SG_TRY(dev_upload(h, &h->bn5_istd, i5));
+    SG_TRY(sg_dev_upload(h, &h->bn5_mean, m5));
+    SG_TRY(sg_dev_upload(h, &h->bn5_istd, i5));
   }
   {  // fc1 (xvecTDNN.py:36, :63) with emb_mean folded into the bias (xvector_extract.py:41-43)
     std::vector<float> Wfc((size_t)SG_STATS * SG_EMB, 0.f), Wfcb((size_t)SG_EMB * SG_STATS, 0.f), b(SG_EMB);
@@ -224,11 +173,11 @@ extern "C" int sg_load_xv(sg_handle* h, const sg_xv_weights* w) {
       }
       b[o] = w->fc1_b[o] - w->emb_mean[o];
     }
-    SG_TRY(dev_upload(h, &h->Wfc, Wfc));
-    SG_TRY(dev_upload(h, &h->Wfc_b, Wfcb));
+    SG_TRY(sg_dev_upload(h, &h->Wfc, Wfc));
+    SG_TRY(sg_dev_upload(h, &h->Wfc_b, Wfcb));
     h->Wfc_k = h->Wfc_b;    // [512, 3072] is the K-major form of the forward matrix
     h->Wfc_bk = h->Wfc;     // and vice versa
-    SG_TRY(dev_upload(h, &h->bfc, b));
+    SG_TRY(sg_dev_upload(h, &h->bfc, b));
   }
   {  // LDA (model/iv_plda.py:423-435): [L, 513], offset in the last column
     std::vector<float> Wl((size_t)SG_EMB * Lp, 0.f), Wlb((size_t)Lp * SG_EMB, 0.f), b(Lp, 0.f);
@@ -240,11 +189,11 @@ extern "C" int sg_load_xv(sg_handle* h, const sg_xv_weights* w) {
       }
       b[i] = w->lda[(size_t)i * (SG_EMB + 1) + SG_EMB];
     }
-    SG_TRY(dev_upload(h, &h->Wlda, Wl));
-    SG_TRY(dev_upload(h, &h->Wlda_b, Wlb));
+    SG_TRY(sg_dev_upload(h, &h->Wlda, Wl));
+    SG_TRY(sg_dev_upload(h, &h->Wlda_b, Wlb));
     h->Wlda_k = h->Wlda_b;  // [Lp, 512]
     h->Wlda_bk = h->Wlda;   // [512, Lp]
-    SG_TRY(dev_upload(h, &h->blda, b));
+    SG_TRY(sg_dev_upload(h, &h->blda, b));
   }
   {  // PLDA (plda.py:27-51, :140-190)
     std::vector<float> mean(w->plda_mean, w->plda_mean + L), T(w->plda_transform, w->plda_transform + (size_t)L * L);
@@ -261,14 +210,14 @@ extern "C" int sg_load_xv(sg_handle* h, const sg_xv_weights* w) {
       ld_given += logf(vg);
       ld_without += logf(psi + 1.0f);
     }
-    SG_TRY(dev_upload(h, &h->plda_mean, mean));
-    SG_TRY(dev_upload(h, &h->plda_T, T));
-    SG_TRY(dev_upload(h, &h->plda_Tt, Tt));
-    SG_TRY(dev_upload(h, &h->inv_psi1, ip));
-    SG_TRY(dev_upload(h, &h->psi_ratio, pr));
-    SG_TRY(dev_upload(h, &h->inv_var_given, ivg));
+    SG_TRY(sg_dev_upload(h, &h->plda_mean, mean));
+    SG_TRY(sg_dev_upload(h, &h->plda_T, T));
+    SG_TRY(sg_dev_upload(h, &h->plda_Tt, Tt));
+    SG_TRY(sg_dev_upload(h, &h->inv_psi1, ip));
+    SG_TRY(sg_dev_upload(h, &h->psi_ratio, pr));
+    SG_TRY(sg_dev_upload(h, &h->inv_var_given, ivg));
     std::vector<float> en(w->enroll, w->enroll + (size_t)S * L);
-    SG_TRY(dev_upload(h, &h->enroll, en));
+    SG_TRY(sg_dev_upload(h, &h->enroll, en));
     h->H.L = L; h->H.Lp = Lp;
     h->H.plda_mean = h->plda_mean; h->H.plda_T = h->plda_T; h->H.plda_Tt = h->plda_Tt;
     h->H.inv_psi1 = h->inv_psi1; h->H.psi_ratio = h->psi_ratio; h->H.inv_var_given = h->inv_var_given;
@@ -329,7 +278,7 @@ extern "C" size_t sg_pgd_ws_bytes(const sg_handle* h, int B, int N) {
 // ---------------------------------------------------------------------------------------------
 // argument checks
 // ---------------------------------------------------------------------------------------------
-static int check_handle(sg_handle* h, bool need_xv) {
+int sg_check_handle(sg_handle* h, bool need_xv) {
   if (!h) { sg_set_error("null handle"); return SG_EINVAL; }
   if (need_xv && !h->xv_loaded) { sg_set_error("x-vector weights not loaded (call sg_load_xv first)"); return SG_ESTATE; }
   return SG_OK;
@@ -352,7 +301,7 @@ extern "C" int sg_num_frames(int N) { return (N + SG_SHIFT / 2) / SG_SHIFT; }
 // ---------------------------------------------------------------------------------------------
 extern "C" int sg_mfcc_fwd(sg_handle* h, const float* x, int B, int N, int dither_mode, const float* dither,
                            uint64_t seed, uint64_t pass, float* raw, int ld, sg_stream stream) {
-  SG_TRY(check_handle(h, false)); SG_TRY(check_wave(B, N)); SG_TRY(check_dither(dither_mode, dither));
+  SG_TRY(sg_check_handle(h, false)); SG_TRY(check_wave(B, N)); SG_TRY(check_dither(dither_mode, dither));
   if (!x || !raw || ld < SG_NCEP || ld > 32) { sg_set_error("sg_mfcc_fwd: bad pointer or ld (%d not in [30,32])", ld); return SG_EINVAL; }
   h->launches += 1;
   PROF(h, SG_PROF_MFCC_FWD, (cudaStream_t)stream, sg_feat_fwd_launch(h->d_tables, x, B, N, sg_num_frames(N), dither_mode, dither, seed, pass, raw, ld, (cudaStream_t)stream));
@@ -362,7 +311,7 @@ extern "C" int sg_mfcc_fwd(sg_handle* h, const float* x, int B, int N, int dithe
 extern "C" int sg_mfcc_bwd(sg_handle* h, const float* x, int B, int N, int dither_mode, const float* dither,
                            uint64_t seed, uint64_t pass, const float* draw, int ld, float* grad, float scale,
                            int accumulate, sg_stream stream) {
-  SG_TRY(check_handle(h, false)); SG_TRY(check_wave(B, N)); SG_TRY(check_dither(dither_mode, dither));
+  SG_TRY(sg_check_handle(h, false)); SG_TRY(check_wave(B, N)); SG_TRY(check_dither(dither_mode, dither));
   if (!x || !draw || !grad || ld < SG_NCEP || ld > 32) { sg_set_error("sg_mfcc_bwd: bad pointer or ld (%d)", ld); return SG_EINVAL; }
   h->launches += 1;
   PROF(h, SG_PROF_MFCC_BWD, (cudaStream_t)stream, sg_feat_bwd_launch(h->d_tables, x, B, N, sg_num_frames(N), dither_mode, dither, seed, pass, draw, ld, grad,
@@ -371,21 +320,21 @@ extern "C" int sg_mfcc_bwd(sg_handle* h, const float* x, int B, int N, int dithe
 }
 
 extern "C" int sg_dither_fill(sg_handle* h, int B, int N, uint64_t seed, uint64_t pass, float* out, sg_stream stream) {
-  SG_TRY(check_handle(h, false)); SG_TRY(check_wave(B, N));
+  SG_TRY(sg_check_handle(h, false)); SG_TRY(check_wave(B, N));
   if (!out) { sg_set_error("sg_dither_fill: null output"); return SG_EINVAL; }
   h->launches += 1;
   return sg_dither_fill_launch(B, sg_num_frames(N), seed, pass, out, (cudaStream_t)stream);
 }
 
 extern "C" int sg_cmvn_fwd(sg_handle* h, const float* raw, int ld_in, float* out, int ld_out, int B, int T, sg_stream stream) {
-  SG_TRY(check_handle(h, false));
+  SG_TRY(sg_check_handle(h, false));
   if (!raw || !out || B < 1 || T < 1 || ld_in < SG_NCEP || ld_out < SG_NCEP || ld_in > 32 || ld_out > 32) { sg_set_error("sg_cmvn_fwd: bad argument"); return SG_EINVAL; }
   h->launches += 1;
   PROF(h, SG_PROF_CMVN, (cudaStream_t)stream, sg_cmvn_launch(raw, ld_in, out, ld_out, B, T, 0, (cudaStream_t)stream));
   return SG_OK;
 }
 extern "C" int sg_cmvn_bwd(sg_handle* h, const float* dout, int ld_in, float* draw, int ld_out, int B, int T, sg_stream stream) {
-  SG_TRY(check_handle(h, false));
+  SG_TRY(sg_check_handle(h, false));
   if (!dout || !draw || B < 1 || T < 1 || ld_in < SG_NCEP || ld_out < SG_NCEP || ld_in > 32 || ld_out > 32) { sg_set_error("sg_cmvn_bwd: bad argument"); return SG_EINVAL; }
   h->launches += 1;
   PROF(h, SG_PROF_CMVN, (cudaStream_t)stream, sg_cmvn_launch(dout, ld_in, draw, ld_out, B, T, 1, (cudaStream_t)stream));
@@ -393,7 +342,7 @@ extern "C" int sg_cmvn_bwd(sg_handle* h, const float* dout, int ld_in, float* dr
 }
 
 // ---- TDNN -------------------------------------------------------------------------------------
-static int run_conv(sg_handle* h, const SgConvArgs& a, bool tensor_ok, int cat, cudaStream_t st) {
+int sg_run_conv(sg_handle* h, const SgConvArgs& a, bool tensor_ok, int cat, cudaStream_t st) {
   h->launches += 1;
   if (h->precision != SG_PREC_FP32 && tensor_ok) { PROF(h, cat, st, sg_conv_tc(a, h->precision, st)); return SG_OK; }
   PROF(h, cat, st, sg_conv_simt(a, st));
@@ -418,7 +367,7 @@ static int embed_fwd(sg_handle* h, const float* feat, int B, int T, const XvWs& 
     a.A = in; a.lda = lda; a.W = h->Wf[l]; a.Wk = h->Wfk[l]; a.bias = h->bias[l]; a.out = w.r[l]; a.ldo = kCoutP[l];
     a.rows = R; a.N = kCoutP[l]; a.cin = kCinP[l]; a.taps = kTaps[l]; a.tap_step = kDil[l];
     a.epilogue = SG_EPI_BIAS_RELU; a.T = T; a.t_valid = tv[l];
-    SG_TRY(run_conv(h, a, true, SG_PROF_TDNN_FWD, st));
+    SG_TRY(sg_run_conv(h, a, true, SG_PROF_TDNN_FWD, st));
     in = w.r[l]; lda = kCoutP[l];
   }
   h->launches += 1;
@@ -428,10 +377,10 @@ static int embed_fwd(sg_handle* h, const float* feat, int B, int T, const XvWs& 
     memset(&a, 0, sizeof(a));
     a.A = w.stats; a.lda = SG_STATS; a.W = h->Wfc; a.Wk = h->Wfc_k; a.bias = h->bfc; a.out = w.e1; a.ldo = SG_EMB;
     a.rows = B; a.N = SG_EMB; a.cin = SG_STATS; a.taps = 1; a.tap_step = 0; a.epilogue = SG_EPI_BIAS; a.T = 1;
-    SG_TRY(run_conv(h, a, true, SG_PROF_HEAD_GEMM, st));
+    SG_TRY(sg_run_conv(h, a, true, SG_PROF_HEAD_GEMM, st));
     a.A = w.e1; a.lda = SG_EMB; a.W = h->Wlda; a.Wk = h->Wlda_k; a.bias = h->blda; a.out = w.e2; a.ldo = h->Lp;
     a.N = h->Lp; a.cin = SG_EMB;
-    SG_TRY(run_conv(h, a, true, SG_PROF_HEAD_GEMM, st));
+    SG_TRY(sg_run_conv(h, a, true, SG_PROF_HEAD_GEMM, st));
   }
   h->launches += 1;
   PROF(h, SG_PROF_HEAD, st, sg_head_fwd_launch(h->H, w.e2, B, w.tsave, w.scal, emb, st));
@@ -449,9 +398,9 @@ static int embed_bwd(sg_handle* h, const float* demb, int B, int T, const XvWs& 
     memset(&a, 0, sizeof(a));
     a.A = w.de2; a.lda = h->Lp; a.W = h->Wlda_b; a.Wk = h->Wlda_bk; a.out = w.de1; a.ldo = SG_EMB;
     a.rows = B; a.N = SG_EMB; a.cin = h->Lp; a.taps = 1; a.epilogue = SG_EPI_NONE; a.T = 1;
-    SG_TRY(run_conv(h, a, true, SG_PROF_HEAD_GEMM, st));
+    SG_TRY(sg_run_conv(h, a, true, SG_PROF_HEAD_GEMM, st));
     a.A = w.de1; a.lda = SG_EMB; a.W = h->Wfc_b; a.Wk = h->Wfc_bk; a.out = w.dstats; a.ldo = SG_STATS; a.N = SG_STATS; a.cin = SG_EMB;
-    SG_TRY(run_conv(h, a, true, SG_PROF_HEAD_GEMM, st));
+    SG_TRY(sg_run_conv(h, a, true, SG_PROF_HEAD_GEMM, st));
   }
   h->launches += 1;
   PROF(h, SG_PROF_POOL, st, sg_pool_bwd_launch(w.r[4], B, T, tv[4], h->bn5_istd, w.dstats, w.save_mean, w.save_std, w.G0, st));
@@ -467,24 +416,24 @@ static int embed_bwd(sg_handle* h, const float* demb, int B, int T, const XvWs& 
       float* out = bufs[(4 - l) & 1];
       a.out = out; a.ldo = kCinP[l]; a.N = kCinP[l];
       a.epilogue = SG_EPI_MASK; a.mask = w.r[l - 1]; a.ldmask = kCoutP[l - 1]; a.t_valid = tv[l - 1];
-      SG_TRY(run_conv(h, a, true, SG_PROF_TDNN_BWD, st));
+      SG_TRY(sg_run_conv(h, a, true, SG_PROF_TDNN_BWD, st));
       gin = out;
     } else {
       a.out = dfeat; a.ldo = SG_FLD; a.N = SG_FLD; a.epilogue = SG_EPI_NONE;
-      SG_TRY(run_conv(h, a, true, SG_PROF_TDNN_BWD, st));
+      SG_TRY(sg_run_conv(h, a, true, SG_PROF_TDNN_BWD, st));
     }
   }
   return SG_OK;
 }
 
 extern "C" int sg_xv_embed_fwd(sg_handle* h, const float* feat, int B, int T, void* ws, float* emb, sg_stream stream) {
-  SG_TRY(check_handle(h, true));
+  SG_TRY(sg_check_handle(h, true));
   if (!feat || !ws || !emb || B < 1) { sg_set_error("sg_xv_embed_fwd: bad argument"); return SG_EINVAL; }
   XvWs w = xv_ws_layout(ws, B, T, h->Lp, h->L, h->S, false, 0);
   return embed_fwd(h, feat, B, T, w, emb, (cudaStream_t)stream);
 }
 extern "C" int sg_xv_embed_bwd(sg_handle* h, const float* demb, int B, int T, void* ws, float* dfeat, sg_stream stream) {
-  SG_TRY(check_handle(h, true));
+  SG_TRY(sg_check_handle(h, true));
   if (!demb || !ws || !dfeat || B < 1) { sg_set_error("sg_xv_embed_bwd: bad argument"); return SG_EINVAL; }
   XvWs w = xv_ws_layout(ws, B, T, h->Lp, h->L, h->S, false, 0);
   return embed_bwd(h, demb, B, T, w, dfeat, (cudaStream_t)stream);
@@ -494,7 +443,7 @@ extern "C" int sg_xv_embed_bwd(sg_handle* h, const float* demb, int B, int T, vo
 extern "C" int sg_debug_conv(sg_handle* h, int precision, const float* A, int lda, const float* W, const float* Wk,
                              const float* bias, float* out, int ldo, int rows, int N, int cin, int taps, int tap_step,
                              int epilogue, const float* mask, int ldmask, int T, int t_valid, sg_stream stream) {
-  SG_TRY(check_handle(h, false));
+  SG_TRY(sg_check_handle(h, false));
   if (!A || !out || rows < 1 || N < 1) { sg_set_error("sg_debug_conv: bad argument"); return SG_EINVAL; }
   SgConvArgs a;
   memset(&a, 0, sizeof(a));
@@ -508,7 +457,7 @@ extern "C" int sg_debug_conv(sg_handle* h, int precision, const float* A, int ld
 // ---- scoring / loss ----------------------------------------------------------------------------
 extern "C" int sg_plda_score_fwd(sg_handle* h, const float* emb, int B, const float* enroll, int S, float threshold,
                                  float* scores, int64_t* decisions, sg_stream stream) {
-  SG_TRY(check_handle(h, true));
+  SG_TRY(sg_check_handle(h, true));
   if (!emb || !scores || B < 1) { sg_set_error("sg_plda_score_fwd: bad argument"); return SG_EINVAL; }
   if (!enroll) { enroll = h->enroll; S = h->S; }
   if (S < 1) { sg_set_error("sg_plda_score_fwd: S must be >= 1"); return SG_EINVAL; }
@@ -518,7 +467,7 @@ extern "C" int sg_plda_score_fwd(sg_handle* h, const float* emb, int B, const fl
 }
 extern "C" int sg_plda_score_bwd(sg_handle* h, const float* emb, const float* dscores, int B, const float* enroll, int S,
                                  float* demb, sg_stream stream) {
-  SG_TRY(check_handle(h, true));
+  SG_TRY(sg_check_handle(h, true));
   if (!emb || !dscores || !demb || B < 1) { sg_set_error("sg_plda_score_bwd: bad argument"); return SG_EINVAL; }
   if (!enroll) { enroll = h->enroll; S = h->S; }
   h->launches += 1;
@@ -533,7 +482,7 @@ static int check_loss(const sg_loss_params* lp, int S) {
 }
 extern "C" int sg_loss_fwd_bwd(sg_handle* h, const float* scores, const int64_t* y, int B, int S, const sg_loss_params* lp,
                                float* loss, float* dscores, sg_stream stream) {
-  SG_TRY(check_handle(h, false)); SG_TRY(check_loss(lp, S));
+  SG_TRY(sg_check_handle(h, false)); SG_TRY(check_loss(lp, S));
   if (!scores || !y || !loss || B < 1 || S < 1) { sg_set_error("sg_loss_fwd_bwd: bad argument"); return SG_EINVAL; }
   h->launches += 1;
   PROF(h, SG_PROF_LOSS, (cudaStream_t)stream, sg_loss_launch(scores, (const long long*)y, B, S, *lp, loss, dscores, (cudaStream_t)stream));
@@ -542,7 +491,7 @@ extern "C" int sg_loss_fwd_bwd(sg_handle* h, const float* scores, const int64_t*
 
 extern "C" int sg_step_linf(sg_handle* h, float* x, const float* x0, const float* grad, size_t n, float step,
                             float grad_sign, float eps, sg_stream stream) {
-  SG_TRY(check_handle(h, false));
+  SG_TRY(sg_check_handle(h, false));
   if (!x || !x0 || !grad) { sg_set_error("sg_step_linf: null pointer"); return SG_EINVAL; }
   h->launches += 1;
   PROF(h, SG_PROF_STEP, (cudaStream_t)stream, sg_step_linf_launch(x, x0, grad, n, step * grad_sign, eps, (cudaStream_t)stream));
@@ -565,7 +514,7 @@ static int forward_pass(sg_handle* h, const float* x, int B, int N, int m, int m
 extern "C" int sg_xv_forward(sg_handle* h, const float* x, int B, int N, int dither_mode, const float* dither,
                              uint64_t seed, uint64_t pass, float decision_threshold, void* ws, float* scores,
                              int64_t* decisions, float* emb, sg_stream stream) {
-  SG_TRY(check_handle(h, true)); SG_TRY(check_wave(B, N)); SG_TRY(check_dither(dither_mode, dither));
+  SG_TRY(sg_check_handle(h, true)); SG_TRY(check_wave(B, N)); SG_TRY(check_dither(dither_mode, dither));
   if (!x || !ws || !scores) { sg_set_error("sg_xv_forward: bad argument"); return SG_EINVAL; }
   const int m = sg_num_frames(N);
   XvWs w = xv_ws_layout(ws, B, m, h->Lp, h->L, h->S, true, N);
@@ -576,7 +525,7 @@ extern "C" int sg_xv_forward(sg_handle* h, const float* x, int B, int N, int dit
 extern "C" int sg_pgd_run(sg_handle* h, float* x_adv, const float* x0, const int64_t* y, const float* dither, int B, int N,
                           const sg_pgd_params* p, void* ws, int64_t* decisions, float* scores, float* loss_hist,
                           sg_stream stream) {
-  SG_TRY(check_handle(h, true)); SG_TRY(check_wave(B, N));
+  SG_TRY(sg_check_handle(h, true)); SG_TRY(check_wave(B, N));
   if (!x_adv || !x0 || !y || !p || !ws) { sg_set_error("sg_pgd_run: null argument"); return SG_EINVAL; }
   SG_TRY(check_dither(p->dither_mode, dither)); SG_TRY(check_loss(&p->loss, h->S));
   if (p->max_iter < 0 || p->eot_size < 1) { sg_set_error("sg_pgd_run: max_iter >= 0 and eot_size >= 1 required"); return SG_EINVAL; }

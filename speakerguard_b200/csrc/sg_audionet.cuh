@@ -1,0 +1,41 @@
+// Internal declarations for the AudioNet path (sg_audionet.cu / sg_api_audionet.cu).
+#pragma once
+#include "sg_common.cuh"
+
+#define AN_NFFT 1024
+#define AN_HOP 160
+#define AN_WIN 800
+#define AN_WOFF 112                 // (1024 - 800) / 2: the window is centred in the FFT frame
+#define AN_MELS 32
+#define AN_BINS 513
+#define AN_MELW 1152
+#define SG_CW2_CHUNKS 16
+
+struct alignas(16) SgAnTables {
+  float window[AN_WIN];
+  float2 twA[8][2][32];
+  float2 twB[8][2][32];
+  float2 twU[16][32];
+  int mel_lo[32], mel_len[32], mel_off[32];
+  float mel_w[AN_MELW];
+  int bin_c0[512], bin_c1[512];
+  float bin_w0[512], bin_w1[512];
+  int mel_maxlen;
+};
+
+int sg_an_tables_build(SgAnTables* host_out);
+int sg_an_init();
+int sg_an_logmel_fwd_launch(const SgAnTables* dT, const float* x, int B, int N, int T, float* feat, cudaStream_t st);
+int sg_an_logmel_bwd_launch(const SgAnTables* dT, const float* x, int B, int N, int T, const float* dfeat, float* dgw,
+                            float* dx, float scale, int accumulate, cudaStream_t st);
+int sg_maxpool2_fwd_launch(const float* in, float* out, int B, int T, int C, cudaStream_t st);
+int sg_maxpool2_bwd_launch(const float* in, const float* dout, float* din, int B, int T, int C, cudaStream_t st);
+int sg_globalmax_fwd_launch(const float* in, float* out, int* arg, int B, int T, int Tv, int C, cudaStream_t st);
+int sg_globalmax_bwd_launch(const float* in, const float* dout, const int* arg, float* din, int B, int T, int C, cudaStream_t st);
+int sg_argmax_rows_launch(const float* s, long long* dec, int B, int S, float threshold, cudaStream_t st);
+int sg_cw2_prepare_launch(const float* x, const float* w, float* inp, float* l2part, float* loss2, int B, int N, cudaStream_t st);
+int sg_cw2_adam_launch(float* w, float* m, float* v, const float* x, const float* inp, const float* gmodel, const float* cst,
+                       int B, int N, float lr, int step, cudaStream_t st);
+int sg_cw2_track_launch(const float* inp, float* best_x, const float* loss1, const float* loss2, const long long* dec,
+                        float* best_l2, long long* best_score, float* gbest_l2, long long* gbest_score, int B, int N, cudaStream_t st);
+int sg_cw2_search_update_launch(float* cst, float* lower, float* upper, const long long* best_score, int B, cudaStream_t st);

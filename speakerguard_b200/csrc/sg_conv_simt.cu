@@ -32,13 +32,16 @@ conv_simt_kernel(SgConvArgs a) {
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
   const int kchunks = a.cin / BK;
+  const int a_t = a.same_utt ? (p0 + a_row) % a.T : 0;          // frame index of this loader's row
   const int nk = a.taps * kchunks;
 
   float4 ra[2], rb[2];
   auto gload = [&](int kt) {
     const int tap = kt / kchunks, c0 = (kt - tap * kchunks) * BK;
-    const long long sr = (long long)p0 + a_row + (long long)tap * a.tap_step;
-    if (sr >= 0 && sr < a.rows) {
+    const int off = a.tap_base + tap * a.tap_step;
+    const long long sr = (long long)p0 + a_row + off;
+    const bool inside = !a.same_utt || (a_t + off >= 0 && a_t + off < a.T);
+    if (sr >= 0 && sr < a.rows && inside) {
       const float4* src = reinterpret_cast<const float4*>(a.A + sr * a.lda + c0 + a_k);
       ra[0] = __ldg(src); ra[1] = __ldg(src + 1);
     } else {

@@ -280,6 +280,7 @@ static int make_map_f32(CUtensorMap* m, const float* base, uint64_t rows, uint64
 // uses a.Wk, the K-major copy of the weights: [N][taps*cin]
 int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
   if (precision != SG_PREC_TF32) { sg_set_error("tensor-core path: only SG_PREC_TF32 is built (fp32 storage)"); return SG_EUNSUPPORTED; }
+  if (a.same_utt || a.tap_base != 0) { sg_set_error("sg_conv_tc: 'same' padding is only built for the FFMA path"); return SG_EUNSUPPORTED; }
   int r = tc_init();
   if (r != SG_OK) return r;
   if (a.cin % TC_BK != 0 || a.N % 32 != 0 || a.lda % 4 != 0 || a.ldo % 4 != 0 || (a.epilogue == SG_EPI_MASK && a.ldmask % 4 != 0)) {

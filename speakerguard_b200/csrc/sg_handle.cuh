@@ -1,0 +1,67 @@
+// Handle layout and small helpers shared by the API translation units (sg_api.cu, sg_api_audionet.cu).
+#pragma once
+#include <vector>
+
+#include "sg_audionet.cuh"
+#include "sg_common.cuh"
+#include "sg_head.cuh"
+
+// per-category device timing (CUDA events on the launching stream); off by default
+struct SgProf {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;      // pairs (start, stop)
+  std::vector<int> cat;             // category of pair i
+  size_t used = 0;                  // pairs recorded since the last reset
+  cudaEvent_t* begin(int c, cudaStream_t st) {
+    if (!on) return nullptr;
+    if (used == cat.size()) {
+      cudaEvent_t a, b;
+      if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return nullptr;
+      ev.push_back(a); ev.push_back(b); cat.push_back(c);
+    }
+    cat[used] = c;
+    cudaEventRecord(ev[2 * used], st);
+    return &ev[2 * used + 1];
+  }
+  void end(cudaEvent_t* stop, cudaStream_t st) {
+    if (!stop) return;
+    cudaEventRecord(*stop, st);
+    ++used;
+  }
+};
+
+struct sg_handle {
+  SgProf prof;
+  int device = 0;
+  int precision = SG_PREC_FP32;
+  long long launches = 0;
+  SgFeatTables* d_tables = nullptr;
+  bool xv_loaded = false;
+  int L = 0, Lp = 0, S = 0;
+  // packed TDNN weights
+  float* Wf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // [taps*cinP, coutP]
+  float* Wb[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // [taps*coutP, cinP]
+  float* Wfk[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // K-major copies for the tensor-core path: [coutP, taps*cinP]
+  float* Wbk[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [cinP, taps*coutP]
+  float* bias[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; // [coutP] (BN of the previous layer folded)
+  float* bn5_mean = nullptr; float* bn5_istd = nullptr;           // [C5P]
+  float* Wfc = nullptr; float* Wfc_b = nullptr; float* bfc = nullptr;     // fc1: [3072,512], [512,3072], [512]
+  float* Wlda = nullptr; float* Wlda_b = nullptr; float* blda = nullptr;  // LDA: [512,Lp], [Lp,512], [Lp]
+  // K-major copies for the tensor-core path ([N, K]): transposes of the four matrices above
+  float* Wfc_k = nullptr; float* Wfc_bk = nullptr; float* Wlda_k = nullptr; float* Wlda_bk = nullptr;
+  float* plda_mean = nullptr; float* plda_T = nullptr; float* plda_Tt = nullptr;
+  float* inv_psi1 = nullptr; float* psi_ratio = nullptr; float* inv_var_given = nullptr;
+  float* enroll = nullptr;
+  SgHeadConst H;
+  std::vector<void*> allocs;
+  struct SgAudioNet* an = nullptr;   // AudioNet state (sg_api_audionet.cu)
+};
+
+
+#define SG_TRY(expr) do { int _r = (expr); if (_r != SG_OK) return _r; } while (0)
+#define PROF(h, c, st, call) do { cudaEvent_t* _pe = (h)->prof.begin((c), (st)); int _pr = (call); (h)->prof.end(_pe, (st)); if (_pr != SG_OK) return _pr; } while (0)
+
+int sg_dev_upload(sg_handle* h, float** dst, const std::vector<float>& src);
+int sg_check_handle(sg_handle* h, bool need_xv);
+int sg_run_conv(sg_handle* h, const SgConvArgs& a, bool tensor_ok, int cat, cudaStream_t st);
+void sg_audionet_free(sg_handle* h);

@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import LossParams, PgdParams, XvWeights, check
+from ._lib import AudioNetWeights, Cw2Params, LossParams, PgdParams, XvWeights, check
 
 FLD = 32  # internal feature row stride
 
@@ -116,6 +116,89 @@ class Engine:
         with torch.cuda.device(self.device):
             check(self.lib.sg_load_xv(self._h, C.byref(w)), "sg_load_xv")
         self.L, self.S = w.L, w.S
+
+    # ---- AudioNet ------------------------------------------------------------------------------
+    AN_CONVS = ["conv2", "conv3", "conv4", "conv5", "conv6", "conv7", "conv8"]
+
+    def load_audionet(self, p: Dict[str, torch.Tensor], bn_eps: float = 1e-5) -> None:
+        """p: 'conv1.weight/.bias', 'conv{2..8}.weight/.bias', '{name}.bn_mean/_var/_gamma/_beta' for
+        conv1..conv8, 'fc.weight/.bias'."""
+        keep = []
+
+        def host(name):
+            a = np.ascontiguousarray(p[name].detach().cpu().numpy().astype(np.float32))
+            keep.append(a)
+            return a.ctypes.data
+
+        w = AudioNetWeights()
+        w.conv1_w, w.conv1_b = host("conv1.weight"), host("conv1.bias")
+        for i, n in enumerate(self.AN_CONVS):
+            w.conv_w[i], w.conv_b[i] = host(f"{n}.weight"), host(f"{n}.bias")
+        for i, n in enumerate(["conv1"] + self.AN_CONVS):
+            w.bn_mean[i], w.bn_var[i] = host(f"{n}.bn_mean"), host(f"{n}.bn_var")
+            w.bn_gamma[i], w.bn_beta[i] = host(f"{n}.bn_gamma"), host(f"{n}.bn_beta")
+        w.fc_w, w.fc_b = host("fc.weight"), host("fc.bias")
+        w.num_class, w.bn_eps = int(p["fc.bias"].shape[0]), float(bn_eps)
+        with torch.cuda.device(self.device):
+            check(self.lib.sg_load_audionet(self._h, C.byref(w)), "sg_load_audionet")
+        self.an_classes = w.num_class
+        self.an_cp = int(self.lib.sg_audionet_num_class_padded(self._h))
+
+    def an_num_frames(self, N: int) -> int:
+        return int(self.lib.sg_audionet_num_frames(N))
+
+    def an_ws(self, B: int, N: int, for_cw2: bool = False) -> torch.Tensor:
+        return self.alloc_ws(self.lib.sg_audionet_ws_bytes(self._h, B, N, int(for_cw2)))
+
+    def an_logmel_fwd(self, x: torch.Tensor) -> torch.Tensor:
+        x = _f32c(x, self.device)
+        B, N = x.shape
+        feat = torch.empty(B, self.an_num_frames(N), 32, device=self.device, dtype=torch.float32)
+        check(self.lib.sg_audionet_logmel_fwd(self._h, _ptr(x), B, N, _ptr(feat), self.stream), "sg_audionet_logmel_fwd")
+        return feat
+
+    def an_logmel_bwd(self, x: torch.Tensor, dfeat: torch.Tensor, ws: Optional[torch.Tensor] = None) -> torch.Tensor:
+        x, dfeat = _f32c(x, self.device), _f32c(dfeat, self.device)
+        B, N = x.shape
+        if ws is None:
+            ws = self.an_ws(B, N)
+        dx = torch.empty(B, N, device=self.device, dtype=torch.float32)
+        check(self.lib.sg_audionet_logmel_bwd(self._h, _ptr(x), B, N, _ptr(dfeat), _ptr(ws), _ptr(dx), 1.0, 0, self.stream),
+              "sg_audionet_logmel_bwd")
+        return dx
+
+    def an_cnn_fwd(self, feat: torch.Tensor, N: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """feat [B,T,32] (T = an_num_frames(N)) -> (logits [B,C], workspace for an_cnn_bwd)."""
+        feat = _f32c(feat, self.device)
+        B = feat.shape[0]
+        ws = self.an_ws(B, N)
+        logits = torch.empty(B, self.an_cp, device=self.device, dtype=torch.float32)
+        check(self.lib.sg_audionet_cnn_fwd(self._h, _ptr(feat), B, N, _ptr(ws), _ptr(logits), self.stream), "sg_audionet_cnn_fwd")
+        return logits[:, :self.an_classes], ws
+
+    def an_cnn_bwd(self, dlogits: torch.Tensor, ws: torch.Tensor, B: int, N: int) -> torch.Tensor:
+        dl = torch.zeros(B, self.an_cp, device=self.device, dtype=torch.float32)
+        dl[:, :self.an_classes] = dlogits
+        dfeat = torch.empty(B, self.an_num_frames(N), 32, device=self.device, dtype=torch.float32)
+        check(self.lib.sg_audionet_cnn_bwd(self._h, _ptr(dl), B, N, _ptr(ws), _ptr(dfeat), self.stream), "sg_audionet_cnn_bwd")
+        return dfeat
+
+    def cw2_audionet_run(self, x: torch.Tensor, y: torch.Tensor, *, lp: LossParams, binary_search_steps: int, max_iter: int,
+                         stop_early: bool, stop_early_iter: int, lr: float, initial_const: float,
+                         decision_threshold: float = -math.inf):
+        """x [B,N] -> (best adversarial x [B,N], success [B] int64, final c [B])."""
+        x = _f32c(x, self.device)
+        y = y.to(device=self.device, dtype=torch.int64).contiguous()
+        B, N = x.shape
+        ws = self.an_ws(B, N, for_cw2=True)
+        best = torch.empty_like(x)
+        suc = torch.empty(B, device=self.device, dtype=torch.int64)
+        cst = torch.empty(B, device=self.device, dtype=torch.float32)
+        pp = Cw2Params(int(binary_search_steps), int(max_iter), int(bool(stop_early)), int(stop_early_iter), float(lr),
+                       float(initial_const), lp, float(decision_threshold))
+        check(self.lib.sg_cw2_audionet_run(self._h, _ptr(x), _ptr(y), B, N, C.byref(pp), _ptr(ws), _ptr(best), _ptr(suc),
+                                           _ptr(cst), self.stream), "sg_cw2_audionet_run")
+        return best, suc, cst
 
     # ---- stage ops -----------------------------------------------------------------------------
     def num_frames(self, N: int) -> int:

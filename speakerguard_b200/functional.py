@@ -84,3 +84,34 @@ class ScoreFn(torch.autograd.Function):
 
 DITHER_MODE = {"off": _lib.DITHER_OFF, "philox": _lib.DITHER_PHILOX, "torch": _lib.DITHER_TENSOR,
                "tensor": _lib.DITHER_TENSOR}
+
+
+class AnLogMelFn(torch.autograd.Function):
+    """x [B,N] -> AudioNet log-mel [B,T,32]  (sg_audionet_logmel_fwd / _bwd)."""
+
+    @staticmethod
+    def forward(ctx, x, eng: Engine):
+        x = x.contiguous()
+        ctx.eng = eng
+        ctx.save_for_backward(x)
+        return eng.an_logmel_fwd(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return ctx.eng.an_logmel_bwd(x, g.contiguous()), None
+
+
+class AnCnnFn(torch.autograd.Function):
+    """log-mel [B,T,32] -> logits [B,C]  (sg_audionet_cnn_fwd / _bwd); N = samples of the waveform."""
+
+    @staticmethod
+    def forward(ctx, feat, eng: Engine, N: int):
+        logits, ws = eng.an_cnn_fwd(feat.contiguous(), N)
+        ctx.eng, ctx.ws, ctx.dims = eng, ws, (feat.shape[0], N)
+        return logits.contiguous()
+
+    @staticmethod
+    def backward(ctx, g):
+        B, N = ctx.dims
+        return ctx.eng.an_cnn_bwd(g.contiguous(), ctx.ws, B, N), None, None

@@ -236,8 +236,8 @@ def audionet_case(out):
         x, _ = make_inputs(777, B, N)
         with torch.no_grad():
             pred = model(x).argmax(1)
-        y = (pred + 1) % 251
-        att = CW2(model, targeted=True, initial_const=1e3, binary_search_steps=2, max_iter=20,
+        y = pred
+        att = CW2(model, targeted=False, initial_const=1e2, binary_search_steps=2, max_iter=40,
                   stop_early=True, stop_early_iter=10, lr=1e-2, batch_size=B, verbose=0)
         import contextlib
         import io
@@ -245,8 +245,8 @@ def audionet_case(out):
             adv, success = att.attack(x, y)
         out.update({"cw2.B": B, "cw2.N": N, "cw2.x_cks": cks(x), "cw2.y": y.numpy(),
                     "cw2.adv": adv.detach()[:, 0].numpy(), "cw2.success": np.array(success)})
-        xa, suc, _ = O.cw2_attack(x[:, 0], y, lambda z: O.audionet_forward(z, p), targeted=True,
-                                  initial_const=1e3, binary_search_steps=2, max_iter=20, stop_early=True,
+        xa, suc, _ = O.cw2_attack(x[:, 0], y, lambda z: O.audionet_forward(z, p), targeted=False,
+                                  initial_const=1e2, binary_search_steps=2, max_iter=40, stop_early=True,
                                   stop_early_iter=10, lr=1e-2)
         print(f"[cw2] success {success}; oracle max|d adv| {float((xa - adv.detach()[:, 0]).abs().max()):.3e} "
               f"success equal: {suc == success}")
@@ -277,6 +277,11 @@ def feco_case(out):
 def main():
     torch.set_num_threads(8)
     out = {}
+    if "--only-audionet" in sys.argv:
+        audionet_case(out)
+        np.savez_compressed(os.path.join(HERE, "audionet_golden.npz"),
+                            **{k: v for k, v in out.items() if k.startswith(("an", "cw2"))})
+        return
     p = O.make_xv_params(seed=0)
     out["params_cks"] = np.float64(O.params_checksum(p))
     with tempfile.TemporaryDirectory() as tmp:

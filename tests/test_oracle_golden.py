@@ -120,3 +120,19 @@ def test_feco_conditional():
     tot = sum((O.feco_means(feat2, g["feco.ids"], int(g["feco.k"])) * w[i]).sum() for i in range(2))
     tot.backward()
     np.testing.assert_allclose(feat2.grad.numpy(), g["feco.grad"], atol=1e-6, rtol=1e-5)
+
+
+def test_cw2_oracle_vs_reference_outcome():
+    """CW2 is chaotic at the last bit (Adam's normalised steps), so the oracle is pinned on outcomes:
+    success flags equal, best-example L2 distortion within 15 %."""
+    g = np.load(os.path.join(G, "audionet_golden.npz"))
+    p = O.make_audionet_params(seed=0, num_class=251)
+    B, N = int(g["cw2.B"]), int(g["cw2.N"])
+    torch.manual_seed(777)
+    x = ((torch.rand(B, 1, N) * 2 - 1) * 0.5)[:, 0]
+    y = torch.tensor(g["cw2.y"])
+    xa, suc, _ = O.cw2_attack(x, y, lambda z: O.audionet_forward(z, p), targeted=False, initial_const=1e2,
+                              binary_search_steps=2, max_iter=40, stop_early=True, stop_early_iter=10, lr=1e-2)
+    assert suc == g["cw2.success"].tolist()
+    l2 = lambda a: (a - x).pow(2).sum(1).numpy()
+    np.testing.assert_allclose(l2(xa), l2(torch.tensor(g["cw2.adv"])), rtol=0.15)
