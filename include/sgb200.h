@@ -213,6 +213,19 @@ int sg_cw2_audionet_run(sg_handle* h, const float* x, const int64_t* y, int B, i
                         const sg_cw2_params* p, void* ws, float* best_x, int64_t* success,
                         float* final_const, sg_stream stream);
 
+/* ---- FeCo feature compression (replaces libKMCUDA) ----------------------------------------------
+ * sg_feco_kmeans: per-utterance Lloyd k-means over the frames (defense/feature_level.py:192-193:
+ *   kmeans_cuda(x, k, yinyang_t=0, metric='L2'); k-means++ seeding, stops when <= tol*n frames
+ *   change cluster, libKMCUDA's default tol 0.01).  feat [B,n,ld] -> ids [B,n] int32 in [0,k).
+ * sg_feco_means_fwd/bwd: the differentiable cluster means built from the ids (:202-217);
+ *   empty cluster i -> feat[i] when force.  out [B,k,dim], counts [B,k], dfeat [B,n,dim]. */
+int sg_feco_kmeans(sg_handle* h, const float* feat, int ld, int B, int n, int dim, int k, uint64_t seed,
+                   int max_iter, float tol, int32_t* ids, sg_stream stream);
+int sg_feco_means_fwd(sg_handle* h, const float* feat, int ld, const int32_t* ids, int B, int n, int dim,
+                      int k, int force, float* out, int32_t* counts, sg_stream stream);
+int sg_feco_means_bwd(sg_handle* h, const float* dout, const int32_t* ids, const int32_t* counts, int B,
+                      int n, int dim, int k, int force, float* dfeat, sg_stream stream);
+
 /* ---- test hook: one conv-as-GEMM launch on either arithmetic path -----------------------------
  * out[p,n] = epi(sum_{tap,c} A[p + tap*tap_step, c] * W[tap*cin + c, n]); W is [taps*cin, N]
  * (FFMA path), Wk its K-major copy [N, taps*cin] (tcgen05 path); epilogue 0 bias, 1 bias+ReLU,

@@ -93,6 +93,9 @@ PROTOTYPES = {
     "sg_audionet_cnn_bwd": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
     "sg_argmax_decide": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_float, _vp, _vp]),
     "sg_cw2_audionet_run": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.POINTER(Cw2Params), _vp, _vp, _vp, _vp, _vp]),
+    "sg_feco_kmeans": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_float, _vp, _vp]),
+    "sg_feco_means_fwd": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "sg_feco_means_bwd": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "sg_debug_conv": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.c_int, C.c_int, _vp, C.c_int, C.c_int, C.c_int, _vp]),
     "sg_profile_enable": (C.c_int, [_vp, C.c_int]),

@@ -353,3 +353,41 @@ extern "C" int sg_cw2_audionet_run(sg_handle* h, const float* x, const int64_t* 
   if (final_const) SG_CUDA_CHECK(cudaMemcpyAsync(final_const, w.cst, (size_t)B * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return SG_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// FeCo (defense/feature_level.py:18-50, :168-217)
+// ---------------------------------------------------------------------------------------------
+size_t sg_kmeans_smem(int n, int dim, int k);
+int sg_feco_kmeans_launch(const float* feat, int ld, int B, int n, int dim, int k, uint64_t seed, int max_iter, float tol,
+                          int* ids, cudaStream_t st);
+int sg_feco_means_fwd_launch(const float* feat, int ld_in, const int* ids, int B, int n, int dim, int k, int force,
+                             float* out, int ld_out, int* counts, cudaStream_t st);
+int sg_feco_means_bwd_launch(const float* dout, int ld_out, const int* ids, const int* counts, int B, int n, int dim, int k,
+                             int force, float* dfeat, int ld_in, cudaStream_t st);
+
+static int feco_check(sg_handle* h, int B, int n, int dim, int k) {
+  SG_TRY(sg_check_handle(h, false));
+  if (B < 1 || n < 1 || dim < 1 || dim > 32 || k < 1 || k > n) { sg_set_error("FeCo: need B >= 1, 1 <= k <= n, 1 <= dim <= 32 (B=%d n=%d dim=%d k=%d)", B, n, dim, k); return SG_EINVAL; }
+  return SG_OK;
+}
+extern "C" int sg_feco_kmeans(sg_handle* h, const float* feat, int ld, int B, int n, int dim, int k, uint64_t seed,
+                              int max_iter, float tol, int32_t* ids, sg_stream stream) {
+  SG_TRY(feco_check(h, B, n, dim, k));
+  if (!feat || !ids || ld < dim || max_iter < 1) { sg_set_error("sg_feco_kmeans: bad argument"); return SG_EINVAL; }
+  h->launches += 1;
+  return sg_feco_kmeans_launch(feat, ld, B, n, dim, k, seed, max_iter, tol, (int*)ids, (cudaStream_t)stream);
+}
+extern "C" int sg_feco_means_fwd(sg_handle* h, const float* feat, int ld, const int32_t* ids, int B, int n, int dim, int k,
+                                 int force, float* out, int32_t* counts, sg_stream stream) {
+  SG_TRY(feco_check(h, B, n, dim, k));
+  if (!feat || !ids || !out || !counts || ld < dim) { sg_set_error("sg_feco_means_fwd: bad argument"); return SG_EINVAL; }
+  h->launches += 1;
+  return sg_feco_means_fwd_launch(feat, ld, (const int*)ids, B, n, dim, k, force, out, dim, (int*)counts, (cudaStream_t)stream);
+}
+extern "C" int sg_feco_means_bwd(sg_handle* h, const float* dout, const int32_t* ids, const int32_t* counts, int B, int n, int dim,
+                                 int k, int force, float* dfeat, sg_stream stream) {
+  SG_TRY(feco_check(h, B, n, dim, k));
+  if (!dout || !ids || !counts || !dfeat) { sg_set_error("sg_feco_means_bwd: bad argument"); return SG_EINVAL; }
+  h->launches += 1;
+  return sg_feco_means_bwd_launch(dout, dim, (const int*)ids, (const int*)counts, B, n, dim, k, force, dfeat, dim, (cudaStream_t)stream);
+}

@@ -1,0 +1,63 @@
+"""FeCo, the feature-level compression defense (reference defense/feature_level.py:18-50,
+:168-217), with libKMCUDA / kmeans_pytorch replaced by the batched k-means kernel of libsgb200.
+
+``FeCo(feat, method='kmeans', param=0.5, other_param='L2')`` keeps the reference's signature:
+feat [B, frames, dim] -> [B, int(frames*param), dim], differentiable through the cluster means.
+All utterances of the batch are clustered by one kernel launch (the reference loops over
+utterances and clusters on the host side of a D2H/H2D round trip).  Like the reference the
+clustering is randomised (k-means++ seeding); pass ``seed`` for reproducibility.
+Not built: method='warped_kmeans' (sequential host algorithm, SURVEY.md marks it out of scope) and
+the 'cos' metric (the reference itself routes it away from kmeans_cuda).
+"""
+import itertools
+
+import torch
+
+from ..engine import default_engine
+
+_seed_counter = itertools.count(1)
+
+
+class _FeCoMeans(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, feat, ids, k, force):
+        eng = default_engine(feat.device)
+        out, counts = eng.feco_means_fwd(feat, ids, k, force)
+        ctx.eng, ctx.ids, ctx.counts, ctx.n, ctx.force = eng, ids, counts, feat.shape[1], force
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return ctx.eng.feco_means_bwd(g.contiguous(), ctx.ids, ctx.counts, ctx.n, ctx.force), None, None, None
+
+
+def kmeans_ids(feat, k, seed=None, max_iter=100, tol=0.01):
+    """Cluster ids [B, n] (int32) of every utterance's frames, L2 metric."""
+    eng = default_engine(feat.device)
+    if seed is None:
+        seed = (int(torch.initial_seed()) * 0x9E3779B97F4A7C15 + next(_seed_counter)) & 0xFFFFFFFFFFFFFFFF
+    return eng.feco_kmeans(feat.detach(), k, seed=seed, max_iter=max_iter, tol=tol)
+
+
+def FEATURE_COMPRESSION(feat, method='kmeans', param=0.5, other_param='L2', seed=None, ids=None):
+    if method != 'kmeans':
+        raise NotImplementedError('speakerguard_b200 FeCo supports method="kmeans" (warped_kmeans stays with the reference)')
+    if other_param != 'L2':
+        raise NotImplementedError('speakerguard_b200 FeCo supports the L2 metric only')
+    assert torch.is_tensor(feat)
+    B, n, dim = feat.shape
+    k = int(n * param)
+    force = B > 1                                   # feature_level.py:37
+    if ids is None:
+        ids = kmeans_ids(feat, k, seed=seed)
+    out = _FeCoMeans.apply(feat, ids, k, True)
+    if not force:                                   # batch of one: empty clusters are dropped, as in the reference
+        counts = torch.bincount(ids[0].long(), minlength=k)
+        if bool((counts == 0).any()):
+            out = out[:, counts > 0, :]
+    return out
+
+
+def FeCo(feat, method='kmeans', param=0.5, other_param='L2', seed=None, ids=None):
+    return FEATURE_COMPRESSION(feat, method, param, other_param, seed=seed, ids=ids)

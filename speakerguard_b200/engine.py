@@ -200,6 +200,34 @@ class Engine:
                                            _ptr(cst), self.stream), "sg_cw2_audionet_run")
         return best, suc, cst
 
+    # ---- FeCo ------------------------------------------------------------------------------------
+    def feco_kmeans(self, feat: torch.Tensor, k: int, seed: int = 0, max_iter: int = 100, tol: float = 0.01) -> torch.Tensor:
+        """feat [B,n,dim] -> cluster ids [B,n] int32."""
+        feat = _f32c(feat, self.device)
+        B, n, dim = feat.shape
+        ids = torch.empty(B, n, device=self.device, dtype=torch.int32)
+        check(self.lib.sg_feco_kmeans(self._h, _ptr(feat), dim, B, n, dim, k, seed, max_iter, tol, _ptr(ids), self.stream),
+              "sg_feco_kmeans")
+        return ids
+
+    def feco_means_fwd(self, feat: torch.Tensor, ids: torch.Tensor, k: int, force: bool = True):
+        feat = _f32c(feat, self.device)
+        ids = ids.to(device=self.device, dtype=torch.int32).contiguous()
+        B, n, dim = feat.shape
+        out = torch.empty(B, k, dim, device=self.device, dtype=torch.float32)
+        counts = torch.empty(B, k, device=self.device, dtype=torch.int32)
+        check(self.lib.sg_feco_means_fwd(self._h, _ptr(feat), dim, _ptr(ids), B, n, dim, k, int(force), _ptr(out), _ptr(counts),
+                                         self.stream), "sg_feco_means_fwd")
+        return out, counts
+
+    def feco_means_bwd(self, dout: torch.Tensor, ids: torch.Tensor, counts: torch.Tensor, n: int, force: bool = True):
+        dout = _f32c(dout, self.device)
+        B, k, dim = dout.shape
+        dfeat = torch.empty(B, n, dim, device=self.device, dtype=torch.float32)
+        check(self.lib.sg_feco_means_bwd(self._h, _ptr(dout), _ptr(ids), _ptr(counts), B, n, dim, k, int(force), _ptr(dfeat),
+                                         self.stream), "sg_feco_means_bwd")
+        return dfeat
+
     # ---- stage ops -----------------------------------------------------------------------------
     def num_frames(self, N: int) -> int:
         return int(self.lib.sg_num_frames(N))
