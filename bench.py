@@ -248,6 +248,10 @@ def main():
         peak, peak_note = peaks["bf16_tflops_sustained"] / 2.0, \
             f"fp32 FFMA parity mode is not on the tensor pipe; quoted against the tf32 tensor peak (half of bf16 sustained, {peak_src})"
 
+    if world > 1:
+        import torch.distributed as tdist
+        tdist.barrier()
+        tdist.destroy_process_group()
     if rank != 0:
         return
     out = {
@@ -273,6 +277,7 @@ def main():
         v, sample, cores = cpu_reference_throughput(p, N)
         out["cpu_baseline"] = {"value": v, "unit": "utt-iter/s", "cores": cores, "kind": "port", "sample": sample}
     print(json.dumps(out))
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":

@@ -10,6 +10,7 @@
 // The fp32 accumulator (128 lanes x BN columns) is double-buffered in TMEM (2 x 256 columns) so
 // the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "sg_common.cuh"
 
@@ -20,7 +21,8 @@
 #define TC_A_BYTES (TC_BM * TC_BK * 4)          // 16 KB
 #define TC_B_BYTES (TC_MAX_BN * TC_BK * 4)      // 32 KB
 #define TC_STAGE_BYTES (TC_A_BYTES + TC_B_BYTES)
-#define TC_SMEM_BYTES (TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/)
+#define TC_STG_BYTES (TC_BM * 32 * 4)            // 16 KB epilogue staging box (128 rows x 32 fp32), x2
+#define TC_SMEM_BYTES (TC_STAGES * TC_STAGE_BYTES + 2 * TC_STG_BYTES + 1024 /*align*/ + 256 /*barriers*/)
 #define TC_THREADS 192
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
@@ -52,6 +54,12 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const void* smem_src, const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"((uint64_t)map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -104,10 +112,12 @@ struct TcArgs {
 
 template <int KIND_BF16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcArgs a) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+               const __grid_constant__ CUtensorMap mapO, TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = (uint64_t*)(smem + TC_STAGES * TC_STAGE_BYTES);
+  uint8_t* stg = smem + TC_STAGES * TC_STAGE_BYTES;                 // 2 x 16 KB, 1024-byte aligned
+  uint64_t* bars = (uint64_t*)(stg + 2 * TC_STG_BYTES);
   uint64_t* full = bars;                       // [TC_STAGES]
   uint64_t* empty = bars + TC_STAGES;          // [TC_STAGES]
   uint64_t* tfull = bars + 2 * TC_STAGES;      // [2]
@@ -182,11 +192,211 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
   } else {
     // ===== epilogue: warps 2..5; a warp may only touch TMEM lanes 32*(warp%4) .. +31 =====
+    // TMEM -> registers -> bias / ReLU / mask -> swizzled smem staging box (128 rows x 32 cols) -> TMA store.
+    // (direct st.global from one-row-per-thread registers ran the short-K layers at ~2 TB/s of output.)
     const int q = warp & 3;
+    const int r_in = q * 32 + lane;                       // row within the tile
+    const bool issuer = (warp == 2 && lane == 0);
     int acc = 0; uint32_t acc_phase = 0;
+    uint32_t nstore = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
-      const int row = mt * TC_BM + q * 32 + lane;
+      const int row = mt * TC_BM + r_in;
+      const int n0 = nt * a.bn;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      bool row_ok = row < a.rows;
+      if (a.epilogue == SG_EPI_MASK) row_ok = row_ok && ((row % a.T) < a.t_valid);
+      for (int c = 0; c < a.bn; c += 32, ++nstore) {
+        float v[32];
+        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TC_MAX_BN + c), v);
+        const int col = n0 + c;
+        if (a.epilogue == SG_EPI_BIAS || a.epilogue == SG_EPI_BIAS_RELU) {
+          const float4* bp = reinterpret_cast<const float4*>(a.bias + col);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = __ldg(bp + j);
+            v[4 * j + 0] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+          }
+          if (a.epilogue == SG_EPI_BIAS_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+        } else if (a.epilogue == SG_EPI_MASK) {
+          if (row_ok) {
+            const float4* mp = reinterpret_cast<const float4*>(a.mask + (size_t)row * a.ldmask + col);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 m4 = __ldg(mp + j);
+              v[4 * j + 0] = m4.x > 0.f ? v[4 * j + 0] : 0.f;
+              v[4 * j + 1] = m4.y > 0.f ? v[4 * j + 1] : 0.f;
+              v[4 * j + 2] = m4.z > 0.f ? v[4 * j + 2] : 0.f;
+              v[4 * j + 3] = m4.w > 0.f ? v[4 * j + 3] : 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          }
+        }
+        uint8_t* buf = stg + (nstore & 1) * TC_STG_BYTES;
+        if (nstore >= 2) {                                  // the store that last read this buffer must have drained it
+          if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          epi_bar();
+        }
+        float4* srow = reinterpret_cast<float4*>(buf + r_in * 128);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) srow[j ^ (r_in & 7)] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        epi_bar();
+        if (issuer) tma_store_2d(buf, &mapO, col, mt * TC_BM);   // rows / columns beyond the tensor are clipped by TMA
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  }
+}
+
+
+// =================================================================================================
+// 2-CTA variant (cta_group::2): a CTA pair on one TPC computes a 256 x BN tile.  Each CTA stages its own
+// 128 rows of A and HALF of the B tile (BN/2 weight rows), so per k-block a pair moves 64 KB from L2
+// for 4.2 MFLOP instead of 96 KB: the fp32-operand kernel above is L2-bandwidth bound
+// (43.7 FLOP/B x ~12 TB/s ~ 520 TFLOP/s), the pair raises the intensity to 65.5 FLOP/B.
+// Rank 0 issues tcgen05.mma.cta_group::2 (M = 256); both CTAs run TMA producers (signalling rank 0's
+// full barrier) and epilogues (each drains its own 128 TMEM lanes); commits are multicast to both.
+// =================================================================================================
+#define TC2_STAGES 6
+#define TC2_BH_BYTES (128 * TC_BK * 4)          // half B tile: up to 128 rows
+#define TC2_STAGE_BYTES (TC_A_BYTES + TC2_BH_BYTES)
+#define TC2_SMEM_BYTES (TC2_STAGES * TC2_STAGE_BYTES + 1024 + 256)
+
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+template <int KIND_BF16>
+__device__ __forceinline__ void tc_mma_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (KIND_BF16) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  } else {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  }
+}
+
+template <int KIND_BF16>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + TC2_STAGES * TC2_STAGE_BYTES);
+  uint64_t* full = bars;                          // [S]  (rank 0's copy is the live one)
+  uint64_t* empty = bars + TC2_STAGES;            // [S]  per CTA
+  uint64_t* tfull = bars + 2 * TC2_STAGES;        // [2]  per CTA
+  uint64_t* tempty = bars + 2 * TC2_STAGES + 2;   // [2]  (rank 0's copy is the live one)
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TC2_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_rank();
+  const int nkb = a.taps * a.kchunks;
+  const int ntiles = a.m_tiles * a.n_tiles;        // m_tiles counts 256-row pair tiles here
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int bh = a.bn >> 1;                        // B rows staged by each CTA
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC2_STAGES; ++s) { mbar_init(&full[s], 2); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();                              // barriers of both CTAs initialised before any remote arrive / TMA signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      const uint32_t tx_pair = 2u * (TC_A_BYTES + (uint32_t)bh * TC_BK * 4);
+      for (int tile = pair; tile < ntiles; tile += npairs) {
+        const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
+        const int p0 = mt * 256 + (int)rank * TC_BM, n0 = nt * a.bn + (int)rank * bh;
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int tap = kb / a.kchunks, kc = kb - tap * a.kchunks;
+          mbar_wait(&empty[stage], phase ^ 1);
+          const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
+          if (rank == 0) mbar_expect_tx(&full[stage], tx_pair);
+          else mbar_arrive_cluster(lead_full);
+          uint8_t* sa = smem + stage * TC2_STAGE_BYTES;
+          tma_load_2d_2sm(sa, &mapA, lead_full, kc * TC_BK, p0 + tap * a.tap_step);
+          tma_load_2d_2sm(sa + TC_A_BYTES, &mapB, lead_full, kb * TC_BK, n0);
+          if (++stage == TC2_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      const uint32_t fmt = KIND_BF16 ? 1u : 2u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(a.bn >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = pair; tile < ntiles; tile += npairs) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)acc * TC_MAX_BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * TC2_STAGE_BYTES);
+          const uint64_t da = make_desc(sa), db = make_desc(sa + TC_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc_mma_2sm<KIND_BF16>(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          tc_commit_2sm(&empty[stage]);
+          if (++stage == TC2_STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit_2sm(&tfull[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = pair; tile < ntiles; tile += npairs) {
+      const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
+      const int row = mt * 256 + (int)rank * TC_BM + q * 32 + lane;
       const int n0 = nt * a.bn;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
@@ -228,8 +438,155 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();                              // the peer may still be reading its TMEM / signalling our barriers
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+
+// =================================================================================================
+// 256 x 256 tile variant for the long-K layers.  ncu on the 128 x 256 kernel shows nothing saturated
+// except the shared-memory operand path (84 %) with the tensor pipe at 53 %: with fp32 operands a
+// k-block is 48 KB for 2.1 MFLOP and only 4 stages (192 KB) fit, so TMA latency (~3000 cycles under
+// load) is not covered (Little: 96 B/clk x 3000 clk = 288 KB in flight needed).  Two M = 128 MMAs that
+// share one B tile move 64 KB per 4.2 MFLOP: 1.5x fewer bytes per FLOP from L2 and through the
+// pipeline.  The two accumulators fill TMEM (2 x 256 columns), so the epilogue (8 warps, one group
+// of 4 per accumulator) is not overlapped with the next tile's MMAs: used only when K is long enough
+// (>= 24 k-blocks) for that to cost < 15 %.
+// =================================================================================================
+#define TC3_STAGES 3
+#define TC3_STAGE_BYTES (2 * TC_A_BYTES + TC_B_BYTES)          // 64 KB
+#define TC3_SMEM_BYTES (TC3_STAGES * TC3_STAGE_BYTES + 1024 + 256)
+#define TC3_THREADS 320
+
+template <int KIND_BF16>
+__global__ void __launch_bounds__(TC3_THREADS, 1)
+conv_tc256_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + TC3_STAGES * TC3_STAGE_BYTES);
+  uint64_t* full = bars;                       // [3]
+  uint64_t* empty = bars + TC3_STAGES;         // [3]
+  uint64_t* tfull = bars + 2 * TC3_STAGES;     // [1]
+  uint64_t* tempty = tfull + 1;                // [1]
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = a.taps * a.kchunks;
+  const int ntiles = a.m_tiles * a.n_tiles;    // m_tiles counts 256-row tiles
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC3_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tfull, 1); mbar_init(tempty, 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
+        const int p0 = mt * 256, n0 = nt * TC_MAX_BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int tap = kb / a.kchunks, kc = kb - tap * a.kchunks;
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], TC3_STAGE_BYTES);
+          uint8_t* sa = smem + stage * TC3_STAGE_BYTES;
+          tma_load_2d(sa, &mapA, &full[stage], kc * TC_BK, p0 + tap * a.tap_step);              // 256 rows: A0 | A1
+          tma_load_2d(sa + 2 * TC_A_BYTES, &mapB, &full[stage], kb * TC_BK, n0);
+          if (++stage == TC3_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t fmt = KIND_BF16 ? 1u : 2u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(TC_MAX_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      int stage = 0; uint32_t phase = 0, tphase = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        mbar_wait(tempty, tphase ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * TC3_STAGE_BYTES);
+          const uint64_t da0 = make_desc(sa), da1 = make_desc(sa + TC_A_BYTES), db = make_desc(sa + 2 * TC_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            tc_mma<KIND_BF16>(tmem_base, da0 + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            tc_mma<KIND_BF16>(tmem_base + TC_MAX_BN, da1 + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          }
+          tc_commit(&empty[stage]);
+          if (++stage == TC3_STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(tfull);
+        tphase ^= 1;
+      }
+    }
+  } else {
+    const int q = warp & 3, g = (warp - 2) >> 2;           // TMEM lane quarter, accumulator (row half)
+    uint32_t tphase = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
+      const int row = mt * 256 + g * TC_BM + q * 32 + lane;
+      const int n0 = nt * TC_MAX_BN;
+      mbar_wait(tfull, tphase);
+      tc_fence_after();
+      const bool row_in = row < a.rows;
+      bool row_ok = row_in;
+      if (a.epilogue == SG_EPI_MASK) row_ok = row_in && ((row % a.T) < a.t_valid);
+      for (int c = 0; c < TC_MAX_BN; c += 32) {
+        float v[32];
+        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * TC_MAX_BN + c), v);
+        const int col = n0 + c;
+        if (a.epilogue == SG_EPI_BIAS || a.epilogue == SG_EPI_BIAS_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += __ldg(a.bias + col + j);
+          if (a.epilogue == SG_EPI_BIAS_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+        } else if (a.epilogue == SG_EPI_MASK) {
+          if (row_ok) {
+            const float4* mp = reinterpret_cast<const float4*>(a.mask + (size_t)row * a.ldmask + col);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 m4 = __ldg(mp + j);
+              v[4 * j + 0] = m4.x > 0.f ? v[4 * j + 0] : 0.f;
+              v[4 * j + 1] = m4.y > 0.f ? v[4 * j + 1] : 0.f;
+              v[4 * j + 2] = m4.z > 0.f ? v[4 * j + 2] : 0.f;
+              v[4 * j + 3] = m4.w > 0.f ? v[4 * j + 3] : 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          }
+        }
+        if (row_in) {
+          float4* op = reinterpret_cast<float4*>(a.out + (size_t)row * a.ldo + col);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty);
+      tphase ^= 1;
     }
   }
   tc_fence_before();
@@ -245,6 +602,8 @@ typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void
                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeFn g_encode = nullptr;
 static int g_num_sms = 0;
+static int g_use_256 = 0;        // 1: 256 x 256 tiles for long-K contractions (measured: no gain, kept for experiments)
+static int g_use_pair = 0;       // 1: 2-CTA (cta_group::2) kernel for tiles with BN >= 64
 
 static int tc_init() {
   if (g_encode) return SG_OK;
@@ -260,6 +619,16 @@ static int tc_init() {
   SG_CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+  SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES));
+  SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc256_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC3_SMEM_BYTES));
+  {
+    const char* e = getenv("SGB200_TC_256");
+    g_use_256 = e ? atoi(e) : 0;
+  }
+  {
+    const char* e = getenv("SGB200_TC_PAIR");
+    g_use_pair = e ? atoi(e) : 0;
+  }
   g_encode = (EncodeFn)fn;
   return SG_OK;
 }
@@ -302,9 +671,34 @@ int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
   t.epilogue = a.epilogue; t.T = a.T > 0 ? a.T : 1; t.t_valid = a.t_valid;
   t.m_tiles = (a.rows + TC_BM - 1) / TC_BM; t.n_tiles = a.N / bn;
   if ((a.epilogue == SG_EPI_BIAS || a.epilogue == SG_EPI_BIAS_RELU) && !a.bias) { sg_set_error("sg_conv_tc: bias epilogue without bias"); return SG_EINVAL; }
+  if (g_use_256 && bn == TC_MAX_BN && a.taps * (a.cin / TC_BK) >= 24 && a.rows >= 256 * 64) {
+    CUtensorMap mapA2;
+    r = make_map_f32(&mapA2, a.A, (uint64_t)a.rows, (uint64_t)a.cin, (uint64_t)a.lda, 256);
+    if (r != SG_OK) return r;
+    t.m_tiles = (a.rows + 255) / 256;
+    int grid3 = t.m_tiles * t.n_tiles;
+    if (grid3 > g_num_sms) grid3 = g_num_sms;
+    conv_tc256_kernel<0><<<grid3, TC3_THREADS, TC3_SMEM_BYTES, st>>>(mapA2, mapB, t);
+    SG_LAUNCH_CHECK();
+    return SG_OK;
+  }
+  if (g_use_pair && bn >= 64 && bn % 64 == 0 && a.rows > 256) {
+    CUtensorMap mapBh;
+    r = make_map_f32(&mapBh, a.Wk, (uint64_t)a.N, (uint64_t)a.taps * a.cin, (uint64_t)a.taps * a.cin, (uint32_t)(bn / 2));
+    if (r != SG_OK) return r;
+    t.m_tiles = (a.rows + 255) / 256;
+    int pairs = t.m_tiles * t.n_tiles;
+    if (pairs > g_num_sms / 2) pairs = g_num_sms / 2;
+    conv_tc2_kernel<0><<<2 * pairs, TC_THREADS, TC2_SMEM_BYTES, st>>>(mapA, mapBh, t);
+    SG_LAUNCH_CHECK();
+    return SG_OK;
+  }
+  CUtensorMap mapO;
+  r = make_map_f32(&mapO, a.out, (uint64_t)a.rows, (uint64_t)a.N, (uint64_t)a.ldo, TC_BM);
+  if (r != SG_OK) return r;
   int grid = t.m_tiles * t.n_tiles;
   if (grid > g_num_sms) grid = g_num_sms;
-  conv_tc_kernel<0><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mapA, mapB, t);
+  conv_tc_kernel<0><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mapA, mapB, mapO, t);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }

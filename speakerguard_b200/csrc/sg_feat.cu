@@ -194,12 +194,15 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   }
   return c;
 }
+// The philox dither is a statistically-equivalent stand-in for torch.randn (SG_DITHER_TENSOR is the
+// bit-parity mode), so the fast intrinsics are fine here; forward, adjoint and sg_dither_fill share
+// this function and therefore see identical noise.
 __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
   float u1 = __uint2float_rn(a) * 2.3283064365386963e-10f + 1.1641532182693481e-10f;
   float u2 = __uint2float_rn(b) * 2.3283064365386963e-10f + 1.1641532182693481e-10f;
-  float r = sqrtf(-2.0f * logf(u1));
+  float r = sqrtf(-2.0f * __logf(u1));
   float s, c;
-  sincospif(2.0f * u2, &s, &c);
+  __sincosf(6.283185307179586f * u2, &s, &c);
   return make_float2(r * c, r * s);
 }
 

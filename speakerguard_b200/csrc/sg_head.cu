@@ -52,20 +52,33 @@ __global__ void pool_fwd_kernel(const float* __restrict__ r5, int T, int Tv, con
 }
 
 // d(stats) -> d(pre-ReLU layer-5 activation), ReLU mask and row validity applied
-// grid (C5P/32, B, tsplit), block (32, 8)
+// grid (C5P/128, B, tsplit), block (32, 8); each thread owns 4 consecutive channels (float4 traffic)
 __global__ void pool_bwd_kernel(const float* __restrict__ r5, int T, int Tv, const float* __restrict__ bn_istd,
                                 const float* __restrict__ dstats, const float* __restrict__ save_mean,
                                 const float* __restrict__ save_std, float* __restrict__ dA5) {
-  const int c = blockIdx.x * 32 + threadIdx.x, b = blockIdx.y;
-  const bool real = c < SG_C5;
-  const float is = real ? bn_istd[c] : 0.f;
-  const float mean = save_mean[(size_t)b * SG_C5P + c], sd = save_std[(size_t)b * SG_C5P + c];
-  const float alpha = real ? dstats[(size_t)b * SG_STATS + c] * is / (float)Tv : 0.f;
-  const float beta = (real && sd > 0.f) ? dstats[(size_t)b * SG_STATS + SG_C5P + c] * is / ((float)(Tv - 1) * sd) : 0.f;
-  const size_t off = (size_t)b * T * SG_C5P + c;
+  const int c0 = blockIdx.x * 128 + threadIdx.x * 4, b = blockIdx.y;
+  float alpha[4], beta[4], mean[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + i;
+    const bool real = c < SG_C5;
+    const float is = real ? bn_istd[c] : 0.f;
+    const float sd = save_std[(size_t)b * SG_C5P + c];
+    mean[i] = save_mean[(size_t)b * SG_C5P + c];
+    alpha[i] = real ? dstats[(size_t)b * SG_STATS + c] * is / (float)Tv : 0.f;
+    beta[i] = (real && sd > 0.f) ? dstats[(size_t)b * SG_STATS + SG_C5P + c] * is / ((float)(Tv - 1) * sd) : 0.f;
+  }
+  const size_t off = (size_t)b * T * SG_C5P + c0;
   for (int t = blockIdx.z * 8 + threadIdx.y; t < T; t += 8 * gridDim.z) {
-    const float r = r5[off + (size_t)t * SG_C5P];
-    dA5[off + (size_t)t * SG_C5P] = (t < Tv && r > 0.f) ? fmaf(beta, r - mean, alpha) : 0.f;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < Tv) {
+      const float4 r = *reinterpret_cast<const float4*>(r5 + off + (size_t)t * SG_C5P);
+      o.x = r.x > 0.f ? fmaf(beta[0], r.x - mean[0], alpha[0]) : 0.f;
+      o.y = r.y > 0.f ? fmaf(beta[1], r.y - mean[1], alpha[1]) : 0.f;
+      o.z = r.z > 0.f ? fmaf(beta[2], r.z - mean[2], alpha[2]) : 0.f;
+      o.w = r.w > 0.f ? fmaf(beta[3], r.w - mean[3], alpha[3]) : 0.f;
+    }
+    *reinterpret_cast<float4*>(dA5 + off + (size_t)t * SG_C5P) = o;
   }
 }
 
@@ -324,7 +337,7 @@ int sg_pool_fwd_launch(const float* r5, int B, int T, int Tv, const float* bn_me
 int sg_pool_bwd_launch(const float* r5, int B, int T, int Tv, const float* bn_istd, const float* dstats,
                        const float* save_mean, const float* save_std, float* dA5, cudaStream_t st) {
   int tsplit = (B >= 64) ? 1 : 4;
-  pool_bwd_kernel<<<dim3(SG_C5P / 32, B, tsplit), dim3(32, 8), 0, st>>>(r5, T, Tv, bn_istd, dstats, save_mean, save_std, dA5);
+  pool_bwd_kernel<<<dim3(SG_C5P / 128, B, tsplit), dim3(32, 8), 0, st>>>(r5, T, Tv, bn_istd, dstats, save_mean, save_std, dA5);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }

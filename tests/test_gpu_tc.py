@@ -16,6 +16,8 @@ SHAPES = [  # rows, cin, N, taps, step, epilogue
     (640, 512, 32, 5, -1, 3),        # layer 1 dgrad
     (128, 512, 512, 1, 0, 0),        # single tile, bias only
     (40000, 512, 512, 5, 2, 1),      # many tiles per CTA (persistent loop, both TMEM stages, barrier phase wrap)
+    (50000, 512, 512, 7, -3, 2),     # long K + many rows: 256 x 256 tile kernel, mask epilogue
+    (33000, 1536, 512, 1, 0, 2),     # layer-5 dgrad shape on the 256 x 256 kernel
 ]
 
 
