@@ -232,6 +232,7 @@ extern "C" int sg_load_xv(sg_handle* h, const sg_xv_weights* w) {
 // workspace layout
 // ---------------------------------------------------------------------------------------------
 struct XvWs {
+  uint32_t* bits[4];
   float *r[5], *G0, *G1, *G2, *stats, *dstats, *save_mean, *save_std, *e1, *de1, *e2, *de2, *tsave, *scal;
   // attack-loop extras
   float *raw, *draw, *feat, *dfeat, *emb, *demb, *scores, *dscores, *loss, *xbuf, *grad;
@@ -247,6 +248,7 @@ static XvWs xv_ws_layout(void* base, int B, int T, int Lp, int L, int S, bool at
   const size_t R = (size_t)B * T;
   for (int l = 0; l < 4; ++l) w.r[l] = take(R * SG_C1);
   w.r[4] = take(R * SG_C5P);
+  for (int l = 0; l < 4; ++l) w.bits[l] = (uint32_t*)take(R * (SG_C1 / 32));
   w.G0 = take(R * SG_C5P); w.G1 = take(R * SG_C1); w.G2 = take(R * SG_C1);
   w.stats = take((size_t)B * SG_STATS); w.dstats = take((size_t)B * SG_STATS);
   w.save_mean = take((size_t)B * SG_C5P); w.save_std = take((size_t)B * SG_C5P);
@@ -367,6 +369,7 @@ static int embed_fwd(sg_handle* h, const float* feat, int B, int T, const XvWs& 
     a.A = in; a.lda = lda; a.W = h->Wf[l]; a.Wk = h->Wfk[l]; a.bias = h->bias[l]; a.out = w.r[l]; a.ldo = kCoutP[l];
     a.rows = R; a.N = kCoutP[l]; a.cin = kCinP[l]; a.taps = kTaps[l]; a.tap_step = kDil[l];
     a.epilogue = SG_EPI_BIAS_RELU; a.T = T; a.t_valid = tv[l];
+    if (l < 4 && h->precision != SG_PREC_FP32) { a.bits_out = w.bits[l]; a.ldbits = SG_C1 / 32; }
     SG_TRY(sg_run_conv(h, a, true, SG_PROF_TDNN_FWD, st));
     in = w.r[l]; lda = kCoutP[l];
   }
@@ -416,6 +419,7 @@ static int embed_bwd(sg_handle* h, const float* demb, int B, int T, const XvWs& 
       float* out = bufs[(4 - l) & 1];
       a.out = out; a.ldo = kCinP[l]; a.N = kCinP[l];
       a.epilogue = SG_EPI_MASK; a.mask = w.r[l - 1]; a.ldmask = kCoutP[l - 1]; a.t_valid = tv[l - 1];
+      if (h->precision != SG_PREC_FP32) { a.bits_in = w.bits[l - 1]; a.ldbits = SG_C1 / 32; }
       SG_TRY(sg_run_conv(h, a, true, SG_PROF_TDNN_BWD, st));
       gin = out;
     } else {

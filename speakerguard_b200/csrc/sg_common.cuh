@@ -83,6 +83,10 @@ struct SgConvArgs {
   int epilogue;
   const float* mask; int ldmask;    // SG_EPI_MASK: post-ReLU activation of the producing layer
   int T; int t_valid;               // rows per utterance / valid rows (SG_EPI_MASK)
+  // tensor-core path only: 1 bit per output element instead of re-reading the fp32 activation as a mask
+  uint32_t* bits_out;               // SG_EPI_BIAS_RELU: bit j of word [row, col/32] = (out[row, col] > 0)
+  const uint32_t* bits_in;          // SG_EPI_MASK: replaces `mask` when non-null
+  int ldbits;                       // words per row
 };
 
 int sg_conv_simt(const SgConvArgs& a, cudaStream_t st);

@@ -101,6 +101,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 }
 
 struct TcArgs {
+  uint32_t* bits_out; const uint32_t* bits_in; int ldbits;
   const float* bias;
   float* out; int ldo;
   const float* mask; int ldmask;
@@ -221,9 +222,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           if (a.epilogue == SG_EPI_BIAS_RELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            if (a.bits_out != nullptr && row < a.rows) {
+              uint32_t wbits = 0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) wbits |= (v[j] > 0.f ? 1u : 0u) << j;
+              a.bits_out[(size_t)row * a.ldbits + (col >> 5)] = wbits;
+            }
           }
         } else if (a.epilogue == SG_EPI_MASK) {
-          if (row_ok) {
+          if (row_ok && a.bits_in != nullptr) {
+            const uint32_t wbits = __ldg(a.bits_in + (size_t)row * a.ldbits + (col >> 5));
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = ((wbits >> j) & 1u) ? v[j] : 0.f;
+          } else if (row_ok) {
             const float4* mp = reinterpret_cast<const float4*>(a.mask + (size_t)row * a.ldmask + col);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -666,6 +677,8 @@ int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
   r = make_map_f32(&mapB, a.Wk, (uint64_t)a.N, (uint64_t)a.taps * a.cin, (uint64_t)a.taps * a.cin, (uint32_t)bn);
   if (r != SG_OK) return r;
   TcArgs t;
+  t.bits_out = a.bits_out; t.bits_in = a.bits_in; t.ldbits = a.ldbits;
+  if (g_use_256 || g_use_pair) { t.bits_out = nullptr; t.bits_in = nullptr; }   // experimental tile variants keep fp32 masks
   t.bias = a.bias; t.out = a.out; t.ldo = a.ldo; t.mask = a.mask; t.ldmask = a.ldmask;
   t.rows = a.rows; t.N = a.N; t.bn = bn; t.kchunks = a.cin / TC_BK; t.taps = a.taps; t.tap_step = a.tap_step;
   t.epilogue = a.epilogue; t.T = a.T > 0 ? a.T : 1; t.t_valid = a.t_valid;

@@ -138,7 +138,29 @@ class xv_plda(nn.Module):
     def scoring_trials(self, enroll_embs, embs):
         return ScoreFn.apply(embs, enroll_embs, self.engine)
 
+    def _fused_forward(self, x):
+        """Forward-only wav -> (scores, decisions, emb) through sg_xv_forward: one call, no autograd
+        bookkeeping (evaluation scripts and black-box attacks call make_decision thousands of times:
+        reference test_attack.py:123-128, attack/FAKEBOB.py:170-174)."""
+        x = check_input_range(x, range_type=self.range_type)
+        x2 = (x[:, 0, :] / float(2 ** 15)).contiguous()
+        B, N = x2.shape
+        mode, d = self._draw_dither(B, self.engine.num_frames(N))
+        key = (B, N)
+        if getattr(self, "_fwd_ws_key", None) != key:
+            self._fwd_ws, self._fwd_ws_key = self.engine.pgd_ws(B, N), key
+        out = self.engine.xv_forward(x2, mode, d, self.seed, self._pass, self.decision_threshold, ws=self._fwd_ws)
+        self._pass += 1
+        return out
+
+    def _can_fuse(self, x, flag, enroll_embs):
+        return (flag == 0 and enroll_embs is None and hasattr(self, "enroll_embs")
+                and not (torch.is_grad_enabled() and x.requires_grad))
+
     def forward(self, x, flag=0, return_emb=False, enroll_embs=None):
+        if self._can_fuse(x, flag, enroll_embs):
+            scores, _, emb = self._fused_forward(x)
+            return (scores, emb) if return_emb else scores
         embedding = self.embedding(x, flag=flag)
         if not hasattr(self, "enroll_embs"):
             assert enroll_embs is not None
@@ -150,6 +172,9 @@ class xv_plda(nn.Module):
         return self.forward(x, flag=flag, enroll_embs=enroll_embs)
 
     def make_decision(self, x, flag=0, enroll_embs=None):
+        if self._can_fuse(x, flag, enroll_embs):
+            scores, decisions, _ = self._fused_forward(x)
+            return decisions, scores
         scores = self.score(x, flag=flag, enroll_embs=enroll_embs)
         decisions = torch.argmax(scores, dim=1)
         max_scores = torch.max(scores, dim=1)[0]

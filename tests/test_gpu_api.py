@@ -74,6 +74,21 @@ def test_model_methods_match_oracle(model, params):
     model.threshold = old
 
 
+def test_forward_only_fast_path_equals_stagewise(model):
+    """make_decision on a tensor that needs no gradient takes the fused sg_xv_forward path and
+    must equal the autograd (stage-by-stage) path bit for bit (dither off)."""
+    x = wave(3, 24000, seed=21).cuda()
+    d1, s1 = model.make_decision(x)                           # fused
+    xg = x.clone().requires_grad_(True)
+    d2, s2 = model.make_decision(xg)                          # stage-wise autograd path
+    assert torch.equal(d1, d2) and torch.equal(s1, s2.detach())
+    with torch.no_grad():
+        d3, s3 = model.make_decision(xg)                      # no_grad -> fused again
+    assert torch.equal(s3, s1)
+    s4, e4 = model(x, return_emb=True)
+    assert torch.equal(s4, s1) and e4.shape == (3, 200)
+
+
 def test_autograd_through_the_stages(model, params):
     """loss.backward() through the CUDA stages == oracle autograd (what EOT.forward relies on)."""
     from speakerguard_b200.attack.utils import resolve_loss
