@@ -32,7 +32,7 @@ enum { SG_OK = 0, SG_EINVAL = -1, SG_ECUDA = -2, SG_ESTATE = -3, SG_EUNSUPPORTED
 
 /* arithmetic of the TDNN contractions (everything else is always fp32) */
 enum { SG_PREC_FP32 = 0 /* FFMA, parity mode */, SG_PREC_TF32 = 1 /* tcgen05 kind::tf32 */,
-       SG_PREC_BF16 = 2 /* tcgen05 kind::f16, bf16 operands, fp32 accumulate */ };
+       SG_PREC_BF16 = 2 /* tcgen05 kind::f16: TDNN activations, gradients and weights in bf16, fp32 accumulate */ };
 /* dither of kaldi.py:179-181 (dither = 1.0 hard-coded at model/xv_plda.py:119) */
 enum { SG_DITHER_OFF = 0, SG_DITHER_TENSOR = 1 /* caller supplies N(0,1) [B,m,400] */,
        SG_DITHER_PHILOX = 2 /* counter-based, regenerated identically in the adjoint */ };
@@ -229,12 +229,13 @@ int sg_feco_means_bwd(sg_handle* h, const float* dout, const int32_t* ids, const
 /* ---- test hook: one conv-as-GEMM launch on either arithmetic path -----------------------------
  * out[p,n] = epi(sum_{tap,c} A[p + tap*tap_step, c] * W[tap*cin + c, n]); W is [taps*cin, N]
  * (FFMA path), Wk its K-major copy [N, taps*cin] (tcgen05 path); epilogue 0 bias, 1 bias+ReLU,
- * 2 ReLU-mask (mask > 0 and row %% T < t_valid), 3 none.  This is the kernel behind the TDNN
- * layers (xvecTDNN.py:16-53) and their dgrad. */
+ * 2 ReLU-mask (mask > 0 and row %% T < t_valid), 3 none.  op_bf16: A and Wk hold bf16 (tcgen05
+ * kind::f16); out_bf16: out holds bf16.  This is the kernel behind the TDNN layers
+ * (xvecTDNN.py:16-53) and their dgrad. */
 int sg_debug_conv(sg_handle* h, int precision, const float* A, int lda, const float* W, const float* Wk,
                   const float* bias, float* out, int ldo, int rows, int N, int cin, int taps,
                   int tap_step, int epilogue, const float* mask, int ldmask, int T, int t_valid,
-                  sg_stream stream);
+                  int op_bf16, int out_bf16, sg_stream stream);
 
 /* ---- device-side timing ------------------------------------------------------------------------
  * With profiling enabled every kernel launch is bracketed by CUDA events on its stream and

@@ -6,6 +6,8 @@
 
 #include <vector>
 
+#include <cuda_bf16.h>
+
 #include "sg_handle.cuh"
 
 // ---------------------------------------------------------------------------------------------
@@ -38,6 +40,15 @@ int sg_dev_upload(sg_handle* h, float** dst, const std::vector<float>& src) {
   SG_CUDA_CHECK(cudaMalloc((void**)dst, src.size() * sizeof(float)));
   h->allocs.push_back(*dst);
   SG_CUDA_CHECK(cudaMemcpy(*dst, src.data(), src.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return SG_OK;
+}
+
+static int upload_bf16(sg_handle* h, void** dst, const std::vector<float>& src) {
+  std::vector<__nv_bfloat16> tmp(src.size());
+  for (size_t i = 0; i < src.size(); ++i) tmp[i] = __float2bfloat16_rn(src[i]);
+  SG_CUDA_CHECK(cudaMalloc(dst, tmp.size() * sizeof(__nv_bfloat16)));
+  h->allocs.push_back(*dst);
+  SG_CUDA_CHECK(cudaMemcpy(*dst, tmp.data(), tmp.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
   return SG_OK;
 }
 
@@ -154,6 +165,8 @@ extern "C" int sg_load_xv(sg_handle* h, const sg_xv_weights* w) {
     SG_TRY(sg_dev_upload(h, &h->Wb[l], Wb));
     SG_TRY(sg_dev_upload(h, &h->Wfk[l], Wfk));
     SG_TRY(sg_dev_upload(h, &h->Wbk[l], Wbk));
+    SG_TRY(upload_bf16(h, &h->Wfk_h[l], Wfk));
+    SG_TRY(upload_bf16(h, &h->Wbk_h[l], Wbk));
     SG_TRY(sg_dev_upload(h, &h->bias[l], bias));
   }
   {
@@ -246,10 +259,13 @@ static XvWs xv_ws_layout(void* base, int B, int T, int Lp, int L, int S, bool at
   size_t off = 0;
   auto take = [&](size_t nfloat) { float* q = (float*)(p + off); off += (nfloat * sizeof(float) + 255) / 256 * 256; return q; };
   const size_t R = (size_t)B * T;
-  for (int l = 0; l < 4; ++l) w.r[l] = take(R * SG_C1);
-  w.r[4] = take(R * SG_C5P);
+  // TDNN activations / gradient ping-pong: fp32, or bf16 in SG_PREC_BF16 mode (then half of each region is used;
+  // the layout does not depend on the precision so a workspace stays valid across sg_set_precision)
+  auto take_act = [&](size_t nelem) { return take(nelem); };
+  for (int l = 0; l < 4; ++l) w.r[l] = take_act(R * SG_C1);
+  w.r[4] = take_act(R * SG_C5P);
   for (int l = 0; l < 4; ++l) w.bits[l] = (uint32_t*)take(R * (SG_C1 / 32));
-  w.G0 = take(R * SG_C5P); w.G1 = take(R * SG_C1); w.G2 = take(R * SG_C1);
+  w.G0 = take_act(R * SG_C5P); w.G1 = take_act(R * SG_C1); w.G2 = take_act(R * SG_C1);
   w.stats = take((size_t)B * SG_STATS); w.dstats = take((size_t)B * SG_STATS);
   w.save_mean = take((size_t)B * SG_C5P); w.save_std = take((size_t)B * SG_C5P);
   w.e1 = take((size_t)B * SG_EMB); w.de1 = take((size_t)B * SG_EMB);
@@ -370,11 +386,15 @@ static int embed_fwd(sg_handle* h, const float* feat, int B, int T, const XvWs& 
     a.rows = R; a.N = kCoutP[l]; a.cin = kCinP[l]; a.taps = kTaps[l]; a.tap_step = kDil[l];
     a.epilogue = SG_EPI_BIAS_RELU; a.T = T; a.t_valid = tv[l];
     if (l < 4 && h->precision != SG_PREC_FP32) { a.bits_out = w.bits[l]; a.ldbits = SG_C1 / 32; }
+    if (h->precision == SG_PREC_BF16) {                  // bf16 activations; layer 1 still reads the fp32 features
+      a.out_bf16 = 1;
+      if (l > 0) { a.op_bf16 = 1; a.Wk = (const float*)h->Wfk_h[l]; }
+    }
     SG_TRY(sg_run_conv(h, a, true, SG_PROF_TDNN_FWD, st));
     in = w.r[l]; lda = kCoutP[l];
   }
   h->launches += 1;
-  PROF(h, SG_PROF_POOL, st, sg_pool_fwd_launch(w.r[4], B, T, tv[4], h->bn5_mean, h->bn5_istd, w.stats, w.save_mean, w.save_std, st));
+  PROF(h, SG_PROF_POOL, st, sg_pool_fwd_launch(w.r[4], h->precision == SG_PREC_BF16, B, T, tv[4], h->bn5_mean, h->bn5_istd, w.stats, w.save_mean, w.save_std, st));
   {
     SgConvArgs a;
     memset(&a, 0, sizeof(a));
@@ -406,7 +426,7 @@ static int embed_bwd(sg_handle* h, const float* demb, int B, int T, const XvWs& 
     SG_TRY(sg_run_conv(h, a, true, SG_PROF_HEAD_GEMM, st));
   }
   h->launches += 1;
-  PROF(h, SG_PROF_POOL, st, sg_pool_bwd_launch(w.r[4], B, T, tv[4], h->bn5_istd, w.dstats, w.save_mean, w.save_std, w.G0, st));
+  PROF(h, SG_PROF_POOL, st, sg_pool_bwd_launch(w.r[4], h->precision == SG_PREC_BF16, B, T, tv[4], h->bn5_istd, w.dstats, w.save_mean, w.save_std, w.G0, st));
   // dgrad chain: dA_l (pre-ReLU grad of layer l) -> dA_{l-1}
   const float* gin = w.G0;
   float* bufs[2] = {w.G1, w.G2};
@@ -415,6 +435,7 @@ static int embed_bwd(sg_handle* h, const float* demb, int B, int T, const XvWs& 
     memset(&a, 0, sizeof(a));
     a.A = gin; a.lda = kCoutP[l]; a.W = h->Wb[l]; a.Wk = h->Wbk[l]; a.rows = R; a.cin = kCoutP[l]; a.taps = kTaps[l];
     a.tap_step = -kDil[l]; a.T = T;
+    if (h->precision == SG_PREC_BF16) { a.op_bf16 = 1; a.out_bf16 = l > 0; a.Wk = (const float*)h->Wbk_h[l]; }
     if (l > 0) {
       float* out = bufs[(4 - l) & 1];
       a.out = out; a.ldo = kCinP[l]; a.N = kCinP[l];
@@ -446,13 +467,15 @@ extern "C" int sg_xv_embed_bwd(sg_handle* h, const float* demb, int B, int T, vo
 // generic contraction, either path (tests): W is [taps*cin, N], Wk its K-major copy [N, taps*cin]
 extern "C" int sg_debug_conv(sg_handle* h, int precision, const float* A, int lda, const float* W, const float* Wk,
                              const float* bias, float* out, int ldo, int rows, int N, int cin, int taps, int tap_step,
-                             int epilogue, const float* mask, int ldmask, int T, int t_valid, sg_stream stream) {
+                             int epilogue, const float* mask, int ldmask, int T, int t_valid, int op_bf16, int out_bf16,
+                             sg_stream stream) {
   SG_TRY(sg_check_handle(h, false));
   if (!A || !out || rows < 1 || N < 1) { sg_set_error("sg_debug_conv: bad argument"); return SG_EINVAL; }
   SgConvArgs a;
   memset(&a, 0, sizeof(a));
   a.A = A; a.lda = lda; a.W = W; a.Wk = Wk; a.bias = bias; a.out = out; a.ldo = ldo; a.rows = rows; a.N = N; a.cin = cin;
   a.taps = taps; a.tap_step = tap_step; a.epilogue = epilogue; a.mask = mask; a.ldmask = ldmask; a.T = T; a.t_valid = t_valid;
+  a.op_bf16 = op_bf16; a.out_bf16 = out_bf16;
   h->launches += 1;
   if (precision == SG_PREC_FP32) return sg_conv_simt(a, (cudaStream_t)stream);
   return sg_conv_tc(a, precision, (cudaStream_t)stream);

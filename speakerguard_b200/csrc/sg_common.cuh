@@ -87,6 +87,8 @@ struct SgConvArgs {
   uint32_t* bits_out;               // SG_EPI_BIAS_RELU: bit j of word [row, col/32] = (out[row, col] > 0)
   const uint32_t* bits_in;          // SG_EPI_MASK: replaces `mask` when non-null
   int ldbits;                       // words per row
+  // bf16 mode (tensor-core path): A / Wk hold __nv_bfloat16 when op_bf16, out is __nv_bfloat16 when out_bf16
+  int op_bf16; int out_bf16;
 };
 
 int sg_conv_simt(const SgConvArgs& a, cudaStream_t st);

@@ -10,6 +10,7 @@
 // The fp32 accumulator (128 lanes x BN columns) is double-buffered in TMEM (2 x 256 columns) so
 // the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <stdlib.h>
 
 #include "sg_common.cuh"
@@ -111,7 +112,7 @@ struct TcArgs {
   int m_tiles, n_tiles;
 };
 
-template <int KIND_BF16>
+template <int KIND_BF16, int OUT_BF16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ CUtensorMap mapO, TcArgs a) {
@@ -128,6 +129,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = a.taps * a.kchunks;
   const int ntiles = a.m_tiles * a.n_tiles;
+  constexpr int KB_ELEMS = KIND_BF16 ? 64 : 32;     // elements per 128-byte k-block
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -157,8 +159,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], tx);
           uint8_t* sa = smem + stage * TC_STAGE_BYTES;
-          tma_load_2d(sa, &mapA, &full[stage], kc * TC_BK, p0 + tap * a.tap_step);
-          tma_load_2d(sa + TC_A_BYTES, &mapB, &full[stage], kb * TC_BK, n0);
+          tma_load_2d(sa, &mapA, &full[stage], kc * KB_ELEMS, p0 + tap * a.tap_step);
+          tma_load_2d(sa + TC_A_BYTES, &mapB, &full[stage], kb * KB_ELEMS, n0);
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -198,6 +200,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int q = warp & 3;
     const int r_in = q * 32 + lane;                       // row within the tile
     const bool issuer = (warp == 2 && lane == 0);
+    constexpr int CW = OUT_BF16 ? 64 : 32;                // columns per 128-byte staging row
     int acc = 0; uint32_t acc_phase = 0;
     uint32_t nstore = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -208,8 +211,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       tc_fence_after();
       bool row_ok = row < a.rows;
       if (a.epilogue == SG_EPI_MASK) row_ok = row_ok && ((row % a.T) < a.t_valid);
-      for (int c = 0; c < a.bn; c += 32, ++nstore) {
-        float v[32];
+      // one 32-column group: TMEM -> registers -> epilogue op
+      auto group = [&](int c, float (&v)[32]) {
         tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TC_MAX_BN + c), v);
         const int col = n0 + c;
         if (a.epilogue == SG_EPI_BIAS || a.epilogue == SG_EPI_BIAS_RELU) {
@@ -249,17 +252,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             for (int j = 0; j < 32; ++j) v[j] = 0.f;
           }
         }
+      };
+      for (int c = 0; c < a.bn; c += CW, ++nstore) {
+        float v[32];
+        group(c, v);
+        uint4 packed[8];
+        if (OUT_BF16) {
+          float v2[32];
+          group(c + 32, v2);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * j + 0], v[8 * j + 1]), p1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]), p3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+            packed[j] = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
+                                   *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+            __nv_bfloat162 s0 = __floats2bfloat162_rn(v2[8 * j + 0], v2[8 * j + 1]), s1 = __floats2bfloat162_rn(v2[8 * j + 2], v2[8 * j + 3]);
+            __nv_bfloat162 s2 = __floats2bfloat162_rn(v2[8 * j + 4], v2[8 * j + 5]), s3 = __floats2bfloat162_rn(v2[8 * j + 6], v2[8 * j + 7]);
+            packed[4 + j] = make_uint4(*reinterpret_cast<uint32_t*>(&s0), *reinterpret_cast<uint32_t*>(&s1),
+                                       *reinterpret_cast<uint32_t*>(&s2), *reinterpret_cast<uint32_t*>(&s3));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            packed[j] = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                                   __float_as_uint(v[4 * j + 3]));
+        }
         uint8_t* buf = stg + (nstore & 1) * TC_STG_BYTES;
         if (nstore >= 2) {                                  // the store that last read this buffer must have drained it
           if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           epi_bar();
         }
-        float4* srow = reinterpret_cast<float4*>(buf + r_in * 128);
+        uint4* srow = reinterpret_cast<uint4*>(buf + r_in * 128);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) srow[j ^ (r_in & 7)] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        for (int j = 0; j < 8; ++j) srow[j ^ (r_in & 7)] = packed[j];
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         epi_bar();
-        if (issuer) tma_store_2d(buf, &mapO, col, mt * TC_BM);   // rows / columns beyond the tensor are clipped by TMA
+        if (issuer) tma_store_2d(buf, &mapO, n0 + c, mt * TC_BM);   // rows / columns beyond the tensor are clipped by TMA
       }
       tc_fence_before();
       __syncwarp();
@@ -628,8 +656,10 @@ static int tc_init() {
   int dev = 0;
   SG_CUDA_CHECK(cudaGetDevice(&dev));
   SG_CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-  SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-  SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+  SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+  SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+  SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+  SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES));
   SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc256_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC3_SMEM_BYTES));
   {
@@ -644,12 +674,12 @@ static int tc_init() {
   return SG_OK;
 }
 
-static int make_map_f32(CUtensorMap* m, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+static int make_map(CUtensorMap* m, const void* base, int bf16, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld * sizeof(float)};
-  cuuint32_t box[2] = {TC_BK, box_rows};
+  cuuint64_t strides[1] = {ld * (bf16 ? 2 : 4)};
+  cuuint32_t box[2] = {(cuuint32_t)(bf16 ? 64 : 32), box_rows};       // 128-byte inner box
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
+  CUresult r = g_encode(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { sg_set_error("cuTensorMapEncodeTiled failed (%d): rows=%llu cols=%llu ld=%llu box=%u", (int)r,
@@ -659,11 +689,13 @@ static int make_map_f32(CUtensorMap* m, const float* base, uint64_t rows, uint64
 
 // uses a.Wk, the K-major copy of the weights: [N][taps*cin]
 int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
-  if (precision != SG_PREC_TF32) { sg_set_error("tensor-core path: only SG_PREC_TF32 is built (fp32 storage)"); return SG_EUNSUPPORTED; }
+  if (precision == SG_PREC_FP32) { sg_set_error("sg_conv_tc called in fp32 mode"); return SG_EINVAL; }
+  const int kbe = a.op_bf16 ? 64 : 32;
   if (a.same_utt || a.tap_base != 0) { sg_set_error("sg_conv_tc: 'same' padding is only built for the FFMA path"); return SG_EUNSUPPORTED; }
   int r = tc_init();
   if (r != SG_OK) return r;
-  if (a.cin % TC_BK != 0 || a.N % 32 != 0 || a.lda % 4 != 0 || a.ldo % 4 != 0 || (a.epilogue == SG_EPI_MASK && a.ldmask % 4 != 0)) {
+  if (a.cin % kbe != 0 || a.N % 32 != 0 || a.lda % 8 != 0 || a.ldo % 8 != 0 || (a.out_bf16 && a.N % 64 != 0) ||
+      (a.epilogue == SG_EPI_MASK && !a.bits_in && (a.ldmask % 4 != 0 || a.op_bf16))) {
     sg_set_error("sg_conv_tc: cin %% 32, N %% 32, lda/ldo %% 4 required (cin=%d N=%d)", a.cin, a.N);
     return SG_EINVAL;
   }
@@ -671,22 +703,22 @@ int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
   while (bn > 32 && a.N % bn != 0) bn -= 32;     // largest N-tile (multiple of 32, <= 256) dividing N
   if (a.N % bn != 0) { sg_set_error("sg_conv_tc: N=%d is not a multiple of 32", a.N); return SG_EINVAL; }
   CUtensorMap mapA, mapB;
-  r = make_map_f32(&mapA, a.A, (uint64_t)a.rows, (uint64_t)a.cin, (uint64_t)a.lda, TC_BM);
+  r = make_map(&mapA, a.A, a.op_bf16, (uint64_t)a.rows, (uint64_t)a.cin, (uint64_t)a.lda, TC_BM);
   if (r != SG_OK) return r;
   if (!a.Wk) { sg_set_error("sg_conv_tc: K-major weights missing"); return SG_EINVAL; }
-  r = make_map_f32(&mapB, a.Wk, (uint64_t)a.N, (uint64_t)a.taps * a.cin, (uint64_t)a.taps * a.cin, (uint32_t)bn);
+  r = make_map(&mapB, a.Wk, a.op_bf16, (uint64_t)a.N, (uint64_t)a.taps * a.cin, (uint64_t)a.taps * a.cin, (uint32_t)bn);
   if (r != SG_OK) return r;
   TcArgs t;
   t.bits_out = a.bits_out; t.bits_in = a.bits_in; t.ldbits = a.ldbits;
   if (g_use_256 || g_use_pair) { t.bits_out = nullptr; t.bits_in = nullptr; }   // experimental tile variants keep fp32 masks
   t.bias = a.bias; t.out = a.out; t.ldo = a.ldo; t.mask = a.mask; t.ldmask = a.ldmask;
-  t.rows = a.rows; t.N = a.N; t.bn = bn; t.kchunks = a.cin / TC_BK; t.taps = a.taps; t.tap_step = a.tap_step;
+  t.rows = a.rows; t.N = a.N; t.bn = bn; t.kchunks = a.cin / kbe; t.taps = a.taps; t.tap_step = a.tap_step;
   t.epilogue = a.epilogue; t.T = a.T > 0 ? a.T : 1; t.t_valid = a.t_valid;
   t.m_tiles = (a.rows + TC_BM - 1) / TC_BM; t.n_tiles = a.N / bn;
   if ((a.epilogue == SG_EPI_BIAS || a.epilogue == SG_EPI_BIAS_RELU) && !a.bias) { sg_set_error("sg_conv_tc: bias epilogue without bias"); return SG_EINVAL; }
-  if (g_use_256 && bn == TC_MAX_BN && a.taps * (a.cin / TC_BK) >= 24 && a.rows >= 256 * 64) {
+  if (g_use_256 && !a.op_bf16 && !a.out_bf16 && bn == TC_MAX_BN && a.taps * (a.cin / TC_BK) >= 24 && a.rows >= 256 * 64) {
     CUtensorMap mapA2;
-    r = make_map_f32(&mapA2, a.A, (uint64_t)a.rows, (uint64_t)a.cin, (uint64_t)a.lda, 256);
+    r = make_map(&mapA2, a.A, 0, (uint64_t)a.rows, (uint64_t)a.cin, (uint64_t)a.lda, 256);
     if (r != SG_OK) return r;
     t.m_tiles = (a.rows + 255) / 256;
     int grid3 = t.m_tiles * t.n_tiles;
@@ -695,9 +727,9 @@ int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
     SG_LAUNCH_CHECK();
     return SG_OK;
   }
-  if (g_use_pair && bn >= 64 && bn % 64 == 0 && a.rows > 256) {
+  if (g_use_pair && !a.op_bf16 && !a.out_bf16 && bn >= 64 && bn % 64 == 0 && a.rows > 256) {
     CUtensorMap mapBh;
-    r = make_map_f32(&mapBh, a.Wk, (uint64_t)a.N, (uint64_t)a.taps * a.cin, (uint64_t)a.taps * a.cin, (uint32_t)(bn / 2));
+    r = make_map(&mapBh, a.Wk, 0, (uint64_t)a.N, (uint64_t)a.taps * a.cin, (uint64_t)a.taps * a.cin, (uint32_t)(bn / 2));
     if (r != SG_OK) return r;
     t.m_tiles = (a.rows + 255) / 256;
     int pairs = t.m_tiles * t.n_tiles;
@@ -707,11 +739,14 @@ int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
     return SG_OK;
   }
   CUtensorMap mapO;
-  r = make_map_f32(&mapO, a.out, (uint64_t)a.rows, (uint64_t)a.N, (uint64_t)a.ldo, TC_BM);
+  r = make_map(&mapO, a.out, a.out_bf16, (uint64_t)a.rows, (uint64_t)a.N, (uint64_t)a.ldo, TC_BM);
   if (r != SG_OK) return r;
   int grid = t.m_tiles * t.n_tiles;
   if (grid > g_num_sms) grid = g_num_sms;
-  conv_tc_kernel<0><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mapA, mapB, mapO, t);
+  if (a.op_bf16 && a.out_bf16) conv_tc_kernel<1, 1><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mapA, mapB, mapO, t);
+  else if (a.op_bf16) conv_tc_kernel<1, 0><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mapA, mapB, mapO, t);
+  else if (a.out_bf16) conv_tc_kernel<0, 1><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mapA, mapB, mapO, t);
+  else conv_tc_kernel<0, 0><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mapA, mapB, mapO, t);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }

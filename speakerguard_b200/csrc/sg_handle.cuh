@@ -43,6 +43,8 @@ struct sg_handle {
   float* Wb[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // [taps*coutP, cinP]
   float* Wfk[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // K-major copies for the tensor-core path: [coutP, taps*cinP]
   float* Wbk[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [cinP, taps*coutP]
+  void* Wfk_h[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; // bf16 copies of Wfk / Wbk (SG_PREC_BF16)
+  void* Wbk_h[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   float* bias[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; // [coutP] (BN of the previous layer folded)
   float* bn5_mean = nullptr; float* bn5_istd = nullptr;           // [C5P]
   float* Wfc = nullptr; float* Wfc_b = nullptr; float* bfc = nullptr;     // fc1: [3072,512], [512,3072], [512]

@@ -4,24 +4,29 @@
 // Reference: stats pooling xvecTDNN.py:62; process_emb model/iv_plda.py:411-443 (length-norm
 // with detached norm: xvector_extract.py:31-38; PLDA transform plda.py:73-97); scoring
 // plda.py:140-190; decision model/defended_model.py:167-170; losses attack/utils.py:7-102.
+#include <cuda_bf16.h>
 #include <math.h>
 
 #include "sg_common.cuh"
 #include "sg_head.cuh"
 
+__device__ __forceinline__ float ldf(const float* p) { return *p; }
+__device__ __forceinline__ float ldf(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
 // ---------------------------------------------------------------------------------------------
 // statistics pooling over the valid frames of the last TDNN layer (post-ReLU, BN folded here)
 // grid (C5P/32, B), block (32, 8)
 // ---------------------------------------------------------------------------------------------
-__global__ void pool_fwd_kernel(const float* __restrict__ r5, int T, int Tv, const float* __restrict__ bn_mean,
+template <typename AT>
+__global__ void pool_fwd_kernel(const AT* __restrict__ r5, int T, int Tv, const float* __restrict__ bn_mean,
                                 const float* __restrict__ bn_istd, float* __restrict__ stats,
                                 float* __restrict__ save_mean, float* __restrict__ save_std) {
   __shared__ float part[8][33];
   __shared__ float bc[32];
   const int c = blockIdx.x * 32 + threadIdx.x, r = threadIdx.y, b = blockIdx.y;
-  const float* base = r5 + (size_t)b * T * SG_C5P + c;
+  const AT* base = r5 + (size_t)b * T * SG_C5P + c;
   float s = 0.f;
-  for (int t = r; t < Tv; t += 8) s += base[(size_t)t * SG_C5P];
+  for (int t = r; t < Tv; t += 8) s += ldf(base + (size_t)t * SG_C5P);
   part[r][threadIdx.x] = s;
   __syncthreads();
   if (r == 0) {
@@ -33,7 +38,7 @@ __global__ void pool_fwd_kernel(const float* __restrict__ r5, int T, int Tv, con
   __syncthreads();
   const float mean = bc[threadIdx.x];
   float q = 0.f;
-  for (int t = r; t < Tv; t += 8) { float d = base[(size_t)t * SG_C5P] - mean; q = fmaf(d, d, q); }
+  for (int t = r; t < Tv; t += 8) { float d = ldf(base + (size_t)t * SG_C5P) - mean; q = fmaf(d, d, q); }
   __syncthreads();
   part[r][threadIdx.x] = q;
   __syncthreads();
@@ -53,9 +58,22 @@ __global__ void pool_fwd_kernel(const float* __restrict__ r5, int T, int Tv, con
 
 // d(stats) -> d(pre-ReLU layer-5 activation), ReLU mask and row validity applied
 // grid (C5P/128, B, tsplit), block (32, 8); each thread owns 4 consecutive channels (float4 traffic)
-__global__ void pool_bwd_kernel(const float* __restrict__ r5, int T, int Tv, const float* __restrict__ bn_istd,
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x), b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+  const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4(__nv_bfloat16* p, float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+}
+template <typename AT>
+__global__ void pool_bwd_kernel(const AT* __restrict__ r5, int T, int Tv, const float* __restrict__ bn_istd,
                                 const float* __restrict__ dstats, const float* __restrict__ save_mean,
-                                const float* __restrict__ save_std, float* __restrict__ dA5) {
+                                const float* __restrict__ save_std, AT* __restrict__ dA5) {
   const int c0 = blockIdx.x * 128 + threadIdx.x * 4, b = blockIdx.y;
   float alpha[4], beta[4], mean[4];
 #pragma unroll
@@ -72,13 +90,13 @@ __global__ void pool_bwd_kernel(const float* __restrict__ r5, int T, int Tv, con
   for (int t = blockIdx.z * 8 + threadIdx.y; t < T; t += 8 * gridDim.z) {
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
     if (t < Tv) {
-      const float4 r = *reinterpret_cast<const float4*>(r5 + off + (size_t)t * SG_C5P);
+      const float4 r = ld4(r5 + off + (size_t)t * SG_C5P);
       o.x = r.x > 0.f ? fmaf(beta[0], r.x - mean[0], alpha[0]) : 0.f;
       o.y = r.y > 0.f ? fmaf(beta[1], r.y - mean[1], alpha[1]) : 0.f;
       o.z = r.z > 0.f ? fmaf(beta[2], r.z - mean[2], alpha[2]) : 0.f;
       o.w = r.w > 0.f ? fmaf(beta[3], r.w - mean[3], alpha[3]) : 0.f;
     }
-    *reinterpret_cast<float4*>(dA5 + off + (size_t)t * SG_C5P) = o;
+    st4(dA5 + off + (size_t)t * SG_C5P, o);
   }
 }
 
@@ -328,16 +346,18 @@ __global__ void loss_kernel(const float* __restrict__ scores, const long long* _
 // ---------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------
-int sg_pool_fwd_launch(const float* r5, int B, int T, int Tv, const float* bn_mean, const float* bn_istd,
+int sg_pool_fwd_launch(const void* r5, int bf16, int B, int T, int Tv, const float* bn_mean, const float* bn_istd,
                        float* stats, float* save_mean, float* save_std, cudaStream_t st) {
-  pool_fwd_kernel<<<dim3(SG_C5P / 32, B), dim3(32, 8), 0, st>>>(r5, T, Tv, bn_mean, bn_istd, stats, save_mean, save_std);
+  if (bf16) pool_fwd_kernel<__nv_bfloat16><<<dim3(SG_C5P / 32, B), dim3(32, 8), 0, st>>>((const __nv_bfloat16*)r5, T, Tv, bn_mean, bn_istd, stats, save_mean, save_std);
+  else pool_fwd_kernel<float><<<dim3(SG_C5P / 32, B), dim3(32, 8), 0, st>>>((const float*)r5, T, Tv, bn_mean, bn_istd, stats, save_mean, save_std);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }
-int sg_pool_bwd_launch(const float* r5, int B, int T, int Tv, const float* bn_istd, const float* dstats,
-                       const float* save_mean, const float* save_std, float* dA5, cudaStream_t st) {
+int sg_pool_bwd_launch(const void* r5, int bf16, int B, int T, int Tv, const float* bn_istd, const float* dstats,
+                       const float* save_mean, const float* save_std, void* dA5, cudaStream_t st) {
   int tsplit = (B >= 64) ? 1 : 4;
-  pool_bwd_kernel<<<dim3(SG_C5P / 128, B, tsplit), dim3(32, 8), 0, st>>>(r5, T, Tv, bn_istd, dstats, save_mean, save_std, dA5);
+  if (bf16) pool_bwd_kernel<__nv_bfloat16><<<dim3(SG_C5P / 128, B, tsplit), dim3(32, 8), 0, st>>>((const __nv_bfloat16*)r5, T, Tv, bn_istd, dstats, save_mean, save_std, (__nv_bfloat16*)dA5);
+  else pool_bwd_kernel<float><<<dim3(SG_C5P / 128, B, tsplit), dim3(32, 8), 0, st>>>((const float*)r5, T, Tv, bn_istd, dstats, save_mean, save_std, (float*)dA5);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }

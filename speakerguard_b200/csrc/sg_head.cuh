@@ -26,10 +26,10 @@ int sg_dither_fill_launch(int B, int m, uint64_t seed, uint64_t pass, float* out
 int sg_step_linf_launch(float* x, const float* x0, const float* grad, size_t n, float step, float eps, cudaStream_t st);
 int sg_cmvn_launch(const float* in, int ld_in, float* out, int ld_out, int B, int T, int backward, cudaStream_t st);
 
-int sg_pool_fwd_launch(const float* r5, int B, int T, int Tv, const float* bn_mean, const float* bn_istd,
+int sg_pool_fwd_launch(const void* r5, int bf16, int B, int T, int Tv, const float* bn_mean, const float* bn_istd,
                        float* stats, float* save_mean, float* save_std, cudaStream_t st);
-int sg_pool_bwd_launch(const float* r5, int B, int T, int Tv, const float* bn_istd, const float* dstats,
-                       const float* save_mean, const float* save_std, float* dA5, cudaStream_t st);
+int sg_pool_bwd_launch(const void* r5, int bf16, int B, int T, int Tv, const float* bn_istd, const float* dstats,
+                       const float* save_mean, const float* save_std, void* dA5, cudaStream_t st);
 int sg_head_fwd_launch(const SgHeadConst& H, const float* e2, int B, float* tsave, float* scal, float* emb, cudaStream_t st);
 int sg_head_bwd_launch(const SgHeadConst& H, const float* dq, int B, const float* tsave, const float* scal, float* de2, cudaStream_t st);
 int sg_score_fwd_launch(const SgHeadConst& H, const float* emb, int B, const float* enroll, int S, float threshold,

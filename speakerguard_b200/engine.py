@@ -380,14 +380,19 @@ def default_engine(device) -> "Engine":
 
 
 def debug_conv(eng: "Engine", precision: str, A: torch.Tensor, W: torch.Tensor, bias, rows: int, N: int, cin: int,
-               taps: int, tap_step: int, epilogue: int, mask=None, T: int = 1, t_valid: int = 0) -> torch.Tensor:
-    """One conv-as-GEMM launch through sg_debug_conv.  A [rows, cin] fp32, W [taps*cin, N] fp32."""
+               taps: int, tap_step: int, epilogue: int, mask=None, T: int = 1, t_valid: int = 0,
+               op_bf16: bool = False, out_bf16: bool = False) -> torch.Tensor:
+    """One conv-as-GEMM launch through sg_debug_conv.  A [rows, cin], W [taps*cin, N] (fp32 on entry;
+    converted to bf16 here when op_bf16)."""
     A, W = _f32c(A, eng.device), _f32c(W, eng.device)
     Wk = W.t().contiguous()
-    out = torch.empty(rows, N, device=eng.device, dtype=torch.float32)
+    if op_bf16:
+        A, Wk = A.to(torch.bfloat16).contiguous(), Wk.to(torch.bfloat16).contiguous()
+    out = torch.empty(rows, N, device=eng.device, dtype=torch.bfloat16 if out_bf16 else torch.float32)
     b = None if bias is None else _f32c(bias, eng.device)
     mk = None if mask is None else _f32c(mask, eng.device)
     check(eng.lib.sg_debug_conv(eng._h, _lib.PRECISIONS[precision], _ptr(A), A.shape[1], _ptr(W), _ptr(Wk), _ptr(b),
                                 _ptr(out), N, rows, N, cin, taps, tap_step, epilogue, _ptr(mk),
-                                0 if mk is None else mk.shape[1], T, t_valid, eng.stream), "sg_debug_conv")
+                                0 if mk is None else mk.shape[1], T, t_valid, int(op_bf16), int(out_bf16), eng.stream),
+          "sg_debug_conv")
     return out

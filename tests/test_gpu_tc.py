@@ -94,3 +94,65 @@ def test_tf32_network_vs_fp32_network():
     assert e_emb < 5e-3 and e_sc < 5e-3
     assert torch.equal(res["tf32"][2], res["fp32"][2])
     assert sign_agree > 0.97 and cos > 0.995
+
+
+BF16_SHAPES = [  # rows, cin, N, taps, step, epilogue, op_bf16, out_bf16
+    (1000, 32, 512, 5, 1, 1, False, True),     # layer 1: tf32 operands (fp32 features) -> bf16 activations
+    (1300, 512, 512, 5, 2, 1, True, True),     # layers 2..4 forward
+    (600, 512, 1536, 1, 0, 1, True, True),     # layer 5 forward
+    (900, 1536, 512, 1, 0, 3, True, True),     # dgrad, bf16 in / bf16 out
+    (640, 512, 32, 5, -1, 3, True, False),     # layer-1 dgrad: bf16 gradients -> fp32 feature gradient
+    (40000, 512, 512, 7, -3, 3, True, True),   # long K, many tiles
+]
+
+
+@pytest.mark.parametrize("rows,cin,N,taps,step,epi,opb,outb", BF16_SHAPES)
+def test_tc_conv_bf16(rows, cin, N, taps, step, epi, opb, outb):
+    """bf16 operand / output variants vs fp64 on the bf16-rounded inputs.  Tolerance: fp32 accumulate is exact
+    to ~1e-5; a bf16 output adds one rounding (2^-9 relative)."""
+    from speakerguard_b200.engine import Engine, debug_conv
+    eng = Engine("cuda:0")
+    g = torch.Generator(device="cuda").manual_seed(rows + cin + N + 1)
+    A = torch.randn(rows, cin, device="cuda", generator=g)
+    W = torch.randn(taps * cin, N, device="cuda", generator=g) / (taps * cin) ** 0.5
+    bias = torch.randn(N, device="cuda", generator=g)
+    Ar = A.to(torch.bfloat16).float() if opb else A
+    Wr = W.to(torch.bfloat16).float() if opb else W
+    ref = ref_conv(Ar, Wr, bias, rows, N, cin, taps, step, epi, None, 1, 0)
+    out = debug_conv(eng, "bf16", A, W, bias, rows, N, cin, taps, step, epi, None, 1, 0, op_bf16=opb, out_bf16=outb)
+    torch.cuda.synchronize()
+    assert out.dtype == (torch.bfloat16 if outb else torch.float32)
+    err = float((out.double() - ref).abs().max() / ref.abs().max())
+    print(f"bf16 rows={rows} cin={cin} N={N} taps={taps} opb={opb} outb={outb}: err {err:.2e}")
+    assert err < (6e-3 if outb else 2e-3)
+
+
+def test_bf16_network_vs_fp32_network():
+    """Whole x-vector pass in BF16 mode vs fp32 parity mode.  Stated tolerances for BF16 mode: embeddings /
+    scores 3e-2 relative (row max), >= 90 % of input-gradient signs equal, gradient cosine >= 0.97."""
+    from oracle import sg_oracle as O
+    from speakerguard_b200 import _lib
+    from speakerguard_b200.engine import Engine, make_loss_params
+    p = O.make_xv_params(seed=0)
+    res = {}
+    torch.manual_seed(77)
+    x = ((torch.rand(6, 1, 32000) * 2 - 1) * 0.5)[:, 0].cuda()
+    y = torch.tensor([0, 1, 2, 3, 4, 5]).cuda()
+    for prec in ("fp32", "bf16"):
+        eng = Engine("cuda:0", precision=prec)
+        eng.load_xv(p)
+        feat = eng.cmvn(eng.mfcc_fwd(x, _lib.DITHER_PHILOX, None, seed=3, pass_=0, ld=32), ld_out=32)
+        emb, ws = eng.embed_fwd(feat)
+        scores, dec = eng.score_fwd(emb)
+        _, ds = eng.loss(scores, y, make_loss_params("Entropy"))
+        dfeat = eng.embed_bwd(eng.score_bwd(emb, ds), ws, 6, feat.shape[1])
+        grad = eng.mfcc_bwd(x, eng.cmvn(dfeat, ld_out=32, backward=True), _lib.DITHER_PHILOX, None, seed=3, pass_=0)
+        res[prec] = (emb.cpu(), scores.cpu(), dec.cpu(), grad.cpu())
+    rel = lambda a, b: float(((a - b).abs().max(1)[0] / b.abs().max(1)[0]).max())
+    e_emb, e_sc = rel(res["bf16"][0], res["fp32"][0]), rel(res["bf16"][1], res["fp32"][1])
+    g1, g0 = res["bf16"][3], res["fp32"][3]
+    sign_agree = float((torch.sign(g1) == torch.sign(g0)).float().mean())
+    cos = float((g1 * g0).sum() / (g1.norm() * g0.norm()))
+    print(f"bf16 vs fp32: emb {e_emb:.2e} scores {e_sc:.2e} grad sign agreement {sign_agree:.4f} cosine {cos:.5f}")
+    assert e_emb < 3e-2 and e_sc < 3e-2
+    assert sign_agree > 0.90 and cos > 0.97
