@@ -48,15 +48,15 @@ void sg_set_error(const char* fmt, ...);
 struct alignas(16) SgFeatTables {
   float window[SG_WIN];          // Povey window
   float2 tw[24][32];             // per-lane FFT twiddles: [0..7] pass A, [8..15] pass B, [16..23] untangle
-  int mel_lo[32];                // first FFT bin of filter c
-  int mel_len[32];               // number of bins
-  int mel_off[32];               // offset into mel_w
-  float mel_w[512];              // packed non-zero weights
+  int mel_lo[32];                // first FFT bin of filter c, rounded down to a multiple of 4 (float4 loads)
+  int mel_len[32];               // number of float4 groups
+  int mel_off[32];               // offset into mel_w (floats, multiple of 4)
+  float mel_w[768];              // packed weights, zero-padded to float4 groups
   int bin_c0[256], bin_c1[256];  // per FFT bin: the (<=2) filters it feeds (31 = none)
   float bin_w0[256], bin_w1[256];
-  float dct[SG_NMEL][32];        // dct[n][k] * lifter[k]   (forward: lane k, loop n)
-  float dct_t[32][32];           // dct_t[k][n] = dct[n][k] (backward: lane n, loop k)
-  int mel_maxlen;
+  float dct_kn[32][36];          // [k][n] = D[n][k] * lifter[k]: forward, lane k reads float4 over n (stride 36: conflict-free)
+  float dct_nk[32][36];          // [n][k] (k >= 1; column 0 zero: C0 is the log-energy): adjoint, lane n reads float4 over k
+  int mel_maxlen;                // max number of float4 groups
 };
 
 int sg_feat_tables_build(SgFeatTables* host_out);

@@ -65,21 +65,23 @@ int sg_feat_tables_build(SgFeatTables* t) {
         if (w[c][b] > 0.0) { if (b < lo) lo = b; hi = b; }
       if (hi < 0) lo = 0;
     }
-    int len = hi - lo + 1;
-    if (len < 0) len = 0;
-    t->mel_lo[c] = lo; t->mel_len[c] = len; t->mel_off[c] = off;
-    if (off + len > 512) return SG_EINVAL;
-    for (int i = 0; i < len; ++i) {
-      int b = lo + i;
-      t->mel_w[off + i] = (float)w[c][b];
-      if (w[c][b] > 0.0) {
-        if (t->bin_c0[b] == 31) { t->bin_c0[b] = c; t->bin_w0[b] = (float)w[c][b]; }
-        else if (t->bin_c1[b] == 31) { t->bin_c1[b] = c; t->bin_w1[b] = (float)w[c][b]; }
+    if (hi >= 252) return SG_EINVAL;                      // float4 groups must stay inside P[0..255]
+    const int lo4 = lo & ~3;
+    const int groups = hi >= lo ? (hi - lo4) / 4 + 1 : 0;
+    t->mel_lo[c] = lo4; t->mel_len[c] = groups; t->mel_off[c] = off;
+    if (off + 4 * groups > 768) return SG_EINVAL;
+    for (int i = 0; i < 4 * groups; ++i) {
+      const int b = lo4 + i;
+      const double wv = (b >= lo && b <= hi) ? w[c][b] : 0.0;
+      t->mel_w[off + i] = (float)wv;
+      if (wv > 0.0) {
+        if (t->bin_c0[b] == 31) { t->bin_c0[b] = c; t->bin_w0[b] = (float)wv; }
+        else if (t->bin_c1[b] == 31) { t->bin_c1[b] = c; t->bin_w1[b] = (float)wv; }
         else return SG_EINVAL;   // triangles overlap at most pairwise
       }
     }
-    off += len;
-    if (len > maxlen) maxlen = len;
+    off += 4 * groups;
+    if (groups > maxlen) maxlen = groups;
   }
   t->mel_maxlen = maxlen;
   // DCT-II (ortho) with kaldi's first column and the lifter folded in: kaldi.py:648-666, :788-796
@@ -87,8 +89,8 @@ int sg_feat_tables_build(SgFeatTables* t) {
     for (int k = 0; k < SG_NCEP; ++k) {
       double d = (k == 0) ? sqrt(1.0 / SG_NMEL) : sqrt(2.0 / SG_NMEL) * cos(PI / SG_NMEL * (n + 0.5) * k);
       double lift = 1.0 + 0.5 * 22.0 * sin(PI * k / 22.0);
-      t->dct[n][k] = (float)(d * lift);
-      t->dct_t[k][n] = (float)(d * lift);
+      t->dct_kn[k][n] = (float)(d * lift);
+      t->dct_nk[n][k] = (k == 0) ? 0.f : (float)(d * lift);
     }
   return SG_OK;
 }
@@ -182,10 +184,10 @@ __device__ __forceinline__ void fft_out_to_smem(const float2 (&z)[8], float* sre
     }
 }
 
-// ---- Philox4x32-10 (counter-based dither) -----------------------------------------------------
+// ---- Philox4x32-7 (counter-based dither; 7 rounds pass BigCrush, Salmon et al. 2011) -----------------------------------------------------
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < 7; ++r) {
     uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
     uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
     c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
@@ -200,7 +202,8 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
   float u1 = __uint2float_rn(a) * 2.3283064365386963e-10f + 1.1641532182693481e-10f;
   float u2 = __uint2float_rn(b) * 2.3283064365386963e-10f + 1.1641532182693481e-10f;
-  float r = sqrtf(-2.0f * __logf(u1));
+  const float t2 = -2.0f * __logf(u1);
+  float r = t2 * rsqrtf(fmaxf(t2, 1e-30f));                      // sqrt(t2) without the IEEE sqrt sequence
   float s, c;
   __sincosf(6.283185307179586f * u2, &s, &c);
   return make_float2(r * c, r * s);
@@ -247,6 +250,20 @@ __device__ __forceinline__ void load_frame(Frame& F, const float* __restrict__ x
     }
   }
   float s = 0.f;
+  const bool interior = (fr * SG_SHIFT - SG_HALO >= 0) && (fr * SG_SHIFT - SG_HALO + SG_WIN <= N);   // warp-uniform
+  if (interior) {
+#pragma unroll
+    for (int n0 = 0; n0 < 7; ++n0) {
+      const bool valid = (n0 < 6) || (lane < 8);
+      float ve = 0.f, vo = 0.f;
+      if (valid) {
+        ve = __ldg(xb + p0 + 64 * n0) * 32768.0f + nz[2 * n0];
+        vo = __ldg(xb + p0 + 64 * n0 + 1) * 32768.0f + nz[2 * n0 + 1];
+      }
+      F.fe[n0] = ve; F.fo[n0] = vo;
+      s += ve + vo;
+    }
+  } else
 #pragma unroll
   for (int n0 = 0; n0 < 7; ++n0) {
     const bool valid = (n0 < 6) || (lane < 8);
@@ -309,12 +326,17 @@ __device__ __forceinline__ void frame_spectrum(Frame& F, const SgFeatTables* T, 
   __syncwarp();
 }
 
-// lane c (< 30): mel energy (before the log); kaldi.py:621-630
+// lane c (< 30): mel energy (before the log); kaldi.py:621-630.  Windows are float4-aligned and zero-padded.
 __device__ __forceinline__ float mel_energy(const SgFeatTables* T, const float* P, int lane) {
   const int lo = T->mel_lo[lane], len = T->mel_len[lane], off = T->mel_off[lane];
+  const float4* w4 = reinterpret_cast<const float4*>(&T->mel_w[off]);
+  const float4* p4 = reinterpret_cast<const float4*>(&P[lo]);
   float acc = 0.f;
   for (int i = 0; i < T->mel_maxlen; ++i)
-    if (i < len) acc = fmaf(T->mel_w[off + i], P[lo + i], acc);
+    if (i < len) {
+      const float4 w = w4[i], p = p4[i];
+      acc = fmaf(w.x, p.x, acc); acc = fmaf(w.y, p.y, acc); acc = fmaf(w.z, p.z, acc); acc = fmaf(w.w, p.w, acc);
+    }
   return acc;
 }
 
@@ -349,9 +371,19 @@ mfcc_fwd_kernel(const float* __restrict__ x, int N, int m, int frames_per_cta, D
     frame_spectrum(F, T, sre, sim, P, lane);
     float me = mel_energy(T, P, lane);
     float lm = logf(fmaxf(me, SG_EPS));                            // kaldi.py:631-633
+    __syncwarp();
+    P[lane] = (lane < SG_NMEL) ? lm : 0.f;                         // P is free after mel_energy: lm[32] for the DCT
+    __syncwarp();
     float c = 0.f;
+    {
+      const float4* d4 = reinterpret_cast<const float4*>(&T->dct_kn[lane][0]);
+      const float4* l4 = reinterpret_cast<const float4*>(P);
 #pragma unroll
-    for (int n = 0; n < SG_NMEL; ++n) c = fmaf(__shfl_sync(0xffffffffu, lm, n), T->dct[n][lane], c);
+      for (int g = 0; g < 8; ++g) {
+        const float4 d = d4[g], l = l4[g];
+        c = fmaf(l.x, d.x, c); c = fmaf(l.y, d.y, c); c = fmaf(l.z, d.z, c); c = fmaf(l.w, d.w, c);
+      }
+    }
     if (lane == 0) c = logE;                                       // kaldi.py:799-800
     if (lane >= SG_NCEP) c = 0.f;
     if (lane < ld) raw[((size_t)b * m + fr) * ld + lane] = c;
@@ -408,12 +440,22 @@ mfcc_bwd_kernel(const float* __restrict__ x, int N, int m, int own_frames, Dithe
       // ---- backward: cepstra -> log-mel -> mel -> power -> spectrum -----------------------
       const float dC = (lane < SG_NCEP) ? __ldg(draw + ((size_t)b * m + fr) * ld + lane) : 0.f;
       const float dE = __shfl_sync(0xffffffffu, dC, 0);            // C0 <- log-energy
+      __syncwarp();
+      P[lane] = dC;                                                // P is free after mel_energy: dC[32] (k >= 30 zero)
+      __syncwarp();
       float dM = 0.f;
+      {
+        const float4* d4 = reinterpret_cast<const float4*>(&T->dct_nk[lane][0]);   // column 0 is zero (C0 <- log-energy)
+        const float4* c4 = reinterpret_cast<const float4*>(P);
 #pragma unroll
-      for (int k = 1; k < SG_NCEP; ++k) dM = fmaf(__shfl_sync(0xffffffffu, dC, k), T->dct_t[k][lane], dM);
+        for (int g = 0; g < 8; ++g) {
+          const float4 d = d4[g], cc = c4[g];
+          dM = fmaf(cc.x, d.x, dM); dM = fmaf(cc.y, d.y, dM); dM = fmaf(cc.z, d.z, dM); dM = fmaf(cc.w, d.w, dM);
+        }
+      }
       const float dmel = (lane < SG_NMEL && me > SG_EPS) ? dM / me : 0.f;
       __syncwarp();
-      P[lane] = dmel;                                              // P is free again: reuse as dmel[32]
+      P[lane] = dmel;                                              // reuse as dmel[32]
       __syncwarp();
       float2 dX[8];
 #pragma unroll
