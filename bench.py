@@ -34,6 +34,14 @@ import torch  # noqa: E402
 
 WORKLOAD = "PGD-100 Linf eps=0.002 step=0.0004 CE-untargeted vs xv_plda CSI-E (random-init TDNN+PLDA, L=200, S=10), " \
            "synthetic 3 s 16 kHz utterances, batch 1024 per GPU"
+PRECISION_NOTE = {
+    "fp32": "FFMA everywhere: parity mode, 1e-4 relative vs the reference (tests/test_gpu_xv.py)",
+    "tf32": "TDNN contractions on tcgen05 kind::tf32, fp32 storage (the reference's own GPU default for cuDNN convs); "
+            "vs fp32 mode: embeddings/scores < 1e-3, 98.6 % input-gradient signs equal (tests/test_gpu_tc.py)",
+    "bf16": "TDNN activations/gradients/weights in bf16, fp32 accumulate (tcgen05 kind::f16), everything else fp32; "
+            "vs fp32 mode: embeddings/scores < 1e-3, 97.3 % input-gradient signs equal, cosine 0.996, identical attack "
+            "success rate (tests/test_gpu_tc.py); --precision tf32 / fp32 select the higher-precision modes",
+}
 TDNN = [(30, 512, 5, 1), (512, 512, 5, 2), (512, 512, 7, 3), (512, 512, 1, 1), (512, 1500, 1, 1)]
 
 
@@ -140,7 +148,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("SGB200_PRECISION", "tf32"), choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("SGB200_PRECISION", "bf16"), choices=["fp32", "tf32", "bf16"])
     ap.add_argument("--batch", type=int, default=1024, help="utterances per GPU")
     ap.add_argument("--seconds", type=float, default=3.0)
     ap.add_argument("--iters", type=int, default=100, help="PGD iterations per attack")
@@ -252,6 +260,11 @@ def main():
         import torch.distributed as tdist
         tdist.barrier()
         tdist.destroy_process_group()
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "conv_tc_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(args.precision, {}).get("dram_bytes_per_launch_avg")
     if rank != 0:
         return
     out = {
@@ -260,13 +273,16 @@ def main():
         "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[args.precision], "data": "synthetic",
         "config": {"workload": WORKLOAD, "batch_per_gpu": B, "samples": N, "frames": m, "pgd_iters": iters,
                    "passes_per_step": passes, "dither": "philox (in-kernel N(0,1), fresh per pass)",
-                   "cache": "inputs larger than L2 (activations ~7.6 GB per pass)", "precision": args.precision},
+                   "cache": "inputs larger than L2 (activations 3.8-7.6 GB per pass)", "precision": args.precision,
+                   "precision_note": PRECISION_NOTE[args.precision]},
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": "utt-iter/s", "h2d_bytes_per_step": B * N * 4 + B * 8,
                 "d2h_bytes_per_step": B * N * 4 + B * 8, "ms_per_step": e2e_s * 1000.0,
                 "api": "speakerguard_b200.attack.PGD(model).attack(x, y) with pinned host buffers"},
         "roofline": {"bound": "tensor", "kernel": "TDNN conv-as-GEMM (forward + dgrad launches)", "achieved": achieved,
-                     "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_note,
+                     "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                     "traffic_note": "dram__bytes_read+write per launch, mean over the TDNN launches of one pass (ncu, profiles/conv_tc_traffic.json)",
+                     "peak_source": peak_note,
                      "launches": tdnn_launches, "avg_launch_ms": tdnn_ms / max(tdnn_launches, 1),
                      "algorithmic_flops_per_utt_iter": tdnn_flops_per_utt(m),
                      "share_of_step": tdnn_ms / tot_prof if tot_prof else None},

@@ -431,6 +431,19 @@ mfcc_bwd_kernel(const float* __restrict__ x, int N, int m, int own_frames, Dithe
 
   for (int gf = fs; gf < f1; gf += FEAT_WARPS) {
     const int fr = gf + warp;
+    // prefetch the iterate / clean waveform of the samples this thread will finalise after the group's frames
+    // (the loads then complete under the FFT work instead of stalling the whole CTA in the finalise phase)
+    float pre_x[6], pre_x0[6];
+    if (O.mode == 1) {
+      const int base0 = SG_SHIFT * gf - SG_HALO;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const int n = base0 + threadIdx.x + i * FEAT_THREADS;
+        const bool ok = (threadIdx.x + i * FEAT_THREADS < ACC_LEN) && n >= own_lo && n < own_hi && n >= 0 && n < N;
+        pre_x[i] = ok ? __ldg(xb + n) : 0.f;
+        pre_x0[i] = ok ? __ldg(O.x0 + (size_t)b * N + n) : 0.f;
+      }
+    }
     if (fr < f1) {
       // ---- recompute the forward for this frame ------------------------------------------
       Frame F;
@@ -528,17 +541,20 @@ mfcc_bwd_kernel(const float* __restrict__ x, int N, int m, int own_frames, Dithe
     const int nfr = min(FEAT_WARPS, f1 - gf);
     for (int q = threadIdx.x; q < ACC_LEN; q += FEAT_THREADS) {
       float a = acc[q];
-#pragma unroll
-      for (int w = 0; w < FEAT_WARPS; ++w) {
-        const int jj = q - SG_SHIFT * w;
-        if (w < nfr && jj >= 0 && jj < SG_WIN) a += framebuf[w * SG_WIN + jj];
-      }
+      // frames w with 0 <= q - 160 w < 400 (at most 3), in increasing w: fixed summation order
+      const int w_hi = min(nfr - 1, q / SG_SHIFT);
+      int w_lo = (q - SG_WIN + SG_SHIFT) / SG_SHIFT;               // ceil((q - 399) / 160) for q >= 240
+      if (q < SG_WIN) w_lo = 0;
+      for (int w = w_lo; w <= w_hi; ++w) a += framebuf[w * SG_WIN + q - SG_SHIFT * w];
       acc[q] = a;
     }
     __syncthreads();
     const bool last = (gf + FEAT_WARPS >= f1);
     const int fin = last ? ACC_LEN : ACC_FIN;
-    for (int q = threadIdx.x; q < fin; q += FEAT_THREADS) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const int q = threadIdx.x + i * FEAT_THREADS;
+      if (q >= fin) continue;
       const int n = base + q;
       if (n < own_lo || n >= own_hi || n < 0 || n >= N) continue;
       float g = acc[q];
@@ -556,7 +572,7 @@ mfcc_bwd_kernel(const float* __restrict__ x, int N, int m, int own_frames, Dithe
         float v = O.scale * g;
         O.grad[gi] = O.accumulate ? O.grad[gi] + v : v;
       } else {
-        const float xc = xb[n], x0 = O.x0[gi];
+        const float xc = pre_x[i], x0 = pre_x0[i];
         const float sg = (g > 0.f) ? 1.f : ((g < 0.f) ? -1.f : 0.f);
         float xn = xc + O.step * sg;                               // attack/FGSM.py:65
         const float lo = fmaxf(x0 - O.eps, -1.f), hi = fminf(x0 + O.eps, 1.f);   // attack/PGD.py:48-49
@@ -709,8 +725,10 @@ int sg_feat_fwd_launch(const SgFeatTables* dT, const float* x, int B, int N, int
 }
 
 static int bwd_own_frames(int B, int m) {
+  // 2 CTAs fit per SM (registers): aim for >= 8 waves of 296 CTAs so the tail wave is cheap; every extra
+  // chunk costs 2 halo frames, so keep chunks >= 32 frames
   int chunks = 1;
-  while (chunks < 16 && (long long)B * chunks < 444 && m / (chunks * 2) >= 16) chunks *= 2;
+  while (chunks < 16 && (long long)B * chunks < 8 * 296 && m / (chunks + 1) >= 32) ++chunks;
   return (m + chunks - 1) / chunks;
 }
 
