@@ -24,7 +24,8 @@
 #define TC_STAGE_BYTES (TC_A_BYTES + TC_B_BYTES)
 #define TC_STG_BYTES (TC_BM * 32 * 4)            // 16 KB epilogue staging box (128 rows x 32 fp32), x2
 #define TC_SMEM_BYTES (TC_STAGES * TC_STAGE_BYTES + 2 * TC_STG_BYTES + 1024 /*align*/ + 256 /*barriers*/)
-#define TC_THREADS 192
+#define TC_THREADS 192                // experimental variants: TMA warp, MMA warp, 4 epilogue warps
+#define TC_MAIN_THREADS 320           // main kernel: TMA warp, MMA warp, 2 x 4 epilogue warps
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -60,7 +61,7 @@ __device__ __forceinline__ void tma_store_2d(const void* smem_src, const CUtenso
                ::"l"((uint64_t)map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -113,7 +114,7 @@ struct TcArgs {
 };
 
 template <int KIND_BF16, int OUT_BF16>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_MAIN_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ CUtensorMap mapO, TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -133,7 +134,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -194,12 +195,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
     }
   } else {
-    // ===== epilogue: warps 2..5; a warp may only touch TMEM lanes 32*(warp%4) .. +31 =====
-    // TMEM -> registers -> bias / ReLU / mask -> swizzled smem staging box (128 rows x 32 cols) -> TMA store.
-    // (direct st.global from one-row-per-thread registers ran the short-K layers at ~2 TB/s of output.)
+    // ===== epilogue: warps 2..9 = two groups of four; a warp may only touch TMEM lanes 32*(warp%4) .. +31 =====
+    // TMEM -> registers -> bias / ReLU / mask -> swizzled smem staging box (128 rows x 128 B) -> TMA store.
+    // (direct st.global from one-row-per-thread registers ran the short-K layers at ~2 TB/s of output; with a
+    // single group of four warps the short-K layers were still epilogue-bound, so two groups take alternate
+    // column chunks, each with its own staging box and named barrier.)
     const int q = warp & 3;
+    const int grp = (warp - 2) >> 2;                      // 0: warps 2..5, 1: warps 6..9
     const int r_in = q * 32 + lane;                       // row within the tile
-    const bool issuer = (warp == 2 && lane == 0);
+    const bool issuer = (((warp - 2) & 3) == 0 && lane == 0);
+    uint8_t* buf = stg + grp * TC_STG_BYTES;
     constexpr int CW = OUT_BF16 ? 64 : 32;                // columns per 128-byte staging row
     int acc = 0; uint32_t acc_phase = 0;
     uint32_t nstore = 0;
@@ -253,7 +258,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           }
         }
       };
-      for (int c = 0; c < a.bn; c += CW, ++nstore) {
+      for (int c = grp * CW; c < a.bn; c += 2 * CW, ++nstore) {
         float v[32];
         group(c, v);
         uint4 packed[8];
@@ -277,16 +282,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             packed[j] = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
                                    __float_as_uint(v[4 * j + 3]));
         }
-        uint8_t* buf = stg + (nstore & 1) * TC_STG_BYTES;
-        if (nstore >= 2) {                                  // the store that last read this buffer must have drained it
-          if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          epi_bar();
+        if (nstore >= 1) {                                  // this group's previous store must have drained the box
+          if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          epi_bar(1 + grp);
         }
         uint4* srow = reinterpret_cast<uint4*>(buf + r_in * 128);
 #pragma unroll
         for (int j = 0; j < 8; ++j) srow[j ^ (r_in & 7)] = packed[j];
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        epi_bar();
+        epi_bar(1 + grp);
         if (issuer) tma_store_2d(buf, &mapO, n0 + c, mt * TC_BM);   // rows / columns beyond the tensor are clipped by TMA
       }
       tc_fence_before();
@@ -743,10 +747,10 @@ int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
   if (r != SG_OK) return r;
   int grid = t.m_tiles * t.n_tiles;
   if (grid > g_num_sms) grid = g_num_sms;
-  if (a.op_bf16 && a.out_bf16) conv_tc_kernel<1, 1><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mapA, mapB, mapO, t);
-  else if (a.op_bf16) conv_tc_kernel<1, 0><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mapA, mapB, mapO, t);
-  else if (a.out_bf16) conv_tc_kernel<0, 1><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mapA, mapB, mapO, t);
-  else conv_tc_kernel<0, 0><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mapA, mapB, mapO, t);
+  if (a.op_bf16 && a.out_bf16) conv_tc_kernel<1, 1><<<grid, TC_MAIN_THREADS, TC_SMEM_BYTES, st>>>(mapA, mapB, mapO, t);
+  else if (a.op_bf16) conv_tc_kernel<1, 0><<<grid, TC_MAIN_THREADS, TC_SMEM_BYTES, st>>>(mapA, mapB, mapO, t);
+  else if (a.out_bf16) conv_tc_kernel<0, 1><<<grid, TC_MAIN_THREADS, TC_SMEM_BYTES, st>>>(mapA, mapB, mapO, t);
+  else conv_tc_kernel<0, 0><<<grid, TC_MAIN_THREADS, TC_SMEM_BYTES, st>>>(mapA, mapB, mapO, t);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }

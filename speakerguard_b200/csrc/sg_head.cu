@@ -10,54 +10,6 @@
 #include "sg_common.cuh"
 #include "sg_head.cuh"
 
-__device__ __forceinline__ float ldf(const float* p) { return *p; }
-__device__ __forceinline__ float ldf(const __nv_bfloat16* p) { return __bfloat162float(*p); }
-
-// ---------------------------------------------------------------------------------------------
-// statistics pooling over the valid frames of the last TDNN layer (post-ReLU, BN folded here)
-// grid (C5P/32, B), block (32, 8)
-// ---------------------------------------------------------------------------------------------
-template <typename AT>
-__global__ void pool_fwd_kernel(const AT* __restrict__ r5, int T, int Tv, const float* __restrict__ bn_mean,
-                                const float* __restrict__ bn_istd, float* __restrict__ stats,
-                                float* __restrict__ save_mean, float* __restrict__ save_std) {
-  __shared__ float part[8][33];
-  __shared__ float bc[32];
-  const int c = blockIdx.x * 32 + threadIdx.x, r = threadIdx.y, b = blockIdx.y;
-  const AT* base = r5 + (size_t)b * T * SG_C5P + c;
-  float s = 0.f;
-  for (int t = r; t < Tv; t += 8) s += ldf(base + (size_t)t * SG_C5P);
-  part[r][threadIdx.x] = s;
-  __syncthreads();
-  if (r == 0) {
-    float a = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) a += part[i][threadIdx.x];
-    bc[threadIdx.x] = a / (float)Tv;
-  }
-  __syncthreads();
-  const float mean = bc[threadIdx.x];
-  float q = 0.f;
-  for (int t = r; t < Tv; t += 8) { float d = ldf(base + (size_t)t * SG_C5P) - mean; q = fmaf(d, d, q); }
-  __syncthreads();
-  part[r][threadIdx.x] = q;
-  __syncthreads();
-  if (r == 0) {
-    float a = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) a += part[i][threadIdx.x];
-    const float sd = sqrtf(a / (float)(Tv - 1));                   // unbiased (torch.std default)
-    const bool real = c < SG_C5;
-    const float mu = real ? bn_mean[c] : 0.f, is = real ? bn_istd[c] : 0.f;
-    stats[(size_t)b * SG_STATS + c] = real ? (mean - mu) * is : 0.f;
-    stats[(size_t)b * SG_STATS + SG_C5P + c] = real ? sd * is : 0.f;
-    save_mean[(size_t)b * SG_C5P + c] = mean;
-    save_std[(size_t)b * SG_C5P + c] = sd;
-  }
-}
-
-// d(stats) -> d(pre-ReLU layer-5 activation), ReLU mask and row validity applied
-// grid (C5P/128, B, tsplit), block (32, 8); each thread owns 4 consecutive channels (float4 traffic)
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ float4 ld4(const __nv_bfloat16* p) {
   const uint2 u = *reinterpret_cast<const uint2*>(p);
@@ -70,6 +22,65 @@ __device__ __forceinline__ void st4(__nv_bfloat16* p, float4 v) {
   __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
   *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
 }
+__device__ __forceinline__ float ldf(const float* p) { return *p; }
+__device__ __forceinline__ float ldf(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+// ---------------------------------------------------------------------------------------------
+// statistics pooling over the valid frames of the last TDNN layer (post-ReLU, BN folded here)
+// ---------------------------------------------------------------------------------------------
+template <typename AT>
+__global__ void pool_fwd_kernel(const AT* __restrict__ r5, int T, int Tv, const float* __restrict__ bn_mean,
+                                const float* __restrict__ bn_istd, float* __restrict__ stats,
+                                float* __restrict__ save_mean, float* __restrict__ save_std) {
+  // grid (C5P/128, B), block (32, 8): each thread owns 4 consecutive channels, 8 row lanes per channel group
+  __shared__ float4 part[8][32];
+  __shared__ float4 bc[32];
+  const int c0 = blockIdx.x * 128 + threadIdx.x * 4, r = threadIdx.y, b = blockIdx.y;
+  const AT* base = r5 + (size_t)b * T * SG_C5P + c0;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = r; t < Tv; t += 8) { const float4 v = ld4(base + (size_t)t * SG_C5P); s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
+  part[r][threadIdx.x] = s;
+  __syncthreads();
+  if (r == 0) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float4 v = part[i][threadIdx.x]; a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
+    const float inv = 1.f / (float)Tv;
+    bc[threadIdx.x] = make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
+  }
+  __syncthreads();
+  const float4 mean = bc[threadIdx.x];
+  float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = r; t < Tv; t += 8) {
+    const float4 v = ld4(base + (size_t)t * SG_C5P);
+    const float dx = v.x - mean.x, dy = v.y - mean.y, dz = v.z - mean.z, dw = v.w - mean.w;
+    q.x = fmaf(dx, dx, q.x); q.y = fmaf(dy, dy, q.y); q.z = fmaf(dz, dz, q.z); q.w = fmaf(dw, dw, q.w);
+  }
+  __syncthreads();
+  part[r][threadIdx.x] = q;
+  __syncthreads();
+  if (r == 0) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float4 v = part[i][threadIdx.x]; a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
+    const float inv = 1.f / (float)(Tv - 1);                       // unbiased (torch.std default)
+    const float sd[4] = {sqrtf(a.x * inv), sqrtf(a.y * inv), sqrtf(a.z * inv), sqrtf(a.w * inv)};
+    const float mu4[4] = {mean.x, mean.y, mean.z, mean.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = c0 + i;
+      const bool real = c < SG_C5;
+      const float mu = real ? bn_mean[c] : 0.f, is = real ? bn_istd[c] : 0.f;
+      stats[(size_t)b * SG_STATS + c] = real ? (mu4[i] - mu) * is : 0.f;
+      stats[(size_t)b * SG_STATS + SG_C5P + c] = real ? sd[i] * is : 0.f;
+      save_mean[(size_t)b * SG_C5P + c] = mu4[i];
+      save_std[(size_t)b * SG_C5P + c] = sd[i];
+    }
+  }
+}
+
+// d(stats) -> d(pre-ReLU layer-5 activation), ReLU mask and row validity applied
+// grid (C5P/128, B, tsplit), block (32, 8); each thread owns 4 consecutive channels (float4 traffic)
 template <typename AT>
 __global__ void pool_bwd_kernel(const AT* __restrict__ r5, int T, int Tv, const float* __restrict__ bn_istd,
                                 const float* __restrict__ dstats, const float* __restrict__ save_mean,
@@ -348,8 +359,8 @@ __global__ void loss_kernel(const float* __restrict__ scores, const long long* _
 // ---------------------------------------------------------------------------------------------
 int sg_pool_fwd_launch(const void* r5, int bf16, int B, int T, int Tv, const float* bn_mean, const float* bn_istd,
                        float* stats, float* save_mean, float* save_std, cudaStream_t st) {
-  if (bf16) pool_fwd_kernel<__nv_bfloat16><<<dim3(SG_C5P / 32, B), dim3(32, 8), 0, st>>>((const __nv_bfloat16*)r5, T, Tv, bn_mean, bn_istd, stats, save_mean, save_std);
-  else pool_fwd_kernel<float><<<dim3(SG_C5P / 32, B), dim3(32, 8), 0, st>>>((const float*)r5, T, Tv, bn_mean, bn_istd, stats, save_mean, save_std);
+  if (bf16) pool_fwd_kernel<__nv_bfloat16><<<dim3(SG_C5P / 128, B), dim3(32, 8), 0, st>>>((const __nv_bfloat16*)r5, T, Tv, bn_mean, bn_istd, stats, save_mean, save_std);
+  else pool_fwd_kernel<float><<<dim3(SG_C5P / 128, B), dim3(32, 8), 0, st>>>((const float*)r5, T, Tv, bn_mean, bn_istd, stats, save_mean, save_std);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }

@@ -156,3 +156,33 @@ def test_bf16_network_vs_fp32_network():
     print(f"bf16 vs fp32: emb {e_emb:.2e} scores {e_sc:.2e} grad sign agreement {sign_agree:.4f} cosine {cos:.5f}")
     assert e_emb < 3e-2 and e_sc < 3e-2
     assert sign_agree > 0.90 and cos > 0.97
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+def test_fused_pgd_loop_in_tensor_core_modes_matches_fp32_outcome(prec):
+    """PGD-5 through sg_pgd_run in the tensor-core modes: same decisions / success as the fp32 parity mode on this
+    batch, iterates inside the epsilon ball, and >= 90 % of the perturbation signs equal after 5 steps."""
+    from oracle import sg_oracle as O
+    from speakerguard_b200 import _lib
+    from speakerguard_b200.engine import Engine, make_loss_params
+    p = O.make_xv_params(seed=0)
+    torch.manual_seed(5)
+    x = ((torch.rand(8, 1, 32000) * 2 - 1) * 0.5)[:, 0].cuda()
+    y = torch.randint(0, 10, (8,)).cuda()
+    out = {}
+    for mode in ("fp32", prec):
+        eng = Engine("cuda:0", precision=mode)
+        eng.load_xv(p)
+        xa = x.clone()
+        dec, scores, hist = eng.pgd_run(xa, x, y, max_iter=5, epsilon=0.002, step_size=0.0004, lp=make_loss_params("Entropy"),
+                                        dither_mode=_lib.DITHER_PHILOX, seed=11, want_loss_hist=True)
+        out[mode] = (xa.cpu(), dec.cpu(), hist.cpu())
+    xa0, dec0, h0 = out["fp32"]
+    xa1, dec1, h1 = out[prec]
+    assert float((xa1 - x.cpu()).abs().max()) <= 0.002 + 1e-7
+    assert torch.equal(dec0, dec1)
+    agree = float((torch.sign(xa1 - x.cpu()) == torch.sign(xa0 - x.cpu())).float().mean())
+    print(f"{prec}: perturbation sign agreement after 5 PGD steps {agree:.4f}; final loss rel diff "
+          f"{float((h1[-1] - h0[-1]).abs().max() / h0[-1].abs().max()):.3e}")
+    assert agree > 0.90
+    assert float((h1[-1] - h0[-1]).abs().max()) < 0.05 * float(h0[-1].abs().max())
