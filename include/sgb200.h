@@ -226,6 +226,56 @@ int sg_feco_means_fwd(sg_handle* h, const float* feat, int ld, const int32_t* id
 int sg_feco_means_bwd(sg_handle* h, const float* dout, const int32_t* ids, const int32_t* counts, int B,
                       int n, int dim, int k, int force, float* dfeat, sg_stream stream);
 
+/* ---- i-vector system (BASELINE config 5) --------------------------------------------------------
+ * iv_plda (model/iv_plda.py:17-153): 24 MFCC (the first 24 columns of sg_mfcc_fwd) -> add_delta
+ * (:248-293) -> sliding CMVN over the 72 columns (:296-377) -> full-covariance UBM posteriors and
+ * Baum-Welch statistics (model/_iv_plda/gmm.py:120-171) -> i-vector (model/_iv_plda/
+ * ivector_extract.py:94-114) -> process_emb (:411-443) -> the PLDA back-end shared with xv_plda
+ * (sg_plda_score_fwd / sg_plda_score_bwd, sg_loss_fwd_bwd).
+ * sg_iv_weights: every matrix dense row-major fp32 (the reference's packed Kaldi text matrices
+ * are unpacked by the host class):
+ *   gmm_gconsts [C], gmm_means_invcovars [C,F], gmm_invcovars [C,F,F]      (gmm.py:73-118)
+ *   ive_T [C,F,D], ive_sigma_inv [C,F,F], ive_offset                       (ivector_extract.py:25-92)
+ *   emb_mean [D], lda [L,D+1] (offset in the last column), plda_* and enroll [S,L] as sg_xv_weights.
+ * C must be a multiple of 16.  All contractions of this path run in fp32 (FFMA) whatever the
+ * handle's precision; the per-utterance SPD solve is an fp64 Cholesky.
+ * sg_iv_embed_fwd: feat [B,T,ld] CMVN'd features -> emb [B,L] (extract_emb, model/iv_plda.py:380-396).
+ * sg_iv_embed_bwd: adjoint, using what the forward left in `ws` (sg_iv_ws_bytes(h,B,T) bytes);
+ *   dfeat [B,T,ld], columns >= F written as zero.
+ * sg_iv_stage_read: intermediate results of the last forward on `ws` (tests, diagnostics).
+ * sg_add_delta_fwd/bwd: order-2, window-3 deltas with replicated edges, [B,T,F] <-> [B,T,3F].
+ * sg_cmvn_cols: sg_cmvn_fwd/bwd (backward != 0: adjoint) for any number of columns. */
+typedef struct {
+  int C, F, D, L, S;
+  const float* gmm_gconsts;
+  const float* gmm_means_invcovars;
+  const float* gmm_invcovars;
+  const float* ive_T;
+  const float* ive_sigma_inv;
+  float ive_offset;
+  const float* emb_mean;
+  const float* lda;
+  const float* plda_mean;
+  const float* plda_transform;
+  const float* plda_psi;
+  const float* enroll;
+} sg_iv_weights;
+enum { SG_IV_STAGE_POST = 0, SG_IV_STAGE_STATS = 1, SG_IV_STAGE_IVECTOR = 2 };
+int sg_load_iv(sg_handle* h, const sg_iv_weights* w);
+size_t sg_iv_ws_bytes(const sg_handle* h, int B, int T);
+int sg_iv_embed_fwd(sg_handle* h, const float* feat, int ld, int B, int T, void* ws, float* emb,
+                    sg_stream stream);
+int sg_iv_embed_bwd(sg_handle* h, const float* demb, int B, int T, void* ws, float* dfeat, int ld,
+                    sg_stream stream);
+int sg_iv_stage_read(sg_handle* h, const void* ws, int B, int T, int stage, float* out,
+                     sg_stream stream);
+int sg_add_delta_fwd(sg_handle* h, const float* in, int ld_in, float* out, int ld_out, int B, int T,
+                     int F, sg_stream stream);
+int sg_add_delta_bwd(sg_handle* h, const float* dout, int ld_in, float* din, int ld_out, int B, int T,
+                     int F, sg_stream stream);
+int sg_cmvn_cols(sg_handle* h, const float* in, int ld_in, float* out, int ld_out, int ncol, int B,
+                 int T, int backward, sg_stream stream);
+
 /* ---- test hook: one conv-as-GEMM launch on either arithmetic path -----------------------------
  * out[p,n] = epi(sum_{tap,c} A[p + tap*tap_step, c] * W[tap*cin + c, n]); W is [taps*cin, N]
  * (FFMA path), Wk its K-major copy [N, taps*cin] (tcgen05 path); epilogue 0 bias, 1 bias+ReLU,
@@ -244,7 +294,7 @@ int sg_debug_conv(sg_handle* h, int precision, const float* A, int lda, const fl
  * uses this for the per-kernel share of a step and for the roofline of the dominant kernel. */
 enum { SG_PROF_MFCC_FWD = 0, SG_PROF_MFCC_BWD, SG_PROF_CMVN, SG_PROF_TDNN_FWD, SG_PROF_TDNN_BWD,
        SG_PROF_POOL, SG_PROF_HEAD_GEMM, SG_PROF_HEAD, SG_PROF_LOSS, SG_PROF_STEP, SG_PROF_AUDIONET,
-       SG_PROF_CW2, SG_PROF_COUNT };
+       SG_PROF_CW2, SG_PROF_IV_GEMM, SG_PROF_IV, SG_PROF_COUNT };
 int sg_profile_enable(sg_handle* h, int enable);
 int sg_profile_read(sg_handle* h, int category, double* total_ms, long long* launches);
 const char* sg_profile_name(int category);

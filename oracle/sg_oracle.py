@@ -358,10 +358,10 @@ def resolve_loss(loss_name="Entropy", targeted=False, confidence=0.0, task="CSI"
 # ----------------------------------------------------------------------------------------------
 # FGSM / PGD (attack/FGSM.py:38-98, attack/PGD.py:40-79, adaptive_attack/EOT.py:16-54, EOT_size 1)
 # ----------------------------------------------------------------------------------------------
-def xv_loss_and_grad(x: torch.Tensor, y: torch.Tensor, p, loss_fn, dither=None, flips=None, preacts=None):
-    """One EOT pass with E=1: scores, loss, d(sum loss)/dx, decisions."""
+def xv_loss_and_grad(x: torch.Tensor, y: torch.Tensor, p, loss_fn, dither=None, flips=None, preacts=None, system="xv"):
+    """One EOT pass with E=1: scores, loss, d(sum loss)/dx, decisions.  system: 'xv' (x-vector) | 'iv' (i-vector)."""
     xr = x.detach().clone().requires_grad_(True)
-    scores = xv_forward(xr, p, dither, flips=flips, preacts=preacts)
+    scores = iv_forward(xr, p, dither) if system == "iv" else xv_forward(xr, p, dither, flips=flips, preacts=preacts)
     loss = loss_fn(scores, y)
     loss.backward(torch.ones_like(loss))                          # EOT.py:35
     thr = p.get("threshold", -math.inf)
@@ -370,7 +370,7 @@ def xv_loss_and_grad(x: torch.Tensor, y: torch.Tensor, p, loss_fn, dither=None, 
 
 def pgd_attack(x: torch.Tensor, y: torch.Tensor, p, epsilon=0.002, step_size=0.0004, max_iter=10,
                loss_name="Entropy", targeted=False, task="CSI", dither: Optional[torch.Tensor] = None,
-               fgsm: bool = False, x_init: Optional[torch.Tensor] = None):
+               fgsm: bool = False, x_init: Optional[torch.Tensor] = None, system: str = "xv"):
     """x [B,N].  dither [max_iter+1,B,m,400] or None.  Returns (adv [B,N], success list, info).
     FGSM = one step of size epsilon with [-1,1] bounds (attack/FGSM.py:35-36,74-81)."""
     thr = p.get("threshold", None)
@@ -387,7 +387,7 @@ def pgd_attack(x: torch.Tensor, y: torch.Tensor, p, epsilon=0.002, step_size=0.0
     success = None
     for it in range(max_iter + 1):
         d = None if dither is None else dither[it]
-        scores, loss, grad, dec = xv_loss_and_grad(xa, y, p, loss_fn, d)
+        scores, loss, grad, dec = xv_loss_and_grad(xa, y, p, loss_fn, d, system=system)
         info["loss"].append(loss)
         info["decisions"].append(dec)
         success = (dec == y).tolist() if targeted else (dec != y).tolist()   # Attack.py:11-15
@@ -584,3 +584,110 @@ def cw2_attack(x: torch.Tensor, y: torch.Tensor, score_fn, targeted=False, confi
                     const[jj] *= 10
     success = [s != -2 for s in g_best_score]
     return g_best_x, success, {"const": const, "best_l2": g_best_l2}
+
+
+# ----------------------------------------------------------------------------------------------
+# iv_plda path (model/iv_plda.py:197-293, :380-396; model/_iv_plda/gmm.py:120-171;
+# model/_iv_plda/ivector_extract.py:94-125): MFCC (24 ceps) -> deltas -> CMVN -> UBM posteriors
+# -> Baum-Welch statistics -> i-vector -> LDA / length-norm / PLDA (shared with xv_plda)
+# ----------------------------------------------------------------------------------------------
+def make_iv_params(seed: int = 0, C: int = 64, Fd: int = 72, D: int = 40, L: int = 30, S: int = 1):
+    """Synthetic full-covariance UBM + i-vector extractor + back-end, sized by the arguments
+    (BASELINE config 5 uses C=2048, Fd=72, D=400, L=200)."""
+    g = torch.Generator().manual_seed(seed + 31337)
+    p = {}
+    mu = 3.0 * torch.randn(C, Fd, generator=g)
+    A = torch.randn(C, Fd, Fd, generator=g) / math.sqrt(Fd)
+    invcov = 0.05 * (A @ A.transpose(1, 2)) + 0.06 * torch.eye(Fd)           # SPD, std ~ 3-4 per dim
+    invcov = 0.5 * (invcov + invcov.transpose(1, 2))
+    w = torch.softmax(torch.randn(C, generator=g), 0)
+    p["gmm.invcovars"] = invcov
+    p["gmm.means_invcovars"] = (invcov @ mu.unsqueeze(-1)).squeeze(-1)
+    logdet = torch.linalg.slogdet(invcov.double())[1].float()
+    quad = (mu.unsqueeze(1) @ invcov @ mu.unsqueeze(-1)).flatten()
+    p["gmm.gconsts"] = torch.log(w) - 0.5 * (Fd * math.log(2 * math.pi) - logdet + quad)
+    p["gmm.weights"] = w
+    p["ive.T"] = 0.3 * torch.randn(C, Fd, D, generator=g)
+    B_ = torch.randn(C, Fd, Fd, generator=g) / math.sqrt(Fd)
+    sig = 0.05 * (B_ @ B_.transpose(1, 2)) + 0.06 * torch.eye(Fd)
+    p["ive.sigma_inv"] = 0.5 * (sig + sig.transpose(1, 2))
+    p["ive.offset"] = torch.tensor(5.0)
+    p["plda.mean"] = _round6(0.1 * torch.randn(L, generator=g))
+    p["plda.transform"] = _round6(torch.randn(L, L, generator=g) / math.sqrt(L))
+    p["plda.psi"] = _round6(torch.randn(L, generator=g).abs() + 0.1)
+    p["emb_mean"] = _round6(0.1 * torch.randn(D, generator=g))
+    p["lda"] = _round6(torch.randn(L, D + 1, generator=g) / math.sqrt(D))
+    p["enroll"] = torch.randn(S, L, generator=g)
+    return p
+
+
+def delta_scales(window: int = 3, order: int = 2) -> List[torch.Tensor]:
+    """Kaldi delta filters, model/iv_plda.py:274-293 (get_scales)."""
+    scales = [torch.tensor([1.0])]
+    for _ in range(order):
+        prev = scales[-1]
+        po = (prev.numel() - 1) // 2
+        cur = torch.zeros(prev.numel() + 2 * window)
+        norm = 0.0
+        for j in range(-window, window + 1):
+            norm += j * j
+            for k in range(-po, po + 1):
+                cur[j + k + po + window] += j * prev[k + po]
+        scales.append(cur / norm)
+    return scales
+
+
+def add_delta(feat: torch.Tensor, window: int = 3, order: int = 2) -> torch.Tensor:
+    """[B,T,F] -> [B,T,F*(order+1)], edge frames replicated (model/iv_plda.py:248-271)."""
+    B, T, Fd = feat.shape
+    outs = []
+    for s in delta_scales(window, order):
+        off = (s.numel() - 1) // 2
+        idx = (torch.arange(T).view(-1, 1) + torch.arange(-off, off + 1).view(1, -1)).clamp(0, T - 1)   # [T,2off+1]
+        outs.append((feat[:, idx, :] * s.to(feat.dtype).view(1, 1, -1, 1)).sum(2))
+    return torch.cat(outs, dim=2)
+
+
+def gmm_loglike(x: torch.Tensor, p) -> torch.Tensor:
+    """x [T,Fd] -> component log-likelihoods [T,C] (gmm.py:120-131)."""
+    dt = x.dtype
+    lin = x @ p["gmm.means_invcovars"].to(dt).T
+    quad = torch.einsum("tf,cfg,tg->tc", x, p["gmm.invcovars"].to(dt), x)
+    return lin - 0.5 * quad + p["gmm.gconsts"].to(dt)
+
+
+def iv_stats(x: torch.Tensor, p) -> Tuple[torch.Tensor, torch.Tensor]:
+    post = torch.softmax(gmm_loglike(x, p), -1)                 # gmm.py:133-136
+    return post.sum(0), post.T @ x                              # gmm.py:166-171
+
+
+def ivector(N: torch.Tensor, Fs: torch.Tensor, p) -> torch.Tensor:
+    """Zeroth [C] / first [C,Fd] order statistics -> i-vector [D] (ivector_extract.py:94-114)."""
+    dt = N.dtype
+    T, Si = p["ive.T"].to(dt), p["ive.sigma_inv"].to(dt)
+    TtS = T.transpose(1, 2) @ Si                                # [C,D,Fd]
+    Lm = torch.eye(T.shape[2], dtype=dt) + (N.view(-1, 1, 1) * (TtS @ T)).sum(0)
+    lin = (TtS @ Fs.unsqueeze(-1)).sum(dim=(0, 2))
+    off = p["ive.offset"].to(dt)
+    lin = lin + off * F.one_hot(torch.tensor(0), lin.numel()).to(dt)
+    iv = torch.linalg.solve(Lm, lin)                            # reference: torch.inverse(L) @ linear
+    return iv - off * F.one_hot(torch.tensor(0), iv.numel()).to(dt)
+
+
+def iv_forward(x: torch.Tensor, p, dither: Optional[torch.Tensor] = None, return_all: bool = False):
+    """x [B,N] -> scores [B,S] through the i-vector system (iv_plda.forward with flag 0)."""
+    if x.dim() == 3:
+        x = x[:, 0]
+    raw = mfcc(x, dither, num_ceps=24)                           # model/iv_plda.py:203-237
+    delta = add_delta(raw)
+    feat = cmvn(delta)
+    ivs = []
+    for f in feat:                                               # per utterance (model/iv_plda.py:380-396)
+        N, Fs = iv_stats(f, p)
+        ivs.append(ivector(N, Fs, p))
+    iv = torch.stack(ivs)
+    emb = process_emb(iv, p)
+    scores = plda_scores(emb, p)
+    if return_all:
+        return {"raw": raw, "delta": delta, "feat": feat, "ivector": iv, "emb": emb, "scores": scores}
+    return scores

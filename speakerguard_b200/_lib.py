@@ -16,7 +16,8 @@ SG_OK, SG_EINVAL, SG_ECUDA, SG_ESTATE, SG_EUNSUPPORTED = 0, -1, -2, -3, -4
 PREC_FP32, PREC_TF32, PREC_BF16 = 0, 1, 2
 DITHER_OFF, DITHER_TENSOR, DITHER_PHILOX = 0, 1, 2
 LOSS_CE, LOSS_MARGIN = 0, 1
-PROF_COUNT = 12
+PROF_COUNT = 14
+IV_STAGE_POST, IV_STAGE_STATS, IV_STAGE_IVECTOR = 0, 1, 2
 TASK_CSI, TASK_SV, TASK_OSI = 0, 1, 2
 TASKS = {"CSI": TASK_CSI, "SV": TASK_SV, "OSI": TASK_OSI}
 PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "bf16": PREC_BF16}
@@ -31,6 +32,13 @@ class XvWeights(C.Structure):
                 ("fc1_w", _vp), ("fc1_b", _vp), ("emb_mean", _vp), ("lda", _vp), ("plda_mean", _vp),
                 ("plda_transform", _vp), ("plda_psi", _vp), ("enroll", _vp),
                 ("L", C.c_int), ("S", C.c_int), ("bn_eps", C.c_float)]
+
+
+class IvWeights(C.Structure):
+    _fields_ = [("C", C.c_int), ("F", C.c_int), ("D", C.c_int), ("L", C.c_int), ("S", C.c_int),
+                ("gmm_gconsts", _vp), ("gmm_means_invcovars", _vp), ("gmm_invcovars", _vp), ("ive_T", _vp),
+                ("ive_sigma_inv", _vp), ("ive_offset", C.c_float), ("emb_mean", _vp), ("lda", _vp), ("plda_mean", _vp),
+                ("plda_transform", _vp), ("plda_psi", _vp), ("enroll", _vp)]
 
 
 class LossParams(C.Structure):
@@ -96,6 +104,14 @@ PROTOTYPES = {
     "sg_feco_kmeans": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_float, _vp, _vp]),
     "sg_feco_means_fwd": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
     "sg_feco_means_bwd": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "sg_load_iv": (C.c_int, [_vp, C.POINTER(IvWeights)]),
+    "sg_iv_ws_bytes": (C.c_size_t, [_vp, C.c_int, C.c_int]),
+    "sg_iv_embed_fwd": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "sg_iv_embed_bwd": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp]),
+    "sg_iv_stage_read": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "sg_add_delta_fwd": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
+    "sg_add_delta_bwd": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
+    "sg_cmvn_cols": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     "sg_debug_conv": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.c_int, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     "sg_profile_enable": (C.c_int, [_vp, C.c_int]),

@@ -34,7 +34,7 @@ static const int kCout[5] = {512, 512, 512, 512, 1500};
 static const int kCoutP[5] = {512, 512, 512, 512, SG_C5P};
 
 static const char* kProfNames[SG_PROF_COUNT] = {
-    "mfcc_fwd", "mfcc_bwd", "cmvn", "tdnn_fwd", "tdnn_dgrad", "pool", "head_gemm", "head", "loss", "step", "audionet", "cw2"};
+    "mfcc_fwd", "mfcc_bwd", "cmvn", "tdnn_fwd", "tdnn_dgrad", "pool", "head_gemm", "head", "loss", "step", "audionet", "cw2", "iv_gemm", "iv"};
 
 int sg_dev_upload(sg_handle* h, float** dst, const std::vector<float>& src) {
   SG_CUDA_CHECK(cudaMalloc((void**)dst, src.size() * sizeof(float)));
@@ -84,6 +84,7 @@ extern "C" void sg_destroy(sg_handle* h) {
   cudaSetDevice(h->device);
   for (cudaEvent_t e : h->prof.ev) cudaEventDestroy(e);
   sg_audionet_free(h);
+  sg_iv_free(h);
   for (void* p : h->allocs) cudaFree(p);
   delete h;
 }
@@ -125,9 +126,45 @@ extern "C" void sg_reset_launch_count(sg_handle* h) { if (h) h->launches = 0; }
 // weights: fold eval-mode BatchNorm (affine=False) of layer l into layer l+1 (exact: valid
 // convolutions), pack [taps*cin, cout] for the forward and [taps*cout, cin] for dgrad
 // ---------------------------------------------------------------------------------------------
+// PLDA back-end shared by the x-vector and i-vector systems (plda.py:27-51, :140-190)
+int sg_load_backend(sg_handle* h, const float* plda_mean, const float* plda_transform, const float* plda_psi,
+                    const float* enroll, int L, int S) {
+  const int Lp = (L + 31) / 32 * 32;
+  h->L = L; h->Lp = Lp; h->S = S;
+  std::vector<float> mean(plda_mean, plda_mean + L), T(plda_transform, plda_transform + (size_t)L * L);
+  std::vector<float> Tt((size_t)L * L), ip(L), pr(L), ivg(L);
+  for (int i = 0; i < L; ++i)
+    for (int j = 0; j < L; ++j) Tt[(size_t)j * L + i] = T[(size_t)i * L + j];
+  float ld_given = 0.f, ld_without = 0.f;
+  for (int i = 0; i < L; ++i) {
+    const float psi = plda_psi[i];
+    ip[i] = 1.0f / (psi + 1.0f);
+    pr[i] = psi / (psi + 1.0f);
+    const float vg = 1.0f + psi / (psi + 1.0f);
+    ivg[i] = 1.0f / vg;
+    ld_given += logf(vg);
+    ld_without += logf(psi + 1.0f);
+  }
+  SG_TRY(sg_dev_upload(h, &h->plda_mean, mean));
+  SG_TRY(sg_dev_upload(h, &h->plda_T, T));
+  SG_TRY(sg_dev_upload(h, &h->plda_Tt, Tt));
+  SG_TRY(sg_dev_upload(h, &h->inv_psi1, ip));
+  SG_TRY(sg_dev_upload(h, &h->psi_ratio, pr));
+  SG_TRY(sg_dev_upload(h, &h->inv_var_given, ivg));
+  std::vector<float> en(enroll, enroll + (size_t)S * L);
+  SG_TRY(sg_dev_upload(h, &h->enroll, en));
+  h->H.L = L; h->H.Lp = Lp;
+  h->H.plda_mean = h->plda_mean; h->H.plda_T = h->plda_T; h->H.plda_Tt = h->plda_Tt;
+  h->H.inv_psi1 = h->inv_psi1; h->H.psi_ratio = h->psi_ratio; h->H.inv_var_given = h->inv_var_given;
+  h->H.logdet_given = ld_given; h->H.logdet_without = ld_without;
+  h->H.log2pi_L = logf(2.0f * 3.1415926f) * (float)L;            // plda.py:179
+  h->backend_loaded = true;
+  return SG_OK;
+}
+
 extern "C" int sg_load_xv(sg_handle* h, const sg_xv_weights* w) {
   if (!h || !w) { sg_set_error("sg_load_xv: null argument"); return SG_EINVAL; }
-  if (h->xv_loaded) { sg_set_error("sg_load_xv: weights already loaded for this handle"); return SG_ESTATE; }
+  if (h->xv_loaded || h->backend_loaded) { sg_set_error("sg_load_xv: a model is already loaded on this handle"); return SG_ESTATE; }
   if (w->L < 1 || w->L > 512 || w->S < 1) { sg_set_error("sg_load_xv: need 1 <= L <= 512, S >= 1 (L=%d S=%d)", w->L, w->S); return SG_EINVAL; }
   for (int l = 0; l < 5; ++l)
     if (!w->tdnn_w[l] || !w->tdnn_b[l] || !w->bn_mean[l] || !w->bn_var[l]) { sg_set_error("sg_load_xv: null TDNN pointer (layer %d)", l + 1); return SG_EINVAL; }
@@ -208,35 +245,7 @@ extern "C" int sg_load_xv(sg_handle* h, const sg_xv_weights* w) {
     h->Wlda_bk = h->Wlda;   // [512, Lp]
     SG_TRY(sg_dev_upload(h, &h->blda, b));
   }
-  {  // PLDA (plda.py:27-51, :140-190)
-    std::vector<float> mean(w->plda_mean, w->plda_mean + L), T(w->plda_transform, w->plda_transform + (size_t)L * L);
-    std::vector<float> Tt((size_t)L * L), ip(L), pr(L), ivg(L);
-    for (int i = 0; i < L; ++i)
-      for (int j = 0; j < L; ++j) Tt[(size_t)j * L + i] = T[(size_t)i * L + j];
-    float ld_given = 0.f, ld_without = 0.f;
-    for (int i = 0; i < L; ++i) {
-      const float psi = w->plda_psi[i];
-      ip[i] = 1.0f / (psi + 1.0f);
-      pr[i] = psi / (psi + 1.0f);
-      const float vg = 1.0f + psi / (psi + 1.0f);
-      ivg[i] = 1.0f / vg;
-      ld_given += logf(vg);
-      ld_without += logf(psi + 1.0f);
-    }
-    SG_TRY(sg_dev_upload(h, &h->plda_mean, mean));
-    SG_TRY(sg_dev_upload(h, &h->plda_T, T));
-    SG_TRY(sg_dev_upload(h, &h->plda_Tt, Tt));
-    SG_TRY(sg_dev_upload(h, &h->inv_psi1, ip));
-    SG_TRY(sg_dev_upload(h, &h->psi_ratio, pr));
-    SG_TRY(sg_dev_upload(h, &h->inv_var_given, ivg));
-    std::vector<float> en(w->enroll, w->enroll + (size_t)S * L);
-    SG_TRY(sg_dev_upload(h, &h->enroll, en));
-    h->H.L = L; h->H.Lp = Lp;
-    h->H.plda_mean = h->plda_mean; h->H.plda_T = h->plda_T; h->H.plda_Tt = h->plda_Tt;
-    h->H.inv_psi1 = h->inv_psi1; h->H.psi_ratio = h->psi_ratio; h->H.inv_var_given = h->inv_var_given;
-    h->H.logdet_given = ld_given; h->H.logdet_without = ld_without;
-    h->H.log2pi_L = logf(2.0f * 3.1415926f) * (float)L;            // plda.py:179
-  }
+  SG_TRY(sg_load_backend(h, w->plda_mean, w->plda_transform, w->plda_psi, w->enroll, L, S));
   h->xv_loaded = true;
   return SG_OK;
 }
@@ -484,7 +493,8 @@ extern "C" int sg_debug_conv(sg_handle* h, int precision, const float* A, int ld
 // ---- scoring / loss ----------------------------------------------------------------------------
 extern "C" int sg_plda_score_fwd(sg_handle* h, const float* emb, int B, const float* enroll, int S, float threshold,
                                  float* scores, int64_t* decisions, sg_stream stream) {
-  SG_TRY(sg_check_handle(h, true));
+  SG_TRY(sg_check_handle(h, false));
+  if (!h->backend_loaded) { sg_set_error("sg_plda_score_fwd: no PLDA back-end loaded (sg_load_xv / sg_load_iv)"); return SG_ESTATE; }
   if (!emb || !scores || B < 1) { sg_set_error("sg_plda_score_fwd: bad argument"); return SG_EINVAL; }
   if (!enroll) { enroll = h->enroll; S = h->S; }
   if (S < 1) { sg_set_error("sg_plda_score_fwd: S must be >= 1"); return SG_EINVAL; }
@@ -494,7 +504,8 @@ extern "C" int sg_plda_score_fwd(sg_handle* h, const float* emb, int B, const fl
 }
 extern "C" int sg_plda_score_bwd(sg_handle* h, const float* emb, const float* dscores, int B, const float* enroll, int S,
                                  float* demb, sg_stream stream) {
-  SG_TRY(sg_check_handle(h, true));
+  SG_TRY(sg_check_handle(h, false));
+  if (!h->backend_loaded) { sg_set_error("sg_plda_score_bwd: no PLDA back-end loaded (sg_load_xv / sg_load_iv)"); return SG_ESTATE; }
   if (!emb || !dscores || !demb || B < 1) { sg_set_error("sg_plda_score_bwd: bad argument"); return SG_EINVAL; }
   if (!enroll) { enroll = h->enroll; S = h->S; }
   h->launches += 1;

@@ -1,0 +1,309 @@
+// C-ABI of the i-vector system (reference model/iv_plda.py: add_delta :248-293, extract_emb :380-396,
+// process_emb :411-443; model/_iv_plda/gmm.py:120-171; model/_iv_plda/ivector_extract.py:94-114).
+//
+// Per pass (B utterances, T frames, padded to Tp = 16-multiple rows each, R = B*Tp):
+//   Xa  [R, Fa]      features + a ones column (the zeroth-order statistic rides along with the first-order ones)
+//   Q   [R, Kq]      packed quadratic expansion  -> post = softmax(Q Wq + gconst)           [R, C]
+//   FsT [B, Fa, C]   = Xa_b^T post_b   (rows 0..F-1: F_c^T, row F: N_c)                      batched GEMM
+//   Lpk [B, Pp]      = N U             (packed upper triangle of sum_c N_c T_c' S_c^-1 T_c)
+//   lin [B, Dp]      = vec(F) Wlin     (sum_c T_c' S_c^-1 F_c)
+//   iv  = (I + L)^-1 (lin + offset e0) - offset e0 - emb_mean ; e2 = LDA iv ; emb = PLDA transform (shared head)
+// The backward pass replays the chain with the transposed operands; the SPD solve keeps its fp64 factor.
+#include <math.h>
+#include <string.h>
+
+#include <thread>
+#include <vector>
+
+#include "sg_handle.cuh"
+#include "sg_head.cuh"
+#include "sg_iv.cuh"
+
+struct SgIv {
+  int C, F, D, L, Lp, Fa, Dp, P, Pp, Kq;
+  float offset;
+  float *Wq, *WqT, *gconst;        // [Kq, C], [C, Kq], [C]
+  float *U, *UT;                   // [C, Pp], [Pp, C]
+  float *Wlin, *WlinT;             // [F*C, Dp], [Dp, F*C]
+  float *Wlda, *Wlda_b, *blda;     // [Dp, Lp], [Lp, Dp], [Lp]
+  float* emb_mean;                 // [Dp]
+};
+
+void sg_iv_free(sg_handle* h) {
+  delete h->iv;                    // device buffers are owned by h->allocs
+  h->iv = nullptr;
+}
+
+static inline int up16(int v) { return (v + 15) / 16 * 16; }
+
+template <typename Fn>
+static void parallel_for(int n, Fn fn) {
+  int nt = (int)std::thread::hardware_concurrency();
+  nt = nt < 1 ? 1 : (nt > 32 ? 32 : nt);
+  if (nt > n) nt = n;
+  std::vector<std::thread> th;
+  for (int t = 0; t < nt; ++t)
+    th.emplace_back([=]() { for (int i = t; i < n; i += nt) fn(i); });
+  for (auto& x : th) x.join();
+}
+
+extern "C" int sg_load_iv(sg_handle* h, const sg_iv_weights* w) {
+  if (!h || !w) { sg_set_error("sg_load_iv: null argument"); return SG_EINVAL; }
+  if (h->iv || h->backend_loaded) { sg_set_error("sg_load_iv: a model is already loaded on this handle"); return SG_ESTATE; }
+  if (w->C < 16 || w->C % 16 != 0 || w->F < 1 || w->F > 128 || w->D < 1 || w->D > 1024 || w->L < 1 || w->L > 512 || w->S < 1) {
+    sg_set_error("sg_load_iv: need C %% 16 == 0, 1 <= F <= 128, 1 <= D <= 1024, 1 <= L <= 512, S >= 1 (C=%d F=%d D=%d L=%d S=%d)",
+                 w->C, w->F, w->D, w->L, w->S);
+    return SG_EINVAL;
+  }
+  if (!w->gmm_gconsts || !w->gmm_means_invcovars || !w->gmm_invcovars || !w->ive_T || !w->ive_sigma_inv || !w->emb_mean ||
+      !w->lda || !w->plda_mean || !w->plda_transform || !w->plda_psi || !w->enroll) {
+    sg_set_error("sg_load_iv: null weight pointer"); return SG_EINVAL;
+  }
+  SG_CUDA_CHECK(cudaSetDevice(h->device));
+  SgIv* m = new SgIv();
+  memset(m, 0, sizeof(*m));
+  h->iv = m;
+  const int C = w->C, F = w->F, D = w->D, L = w->L;
+  m->C = C; m->F = F; m->D = D; m->L = L; m->Lp = (L + 31) / 32 * 32;
+  m->Fa = up16(F + 1); m->Dp = up16(D); m->P = D * (D + 1) / 2; m->Pp = up16(m->P);
+  m->Kq = up16(F + F * (F + 1) / 2);
+  m->offset = w->ive_offset;
+  const int Kq = m->Kq, Pp = m->Pp, Dp = m->Dp, Lp = m->Lp;
+
+  {  // UBM: ll = gconst + (S^-1 mu).x - 1/2 x' S^-1 x on the packed expansion (gmm.py:120-131)
+    std::vector<float> Wq((size_t)Kq * C, 0.f), WqT((size_t)C * Kq, 0.f);
+    for (int c = 0; c < C; ++c) {
+      const float* P = w->gmm_invcovars + (size_t)c * F * F;
+      for (int f = 0; f < F; ++f) Wq[(size_t)f * C + c] = w->gmm_means_invcovars[(size_t)c * F + f];
+      int p = F;
+      for (int i = 0; i < F; ++i)
+        for (int j = i; j < F; ++j, ++p)
+          Wq[(size_t)p * C + c] = (i == j) ? -0.5f * P[i * F + i] : -0.5f * (P[i * F + j] + P[j * F + i]);
+      for (int k = 0; k < Kq; ++k) WqT[(size_t)c * Kq + k] = Wq[(size_t)k * C + c];
+    }
+    SG_TRY(sg_dev_upload(h, &m->Wq, Wq));
+    SG_TRY(sg_dev_upload(h, &m->WqT, WqT));
+    SG_TRY(sg_dev_upload(h, &m->gconst, std::vector<float>(w->gmm_gconsts, w->gmm_gconsts + C)));
+  }
+  {  // extractor (ivector_extract.py:94-107): G_c = T_c' S_c^-1 [D,F], U_c = G_c T_c [D,D]
+    std::vector<float> U((size_t)C * Pp, 0.f), Wlin((size_t)F * C * Dp, 0.f);
+    parallel_for(C, [&](int c) {
+      const float* T = w->ive_T + (size_t)c * F * D;          // [F, D]
+      const float* S = w->ive_sigma_inv + (size_t)c * F * F;  // [F, F]
+      std::vector<float> G((size_t)D * F, 0.f);
+      for (int g = 0; g < F; ++g)
+        for (int d = 0; d < D; ++d) {
+          const float t = T[(size_t)g * D + d];
+          float* gr = &G[(size_t)d * F];
+          const float* sr = S + (size_t)g * F;
+          for (int f = 0; f < F; ++f) gr[f] += t * sr[f];
+        }
+      for (int f = 0; f < F; ++f)
+        for (int d = 0; d < D; ++d) Wlin[((size_t)f * C + c) * Dp + d] = G[(size_t)d * F + f];
+      float* u = &U[(size_t)c * Pp];
+      for (int i = 0; i < D; ++i) {
+        float* ur = u + ((size_t)i * D - (size_t)i * (i - 1) / 2) - i;   // ur[j] = packed (i, j)
+        for (int f = 0; f < F; ++f) {
+          const float g = G[(size_t)i * F + f];
+          const float* tr = T + (size_t)f * D;
+          for (int j = i; j < D; ++j) ur[j] += g * tr[j];
+        }
+      }
+    });
+    SG_TRY(sg_dev_upload(h, &m->U, U));
+    SG_TRY(sg_dev_upload(h, &m->Wlin, Wlin));
+    {
+      std::vector<float> UT((size_t)Pp * C, 0.f);
+      parallel_for(C, [&](int c) { for (int p = 0; p < Pp; ++p) UT[(size_t)p * C + c] = U[(size_t)c * Pp + p]; });
+      SG_TRY(sg_dev_upload(h, &m->UT, UT));
+    }
+    {
+      std::vector<float> WlinT((size_t)Dp * F * C, 0.f);
+      const size_t K = (size_t)F * C;
+      parallel_for(Dp, [&](int d) { for (size_t k = 0; k < K; ++k) WlinT[(size_t)d * K + k] = Wlin[k * Dp + d]; });
+      SG_TRY(sg_dev_upload(h, &m->WlinT, WlinT));
+    }
+  }
+  {  // LDA [L, D+1], offset in the last column (model/iv_plda.py:423-435)
+    std::vector<float> Wl((size_t)Dp * Lp, 0.f), Wlb((size_t)Lp * Dp, 0.f), b(Lp, 0.f), mean(Dp, 0.f);
+    for (int i = 0; i < L; ++i) {
+      for (int d = 0; d < D; ++d) {
+        const float v = w->lda[(size_t)i * (D + 1) + d];
+        Wl[(size_t)d * Lp + i] = v;
+        Wlb[(size_t)i * Dp + d] = v;
+      }
+      b[i] = w->lda[(size_t)i * (D + 1) + D];
+    }
+    for (int d = 0; d < D; ++d) mean[d] = w->emb_mean[d];
+    SG_TRY(sg_dev_upload(h, &m->Wlda, Wl));
+    SG_TRY(sg_dev_upload(h, &m->Wlda_b, Wlb));
+    SG_TRY(sg_dev_upload(h, &m->blda, b));
+    SG_TRY(sg_dev_upload(h, &m->emb_mean, mean));
+  }
+  SG_TRY(sg_load_backend(h, w->plda_mean, w->plda_transform, w->plda_psi, w->enroll, L, w->S));
+  return SG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+struct IvWs {
+  float *Xa, *XaT, *Q, *post, *dpost, *FsT, *dFsT, *dFs, *Lpk, *dLpk, *lin, *dlin, *wfull, *iv, *div, *e2, *de2, *tsave, *scal, *dXa;
+  double* fac;
+  size_t bytes;
+};
+static IvWs iv_ws_layout(void* base, const SgIv* m, int B, int T) {
+  IvWs w;
+  char* p = (char*)base;
+  size_t off = 0;
+  auto take = [&](size_t nfloat) { float* q = (float*)(p + off); off += (nfloat * sizeof(float) + 255) / 256 * 256; return q; };
+  const size_t Tp = up16(T), R = (size_t)B * Tp;
+  w.Xa = take(R * m->Fa); w.XaT = take(R * m->Fa); w.dXa = take(R * m->Fa);
+  w.Q = take(R * m->Kq);
+  w.post = take(R * m->C); w.dpost = take(R * m->C);
+  w.FsT = take((size_t)B * m->Fa * m->C); w.dFsT = take((size_t)B * m->Fa * m->C); w.dFs = take((size_t)B * m->Fa * m->C);
+  w.Lpk = take((size_t)B * m->Pp); w.dLpk = take((size_t)B * m->Pp);
+  w.lin = take((size_t)B * m->Dp); w.dlin = take((size_t)B * m->Dp);
+  w.wfull = take((size_t)B * m->Dp); w.iv = take((size_t)B * m->Dp); w.div = take((size_t)B * m->Dp);
+  w.e2 = take((size_t)B * m->Lp); w.de2 = take((size_t)B * m->Lp); w.tsave = take((size_t)B * m->Lp);
+  w.scal = take((size_t)B * 4);
+  w.fac = (double*)take((size_t)B * m->D * m->D * 2);
+  w.bytes = off;
+  return w;
+}
+
+static int check_iv(sg_handle* h) {
+  SG_TRY(sg_check_handle(h, false));
+  if (!h->iv) { sg_set_error("i-vector weights not loaded (call sg_load_iv first)"); return SG_ESTATE; }
+  return SG_OK;
+}
+
+extern "C" size_t sg_iv_ws_bytes(const sg_handle* h, int B, int T) {
+  if (!h || !h->iv || B < 1 || T < 1) return 0;
+  return iv_ws_layout(nullptr, h->iv, B, T).bytes;
+}
+
+static SgConvArgs gemm_args(const float* A, int lda, const float* W, const float* Wk, const float* bias, float* out, int ldo,
+                            int rows, int N, int K) {
+  SgConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.A = A; a.lda = lda; a.W = W; a.Wk = Wk; a.bias = bias; a.out = out; a.ldo = ldo; a.rows = rows; a.N = N; a.cin = K;
+  a.taps = 1; a.T = 1; a.epilogue = bias ? SG_EPI_BIAS : SG_EPI_NONE;
+  return a;
+}
+// fp32 FFMA for every contraction of this path: the UBM log-likelihoods cancel O(100) terms against each other, so the
+// reduced-precision tensor-core modes of the TDNN path are not offered here
+static int iv_gemm(sg_handle* h, const SgConvArgs& a, cudaStream_t st) {
+  h->launches += 1;
+  PROF(h, SG_PROF_IV_GEMM, st, sg_conv_simt(a, st));
+  return SG_OK;
+}
+#define IV_K(call) do { h->launches += 1; PROF(h, SG_PROF_IV, st, (call)); } while (0)
+
+static int iv_embed_fwd(sg_handle* h, const float* feat, int ld, int B, int T, const IvWs& w, float* emb, cudaStream_t st) {
+  const SgIv* m = h->iv;
+  const int Tp = up16(T), R = B * Tp, C = m->C, F = m->F, Fa = m->Fa;
+  IV_K(sg_pad_aug_launch(feat, ld, w.Xa, Fa, B, T, Tp, F, st));
+  IV_K(sg_transpose_batched_launch(w.Xa, w.XaT, Tp, Fa, Fa, Tp, (size_t)Tp * Fa, (size_t)Tp * Fa, B, st));
+  IV_K(sg_quad_expand_launch(w.Xa, Fa, w.Q, m->Kq, R, F, st));
+  SG_TRY(iv_gemm(h, gemm_args(w.Q, m->Kq, m->Wq, m->WqT, m->gconst, w.post, C, R, C, m->Kq), st));
+  IV_K(sg_softmax_rows_launch(w.post, nullptr, w.post, R, C, T, Tp, 0, st));
+  {  // Baum-Welch statistics (gmm.py:166-171), one GEMM per utterance: [Fa, Tp] x [Tp, C]
+    SgConvArgs a = gemm_args(w.XaT, Tp, w.post, nullptr, nullptr, w.FsT, C, Fa, C, Tp);
+    a.nbatch = B; a.strideA = (long long)Fa * Tp; a.strideW = (long long)Tp * C; a.strideO = (long long)Fa * C;
+    SG_TRY(iv_gemm(h, a, st));
+  }
+  SG_TRY(iv_gemm(h, gemm_args(w.FsT + (size_t)F * C, Fa * C, m->U, m->UT, nullptr, w.Lpk, m->Pp, B, m->Pp, C), st));
+  SG_TRY(iv_gemm(h, gemm_args(w.FsT, Fa * C, m->Wlin, m->WlinT, nullptr, w.lin, m->Dp, B, m->Dp, F * C), st));
+  IV_K(sg_chol_solve_launch(w.Lpk, m->Pp, w.lin, m->Dp, m->offset, m->emb_mean, w.fac, w.wfull, w.iv, B, m->D, st));
+  SG_TRY(iv_gemm(h, gemm_args(w.iv, m->Dp, m->Wlda, m->Wlda_b, m->blda, w.e2, m->Lp, B, m->Lp, m->Dp), st));
+  h->launches += 1;
+  PROF(h, SG_PROF_HEAD, st, sg_head_fwd_launch(h->H, w.e2, B, w.tsave, w.scal, emb, st));
+  return SG_OK;
+}
+
+static int iv_embed_bwd(sg_handle* h, const float* demb, int B, int T, const IvWs& w, float* dfeat, int ld, cudaStream_t st) {
+  const SgIv* m = h->iv;
+  const int Tp = up16(T), R = B * Tp, C = m->C, F = m->F, Fa = m->Fa;
+  h->launches += 1;
+  PROF(h, SG_PROF_HEAD, st, sg_head_bwd_launch(h->H, demb, B, w.tsave, w.scal, w.de2, st));
+  SG_TRY(iv_gemm(h, gemm_args(w.de2, m->Lp, m->Wlda_b, m->Wlda, nullptr, w.div, m->Dp, B, m->Dp, m->Lp), st));
+  IV_K(sg_chol_solve_bwd_launch(w.fac, w.wfull, w.div, m->Dp, w.dlin, w.dLpk, m->Pp, B, m->D, st));
+  SG_CUDA_CHECK(cudaMemsetAsync(w.dFsT, 0, (size_t)B * Fa * C * sizeof(float), st));
+  SG_TRY(iv_gemm(h, gemm_args(w.dLpk, m->Pp, m->UT, m->U, nullptr, w.dFsT + (size_t)F * C, Fa * C, B, C, m->Pp), st));
+  SG_TRY(iv_gemm(h, gemm_args(w.dlin, m->Dp, m->WlinT, m->Wlin, nullptr, w.dFsT, Fa * C, B, F * C, m->Dp), st));
+  {  // d post_b = Xa_b dFsT_b : [Tp, Fa] x [Fa, C]
+    SgConvArgs a = gemm_args(w.Xa, Fa, w.dFsT, nullptr, nullptr, w.dpost, C, Tp, C, Fa);
+    a.nbatch = B; a.strideA = (long long)Tp * Fa; a.strideW = (long long)Fa * C; a.strideO = (long long)Tp * C;
+    SG_TRY(iv_gemm(h, a, st));
+  }
+  IV_K(sg_softmax_rows_launch(w.post, w.dpost, w.dpost, R, C, T, Tp, 1, st));
+  SG_TRY(iv_gemm(h, gemm_args(w.dpost, C, m->WqT, m->Wq, nullptr, w.Q, m->Kq, R, m->Kq, C), st));
+  // the first-order statistics also depend on x directly: dXa_b = post_b dFs_b, dFs_b = dFsT_b^T  [C, Fa]
+  IV_K(sg_transpose_batched_launch(w.dFsT, w.dFs, Fa, C, C, Fa, (size_t)Fa * C, (size_t)Fa * C, B, st));
+  {
+    SgConvArgs a = gemm_args(w.post, C, w.dFs, nullptr, nullptr, w.dXa, Fa, Tp, Fa, C);
+    a.nbatch = B; a.strideA = (long long)Tp * C; a.strideW = (long long)C * Fa; a.strideO = (long long)Tp * Fa;
+    SG_TRY(iv_gemm(h, a, st));
+  }
+  IV_K(sg_quad_expand_bwd_launch(w.Q, m->Kq, w.Xa, Fa, w.dXa, dfeat, ld, B, T, Tp, F, st));
+  return SG_OK;
+}
+
+extern "C" int sg_iv_embed_fwd(sg_handle* h, const float* feat, int ld, int B, int T, void* ws, float* emb, sg_stream stream) {
+  SG_TRY(check_iv(h));
+  if (!feat || !ws || !emb || B < 1 || T < 1 || ld < h->iv->F) { sg_set_error("sg_iv_embed_fwd: bad argument"); return SG_EINVAL; }
+  return iv_embed_fwd(h, feat, ld, B, T, iv_ws_layout(ws, h->iv, B, T), emb, (cudaStream_t)stream);
+}
+extern "C" int sg_iv_embed_bwd(sg_handle* h, const float* demb, int B, int T, void* ws, float* dfeat, int ld, sg_stream stream) {
+  SG_TRY(check_iv(h));
+  if (!demb || !ws || !dfeat || B < 1 || T < 1 || ld < h->iv->F) { sg_set_error("sg_iv_embed_bwd: bad argument"); return SG_EINVAL; }
+  return iv_embed_bwd(h, demb, B, T, iv_ws_layout(ws, h->iv, B, T), dfeat, ld, (cudaStream_t)stream);
+}
+
+// intermediate results of the last sg_iv_embed_fwd on this workspace (tests / diagnostics)
+extern "C" int sg_iv_stage_read(sg_handle* h, const void* ws, int B, int T, int stage, float* out, sg_stream stream) {
+  SG_TRY(check_iv(h));
+  if (!ws || !out || B < 1 || T < 1) { sg_set_error("sg_iv_stage_read: bad argument"); return SG_EINVAL; }
+  const SgIv* m = h->iv;
+  const IvWs w = iv_ws_layout((void*)ws, m, B, T);
+  const int Tp = up16(T);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (stage) {
+    case SG_IV_STAGE_POST:     // [B, T, C]
+      SG_CUDA_CHECK(cudaMemcpy2DAsync(out, (size_t)T * m->C * 4, w.post, (size_t)Tp * m->C * 4, (size_t)T * m->C * 4, B, cudaMemcpyDeviceToDevice, st));
+      break;
+    case SG_IV_STAGE_STATS:    // [B, F+1, C]: first-order statistics transposed, zeroth-order in the last row
+      SG_CUDA_CHECK(cudaMemcpy2DAsync(out, (size_t)(m->F + 1) * m->C * 4, w.FsT, (size_t)m->Fa * m->C * 4, (size_t)(m->F + 1) * m->C * 4, B, cudaMemcpyDeviceToDevice, st));
+      break;
+    case SG_IV_STAGE_IVECTOR:  // [B, D]: i-vector with the prior offset removed, before mean subtraction
+      SG_CUDA_CHECK(cudaMemcpy2DAsync(out, (size_t)m->D * 4, w.wfull, (size_t)m->Dp * 4, (size_t)m->D * 4, B, cudaMemcpyDeviceToDevice, st));
+      break;
+    default:
+      sg_set_error("sg_iv_stage_read: unknown stage %d", stage);
+      return SG_EINVAL;
+  }
+  return SG_OK;
+}
+
+// ---- feature-level pieces ----------------------------------------------------------------------
+extern "C" int sg_add_delta_fwd(sg_handle* h, const float* in, int ld_in, float* out, int ld_out, int B, int T, int F, sg_stream stream) {
+  SG_TRY(sg_check_handle(h, false));
+  if (!in || !out || B < 1 || T < 1 || F < 1 || ld_in < F || ld_out < 3 * F) { sg_set_error("sg_add_delta_fwd: bad argument"); return SG_EINVAL; }
+  cudaStream_t st = (cudaStream_t)stream;
+  IV_K(sg_delta_launch(in, ld_in, out, ld_out, B, T, F, 0, st));
+  return SG_OK;
+}
+extern "C" int sg_add_delta_bwd(sg_handle* h, const float* dout, int ld_in, float* din, int ld_out, int B, int T, int F, sg_stream stream) {
+  SG_TRY(sg_check_handle(h, false));
+  if (!dout || !din || B < 1 || T < 1 || F < 1 || ld_in < 3 * F || ld_out < F) { sg_set_error("sg_add_delta_bwd: bad argument"); return SG_EINVAL; }
+  cudaStream_t st = (cudaStream_t)stream;
+  IV_K(sg_delta_launch(dout, ld_in, din, ld_out, B, T, F, 1, st));
+  return SG_OK;
+}
+extern "C" int sg_cmvn_cols(sg_handle* h, const float* in, int ld_in, float* out, int ld_out, int ncol, int B, int T, int backward,
+                            sg_stream stream) {
+  SG_TRY(sg_check_handle(h, false));
+  if (!in || !out || B < 1 || T < 1 || ncol < 1 || ld_in < ncol || ld_out < ncol) { sg_set_error("sg_cmvn_cols: bad argument"); return SG_EINVAL; }
+  h->launches += 1;
+  PROF(h, SG_PROF_CMVN, (cudaStream_t)stream, sg_cmvn_cols_launch(in, ld_in, out, ld_out, B, T, ncol, backward ? 1 : 0, (cudaStream_t)stream));
+  return SG_OK;
+}

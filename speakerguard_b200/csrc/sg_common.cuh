@@ -89,6 +89,8 @@ struct SgConvArgs {
   int ldbits;                       // words per row
   // bf16 mode (tensor-core path): A / Wk hold __nv_bfloat16 when op_bf16, out is __nv_bfloat16 when out_bf16
   int op_bf16; int out_bf16;
+  // batched GEMM (SIMT path only): blockIdx.z selects an item; element strides, 0 = shared operand
+  int nbatch; long long strideA, strideW, strideO;
 };
 
 int sg_conv_simt(const SgConvArgs& a, cudaStream_t st);

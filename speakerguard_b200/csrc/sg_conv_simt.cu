@@ -18,6 +18,9 @@ conv_simt_kernel(SgConvArgs a) {
   __shared__ __align__(16) float As[2][BK][BM];
   __shared__ __align__(16) float Bs[2][BK][BN];
   const int tid = threadIdx.x;
+  a.A += (long long)blockIdx.z * a.strideA;
+  a.W += (long long)blockIdx.z * a.strideW;
+  a.out += (long long)blockIdx.z * a.strideO;
   const int n0 = blockIdx.x * BN;
   const int p0 = blockIdx.y * BM;
   const int ty = tid >> 4, tx = tid & 15;
@@ -130,7 +133,11 @@ int sg_conv_simt(const SgConvArgs& a, cudaStream_t st) {
                  a.cin, a.N, a.lda, a.ldo);
     return SG_EINVAL;
   }
-  dim3 grid((a.N + BN - 1) / BN, (a.rows + BM - 1) / BM);
+  if (a.nbatch > 1 && (a.strideA % 4 != 0 || a.strideW % 4 != 0 || a.strideO % 4 != 0 || a.nbatch > 65535)) {
+    sg_set_error("sg_conv_simt: batch strides must be multiples of 4 floats and nbatch <= 65535");
+    return SG_EINVAL;
+  }
+  dim3 grid((a.N + BN - 1) / BN, (a.rows + BM - 1) / BM, a.nbatch > 1 ? a.nbatch : 1);
   conv_simt_kernel<<<grid, 256, 0, st>>>(a);
   SG_LAUNCH_CHECK();
   return SG_OK;

@@ -635,7 +635,7 @@ __global__ void cmvn_kernel(const float* __restrict__ in, int ld_in, float* __re
                             int T, int ncol, int backward) {
   __shared__ float part[8][33];
   __shared__ float tot[32];
-  const int c = threadIdx.x, r = threadIdx.y, b = blockIdx.x;
+  const int lc = threadIdx.x, c = blockIdx.y * 32 + lc, r = threadIdx.y, b = blockIdx.x;
   const float* ib = in + (size_t)b * T * ld_in;
   float* ob = out + (size_t)b * T * ld_out;
   const bool cin = c < ncol && c < ld_in;
@@ -643,16 +643,16 @@ __global__ void cmvn_kernel(const float* __restrict__ in, int ld_in, float* __re
     // every window is [0,T): global mean.  Self-adjoint: dx = dy - mean(dy).
     float s = 0.f;
     for (int t = r; t < T; t += 8) s += cin ? ib[(size_t)t * ld_in + c] : 0.f;
-    part[r][c] = s;
+    part[r][lc] = s;
     __syncthreads();
     if (r == 0) {
       float a = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) a += part[i][c];
-      tot[c] = a / (float)T;
+      for (int i = 0; i < 8; ++i) a += part[i][lc];
+      tot[lc] = a / (float)T;
     }
     __syncthreads();
-    const float mu = tot[c];
+    const float mu = tot[lc];
     for (int t = r; t < T; t += 8)
       if (c < ld_out) ob[(size_t)t * ld_out + c] = cin ? ib[(size_t)t * ld_in + c] - mu : 0.f;
     return;
@@ -779,6 +779,12 @@ int sg_step_linf_launch(float* x, const float* x0, const float* grad, size_t n, 
 
 int sg_cmvn_launch(const float* in, int ld_in, float* out, int ld_out, int B, int T, int backward, cudaStream_t st) {
   cmvn_kernel<<<B, dim3(32, 8), 0, st>>>(in, ld_in, out, ld_out, T, SG_NCEP, backward);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+// any number of columns (the 72-dim MFCC+delta features of the i-vector system)
+int sg_cmvn_cols_launch(const float* in, int ld_in, float* out, int ld_out, int B, int T, int ncol, int backward, cudaStream_t st) {
+  cmvn_kernel<<<dim3(B, (max(ncol, ld_out) + 31) / 32), dim3(32, 8), 0, st>>>(in, ld_in, out, ld_out, T, ncol, backward);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }

@@ -37,6 +37,7 @@ struct sg_handle {
   long long launches = 0;
   SgFeatTables* d_tables = nullptr;
   bool xv_loaded = false;
+  bool backend_loaded = false;      // PLDA back-end + enrolled speakers (set by sg_load_xv / sg_load_iv)
   int L = 0, Lp = 0, S = 0;
   // packed TDNN weights
   float* Wf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // [taps*cinP, coutP]
@@ -57,6 +58,7 @@ struct sg_handle {
   SgHeadConst H;
   std::vector<void*> allocs;
   struct SgAudioNet* an = nullptr;   // AudioNet state (sg_api_audionet.cu)
+  struct SgIv* iv = nullptr;         // i-vector system state (sg_api_iv.cu)
 };
 
 
@@ -67,3 +69,6 @@ int sg_dev_upload(sg_handle* h, float** dst, const std::vector<float>& src);
 int sg_check_handle(sg_handle* h, bool need_xv);
 int sg_run_conv(sg_handle* h, const SgConvArgs& a, bool tensor_ok, int cat, cudaStream_t st);
 void sg_audionet_free(sg_handle* h);
+void sg_iv_free(sg_handle* h);
+int sg_load_backend(sg_handle* h, const float* plda_mean, const float* plda_transform, const float* plda_psi,
+                    const float* enroll, int L, int S);

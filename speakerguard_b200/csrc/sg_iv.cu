@@ -1,0 +1,353 @@
+// i-vector front half of iv_plda (reference model/iv_plda.py:248-293 add_delta, :380-396
+// extract_emb; model/_iv_plda/gmm.py:120-171 UBM posteriors and Baum-Welch statistics;
+// model/_iv_plda/ivector_extract.py:94-114 i-vector = (I + sum_c N_c T_c' S_c^-1 T_c)^-1 (sum_c T_c' S_c^-1 F_c)).
+//
+// Building blocks, each with its adjoint, composed by the host class (speakerguard_b200/model/iv_plda.py);
+// the dense contractions (UBM log-likelihoods on packed quadratic features, statistics, the L / linear
+// assembly) go through the conv-as-GEMM kernel (sg_gemm), so this file only holds the element-wise
+// and per-utterance pieces:
+//   delta filters, quadratic feature expansion, row softmax, and a batched SPD solve (fp64 Cholesky).
+#include <math.h>
+
+#include "sg_common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// add_delta: out[b,t,i*F+f] = sum_j s_i[j] x[b, clamp(t+j), f], i = 0..2 (window 3, order 2)
+// ---------------------------------------------------------------------------------------------
+__constant__ float c_delta1[7];    // first-order filter, offsets -3..3
+__constant__ float c_delta2[13];   // second-order filter, offsets -6..6
+
+__global__ void delta_fwd_kernel(const float* __restrict__ x, int ldx, float* __restrict__ out, int ldo, int B, int T, int F) {
+  const size_t n = (size_t)B * T * F;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int f = (int)(i % F);
+    const size_t bt = i / F;
+    const int t = (int)(bt % T), b = (int)(bt / T);
+    const float* xb = x + (size_t)b * T * ldx + f;
+    float d1 = 0.f, d2 = 0.f;
+#pragma unroll
+    for (int j = -3; j <= 3; ++j) d1 = fmaf(c_delta1[j + 3], xb[(size_t)min(max(t + j, 0), T - 1) * ldx], d1);
+#pragma unroll
+    for (int j = -6; j <= 6; ++j) d2 = fmaf(c_delta2[j + 6], xb[(size_t)min(max(t + j, 0), T - 1) * ldx], d2);
+    float* o = out + ((size_t)b * T + t) * ldo;
+    o[f] = xb[(size_t)t * ldx];
+    o[F + f] = d1;
+    o[2 * F + f] = d2;
+  }
+}
+// adjoint: dx[b,u,f] = sum_i sum_{t,j : clamp(t+j) == u} s_i[j] dout[b,t,i*F+f]
+__global__ void delta_bwd_kernel(const float* __restrict__ dout, int ldo, float* __restrict__ dx, int ldx, int B, int T, int F) {
+  const size_t n = (size_t)B * T * F;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int f = (int)(i % F);
+    const size_t bt = i / F;
+    const int u = (int)(bt % T), b = (int)(bt / T);
+    const float* db = dout + (size_t)b * T * ldo;
+    float g = db[(size_t)u * ldo + f];
+    // a frame t reaches u through offset j = u - t, or through the clamp when u is an edge frame
+    for (int t = max(0, u - 6); t <= min(T - 1, u + 6); ++t) {
+      const int j = u - t;
+      if (j >= -3 && j <= 3) g = fmaf(c_delta1[j + 3], db[(size_t)t * ldo + F + f], g);
+      g = fmaf(c_delta2[j + 6], db[(size_t)t * ldo + 2 * F + f], g);
+    }
+    if (u == 0) {
+      for (int t = 0; t < min(T, 6); ++t)
+        for (int j = -6; j < -t; ++j) {                            // t + j < 0 clamps to frame 0
+          if (j >= -3) g = fmaf(c_delta1[j + 3], db[(size_t)t * ldo + F + f], g);
+          g = fmaf(c_delta2[j + 6], db[(size_t)t * ldo + 2 * F + f], g);
+        }
+    }
+    if (u == T - 1) {
+      for (int t = max(0, T - 6); t < T; ++t)
+        for (int j = T - t; j <= 6; ++j) {                         // t + j > T-1 clamps to frame T-1
+          if (j <= 3) g = fmaf(c_delta1[j + 3], db[(size_t)t * ldo + F + f], g);
+          g = fmaf(c_delta2[j + 6], db[(size_t)t * ldo + 2 * F + f], g);
+        }
+    }
+    dx[((size_t)b * T + u) * ldx + f] = g;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// quadratic feature expansion for the full-covariance UBM (gmm.py:120-131):
+//   ll[t,c] = gconst_c + (S_c^-1 mu_c) . x_t - 1/2 x_t' S_c^-1 x_t  =  q_t . w_c + gconst_c
+//   q_t = [x (F), x_i x_j for i <= j (F(F+1)/2), 0-pad];  rows are stacked per utterance with stride Tp,
+//   rows t >= T are zero.
+// ---------------------------------------------------------------------------------------------
+__global__ void quad_expand_fwd_kernel(const float* __restrict__ xa, int ldx, float* __restrict__ q, int ldq, int F) {
+  extern __shared__ float xs[];                                   // [F]
+  const int row = blockIdx.x;
+  float* qr = q + (size_t)row * ldq;
+  for (int i = threadIdx.x; i < F; i += blockDim.x) xs[i] = xa[(size_t)row * ldx + i];
+  __syncthreads();
+  const int P = F * (F + 1) / 2;
+  for (int i = threadIdx.x; i < F; i += blockDim.x) qr[i] = xs[i];
+  for (int p = threadIdx.x; p < P; p += blockDim.x) {
+    // p -> (i, j), i <= j, row-major upper triangle: p = i*F - i(i-1)/2 + (j - i)
+    int i = (int)((2.f * F + 1.f - sqrtf((2.f * F + 1.f) * (2.f * F + 1.f) - 8.f * p)) * 0.5f);
+    i = min(max(i, 0), F - 1);
+    while (i > 0 && i * F - i * (i - 1) / 2 > p) --i;
+    while (i + 1 < F && (i + 1) * F - (i + 1) * i / 2 <= p) ++i;
+    const int j = i + (p - (i * F - i * (i - 1) / 2));
+    qr[F + p] = xs[i] * xs[j];
+  }
+  for (int i = F + P + threadIdx.x; i < ldq; i += blockDim.x) qr[i] = 0.f;
+}
+// dx_i = dq_lin[i] + sum_j dq_sym(i,j) x_j (1 + [i == j]) + add_i   (add: the path through the first-order statistics)
+__global__ void quad_expand_bwd_kernel(const float* __restrict__ dq, int ldq, const float* __restrict__ xa, int ldx,
+                                       const float* __restrict__ add, float* __restrict__ dx, int lddx, int T, int Tp, int F) {
+  extern __shared__ float xs[];
+  const int row = blockIdx.x, b = row / Tp, t = row - b * Tp;
+  if (t >= T) return;
+  const float* dr = dq + (size_t)row * ldq;
+  for (int i = threadIdx.x; i < F; i += blockDim.x) xs[i] = xa[(size_t)row * ldx + i];
+  __syncthreads();
+  float* o = dx + ((size_t)b * T + t) * lddx;
+  for (int i = threadIdx.x; i < lddx; i += blockDim.x) {
+    if (i >= F) { o[i] = 0.f; continue; }
+    float g = dr[i] + add[(size_t)row * ldx + i];
+    for (int j = 0; j < F; ++j) {
+      const int a = min(i, j), c = max(i, j);
+      const float d = dr[F + a * F - a * (a - 1) / 2 + (c - a)];
+      g = fmaf(d * (i == j ? 2.f : 1.f), xs[j], g);
+    }
+    o[i] = g;
+  }
+}
+// feat [B,T,ld] -> Xa [B*Tp, Fa] = [x, 1, 0...]; rows t >= T are zero
+__global__ void pad_aug_kernel(const float* __restrict__ feat, int ld, float* __restrict__ xa, int Fa, int B, int T, int Tp, int F) {
+  const size_t n = (size_t)B * Tp * Fa;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int f = (int)(i % Fa);
+    const size_t row = i / Fa;
+    const int t = (int)(row % Tp), b = (int)(row / Tp);
+    float v = 0.f;
+    if (t < T) v = f < F ? feat[((size_t)b * T + t) * ld + f] : (f == F ? 1.f : 0.f);
+    xa[i] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// row softmax over C components (gmm.py:133-136); rows with t >= T (padding) are written as zero
+// one CTA (256 threads) per row
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float iv_block_reduce(float v, float* red, bool is_max) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { float w = __shfl_xor_sync(0xffffffffu, v, o); v = is_max ? fmaxf(v, w) : v + w; }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float a = red[0];
+  for (int i = 1; i < (int)(blockDim.x >> 5); ++i) a = is_max ? fmaxf(a, red[i]) : a + red[i];
+  return a;
+}
+// (ll and post may alias: each thread rewrites only the elements it read)
+__global__ void softmax_rows_fwd_kernel(const float* ll, float* post, int C, int T, int Tp) {
+  __shared__ float red[8];
+  const int row = blockIdx.x, t = row % Tp;
+  const float* lr = ll + (size_t)row * C;
+  float* pr = post + (size_t)row * C;
+  if (t >= T) { for (int c = threadIdx.x; c < C; c += blockDim.x) pr[c] = 0.f; return; }
+  float mx = -INFINITY;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) mx = fmaxf(mx, lr[c]);
+  mx = iv_block_reduce(mx, red, true);
+  float s = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) s += expf(lr[c] - mx);
+  s = iv_block_reduce(s, red, false);
+  const float inv = 1.f / s;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) pr[c] = expf(lr[c] - mx) * inv;
+}
+// dll = post * (dpost - sum_c dpost_c post_c)
+__global__ void softmax_rows_bwd_kernel(const float* __restrict__ post, const float* dpost, float* dll, int C, int T, int Tp) {
+  __shared__ float red[8];
+  const int row = blockIdx.x, t = row % Tp;
+  const float* pr = post + (size_t)row * C;
+  const float* dr = dpost + (size_t)row * C;
+  float* o = dll + (size_t)row * C;
+  if (t >= T) { for (int c = threadIdx.x; c < C; c += blockDim.x) o[c] = 0.f; return; }
+  float s = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) s = fmaf(dr[c], pr[c], s);
+  s = iv_block_reduce(s, red, false);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) o[c] = pr[c] * (dr[c] - s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// batched SPD solve: Lp [B, D(D+1)/2] packed upper triangle (fp32) -> fp64 Cholesky (kept in `fac`,
+// [B, D, D], lower triangle) ; w = L^-1 rhs.  Second entry point solves with the stored factor and forms
+// the adjoints of the system: lambda = L^-1 dw, dLp(i<=j) = -(lambda_i w_j + lambda_j w_i) / (1 + [i==j]).
+// One CTA per utterance.
+// ---------------------------------------------------------------------------------------------
+__device__ void chol_solve_with_factor(const double* __restrict__ A, int D, double* v /* smem [D], in/out */) {
+  // forward substitution L y = v, then back substitution L' w = y  (L lower-triangular, row-major A[i*D + j])
+  for (int k = 0; k < D; ++k) {
+    __syncthreads();
+    if (threadIdx.x == 0) v[k] /= A[(size_t)k * D + k];
+    __syncthreads();
+    const double yk = v[k];
+    for (int i = k + 1 + threadIdx.x; i < D; i += blockDim.x) v[i] -= A[(size_t)i * D + k] * yk;
+  }
+  for (int k = D - 1; k >= 0; --k) {
+    __syncthreads();
+    if (threadIdx.x == 0) v[k] /= A[(size_t)k * D + k];
+    __syncthreads();
+    const double wk = v[k];
+    for (int i = threadIdx.x; i < k; i += blockDim.x) v[i] -= A[(size_t)k * D + i] * wk;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+chol_factor_solve_kernel(const float* __restrict__ Lp, int ldp, const float* __restrict__ rhs, int ldr, float offset,
+                         const float* __restrict__ emb_mean, double* __restrict__ fac, float* __restrict__ wfull,
+                         float* __restrict__ iv, int D) {
+  extern __shared__ double vs[];                                  // [2 D]: right-hand side, staged column
+  const int b = blockIdx.x;
+  double* A = fac + (size_t)b * D * D;
+  const float* lp = Lp + (size_t)b * ldp;
+  // unpack (upper-triangle packing: p = i*D - i(i-1)/2 + (j-i), i <= j) into the lower triangle; L = I + sum_c N_c U_c
+  for (int i = 0; i < D; ++i)
+    for (int j = i + threadIdx.x; j < D; j += blockDim.x)
+      A[(size_t)j * D + i] = (double)lp[(size_t)i * D - (size_t)i * (i - 1) / 2 + (j - i)] + (i == j ? 1.0 : 0.0);
+  __syncthreads();
+  // right-looking Cholesky, in place in the lower triangle; column k is staged in shared memory for the rank-1 update
+  double* colk = vs + D;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  for (int k = 0; k < D; ++k) {
+    __syncthreads();
+    const double dkk = sqrt(A[(size_t)k * D + k]);
+    __syncthreads();
+    if (threadIdx.x == 0) A[(size_t)k * D + k] = dkk;
+    for (int i = k + 1 + threadIdx.x; i < D; i += blockDim.x) {
+      const double v = A[(size_t)i * D + k] / dkk;
+      colk[i] = v;
+      A[(size_t)i * D + k] = v;
+    }
+    __syncthreads();
+    for (int i = k + 1 + warp; i < D; i += nwarp) {
+      const double ci = colk[i];
+      double* ar = A + (size_t)i * D;
+      for (int j = k + 1 + lane; j <= i; j += 32) ar[j] -= ci * colk[j];
+    }
+  }
+  __syncthreads();
+  // linear[0] += prior_offset; ivector[0] -= prior_offset (ivector_extract.py:108-113); then the global mean is removed
+  for (int i = threadIdx.x; i < D; i += blockDim.x) vs[i] = (double)rhs[(size_t)b * ldr + i] + (i == 0 ? (double)offset : 0.0);
+  chol_solve_with_factor(A, D, vs);
+  for (int i = threadIdx.x; i < ldr; i += blockDim.x) {
+    wfull[(size_t)b * ldr + i] = i < D ? (float)vs[i] : 0.f;
+    iv[(size_t)b * ldr + i] = i < D ? (float)(vs[i] - (i == 0 ? (double)offset : 0.0)) - emb_mean[i] : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+chol_solve_bwd_kernel(const double* __restrict__ fac, const float* __restrict__ w, const float* __restrict__ dw, int ldr,
+                      float* __restrict__ drhs, float* __restrict__ dLp, int ldp, int D) {
+  extern __shared__ double vs[];
+  const int b = blockIdx.x;
+  const size_t P = (size_t)D * (D + 1) / 2;
+  const double* A = fac + (size_t)b * D * D;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) vs[i] = (double)dw[(size_t)b * ldr + i];
+  chol_solve_with_factor(A, D, vs);
+  for (int i = threadIdx.x; i < ldr; i += blockDim.x) drhs[(size_t)b * ldr + i] = i < D ? (float)vs[i] : 0.f;
+  const float* wb = w + (size_t)b * ldr;
+  float* o = dLp + (size_t)b * ldp;
+  for (int i = 0; i < D; ++i) {
+    const double li = vs[i];
+    const double wi = (double)wb[i];
+    for (int j = i + threadIdx.x; j < D; j += blockDim.x) {
+      // the packed entry (i,j), i < j, stands for both L_ij and L_ji
+      const double g = (i == j) ? -li * wi : -(li * (double)wb[j] + vs[j] * wi);
+      o[(size_t)i * D - (size_t)i * (i - 1) / 2 + (j - i)] = (float)g;
+    }
+  }
+  for (size_t p = P + threadIdx.x; p < (size_t)ldp; p += blockDim.x) o[p] = 0.f;
+}
+
+// row-major [R, C] -> [C, R] per batch item (layout helper: X^T for the statistics GEMM)
+__global__ void transpose_batched_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int C, int ld_in,
+                                         int ld_out, size_t stride_in, size_t stride_out) {
+  __shared__ float tile[32][33];
+  const float* ib = in + blockIdx.z * stride_in;
+  float* ob = out + blockIdx.z * stride_out;
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < C) ? ib[(size_t)r * ld_in + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < C && r < R) ob[(size_t)c * ld_out + r] = tile[threadIdx.x][i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------------
+static bool g_delta_init = false;
+static int delta_init() {
+  if (g_delta_init) return SG_OK;
+  // get_scales(window 3, order 2): first filter j/28 for j=-3..3, second = first convolved with itself
+  float d1[7], d2[13];
+  for (int j = -3; j <= 3; ++j) d1[j + 3] = (float)j / 28.f;
+  for (int i = 0; i < 13; ++i) d2[i] = 0.f;
+  for (int j = -3; j <= 3; ++j)
+    for (int k = -3; k <= 3; ++k) d2[j + k + 6] += (float)j * d1[k + 3];
+  for (int i = 0; i < 13; ++i) d2[i] *= 1.f / 28.f;
+  SG_CUDA_CHECK(cudaMemcpyToSymbol(c_delta1, d1, sizeof(d1)));
+  SG_CUDA_CHECK(cudaMemcpyToSymbol(c_delta2, d2, sizeof(d2)));
+  g_delta_init = true;
+  return SG_OK;
+}
+static int iv_blocks(size_t n) { size_t b = (n + 255) / 256; return (int)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b)); }
+
+int sg_delta_launch(const float* in, int ld_in, float* out, int ld_out, int B, int T, int F, int backward, cudaStream_t st) {
+  int r = delta_init();
+  if (r != SG_OK) return r;
+  if (!backward) delta_fwd_kernel<<<iv_blocks((size_t)B * T * F), 256, 0, st>>>(in, ld_in, out, ld_out, B, T, F);
+  else delta_bwd_kernel<<<iv_blocks((size_t)B * T * F), 256, 0, st>>>(in, ld_in, out, ld_out, B, T, F);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+int sg_pad_aug_launch(const float* feat, int ld, float* xa, int Fa, int B, int T, int Tp, int F, cudaStream_t st) {
+  pad_aug_kernel<<<iv_blocks((size_t)B * Tp * Fa), 256, 0, st>>>(feat, ld, xa, Fa, B, T, Tp, F);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+int sg_quad_expand_launch(const float* xa, int ldx, float* q, int ldq, int rows, int F, cudaStream_t st) {
+  quad_expand_fwd_kernel<<<rows, 128, F * sizeof(float), st>>>(xa, ldx, q, ldq, F);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+int sg_quad_expand_bwd_launch(const float* dq, int ldq, const float* xa, int ldx, const float* add, float* dx, int lddx,
+                              int B, int T, int Tp, int F, cudaStream_t st) {
+  quad_expand_bwd_kernel<<<B * Tp, 96, F * sizeof(float), st>>>(dq, ldq, xa, ldx, add, dx, lddx, T, Tp, F);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+int sg_softmax_rows_launch(const float* a, const float* b, float* out, int rows, int C, int T, int Tp, int backward,
+                           cudaStream_t st) {
+  if (!backward) softmax_rows_fwd_kernel<<<rows, 256, 0, st>>>(a, out, C, T, Tp);
+  else softmax_rows_bwd_kernel<<<rows, 256, 0, st>>>(a, b, out, C, T, Tp);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+int sg_chol_solve_launch(const float* Lp, int ldp, const float* rhs, int ldr, float offset, const float* emb_mean, double* fac,
+                         float* wfull, float* iv, int B, int D, cudaStream_t st) {
+  chol_factor_solve_kernel<<<B, 256, 2 * D * sizeof(double), st>>>(Lp, ldp, rhs, ldr, offset, emb_mean, fac, wfull, iv, D);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+int sg_chol_solve_bwd_launch(const double* fac, const float* w, const float* dw, int ldr, float* drhs, float* dLp, int ldp,
+                             int B, int D, cudaStream_t st) {
+  chol_solve_bwd_kernel<<<B, 256, D * sizeof(double), st>>>(fac, w, dw, ldr, drhs, dLp, ldp, D);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+int sg_transpose_batched_launch(const float* in, float* out, int R, int C, int ld_in, int ld_out, size_t stride_in,
+                                size_t stride_out, int nbatch, cudaStream_t st) {
+  transpose_batched_kernel<<<dim3((C + 31) / 32, (R + 31) / 32, nbatch), dim3(32, 8), 0, st>>>(in, out, R, C, ld_in, ld_out,
+                                                                                               stride_in, stride_out);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}

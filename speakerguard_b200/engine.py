@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import AudioNetWeights, Cw2Params, LossParams, PgdParams, XvWeights, check
+from ._lib import AudioNetWeights, Cw2Params, IvWeights, LossParams, PgdParams, XvWeights, check
 
 FLD = 32  # internal feature row stride
 
@@ -116,6 +116,78 @@ class Engine:
         with torch.cuda.device(self.device):
             check(self.lib.sg_load_xv(self._h, C.byref(w)), "sg_load_xv")
         self.L, self.S = w.L, w.S
+
+    # ---- i-vector system -----------------------------------------------------------------------
+    def load_iv(self, p: Dict[str, torch.Tensor]) -> None:
+        """p: 'gmm.gconsts' [C], 'gmm.means_invcovars' [C,F], 'gmm.invcovars' [C,F,F], 'ive.T' [C,F,D],
+        'ive.sigma_inv' [C,F,F], 'ive.offset', 'emb_mean' [D], 'lda' [L,D+1], 'plda.mean/.transform/.psi',
+        'enroll' [S,L] (any device; copied to host)."""
+        keep = []
+
+        def host(name):
+            a = np.ascontiguousarray(p[name].detach().cpu().numpy().astype(np.float32))
+            keep.append(a)
+            return a.ctypes.data
+
+        w = IvWeights()
+        Cn, F, D = (int(v) for v in p["ive.T"].shape)
+        w.C, w.F, w.D = Cn, F, D
+        w.L, w.S = int(p["plda.mean"].shape[0]), int(p["enroll"].shape[0])
+        if tuple(p["gmm.invcovars"].shape) != (Cn, F, F) or tuple(p["ive.sigma_inv"].shape) != (Cn, F, F):
+            raise ValueError("gmm.invcovars / ive.sigma_inv must be [C,F,F] matching ive.T [C,F,D]")
+        if tuple(p["lda"].shape) != (w.L, D + 1):
+            raise ValueError(f"lda must be [L, D+1] = [{w.L}, {D + 1}], got {tuple(p['lda'].shape)}")
+        w.gmm_gconsts, w.gmm_means_invcovars = host("gmm.gconsts"), host("gmm.means_invcovars")
+        w.gmm_invcovars, w.ive_T, w.ive_sigma_inv = host("gmm.invcovars"), host("ive.T"), host("ive.sigma_inv")
+        w.ive_offset = float(p["ive.offset"])
+        w.emb_mean, w.lda = host("emb_mean"), host("lda")
+        w.plda_mean, w.plda_transform, w.plda_psi = host("plda.mean"), host("plda.transform"), host("plda.psi")
+        w.enroll = host("enroll")
+        with torch.cuda.device(self.device):
+            check(self.lib.sg_load_iv(self._h, C.byref(w)), "sg_load_iv")
+        self.L, self.S = w.L, w.S
+        self.iv_dims = (Cn, F, D)
+
+    def add_delta(self, feat: torch.Tensor, backward: bool = False) -> torch.Tensor:
+        """[B,T,F] -> [B,T,3F] (or the adjoint, [B,T,3F] -> [B,T,F])."""
+        feat = _f32c(feat, self.device)
+        B, T, ld = feat.shape
+        F = ld // 3 if backward else ld
+        out = torch.empty(B, T, F if backward else 3 * F, device=self.device, dtype=torch.float32)
+        fn = self.lib.sg_add_delta_bwd if backward else self.lib.sg_add_delta_fwd
+        check(fn(self._h, _ptr(feat), ld, _ptr(out), out.shape[2], B, T, F, self.stream), "sg_add_delta")
+        return out
+
+    def cmvn_cols(self, feat: torch.Tensor, backward: bool = False) -> torch.Tensor:
+        feat = _f32c(feat, self.device)
+        B, T, ld = feat.shape
+        out = torch.empty_like(feat)
+        check(self.lib.sg_cmvn_cols(self._h, _ptr(feat), ld, _ptr(out), ld, ld, B, T, int(backward), self.stream), "sg_cmvn_cols")
+        return out
+
+    def iv_embed_fwd(self, feat: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """feat [B,T,F] CMVN'd MFCC+deltas -> (emb [B,L], workspace for iv_embed_bwd / iv_stage)."""
+        feat = _f32c(feat, self.device)
+        B, T, ld = feat.shape
+        ws = self.alloc_ws(self.lib.sg_iv_ws_bytes(self._h, B, T))
+        emb = torch.empty(B, self.L, device=self.device, dtype=torch.float32)
+        check(self.lib.sg_iv_embed_fwd(self._h, _ptr(feat), ld, B, T, _ptr(ws), _ptr(emb), self.stream), "sg_iv_embed_fwd")
+        return emb, ws
+
+    def iv_embed_bwd(self, demb: torch.Tensor, ws: torch.Tensor, B: int, T: int) -> torch.Tensor:
+        demb = _f32c(demb, self.device)
+        F = self.iv_dims[1]
+        dfeat = torch.empty(B, T, F, device=self.device, dtype=torch.float32)
+        check(self.lib.sg_iv_embed_bwd(self._h, _ptr(demb), B, T, _ptr(ws), _ptr(dfeat), F, self.stream), "sg_iv_embed_bwd")
+        return dfeat
+
+    def iv_stage(self, ws: torch.Tensor, B: int, T: int, stage: str) -> torch.Tensor:
+        Cn, F, D = self.iv_dims
+        shape, code = {"post": ((B, T, Cn), _lib.IV_STAGE_POST), "stats": ((B, F + 1, Cn), _lib.IV_STAGE_STATS),
+                       "ivector": ((B, D), _lib.IV_STAGE_IVECTOR)}[stage]
+        out = torch.empty(*shape, device=self.device, dtype=torch.float32)
+        check(self.lib.sg_iv_stage_read(self._h, _ptr(ws), B, T, code, _ptr(out), self.stream), "sg_iv_stage_read")
+        return out
 
     # ---- AudioNet ------------------------------------------------------------------------------
     AN_CONVS = ["conv2", "conv3", "conv4", "conv5", "conv6", "conv7", "conv8"]

@@ -115,3 +115,65 @@ class AnCnnFn(torch.autograd.Function):
     def backward(ctx, g):
         B, N = ctx.dims
         return ctx.eng.an_cnn_bwd(g.contiguous(), ctx.ws, B, N), None, None
+
+
+class Mfcc24Fn(torch.autograd.Function):
+    """x [B,N] -> the first ``num_ceps`` MFCCs [B,m,num_ceps] (iv_plda.raw asks kaldi.mfcc for 24 of the
+    30 cepstra, model/iv_plda.py:203-237; lifter and DCT columns do not depend on num_ceps)."""
+
+    @staticmethod
+    def forward(ctx, x, eng: Engine, mode: int, dither: Optional[torch.Tensor], seed: int, pass_: int, num_ceps: int):
+        x = x.contiguous()
+        ctx.eng, ctx.mode, ctx.dither, ctx.seed, ctx.pass_, ctx.nc = eng, mode, dither, seed, pass_, num_ceps
+        ctx.save_for_backward(x)
+        return eng.mfcc_fwd(x, mode, dither, seed, pass_, ld=30)[:, :, :num_ceps].contiguous()
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        g30 = torch.zeros(g.shape[0], g.shape[1], 30, device=g.device, dtype=torch.float32)
+        g30[:, :, :ctx.nc] = g
+        grad = ctx.eng.mfcc_bwd(x, g30, ctx.mode, ctx.dither, ctx.seed, ctx.pass_)
+        return grad, None, None, None, None, None, None
+
+
+class DeltaFn(torch.autograd.Function):
+    """[B,T,F] -> [B,T,3F] delta + delta-delta features  (sg_add_delta_fwd / _bwd)."""
+
+    @staticmethod
+    def forward(ctx, feat, eng: Engine):
+        ctx.eng = eng
+        return eng.add_delta(feat.contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        return ctx.eng.add_delta(g.contiguous(), backward=True), None
+
+
+class CmvnColsFn(torch.autograd.Function):
+    """Sliding-window CMVN over any number of columns  (sg_cmvn_cols)."""
+
+    @staticmethod
+    def forward(ctx, feat, eng: Engine):
+        ctx.eng = eng
+        return eng.cmvn_cols(feat.contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        return ctx.eng.cmvn_cols(g.contiguous(), backward=True), None
+
+
+class IvEmbedFn(torch.autograd.Function):
+    """CMVN features [B,T,72] -> PLDA-space i-vector embedding [B,L]  (sg_iv_embed_fwd / _bwd)."""
+
+    @staticmethod
+    def forward(ctx, feat, eng: Engine):
+        B, T, F = feat.shape
+        emb, ws = eng.iv_embed_fwd(feat.contiguous())
+        ctx.eng, ctx.ws, ctx.shape = eng, ws, (B, T, F)
+        return emb
+
+    @staticmethod
+    def backward(ctx, g):
+        B, T, F = ctx.shape
+        return ctx.eng.iv_embed_bwd(g.contiguous(), ctx.ws, B, T), None

@@ -73,3 +73,82 @@ def parse_enroll_model_file(path: str, device):
         warnings.warn("model_file holds more than one speaker: make sure the task is not SV "
                       "(SV expects exactly one enrolled speaker).")
     return len(spk_ids), spk_ids, z_means, z_stds, enroll
+
+
+# ---- Kaldi text models of the i-vector system (model/_iv_plda/gmm.py:33-81, ivector_extract.py:28-70) ----
+class _Tokens:
+    """Whitespace token stream over a Kaldi text-mode model file."""
+
+    def __init__(self, path: str):
+        with open(path, "r") as f:
+            self.t = f.read().split()
+        self.i = 0
+
+    def seek(self, tag: str) -> None:
+        try:
+            self.i = self.t.index(tag, self.i) + 1
+        except ValueError:
+            raise ValueError(f"tag {tag} not found") from None
+
+    def take_bracketed(self) -> np.ndarray:
+        """Numbers of the next '[ ... ]' group (vector, matrix or packed triangle), flattened."""
+        while self.t[self.i] != "[":
+            self.i += 1                       # e.g. the component count after <M> / <SigmaInv>
+        j = self.t.index("]", self.i)
+        vals = np.asarray(self.t[self.i + 1:j], dtype=np.float64)
+        self.i = j + 1
+        return vals
+
+
+def _unpack_lower(packed: np.ndarray, dim: int) -> np.ndarray:
+    """Kaldi SpMatrix text order (row-wise lower triangle) -> dense symmetric [dim, dim]."""
+    if packed.size != dim * (dim + 1) // 2:
+        raise ValueError(f"packed matrix has {packed.size} entries, expected {dim * (dim + 1) // 2}")
+    m = np.zeros((dim, dim), dtype=np.float64)
+    m[np.tril_indices(dim)] = packed
+    return m + np.tril(m, -1).T
+
+
+def parse_fgmm_file(path: str):
+    """Full-covariance UBM, Kaldi text: <GCONSTS> [C], <WEIGHTS> [C], <MEANS_INVCOVARS> [C,F],
+    <INV_COVARS> C packed triangles.  Returns float32 arrays (gconsts, weights, means_invcovars, invcovars [C,F,F])."""
+    tk = _Tokens(path)
+    tk.seek("<GCONSTS>")
+    gconsts = tk.take_bracketed()
+    tk.seek("<WEIGHTS>")
+    weights = tk.take_bracketed()
+    C = gconsts.size
+    tk.seek("<MEANS_INVCOVARS>")
+    mic = tk.take_bracketed()
+    if mic.size % C != 0:
+        raise ValueError(f"malformed UBM file {path}: {mic.size} mean entries for {C} components")
+    F = mic.size // C
+    tk.seek("<INV_COVARS>")
+    inv = np.stack([_unpack_lower(tk.take_bracketed(), F) for _ in range(C)])
+    f32 = np.float32
+    return gconsts.astype(f32), weights.astype(f32), mic.reshape(C, F).astype(f32), inv.astype(f32)
+
+
+def parse_ivector_extractor_file(path: str):
+    """i-vector extractor, Kaldi text: <w_vec> [C], <M> C matrices [F,D], <SigmaInv> C packed triangles,
+    <IvectorOffset> scalar.  Returns float32 (T [C,F,D], sigma_inv [C,F,F], offset)."""
+    tk = _Tokens(path)
+    tk.seek("<w_vec>")
+    C = tk.take_bracketed().size
+    tk.seek("<M>")
+    mats = []
+    for _ in range(C):
+        start = tk.i
+        flat = tk.take_bracketed()
+        mats.append((flat, start))
+    tk.seek("<SigmaInv>")
+    packed = [tk.take_bracketed() for _ in range(C)]
+    # F from the packed triangle size, D from the matrix size
+    n = packed[0].size
+    F = int((np.sqrt(8 * n + 1) - 1) / 2 + 0.5)
+    D = mats[0][0].size // F
+    T = np.stack([m.reshape(F, D) for m, _ in mats])
+    sig = np.stack([_unpack_lower(p, F) for p in packed])
+    tk.seek("<IvectorOffset>")
+    offset = float(tk.t[tk.i])
+    return T.astype(np.float32), sig.astype(np.float32), offset

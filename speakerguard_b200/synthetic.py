@@ -86,3 +86,80 @@ def synthetic_batch(B: int, N: int, S: int = 10, seed: int = 1234):
     x = (torch.rand(B, 1, N, generator=g) * 2 - 1) * 0.5
     y = torch.randint(0, S, (B,), generator=g)
     return x, y
+
+
+# ---- i-vector system (BASELINE config 5) ---------------------------------------------------------
+def make_iv_params(seed: int = 0, C: int = 64, F: int = 72, D: int = 40, L: int = 30, S: int = 1) -> Dict[str, torch.Tensor]:
+    """Synthetic full-covariance UBM + i-vector extractor + back-end (config 5: C=2048, F=72, D=400, L=200).
+    SPD inverse covariances with per-dimension std around 3-4, the range of CMVN'd MFCC+delta features."""
+    g = torch.Generator().manual_seed(seed + 31337)
+    p: Dict[str, torch.Tensor] = {}
+    mu = 3.0 * torch.randn(C, F, generator=g)
+    A = torch.randn(C, F, F, generator=g) / math.sqrt(F)
+    invcov = 0.05 * (A @ A.transpose(1, 2)) + 0.06 * torch.eye(F)
+    invcov = 0.5 * (invcov + invcov.transpose(1, 2))
+    w = torch.softmax(torch.randn(C, generator=g), 0)
+    p["gmm.invcovars"] = invcov
+    p["gmm.means_invcovars"] = (invcov @ mu.unsqueeze(-1)).squeeze(-1)
+    logdet = torch.linalg.slogdet(invcov.double())[1].float()
+    quad = (mu.unsqueeze(1) @ invcov @ mu.unsqueeze(-1)).flatten()
+    p["gmm.gconsts"] = torch.log(w) - 0.5 * (F * math.log(2 * math.pi) - logdet + quad)
+    p["gmm.weights"] = w
+    p["ive.T"] = 0.3 * torch.randn(C, F, D, generator=g)
+    Bm = torch.randn(C, F, F, generator=g) / math.sqrt(F)
+    sig = 0.05 * (Bm @ Bm.transpose(1, 2)) + 0.06 * torch.eye(F)
+    p["ive.sigma_inv"] = 0.5 * (sig + sig.transpose(1, 2))
+    p["ive.offset"] = torch.tensor(5.0)
+    p["plda.mean"] = _round6(0.1 * torch.randn(L, generator=g))
+    p["plda.transform"] = _round6(torch.randn(L, L, generator=g) / math.sqrt(L))
+    p["plda.psi"] = _round6(torch.randn(L, generator=g).abs() + 0.1)
+    p["emb_mean"] = _round6(0.1 * torch.randn(D, generator=g))
+    p["lda"] = _round6(torch.randn(L, D + 1, generator=g) / math.sqrt(D))
+    p["enroll"] = torch.randn(S, L, generator=g)
+    return p
+
+
+def _packed_rows(M) -> str:
+    """Kaldi SpMatrix text: row i holds the i+1 lower-triangle entries; ']' closes the last row."""
+    n = len(M)
+    return "".join(" ".join("%.9g" % M[i][j] for j in range(i + 1)) + (" \n" if i < n - 1 else " ]\n") for i in range(n))
+
+
+def _rows9(M) -> str:
+    return "".join("  " + " ".join("%.9g" % x for x in r) + (" \n" if i < len(M) - 1 else " ]\n") for i, r in enumerate(M))
+
+
+def _vec9(v) -> str:
+    return " [ " + " ".join("%.9g" % x for x in v) + " ]\n"
+
+
+def write_iv_model_files(p: Dict[str, torch.Tensor], out_dir: str) -> Dict[str, str]:
+    """final_ubm.txt / final_ie.txt in the Kaldi text layout the reference's line parsers expect
+    (gmm.py:33-81, ivector_extract.py:28-70) plus the back-end files of write_xv_model_files."""
+    f = write_xv_model_files(p, out_dir)
+    f["final_ubm.txt"], f["final_ie.txt"] = os.path.join(out_dir, "final_ubm.txt"), os.path.join(out_dir, "final_ie.txt")
+    C = p["gmm.gconsts"].shape[0]
+    with open(f["final_ubm.txt"], "w") as fh:
+        fh.write("<FullGMM> \n<GCONSTS> " + _vec9(p["gmm.gconsts"].tolist()))
+        fh.write("<WEIGHTS> " + _vec9(p["gmm.weights"].tolist()))
+        fh.write("<MEANS_INVCOVARS>  [\n" + _rows9(p["gmm.means_invcovars"].tolist()))
+        fh.write("<INV_COVARS>  [\n")
+        for c in range(C):
+            if c:
+                fh.write(" [\n")
+            fh.write(_packed_rows(p["gmm.invcovars"][c].tolist()))
+        fh.write("</FullGMM> \n")
+    with open(f["final_ie.txt"], "w") as fh:
+        fh.write("<IvectorExtractor> \n<w> [ ]\n<w_vec> " + _vec9([1.0 / C] * C))
+        fh.write(f"<M> {C}  [\n")
+        for c in range(C):
+            if c:
+                fh.write(" [\n")
+            fh.write(_rows9(p["ive.T"][c].tolist()))
+        fh.write(f"<SigmaInv> {C}  [\n")
+        for c in range(C):
+            if c:
+                fh.write(" [\n")
+            fh.write(_packed_rows(p["ive.sigma_inv"][c].tolist()))
+        fh.write("<IvectorOffset> %.9g \n</IvectorExtractor> \n" % float(p["ive.offset"]))
+    return f

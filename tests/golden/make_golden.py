@@ -274,9 +274,82 @@ def feco_case(out):
                 "feco.out": y.detach().numpy()[0], "feco.w": w.numpy(), "feco.grad": feat.grad.numpy()[0]})
 
 
+def build_reference_iv(p, threshold):
+    """Reference iv_plda built by attribute injection (its __init__ parses / pickles huge text files)."""
+    from model._iv_plda.gmm import FullGMM
+    from model._iv_plda.ivector_extract import ivectorExtractor
+    from model._iv_plda.plda import PLDA
+    from model.iv_plda import iv_plda
+    fg = FullGMM.__new__(FullGMM)
+    fg.device = "cpu"
+    fg.num_gaussians, fg.dim = p["gmm.gconsts"].shape[0], p["gmm.means_invcovars"].shape[1]
+    fg.gconsts, fg.weights = p["gmm.gconsts"].clone(), p["gmm.weights"].clone()
+    fg.means_invcovars, fg.invcovars = p["gmm.means_invcovars"].clone(), p["gmm.invcovars"].clone()
+    fg.Means()
+    ex = ivectorExtractor.__new__(ivectorExtractor)
+    ex.device = "cpu"
+    ex.num_gaussian, ex.dim, ex.ivector_dim = p["ive.T"].shape
+    ex.extractor_matrix, ex.sigma_inv, ex.offset = p["ive.T"].clone(), p["ive.sigma_inv"].clone(), p["ive.offset"].clone()
+    pl = PLDA.__new__(PLDA)
+    pl.device, pl.dim = "cpu", p["plda.mean"].shape[0]
+    pl.mean, pl.transform, pl.psi = p["plda.mean"].clone(), p["plda.transform"].clone(), p["plda.psi"].clone()
+    m = iv_plda.__new__(iv_plda)
+    torch.nn.Module.__init__(m)
+    m.device, m.fgmm, m.extractor, m.plda = "cpu", fg, ex, pl
+    m.emb_mean, m.transform_mat, m.enroll_embs = p["emb_mean"].clone(), p["lda"].clone(), p["enroll"].clone()
+    m.num_spks, m.spk_ids = p["enroll"].shape[0], [f"spk{i}" for i in range(p["enroll"].shape[0])]
+    m.threshold = threshold
+    m.allowed_flags, m.range_type, m.gmm_frame_bs = [0, 1, 2, 3], "origin", 200
+    m.eval()
+    return m
+
+
+def iv_case(out):
+    from attack.PGD import PGD
+    from attack.utils import SEC4SR_MarginLoss
+    p = O.make_iv_params(seed=0)
+    thr = 0.35
+    model = build_reference_iv(p, thr)
+    B, N = 2, 32000
+    x, _ = make_inputs(606, B, N)
+    y = torch.tensor([0, -1])
+    xr = x.clone().requires_grad_(True)
+    torch.manual_seed(607)
+    with RandnTap() as tap:
+        raw = model.compute_feat(xr, flag=1)
+    dither = torch.stack(tap.draws)
+    delta = model.comput_feat_from_feat(raw, 1, 2)
+    feat = model.comput_feat_from_feat(delta, 2, 3)
+    emb = model.embedding(feat, flag=3)
+    scores = model.scoring_trials(model.enroll_embs, emb)
+    loss = SEC4SR_MarginLoss(targeted=False, task="SV", threshold=thr, clip_max=False)(scores, y)
+    loss.backward(torch.ones_like(loss))
+    out.update({"iv.B": B, "iv.N": N, "iv.thr": thr, "iv.x_cks": cks(x), "iv.dither_cks": cks(dither), "iv.y": y.numpy(),
+                "iv.raw": raw.detach().numpy(), "iv.delta": delta.detach().numpy(), "iv.feat": feat.detach().numpy(),
+                "iv.emb": emb.detach().numpy(), "iv.scores": scores.detach().numpy(), "iv.loss": loss.detach().numpy(),
+                "iv.grad": xr.grad[:, 0].numpy()})
+    o = O.iv_forward(x[:, 0], p, dither, return_all=True)
+    print(f"[iv] oracle-vs-ref max|d| raw {float((o['raw'] - raw).abs().max()):.3e} delta {float((o['delta'] - delta).abs().max()):.3e} "
+          f"feat {float((o['feat'] - feat).abs().max()):.3e} emb {float((o['emb'] - emb).abs().max()):.3e} "
+          f"scores {float((o['scores'] - scores).abs().max()):.3e}")
+    # PGD-2, SV task (margin loss forced, attack/utils.py:107-111)
+    att = PGD(model, task="SV", epsilon=0.002, step_size=0.0004, max_iter=2, batch_size=B, verbose=0)
+    torch.manual_seed(608)
+    with RandnTap() as tap:
+        adv, success = att.attack(x, y)
+    out.update({"ivpgd.dither_cks": cks(torch.stack(tap.draws)), "ivpgd.adv": adv.detach()[:, 0].numpy(),
+                "ivpgd.success": np.array(success)})
+    print(f"[iv] PGD-2 SV success {success}")
+
+
 def main():
     torch.set_num_threads(8)
     out = {}
+    if "--only-iv" in sys.argv:
+        iv_case(out)
+        np.savez_compressed(os.path.join(HERE, "iv_golden.npz"), **out)
+        print("iv_golden.npz", os.path.getsize(os.path.join(HERE, "iv_golden.npz")) // 1024, "KiB")
+        return
     if "--only-audionet" in sys.argv:
         audionet_case(out)
         np.savez_compressed(os.path.join(HERE, "audionet_golden.npz"),

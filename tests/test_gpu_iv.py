@@ -1,0 +1,240 @@
+"""GPU parity tests for the i-vector path (BASELINE config 5): libsgb200 through the C-ABI and the
+drop-in ``iv_plda`` class vs the CPU oracle and the golden fixtures produced by the reference's own
+``model.iv_plda.iv_plda`` (tests/golden/make_golden.py --only-iv).
+
+Tolerances: features / posteriors / statistics / i-vectors / embeddings / scores / input gradients within
+1e-4 relative (max-norm per row) unless a looser bound is stated next to the assertion with its reason.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sg_oracle as O
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def relerr(a, b) -> float:
+    a, b = torch.as_tensor(a).detach().double().cpu().flatten(1), torch.as_tensor(b).detach().double().cpu().flatten(1)
+    return float(((a - b).abs().max(1)[0] / b.abs().max(1)[0].clamp_min(1e-30)).max())
+
+
+@pytest.fixture(scope="module")
+def params():
+    return O.make_iv_params(seed=0)
+
+
+@pytest.fixture(scope="module")
+def eng(params):
+    from speakerguard_b200.engine import Engine
+    e = Engine("cuda:0", precision="fp32")
+    e.load_iv(params)
+    return e
+
+
+@pytest.fixture(scope="module")
+def ivg():
+    return np.load(os.path.join(G, "iv_golden.npz"))
+
+
+def feats(B, T, F=72, seed=5):
+    g = torch.Generator().manual_seed(seed)
+    return 3.0 * torch.randn(B, T, F, generator=g)
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,T,F", [(2, 200, 24), (1, 7, 24), (3, 5, 8), (1, 1, 24), (2, 501, 24)])
+def test_add_delta_forward_and_adjoint(eng, B, T, F):
+    x = feats(B, T, F)
+    ref = O.add_delta(x)
+    got = eng.add_delta(x.cuda()).cpu()
+    assert got.shape == ref.shape == (B, T, 3 * F)
+    assert float((got - ref).abs().max()) < 1e-5 * max(1.0, float(ref.abs().max()))
+    g = feats(B, T, 3 * F, seed=6)
+    xr = x.clone().requires_grad_(True)
+    O.add_delta(xr).backward(g)
+    back = eng.add_delta(g.cuda(), backward=True).cpu()
+    assert back.shape == x.shape
+    assert relerr(back, xr.grad) < 1e-5
+
+
+@pytest.mark.parametrize("T", [40, 300, 301, 500])
+def test_cmvn_72_columns(eng, T):
+    x = feats(2, T)
+    ref = O.cmvn(x)
+    got = eng.cmvn_cols(x.cuda()).cpu()
+    assert float((got - ref).abs().max()) < 2e-5
+    g = feats(2, T, seed=9)
+    xr = x.clone().requires_grad_(True)
+    O.cmvn(xr).backward(g)
+    assert relerr(eng.cmvn_cols(g.cuda(), backward=True).cpu(), xr.grad) < 1e-5
+
+
+def oracle_embed(feat, p):
+    """feat [B,T,72] -> dict of per-stage oracle results (same composition as O.iv_forward)."""
+    post, stats, ivs = [], [], []
+    for f in feat:
+        ll = O.gmm_loglike(f, p)
+        po = torch.softmax(ll, -1)
+        N, Fs = po.sum(0), po.T @ f
+        post.append(po)
+        stats.append(torch.cat([Fs.T, N.view(1, -1)], 0))
+        ivs.append(O.ivector(N, Fs, p))
+    iv = torch.stack(ivs)
+    return {"post": torch.stack(post), "stats": torch.stack(stats), "ivector": iv, "emb": O.process_emb(iv, p)}
+
+
+@pytest.mark.parametrize("B,T", [(2, 200), (3, 37), (1, 512)])
+def test_embed_stages_against_oracle(eng, params, B, T):
+    x = feats(B, T, seed=11 + T)
+    ref = oracle_embed(x.double(), {k: v.double() for k, v in params.items()})
+    emb, ws = eng.iv_embed_fwd(x.cuda())
+    post = eng.iv_stage(ws, B, T, "post").cpu()
+    stats = eng.iv_stage(ws, B, T, "stats").cpu()
+    iv = eng.iv_stage(ws, B, T, "ivector").cpu()
+    e = {"post": float((post - ref["post"]).abs().max()), "stats": relerr(stats, ref["stats"]),
+         "ivector": relerr(iv, ref["ivector"]), "emb": relerr(emb, ref["emb"])}
+    print(f"iv stages B={B} T={T}: {e}")
+    assert e["post"] < 1e-4          # posteriors are in [0,1]: absolute
+    assert e["stats"] < 1e-4 and e["ivector"] < 1e-4 and e["emb"] < 1e-4
+
+
+@pytest.mark.parametrize("B,T", [(2, 200), (2, 45)])
+def test_embed_backward_against_oracle(eng, params, B, T):
+    x = feats(B, T, seed=3 + T)
+    g = torch.randn(B, params["plda.mean"].shape[0], generator=torch.Generator().manual_seed(8))
+    pd = {k: v.double() for k, v in params.items()}
+    xr = x.double().requires_grad_(True)
+    oracle_embed(xr, pd)["emb"].backward(g.double())
+    emb, ws = eng.iv_embed_fwd(x.cuda())
+    got = eng.iv_embed_bwd(g.cuda(), ws, B, T).cpu()
+    e = relerr(got, xr.grad)
+    print(f"iv embed backward B={B} T={T}: rel {e:.3e}")
+    assert e < 1e-4
+
+
+def test_load_errors(params):
+    from speakerguard_b200 import _lib
+    from speakerguard_b200.engine import Engine
+    e = Engine("cuda:0")
+    with pytest.raises(_lib.SgError, match="not loaded"):
+        e.iv_dims = (64, 72, 40)
+        e.L = 30
+        e.iv_embed_fwd(torch.zeros(1, 10, 72).cuda())
+    bad = dict(params)
+    bad["ive.T"] = params["ive.T"][:60]
+    bad["gmm.invcovars"], bad["ive.sigma_inv"] = params["gmm.invcovars"][:60], params["ive.sigma_inv"][:60]
+    with pytest.raises(_lib.SgError, match="C % 16"):
+        e.load_iv(bad)
+
+
+# ---- drop-in class ------------------------------------------------------------------------------
+def iv_regen(g, n_pass=None, seeds=(606, 607)):
+    B, N = int(g["iv.B"]), int(g["iv.N"])
+    torch.manual_seed(seeds[0])
+    x = (torch.rand(B, 1, N) * 2 - 1) * 0.5
+    m = O.num_frames(N)
+    torch.manual_seed(seeds[1])
+    n = B if n_pass is None else n_pass * B
+    d = torch.stack([torch.randn((m, 400)) for _ in range(n)])
+    return x, torch.from_numpy(g["iv.y"]), d if n_pass is None else d.view(n_pass, B, m, 400)
+
+
+class DitherFeed:
+    """Feeds a recorded dither stream to the model, one [B,m,400] block per pass (the reference draws
+    torch.randn per utterance, kaldi.py:180; the fixtures hold the stream it drew)."""
+
+    def __init__(self, d):
+        self.d, self.i = (d if d.dim() == 4 else d.unsqueeze(0)), 0
+
+    def __call__(self, B, m):
+        out = self.d[self.i]
+        self.i += 1
+        return out
+
+
+def make_model(params, thr, **kw):
+    from speakerguard_b200.model.iv_plda import iv_plda
+    return iv_plda(None, None, None, None, None, threshold=thr, device="cuda:0", params=params, **kw)
+
+
+def test_class_against_reference_golden(params, ivg):
+    from speakerguard_b200.attack.utils import SEC4SR_MarginLoss
+    x, y, d = iv_regen(ivg)
+    thr = float(ivg["iv.thr"])
+    model = make_model(params, thr, dither=DitherFeed(d))
+    assert model.allowed_flags == [0, 1, 2, 3] and model.range_type == "origin"
+    xr = x.cuda().requires_grad_(True)
+    raw = model.compute_feat(xr, flag=1)
+    delta = model.comput_feat_from_feat(raw, 1, 2)
+    feat = model.comput_feat_from_feat(delta, 2, 3)
+    emb = model.embedding(feat, flag=3)
+    scores = model.scoring_trials(model.enroll_embs, emb)
+    loss = SEC4SR_MarginLoss(targeted=False, task="SV", threshold=thr, clip_max=False)(scores, y.cuda())
+    loss.backward(torch.ones_like(loss))
+    e = {k: relerr(v, ivg[f"iv.{k}"]) for k, v in [("raw", raw), ("delta", delta), ("feat", feat), ("emb", emb)]}
+    e["scores"] = float((scores.detach().cpu() - torch.from_numpy(ivg["iv.scores"])).abs().max())
+    e["loss"] = float((loss.detach().cpu() - torch.from_numpy(ivg["iv.loss"])).abs().max())
+    e["grad"] = relerr(xr.grad[:, 0], ivg["iv.grad"])
+    print(f"iv class vs reference golden: {e}")
+    assert e["raw"] < 1e-4 and e["delta"] < 1e-4 and e["feat"] < 1e-4 and e["emb"] < 1e-4
+    assert e["scores"] < 1e-4 and e["loss"] < 1e-4
+    # the golden gradient is the reference's own fp32 autograd through torch.inverse: 1e-3 covers its round-off
+    assert e["grad"] < 1e-3
+    # other entry levels give the same scores; decisions follow the threshold
+    model.dither = DitherFeed(d)
+    dec, s0 = model.make_decision(x.cuda())
+    assert float((s0 - scores.detach()).abs().max()) < 1e-5
+    assert torch.equal(dec.cpu(), O.decide(torch.from_numpy(ivg["iv.scores"]), thr))
+    for flag, inp in [(1, raw), (2, delta), (3, feat)]:
+        assert float((model.score(inp.detach(), flag=flag) - scores.detach()).abs().max()) < 1e-5
+
+
+def test_pgd_sv_against_reference_golden(params, ivg):
+    from speakerguard_b200.attack.PGD import PGD
+    x, y, _ = iv_regen(ivg)
+    _, _, d = iv_regen(ivg, n_pass=3, seeds=(606, 608))
+    model = make_model(params, float(ivg["iv.thr"]), dither=DitherFeed(d))
+    att = PGD(model, task="SV", epsilon=0.002, step_size=0.0004, max_iter=2, batch_size=2, verbose=0)
+    adv, success = att.attack(x.cuda(), y.cuda())
+    assert list(success) == ivg["ivpgd.success"].tolist()
+    ref = torch.from_numpy(ivg["ivpgd.adv"])
+    same = float(((adv[:, 0].cpu() - ref).abs() < 1e-7).float().mean())
+    print(f"iv PGD-2 SV: identical samples {same:.5f}")
+    assert same > 0.99                       # sign flips only where |grad| is at round-off level
+
+
+def test_class_from_kaldi_text_files(params, tmp_path):
+    from speakerguard_b200.model.iv_plda import iv_plda
+    from speakerguard_b200.synthetic import write_iv_model_files
+    f = write_iv_model_files(params, str(tmp_path))
+    m1 = iv_plda(f["final_ubm.txt"], f["final_ie.txt"], f["plda.txt"], f["mean.vec"], f["transform.txt"],
+                 model_file=f["speaker_model"], threshold=0.35, device="cuda:0", dither="off")
+    m2 = make_model(params, 0.35, dither="off")
+    torch.manual_seed(5)
+    x = ((torch.rand(2, 1, 24000) * 2 - 1) * 0.5).cuda()
+    s1, s2 = m1.score(x), m2.score(x)
+    assert m1.num_spks == 1 and s1.shape == (2, 1)
+    # %.9g text round trip of the UBM / extractor: identical to fp32 round-off
+    assert float((s1 - s2).abs().max()) < 1e-4 * float(s2.abs().max())
+
+
+def test_medium_system_five_seconds():
+    """C=256 components, 100-dim i-vectors, 5 s utterances (T=500 > the 300-frame CMVN window)."""
+    p = O.make_iv_params(seed=3, C=256, D=100, L=50)
+    torch.manual_seed(77)
+    x = (torch.rand(2, 1, 80000) * 2 - 1) * 0.5
+    model = make_model(p, 0.0, dither="off")
+    xr = x.cuda().requires_grad_(True)
+    scores = model(xr)
+    scores.sum().backward()
+    xo = x[:, 0].clone().requires_grad_(True)
+    ref = O.iv_forward(xo, p, None)
+    ref.sum().backward()
+    es, eg = float((scores.detach().cpu() - ref.detach()).abs().max()), relerr(xr.grad[:, 0], xo.grad)
+    print(f"iv medium: scores abs {es:.3e} grad rel {eg:.3e}")
+    assert es < 1e-3 * max(1.0, float(ref.abs().max()))
+    assert eg < 1e-3                         # fp32 oracle (torch.linalg.solve, einsum) vs fp32 kernels + fp64 solve

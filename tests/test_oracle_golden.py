@@ -136,3 +136,71 @@ def test_cw2_oracle_vs_reference_outcome():
     assert suc == g["cw2.success"].tolist()
     l2 = lambda a: (a - x).pow(2).sum(1).numpy()
     np.testing.assert_allclose(l2(xa), l2(torch.tensor(g["cw2.adv"])), rtol=0.15)
+
+
+# ---- i-vector system (BASELINE config 5) -----------------------------------------------------------
+def iv_regen(g, n_pass=None, seeds=(606, 607)):
+    B, N = int(g["iv.B"]), int(g["iv.N"])
+    torch.manual_seed(seeds[0])
+    x = (torch.rand(B, 1, N) * 2 - 1) * 0.5
+    m = O.num_frames(N)
+    torch.manual_seed(seeds[1])
+    n = B if n_pass is None else n_pass * B
+    d = torch.stack([torch.randn((m, 400)) for _ in range(n)])
+    d = d if n_pass is None else d.view(n_pass, B, m, 400)
+    assert abs(float(x.double().abs().sum()) - float(g["iv.x_cks"])) < 1e-9, "input regeneration drifted"
+    return x[:, 0], torch.from_numpy(g["iv.y"]), d
+
+
+@pytest.fixture(scope="module")
+def ivg():
+    return np.load(os.path.join(G, "iv_golden.npz"))
+
+
+def test_iv_forward_stages(ivg):
+    p = O.make_iv_params(seed=0)
+    x, y, d = iv_regen(ivg)
+    assert abs(float(d.double().abs().sum()) - float(ivg["iv.dither_cks"])) < 1e-6
+    o = O.iv_forward(x, p, d, return_all=True)
+    assert np.array_equal(o["raw"].numpy(), ivg["iv.raw"])
+    np.testing.assert_allclose(o["delta"].numpy(), ivg["iv.delta"], atol=5e-6, rtol=0)
+    np.testing.assert_allclose(o["feat"].numpy(), ivg["iv.feat"], atol=1e-5, rtol=0)
+    np.testing.assert_allclose(o["emb"].numpy(), ivg["iv.emb"], atol=1e-5, rtol=1e-5)
+    np.testing.assert_allclose(o["scores"].numpy(), ivg["iv.scores"], atol=1e-4, rtol=0)
+
+
+def test_iv_sv_margin_gradient(ivg):
+    p = O.make_iv_params(seed=0)
+    x, y, d = iv_regen(ivg)
+    thr = float(ivg["iv.thr"])
+    loss_fn, _ = O.resolve_loss("Margin", False, 0.0, "SV", thr, clip_max=False)
+    scores, loss, grad, dec = O.xv_loss_and_grad(x, y, p, loss_fn, d, system="iv")
+    np.testing.assert_allclose(loss.numpy(), ivg["iv.loss"], atol=1e-4, rtol=0)
+    ref = ivg["iv.grad"]
+    err = np.abs(grad.numpy() - ref).max(axis=1) / np.abs(ref).max(axis=1)
+    assert err.max() < 1e-3, err
+
+
+def test_iv_pgd_sv(ivg):
+    p = dict(O.make_iv_params(seed=0))
+    p["threshold"] = float(ivg["iv.thr"])
+    x, y, _ = iv_regen(ivg)
+    _, _, d = iv_regen(ivg, n_pass=3, seeds=(606, 608))
+    assert abs(float(d.double().abs().sum()) - float(ivg["ivpgd.dither_cks"])) < 1e-6
+    adv, success, _ = O.pgd_attack(x, y, p, epsilon=0.002, step_size=0.0004, max_iter=2, task="SV", dither=d, system="iv")
+    assert success == ivg["ivpgd.success"].tolist()
+    ref = ivg["ivpgd.adv"]
+    frac = float((np.abs(adv.numpy() - ref) < 1e-7).mean())
+    assert frac > 0.995, frac
+
+
+def test_iv_delta_filters_and_solver_adjoint():
+    """add_delta equals two passes of the first-order filter away from the edges; the i-vector of zero
+    statistics is the prior (offset in the first coordinate, removed again: ivector_extract.py:108-113)."""
+    s = O.delta_scales()
+    assert [t.numel() for t in s] == [1, 7, 13]
+    np.testing.assert_allclose(s[1].numpy(), np.arange(-3, 4) / 28.0, atol=1e-7)
+    p = O.make_iv_params(seed=0)
+    C, Fd = p["gmm.gconsts"].shape[0], p["gmm.means_invcovars"].shape[1]
+    iv = O.ivector(torch.zeros(C), torch.zeros(C, Fd), p)
+    np.testing.assert_allclose(iv.numpy(), 0.0, atol=1e-6)
