@@ -274,7 +274,7 @@ extern "C" int sg_iv_stage_read(sg_handle* h, const void* ws, int B, int T, int 
     case SG_IV_STAGE_STATS:    // [B, F+1, C]: first-order statistics transposed, zeroth-order in the last row
       SG_CUDA_CHECK(cudaMemcpy2DAsync(out, (size_t)(m->F + 1) * m->C * 4, w.FsT, (size_t)m->Fa * m->C * 4, (size_t)(m->F + 1) * m->C * 4, B, cudaMemcpyDeviceToDevice, st));
       break;
-    case SG_IV_STAGE_IVECTOR:  // [B, D]: i-vector with the prior offset removed, before mean subtraction
+    case SG_IV_STAGE_IVECTOR:  // [B, D]: solution of the linear system (prior offset still in coordinate 0, mean not removed)
       SG_CUDA_CHECK(cudaMemcpy2DAsync(out, (size_t)m->D * 4, w.wfull, (size_t)m->Dp * 4, (size_t)m->D * 4, B, cudaMemcpyDeviceToDevice, st));
       break;
     default:

@@ -95,5 +95,35 @@ def main():
                       "utt_iter_per_s": 512 * 100 / t, "success_rate": sum(suc) / len(suc)}))
 
 
+def config5():
+    """config 5: PGD vs iv_plda, SV task, 5 s utterances, B=256 (C=2048 UBM, 400-dim i-vectors, LDA 200)."""
+    from speakerguard_b200.attack.PGD import PGD
+    from speakerguard_b200.model.iv_plda import iv_plda
+    from speakerguard_b200.synthetic import make_iv_params, synthetic_batch
+    B = int(os.environ.get("SGB200_CFG5_B", "256"))
+    iters = int(os.environ.get("SGB200_CFG5_ITERS", "5"))
+    t0 = time.perf_counter()
+    p = make_iv_params(0, C=2048, F=72, D=400, L=200, S=1)
+    t1 = time.perf_counter()
+    model = iv_plda(None, None, None, None, None, threshold=0.0, device="cuda:0", params=p)
+    t2 = time.perf_counter()
+    x, _ = synthetic_batch(B, 80000)
+    x = x.cuda()
+    y = torch.zeros(B, dtype=torch.int64, device="cuda")
+    att = PGD(model, task="SV", epsilon=0.002, step_size=0.0004, max_iter=iters, batch_size=B, verbose=0)
+    model.engine.profile(True)
+    t, _ = timed(lambda: att.attack(x, y), reps=1)
+    prof = model.engine.profile_read()
+    model.engine.profile(False)
+    tot = sum(v[0] for v in prof.values())
+    print(json.dumps({"config": f"5: PGD-{iters} vs iv_plda SV, B={B}, 5 s, C=2048 D=400", "s_per_iteration": t / (iters + 1),
+                      "utt_iter_per_s": B * (iters + 1) / t, "params_s": t1 - t0, "load_s": t2 - t1,
+                      "profile_ms": {k: round(v[0], 2) for k, v in prof.items() if v[1]},
+                      "profile_total_ms": round(tot, 2)}))
+
+
 if __name__ == "__main__":
+    if os.environ.get("SGB200_ONLY_CFG5"):
+        config5()
+        sys.exit(0)
     main()
