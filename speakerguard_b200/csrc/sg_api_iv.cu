@@ -19,6 +19,8 @@
 #include "sg_head.cuh"
 #include "sg_iv.cuh"
 
+#define IV_SPLITS 32
+
 struct SgIv {
   int C, F, D, L, Lp, Fa, Dp, P, Pp, Kq;
   float offset;
@@ -50,8 +52,8 @@ static void parallel_for(int n, Fn fn) {
 extern "C" int sg_load_iv(sg_handle* h, const sg_iv_weights* w) {
   if (!h || !w) { sg_set_error("sg_load_iv: null argument"); return SG_EINVAL; }
   if (h->iv || h->backend_loaded) { sg_set_error("sg_load_iv: a model is already loaded on this handle"); return SG_ESTATE; }
-  if (w->C < 16 || w->C % 16 != 0 || w->F < 1 || w->F > 128 || w->D < 1 || w->D > 1024 || w->L < 1 || w->L > 512 || w->S < 1) {
-    sg_set_error("sg_load_iv: need C %% 16 == 0, 1 <= F <= 128, 1 <= D <= 1024, 1 <= L <= 512, S >= 1 (C=%d F=%d D=%d L=%d S=%d)",
+  if (w->C < 16 || w->C % 16 != 0 || w->F < 1 || w->F > 128 || w->D < 1 || w->D > 800 || w->L < 1 || w->L > 512 || w->S < 1) {
+    sg_set_error("sg_load_iv: need C %% 16 == 0, 1 <= F <= 128, 1 <= D <= 800, 1 <= L <= 512, S >= 1 (C=%d F=%d D=%d L=%d S=%d)",
                  w->C, w->F, w->D, w->L, w->S);
     return SG_EINVAL;
   }
@@ -65,7 +67,7 @@ extern "C" int sg_load_iv(sg_handle* h, const sg_iv_weights* w) {
   h->iv = m;
   const int C = w->C, F = w->F, D = w->D, L = w->L;
   m->C = C; m->F = F; m->D = D; m->L = L; m->Lp = (L + 31) / 32 * 32;
-  m->Fa = up16(F + 1); m->Dp = up16(D); m->P = D * (D + 1) / 2; m->Pp = up16(m->P);
+  m->Fa = up16(F + 1); m->Dp = up16(D); m->P = D * (D + 1) / 2; m->Pp = (m->P + 511) / 512 * 512;   // 512: split-K friendly
   m->Kq = up16(F + F * (F + 1) / 2);
   m->offset = w->ive_offset;
   const int Kq = m->Kq, Pp = m->Pp, Dp = m->Dp, Lp = m->Lp;
@@ -146,7 +148,7 @@ extern "C" int sg_load_iv(sg_handle* h, const sg_iv_weights* w) {
 
 // ---------------------------------------------------------------------------------------------
 struct IvWs {
-  float *Xa, *XaT, *Q, *post, *dpost, *FsT, *dFsT, *dFs, *Lpk, *dLpk, *lin, *dlin, *wfull, *iv, *div, *e2, *de2, *tsave, *scal, *dXa;
+  float *Xa, *XaT, *Q, *post, *dpost, *FsT, *dFsT, *dFs, *Lpk, *dLpk, *lin, *dlin, *wfull, *iv, *div, *e2, *de2, *tsave, *scal, *dXa, *part;
   double* fac;
   size_t bytes;
 };
@@ -166,6 +168,7 @@ static IvWs iv_ws_layout(void* base, const SgIv* m, int B, int T) {
   w.e2 = take((size_t)B * m->Lp); w.de2 = take((size_t)B * m->Lp); w.tsave = take((size_t)B * m->Lp);
   w.scal = take((size_t)B * 4);
   w.fac = (double*)take((size_t)B * m->D * m->D * 2);
+  w.part = take((size_t)IV_SPLITS * B * (m->C > m->Dp ? m->C : m->Dp));
   w.bytes = off;
   return w;
 }
@@ -196,6 +199,21 @@ static int iv_gemm(sg_handle* h, const SgConvArgs& a, cudaStream_t st) {
   PROF(h, SG_PROF_IV_GEMM, st, sg_conv_simt(a, st));
   return SG_OK;
 }
+// skinny contraction (rows = B utterances, long K): split K across IV_SPLITS CTAs per tile, then add the partial sums
+static int iv_gemm_splitk(sg_handle* h, SgConvArgs a, float* part, cudaStream_t st) {
+  int splits = IV_SPLITS;
+  while (splits > 1 && (a.cin % (16 * splits) != 0)) splits >>= 1;
+  if (splits == 1) return iv_gemm(h, a, st);
+  float* out = a.out;
+  const int ldo = a.ldo;
+  const int kc = a.cin / splits;
+  a.cin = kc; a.nbatch = splits; a.strideA = kc; a.strideW = (long long)kc * a.N; a.strideO = (long long)a.rows * a.N;
+  a.out = part; a.ldo = a.N; a.bias = nullptr; a.epilogue = SG_EPI_NONE;
+  SG_TRY(iv_gemm(h, a, st));
+  h->launches += 1;
+  PROF(h, SG_PROF_IV_GEMM, st, sg_splitk_reduce_launch(part, splits, a.rows, a.N, out, ldo, st));
+  return SG_OK;
+}
 #define IV_K(call) do { h->launches += 1; PROF(h, SG_PROF_IV, st, (call)); } while (0)
 
 static int iv_embed_fwd(sg_handle* h, const float* feat, int ld, int B, int T, const IvWs& w, float* emb, cudaStream_t st) {
@@ -212,7 +230,7 @@ static int iv_embed_fwd(sg_handle* h, const float* feat, int ld, int B, int T, c
     SG_TRY(iv_gemm(h, a, st));
   }
   SG_TRY(iv_gemm(h, gemm_args(w.FsT + (size_t)F * C, Fa * C, m->U, m->UT, nullptr, w.Lpk, m->Pp, B, m->Pp, C), st));
-  SG_TRY(iv_gemm(h, gemm_args(w.FsT, Fa * C, m->Wlin, m->WlinT, nullptr, w.lin, m->Dp, B, m->Dp, F * C), st));
+  SG_TRY(iv_gemm_splitk(h, gemm_args(w.FsT, Fa * C, m->Wlin, m->WlinT, nullptr, w.lin, m->Dp, B, m->Dp, F * C), w.part, st));
   IV_K(sg_chol_solve_launch(w.Lpk, m->Pp, w.lin, m->Dp, m->offset, m->emb_mean, w.fac, w.wfull, w.iv, B, m->D, st));
   SG_TRY(iv_gemm(h, gemm_args(w.iv, m->Dp, m->Wlda, m->Wlda_b, m->blda, w.e2, m->Lp, B, m->Lp, m->Dp), st));
   h->launches += 1;
@@ -228,7 +246,7 @@ static int iv_embed_bwd(sg_handle* h, const float* demb, int B, int T, const IvW
   SG_TRY(iv_gemm(h, gemm_args(w.de2, m->Lp, m->Wlda_b, m->Wlda, nullptr, w.div, m->Dp, B, m->Dp, m->Lp), st));
   IV_K(sg_chol_solve_bwd_launch(w.fac, w.wfull, w.div, m->Dp, w.dlin, w.dLpk, m->Pp, B, m->D, st));
   SG_CUDA_CHECK(cudaMemsetAsync(w.dFsT, 0, (size_t)B * Fa * C * sizeof(float), st));
-  SG_TRY(iv_gemm(h, gemm_args(w.dLpk, m->Pp, m->UT, m->U, nullptr, w.dFsT + (size_t)F * C, Fa * C, B, C, m->Pp), st));
+  SG_TRY(iv_gemm_splitk(h, gemm_args(w.dLpk, m->Pp, m->UT, m->U, nullptr, w.dFsT + (size_t)F * C, Fa * C, B, C, m->Pp), w.part, st));
   SG_TRY(iv_gemm(h, gemm_args(w.dlin, m->Dp, m->WlinT, m->Wlin, nullptr, w.dFsT, Fa * C, B, F * C, m->Dp), st));
   {  // d post_b = Xa_b dFsT_b : [Tp, Fa] x [Fa, C]
     SgConvArgs a = gemm_args(w.Xa, Fa, w.dFsT, nullptr, nullptr, w.dpost, C, Tp, C, Fa);

@@ -177,21 +177,129 @@ __global__ void softmax_rows_bwd_kernel(const float* __restrict__ post, const fl
 // the adjoints of the system: lambda = L^-1 dw, dLp(i<=j) = -(lambda_i w_j + lambda_j w_i) / (1 + [i==j]).
 // One CTA per utterance.
 // ---------------------------------------------------------------------------------------------
-__device__ void chol_solve_with_factor(const double* __restrict__ A, int D, double* v /* smem [D], in/out */) {
-  // forward substitution L y = v, then back substitution L' w = y  (L lower-triangular, row-major A[i*D + j])
-  for (int k = 0; k < D; ++k) {
-    __syncthreads();
-    if (threadIdx.x == 0) v[k] /= A[(size_t)k * D + k];
-    __syncthreads();
-    const double yk = v[k];
-    for (int i = k + 1 + threadIdx.x; i < D; i += blockDim.x) v[i] -= A[(size_t)i * D + k] * yk;
+#define CH_NB 32                 // panel width of the blocked factorisation
+#define CH_LD (CH_NB + 1)        // padded panel row stride (doubles)
+
+// rows k0..D-1 of the nb panel columns -> shared memory (upper part of the diagonal block zeroed)
+__device__ __forceinline__ void chol_load_panel(const double* __restrict__ A, int D, int k0, int nb, double* Pn) {
+  const int rows = D - k0;
+  for (int e = threadIdx.x; e < rows * nb; e += blockDim.x) {
+    const int r = e / nb, c = e - r * nb;
+    Pn[r * CH_LD + c] = (r >= c) ? A[(size_t)(k0 + r) * D + k0 + c] : 0.0;
   }
-  for (int k = D - 1; k >= 0; --k) {
+}
+
+// forward substitution L y = v, then back substitution L' w = y, panel by panel (L lower-triangular, row-major)
+__device__ void chol_solve_with_factor(const double* __restrict__ A, int D, double* v /* smem [D], in/out */, double* Pn,
+                                       double* red /* smem [8 * CH_NB] */) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int k0 = 0; k0 < D; k0 += CH_NB) {
+    const int nb = min(CH_NB, D - k0), rows = D - k0;
     __syncthreads();
-    if (threadIdx.x == 0) v[k] /= A[(size_t)k * D + k];
+    chol_load_panel(A, D, k0, nb, Pn);
     __syncthreads();
-    const double wk = v[k];
-    for (int i = threadIdx.x; i < k; i += blockDim.x) v[i] -= A[(size_t)k * D + i] * wk;
+    if (warp == 0) {
+      double val = lane < nb ? v[k0 + lane] : 0.0;
+      for (int j = 0; j < nb; ++j) {
+        if (lane == j) val /= Pn[j * CH_LD + j];
+        const double yj = __shfl_sync(0xffffffffu, val, j);
+        if (lane > j && lane < nb) val -= Pn[lane * CH_LD + j] * yj;
+      }
+      if (lane < nb) v[k0 + lane] = val;
+    }
+    __syncthreads();
+    for (int i = nb + tid; i < rows; i += blockDim.x) {
+      double sacc = 0.0;
+      for (int c = 0; c < nb; ++c) sacc += Pn[i * CH_LD + c] * v[k0 + c];
+      v[k0 + i] -= sacc;
+    }
+  }
+  for (int k0 = (D - 1) / CH_NB * CH_NB; k0 >= 0; k0 -= CH_NB) {
+    const int nb = min(CH_NB, D - k0), rows = D - k0;
+    __syncthreads();
+    chol_load_panel(A, D, k0, nb, Pn);
+    __syncthreads();
+    {  // s_c = sum_{i >= nb} L[k0+i][k0+c] w[k0+i]
+      double sacc = 0.0;
+      if (lane < nb)
+        for (int i = nb + warp; i < rows; i += (blockDim.x >> 5)) sacc += Pn[i * CH_LD + lane] * v[k0 + i];
+      red[warp * CH_NB + lane] = sacc;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      double val = 0.0;
+      if (lane < nb) {
+        val = v[k0 + lane];
+        for (int g = 0; g < (int)(blockDim.x >> 5); ++g) val -= red[g * CH_NB + lane];
+      }
+      for (int j = nb - 1; j >= 0; --j) {
+        if (lane == j) val /= Pn[j * CH_LD + j];
+        const double wj = __shfl_sync(0xffffffffu, val, j);
+        if (lane < j) val -= Pn[j * CH_LD + lane] * wj;
+      }
+      if (lane < nb) v[k0 + lane] = val;
+    }
+  }
+  __syncthreads();
+}
+
+// blocked right-looking Cholesky, in place in the lower triangle of A (row-major [D, D], global memory):
+// the 32-column panel is factorised in shared memory, the trailing matrix gets one rank-32 update per panel
+__device__ void chol_factor_blocked(double* __restrict__ A, int D, double* Pn) {
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  for (int k0 = 0; k0 < D; k0 += CH_NB) {
+    const int nb = min(CH_NB, D - k0), rows = D - k0;
+    __syncthreads();
+    chol_load_panel(A, D, k0, nb, Pn);
+    __syncthreads();
+    for (int j = 0; j < nb; ++j) {
+      const double d = sqrt(Pn[j * CH_LD + j]);
+      __syncthreads();
+      for (int r = j + tid; r < rows; r += nthr) Pn[r * CH_LD + j] = (r == j) ? d : Pn[r * CH_LD + j] / d;
+      __syncthreads();
+      const int nc = nb - j - 1;
+      for (int e = tid; e < (rows - j - 1) * nc; e += nthr) {
+        const int q = e / nc, r = j + 1 + q, c = j + 1 + (e - q * nc);
+        if (r >= c) Pn[r * CH_LD + c] -= Pn[r * CH_LD + j] * Pn[c * CH_LD + j];
+      }
+      __syncthreads();
+    }
+    for (int e = tid; e < rows * nb; e += nthr) {
+      const int r = e / nb, c = e - r * nb;
+      if (r >= c) A[(size_t)(k0 + r) * D + k0 + c] = Pn[r * CH_LD + c];
+    }
+    // trailing update in 4x4 register tiles over the lower triangle of the (n2 x n2) block
+    const int n2 = rows - nb, nt = (n2 + 3) / 4;
+    for (int t = tid; t < nt * (nt + 1) / 2; t += nthr) {
+      int ti = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
+      while (ti * (ti + 1) / 2 > t) --ti;
+      while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+      const int tj = t - ti * (ti + 1) / 2;
+      double acc[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int w = 0; w < 4; ++w) acc[u][w] = 0.0;
+      int ri[4], rj[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { ri[u] = min(nb + ti * 4 + u, rows - 1) * CH_LD; rj[u] = min(nb + tj * 4 + u, rows - 1) * CH_LD; }
+      for (int c = 0; c < nb; ++c) {
+        double a[4], bq[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { a[u] = Pn[ri[u] + c]; bq[u] = Pn[rj[u] + c]; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int w = 0; w < 4; ++w) acc[u][w] = fma(a[u], bq[w], acc[u][w]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const int gi = nb + ti * 4 + u, gj = nb + tj * 4 + w;
+          if (gi < rows && gj <= gi) A[(size_t)(k0 + gi) * D + k0 + gj] -= acc[u][w];
+        }
+    }
   }
   __syncthreads();
 }
@@ -200,7 +308,9 @@ __global__ void __launch_bounds__(256)
 chol_factor_solve_kernel(const float* __restrict__ Lp, int ldp, const float* __restrict__ rhs, int ldr, float offset,
                          const float* __restrict__ emb_mean, double* __restrict__ fac, float* __restrict__ wfull,
                          float* __restrict__ iv, int D) {
-  extern __shared__ double vs[];                                  // [2 D]: right-hand side, staged column
+  extern __shared__ double vs[];                                  // [D] right-hand side, [8*32] reduction, [D*33] panel
+  double* red = vs + D;
+  double* Pn = red + 8 * CH_NB;
   const int b = blockIdx.x;
   double* A = fac + (size_t)b * D * D;
   const float* lp = Lp + (size_t)b * ldp;
@@ -208,31 +318,10 @@ chol_factor_solve_kernel(const float* __restrict__ Lp, int ldp, const float* __r
   for (int i = 0; i < D; ++i)
     for (int j = i + threadIdx.x; j < D; j += blockDim.x)
       A[(size_t)j * D + i] = (double)lp[(size_t)i * D - (size_t)i * (i - 1) / 2 + (j - i)] + (i == j ? 1.0 : 0.0);
-  __syncthreads();
-  // right-looking Cholesky, in place in the lower triangle; column k is staged in shared memory for the rank-1 update
-  double* colk = vs + D;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-  for (int k = 0; k < D; ++k) {
-    __syncthreads();
-    const double dkk = sqrt(A[(size_t)k * D + k]);
-    __syncthreads();
-    if (threadIdx.x == 0) A[(size_t)k * D + k] = dkk;
-    for (int i = k + 1 + threadIdx.x; i < D; i += blockDim.x) {
-      const double v = A[(size_t)i * D + k] / dkk;
-      colk[i] = v;
-      A[(size_t)i * D + k] = v;
-    }
-    __syncthreads();
-    for (int i = k + 1 + warp; i < D; i += nwarp) {
-      const double ci = colk[i];
-      double* ar = A + (size_t)i * D;
-      for (int j = k + 1 + lane; j <= i; j += 32) ar[j] -= ci * colk[j];
-    }
-  }
-  __syncthreads();
+  chol_factor_blocked(A, D, Pn);
   // linear[0] += prior_offset; ivector[0] -= prior_offset (ivector_extract.py:108-113); then the global mean is removed
   for (int i = threadIdx.x; i < D; i += blockDim.x) vs[i] = (double)rhs[(size_t)b * ldr + i] + (i == 0 ? (double)offset : 0.0);
-  chol_solve_with_factor(A, D, vs);
+  chol_solve_with_factor(A, D, vs, Pn, red);
   for (int i = threadIdx.x; i < ldr; i += blockDim.x) {
     wfull[(size_t)b * ldr + i] = i < D ? (float)vs[i] : 0.f;
     iv[(size_t)b * ldr + i] = i < D ? (float)(vs[i] - (i == 0 ? (double)offset : 0.0)) - emb_mean[i] : 0.f;
@@ -243,11 +332,13 @@ __global__ void __launch_bounds__(256)
 chol_solve_bwd_kernel(const double* __restrict__ fac, const float* __restrict__ w, const float* __restrict__ dw, int ldr,
                       float* __restrict__ drhs, float* __restrict__ dLp, int ldp, int D) {
   extern __shared__ double vs[];
+  double* red = vs + D;
+  double* Pn = red + 8 * CH_NB;
   const int b = blockIdx.x;
   const size_t P = (size_t)D * (D + 1) / 2;
   const double* A = fac + (size_t)b * D * D;
   for (int i = threadIdx.x; i < D; i += blockDim.x) vs[i] = (double)dw[(size_t)b * ldr + i];
-  chol_solve_with_factor(A, D, vs);
+  chol_solve_with_factor(A, D, vs, Pn, red);
   for (int i = threadIdx.x; i < ldr; i += blockDim.x) drhs[(size_t)b * ldr + i] = i < D ? (float)vs[i] : 0.f;
   const float* wb = w + (size_t)b * ldr;
   float* o = dLp + (size_t)b * ldp;
@@ -261,6 +352,16 @@ chol_solve_bwd_kernel(const double* __restrict__ fac, const float* __restrict__ 
     }
   }
   for (size_t p = P + threadIdx.x; p < (size_t)ldp; p += blockDim.x) o[p] = 0.f;
+}
+
+// out[r, n] = sum_s part[s][r][n]   (split-K partial sums of the skinny contractions)
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, int rows, int N, float* __restrict__ out, int ldo) {
+  const size_t n = (size_t)rows * N;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int sp = 0; sp < splits; ++sp) acc += part[(size_t)sp * n + i];
+    out[(i / N) * ldo + (i % N)] = acc;
+  }
 }
 
 // row-major [R, C] -> [C, R] per batch item (layout helper: X^T for the statistics GEMM)
@@ -332,15 +433,36 @@ int sg_softmax_rows_launch(const float* a, const float* b, float* out, int rows,
   SG_LAUNCH_CHECK();
   return SG_OK;
 }
+static size_t chol_smem(int D) { return ((size_t)D + 8 * CH_NB + (size_t)D * CH_LD) * sizeof(double); }
+static int chol_init(int D) {
+  static int configured = 0;
+  const int need = (int)chol_smem(D);
+  if (need > 227 * 1024) { sg_set_error("i-vector dimension %d too large for the shared-memory panel (max 800)", D); return SG_EINVAL; }
+  if (need > configured) {
+    SG_CUDA_CHECK(cudaFuncSetAttribute(chol_factor_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
+    SG_CUDA_CHECK(cudaFuncSetAttribute(chol_solve_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
+    configured = need;
+  }
+  return SG_OK;
+}
 int sg_chol_solve_launch(const float* Lp, int ldp, const float* rhs, int ldr, float offset, const float* emb_mean, double* fac,
                          float* wfull, float* iv, int B, int D, cudaStream_t st) {
-  chol_factor_solve_kernel<<<B, 256, 2 * D * sizeof(double), st>>>(Lp, ldp, rhs, ldr, offset, emb_mean, fac, wfull, iv, D);
+  int r = chol_init(D);
+  if (r != SG_OK) return r;
+  chol_factor_solve_kernel<<<B, 256, chol_smem(D), st>>>(Lp, ldp, rhs, ldr, offset, emb_mean, fac, wfull, iv, D);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }
 int sg_chol_solve_bwd_launch(const double* fac, const float* w, const float* dw, int ldr, float* drhs, float* dLp, int ldp,
                              int B, int D, cudaStream_t st) {
-  chol_solve_bwd_kernel<<<B, 256, D * sizeof(double), st>>>(fac, w, dw, ldr, drhs, dLp, ldp, D);
+  int r = chol_init(D);
+  if (r != SG_OK) return r;
+  chol_solve_bwd_kernel<<<B, 256, chol_smem(D), st>>>(fac, w, dw, ldr, drhs, dLp, ldp, D);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+int sg_splitk_reduce_launch(const float* part, int splits, int rows, int N, float* out, int ldo, cudaStream_t st) {
+  splitk_reduce_kernel<<<iv_blocks((size_t)rows * N), 256, 0, st>>>(part, splits, rows, N, out, ldo);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }

@@ -16,3 +16,4 @@ int sg_chol_solve_bwd_launch(const double* fac, const float* w, const float* dw,
                              int B, int D, cudaStream_t st);
 int sg_transpose_batched_launch(const float* in, float* out, int R, int C, int ld_in, int ld_out, size_t stride_in,
                                 size_t stride_out, int nbatch, cudaStream_t st);
+int sg_splitk_reduce_launch(const float* part, int splits, int rows, int N, float* out, int ldo, cudaStream_t st);
