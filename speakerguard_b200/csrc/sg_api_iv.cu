@@ -25,6 +25,7 @@ struct SgIv {
   int C, F, D, L, Lp, Fa, Dp, P, Pp, Kq;
   float offset;
   float *Wq, *WqT, *gconst;        // [Kq, C], [C, Kq], [C]
+  float *Wq3K, *WqT3K;             // 3xTF32 operands (K-major): [C, 3Kq] = [hi|lo|hi](WqT), [Kq, 3C] = [hi|lo|hi](Wq)
   float *U, *UT;                   // [C, Pp], [Pp, C]
   float *Wlin, *WlinT;             // [F*C, Dp], [Dp, F*C]
   float *Wlda, *Wlda_b, *blda;     // [Dp, Lp], [Lp, Dp], [Lp]
@@ -68,7 +69,7 @@ extern "C" int sg_load_iv(sg_handle* h, const sg_iv_weights* w) {
   const int C = w->C, F = w->F, D = w->D, L = w->L;
   m->C = C; m->F = F; m->D = D; m->L = L; m->Lp = (L + 31) / 32 * 32;
   m->Fa = up16(F + 1); m->Dp = up16(D); m->P = D * (D + 1) / 2; m->Pp = (m->P + 511) / 512 * 512;   // 512: split-K friendly
-  m->Kq = up16(F + F * (F + 1) / 2);
+  m->Kq = (F + F * (F + 1) / 2 + 255) / 256 * 256;   // 256: whole N-tiles for the tensor-core dgrad
   m->offset = w->ive_offset;
   const int Kq = m->Kq, Pp = m->Pp, Dp = m->Dp, Lp = m->Lp;
 
@@ -85,6 +86,21 @@ extern "C" int sg_load_iv(sg_handle* h, const sg_iv_weights* w) {
     }
     SG_TRY(sg_dev_upload(h, &m->Wq, Wq));
     SG_TRY(sg_dev_upload(h, &m->WqT, WqT));
+    {  // split operands: x*w ~ x_lo*w_hi + x_hi*w_lo + x_hi*w_hi (small terms first), the hi factors exactly representable in tf32;
+      // activations are laid out [lo|hi|hi] along K, weights [hi|lo|hi]
+      auto hi = [](float v) { uint32_t u; memcpy(&u, &v, 4); u &= 0xffffe000u; float r; memcpy(&r, &u, 4); return r; };
+      std::vector<float> A3((size_t)C * 3 * Kq), B3((size_t)Kq * 3 * C);
+      for (int c = 0; c < C; ++c)
+        for (int k = 0; k < Kq; ++k) {
+          const float v = WqT[(size_t)c * Kq + k], vh = hi(v);
+          float* r = &A3[(size_t)c * 3 * Kq];
+          r[k] = vh; r[Kq + k] = v - vh; r[2 * Kq + k] = vh;
+          float* q = &B3[(size_t)k * 3 * C];
+          q[c] = vh; q[C + c] = v - vh; q[2 * C + c] = vh;
+        }
+      SG_TRY(sg_dev_upload(h, &m->Wq3K, A3));
+      SG_TRY(sg_dev_upload(h, &m->WqT3K, B3));
+    }
     SG_TRY(sg_dev_upload(h, &m->gconst, std::vector<float>(w->gmm_gconsts, w->gmm_gconsts + C)));
   }
   {  // extractor (ivector_extract.py:94-107): G_c = T_c' S_c^-1 [D,F], U_c = G_c T_c [D,D]
@@ -148,7 +164,7 @@ extern "C" int sg_load_iv(sg_handle* h, const sg_iv_weights* w) {
 
 // ---------------------------------------------------------------------------------------------
 struct IvWs {
-  float *Xa, *XaT, *Q, *post, *dpost, *FsT, *dFsT, *dFs, *Lpk, *dLpk, *lin, *dlin, *wfull, *iv, *div, *e2, *de2, *tsave, *scal, *dXa, *part;
+  float *Xa, *XaT, *Q, *post, *dpost, *FsT, *dFsT, *dFs, *Lpk, *dLpk, *lin, *dlin, *wfull, *iv, *div, *e2, *de2, *tsave, *scal, *dXa, *part, *dll3;
   double* fac;
   size_t bytes;
 };
@@ -159,7 +175,8 @@ static IvWs iv_ws_layout(void* base, const SgIv* m, int B, int T) {
   auto take = [&](size_t nfloat) { float* q = (float*)(p + off); off += (nfloat * sizeof(float) + 255) / 256 * 256; return q; };
   const size_t Tp = up16(T), R = (size_t)B * Tp;
   w.Xa = take(R * m->Fa); w.XaT = take(R * m->Fa); w.dXa = take(R * m->Fa);
-  w.Q = take(R * m->Kq);
+  w.Q = take(R * m->Kq * 3);                            // [R, Kq], or [R, 3Kq] split operand in tensor-core mode
+  w.dll3 = take(R * m->C * 3);
   w.post = take(R * m->C); w.dpost = take(R * m->C);
   w.FsT = take((size_t)B * m->Fa * m->C); w.dFsT = take((size_t)B * m->Fa * m->C); w.dFs = take((size_t)B * m->Fa * m->C);
   w.Lpk = take((size_t)B * m->Pp); w.dLpk = take((size_t)B * m->Pp);
@@ -192,8 +209,19 @@ static SgConvArgs gemm_args(const float* A, int lda, const float* W, const float
   a.taps = 1; a.T = 1; a.epilogue = bias ? SG_EPI_BIAS : SG_EPI_NONE;
   return a;
 }
-// fp32 FFMA for every contraction of this path: the UBM log-likelihoods cancel O(100) terms against each other, so the
-// reduced-precision tensor-core modes of the TDNN path are not offered here
+// fp32 FFMA for the contractions of this path.  The UBM log-likelihoods cancel O(100) terms against each other, so plain
+// tf32 / bf16 operands are not offered; with a tensor-core precision set on the handle the two large contractions (frames x
+// components) run as 3xTF32 instead: both operands split into tf32-exact hi + lo parts, three tcgen05 products, fp32 accumulate
+static int iv_gemm_tc3(sg_handle* h, const float* A3, int K3, const float* W3k, const float* bias, float* out, int ldo,
+                       int rows, int N, cudaStream_t st) {
+  SgConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.A = A3; a.lda = K3; a.Wk = W3k; a.bias = bias; a.out = out; a.ldo = ldo; a.rows = rows; a.N = N; a.cin = K3;
+  a.taps = 1; a.T = 1; a.epilogue = bias ? SG_EPI_BIAS : SG_EPI_NONE;
+  h->launches += 1;
+  PROF(h, SG_PROF_IV_GEMM, st, sg_conv_tc(a, SG_PREC_TF32, st));
+  return SG_OK;
+}
 static int iv_gemm(sg_handle* h, const SgConvArgs& a, cudaStream_t st) {
   h->launches += 1;
   PROF(h, SG_PROF_IV_GEMM, st, sg_conv_simt(a, st));
@@ -221,9 +249,15 @@ static int iv_embed_fwd(sg_handle* h, const float* feat, int ld, int B, int T, c
   const int Tp = up16(T), R = B * Tp, C = m->C, F = m->F, Fa = m->Fa;
   IV_K(sg_pad_aug_launch(feat, ld, w.Xa, Fa, B, T, Tp, F, st));
   IV_K(sg_transpose_batched_launch(w.Xa, w.XaT, Tp, Fa, Fa, Tp, (size_t)Tp * Fa, (size_t)Tp * Fa, B, st));
-  IV_K(sg_quad_expand_launch(w.Xa, Fa, w.Q, m->Kq, R, F, st));
-  SG_TRY(iv_gemm(h, gemm_args(w.Q, m->Kq, m->Wq, m->WqT, m->gconst, w.post, C, R, C, m->Kq), st));
-  IV_K(sg_softmax_rows_launch(w.post, nullptr, w.post, R, C, T, Tp, 0, st));
+  const bool tc = h->precision != SG_PREC_FP32;
+  if (tc) {
+    IV_K(sg_quad_expand_launch(w.Xa, Fa, w.Q, 3 * m->Kq, R, F, 1, m->Kq, st));
+    SG_TRY(iv_gemm_tc3(h, w.Q, 3 * m->Kq, m->Wq3K, m->gconst, w.post, C, R, C, st));
+  } else {
+    IV_K(sg_quad_expand_launch(w.Xa, Fa, w.Q, m->Kq, R, F, 0, 0, st));
+    SG_TRY(iv_gemm(h, gemm_args(w.Q, m->Kq, m->Wq, m->WqT, m->gconst, w.post, C, R, C, m->Kq), st));
+  }
+  IV_K(sg_softmax_rows_launch(w.post, nullptr, w.post, R, C, T, Tp, 0, 0, st));
   {  // Baum-Welch statistics (gmm.py:166-171), one GEMM per utterance: [Fa, Tp] x [Tp, C]
     SgConvArgs a = gemm_args(w.XaT, Tp, w.post, nullptr, nullptr, w.FsT, C, Fa, C, Tp);
     a.nbatch = B; a.strideA = (long long)Fa * Tp; a.strideW = (long long)Tp * C; a.strideO = (long long)Fa * C;
@@ -253,8 +287,13 @@ static int iv_embed_bwd(sg_handle* h, const float* demb, int B, int T, const IvW
     a.nbatch = B; a.strideA = (long long)Tp * Fa; a.strideW = (long long)Fa * C; a.strideO = (long long)Tp * C;
     SG_TRY(iv_gemm(h, a, st));
   }
-  IV_K(sg_softmax_rows_launch(w.post, w.dpost, w.dpost, R, C, T, Tp, 1, st));
-  SG_TRY(iv_gemm(h, gemm_args(w.dpost, C, m->WqT, m->Wq, nullptr, w.Q, m->Kq, R, m->Kq, C), st));
+  if (h->precision != SG_PREC_FP32) {
+    IV_K(sg_softmax_rows_launch(w.post, w.dpost, w.dll3, R, C, T, Tp, 1, 1, st));
+    SG_TRY(iv_gemm_tc3(h, w.dll3, 3 * C, m->WqT3K, nullptr, w.Q, m->Kq, R, m->Kq, st));
+  } else {
+    IV_K(sg_softmax_rows_launch(w.post, w.dpost, w.dpost, R, C, T, Tp, 1, 0, st));
+    SG_TRY(iv_gemm(h, gemm_args(w.dpost, C, m->WqT, m->Wq, nullptr, w.Q, m->Kq, R, m->Kq, C), st));
+  }
   // the first-order statistics also depend on x directly: dXa_b = post_b dFs_b, dFs_b = dFsT_b^T  [C, Fa]
   IV_K(sg_transpose_batched_launch(w.dFsT, w.dFs, Fa, C, C, Fa, (size_t)Fa * C, (size_t)Fa * C, B, st));
   {

@@ -74,10 +74,35 @@ __global__ void delta_bwd_kernel(const float* __restrict__ dout, int ldo, float*
 //   q_t = [x (F), x_i x_j for i <= j (F(F+1)/2), 0-pad];  rows are stacked per utterance with stride Tp,
 //   rows t >= T are zero.
 // ---------------------------------------------------------------------------------------------
-__global__ void quad_expand_fwd_kernel(const float* __restrict__ xa, int ldx, float* __restrict__ q, int ldq, int F) {
+// tf32 split of an fp32 value: hi keeps the 10 mantissa bits the tensor core reads, lo = x - hi is exact in fp32
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+// split3 != 0: the row holds three K-segments [lo | hi | hi] of width kseg (3xTF32 operand layout, see sg_api_iv.cu)
+__global__ void quad_expand_fwd_kernel(const float* __restrict__ xa, int ldx, float* __restrict__ q, int ldq, int F,
+                                       int split3, int kseg) {
   extern __shared__ float xs[];                                   // [F]
   const int row = blockIdx.x;
   float* qr = q + (size_t)row * ldq;
+  if (split3) {
+    for (int i = threadIdx.x; i < F; i += blockDim.x) xs[i] = xa[(size_t)row * ldx + i];
+    __syncthreads();
+    const int P = F * (F + 1) / 2;
+    for (int k = threadIdx.x; k < kseg; k += blockDim.x) {
+      float v = 0.f;
+      if (k < F) v = xs[k];
+      else if (k < F + P) {
+        const int p = k - F;
+        int i = (int)((2.f * F + 1.f - sqrtf((2.f * F + 1.f) * (2.f * F + 1.f) - 8.f * p)) * 0.5f);
+        i = min(max(i, 0), F - 1);
+        while (i > 0 && i * F - i * (i - 1) / 2 > p) --i;
+        while (i + 1 < F && (i + 1) * F - (i + 1) * i / 2 <= p) ++i;
+        v = xs[i] * xs[i + (p - (i * F - i * (i - 1) / 2))];
+      }
+      const float hi = tf32_hi(v);
+      qr[k] = v - hi; qr[kseg + k] = hi; qr[2 * kseg + k] = hi;
+    }
+    return;
+  }
   for (int i = threadIdx.x; i < F; i += blockDim.x) xs[i] = xa[(size_t)row * ldx + i];
   __syncthreads();
   const int P = F * (F + 1) / 2;
@@ -158,17 +183,23 @@ __global__ void softmax_rows_fwd_kernel(const float* ll, float* post, int C, int
   for (int c = threadIdx.x; c < C; c += blockDim.x) pr[c] = expf(lr[c] - mx) * inv;
 }
 // dll = post * (dpost - sum_c dpost_c post_c)
-__global__ void softmax_rows_bwd_kernel(const float* __restrict__ post, const float* dpost, float* dll, int C, int T, int Tp) {
+// split3: dll is written as [lo | hi | hi] segments of width C into a row of 3C (operand of the 3xTF32 contraction)
+__global__ void softmax_rows_bwd_kernel(const float* __restrict__ post, const float* dpost, float* dll, int C, int T, int Tp,
+                                        int split3) {
   __shared__ float red[8];
   const int row = blockIdx.x, t = row % Tp;
   const float* pr = post + (size_t)row * C;
   const float* dr = dpost + (size_t)row * C;
-  float* o = dll + (size_t)row * C;
-  if (t >= T) { for (int c = threadIdx.x; c < C; c += blockDim.x) o[c] = 0.f; return; }
+  float* o = dll + (size_t)row * C * (split3 ? 3 : 1);
+  if (t >= T) { for (int c = threadIdx.x; c < C * (split3 ? 3 : 1); c += blockDim.x) o[c] = 0.f; return; }
   float s = 0.f;
   for (int c = threadIdx.x; c < C; c += blockDim.x) s = fmaf(dr[c], pr[c], s);
   s = iv_block_reduce(s, red, false);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) o[c] = pr[c] * (dr[c] - s);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float v = pr[c] * (dr[c] - s);
+    if (split3) { const float hi = tf32_hi(v); o[c] = v - hi; o[C + c] = hi; o[2 * C + c] = hi; }
+    else o[c] = v;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -415,8 +446,8 @@ int sg_pad_aug_launch(const float* feat, int ld, float* xa, int Fa, int B, int T
   SG_LAUNCH_CHECK();
   return SG_OK;
 }
-int sg_quad_expand_launch(const float* xa, int ldx, float* q, int ldq, int rows, int F, cudaStream_t st) {
-  quad_expand_fwd_kernel<<<rows, 128, F * sizeof(float), st>>>(xa, ldx, q, ldq, F);
+int sg_quad_expand_launch(const float* xa, int ldx, float* q, int ldq, int rows, int F, int split3, int kseg, cudaStream_t st) {
+  quad_expand_fwd_kernel<<<rows, 256, F * sizeof(float), st>>>(xa, ldx, q, ldq, F, split3, kseg);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }
@@ -427,9 +458,9 @@ int sg_quad_expand_bwd_launch(const float* dq, int ldq, const float* xa, int ldx
   return SG_OK;
 }
 int sg_softmax_rows_launch(const float* a, const float* b, float* out, int rows, int C, int T, int Tp, int backward,
-                           cudaStream_t st) {
+                           int split3, cudaStream_t st) {
   if (!backward) softmax_rows_fwd_kernel<<<rows, 256, 0, st>>>(a, out, C, T, Tp);
-  else softmax_rows_bwd_kernel<<<rows, 256, 0, st>>>(a, b, out, C, T, Tp);
+  else softmax_rows_bwd_kernel<<<rows, 256, 0, st>>>(a, b, out, C, T, Tp, split3);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }

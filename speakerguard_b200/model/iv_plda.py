@@ -7,6 +7,9 @@ as the reference class.  ``gmm_frame_bs`` is accepted and ignored: the engine ev
 frames of the batch in one contraction.  There is no PyTorch/CPU implementation behind these methods.
 
 Extra keyword arguments (engine options):
+  precision 'fp32' (every contraction in FFMA, the parity mode) | 'tf32x3' (the two frames-x-components contractions, UBM
+           log-likelihoods and their adjoint, on the tcgen05 tensor cores as split-TF32: operands split into tf32-exact hi + lo
+           parts, three products, fp32 accumulation: fp32-level accuracy at tensor-core speed)
   params   dict of dense tensors instead of the Kaldi text files ('gmm.gconsts', 'gmm.means_invcovars',
            'gmm.invcovars', 'ive.T', 'ive.sigma_inv', 'ive.offset', 'plda.mean/.transform/.psi',
            'emb_mean', 'lda', optionally 'enroll'); the five file arguments may then be None
@@ -35,12 +38,14 @@ class iv_plda(nn.Module):
 
     def __init__(self, fgmm_file, extractor_file, plda_file, mean_file, transform_mat_file, model_file=None, threshold=None,
                  device="cuda", gmm_frame_bs=200, params: Optional[Dict[str, torch.Tensor]] = None,
-                 dither: Union[str, Callable] = "philox", seed: int = 0):
+                 dither: Union[str, Callable] = "philox", seed: int = 0, precision: str = "fp32"):
         super().__init__()
         dev = torch.device(device)
         if dev.type != "cuda":
             raise _lib.SgError("speakerguard_b200.iv_plda needs a CUDA device (no CPU fallback); got '%s'" % device)
-        self.engine = Engine(dev, precision="fp32")
+        if precision not in ("fp32", "tf32x3"):
+            raise ValueError(f"iv_plda precision must be 'fp32' or 'tf32x3', got {precision!r}")
+        self.engine = Engine(dev, precision="fp32" if precision == "fp32" else "tf32")
         self.device = self.engine.device
         self.fgmm_file, self.extractor_file, self.plda_file = fgmm_file, extractor_file, plda_file
         self.gmm_frame_bs = gmm_frame_bs

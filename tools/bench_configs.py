@@ -105,7 +105,8 @@ def config5():
     t0 = time.perf_counter()
     p = make_iv_params(0, C=2048, F=72, D=400, L=200, S=1)
     t1 = time.perf_counter()
-    model = iv_plda(None, None, None, None, None, threshold=0.0, device="cuda:0", params=p)
+    model = iv_plda(None, None, None, None, None, threshold=0.0, device="cuda:0", params=p,
+                    precision=os.environ.get("SGB200_IV_PRECISION", "tf32x3"))
     t2 = time.perf_counter()
     x, _ = synthetic_batch(B, 80000)
     x = x.cuda()
@@ -116,7 +117,8 @@ def config5():
     prof = model.engine.profile_read()
     model.engine.profile(False)
     tot = sum(v[0] for v in prof.values())
-    print(json.dumps({"config": f"5: PGD-{iters} vs iv_plda SV, B={B}, 5 s, C=2048 D=400", "s_per_iteration": t / (iters + 1),
+    print(json.dumps({"config": f"5: PGD-{iters} vs iv_plda SV, B={B}, 5 s, C=2048 D=400",
+                      "precision": os.environ.get("SGB200_IV_PRECISION", "tf32x3"), "s_per_iteration": t / (iters + 1),
                       "utt_iter_per_s": B * (iters + 1) / t, "params_s": t1 - t0, "load_s": t2 - t1,
                       "profile_ms": {k: round(v[0], 2) for k, v in prof.items() if v[1]},
                       "profile_total_ms": round(tot, 2)}))
