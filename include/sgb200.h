@@ -276,6 +276,24 @@ int sg_add_delta_bwd(sg_handle* h, const float* dout, int ld_in, float* din, int
 int sg_cmvn_cols(sg_handle* h, const float* in, int ld_in, float* out, int ld_out, int ncol, int B,
                  int T, int backward, sg_stream stream);
 
+/* ---- caller I/O -------------------------------------------------------------
+ * sg_pcm16_quantize: save_audio's conversion (attackMain.py:154-160) for a whole batch on the device:
+ *   per utterance, if 0.9*max <= 1 and 0.9*min >= -1 multiply by 2^15; then numpy's astype(int16)
+ *   (truncate toward zero through int32, keep the low 16 bits).  adv [B,N] float -> pcm [B,N] int16 (device);
+ *   scaled [B] (optional, device) receives 1 where the 2^15 scale was applied.
+ * sg_wav_write_batch: scipy.io.wavfile.write (attackMain.py:166) for B mono PCM16 files from one host
+ *   buffer pcm [B,N], by `nthreads` host threads (0 = all cores); parent directories are created
+ *   (attackMain.py:161-164).  Files are byte-identical to scipy's.
+ * sg_wav_read_batch: Dataset.__getitem__ (dataset/Dataset.py:72-84) for B files into one host buffer
+ *   out [B,wav_length]: first channel, crop at starts[i] (or centred when starts is null / negative) or
+ *   zero-pad at the end; normalize != 0 -> [-1,1) scale, else int16 range; lens [B] (optional) = frames per file.
+ * The two host functions do no device work and need no handle. */
+int sg_pcm16_quantize(sg_handle* h, const float* adv, int B, int N, int16_t* pcm, int32_t* scaled,
+                      sg_stream stream);
+int sg_wav_write_batch(const char* const* paths, const int16_t* pcm, int B, int N, int fs, int nthreads);
+int sg_wav_read_batch(const char* const* paths, int B, int wav_length, const int64_t* starts,
+                      int normalize, float* out, int32_t* lens, int nthreads);
+
 /* ---- test hook: one conv-as-GEMM launch on either arithmetic path -----------------------------
  * out[p,n] = epi(sum_{tap,c} A[p + tap*tap_step, c] * W[tap*cin + c, n]); W is [taps*cin, N]
  * (FFMA path), Wk its K-major copy [N, taps*cin] (tcgen05 path); epilogue 0 bias, 1 bias+ReLU,

@@ -112,6 +112,9 @@ PROTOTYPES = {
     "sg_add_delta_fwd": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     "sg_add_delta_bwd": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     "sg_cmvn_cols": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
+    "sg_pcm16_quantize": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "sg_wav_write_batch": (C.c_int, [C.POINTER(C.c_char_p), _vp, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "sg_wav_read_batch": (C.c_int, [C.POINTER(C.c_char_p), C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, C.c_int]),
     "sg_debug_conv": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.c_int, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     "sg_profile_enable": (C.c_int, [_vp, C.c_int]),
