@@ -527,6 +527,65 @@ def audionet_forward(x: torch.Tensor, p, return_all: bool = False):
 
 
 # ----------------------------------------------------------------------------------------------
+# AudioNet in training mode (adver_train.py:183-223, natural_train.py:127-160): BatchNorm with batch
+# statistics, running statistics updated with momentum 0.1, all parameter gradients, Adam
+# ----------------------------------------------------------------------------------------------
+AN_BN_NAMES = ["conv1"] + [n for n, *_ in AN_CONVS]
+
+
+def audionet_train_forward(x: torch.Tensor, p, momentum: float = 0.1, eps: float = 1e-5, from_feat: bool = False):
+    """x [B,N] waveform (or log-mel [B,T,32] when from_feat) -> (logits, new running stats dict).
+    p holds tensors (leaf tensors with requires_grad for the parameters to differentiate)."""
+    if from_feat:
+        feat = x.transpose(1, 2)
+    else:
+        feat = audionet_logmel(x[:, 0] if x.dim() == 3 else x)
+    new_stats = {}
+
+    def bn(h, name, red):
+        mean = h.mean(red)
+        var_b = h.var(red, unbiased=False)
+        n = h.numel() / mean.numel()
+        new_stats[f"{name}.bn_mean"] = (1 - momentum) * p[f"{name}.bn_mean"] + momentum * mean.detach()
+        new_stats[f"{name}.bn_var"] = (1 - momentum) * p[f"{name}.bn_var"] + momentum * var_b.detach() * n / (n - 1)
+        shape = [1, -1] + [1] * (h.dim() - 2)
+        return (h - mean.view(shape)) / torch.sqrt(var_b.view(shape) + eps) * p[f"{name}.bn_gamma"].view(shape) \
+            + p[f"{name}.bn_beta"].view(shape)
+
+    h = F.conv2d(feat.unsqueeze(1), p["conv1.weight"], p["conv1.bias"], padding=2)
+    h = bn(h, "conv1", (0, 2, 3)).squeeze(1)
+    for name, _, _, _, pad, pool in AN_CONVS:
+        h = F.conv1d(h, p[f"{name}.weight"], p[f"{name}.bias"], padding=pad)
+        h = F.relu(bn(h, name, (0, 2)))
+        if pool:
+            h = F.max_pool1d(h, 2, stride=2)
+    emb = h.max(2)[0]
+    return emb @ p["fc.weight"].T + p["fc.bias"], new_stats
+
+
+AN_PARAM_KEYS = [f"{n}.{k}" for n in AN_BN_NAMES for k in ("weight", "bias", "bn_gamma", "bn_beta")] + ["fc.weight", "fc.bias"]
+
+
+def audionet_train_step(x: torch.Tensor, y: torch.Tensor, p, lr: float = 1e-3, from_feat: bool = False):
+    """One optimisation step as in adver_train.py:216-221 (CrossEntropyLoss mean, torch.optim.Adam defaults, first step).
+    Returns dict: logits, loss, grads (per parameter), input grad, new running stats, updated parameters."""
+    q = {k: v.detach().clone() for k, v in p.items()}
+    for k in AN_PARAM_KEYS:
+        q[k].requires_grad_(True)
+    xr = x.detach().clone().requires_grad_(True)
+    logits, stats = audionet_train_forward(xr, q, from_feat=from_feat)
+    loss = F.cross_entropy(logits, y)
+    params = [q[k] for k in AN_PARAM_KEYS]
+    opt = torch.optim.Adam(params, lr=lr)
+    opt.zero_grad()
+    loss.backward()
+    grads = {k: q[k].grad.detach().clone() for k in AN_PARAM_KEYS}
+    opt.step()
+    return {"logits": logits.detach(), "loss": loss.detach(), "grads": grads, "xgrad": xr.grad.detach(), "stats": stats,
+            "params": {k: q[k].detach().clone() for k in AN_PARAM_KEYS}}
+
+
+# ----------------------------------------------------------------------------------------------
 # CW2 (attack/CW2.py:41-132) against a generic score function
 # ----------------------------------------------------------------------------------------------
 def cw2_attack(x: torch.Tensor, y: torch.Tensor, score_fn, targeted=False, confidence=0.0,

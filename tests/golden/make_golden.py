@@ -254,6 +254,58 @@ def audionet_case(out):
         torch.stft = _orig_stft
 
 
+def audionet_train_case(out):
+    """One adversarial-training style optimisation step of the reference AudioNet in train mode (adver_train.py:183-221)."""
+    torch.stft = _stft
+    try:
+        from model.audionet_csine import audionet_csine
+        p = O.make_audionet_params(seed=0, num_class=251)
+        torch.manual_seed(0)
+        model = audionet_csine(num_class=251)
+        mods = {"conv1": model.conv1[1], **{n: getattr(model, n)[1] for n, *_ in O.AN_CONVS}}
+        for n, bn in mods.items():
+            bn.running_mean.copy_(p[f"{n}.bn_mean"])
+            bn.running_var.copy_(p[f"{n}.bn_var"])
+            bn.weight.data.copy_(p[f"{n}.bn_gamma"])
+            bn.bias.data.copy_(p[f"{n}.bn_beta"])
+        model.train()
+        B, N = 6, 16000
+        x, _ = make_inputs(9091, B, N)
+        torch.manual_seed(6)
+        y = torch.randint(0, 251, (B,))
+        opt = torch.optim.Adam(model.parameters())
+        xr = x.clone().requires_grad_(True)
+        outputs = model(xr)
+        loss = torch.nn.CrossEntropyLoss()(outputs, y)
+        opt.zero_grad()
+        loss.backward()
+        ref_grads = {}
+        name_of = {"conv1": model.conv1, **{n: getattr(model, n) for n, *_ in O.AN_CONVS}}
+        for n, seq in name_of.items():
+            ref_grads[f"{n}.weight"], ref_grads[f"{n}.bias"] = seq[0].weight.grad.clone(), seq[0].bias.grad.clone()
+            ref_grads[f"{n}.bn_gamma"], ref_grads[f"{n}.bn_beta"] = seq[1].weight.grad.clone(), seq[1].bias.grad.clone()
+        ref_grads["fc.weight"], ref_grads["fc.bias"] = model.fc.weight.grad.clone(), model.fc.bias.grad.clone()
+        opt.step()
+        out.update({"antrain.B": B, "antrain.N": N, "antrain.x_cks": cks(x), "antrain.y": y.numpy(),
+                    "antrain.logits": outputs.detach().numpy(), "antrain.loss": loss.detach().numpy(),
+                    "antrain.xgrad": xr.grad[:, 0].numpy()})
+        for k, v in ref_grads.items():
+            out[f"antrain.grad.{k}"] = v.numpy()
+        for n, seq in name_of.items():
+            out[f"antrain.stat.{n}.bn_mean"] = seq[1].running_mean.numpy().copy()
+            out[f"antrain.stat.{n}.bn_var"] = seq[1].running_var.numpy().copy()
+            out[f"antrain.new.{n}.weight"] = seq[0].weight.detach().numpy().copy()
+            out[f"antrain.new.{n}.bn_gamma"] = seq[1].weight.detach().numpy().copy()
+        out["antrain.new.fc.weight"] = model.fc.weight.detach().numpy().copy()
+        o = O.audionet_train_step(x[:, 0], y, p)
+        worst = max(float((o["grads"][k] - ref_grads[k]).abs().max() / ref_grads[k].abs().max().clamp_min(1e-12))
+                    for k in ref_grads if "bias" not in k or k == "fc.bias")
+        print(f"[antrain] oracle-vs-ref logits {float((o['logits'] - outputs).abs().max()):.3e} loss {float((o['loss'] - loss).abs()):.3e} "
+              f"worst rel param-grad {worst:.3e} xgrad rel {float((o['xgrad'] - xr.grad[:, 0]).abs().max() / xr.grad.abs().max()):.3e}")
+    finally:
+        torch.stft = _orig_stft
+
+
 def feco_case(out):
     """Conditional FeCo golden: the reference's own mean-by-cluster code driven with fixed ids."""
     km = types.ModuleType("kmeans_pytorch")
@@ -349,6 +401,11 @@ def main():
         iv_case(out)
         np.savez_compressed(os.path.join(HERE, "iv_golden.npz"), **out)
         print("iv_golden.npz", os.path.getsize(os.path.join(HERE, "iv_golden.npz")) // 1024, "KiB")
+        return
+    if "--only-antrain" in sys.argv:
+        audionet_train_case(out)
+        np.savez_compressed(os.path.join(HERE, "antrain_golden.npz"), **out)
+        print("antrain_golden.npz", os.path.getsize(os.path.join(HERE, "antrain_golden.npz")) // 1024, "KiB")
         return
     if "--only-audionet" in sys.argv:
         audionet_case(out)

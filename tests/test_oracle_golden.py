@@ -204,3 +204,36 @@ def test_iv_delta_filters_and_solver_adjoint():
     C, Fd = p["gmm.gconsts"].shape[0], p["gmm.means_invcovars"].shape[1]
     iv = O.ivector(torch.zeros(C), torch.zeros(C, Fd), p)
     np.testing.assert_allclose(iv.numpy(), 0.0, atol=1e-6)
+
+
+# ---- AudioNet training step ----------------------------------------------------
+def test_audionet_train_step_against_reference():
+    g = np.load(os.path.join(G, "antrain_golden.npz"))
+    p = O.make_audionet_params(seed=0, num_class=251)
+    B, N = int(g["antrain.B"]), int(g["antrain.N"])
+    torch.manual_seed(9091)
+    x = (torch.rand(B, 1, N) * 2 - 1) * 0.5
+    assert abs(float(x.double().abs().sum()) - float(g["antrain.x_cks"])) < 1e-9
+    y = torch.from_numpy(g["antrain.y"])
+    o = O.audionet_train_step(x[:, 0], y, p)
+    np.testing.assert_allclose(o["logits"].numpy(), g["antrain.logits"], atol=1e-4, rtol=0)
+    np.testing.assert_allclose(float(o["loss"]), float(g["antrain.loss"]), atol=1e-5)
+    ref = g["antrain.xgrad"]
+    assert np.abs(o["xgrad"].numpy() - ref).max() < 1e-4 * np.abs(ref).max()
+    for k in O.AN_PARAM_KEYS:
+        r = g[f"antrain.grad.{k}"]
+        got = o["grads"][k].numpy()
+        if k.endswith(".bias") and k != "fc.bias":
+            # a conv bias in front of a train-mode BatchNorm has zero gradient; both sides hold round-off only
+            assert np.abs(got).max() < 1e-5 and np.abs(r).max() < 1e-5
+            continue
+        assert np.abs(got - r).max() < 2e-3 * np.abs(r).max(), k       # fp32 reductions over B*T in different orders
+    for n in O.AN_BN_NAMES:
+        np.testing.assert_allclose(o["stats"][f"{n}.bn_mean"].numpy(), g[f"antrain.stat.{n}.bn_mean"], atol=1e-5, rtol=1e-5)
+        np.testing.assert_allclose(o["stats"][f"{n}.bn_var"].numpy(), g[f"antrain.stat.{n}.bn_var"], atol=1e-5, rtol=1e-4)
+        # first Adam step moves every weight by lr * sign(grad) (up to eps): compare where the gradient is not round-off
+        for key in ("weight", "bn_gamma"):
+            r = g[f"antrain.new.{n}.{key}"]
+            gr = np.abs(g[f"antrain.grad.{n}.{key}"])
+            sel = gr > 1e-6
+            assert np.abs(o["params"][f"{n}.{key}"].numpy() - r)[sel].max() < 1e-5     # 1 % of one Adam step (lr 1e-3)
