@@ -276,6 +276,39 @@ int sg_add_delta_bwd(sg_handle* h, const float* dout, int ld_in, float* din, int
 int sg_cmvn_cols(sg_handle* h, const float* in, int ld_in, float* out, int ld_out, int ncol, int B,
                  int T, int backward, sg_stream stream);
 
+/* ---- AudioNet in training mode -----------------------------------------------
+ * What `outputs = model(x_batch); loss.backward(); optimizer.step()` runs for an audionet_csine in
+ * train() mode (adver_train.py:183-221, natural_train.py:127-160; model/audionet_csine.py:58-121):
+ * BatchNorm with batch statistics and the momentum update of the running ones, the input gradient through
+ * those statistics (the attack inside the training loop runs on the train-mode model) and the gradient of
+ * every parameter.  sg_load_audionet must have been called (front-end tables, class count).
+ * sg_audionet_train_tensors: DEVICE pointers in PyTorch's own layouts - conv1_w [1,1,5,5], conv1_b [1],
+ *   conv_w[l] [C_out,C_in,3], conv_b[l] [C_out] (conv2..conv8), bn_gamma/bn_beta/bn_mean/bn_var[0..7]
+ *   ([1] for the BatchNorm2d(1) of the pre-filter, then [C_out]), fc_w [C,32], fc_b [C].  As parameters:
+ *   the live values (bn_mean / bn_var are the running statistics, updated in place when momentum > 0;
+ *   they may be null when momentum == 0).  As gradients: where to write each gradient (bn_mean / bn_var unused).
+ * sg_audionet_train_fwd: feat [B,T,32] log-mel (sg_audionet_logmel_fwd) -> logits [B,Cp]; eps <= 0 -> 1e-5.
+ * sg_audionet_train_bwd: dlogits [B,Cp] -> dfeat [B,T,32] (may be null) and parameter gradients g (may be
+ *   null: input gradient only, the attack's case), using what the forward left in ws
+ *   (sg_audionet_train_ws_bytes(h,B,N) bytes).
+ * sg_adam_step: torch.optim.Adam's update (no amsgrad; weight_decay added to the gradient) on one flat
+ *   tensor; step counts from 1. */
+typedef struct {
+  float* conv1_w; float* conv1_b;
+  float* conv_w[7]; float* conv_b[7];
+  float* bn_gamma[8]; float* bn_beta[8];
+  float* bn_mean[8]; float* bn_var[8];
+  float* fc_w; float* fc_b;
+} sg_audionet_train_tensors;
+size_t sg_audionet_train_ws_bytes(const sg_handle* h, int B, int N);
+int sg_audionet_train_fwd(sg_handle* h, const sg_audionet_train_tensors* p, const float* feat, int B, int N,
+                          float momentum, float eps, void* ws, float* logits, sg_stream stream);
+int sg_audionet_train_bwd(sg_handle* h, const sg_audionet_train_tensors* p, const float* feat,
+                          const float* dlogits, int B, int N, void* ws, float* dfeat,
+                          const sg_audionet_train_tensors* g, sg_stream stream);
+int sg_adam_step(sg_handle* h, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n,
+                 float lr, float beta1, float beta2, float eps, float weight_decay, int step, sg_stream stream);
+
 /* ---- caller I/O -------------------------------------------------------------
  * sg_pcm16_quantize: save_audio's conversion (attackMain.py:154-160) for a whole batch on the device:
  *   per utterance, if 0.9*max <= 1 and 0.9*min >= -1 multiply by 2^15; then numpy's astype(int16)

@@ -52,6 +52,11 @@ class AudioNetWeights(C.Structure):
                 ("num_class", C.c_int), ("bn_eps", C.c_float)]
 
 
+class AudioNetTrainTensors(C.Structure):
+    _fields_ = [("conv1_w", _vp), ("conv1_b", _vp), ("conv_w", _vp * 7), ("conv_b", _vp * 7), ("bn_gamma", _vp * 8),
+                ("bn_beta", _vp * 8), ("bn_mean", _vp * 8), ("bn_var", _vp * 8), ("fc_w", _vp), ("fc_b", _vp)]
+
+
 class Cw2Params(C.Structure):
     _fields_ = [("binary_search_steps", C.c_int), ("max_iter", C.c_int), ("stop_early", C.c_int),
                 ("stop_early_iter", C.c_int), ("lr", C.c_float), ("initial_const", C.c_float), ("loss", LossParams),
@@ -112,6 +117,13 @@ PROTOTYPES = {
     "sg_add_delta_fwd": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     "sg_add_delta_bwd": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     "sg_cmvn_cols": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
+    "sg_audionet_train_ws_bytes": (C.c_size_t, [_vp, C.c_int, C.c_int]),
+    "sg_audionet_train_fwd": (C.c_int, [_vp, C.POINTER(AudioNetTrainTensors), _vp, C.c_int, C.c_int, C.c_float, C.c_float, _vp, _vp,
+                                        _vp]),
+    "sg_audionet_train_bwd": (C.c_int, [_vp, C.POINTER(AudioNetTrainTensors), _vp, _vp, C.c_int, C.c_int, _vp, _vp,
+                                        C.POINTER(AudioNetTrainTensors), _vp]),
+    "sg_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_size_t, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int,
+                               _vp]),
     "sg_pcm16_quantize": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
     "sg_wav_write_batch": (C.c_int, [C.POINTER(C.c_char_p), _vp, C.c_int, C.c_int, C.c_int, C.c_int]),
     "sg_wav_read_batch": (C.c_int, [C.POINTER(C.c_char_p), C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, C.c_int]),

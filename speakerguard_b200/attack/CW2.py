@@ -21,7 +21,8 @@ def _fused_audionet(model):
     from ..model.defended_model import defended_model
     if isinstance(model, defended_model) and model.defense is None:
         model = model.base_model
-    return model if isinstance(model, audionet_csine) else None
+    # the device loop runs the inference-mode network (running statistics); a model in train() mode takes the generic path
+    return model if isinstance(model, audionet_csine) and not model.training else None
 
 
 class CW2(FGSM):
@@ -51,6 +52,7 @@ class CW2(FGSM):
 
     def _fused_batch(self, an, x_batch, y_batch):
         lp = make_loss_params("Margin", self.targeted, self.task, self.confidence, self.threshold, True)
+        an._sync_engine()
         best, suc, cst = an.engine.cw2_audionet_run(
             x_batch[:, 0, :], y_batch, lp=lp, binary_search_steps=self.binary_search_steps, max_iter=self.max_iter,
             stop_early=self.stop_early, stop_early_iter=self.stop_early_iter, lr=self.lr, initial_const=self.initial_const)

@@ -6,20 +6,6 @@
 
 #include "sg_handle.cuh"
 
-// conv stack after the 5x5 pre-filter: (C_in, C_out, pad, pool)   audionet_csine.py:66-118
-static const int kAnCin[7] = {32, 64, 128, 128, 128, 128, 64};
-static const int kAnCout[7] = {64, 128, 128, 128, 128, 64, 32};
-static const int kAnPad[7] = {1, 1, 1, 1, 1, 1, 0};
-static const int kAnPool[7] = {1, 0, 0, 1, 0, 1, 0};
-
-struct SgAudioNet {
-  SgAnTables* d_tables = nullptr;
-  int C = 0, Cp = 0;                    // classes, padded to a multiple of 16
-  float *W1 = nullptr, *W1b = nullptr, *b1 = nullptr;         // banded 5x5 pre-filter as a 5-tap 32->32 conv
-  float *W[7] = {}, *Wb[7] = {}, *bias[7] = {};               // [3*cin, cout], [3*cout, cin], [cout]
-  float *Wfc = nullptr, *Wfcb = nullptr, *bfc = nullptr;      // [32, Cp], [Cp, 32], [Cp]
-};
-
 void sg_audionet_free(sg_handle* h) {
   if (h && h->an) { delete h->an; h->an = nullptr; }            // device buffers are in h->allocs
 }

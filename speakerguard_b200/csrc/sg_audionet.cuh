@@ -39,3 +39,18 @@ int sg_cw2_adam_launch(float* w, float* m, float* v, const float* x, const float
 int sg_cw2_track_launch(const float* inp, float* best_x, const float* loss1, const float* loss2, const long long* dec,
                         float* best_l2, long long* best_score, float* gbest_l2, long long* gbest_score, int B, int N, cudaStream_t st);
 int sg_cw2_search_update_launch(float* cst, float* lower, float* upper, const long long* best_score, int B, cudaStream_t st);
+
+// conv stack after the 5x5 pre-filter: (C_in, C_out, pad, pool)   audionet_csine.py:66-118
+static const int kAnCin[7] = {32, 64, 128, 128, 128, 128, 64};
+static const int kAnCout[7] = {64, 128, 128, 128, 128, 64, 32};
+static const int kAnPad[7] = {1, 1, 1, 1, 1, 1, 0};
+static const int kAnPool[7] = {1, 0, 0, 1, 0, 1, 0};
+
+struct SgAudioNet {
+  SgAnTables* d_tables = nullptr;
+  int C = 0, Cp = 0;                    // classes, padded to a multiple of 16
+  float *W1 = nullptr, *W1b = nullptr, *b1 = nullptr;         // banded 5x5 pre-filter as a 5-tap 32->32 conv
+  float *W[7] = {}, *Wb[7] = {}, *bias[7] = {};               // [3*cin, cout], [3*cout, cin], [cout]
+  float *Wfc = nullptr, *Wfcb = nullptr, *bfc = nullptr;      // [32, Cp], [Cp, 32], [Cp]
+};
+

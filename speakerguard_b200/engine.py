@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import AudioNetWeights, Cw2Params, IvWeights, LossParams, PgdParams, XvWeights, check
+from ._lib import AudioNetTrainTensors, AudioNetWeights, Cw2Params, IvWeights, LossParams, PgdParams, XvWeights, check
 
 FLD = 32  # internal feature row stride
 
@@ -188,6 +188,49 @@ class Engine:
         out = torch.empty(*shape, device=self.device, dtype=torch.float32)
         check(self.lib.sg_iv_stage_read(self._h, _ptr(ws), B, T, code, _ptr(out), self.stream), "sg_iv_stage_read")
         return out
+
+    # ---- AudioNet, training mode ---------------------------------------------------------------
+    @staticmethod
+    def an_train_struct(conv1_w, conv1_b, conv_w, conv_b, bn_gamma, bn_beta, fc_w, fc_b, bn_mean=None, bn_var=None):
+        """Pack device tensors (PyTorch layouts) into sg_audionet_train_tensors."""
+        t = AudioNetTrainTensors()
+        t.conv1_w, t.conv1_b, t.fc_w, t.fc_b = _ptr(conv1_w), _ptr(conv1_b), _ptr(fc_w), _ptr(fc_b)
+        for i in range(7):
+            t.conv_w[i], t.conv_b[i] = _ptr(conv_w[i]), _ptr(conv_b[i])
+        for i in range(8):
+            t.bn_gamma[i], t.bn_beta[i] = _ptr(bn_gamma[i]), _ptr(bn_beta[i])
+            t.bn_mean[i] = _ptr(bn_mean[i]) if bn_mean is not None else None
+            t.bn_var[i] = _ptr(bn_var[i]) if bn_var is not None else None
+        return t
+
+    def an_train_fwd(self, tensors, feat: torch.Tensor, N: int, momentum: float = 0.1, eps: float = 1e-5):
+        """feat [B,T,32] -> (logits [B,C], workspace) with batch-statistics BatchNorm; running statistics behind
+        ``tensors`` are updated in place when momentum > 0."""
+        feat = _f32c(feat, self.device)
+        B = feat.shape[0]
+        ws = self.alloc_ws(self.lib.sg_audionet_train_ws_bytes(self._h, B, N))
+        Cp = self.lib.sg_audionet_num_class_padded(self._h)
+        logits = torch.empty(B, Cp, device=self.device, dtype=torch.float32)
+        check(self.lib.sg_audionet_train_fwd(self._h, C.byref(tensors), _ptr(feat), B, N, float(momentum), float(eps), _ptr(ws),
+                                             _ptr(logits), self.stream), "sg_audionet_train_fwd")
+        return logits, ws
+
+    def an_train_bwd(self, tensors, feat: torch.Tensor, dlogits: torch.Tensor, N: int, ws: torch.Tensor, grads=None,
+                     want_dfeat: bool = True):
+        feat, dlogits = _f32c(feat, self.device), _f32c(dlogits, self.device)
+        B = feat.shape[0]
+        dfeat = torch.empty_like(feat) if want_dfeat else None
+        check(self.lib.sg_audionet_train_bwd(self._h, C.byref(tensors), _ptr(feat), _ptr(dlogits), B, N, _ptr(ws), _ptr(dfeat),
+                                             C.byref(grads) if grads is not None else None, self.stream), "sg_audionet_train_bwd")
+        return dfeat
+
+    def adam_step(self, param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, step: int,
+                  lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0) -> None:
+        for t in (param, grad, exp_avg, exp_avg_sq):
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+        check(self.lib.sg_adam_step(self._h, _ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(), float(lr),
+                                    float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step), self.stream),
+              "sg_adam_step")
 
     # ---- AudioNet ------------------------------------------------------------------------------
     AN_CONVS = ["conv2", "conv3", "conv4", "conv5", "conv6", "conv7", "conv8"]

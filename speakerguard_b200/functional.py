@@ -177,3 +177,39 @@ class IvEmbedFn(torch.autograd.Function):
     def backward(ctx, g):
         B, T, F = ctx.shape
         return ctx.eng.iv_embed_bwd(g.contiguous(), ctx.ws, B, T), None
+
+
+class AnCnnTrainFn(torch.autograd.Function):
+    """AudioNet CNN in training mode: log-mel [B,T,32] + the 34 parameter tensors -> logits [B,C]
+    (sg_audionet_train_fwd / _bwd).  BatchNorm uses batch statistics; ``running`` = (list of 8 running means, list of 8
+    running variances) is updated in place with ``momentum``.  Parameter order: conv1.w, conv1.b, conv2..8 w (7),
+    conv2..8 b (7), BN gamma (8), BN beta (8), fc.w, fc.b."""
+
+    @staticmethod
+    def forward(ctx, feat, eng: Engine, N: int, running, momentum: float, eps: float, *params):
+        assert len(params) == 34
+        ps = [p.detach().contiguous() for p in params]
+        feat_c = feat.detach().contiguous()
+        t = eng.an_train_struct(ps[0], ps[1], ps[2:9], ps[9:16], ps[16:24], ps[24:32], ps[32], ps[33],
+                                running[0] if running else None, running[1] if running else None)
+        logits, ws = eng.an_train_fwd(t, feat_c, N, momentum if running else 0.0, eps)
+        ctx.eng, ctx.N, ctx.ws, ctx.ps, ctx.feat = eng, N, ws, ps, feat_c
+        ctx.C = ps[33].shape[0]
+        return logits[:, :ctx.C].contiguous()
+
+    @staticmethod
+    def backward(ctx, g):
+        eng, ps = ctx.eng, ctx.ps
+        Cp = eng.lib.sg_audionet_num_class_padded(eng._h)
+        dl = torch.zeros(g.shape[0], Cp, device=g.device, dtype=torch.float32)
+        dl[:, :ctx.C] = g
+        want_params = any(ctx.needs_input_grad[6:])
+        grads = [torch.empty_like(p) for p in ps] if want_params else None
+        t = eng.an_train_struct(ps[0], ps[1], ps[2:9], ps[9:16], ps[16:24], ps[24:32], ps[32], ps[33])
+        gt = None
+        if want_params:
+            gt = eng.an_train_struct(grads[0], grads[1], grads[2:9], grads[9:16], grads[16:24], grads[24:32], grads[32], grads[33])
+        dfeat = eng.an_train_bwd(t, ctx.feat, dl, ctx.N, ctx.ws, gt, want_dfeat=ctx.needs_input_grad[0] or not want_params)
+        out = [dfeat if ctx.needs_input_grad[0] else None, None, None, None, None, None]
+        out += grads if want_params else [None] * 34
+        return tuple(out)
