@@ -69,16 +69,20 @@ def test_train_step_against_fp64_oracle(params, B, N):
     loss.backward()
     e = {"logits": rel(out, o["logits"]), "loss": abs(float(loss) - float(o["loss"])), "xgrad": rel(xr.grad[:, 0], o["xgrad"])}
     got = grads_of(model)
-    worst = ("", 0.0)
+    errs = {}
     for k in O.AN_PARAM_KEYS:
         if k.endswith(".bias") and k != "fc.bias":
             assert float(got[k].abs().max()) < 1e-4 * max(1.0, float(got[k.replace(".bias", ".weight")].abs().max())), k
             continue
-        r = rel(got[k], o["grads"][k])
-        worst = max(worst, (k, r), key=lambda t: t[1])
-    print(f"AudioNet train step B={B} N={N}: {e} worst param-grad {worst}")
+        errs[k] = rel(got[k], o["grads"][k])
+    top = sorted(errs.items(), key=lambda t: -t[1])[:4]
+    print(f"AudioNet train step B={B} N={N}: {e} largest param-grad errors {top}")
     assert e["logits"] < 1e-4 and e["loss"] < 1e-5 and e["xgrad"] < 1e-4
-    assert worst[1] < 1e-4, worst
+    # the BatchNorm2d(1) of the pre-filter reduces B*32*T signed terms to ONE number: the sum cancels to ~1e-4 of its terms, so
+    # fp32 inputs bound the relative accuracy near 1e-3 (the reference's own fp32 run differs from fp64 by 7e-4 there)
+    loose = {"conv1.bn_gamma", "conv1.bn_beta"}
+    for k, v in errs.items():
+        assert v < (2e-3 if k in loose else 1e-4), (k, v)
     for i, n in enumerate(O.AN_BN_NAMES):
         bn = model._bn_modules()[i]
         assert rel(bn.running_mean, o["stats"][f"{n}.bn_mean"]) < 1e-5
