@@ -274,9 +274,120 @@ def run_iv(args):
     sys.stdout.flush()
 
 
+def antrain_cpu_throughput(N, budget_s=12.0, batch=8, pgd_iters=10):
+    """utterances/s of one adversarial-training step (PGD-10 on the train-mode model + optimisation step) of the oracle port."""
+    from oracle import sg_oracle as O
+    import torch.nn.functional as F
+    torch.set_num_threads(os.cpu_count() or 1)
+    p = O.make_audionet_params(seed=0, num_class=251)
+    g = torch.Generator().manual_seed(0)
+    x = (torch.rand(batch, N, generator=g) * 2 - 1) * 0.5
+    y = torch.randint(0, 251, (batch,), generator=g)
+    done, t0 = 0, time.perf_counter()
+    while True:
+        xa = x.clone()
+        for _ in range(pgd_iters):
+            xr = xa.clone().requires_grad_(True)
+            logits, _ = O.audionet_train_forward(xr, p)
+            F.cross_entropy(logits, y, reduction="sum").backward()
+            xa = torch.min(torch.max(xa + 0.0004 * xr.grad.sign(), x - 0.002), x + 0.002).clamp(-1, 1)
+        O.audionet_train_step(xa, y, p)
+        done += 1
+        el = time.perf_counter() - t0
+        if el >= budget_s:
+            break
+    return batch * done / el, f"oracle: {done} steps of (PGD-{pgd_iters} + train step), B={batch}, {N / 16000:g} s, {el:.1f} s of CPU work", \
+        torch.get_num_threads()
+
+
+def run_antrain(args):
+    """Adversarial training of AudioNet (adver_train.py:183-221): per step PGD-10 on the train-mode model, then forward /
+    backward with parameter gradients and Adam.  Metric: training utterances per second."""
+    from speakerguard_b200 import dist
+    from speakerguard_b200.attack.PGD import PGD
+    from speakerguard_b200.model.audionet_csine import audionet_csine
+    rank, world, local = dist.init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: speakerguard_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    B, N, iters = args.batch, int(args.seconds * 16000), args.iters
+    torch.manual_seed(rank)
+    model = audionet_csine(num_class=251, device=dev)
+    model.train()
+    opt = torch.optim.Adam(model.parameters())
+    attacker = PGD(model, targeted=False, step_size=0.0004, epsilon=0.002, max_iter=iters, batch_size=B, loss="Entropy", verbose=0)
+    crit = torch.nn.CrossEntropyLoss()
+    g = torch.Generator().manual_seed(100 + rank)
+    x_host = ((torch.rand(B, 1, N, generator=g) * 2 - 1) * 0.5).pin_memory()
+    y_host = torch.randint(0, 251, (B,), generator=g).pin_memory()
+    x_dev, y_dev = x_host.to(dev), y_host.to(dev)
+
+    def step(x, y):
+        adv, _ = attacker.attack(x, y)
+        out = model(adv)
+        loss = crit(out, y)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(args.warmup):
+        step(x_dev, y_dev)
+    torch.cuda.synchronize()
+    dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    model.engine.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step(x_dev, y_dev)
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    launches = model.engine.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = dist.max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
+    t0 = time.perf_counter()
+    for _ in range(max(args.e2e_steps, 1)):
+        l_ = step(x_host.to(dev, non_blocking=True), y_host.to(dev, non_blocking=True))
+        float(l_)                                                   # device -> host read of the step's loss
+    e2e_s = dist.max_over_ranks(time.perf_counter() - t0, dev) / max(args.e2e_steps, 1)
+    model.engine.profile(True)
+    step(x_dev, y_dev)
+    prof = model.engine.profile_read()
+    model.engine.profile(False)
+    if world > 1:
+        import torch.distributed as tdist
+        tdist.barrier()
+        tdist.destroy_process_group()
+    if rank != 0:
+        return
+    T = 1 + (N - 1) // 160
+    out = {"metric": "adversarial-training utterances/s (AudioNet, PGD-%d inside the step)" % iters, "value": world * B / (ms_step / 1000.0),
+           "unit": "utt/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "adver_train.py step: PGD-%d (eps 0.002) on the train-mode AudioNet (251 classes) + CE + Adam, "
+                                  "synthetic %g s utterances, batch %d per GPU; replicas are independent (no gradient all-reduce: "
+                                  "the reference trains on one device)" % (iters, args.seconds, B), "batch_per_gpu": B, "samples": N,
+                      "frames": T},
+           "clocks": clocks, "gpu_launches": launches,
+           "e2e": {"value": world * B / e2e_s, "unit": "utt/s", "h2d_bytes_per_step": B * N * 4 + B * 8, "d2h_bytes_per_step": 4,
+                   "ms_per_step": e2e_s * 1000.0},
+           "kernel_ms_per_step": {k: round(v[0], 3) for k, v in prof.items() if v[1]},
+           "roofline": None, "final_loss": float(loss)}
+    if not args.no_cpu_baseline and world == 1:
+        v, sample, cores = antrain_cpu_throughput(N, pgd_iters=iters)
+        out["cpu_baseline"] = {"value": v, "unit": "utt/s", "cores": cores, "kind": "port", "sample": sample}
+    print(json.dumps(out))
+    sys.stdout.flush()
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="xv", choices=["xv", "iv"],
+    ap.add_argument("--workload", default="xv", choices=["xv", "iv", "antrain"],
                     help="xv: the headline (BASELINE configs[1]); iv: configs[4], PGD vs iv_plda (defaults B=256, 5 s, 50 iterations)")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -298,6 +409,14 @@ def main():
             if getattr(args, k) == ap.get_default(k):
                 setattr(args, k, v)
         run_iv(args)
+        return
+    if args.workload == "antrain":
+        if args.impl == "reference":
+            raise SystemExit("--impl reference is defined for the headline workload only")
+        for k, v in {"batch": 128, "seconds": 3.0, "iters": 10}.items():
+            if getattr(args, k) == ap.get_default(k):
+                setattr(args, k, v)
+        run_antrain(args)
         return
     if args.impl == "reference":
         run_reference(args)
