@@ -60,7 +60,7 @@ class FGSM(Attack):
         self.use_fused = True                   # set False to force the generic autograd path
 
     # ---- generic path (reference attack/FGSM.py:38-70) -----------------------------------------
-    def attack_batch(self, x_batch, y_batch, lower, upper, batch_id):
+    def attack_batch(self, x_batch, y_batch, lower, upper, batch_id, x0_batch=None, epsilon=None):
         x_batch = x_batch.detach().clone().contiguous()
         eng = default_engine(x_batch.device)
         success = None
@@ -78,9 +78,13 @@ class FGSM(Attack):
                 print("batch:{} iter:{} loss: {} predict: {}, target: {}".format(
                     batch_id, it, loss.cpu().numpy().tolist(), predict, target))
             if not last:
-                grad = grad / n_b
-                x_batch = x_batch + self.step_size * torch.sign(grad) * self.grad_sign
-                x_batch = torch.min(torch.max(x_batch, lower), upper).contiguous()
+                if x0_batch is not None and x_batch.dtype == torch.float32:
+                    # sign step + eps-ball + [-1,1] box in one kernel (bounds recomputed from x0: attack/PGD.py:48-49)
+                    eng.step_linf(x_batch, x0_batch, grad, self.step_size, self.grad_sign, epsilon)
+                else:
+                    grad = grad / n_b
+                    x_batch = x_batch + self.step_size * torch.sign(grad) * self.grad_sign
+                    x_batch = torch.min(torch.max(x_batch, lower), upper).contiguous()
         return x_batch, success
 
     # ---- fused path -----------------------------------------------------------------------------
@@ -126,7 +130,8 @@ class FGSM(Attack):
             if xv is not None:
                 a, s = self._fused_batch(xv, x[sl], x0[sl], y[sl], epsilon, bid)
             else:
-                a, s = self.attack_batch(x[sl], y[sl], lower[sl], upper[sl], bid)
+                a, s = self.attack_batch(x[sl], y[sl], lower[sl], upper[sl], bid, x0_batch=x0[sl].detach().contiguous(),
+                                         epsilon=epsilon)
             adver.append(a)
             success += s
         return torch.cat(adver, 0), success
