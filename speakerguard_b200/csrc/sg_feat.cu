@@ -692,6 +692,52 @@ __global__ void cmvn_kernel(const float* __restrict__ in, int ld_in, float* __re
   }
 }
 
+// T > 300, parallel form: per-column prefix sums (fp64, shared memory) turn every window sum into a difference, so all
+// 8 row lanes work; used while (T+1) x 32 doubles fit (T <= 850), the serial path above handles longer utterances.
+__global__ void cmvn_prefix_kernel(const float* __restrict__ in, int ld_in, float* __restrict__ out, int ld_out,
+                                   int T, int ncol, int backward) {
+  extern __shared__ double cm_prefix[];                             // [(T+1)][32]
+  const int lc = threadIdx.x, c = blockIdx.y * 32 + lc, r = threadIdx.y, b = blockIdx.x;
+  const float* ib = in + (size_t)b * T * ld_in;
+  float* ob = out + (size_t)b * T * ld_out;
+  const bool cin = c < ncol && c < ld_in;
+  if (r == 0) {
+    double acc = 0.0;
+    cm_prefix[lc] = 0.0;
+    int t = 0;
+    for (; t + 8 <= T; t += 8) {                                    // loads issued together, adds in order
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = cin ? ib[(size_t)(t + u) * ld_in + c] : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { acc += (double)v[u]; cm_prefix[(size_t)(t + u + 1) * 32 + lc] = acc; }
+    }
+    for (; t < T; ++t) { acc += cin ? (double)ib[(size_t)t * ld_in + c] : 0.0; cm_prefix[(size_t)(t + 1) * 32 + lc] = acc; }
+  }
+  __syncthreads();
+  if (c >= ld_out) return;
+  if (!backward) {
+    for (int t = r; t < T; t += 8) {
+      int ws, we;
+      cmvn_window(t, T, ws, we);
+      const double sum = cm_prefix[(size_t)we * 32 + lc] - cm_prefix[(size_t)ws * 32 + lc];
+      ob[(size_t)t * ld_out + c] = cin ? ib[(size_t)t * ld_in + c] - (float)(sum / (double)(we - ws)) : 0.f;
+    }
+  } else {
+    // dx[s] = dy[s] - (1/300) * sum_{t : ws(t) <= s < we(t)} dy[t]  (all windows have 300 frames when T > 300)
+    // t < 150 -> [0,300);  150 <= t <= T-150 -> [t-150,t+150);  t > T-150 -> [T-300,T)
+    const double head = cm_prefix[(size_t)(CMN_WIN / 2) * 32 + lc];
+    const double tail = cm_prefix[(size_t)T * 32 + lc] - cm_prefix[(size_t)(T - CMN_WIN / 2 + 1) * 32 + lc];
+    for (int s = r; s < T; s += 8) {
+      const int lo = max(s - 149, 150), hi = min(s + 150, T - 150);
+      double sum = (hi >= lo) ? cm_prefix[(size_t)(hi + 1) * 32 + lc] - cm_prefix[(size_t)lo * 32 + lc] : 0.0;
+      if (s < CMN_WIN) sum += head;
+      if (s >= T - CMN_WIN) sum += tail;
+      ob[(size_t)s * ld_out + c] = cin ? ib[(size_t)s * ld_in + c] - (float)(sum * (1.0 / CMN_WIN)) : 0.f;
+    }
+  }
+}
+
 // =============================================================================================
 // host launchers (called from sg_api.cu)
 // =============================================================================================
@@ -777,14 +823,27 @@ int sg_step_linf_launch(float* x, const float* x0, const float* grad, size_t n, 
   return SG_OK;
 }
 
-int sg_cmvn_launch(const float* in, int ld_in, float* out, int ld_out, int B, int T, int backward, cudaStream_t st) {
-  cmvn_kernel<<<B, dim3(32, 8), 0, st>>>(in, ld_in, out, ld_out, T, SG_NCEP, backward);
+#define CMN_PREFIX_MAX_T 850
+static int cmvn_dispatch(const float* in, int ld_in, float* out, int ld_out, int B, int T, int ncol, int backward, dim3 grid,
+                         cudaStream_t st) {
+  if (T > CMN_WIN && T <= CMN_PREFIX_MAX_T) {
+    static bool attr = false;
+    if (!attr) {
+      SG_CUDA_CHECK(cudaFuncSetAttribute(cmvn_prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (CMN_PREFIX_MAX_T + 1) * 32 * (int)sizeof(double)));
+      attr = true;
+    }
+    cmvn_prefix_kernel<<<grid, dim3(32, 8), (size_t)(T + 1) * 32 * sizeof(double), st>>>(in, ld_in, out, ld_out, T, ncol, backward);
+  } else {
+    cmvn_kernel<<<grid, dim3(32, 8), 0, st>>>(in, ld_in, out, ld_out, T, ncol, backward);
+  }
   SG_LAUNCH_CHECK();
   return SG_OK;
 }
+int sg_cmvn_launch(const float* in, int ld_in, float* out, int ld_out, int B, int T, int backward, cudaStream_t st) {
+  return cmvn_dispatch(in, ld_in, out, ld_out, B, T, SG_NCEP, backward, dim3(B), st);
+}
 // any number of columns (the 72-dim MFCC+delta features of the i-vector system)
 int sg_cmvn_cols_launch(const float* in, int ld_in, float* out, int ld_out, int B, int T, int ncol, int backward, cudaStream_t st) {
-  cmvn_kernel<<<dim3(B, (max(ncol, ld_out) + 31) / 32), dim3(32, 8), 0, st>>>(in, ld_in, out, ld_out, T, ncol, backward);
-  SG_LAUNCH_CHECK();
-  return SG_OK;
+  return cmvn_dispatch(in, ld_in, out, ld_out, B, T, ncol, backward, dim3(B, (max(ncol, ld_out) + 31) / 32), st);
 }

@@ -75,7 +75,7 @@ def test_add_delta_forward_and_adjoint(eng, B, T, F):
     assert relerr(back, xr.grad) < 1e-5
 
 
-@pytest.mark.parametrize("T", [40, 300, 301, 500])
+@pytest.mark.parametrize("T", [40, 300, 301, 500, 850, 900])
 def test_cmvn_72_columns(eng, T):
     x = feats(2, T)
     ref = O.cmvn(x)

@@ -90,7 +90,7 @@ def test_mfcc_philox_dither_is_reproducible_and_normal(eng):
     assert e < 1e-4
 
 
-@pytest.mark.parametrize("T", [40, 200, 300, 301, 500])
+@pytest.mark.parametrize("T", [40, 200, 300, 301, 500, 850, 851])
 def test_cmvn_forward_backward(eng, T):
     g = torch.Generator().manual_seed(T)
     f = (torch.randn(3, T, 30, generator=g) * 8).requires_grad_(True)
