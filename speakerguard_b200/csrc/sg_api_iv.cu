@@ -26,7 +26,9 @@ struct SgIv {
   float offset;
   float *Wq, *WqT, *gconst;        // [Kq, C], [C, Kq], [C]
   float *Wq3K, *WqT3K;             // 3xTF32 operands (K-major): [C, 3Kq] = [hi|lo|hi](WqT), [Kq, 3C] = [hi|lo|hi](Wq)
-  float *U, *UT;                   // [C, Pp], [Pp, C]
+  float *U;                        // [C, Pp]: packed upper triangles of U_c = T_c' S_c^-1 T_c
+  float *UT3;                      // 3xTF32 operand of the L assembly, K-major [Pp, 3C] = [hi|lo|hi](U^T); built on first use
+  float *Tt;                       // [Dp, F*C]: Tt[d, f*C + c] = T_c[f, d]   (adjoint of the L assembly)
   float *Wlin, *WlinT;             // [F*C, Dp], [Dp, F*C]
   float *Wlda, *Wlda_b, *blda;     // [Dp, Lp], [Lp, Dp], [Lp]
   float* emb_mean;                 // [Dp]
@@ -131,9 +133,13 @@ extern "C" int sg_load_iv(sg_handle* h, const sg_iv_weights* w) {
     SG_TRY(sg_dev_upload(h, &m->U, U));
     SG_TRY(sg_dev_upload(h, &m->Wlin, Wlin));
     {
-      std::vector<float> UT((size_t)Pp * C, 0.f);
-      parallel_for(C, [&](int c) { for (int p = 0; p < Pp; ++p) UT[(size_t)p * C + c] = U[(size_t)c * Pp + p]; });
-      SG_TRY(sg_dev_upload(h, &m->UT, UT));
+      std::vector<float> Tt((size_t)Dp * F * C, 0.f);
+      parallel_for(C, [&](int c) {
+        const float* T = w->ive_T + (size_t)c * F * D;
+        for (int f = 0; f < F; ++f)
+          for (int d = 0; d < D; ++d) Tt[(size_t)d * F * C + (size_t)f * C + c] = T[(size_t)f * D + d];
+      });
+      SG_TRY(sg_dev_upload(h, &m->Tt, Tt));
     }
     {
       std::vector<float> WlinT((size_t)Dp * F * C, 0.f);
@@ -164,7 +170,7 @@ extern "C" int sg_load_iv(sg_handle* h, const sg_iv_weights* w) {
 
 // ---------------------------------------------------------------------------------------------
 struct IvWs {
-  float *Xa, *XaT, *Q, *post, *dpost, *FsT, *dFsT, *dFs, *Lpk, *dLpk, *lin, *dlin, *wfull, *iv, *div, *e2, *de2, *tsave, *scal, *dXa, *part, *dll3;
+  float *Xa, *XaT, *Q, *post, *dpost, *FsT, *dFsT, *dFs, *Lpk, *lin, *dlin, *wfull, *iv, *div, *e2, *de2, *tsave, *scal, *dXa, *part, *dll3, *N3;
   double* fac;
   size_t bytes;
 };
@@ -179,7 +185,7 @@ static IvWs iv_ws_layout(void* base, const SgIv* m, int B, int T) {
   w.dll3 = take(R * m->C * 3);
   w.post = take(R * m->C); w.dpost = take(R * m->C);
   w.FsT = take((size_t)B * m->Fa * m->C); w.dFsT = take((size_t)B * m->Fa * m->C); w.dFs = take((size_t)B * m->Fa * m->C);
-  w.Lpk = take((size_t)B * m->Pp); w.dLpk = take((size_t)B * m->Pp);
+  w.Lpk = take((size_t)B * m->Pp); w.N3 = take((size_t)B * 3 * m->C);
   w.lin = take((size_t)B * m->Dp); w.dlin = take((size_t)B * m->Dp);
   w.wfull = take((size_t)B * m->Dp); w.iv = take((size_t)B * m->Dp); w.div = take((size_t)B * m->Dp);
   w.e2 = take((size_t)B * m->Lp); w.de2 = take((size_t)B * m->Lp); w.tsave = take((size_t)B * m->Lp);
@@ -222,6 +228,14 @@ static int iv_gemm_tc3(sg_handle* h, const float* A3, int K3, const float* W3k, 
   PROF(h, SG_PROF_IV_GEMM, st, sg_conv_tc(a, SG_PREC_TF32, st));
   return SG_OK;
 }
+// the 2 GB split operand of the L assembly is only needed in tensor-core mode: built from U on the device at first use
+static int iv_build_ut3(sg_handle* h, cudaStream_t st) {
+  SgIv* m = h->iv;
+  if (m->UT3) return SG_OK;
+  SG_CUDA_CHECK(cudaMalloc((void**)&m->UT3, (size_t)m->Pp * 3 * m->C * sizeof(float)));
+  h->allocs.push_back(m->UT3);
+  return sg_build_ut3_launch(m->U, m->UT3, m->C, m->Pp, st);
+}
 static int iv_gemm(sg_handle* h, const SgConvArgs& a, cudaStream_t st) {
   h->launches += 1;
   PROF(h, SG_PROF_IV_GEMM, st, sg_conv_simt(a, st));
@@ -263,7 +277,13 @@ static int iv_embed_fwd(sg_handle* h, const float* feat, int ld, int B, int T, c
     a.nbatch = B; a.strideA = (long long)Fa * Tp; a.strideW = (long long)Tp * C; a.strideO = (long long)Fa * C;
     SG_TRY(iv_gemm(h, a, st));
   }
-  SG_TRY(iv_gemm(h, gemm_args(w.FsT + (size_t)F * C, Fa * C, m->U, m->UT, nullptr, w.Lpk, m->Pp, B, m->Pp, C), st));
+  if (tc) {      // L assembly N x U as 3xTF32: [B, 3C] x [3C, Pp]
+    SG_TRY(iv_build_ut3(h, st));
+    IV_K(sg_split3_rows_launch(w.FsT + (size_t)F * C, Fa * C, w.N3, B, C, st));
+    SG_TRY(iv_gemm_tc3(h, w.N3, 3 * C, m->UT3, nullptr, w.Lpk, m->Pp, B, m->Pp, st));
+  } else {
+    SG_TRY(iv_gemm(h, gemm_args(w.FsT + (size_t)F * C, Fa * C, m->U, nullptr, nullptr, w.Lpk, m->Pp, B, m->Pp, C), st));
+  }
   SG_TRY(iv_gemm_splitk(h, gemm_args(w.FsT, Fa * C, m->Wlin, m->WlinT, nullptr, w.lin, m->Dp, B, m->Dp, F * C), w.part, st));
   IV_K(sg_chol_solve_launch(w.Lpk, m->Pp, w.lin, m->Dp, m->offset, m->emb_mean, w.fac, w.wfull, w.iv, B, m->D, st));
   SG_TRY(iv_gemm(h, gemm_args(w.iv, m->Dp, m->Wlda, m->Wlda_b, m->blda, w.e2, m->Lp, B, m->Lp, m->Dp), st));
@@ -278,10 +298,12 @@ static int iv_embed_bwd(sg_handle* h, const float* demb, int B, int T, const IvW
   h->launches += 1;
   PROF(h, SG_PROF_HEAD, st, sg_head_bwd_launch(h->H, demb, B, w.tsave, w.scal, w.de2, st));
   SG_TRY(iv_gemm(h, gemm_args(w.de2, m->Lp, m->Wlda_b, m->Wlda, nullptr, w.div, m->Dp, B, m->Dp, m->Lp), st));
-  IV_K(sg_chol_solve_bwd_launch(w.fac, w.wfull, w.div, m->Dp, w.dlin, w.dLpk, m->Pp, B, m->D, st));
+  IV_K(sg_chol_solve_bwd_launch(w.fac, w.wfull, w.div, m->Dp, w.dlin, nullptr, m->Pp, B, m->D, st));
   SG_CUDA_CHECK(cudaMemsetAsync(w.dFsT, 0, (size_t)B * Fa * C * sizeof(float), st));
-  SG_TRY(iv_gemm_splitk(h, gemm_args(w.dLpk, m->Pp, m->UT, m->U, nullptr, w.dFsT + (size_t)F * C, Fa * C, B, C, m->Pp), w.part, st));
   SG_TRY(iv_gemm(h, gemm_args(w.dlin, m->Dp, m->WlinT, m->Wlin, nullptr, w.dFsT, Fa * C, B, F * C, m->Dp), st));
+  // dL = -lambda w' contracts with U_c = G_c T_c without forming it: dN_c = -(G_c' lambda) . (T_c w) = -dF_c . (T_c w)
+  SG_TRY(iv_gemm(h, gemm_args(w.wfull, m->Dp, m->Tt, nullptr, nullptr, w.dFs, Fa * C, B, F * C, m->Dp), st));
+  IV_K(sg_dn_from_df_launch(w.dFsT, w.dFs, B, F, Fa, C, st));
   {  // d post_b = Xa_b dFsT_b : [Tp, Fa] x [Fa, C]
     SgConvArgs a = gemm_args(w.Xa, Fa, w.dFsT, nullptr, nullptr, w.dpost, C, Tp, C, Fa);
     a.nbatch = B; a.strideA = (long long)Tp * Fa; a.strideW = (long long)Fa * C; a.strideO = (long long)Tp * C;

@@ -371,6 +371,7 @@ chol_solve_bwd_kernel(const double* __restrict__ fac, const float* __restrict__ 
   for (int i = threadIdx.x; i < D; i += blockDim.x) vs[i] = (double)dw[(size_t)b * ldr + i];
   chol_solve_with_factor(A, D, vs, Pn, red);
   for (int i = threadIdx.x; i < ldr; i += blockDim.x) drhs[(size_t)b * ldr + i] = i < D ? (float)vs[i] : 0.f;
+  if (!dLp) return;                 // the caller contracts dL = -lambda w' implicitly (sg_api_iv.cu)
   const float* wb = w + (size_t)b * ldr;
   float* o = dLp + (size_t)b * ldp;
   for (int i = 0; i < D; ++i) {
@@ -392,6 +393,44 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits,
     float acc = 0.f;
     for (int sp = 0; sp < splits; ++sp) acc += part[(size_t)sp * n + i];
     out[(i / N) * ldo + (i % N)] = acc;
+  }
+}
+
+// [rows, C] (row stride ld) -> [rows, 3C] = [lo | hi | hi]  (activation-side operand of a 3xTF32 contraction)
+__global__ void split3_rows_kernel(const float* __restrict__ in, int ld, float* __restrict__ out, int rows, int C) {
+  const size_t n = (size_t)rows * C;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / C;
+    const int c = (int)(i - r * C);
+    const float v = in[r * ld + c], hi = tf32_hi(v);
+    float* o = out + r * 3 * C;
+    o[c] = v - hi; o[C + c] = hi; o[2 * C + c] = hi;
+  }
+}
+// U [C, Pp] -> UT3 [Pp, 3C] = [hi | lo | hi](U^T)  (weight-side operand, K-major)
+__global__ void build_ut3_kernel(const float* __restrict__ U, float* __restrict__ UT3, int C, int Pp) {
+  __shared__ float tile[32][33];
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) tile[i][threadIdx.x] = (c0 + i < C) ? U[(size_t)(c0 + i) * Pp + p0 + threadIdx.x] : 0.f;
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const float v = tile[threadIdx.x][i], hi = tf32_hi(v);
+    if (c0 + threadIdx.x >= C) continue;
+    float* o = UT3 + (size_t)(p0 + i) * 3 * C + c0 + threadIdx.x;
+    o[0] = hi; o[C] = v - hi; o[2 * C] = hi;
+  }
+}
+// dFsT[b, F, c] = -sum_f dFsT[b, f, c] * a[b, f, c]   (zeroth-order statistics gradient from the first-order one)
+__global__ void dn_from_df_kernel(float* __restrict__ dFsT, const float* __restrict__ a, int B, int F, int Fa, int C) {
+  const size_t n = (size_t)B * C;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / C;
+    const int c = (int)(i - b * C);
+    const float* d = dFsT + b * Fa * C + c;
+    const float* q = a + b * Fa * C + c;
+    float acc = 0.f;
+    for (int f = 0; f < F; ++f) acc = fmaf(d[(size_t)f * C], q[(size_t)f * C], acc);
+    dFsT[b * Fa * C + (size_t)F * C + c] = -acc;
   }
 }
 
@@ -489,6 +528,21 @@ int sg_chol_solve_bwd_launch(const double* fac, const float* w, const float* dw,
   int r = chol_init(D);
   if (r != SG_OK) return r;
   chol_solve_bwd_kernel<<<B, 256, chol_smem(D), st>>>(fac, w, dw, ldr, drhs, dLp, ldp, D);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+int sg_split3_rows_launch(const float* in, int ld, float* out, int rows, int C, cudaStream_t st) {
+  split3_rows_kernel<<<iv_blocks((size_t)rows * C), 256, 0, st>>>(in, ld, out, rows, C);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+int sg_build_ut3_launch(const float* U, float* UT3, int C, int Pp, cudaStream_t st) {
+  build_ut3_kernel<<<dim3(Pp / 32, (C + 31) / 32), dim3(32, 8), 0, st>>>(U, UT3, C, Pp);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+int sg_dn_from_df_launch(float* dFsT, const float* a, int B, int F, int Fa, int C, cudaStream_t st) {
+  dn_from_df_kernel<<<iv_blocks((size_t)B * C), 256, 0, st>>>(dFsT, a, B, F, Fa, C);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }

@@ -17,3 +17,6 @@ int sg_chol_solve_bwd_launch(const double* fac, const float* w, const float* dw,
 int sg_transpose_batched_launch(const float* in, float* out, int R, int C, int ld_in, int ld_out, size_t stride_in,
                                 size_t stride_out, int nbatch, cudaStream_t st);
 int sg_splitk_reduce_launch(const float* part, int splits, int rows, int N, float* out, int ldo, cudaStream_t st);
+int sg_split3_rows_launch(const float* in, int ld, float* out, int rows, int C, cudaStream_t st);
+int sg_build_ut3_launch(const float* U, float* UT3, int C, int Pp, cudaStream_t st);
+int sg_dn_from_df_launch(float* dFsT, const float* a, int B, int F, int Fa, int C, cudaStream_t st);
