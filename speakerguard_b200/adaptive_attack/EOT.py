@@ -23,27 +23,28 @@ class EOT(nn.Module):
         self.use_grad = use_grad
 
     def forward(self, x_batch, y_batch, EOT_num_batches=None, EOT_batch_size=None, use_grad=None):
-        EOT_num_batches = EOT_num_batches if EOT_num_batches else self.EOT_num_batches
-        EOT_batch_size = EOT_batch_size if EOT_batch_size else self.EOT_batch_size
-        use_grad = self.use_grad if use_grad is None else use_grad
-        n_audios, n_channels, max_len = x_batch.size()
-        grad, scores, loss = None, None, None
-        all_dec = []
-        for _ in range(EOT_num_batches):
-            xr = x_batch.detach().repeat(EOT_batch_size, 1, 1).requires_grad_(use_grad)
-            yr = y_batch.repeat(EOT_batch_size)
-            with torch.set_grad_enabled(use_grad):
-                dec, sc = self.model.make_decision(xr)
-                ls = self.loss(sc, yr)
-            if use_grad:
-                ls.backward(torch.ones_like(ls))
-                g = xr.grad.view(EOT_batch_size, n_audios, n_channels, max_len).mean(0)
-                grad = g if grad is None else grad + g
-            s = sc.detach().view(EOT_batch_size, n_audios, -1).mean(0)
-            l = ls.detach().view(EOT_batch_size, n_audios).mean(0)
-            scores = s if scores is None else scores + s
-            loss = l if loss is None else loss + l
-            all_dec.append(dec.detach().view(EOT_batch_size, n_audios))
-        dec_host = torch.cat(all_dec, 0).cpu().numpy()          # one D2H copy per call
-        decisions = [list(dec_host[:, i]) for i in range(n_audios)]
-        return scores, loss, grad, decisions
+        rounds = EOT_num_batches or self.EOT_num_batches
+        copies = EOT_batch_size or self.EOT_batch_size
+        want_grad = self.use_grad if use_grad is None else use_grad
+        n = x_batch.shape[0]
+        totals = {"scores": None, "loss": None, "grad": None}
+        votes = []
+
+        def accumulate(key, value):
+            totals[key] = value if totals[key] is None else totals[key] + value
+
+        for _ in range(rounds):
+            tiled = x_batch.detach().repeat(copies, 1, 1).requires_grad_(want_grad)     # a leaf: its .grad is read once
+            labels = y_batch.repeat(copies)
+            with torch.set_grad_enabled(want_grad):
+                decided, sc = self.model.make_decision(tiled)
+                per_copy_loss = self.loss(sc, labels)
+            if want_grad:
+                per_copy_loss.backward(torch.ones_like(per_copy_loss))
+                accumulate("grad", tiled.grad.view(copies, *x_batch.shape).mean(0))
+            accumulate("scores", sc.detach().view(copies, n, -1).mean(0))
+            accumulate("loss", per_copy_loss.detach().view(copies, n).mean(0))
+            votes.append(decided.detach().view(copies, n))
+        ballot = torch.cat(votes, 0).cpu().numpy()                                     # one device->host copy per call
+        decisions = [list(ballot[:, i]) for i in range(n)]
+        return totals["scores"], totals["loss"], totals["grad"], decisions

@@ -29,19 +29,11 @@ class CW2(FGSM):
 
     def __init__(self, model, task='CSI', targeted=False, confidence=0., initial_const=1e-3, binary_search_steps=9,
                  max_iter=10000, stop_early=True, stop_early_iter=1000, lr=1e-2, batch_size=1, verbose=1):
-        self.model = model
-        self.task = task
-        self.targeted = targeted
-        self.confidence = confidence
-        self.initial_const = initial_const
-        self.binary_search_steps = binary_search_steps
-        self.max_iter = max_iter
-        self.stop_early = stop_early
-        self.stop_early_iter = stop_early_iter
-        self.lr = lr
-        self.batch_size = batch_size
-        self.verbose = verbose
-        self.threshold = None
+        for name, value in dict(model=model, task=task, targeted=targeted, confidence=confidence, initial_const=initial_const,
+                                binary_search_steps=binary_search_steps, max_iter=max_iter, stop_early=stop_early,
+                                stop_early_iter=stop_early_iter, lr=lr, batch_size=batch_size, verbose=verbose,
+                                threshold=None).items():
+            setattr(self, name, value)
         if self.task in ['SV', 'OSI']:
             self.threshold = self.model.threshold
             print('Running white box attack for {} task, directly using the true threshold {}'.format(

@@ -10,35 +10,28 @@ class PGD(FGSM):
 
     def __init__(self, model, task='CSI', epsilon=0.002, step_size=0.0004, max_iter=10, num_random_init=0,
                  loss='Entropy', targeted=False, batch_size=1, EOT_size=1, EOT_batch_size=1, verbose=1):
-        self.model = model
-        self.task = task
-        self.epsilon = epsilon
-        self.step_size = step_size
-        self.max_iter = max_iter
-        self.num_random_init = num_random_init
-        self.loss_name = loss
-        self.targeted = targeted
-        self.batch_size = batch_size
-        EOT_size, EOT_batch_size = max(1, EOT_size), max(1, EOT_batch_size)
-        assert EOT_size % EOT_batch_size == 0, 'EOT size should be divisible by EOT batch size'
-        self.EOT_size, self.EOT_batch_size = EOT_size, EOT_batch_size
-        self.verbose = verbose
-        self._setup()
+        eot, eot_bs = max(1, EOT_size), max(1, EOT_batch_size)
+        if eot % eot_bs:
+            raise AssertionError('EOT size should be divisible by EOT batch size')
+        for name, value in dict(model=model, task=task, epsilon=epsilon, step_size=step_size, max_iter=max_iter,
+                                num_random_init=num_random_init, loss_name=loss, targeted=targeted, batch_size=batch_size,
+                                EOT_size=eot, EOT_batch_size=eot_bs, verbose=verbose).items():
+            setattr(self, name, value)
+        self._setup()                      # loss object, grad sign, EOT wrapper, threshold (shared with FGSM)
 
     def attack(self, x, y):
-        n_audios = self._check(x, y)
-        _, n_channels, max_len = x.size()
-        upper = torch.clamp(x + self.epsilon, max=1)
-        lower = torch.clamp(x - self.epsilon, min=-1)
-        x_ori = x.clone()
-        best_rate, best_success, best_adver = -1, None, None
-        for init in range(max(1, self.num_random_init)):
-            x_start = x_ori
-            if self.num_random_init > 0:
-                noise = np.random.uniform(-self.epsilon, self.epsilon, (n_audios, n_channels, max_len))
-                x_start = x_ori + torch.tensor(noise, device=x.device, dtype=x.dtype)
-            adver_x, success = self._run(x_start, x_ori, y, lower, upper, self.epsilon, tag='{}-'.format(init))
-            rate = sum(success) / len(success)
-            if rate > best_rate:
-                best_rate, best_success, best_adver = rate, success, adver_x
-        return best_adver, best_success
+        self._check(x, y)
+        eps = self.epsilon
+        x0 = x.clone()
+        box = (torch.clamp(x - eps, min=-1), torch.clamp(x + eps, max=1))      # the eps-ball cut by the [-1, 1] range
+        restarts = max(1, self.num_random_init)
+        winner = (-1.0, None, None)                                             # (success rate, success list, adversarial batch)
+        for trial in range(restarts):
+            start = x0
+            if self.num_random_init > 0:                                        # host numpy draw, like the reference (quirk Q10)
+                start = x0 + torch.as_tensor(np.random.uniform(-eps, eps, tuple(x.shape)), device=x.device, dtype=x.dtype)
+            adv, ok = self._run(start, x0, y, box[0], box[1], eps, tag=f'{trial}-')
+            rate = float(sum(ok)) / len(ok)
+            if rate > winner[0]:
+                winner = (rate, ok, adv)
+        return winner[2], winner[1]
