@@ -10,11 +10,16 @@
 #include "sg_common.cuh"
 
 #define BM 128
-#define BN 128
 #define BK 16
 
+// BN = 128 / 64 / 32 output columns per CTA (the narrow tiles serve the 32- and 64-channel AudioNet stages and the skinny
+// i-vector contractions); every thread owns 8 rows x NT = BN/16 columns
+template <int BN>
 __global__ void __launch_bounds__(256, 2)
 conv_simt_kernel(SgConvArgs a) {
+  constexpr int NT = BN / 16;            // columns per thread: 8 (two float4), 4 (one float4) or 2 (one float2)
+  constexpr int H = NT == 8 ? 2 : 1;     // column groups per thread
+  constexpr int W = NT == 8 ? 4 : NT;    // columns per group
   __shared__ __align__(16) float As[2][BK][BM];
   __shared__ __align__(16) float Bs[2][BK][BN];
   const int tid = threadIdx.x;
@@ -26,13 +31,13 @@ conv_simt_kernel(SgConvArgs a) {
   const int ty = tid >> 4, tx = tid & 15;
   // loaders
   const int a_row = tid & 127, a_k = (tid >> 7) * 8;
-  const int b_k = tid >> 4, b_col = (tid & 15) * 8;
+  const int b_k = tid >> 4, b_col = (tid & 15) * NT;
 
-  float acc[8][8];
+  float acc[8][NT];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < NT; ++j) acc[i][j] = 0.f;
 
   const int kchunks = a.cin / BK;
   const int a_t = a.same_utt ? (p0 + a_row) % a.T : 0;          // frame index of this loader's row
@@ -51,16 +56,26 @@ conv_simt_kernel(SgConvArgs a) {
       ra[0] = ra[1] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     const float* wrow = a.W + (size_t)(tap * a.cin + c0 + b_k) * a.N + n0 + b_col;
-    rb[0] = (n0 + b_col + 3 < a.N) ? __ldg(reinterpret_cast<const float4*>(wrow)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    rb[1] = (n0 + b_col + 7 < a.N) ? __ldg(reinterpret_cast<const float4*>(wrow + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    rb[0] = rb[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (NT >= 4) {
+      if (n0 + b_col + 3 < a.N) rb[0] = __ldg(reinterpret_cast<const float4*>(wrow));
+      if (NT == 8 && n0 + b_col + 7 < a.N) rb[1] = __ldg(reinterpret_cast<const float4*>(wrow + 4));
+    } else if (n0 + b_col + 1 < a.N) {
+      const float2 t = __ldg(reinterpret_cast<const float2*>(wrow));
+      rb[0].x = t.x; rb[0].y = t.y;
+    }
   };
   auto sstore = [&](int buf) {
     As[buf][a_k + 0][a_row] = ra[0].x; As[buf][a_k + 1][a_row] = ra[0].y;
     As[buf][a_k + 2][a_row] = ra[0].z; As[buf][a_k + 3][a_row] = ra[0].w;
     As[buf][a_k + 4][a_row] = ra[1].x; As[buf][a_k + 5][a_row] = ra[1].y;
     As[buf][a_k + 6][a_row] = ra[1].z; As[buf][a_k + 7][a_row] = ra[1].w;
-    *reinterpret_cast<float4*>(&Bs[buf][b_k][b_col]) = rb[0];
-    *reinterpret_cast<float4*>(&Bs[buf][b_k][b_col + 4]) = rb[1];
+    if (NT >= 4) {
+      *reinterpret_cast<float4*>(&Bs[buf][b_k][b_col]) = rb[0];
+      if (NT == 8) *reinterpret_cast<float4*>(&Bs[buf][b_k][b_col + 4]) = rb[1];
+    } else {
+      *reinterpret_cast<float2*>(&Bs[buf][b_k][b_col]) = make_float2(rb[0].x, rb[0].y);
+    }
   };
 
   gload(0);
@@ -73,14 +88,24 @@ conv_simt_kernel(SgConvArgs a) {
     for (int k = 0; k < BK; ++k) {
       float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
       float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
-      float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
-      float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
       const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float bv[NT];
+      if (NT == 8) {
+        const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+        const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+        bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w;
+        bv[NT - 4] = b1.x; bv[NT - 3] = b1.y; bv[NT - 2] = b1.z; bv[NT - 1] = b1.w;
+      } else if (NT == 4) {
+        const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+        bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w;
+      } else {
+        const float2 b0 = *reinterpret_cast<const float2*>(&Bs[buf][k][tx * 2]);
+        bv[0] = b0.x; bv[1] = b0.y;
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int j = 0; j < NT; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
     if (kt + 1 < nk) {
       sstore(buf ^ 1);
@@ -96,31 +121,35 @@ conv_simt_kernel(SgConvArgs a) {
     bool row_ok = true;
     if (a.epilogue == SG_EPI_MASK) row_ok = (row % a.T) < a.t_valid;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int col = n0 + (h == 0 ? tx * 4 : 64 + tx * 4);
+    for (int h = 0; h < H; ++h) {
+      const int col = n0 + (NT == 8 ? (h == 0 ? tx * 4 : 64 + tx * 4) : tx * W);
       if (col >= a.N) continue;
-      float v[4] = {acc[i][h * 4 + 0], acc[i][h * 4 + 1], acc[i][h * 4 + 2], acc[i][h * 4 + 3]};
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < W; ++j) v[j] = acc[i][h * W + j];
       if (a.epilogue == SG_EPI_BIAS || a.epilogue == SG_EPI_BIAS_RELU) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < W; ++j)
           if (col + j < a.N) v[j] += a.bias ? __ldg(a.bias + col + j) : 0.f;
       }
       if (a.epilogue == SG_EPI_BIAS_RELU) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = fmaxf(v[j], 0.f);
+        for (int j = 0; j < W; ++j) v[j] = fmaxf(v[j], 0.f);
       } else if (a.epilogue == SG_EPI_MASK) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < W; ++j) {
           const bool on = row_ok && (col + j < a.N) && (__ldg(a.mask + (size_t)row * a.ldmask + col + j) > 0.f);
           v[j] = on ? v[j] : 0.f;
         }
       }
       float* o = a.out + (size_t)row * a.ldo + col;
-      if (col + 3 < a.N) {
+      if (W == 4 && col + 3 < a.N) {
         *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+      } else if (W == 2 && col + 1 < a.N) {
+        *reinterpret_cast<float2*>(o) = make_float2(v[0], v[1]);
       } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < W; ++j)
           if (col + j < a.N) o[j] = v[j];
       }
     }
@@ -137,8 +166,14 @@ int sg_conv_simt(const SgConvArgs& a, cudaStream_t st) {
     sg_set_error("sg_conv_simt: batch strides must be multiples of 4 floats and nbatch <= 65535");
     return SG_EINVAL;
   }
-  dim3 grid((a.N + BN - 1) / BN, (a.rows + BM - 1) / BM, a.nbatch > 1 ? a.nbatch : 1);
-  conv_simt_kernel<<<grid, 256, 0, st>>>(a);
+  // 128-column tiles unless more than a quarter of their columns would be padding; then the narrower tile with less padding
+  auto padded = [&](int t) { return (a.N + t - 1) / t * t; };
+  int bn = 128;
+  if (4 * (padded(128) - a.N) > padded(128)) bn = padded(32) < padded(64) ? 32 : 64;
+  dim3 grid((a.N + bn - 1) / bn, (a.rows + BM - 1) / BM, a.nbatch > 1 ? a.nbatch : 1);
+  if (bn == 32) conv_simt_kernel<32><<<grid, 256, 0, st>>>(a);
+  else if (bn == 64) conv_simt_kernel<64><<<grid, 256, 0, st>>>(a);
+  else conv_simt_kernel<128><<<grid, 256, 0, st>>>(a);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }
