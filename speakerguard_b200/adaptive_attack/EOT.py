@@ -3,12 +3,14 @@
 Generic path: works with any model exposing ``make_decision`` (including defended models with
 randomised feature-level defenses).  Scores / loss / gradient are the sum over EOT batches of
 the mean within each batch (the caller divides by the number of batches, attack/FGSM.py:50-53).
-Differences from the reference that do not change results: the repeated input is a leaf tensor
-whose ``.grad`` is read once per EOT batch, decisions are gathered on the device and copied to
+Differences from the reference that do not change results: the input gradient is taken with
+``torch.autograd.grad`` on the repeated input (one read per EOT batch, no parameter gradients), decisions are gathered on the device and copied to
 the host once per call, and ``use_grad=False`` really skips the backward pass (reference quirk Q1).
 """
 import torch
 import torch.nn as nn
+
+from ..functional import input_grad_only
 
 
 class EOT(nn.Module):
@@ -22,7 +24,7 @@ class EOT(nn.Module):
         self.EOT_num_batches = self.EOT_size // self.EOT_batch_size
         self.use_grad = use_grad
 
-    def forward(self, x_batch, y_batch, EOT_num_batches=None, EOT_batch_size=None, use_grad=None):
+    def forward(self, x_batch, y_batch, EOT_num_batches=None, EOT_batch_size=None, use_grad=None, need_decisions=True):
         rounds = EOT_num_batches or self.EOT_num_batches
         copies = EOT_batch_size or self.EOT_batch_size
         want_grad = self.use_grad if use_grad is None else use_grad
@@ -40,11 +42,16 @@ class EOT(nn.Module):
                 decided, sc = self.model.make_decision(tiled)
                 per_copy_loss = self.loss(sc, labels)
             if want_grad:
-                per_copy_loss.backward(torch.ones_like(per_copy_loss))
-                accumulate("grad", tiled.grad.view(copies, *x_batch.shape).mean(0))
+                # only d(loss)/d(input) is needed here: parameter gradients of a trainable model (adver_train.py runs the
+                # attack on the train-mode network) are not formed, and nothing accumulates into their .grad
+                with input_grad_only():
+                    (g,) = torch.autograd.grad(per_copy_loss, tiled, torch.ones_like(per_copy_loss))
+                accumulate("grad", g.view(copies, *x_batch.shape).mean(0))
             accumulate("scores", sc.detach().view(copies, n, -1).mean(0))
             accumulate("loss", per_copy_loss.detach().view(copies, n).mean(0))
             votes.append(decided.detach().view(copies, n))
+        if not need_decisions:            # intermediate attack iterations: no device->host copy, the host keeps enqueueing
+            return totals["scores"], totals["loss"], totals["grad"], None
         ballot = torch.cat(votes, 0).cpu().numpy()                                     # one device->host copy per call
         decisions = [list(ballot[:, i]) for i in range(n)]
         return totals["scores"], totals["loss"], totals["grad"], decisions

@@ -16,6 +16,7 @@ import numpy as np
 import torch
 
 from ..adaptive_attack.EOT import EOT
+from ..model.utils import known_input_range
 from ..engine import default_engine, make_loss_params
 from .Attack import Attack
 from .utils import resolve_loss, resolve_prediction
@@ -69,14 +70,19 @@ class FGSM(Attack):
             last = it == self.max_iter
             n_b = 1 if last else int(self.EOT_size // self.EOT_batch_size)
             e_b = 1 if last else self.EOT_batch_size
-            scores, loss, grad, decisions = self.EOT_wrapper(x_batch, y_batch, n_b, e_b, not last)
-            scores, loss = scores / n_b, loss / n_b
-            predict = resolve_prediction(decisions)
-            target = y_batch.detach().cpu().numpy()
-            success = self.compare(target, predict, self.targeted)
-            if self.verbose:
-                print("batch:{} iter:{} loss: {} predict: {}, target: {}".format(
-                    batch_id, it, loss.cpu().numpy().tolist(), predict, target))
+            # decisions are only read back (a host sync) when they are used: the last pass, or every pass when verbose;
+            # the iterate is inside [-1, 1] by construction (_check + the clipping below), so the model's range detection
+            # (another host sync per pass) is told the answer
+            with known_input_range("scale"):
+                scores, loss, grad, decisions = self.EOT_wrapper(x_batch, y_batch, n_b, e_b, not last,
+                                                                 need_decisions=last or bool(self.verbose))
+            if decisions is not None:
+                predict = resolve_prediction(decisions)
+                target = y_batch.detach().cpu().numpy()
+                success = self.compare(target, predict, self.targeted)
+                if self.verbose:
+                    print("batch:{} iter:{} loss: {} predict: {}, target: {}".format(
+                        batch_id, it, (loss / n_b).cpu().numpy().tolist(), predict, target))
             if not last:
                 if x0_batch is not None and x_batch.dtype == torch.float32:
                     # sign step + eps-ball + [-1,1] box in one kernel (bounds recomputed from x0: attack/PGD.py:48-49)

@@ -179,6 +179,23 @@ class IvEmbedFn(torch.autograd.Function):
         return ctx.eng.iv_embed_bwd(g.contiguous(), ctx.ws, B, T), None
 
 
+_INPUT_GRAD_ONLY = [0]
+
+
+class input_grad_only:
+    """``with input_grad_only():`` - backward passes started inside the block only need the gradient with respect to the
+    waveform / features (an attack step on a trainable model): parameter-gradient kernels are skipped and the corresponding
+    autograd outputs are None."""
+
+    def __enter__(self):
+        _INPUT_GRAD_ONLY[0] += 1
+        return self
+
+    def __exit__(self, *exc):
+        _INPUT_GRAD_ONLY[0] -= 1
+        return False
+
+
 class AnCnnTrainFn(torch.autograd.Function):
     """AudioNet CNN in training mode: log-mel [B,T,32] + the 34 parameter tensors -> logits [B,C]
     (sg_audionet_train_fwd / _bwd).  BatchNorm uses batch statistics; ``running`` = (list of 8 running means, list of 8
@@ -203,7 +220,7 @@ class AnCnnTrainFn(torch.autograd.Function):
         Cp = eng.lib.sg_audionet_num_class_padded(eng._h)
         dl = torch.zeros(g.shape[0], Cp, device=g.device, dtype=torch.float32)
         dl[:, :ctx.C] = g
-        want_params = any(ctx.needs_input_grad[6:])
+        want_params = any(ctx.needs_input_grad[6:]) and not _INPUT_GRAD_ONLY[0]
         grads = [torch.empty_like(p) for p in ps] if want_params else None
         t = eng.an_train_struct(ps[0], ps[1], ps[2:9], ps[9:16], ps[16:24], ps[24:32], ps[32], ps[33])
         gt = None
