@@ -405,7 +405,7 @@ struct BwdOut {
   float eps;              // mode 1
 };
 
-__global__ void __launch_bounds__(FEAT_THREADS)
+__global__ void __launch_bounds__(FEAT_THREADS, 3)
 mfcc_bwd_kernel(const float* __restrict__ x, int N, int m, int own_frames, DitherSpec D,
                 const float* __restrict__ draw, int ld, BwdOut O, const SgFeatTables* __restrict__ gT) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
