@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libsgb200.so")
 SG_OK, SG_EINVAL, SG_ECUDA, SG_ESTATE, SG_EUNSUPPORTED = 0, -1, -2, -3, -4
 PREC_FP32, PREC_TF32, PREC_BF16 = 0, 1, 2
 DITHER_OFF, DITHER_TENSOR, DITHER_PHILOX = 0, 1, 2
+OPT_POOL_FUSION, OPT_FEAT_STASH = 1, 2
 LOSS_CE, LOSS_MARGIN = 0, 1
 PROF_COUNT = 14
 IV_STAGE_POST, IV_STAGE_STATS, IV_STAGE_IVECTOR = 0, 1, 2
@@ -77,6 +78,7 @@ PROTOTYPES = {
     "sg_destroy": (None, [_vp]),
     "sg_set_precision": (C.c_int, [_vp, C.c_int]),
     "sg_get_precision": (C.c_int, [_vp]),
+    "sg_set_option": (C.c_int, [_vp, C.c_int, C.c_int]),
     "sg_load_xv": (C.c_int, [_vp, C.POINTER(XvWeights)]),
     "sg_num_frames": (C.c_int, [C.c_int]),
     "sg_mfcc_fwd": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, C.c_uint64, C.c_uint64, _vp, C.c_int, _vp]),

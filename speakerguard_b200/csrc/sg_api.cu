@@ -65,6 +65,8 @@ extern "C" int sg_create(sg_handle** out, int device) {
   SG_CUDA_CHECK(cudaSetDevice(device));
   sg_handle* h = new sg_handle();
   h->device = device;
+  if (const char* e = getenv("SGB200_POOL_FUSION")) h->pool_fusion = atoi(e) != 0;   // A/B switches for bench.py runs
+  if (const char* e = getenv("SGB200_FEAT_STASH")) h->feat_stash = atoi(e) != 0;
   SgFeatTables* host = new SgFeatTables();
   int r = sg_feat_tables_build(host);
   if (r != SG_OK) { delete host; delete h; sg_set_error("sg_create: feature table construction failed"); return r; }
@@ -96,6 +98,13 @@ extern "C" int sg_set_precision(sg_handle* h, int precision) {
   return SG_OK;
 }
 extern "C" int sg_get_precision(const sg_handle* h) { return h ? h->precision : SG_EINVAL; }
+extern "C" int sg_set_option(sg_handle* h, int option, int value) {
+  if (!h) { sg_set_error("null handle"); return SG_EINVAL; }
+  if (option == SG_OPT_POOL_FUSION) { h->pool_fusion = value != 0; return SG_OK; }
+  if (option == SG_OPT_FEAT_STASH) { h->feat_stash = value != 0; return SG_OK; }
+  sg_set_error("unknown option %d", option);
+  return SG_EINVAL;
+}
 extern "C" int sg_profile_enable(sg_handle* h, int enable) {
   if (!h) { sg_set_error("null handle"); return SG_EINVAL; }
   h->prof.on = enable != 0;
@@ -255,9 +264,9 @@ extern "C" int sg_load_xv(sg_handle* h, const sg_xv_weights* w) {
 // ---------------------------------------------------------------------------------------------
 struct XvWs {
   uint32_t* bits[4];
-  float *r[5], *G0, *G1, *G2, *stats, *dstats, *save_mean, *save_std, *e1, *de1, *e2, *de2, *tsave, *scal;
+  float *r[5], *G0, *G1, *G2, *stats, *dstats, *save_mean, *save_std, *ab, *e1, *de1, *e2, *de2, *tsave, *scal;
   // attack-loop extras
-  float *raw, *draw, *feat, *dfeat, *emb, *demb, *scores, *dscores, *loss, *xbuf, *grad;
+  float *raw, *draw, *feat, *dfeat, *emb, *demb, *scores, *dscores, *loss, *xbuf, *grad, *stash;
   long long* dec;
   size_t bytes;
 };
@@ -277,10 +286,11 @@ static XvWs xv_ws_layout(void* base, int B, int T, int Lp, int L, int S, bool at
   w.G0 = take_act(R * SG_C5P); w.G1 = take_act(R * SG_C1); w.G2 = take_act(R * SG_C1);
   w.stats = take((size_t)B * SG_STATS); w.dstats = take((size_t)B * SG_STATS);
   w.save_mean = take((size_t)B * SG_C5P); w.save_std = take((size_t)B * SG_C5P);
+  w.ab = take((size_t)B * SG_C5P * 2);
   w.e1 = take((size_t)B * SG_EMB); w.de1 = take((size_t)B * SG_EMB);
   w.e2 = take((size_t)B * Lp); w.de2 = take((size_t)B * Lp); w.tsave = take((size_t)B * Lp);
   w.scal = take((size_t)B * 4);
-  w.raw = w.draw = w.feat = w.dfeat = w.emb = w.demb = w.scores = w.dscores = w.loss = w.xbuf = w.grad = nullptr;
+  w.raw = w.draw = w.feat = w.dfeat = w.emb = w.demb = w.scores = w.dscores = w.loss = w.xbuf = w.grad = w.stash = nullptr;
   w.dec = nullptr;
   if (attack) {
     w.raw = take(R * SG_FLD); w.draw = take(R * SG_FLD); w.feat = take(R * SG_FLD); w.dfeat = take(R * SG_FLD);
@@ -288,6 +298,7 @@ static XvWs xv_ws_layout(void* base, int B, int T, int Lp, int L, int S, bool at
     w.scores = take((size_t)B * S); w.dscores = take((size_t)B * S); w.loss = take(B);
     w.dec = (long long*)take((size_t)B * 2);
     w.xbuf = take((size_t)B * N); w.grad = take((size_t)B * N);
+    w.stash = take(sg_feat_stash_floats(B, T));      // forward -> adjoint hand-over of the MFCC kernels
   }
   w.bytes = off;
   return w;
@@ -434,8 +445,11 @@ static int embed_bwd(sg_handle* h, const float* demb, int B, int T, const XvWs& 
     a.A = w.de1; a.lda = SG_EMB; a.W = h->Wfc_b; a.Wk = h->Wfc_bk; a.out = w.dstats; a.ldo = SG_STATS; a.N = SG_STATS; a.cin = SG_EMB;
     SG_TRY(sg_run_conv(h, a, true, SG_PROF_HEAD_GEMM, st));
   }
+  // bf16 mode: the pooling adjoint is applied to the staged r5 tiles inside the layer-5 dgrad (no dA5 round trip through HBM)
+  const bool fuse_pool = h->precision == SG_PREC_BF16 && h->pool_fusion && T >= 128;
   h->launches += 1;
-  PROF(h, SG_PROF_POOL, st, sg_pool_bwd_launch(w.r[4], h->precision == SG_PREC_BF16, B, T, tv[4], h->bn5_istd, w.dstats, w.save_mean, w.save_std, w.G0, st));
+  if (fuse_pool) PROF(h, SG_PROF_POOL, st, sg_pool_bwd_params_launch(B, tv[4], h->bn5_istd, w.dstats, w.save_mean, w.save_std, w.ab, st));
+  else PROF(h, SG_PROF_POOL, st, sg_pool_bwd_launch(w.r[4], h->precision == SG_PREC_BF16, B, T, tv[4], h->bn5_istd, w.dstats, w.save_mean, w.save_std, w.G0, st));
   // dgrad chain: dA_l (pre-ReLU grad of layer l) -> dA_{l-1}
   const float* gin = w.G0;
   float* bufs[2] = {w.G1, w.G2};
@@ -445,6 +459,7 @@ static int embed_bwd(sg_handle* h, const float* demb, int B, int T, const XvWs& 
     a.A = gin; a.lda = kCoutP[l]; a.W = h->Wb[l]; a.Wk = h->Wbk[l]; a.rows = R; a.cin = kCoutP[l]; a.taps = kTaps[l];
     a.tap_step = -kDil[l]; a.T = T;
     if (h->precision == SG_PREC_BF16) { a.op_bf16 = 1; a.out_bf16 = l > 0; a.Wk = (const float*)h->Wbk_h[l]; }
+    if (l == 4 && fuse_pool) { a.A = w.r[4]; a.xf_ab = w.ab; a.xf_ld = SG_C5P; a.xf_tv = tv[4]; }
     if (l > 0) {
       float* out = bufs[(4 - l) & 1];
       a.out = out; a.ldo = kCinP[l]; a.N = kCinP[l];
@@ -540,9 +555,10 @@ extern "C" int sg_step_linf(sg_handle* h, float* x, const float* x0, const float
 // fused passes
 // ---------------------------------------------------------------------------------------------
 static int forward_pass(sg_handle* h, const float* x, int B, int N, int m, int mode, const float* dither, uint64_t seed,
-                        uint64_t pass, float thr, const XvWs& w, float* emb, float* scores, long long* dec, cudaStream_t st) {
+                        uint64_t pass, float thr, const XvWs& w, float* emb, float* scores, long long* dec, cudaStream_t st,
+                        float* stash = nullptr) {
   h->launches += 3;
-  PROF(h, SG_PROF_MFCC_FWD, st, sg_feat_fwd_launch(h->d_tables, x, B, N, m, mode, dither, seed, pass, w.raw, SG_FLD, st));
+  PROF(h, SG_PROF_MFCC_FWD, st, sg_feat_fwd_launch(h->d_tables, x, B, N, m, mode, dither, seed, pass, w.raw, SG_FLD, st, stash));
   PROF(h, SG_PROF_CMVN, st, sg_cmvn_launch(w.raw, SG_FLD, w.feat, SG_FLD, B, m, 0, st));
   SG_TRY(embed_fwd(h, w.feat, B, m, w, emb, st));
   PROF(h, SG_PROF_HEAD, st, sg_score_fwd_launch(h->H, emb, B, h->enroll, h->S, thr, scores, dec, st));
@@ -575,13 +591,14 @@ extern "C" int sg_pgd_run(sg_handle* h, float* x_adv, const float* x0, const int
   const float grad_sign = (p->loss.loss == SG_LOSS_CE) ? (p->loss.targeted ? -1.f : 1.f) : -1.f;
   float* cur = x_adv;
   float* other = w.xbuf;
+  float* const stash = h->feat_stash ? w.stash : nullptr;
   float* sc = scores ? scores : w.scores;
   long long* dec = decisions ? (long long*)decisions : w.dec;
   for (int it = 0; it < p->max_iter; ++it) {
     for (int e = 0; e < E; ++e) {
       const uint64_t pass = (uint64_t)it * E + e;
       const float* dth = dither ? dither + pass * dstride : nullptr;
-      SG_TRY(forward_pass(h, cur, B, N, m, p->dither_mode, dth, p->seed, pass, p->decision_threshold, w, w.emb, sc, dec, st));
+      SG_TRY(forward_pass(h, cur, B, N, m, p->dither_mode, dth, p->seed, pass, p->decision_threshold, w, w.emb, sc, dec, st, stash));
       float* lossp = (loss_hist && e == 0) ? loss_hist + (size_t)it * B : w.loss;
       h->launches += 3;
       PROF(h, SG_PROF_LOSS, st, sg_loss_launch(sc, (const long long*)y, B, h->S, p->loss, lossp, w.dscores, st));
@@ -591,11 +608,11 @@ extern "C" int sg_pgd_run(sg_handle* h, float* x_adv, const float* x0, const int
       h->launches += 1;
       if (E == 1) {
         PROF(h, SG_PROF_MFCC_BWD, st, sg_feat_bwd_step_launch(h->d_tables, cur, B, N, m, p->dither_mode, dth, p->seed, pass, w.draw, SG_FLD, x0,
-                                       other, p->step_size * grad_sign, p->epsilon, st));
+                                       other, p->step_size * grad_sign, p->epsilon, st, stash));
         float* t = cur; cur = other; other = t;
       } else {
         PROF(h, SG_PROF_MFCC_BWD, st, sg_feat_bwd_launch(h->d_tables, cur, B, N, m, p->dither_mode, dth, p->seed, pass, w.draw, SG_FLD, w.grad,
-                                  1.0f / (float)E, e > 0, st));
+                                  1.0f / (float)E, e > 0, st, stash));
       }
     }
     if (E > 1) {

@@ -89,6 +89,9 @@ struct SgConvArgs {
   int ldbits;                       // words per row
   // bf16 mode (tensor-core path): A / Wk hold __nv_bfloat16 when op_bf16, out is __nv_bfloat16 when out_bf16
   int op_bf16; int out_bf16;
+  // tensor-core path, bf16 only: fuse the statistics-pooling adjoint into this (layer-5 dgrad) contraction.  A is then the
+  // stored activation r5 and xf_ab [rows / T][xf_ld] holds (alpha', beta) pairs: dA5 = (t < xf_tv && r > 0) ? alpha' + beta r : 0
+  const float* xf_ab; int xf_ld; int xf_tv;
   // batched GEMM (SIMT path only): blockIdx.z selects an item; element strides, 0 = shared operand
   int nbatch; long long strideA, strideW, strideO;
 };

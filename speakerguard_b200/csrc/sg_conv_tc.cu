@@ -26,6 +26,7 @@
 #define TC_SMEM_BYTES (TC_STAGES * TC_STAGE_BYTES + 2 * TC_STG_BYTES + 1024 /*align*/ + 256 /*barriers*/)
 #define TC_THREADS 192                // experimental variants: TMA warp, MMA warp, 4 epilogue warps
 #define TC_MAIN_THREADS 320           // main kernel: TMA warp, MMA warp, 2 x 4 epilogue warps
+#define TC_XF_THREADS (TC_MAIN_THREADS + 256)   // XFORM variant: + 8 warps that rewrite the staged A tile in place
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -111,10 +112,28 @@ struct TcArgs {
   int kchunks, taps, tap_step;     // kchunks = cin / 32
   int epilogue, T, t_valid;
   int m_tiles, n_tiles;
+  // XFORM variant (statistics-pooling adjoint fused into the layer-5 dgrad): A is the stored post-ReLU activation r5;
+  // the transform warps turn each staged tile into dA5 = (t < xf_tv && r > 0) ? alpha' + beta * r : 0 before the MMA
+  // reads it.  xf_ab: [rows / T][xf_ld] pairs (alpha', beta) per utterance and channel.
+  const float4* xf_ab; int xf_ld, xf_tv;
 };
 
-template <int KIND_BF16, int OUT_BF16>
-__global__ void __launch_bounds__(TC_MAIN_THREADS, 1)
+// one 16-byte chunk (8 bf16 channels) of the pooling adjoint; P holds (alpha', beta) for the 8 channels
+__device__ __forceinline__ void xf8(uint4& w, const float4 (&P)[4], bool ok) {
+  uint32_t u[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float lo = __uint_as_float(u[k] << 16), hi = __uint_as_float(u[k] & 0xffff0000u);
+    const float olo = (ok && lo > 0.f) ? fmaf(P[k].y, lo, P[k].x) : 0.f;
+    const float ohi = (ok && hi > 0.f) ? fmaf(P[k].w, hi, P[k].z) : 0.f;
+    const __nv_bfloat162 o = __floats2bfloat162_rn(olo, ohi);
+    u[k] = *reinterpret_cast<const uint32_t*>(&o);
+  }
+  w = make_uint4(u[0], u[1], u[2], u[3]);
+}
+
+template <int KIND_BF16, int OUT_BF16, int XFORM = 0>
+__global__ void __launch_bounds__(XFORM ? TC_XF_THREADS : TC_MAIN_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ CUtensorMap mapO, TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -125,7 +144,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   uint64_t* empty = bars + TC_STAGES;          // [TC_STAGES]
   uint64_t* tfull = bars + 2 * TC_STAGES;      // [2]
   uint64_t* tempty = bars + 2 * TC_STAGES + 2; // [2]
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TC_STAGES + 4);
+  uint64_t* xfull = bars + 2 * TC_STAGES + 4;  // [TC_STAGES] (XFORM: tile transformed, ready for the MMA)
+  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * TC_STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = a.taps * a.kchunks;
@@ -133,7 +153,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   constexpr int KB_ELEMS = KIND_BF16 ? 64 : 32;     // elements per 128-byte k-block
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&xfull[s], 8); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -180,7 +200,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)acc * TC_MAX_BN;
         for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&full[stage], phase);
+          mbar_wait(XFORM ? &xfull[stage] : &full[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * TC_STAGE_BYTES);
           const uint64_t da = make_desc(sa), db = make_desc(sa + TC_A_BYTES);
@@ -192,6 +212,53 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
         tc_commit(&tfull[acc]);          // accumulator complete
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (XFORM && warp >= TC_MAIN_THREADS / 32) {
+    // ===== A-operand transform: warps 10..17 (bf16 tiles: 128 rows x 64 channels, SWIZZLE_128B) =====
+    // thread -> logical 16-byte chunk j (8 channels) of rows g, g+32, g+64, g+96; (g + 32 i) & 7 == g & 7, so the
+    // physical chunk position j ^ (row & 7) is the same for all four rows.  A tile spans at most two utterances
+    // (the host only selects this variant for T >= 128): rows before `isplit` use the parameters of utterance b0,
+    // the others those of b0 + 1.
+    const int t = (int)threadIdx.x - TC_MAIN_THREADS;
+    const int j = t & 7, g = t >> 3;
+    const uint32_t off = (uint32_t)g * 128u + (uint32_t)((j ^ (g & 7)) << 4);
+    const int nutt = a.rows / a.T;
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int mt = tile / a.n_tiles;
+      const int row0 = mt * TC_BM + g;
+      const int b0 = row0 / a.T;
+      const int tt0 = row0 - b0 * a.T;
+      int isplit = (a.T - tt0 + 31) >> 5;
+      if (isplit > 4) isplit = 4;
+      bool ok[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int tt = tt0 + 32 * i - (i >= isplit ? a.T : 0);
+        ok[i] = (row0 + 32 * i < a.rows) && (tt < a.xf_tv);
+      }
+      const bool second = (isplit < 4) && (b0 + 1 < nutt);
+      const float4* q0 = a.xf_ab + (((size_t)(b0 < nutt ? b0 : 0) * a.xf_ld + j * 8) >> 1);
+      const float4* q1 = q0 + (second ? (a.xf_ld >> 1) : 0);
+      for (int kb = 0; kb < nkb; ++kb) {
+        float4 P[4], Q[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { P[k] = __ldg(q0 + kb * 32 + k); Q[k] = __ldg(q1 + kb * 32 + k); }
+        mbar_wait(&full[stage], phase);
+        uint8_t* sa = smem + stage * TC_STAGE_BYTES + off;
+        uint4 w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w[i] = *reinterpret_cast<const uint4*>(sa + i * 4096);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (i < isplit) xf8(w[i], P, ok[i]); else xf8(w[i], Q, ok[i]);
+          *reinterpret_cast<uint4*>(sa + i * 4096) = w[i];
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&xfull[stage]);
+        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else {
@@ -664,6 +731,7 @@ static int tc_init() {
   SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+  SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES));
   SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc256_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC3_SMEM_BYTES));
   {
@@ -719,6 +787,12 @@ int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
   t.rows = a.rows; t.N = a.N; t.bn = bn; t.kchunks = a.cin / kbe; t.taps = a.taps; t.tap_step = a.tap_step;
   t.epilogue = a.epilogue; t.T = a.T > 0 ? a.T : 1; t.t_valid = a.t_valid;
   t.m_tiles = (a.rows + TC_BM - 1) / TC_BM; t.n_tiles = a.N / bn;
+  t.xf_ab = reinterpret_cast<const float4*>(a.xf_ab); t.xf_ld = a.xf_ld; t.xf_tv = a.xf_tv;
+  if (a.xf_ab && !(a.op_bf16 && a.out_bf16 && a.taps == 1 && a.T >= TC_BM && a.rows % a.T == 0 && a.xf_ld % 8 == 0 && a.cin <= a.xf_ld &&
+                   !g_use_256 && !g_use_pair)) {
+    sg_set_error("sg_conv_tc: the fused pooling adjoint needs bf16 operands/output, one tap, T >= 128 (T=%d taps=%d)", a.T, a.taps);
+    return SG_EINVAL;
+  }
   if ((a.epilogue == SG_EPI_BIAS || a.epilogue == SG_EPI_BIAS_RELU) && !a.bias) { sg_set_error("sg_conv_tc: bias epilogue without bias"); return SG_EINVAL; }
   if (g_use_256 && !a.op_bf16 && !a.out_bf16 && bn == TC_MAX_BN && a.taps * (a.cin / TC_BK) >= 24 && a.rows >= 256 * 64) {
     CUtensorMap mapA2;
@@ -747,7 +821,8 @@ int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
   if (r != SG_OK) return r;
   int grid = t.m_tiles * t.n_tiles;
   if (grid > g_num_sms) grid = g_num_sms;
-  if (a.op_bf16 && a.out_bf16) conv_tc_kernel<1, 1><<<grid, TC_MAIN_THREADS, TC_SMEM_BYTES, st>>>(mapA, mapB, mapO, t);
+  if (a.xf_ab) conv_tc_kernel<1, 1, 1><<<grid, TC_XF_THREADS, TC_SMEM_BYTES, st>>>(mapA, mapB, mapO, t);
+  else if (a.op_bf16 && a.out_bf16) conv_tc_kernel<1, 1><<<grid, TC_MAIN_THREADS, TC_SMEM_BYTES, st>>>(mapA, mapB, mapO, t);
   else if (a.op_bf16) conv_tc_kernel<1, 0><<<grid, TC_MAIN_THREADS, TC_SMEM_BYTES, st>>>(mapA, mapB, mapO, t);
   else if (a.out_bf16) conv_tc_kernel<0, 1><<<grid, TC_MAIN_THREADS, TC_SMEM_BYTES, st>>>(mapA, mapB, mapO, t);
   else conv_tc_kernel<0, 0><<<grid, TC_MAIN_THREADS, TC_SMEM_BYTES, st>>>(mapA, mapB, mapO, t);

@@ -347,12 +347,37 @@ __device__ __forceinline__ void copy_tables(SgFeatTables* dst, const SgFeatTable
 }
 static_assert(sizeof(SgFeatTables) % 16 == 0, "SgFeatTables must be int4-copyable");
 
+// ---- per-frame stash: what the adjoint needs from the forward (spectrum, DC-removed dithered frame, mel energies,
+// raw energy).  Written by mfcc_fwd_kernel when the attack loop asks for it, so that mfcc_bwd_kernel neither regenerates
+// the dither nor repeats the forward FFT: 4 KB per frame of extra HBM traffic each way instead of ~1 200 instructions
+// per frame-warp (the adjoint is issue-bound, not bandwidth-bound).  Layout (floats): X[8][32] float2 | f[7][32] float2
+// | mel[32] | sumsq | pad.
+#define SG_STASH_FLOATS 1024
+__device__ __forceinline__ void stash_store(float* __restrict__ sp, const Frame& F, float me, int lane) {
+  float2* s2 = reinterpret_cast<float2*>(sp);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) __stcs(s2 + i * 32 + lane, F.X[i]);
+#pragma unroll
+  for (int n0 = 0; n0 < 7; ++n0) __stcs(s2 + 256 + n0 * 32 + lane, make_float2(F.fe[n0], F.fo[n0]));
+  __stcs(sp + 960 + lane, me);
+  if (lane == 0) __stcs(sp + 992, F.sumsq);
+}
+__device__ __forceinline__ float stash_load(const float* __restrict__ sp, Frame& F, int lane) {
+  const float2* s2 = reinterpret_cast<const float2*>(sp);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) F.X[i] = __ldcs(s2 + i * 32 + lane);
+#pragma unroll
+  for (int n0 = 0; n0 < 7; ++n0) { const float2 v = __ldcs(s2 + 256 + n0 * 32 + lane); F.fe[n0] = v.x; F.fo[n0] = v.y; }
+  F.sumsq = __ldcs(sp + 992);
+  return __ldcs(sp + 960 + lane);
+}
+
 // =============================================================================================
 // F1: waveform -> raw MFCC
 // =============================================================================================
 __global__ void __launch_bounds__(FEAT_THREADS)
 mfcc_fwd_kernel(const float* __restrict__ x, int N, int m, int frames_per_cta, DitherSpec D,
-                float* __restrict__ raw, int ld, const SgFeatTables* __restrict__ gT) {
+                float* __restrict__ raw, int ld, const SgFeatTables* __restrict__ gT, float* __restrict__ stash) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SgFeatTables* T = reinterpret_cast<SgFeatTables*>(smem_raw);
   copy_tables(T, gT);
@@ -370,6 +395,7 @@ mfcc_fwd_kernel(const float* __restrict__ x, int N, int m, int frames_per_cta, D
     const float logE = logf(fmaxf(F.sumsq, SG_EPS));               // kaldi.py:119
     frame_spectrum(F, T, sre, sim, P, lane);
     float me = mel_energy(T, P, lane);
+    if (stash != nullptr) stash_store(stash + ((size_t)b * m + fr) * SG_STASH_FLOATS, F, me, lane);
     float lm = logf(fmaxf(me, SG_EPS));                            // kaldi.py:631-633
     __syncwarp();
     P[lane] = (lane < SG_NMEL) ? lm : 0.f;                         // P is free after mel_energy: lm[32] for the DCT
@@ -405,9 +431,11 @@ struct BwdOut {
   float eps;              // mode 1
 };
 
+template <bool STASH>
 __global__ void __launch_bounds__(FEAT_THREADS, 3)
 mfcc_bwd_kernel(const float* __restrict__ x, int N, int m, int own_frames, DitherSpec D,
-                const float* __restrict__ draw, int ld, BwdOut O, const SgFeatTables* __restrict__ gT) {
+                const float* __restrict__ draw, int ld, BwdOut O, const SgFeatTables* __restrict__ gT,
+                const float* __restrict__ stash) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SgFeatTables* T = reinterpret_cast<SgFeatTables*>(smem_raw);
   float* fbase = reinterpret_cast<float*>(smem_raw + sizeof(SgFeatTables));
@@ -445,11 +473,16 @@ mfcc_bwd_kernel(const float* __restrict__ x, int N, int m, int own_frames, Dithe
       }
     }
     if (fr < f1) {
-      // ---- recompute the forward for this frame ------------------------------------------
+      // ---- the forward of this frame: read back from the stash, or recomputed ----------------
       Frame F;
-      load_frame(F, xb, N, b, m, fr, D, lane);
-      frame_spectrum(F, T, sre, sim, P, lane);
-      const float me = mel_energy(T, P, lane);
+      float me;
+      if (STASH) {
+        me = stash_load(stash + ((size_t)b * m + fr) * SG_STASH_FLOATS, F, lane);
+      } else {
+        load_frame(F, xb, N, b, m, fr, D, lane);
+        frame_spectrum(F, T, sre, sim, P, lane);
+        me = mel_energy(T, P, lane);
+      }
       // ---- backward: cepstra -> log-mel -> mel -> power -> spectrum -----------------------
       const float dC = (lane < SG_NCEP) ? __ldg(draw + ((size_t)b * m + fr) * ld + lane) : 0.f;
       const float dE = __shfl_sync(0xffffffffu, dC, 0);            // C0 <- log-energy
@@ -755,17 +788,18 @@ static DitherSpec make_dither(int mode, const float* tensor, uint64_t seed, uint
 
 int sg_feat_init() {
   SG_CUDA_CHECK(cudaFuncSetAttribute(mfcc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)feat_fwd_smem()));
-  SG_CUDA_CHECK(cudaFuncSetAttribute(mfcc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)feat_bwd_smem()));
+  SG_CUDA_CHECK(cudaFuncSetAttribute(mfcc_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)feat_bwd_smem()));
+  SG_CUDA_CHECK(cudaFuncSetAttribute(mfcc_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)feat_bwd_smem()));
   return SG_OK;
 }
 
 int sg_feat_fwd_launch(const SgFeatTables* dT, const float* x, int B, int N, int m, int mode, const float* dither,
-                       uint64_t seed, uint64_t pass, float* raw, int ld, cudaStream_t st) {
+                       uint64_t seed, uint64_t pass, float* raw, int ld, cudaStream_t st, float* stash) {
   int fpc = 64;
   while (fpc > 8 && (long long)B * ((m + fpc - 1) / fpc) < 592) fpc >>= 1;   // >= 4 CTAs per SM when possible
   dim3 grid((m + fpc - 1) / fpc, B);
   mfcc_fwd_kernel<<<grid, FEAT_THREADS, feat_fwd_smem(), st>>>(x, N, m, fpc, make_dither(mode, dither, seed, pass),
-                                                              raw, ld, dT);
+                                                              raw, ld, dT, stash);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }
@@ -780,28 +814,32 @@ static int bwd_own_frames(int B, int m) {
 
 int sg_feat_bwd_launch(const SgFeatTables* dT, const float* x, int B, int N, int m, int mode, const float* dither,
                        uint64_t seed, uint64_t pass, const float* draw, int ld, float* grad, float scale,
-                       int accumulate, cudaStream_t st) {
+                       int accumulate, cudaStream_t st, const float* stash) {
   BwdOut O;
   memset(&O, 0, sizeof(O));
   O.mode = 0; O.grad = grad; O.scale = scale; O.accumulate = accumulate;
   int own = bwd_own_frames(B, m);
   dim3 grid((m + own - 1) / own, B);
-  mfcc_bwd_kernel<<<grid, FEAT_THREADS, feat_bwd_smem(), st>>>(x, N, m, own, make_dither(mode, dither, seed, pass),
-                                                              draw, ld, O, dT);
+  if (stash) mfcc_bwd_kernel<true><<<grid, FEAT_THREADS, feat_bwd_smem(), st>>>(x, N, m, own, make_dither(mode, dither, seed, pass),
+                                                                            draw, ld, O, dT, stash);
+  else mfcc_bwd_kernel<false><<<grid, FEAT_THREADS, feat_bwd_smem(), st>>>(x, N, m, own, make_dither(mode, dither, seed, pass),
+                                                                         draw, ld, O, dT, nullptr);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }
 
 int sg_feat_bwd_step_launch(const SgFeatTables* dT, const float* x, int B, int N, int m, int mode,
                             const float* dither, uint64_t seed, uint64_t pass, const float* draw, int ld,
-                            const float* x0, float* x_out, float step, float eps, cudaStream_t st) {
+                            const float* x0, float* x_out, float step, float eps, cudaStream_t st, const float* stash) {
   BwdOut O;
   memset(&O, 0, sizeof(O));
   O.mode = 1; O.x0 = x0; O.x_out = x_out; O.step = step; O.eps = eps;
   int own = bwd_own_frames(B, m);
   dim3 grid((m + own - 1) / own, B);
-  mfcc_bwd_kernel<<<grid, FEAT_THREADS, feat_bwd_smem(), st>>>(x, N, m, own, make_dither(mode, dither, seed, pass),
-                                                              draw, ld, O, dT);
+  if (stash) mfcc_bwd_kernel<true><<<grid, FEAT_THREADS, feat_bwd_smem(), st>>>(x, N, m, own, make_dither(mode, dither, seed, pass),
+                                                                            draw, ld, O, dT, stash);
+  else mfcc_bwd_kernel<false><<<grid, FEAT_THREADS, feat_bwd_smem(), st>>>(x, N, m, own, make_dither(mode, dither, seed, pass),
+                                                                         draw, ld, O, dT, nullptr);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }
@@ -847,3 +885,5 @@ int sg_cmvn_launch(const float* in, int ld_in, float* out, int ld_out, int B, in
 int sg_cmvn_cols_launch(const float* in, int ld_in, float* out, int ld_out, int B, int T, int ncol, int backward, cudaStream_t st) {
   return cmvn_dispatch(in, ld_in, out, ld_out, B, T, ncol, backward, dim3(B, (max(ncol, ld_out) + 31) / 32), st);
 }
+
+size_t sg_feat_stash_floats(int B, int m) { return (size_t)B * m * SG_STASH_FLOATS; }

@@ -111,6 +111,22 @@ __global__ void pool_bwd_kernel(const AT* __restrict__ r5, int T, int Tv, const 
   }
 }
 
+// Per-(utterance, channel) coefficients of the pooling adjoint for the fused layer-5 dgrad (sg_conv_tc.cu, XFORM):
+// dA5[t, c] = (t < Tv && r5 > 0) ? alpha' + beta * r5,  alpha' = alpha - beta * mean  (same alpha / beta as pool_bwd_kernel)
+__global__ void pool_bwd_params_kernel(int Tv, int n, const float* __restrict__ bn_istd, const float* __restrict__ dstats,
+                                       const float* __restrict__ save_mean, const float* __restrict__ save_std,
+                                       float2* __restrict__ ab) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const int b = idx / SG_C5P, c = idx - b * SG_C5P;
+  const bool real = c < SG_C5;
+  const float is = real ? bn_istd[c] : 0.f;
+  const float sd = save_std[idx], mean = save_mean[idx];
+  const float alpha = real ? dstats[(size_t)b * SG_STATS + c] * is / (float)Tv : 0.f;
+  const float beta = (real && sd > 0.f) ? dstats[(size_t)b * SG_STATS + SG_C5P + c] * is / ((float)(Tv - 1) * sd) : 0.f;
+  ab[idx] = make_float2(fmaf(-beta, mean, alpha), beta);
+}
+
 // ---------------------------------------------------------------------------------------------
 // block helpers (blockDim.x == 256)
 // ---------------------------------------------------------------------------------------------
@@ -369,6 +385,13 @@ int sg_pool_bwd_launch(const void* r5, int bf16, int B, int T, int Tv, const flo
   int tsplit = (B >= 64) ? 1 : 4;
   if (bf16) pool_bwd_kernel<__nv_bfloat16><<<dim3(SG_C5P / 128, B, tsplit), dim3(32, 8), 0, st>>>((const __nv_bfloat16*)r5, T, Tv, bn_istd, dstats, save_mean, save_std, (__nv_bfloat16*)dA5);
   else pool_bwd_kernel<float><<<dim3(SG_C5P / 128, B, tsplit), dim3(32, 8), 0, st>>>((const float*)r5, T, Tv, bn_istd, dstats, save_mean, save_std, (float*)dA5);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+int sg_pool_bwd_params_launch(int B, int Tv, const float* bn_istd, const float* dstats, const float* save_mean,
+                              const float* save_std, float* ab, cudaStream_t st) {
+  const int n = B * SG_C5P;
+  pool_bwd_params_kernel<<<(n + 255) / 256, 256, 0, st>>>(Tv, n, bn_istd, dstats, save_mean, save_std, reinterpret_cast<float2*>(ab));
   SG_LAUNCH_CHECK();
   return SG_OK;
 }

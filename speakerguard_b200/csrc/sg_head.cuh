@@ -15,13 +15,14 @@ struct SgHeadConst {           // device pointers + scalars describing the PLDA 
 
 int sg_feat_init();
 int sg_feat_fwd_launch(const SgFeatTables* dT, const float* x, int B, int N, int m, int mode, const float* dither,
-                       uint64_t seed, uint64_t pass, float* raw, int ld, cudaStream_t st);
+                       uint64_t seed, uint64_t pass, float* raw, int ld, cudaStream_t st, float* stash = nullptr);
 int sg_feat_bwd_launch(const SgFeatTables* dT, const float* x, int B, int N, int m, int mode, const float* dither,
                        uint64_t seed, uint64_t pass, const float* draw, int ld, float* grad, float scale,
-                       int accumulate, cudaStream_t st);
+                       int accumulate, cudaStream_t st, const float* stash = nullptr);
 int sg_feat_bwd_step_launch(const SgFeatTables* dT, const float* x, int B, int N, int m, int mode,
                             const float* dither, uint64_t seed, uint64_t pass, const float* draw, int ld,
-                            const float* x0, float* x_out, float step, float eps, cudaStream_t st);
+                            const float* x0, float* x_out, float step, float eps, cudaStream_t st, const float* stash = nullptr);
+size_t sg_feat_stash_floats(int B, int m);   // per-frame forward stash consumed by the adjoint (attack loop only)
 int sg_dither_fill_launch(int B, int m, uint64_t seed, uint64_t pass, float* out, cudaStream_t st);
 int sg_step_linf_launch(float* x, const float* x0, const float* grad, size_t n, float step, float eps, cudaStream_t st);
 int sg_cmvn_launch(const float* in, int ld_in, float* out, int ld_out, int B, int T, int backward, cudaStream_t st);
@@ -30,6 +31,8 @@ int sg_pool_fwd_launch(const void* r5, int bf16, int B, int T, int Tv, const flo
                        float* stats, float* save_mean, float* save_std, cudaStream_t st);
 int sg_pool_bwd_launch(const void* r5, int bf16, int B, int T, int Tv, const float* bn_istd, const float* dstats,
                        const float* save_mean, const float* save_std, void* dA5, cudaStream_t st);
+int sg_pool_bwd_params_launch(int B, int Tv, const float* bn_istd, const float* dstats, const float* save_mean,
+                              const float* save_std, float* ab, cudaStream_t st);
 int sg_head_fwd_launch(const SgHeadConst& H, const float* e2, int B, float* tsave, float* scal, float* emb, cudaStream_t st);
 int sg_head_bwd_launch(const SgHeadConst& H, const float* dq, int B, const float* tsave, const float* scal, float* de2, cudaStream_t st);
 int sg_score_fwd_launch(const SgHeadConst& H, const float* emb, int B, const float* enroll, int S, float threshold,

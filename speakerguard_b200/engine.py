@@ -68,6 +68,10 @@ class Engine:
         check(self.lib.sg_set_precision(self._h, _lib.PRECISIONS[precision]), "sg_set_precision")
         self.precision = precision
 
+    def set_option(self, option: int, value: int) -> None:
+        """Engine options of include/sgb200.h (SG_OPT_*)."""
+        check(self.lib.sg_set_option(self._h, int(option), int(value)), "sg_set_option")
+
     @property
     def stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)

@@ -186,3 +186,57 @@ def test_fused_pgd_loop_in_tensor_core_modes_matches_fp32_outcome(prec):
           f"{float((h1[-1] - h0[-1]).abs().max() / h0[-1].abs().max()):.3e}")
     assert agree > 0.90
     assert float((h1[-1] - h0[-1]).abs().max()) < 0.05 * float(h0[-1].abs().max())
+
+
+def test_pool_adjoint_fused_into_layer5_dgrad_matches_two_kernel_form():
+    """SG_OPT_POOL_FUSION (bf16 mode, T >= 128): the statistics-pooling adjoint applied to the staged r5 tiles inside the
+    layer-5 dgrad contraction vs the separate pool_bwd pass.  Both round dA5 to bf16 once (the fused form evaluates
+    alpha' + beta r with alpha' = alpha - beta mean instead of alpha + beta (r - mean)), so the feature gradients agree
+    to bf16 rounding: <= 2e-2 of the per-utterance max (stated), rows beyond the valid frames zero in both."""
+    from oracle import sg_oracle as O
+    from speakerguard_b200 import _lib
+    from speakerguard_b200.engine import Engine, make_loss_params
+    p = O.make_xv_params(seed=0)
+    torch.manual_seed(9)
+    # 3 s (T = 300: tiles straddle utterance boundaries at changing offsets) and an odd batch (ragged last tile)
+    x = ((torch.rand(7, 1, 48000) * 2 - 1) * 0.5)[:, 0].cuda()
+    y = torch.tensor([0, 1, 2, 3, 4, 5, 6]).cuda()
+    res = {}
+    for fuse in (0, 1):
+        eng = Engine("cuda:0", precision="bf16")
+        eng.load_xv(p)
+        eng.set_option(_lib.OPT_POOL_FUSION, fuse)
+        feat = eng.cmvn(eng.mfcc_fwd(x, _lib.DITHER_PHILOX, None, seed=3, pass_=0, ld=32), ld_out=32)
+        emb, ws = eng.embed_fwd(feat)
+        scores, _ = eng.score_fwd(emb)
+        _, ds = eng.loss(scores, y, make_loss_params("Entropy"))
+        res[fuse] = eng.embed_bwd(eng.score_bwd(emb, ds), ws, 7, feat.shape[1]).float().cpu()
+    g0, g1 = res[0], res[1]
+    assert torch.isfinite(g1).all()
+    err = float(((g1 - g0).abs().amax((1, 2)) / g0.abs().amax((1, 2))).max())
+    cos = float((g1 * g0).sum() / (g1.norm() * g0.norm()))
+    print(f"pool fusion vs two-kernel form: max rel diff {err:.2e}, cosine {cos:.6f}")
+    assert err < 2e-2 and cos > 0.9995
+
+
+def test_feat_stash_is_bit_identical_to_recomputing_adjoint():
+    """SG_OPT_FEAT_STASH: the fused loop with the forward -> adjoint hand-over gives the same iterates, bit for bit, as the
+    adjoint that recomputes the forward (fp32 mode; PGD-3 and EOT size 2)."""
+    from oracle import sg_oracle as O
+    from speakerguard_b200 import _lib
+    from speakerguard_b200.engine import Engine, make_loss_params
+    p = O.make_xv_params(seed=0)
+    torch.manual_seed(21)
+    x = ((torch.rand(5, 1, 24000) * 2 - 1) * 0.5)[:, 0].cuda()
+    y = torch.tensor([0, 3, 5, 7, 9]).cuda()
+    for eot in (1, 2):
+        out = []
+        for stash in (0, 1):
+            eng = Engine("cuda:0", precision="fp32")
+            eng.load_xv(p)
+            eng.set_option(_lib.OPT_FEAT_STASH, stash)
+            xa = x.clone()
+            eng.pgd_run(xa, x, y, max_iter=3, epsilon=0.002, step_size=0.0004, lp=make_loss_params("Entropy"),
+                        dither_mode=_lib.DITHER_PHILOX, seed=13, eot_size=eot)
+            out.append(xa.cpu())
+        assert torch.equal(out[0], out[1])
