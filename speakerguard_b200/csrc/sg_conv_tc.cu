@@ -23,7 +23,7 @@
 #define TC_B_BYTES (TC_MAX_BN * TC_BK * 4)      // 32 KB
 #define TC_STAGE_BYTES (TC_A_BYTES + TC_B_BYTES)
 #define TC_STG_BYTES (TC_BM * 32 * 4)            // 16 KB epilogue staging box (128 rows x 32 fp32), x2
-#define TC_SMEM_BYTES (TC_STAGES * TC_STAGE_BYTES + 2 * TC_STG_BYTES + 1024 /*align*/ + 256 /*barriers*/)
+#define TC_SMEM_BYTES (TC_STAGES * TC_STAGE_BYTES + 2 * TC_STG_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*bias*/)
 #define TC_THREADS 192                // experimental variants: TMA warp, MMA warp, 4 epilogue warps
 #define TC_MAIN_THREADS 320           // main kernel: TMA warp, MMA warp, 2 x 4 epilogue warps
 #define TC_XF_THREADS (TC_MAIN_THREADS + 256)   // XFORM variant: + 8 warps that rewrite the staged A tile in place
@@ -96,6 +96,20 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// split form: several loads in flight, one wait (the registers must not be read before tc_ld_wait)
+__device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, float (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]),
+        "=f"(v[8]), "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]),
+        "=f"(v[16]), "=f"(v[17]), "=f"(v[18]), "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]),
+        "=f"(v[24]), "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp):
 // start address >> 4 in [0,14), LBO (unused for swizzled K-major) = 1 in [16,30), SBO = 1024 B
 // (8 rows x 128 B) >> 4 in [32,46), version 1 in [46,48), layout SWIZZLE_128B = 2 in [61,64).
@@ -146,6 +160,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   uint64_t* tempty = bars + 2 * TC_STAGES + 2; // [2]
   uint64_t* xfull = bars + 2 * TC_STAGES + 4;  // [TC_STAGES] (XFORM: tile transformed, ready for the MMA)
   uint32_t* tmem_slot = (uint32_t*)(bars + 3 * TC_STAGES + 4);
+  float* bias_s = (float*)(bars + 32);         // [2 epilogue groups][128]: the bias of the current tile's columns
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = a.taps * a.kchunks;
@@ -188,6 +203,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
+    // (a warp-convergent loop with an elected issuing lane was measured: fewer uniform-datapath instructions per k-block,
+    // but no faster - the issue loop is not what limits the tensor pipe here)
     if (lane == 0) {
       // instruction descriptor: D=f32 [4,6)=1, A/B format [7,10)/[10,13) (tf32=2, bf16=1), K-major both,
       // N>>3 in [17,23), M>>4 in [24,29)
@@ -273,40 +290,50 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const bool issuer = (((warp - 2) & 3) == 0 && lane == 0);
     uint8_t* buf = stg + grp * TC_STG_BYTES;
     constexpr int CW = OUT_BF16 ? 64 : 32;                // columns per 128-byte staging row
+    const bool has_bias = (a.epilogue == SG_EPI_BIAS || a.epilogue == SG_EPI_BIAS_RELU);
+    float* bias_g = bias_s + grp * 128;
     int acc = 0; uint32_t acc_phase = 0;
     uint32_t nstore = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
       const int row = mt * TC_BM + r_in;
       const int n0 = nt * a.bn;
+      if (has_bias) {
+        // this group's 128 columns of the bias (chunk k, column i -> bias_g[k * CW + i]); the last named barrier of the
+        // previous tile ordered every read of bias_g before this write
+        const int t = ((warp - 2) & 3) * 32 + lane;
+        const int cc = grp * CW + (t / CW) * 2 * CW + (t % CW);
+        bias_g[t] = cc < a.bn ? __ldg(a.bias + n0 + cc) : 0.f;
+        epi_bar(1 + grp);
+      }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       bool row_ok = row < a.rows;
       if (a.epilogue == SG_EPI_MASK) row_ok = row_ok && ((row % a.T) < a.t_valid);
-      // one 32-column group: TMEM -> registers -> epilogue op
-      auto group = [&](int c, float (&v)[32]) {
-        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TC_MAX_BN + c), v);
-        const int col = n0 + c;
-        if (a.epilogue == SG_EPI_BIAS || a.epilogue == SG_EPI_BIAS_RELU) {
-          const float4* bp = reinterpret_cast<const float4*>(a.bias + col);
+      // One chunk = NG groups of 32 columns.  The operands of the epilogue op (bias / ReLU bits) are requested first,
+      // then all TMEM loads of the chunk are issued with a single wait, so that their latencies overlap instead of
+      // adding up (the short-K layers are bound by this warp's critical path, not by issue slots).
+      constexpr int NG = OUT_BF16 ? 2 : 1;
+      const bool use_bits = (a.epilogue == SG_EPI_MASK) && a.bits_in != nullptr;
+      auto apply = [&](int col, float (&v)[32], const float* bsm, uint32_t wbits) {
+        if (has_bias) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 b4 = __ldg(bp + j);
+            const float4 b4 = *reinterpret_cast<const float4*>(bsm + 4 * j);      // uniform address: one broadcast wavefront
             v[4 * j + 0] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
           }
           if (a.epilogue == SG_EPI_BIAS_RELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
             if (a.bits_out != nullptr && row < a.rows) {
-              uint32_t wbits = 0;
+              uint32_t ob = 0;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) wbits |= (v[j] > 0.f ? 1u : 0u) << j;
-              a.bits_out[(size_t)row * a.ldbits + (col >> 5)] = wbits;
+              for (int j = 0; j < 32; ++j) ob |= (v[j] > 0.f ? 1u : 0u) << j;
+              a.bits_out[(size_t)row * a.ldbits + (col >> 5)] = ob;
             }
           }
         } else if (a.epilogue == SG_EPI_MASK) {
-          if (row_ok && a.bits_in != nullptr) {
-            const uint32_t wbits = __ldg(a.bits_in + (size_t)row * a.ldbits + (col >> 5));
+          if (use_bits) {                                     // wbits is 0 for rows outside the valid range
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = ((wbits >> j) & 1u) ? v[j] : 0.f;
           } else if (row_ok) {
@@ -326,16 +353,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
       };
       for (int c = grp * CW; c < a.bn; c += 2 * CW, ++nstore) {
-        float v[32];
-        group(c, v);
+        float v[NG][32];
+        uint32_t wb[NG];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          const int col = n0 + c + 32 * g;
+          wb[g] = 0u;
+          if (use_bits && row_ok) {
+            wb[g] = __ldg(a.bits_in + (size_t)row * a.ldbits + (col >> 5));
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < NG; ++g)
+          tc_ld32_issue(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TC_MAX_BN + c + 32 * g), v[g]);
+        tc_ld_wait();
+#pragma unroll
+        for (int g = 0; g < NG; ++g) apply(n0 + c + 32 * g, v[g], bias_g + (c - grp * CW) / 2 + 32 * g, wb[g]);
         uint4 packed[8];
         if (OUT_BF16) {
-          float v2[32];
-          group(c + 32, v2);
+          const float (&v1)[32] = v[0];
+          const float (&v2)[32] = v[NG - 1];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * j + 0], v[8 * j + 1]), p1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
-            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]), p3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(v1[8 * j + 0], v1[8 * j + 1]), p1 = __floats2bfloat162_rn(v1[8 * j + 2], v1[8 * j + 3]);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(v1[8 * j + 4], v1[8 * j + 5]), p3 = __floats2bfloat162_rn(v1[8 * j + 6], v1[8 * j + 7]);
             packed[j] = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
                                    *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
             __nv_bfloat162 s0 = __floats2bfloat162_rn(v2[8 * j + 0], v2[8 * j + 1]), s1 = __floats2bfloat162_rn(v2[8 * j + 2], v2[8 * j + 3]);
@@ -346,8 +387,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         } else {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            packed[j] = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
-                                   __float_as_uint(v[4 * j + 3]));
+            packed[j] = make_uint4(__float_as_uint(v[0][4 * j]), __float_as_uint(v[0][4 * j + 1]), __float_as_uint(v[0][4 * j + 2]),
+                                   __float_as_uint(v[0][4 * j + 3]));
         }
         if (nstore >= 1) {                                  // this group's previous store must have drained the box
           if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
