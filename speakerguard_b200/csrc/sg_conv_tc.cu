@@ -96,6 +96,12 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// bf16x2 {lo, hi} = {max(lo, 0), max(hi, 0)} rounded to nearest even: ReLU folded into the conversion
+__device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
 // split form: several loads in flight, one wait (the registers must not be read before tc_ld_wait)
 __device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, float (&v)[32]) {
   asm volatile(
@@ -323,12 +329,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             v[4 * j + 0] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
           }
           if (a.epilogue == SG_EPI_BIAS_RELU) {
+            // The epilogue warps are bound by the 16-lane integer/ALU pipe (2 warps per scheduler), so every instruction per
+            // element counts: the ReLU of a bf16 output is folded into the conversion (cvt.rn.relu.bf16x2.f32) and the
+            // ReLU bit is one set + one lop3.
+            if (!OUT_BF16) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
             if (a.bits_out != nullptr && row < a.rows) {
+              // bit j = (x_j > 0): 0 - x has its sign bit set exactly then (0 - (+-0) = +0), and a funnel shift moves that
+              // sign into the word: two FADDs on the wide FMA pipe + one SHF per element instead of FSETP + SEL + IADD3
               uint32_t ob = 0;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) ob |= (v[j] > 0.f ? 1u : 0u) << j;
+              for (int j = 31; j >= 0; --j) ob = __funnelshift_l(__float_as_uint(0.f - v[j]), ob, 1);
               a.bits_out[(size_t)row * a.ldbits + (col >> 5)] = ob;
             }
           }
@@ -370,7 +383,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
         for (int g = 0; g < NG; ++g) apply(n0 + c + 32 * g, v[g], bias_g + (c - grp * CW) / 2 + 32 * g, wb[g]);
         uint4 packed[8];
-        if (OUT_BF16) {
+        if (OUT_BF16 && a.epilogue == SG_EPI_BIAS_RELU) {
+#pragma unroll
+          for (int g = 0; g < NG; ++g)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              packed[4 * g + j] = make_uint4(pack_relu_bf16x2(v[g][8 * j + 0], v[g][8 * j + 1]), pack_relu_bf16x2(v[g][8 * j + 2], v[g][8 * j + 3]),
+                                             pack_relu_bf16x2(v[g][8 * j + 4], v[g][8 * j + 5]), pack_relu_bf16x2(v[g][8 * j + 6], v[g][8 * j + 7]));
+        } else if (OUT_BF16) {
           const float (&v1)[32] = v[0];
           const float (&v2)[32] = v[NG - 1];
 #pragma unroll
