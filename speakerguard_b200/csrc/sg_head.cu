@@ -79,6 +79,68 @@ __global__ void pool_fwd_kernel(const AT* __restrict__ r5, int T, int Tv, const 
   }
 }
 
+// bf16 mode: single pass over r5 (the two-pass form above re-reads every CTA's 70 KB slab through L2, which costs as much
+// as the first read).  Shifted sums with the first frame as pivot: d = x - x[0], mean = x[0] + S1/n,
+// var = (S2 - S1^2/n)/(n-1) clamped at 0; exact (var = 0) for constant / dead channels.  The fp32 accumulation error is
+// far below the bf16 rounding of the activations themselves; fp32 / tf32 modes keep the reference's two-pass form.
+// grid (C5P/256, B), block (32, 8): each thread owns 8 consecutive channels (16-byte loads), 8 row lanes.
+__device__ __forceinline__ void unpack8(const uint4 u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { f[2 * k] = __uint_as_float(w[k] << 16); f[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u); }
+}
+__global__ void __launch_bounds__(256)
+pool_fwd_onepass_kernel(const __nv_bfloat16* __restrict__ r5, int T, int Tv, const float* __restrict__ bn_mean,
+                        const float* __restrict__ bn_istd, float* __restrict__ stats,
+                        float* __restrict__ save_mean, float* __restrict__ save_std) {
+  __shared__ float p1[8][32][9], p2[8][32][9];                     // [row lane][channel group][8 channels + pad]
+  const int c0 = blockIdx.x * 256 + threadIdx.x * 8, r = threadIdx.y, b = blockIdx.y;
+  const __nv_bfloat16* base = r5 + (size_t)b * T * SG_C5P + c0;
+  float K[8], s1[8], s2[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(base)), K);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+  int t = r;
+  for (; t + 24 < Tv; t += 32) {                                   // 4 independent 16-byte loads in flight per thread
+    uint4 u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) u[k] = __ldcs(reinterpret_cast<const uint4*>(base + (size_t)(t + 8 * k) * SG_C5P));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float f[8];
+      unpack8(u[k], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const float d = f[i] - K[i]; s1[i] += d; s2[i] = fmaf(d, d, s2[i]); }
+    }
+  }
+  for (; t < Tv; t += 8) {
+    float f[8];
+    unpack8(__ldcs(reinterpret_cast<const uint4*>(base + (size_t)t * SG_C5P)), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float d = f[i] - K[i]; s1[i] += d; s2[i] = fmaf(d, d, s2[i]); }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { p1[r][threadIdx.x][i] = s1[i]; p2[r][threadIdx.x][i] = s2[i]; }
+  __syncthreads();
+  // 256 threads -> 256 channels: thread (x, y) finishes channel y * 32 + x of this block
+  const int cl = r * 32 + threadIdx.x, g = cl >> 3, i = cl & 7;
+  float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { a1 += p1[k][g][i]; a2 += p2[k][g][i]; }
+  const int c = blockIdx.x * 256 + cl;
+  const float n = (float)Tv;
+  const float pivot = __bfloat162float(r5[(size_t)b * T * SG_C5P + c]);
+  const float mean = pivot + a1 / n;
+  const float var = fmaxf(a2 - a1 * a1 / n, 0.f) / (float)(Tv - 1);   // unbiased (torch.std default)
+  const float sd = sqrtf(var);
+  const bool real = c < SG_C5;
+  const float mu = real ? bn_mean[c] : 0.f, is = real ? bn_istd[c] : 0.f;
+  stats[(size_t)b * SG_STATS + c] = real ? (mean - mu) * is : 0.f;
+  stats[(size_t)b * SG_STATS + SG_C5P + c] = real ? sd * is : 0.f;
+  save_mean[(size_t)b * SG_C5P + c] = mean;
+  save_std[(size_t)b * SG_C5P + c] = sd;
+}
+
 // d(stats) -> d(pre-ReLU layer-5 activation), ReLU mask and row validity applied
 // grid (C5P/128, B, tsplit), block (32, 8); each thread owns 4 consecutive channels (float4 traffic)
 template <typename AT>
@@ -375,7 +437,8 @@ __global__ void loss_kernel(const float* __restrict__ scores, const long long* _
 // ---------------------------------------------------------------------------------------------
 int sg_pool_fwd_launch(const void* r5, int bf16, int B, int T, int Tv, const float* bn_mean, const float* bn_istd,
                        float* stats, float* save_mean, float* save_std, cudaStream_t st) {
-  if (bf16) pool_fwd_kernel<__nv_bfloat16><<<dim3(SG_C5P / 128, B), dim3(32, 8), 0, st>>>((const __nv_bfloat16*)r5, T, Tv, bn_mean, bn_istd, stats, save_mean, save_std);
+  if (bf16 && Tv >= 2) pool_fwd_onepass_kernel<<<dim3(SG_C5P / 256, B), dim3(32, 8), 0, st>>>((const __nv_bfloat16*)r5, T, Tv, bn_mean, bn_istd, stats, save_mean, save_std);
+  else if (bf16) pool_fwd_kernel<__nv_bfloat16><<<dim3(SG_C5P / 128, B), dim3(32, 8), 0, st>>>((const __nv_bfloat16*)r5, T, Tv, bn_mean, bn_istd, stats, save_mean, save_std);
   else pool_fwd_kernel<float><<<dim3(SG_C5P / 128, B), dim3(32, 8), 0, st>>>((const float*)r5, T, Tv, bn_mean, bn_istd, stats, save_mean, save_std);
   SG_LAUNCH_CHECK();
   return SG_OK;
