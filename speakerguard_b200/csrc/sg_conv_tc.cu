@@ -134,20 +134,23 @@ struct TcArgs {
   int m_tiles, n_tiles;
   // XFORM variant (statistics-pooling adjoint fused into the layer-5 dgrad): A is the stored post-ReLU activation r5;
   // the transform warps turn each staged tile into dA5 = (t < xf_tv && r > 0) ? alpha' + beta * r : 0 before the MMA
-  // reads it.  xf_ab: [rows / T][xf_ld] pairs (alpha', beta) per utterance and channel.
-  const float4* xf_ab; int xf_ld, xf_tv;
+  // reads it.  xf_ab: [rows / T][xf_ld / 2] x {alpha' pair, beta pair} (bf16x2 each) per utterance and channel pair.
+  const uint4* xf_ab; int xf_ld, xf_tv;
 };
 
-// one 16-byte chunk (8 bf16 channels) of the pooling adjoint; P holds (alpha', beta) for the 8 channels
-__device__ __forceinline__ void xf8(uint4& w, const float4 (&P)[4], bool ok) {
+// one 16-byte chunk (8 bf16 channels) of the pooling adjoint in packed bf16x2 arithmetic: P holds, per channel pair,
+// {alpha' pair, beta pair}; one fma.rn.bf16x2 + one compare mask + one lop3 per pair (the first version did this in fp32,
+// ~9 instructions per pair, and made the transform warps - not the tensor pipe - the limiter of the contraction).
+// r5 is post-ReLU (>= +0), so r > 0 <=> r != 0.  okm: all ones for valid frames, 0 otherwise.
+__device__ __forceinline__ void xf8(uint4& w, const uint4 (&P)[2], uint32_t okm) {
   uint32_t u[4] = {w.x, w.y, w.z, w.w};
+  const uint32_t al[4] = {P[0].x, P[0].z, P[1].x, P[1].z}, be[4] = {P[0].y, P[0].w, P[1].y, P[1].w};
+  const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const float lo = __uint_as_float(u[k] << 16), hi = __uint_as_float(u[k] & 0xffff0000u);
-    const float olo = (ok && lo > 0.f) ? fmaf(P[k].y, lo, P[k].x) : 0.f;
-    const float ohi = (ok && hi > 0.f) ? fmaf(P[k].w, hi, P[k].z) : 0.f;
-    const __nv_bfloat162 o = __floats2bfloat162_rn(olo, ohi);
-    u[k] = *reinterpret_cast<const uint32_t*>(&o);
+    const __nv_bfloat162 r = *reinterpret_cast<const __nv_bfloat162*>(&u[k]);
+    const __nv_bfloat162 f = __hfma2(*reinterpret_cast<const __nv_bfloat162*>(&be[k]), r, *reinterpret_cast<const __nv_bfloat162*>(&al[k]));
+    u[k] = *reinterpret_cast<const uint32_t*>(&f) & __hne2_mask(r, zero) & okm;
   }
   w = make_uint4(u[0], u[1], u[2], u[3]);
 }
@@ -255,19 +258,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const int tt0 = row0 - b0 * a.T;
       int isplit = (a.T - tt0 + 31) >> 5;
       if (isplit > 4) isplit = 4;
-      bool ok[4];
+      uint32_t okm[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int tt = tt0 + 32 * i - (i >= isplit ? a.T : 0);
-        ok[i] = (row0 + 32 * i < a.rows) && (tt < a.xf_tv);
+        okm[i] = ((row0 + 32 * i < a.rows) && (tt < a.xf_tv)) ? 0xffffffffu : 0u;
       }
       const bool second = (isplit < 4) && (b0 + 1 < nutt);
-      const float4* q0 = a.xf_ab + (((size_t)(b0 < nutt ? b0 : 0) * a.xf_ld + j * 8) >> 1);
-      const float4* q1 = q0 + (second ? (a.xf_ld >> 1) : 0);
+      const uint4* q0 = a.xf_ab + (((size_t)(b0 < nutt ? b0 : 0) * a.xf_ld + j * 8) >> 2);   // one uint4 = 4 channels
+      const uint4* q1 = q0 + (second ? (a.xf_ld >> 2) : 0);
       for (int kb = 0; kb < nkb; ++kb) {
-        float4 P[4], Q[4];
+        uint4 P[2], Q[2];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { P[k] = __ldg(q0 + kb * 32 + k); Q[k] = __ldg(q1 + kb * 32 + k); }
+        for (int k = 0; k < 2; ++k) { P[k] = __ldg(q0 + kb * 16 + k); Q[k] = __ldg(q1 + kb * 16 + k); }
         mbar_wait(&full[stage], phase);
         uint8_t* sa = smem + stage * TC_STAGE_BYTES + off;
         uint4 w[4];
@@ -275,7 +278,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int i = 0; i < 4; ++i) w[i] = *reinterpret_cast<const uint4*>(sa + i * 4096);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          if (i < isplit) xf8(w[i], P, ok[i]); else xf8(w[i], Q, ok[i]);
+          if (i < isplit) xf8(w[i], P, okm[i]); else xf8(w[i], Q, okm[i]);
           *reinterpret_cast<uint4*>(sa + i * 4096) = w[i];
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
@@ -848,7 +851,7 @@ int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
   t.rows = a.rows; t.N = a.N; t.bn = bn; t.kchunks = a.cin / kbe; t.taps = a.taps; t.tap_step = a.tap_step;
   t.epilogue = a.epilogue; t.T = a.T > 0 ? a.T : 1; t.t_valid = a.t_valid;
   t.m_tiles = (a.rows + TC_BM - 1) / TC_BM; t.n_tiles = a.N / bn;
-  t.xf_ab = reinterpret_cast<const float4*>(a.xf_ab); t.xf_ld = a.xf_ld; t.xf_tv = a.xf_tv;
+  t.xf_ab = reinterpret_cast<const uint4*>(a.xf_ab); t.xf_ld = a.xf_ld; t.xf_tv = a.xf_tv;
   if (a.xf_ab && !(a.op_bf16 && a.out_bf16 && a.taps == 1 && a.T >= TC_BM && a.rows % a.T == 0 && a.xf_ld % 8 == 0 && a.cin <= a.xf_ld &&
                    !g_use_256 && !g_use_pair)) {
     sg_set_error("sg_conv_tc: the fused pooling adjoint needs bf16 operands/output, one tap, T >= 128 (T=%d taps=%d)", a.T, a.taps);

@@ -36,7 +36,7 @@ struct sg_handle {
   int precision = SG_PREC_FP32;
   long long launches = 0;
   int feat_stash = 1;               // SG_OPT_FEAT_STASH: the fused attack loop hands the per-frame forward state to the MFCC adjoint
-  int pool_fusion = 0;              // SG_OPT_POOL_FUSION: bf16 mode contracts the pooling adjoint inside the layer-5 dgrad (measured slower: off)
+  int pool_fusion = 1;              // SG_OPT_POOL_FUSION: bf16 mode contracts the pooling adjoint inside the layer-5 dgrad
   SgFeatTables* d_tables = nullptr;
   bool xv_loaded = false;
   bool backend_loaded = false;      // PLDA back-end + enrolled speakers (set by sg_load_xv / sg_load_iv)

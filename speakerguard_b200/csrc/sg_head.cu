@@ -173,20 +173,28 @@ __global__ void pool_bwd_kernel(const AT* __restrict__ r5, int T, int Tv, const 
   }
 }
 
-// Per-(utterance, channel) coefficients of the pooling adjoint for the fused layer-5 dgrad (sg_conv_tc.cu, XFORM):
-// dA5[t, c] = (t < Tv && r5 > 0) ? alpha' + beta * r5,  alpha' = alpha - beta * mean  (same alpha / beta as pool_bwd_kernel)
-__global__ void pool_bwd_params_kernel(int Tv, int n, const float* __restrict__ bn_istd, const float* __restrict__ dstats,
+// Per-(utterance, channel pair) coefficients of the pooling adjoint for the fused layer-5 dgrad (sg_conv_tc.cu, XFORM):
+// dA5[t, c] = (t < Tv && r5 > 0) ? alpha' + beta * r5,  alpha' = alpha - beta * mean  (same alpha / beta as pool_bwd_kernel),
+// stored as bf16x2 {alpha'(c), alpha'(c+1)}, {beta(c), beta(c+1)} for the packed arithmetic of the tile transform.
+__global__ void pool_bwd_params_kernel(int Tv, int npair, const float* __restrict__ bn_istd, const float* __restrict__ dstats,
                                        const float* __restrict__ save_mean, const float* __restrict__ save_std,
-                                       float2* __restrict__ ab) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n) return;
-  const int b = idx / SG_C5P, c = idx - b * SG_C5P;
-  const bool real = c < SG_C5;
-  const float is = real ? bn_istd[c] : 0.f;
-  const float sd = save_std[idx], mean = save_mean[idx];
-  const float alpha = real ? dstats[(size_t)b * SG_STATS + c] * is / (float)Tv : 0.f;
-  const float beta = (real && sd > 0.f) ? dstats[(size_t)b * SG_STATS + SG_C5P + c] * is / ((float)(Tv - 1) * sd) : 0.f;
-  ab[idx] = make_float2(fmaf(-beta, mean, alpha), beta);
+                                       uint2* __restrict__ ab) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npair) return;
+  float al[2], be[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int idx = 2 * p + k;
+    const int b = idx / SG_C5P, c = idx - b * SG_C5P;
+    const bool real = c < SG_C5;
+    const float is = real ? bn_istd[c] : 0.f;
+    const float sd = save_std[idx], mean = save_mean[idx];
+    const float alpha = real ? dstats[(size_t)b * SG_STATS + c] * is / (float)Tv : 0.f;
+    be[k] = (real && sd > 0.f) ? dstats[(size_t)b * SG_STATS + SG_C5P + c] * is / ((float)(Tv - 1) * sd) : 0.f;
+    al[k] = fmaf(-be[k], mean, alpha);
+  }
+  const __nv_bfloat162 a2 = __floats2bfloat162_rn(al[0], al[1]), b2 = __floats2bfloat162_rn(be[0], be[1]);
+  ab[p] = make_uint2(*reinterpret_cast<const uint32_t*>(&a2), *reinterpret_cast<const uint32_t*>(&b2));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -453,8 +461,8 @@ int sg_pool_bwd_launch(const void* r5, int bf16, int B, int T, int Tv, const flo
 }
 int sg_pool_bwd_params_launch(int B, int Tv, const float* bn_istd, const float* dstats, const float* save_mean,
                               const float* save_std, float* ab, cudaStream_t st) {
-  const int n = B * SG_C5P;
-  pool_bwd_params_kernel<<<(n + 255) / 256, 256, 0, st>>>(Tv, n, bn_istd, dstats, save_mean, save_std, reinterpret_cast<float2*>(ab));
+  const int n = B * SG_C5P / 2;
+  pool_bwd_params_kernel<<<(n + 255) / 256, 256, 0, st>>>(Tv, n, bn_istd, dstats, save_mean, save_std, reinterpret_cast<uint2*>(ab));
   SG_LAUNCH_CHECK();
   return SG_OK;
 }
