@@ -57,6 +57,9 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"((uint64_t)map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const void* smem_src, const CUtensorMap* map, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"((uint64_t)map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
@@ -136,7 +139,45 @@ struct TcArgs {
   // the transform warps turn each staged tile into dA5 = (t < xf_tv && r > 0) ? alpha' + beta * r : 0 before the MMA
   // reads it.  xf_ab: [rows / T][xf_ld / 2] x {alpha' pair, beta pair} (bf16x2 each) per utterance and channel pair.
   const uint4* xf_ab; int xf_ld, xf_tv;
+  int pf_dist;                     // L2 prefetch distance of the A operand in k-blocks (0 = off)
 };
+
+// ---- cluster / cta_group::2 helpers ------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+template <int KIND_BF16>
+__device__ __forceinline__ void tc_mma_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (KIND_BF16) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  } else {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  }
+}
+
 
 // one 16-byte chunk (8 bf16 channels) of the pooling adjoint in packed bf16x2 arithmetic: P holds, per channel pair,
 // {alpha' pair, beta pair}; one fma.rn.bf16x2 + one compare mask + one lop3 per pair (the first version did this in fp32,
@@ -155,39 +196,59 @@ __device__ __forceinline__ void xf8(uint4& w, const uint4 (&P)[2], uint32_t okm)
   w = make_uint4(u[0], u[1], u[2], u[3]);
 }
 
-template <int KIND_BF16, int OUT_BF16, int XFORM = 0>
+template <int KIND_BF16, int OUT_BF16, int XFORM = 0, int PAIR = 0>
 __global__ void __launch_bounds__(XFORM ? TC_XF_THREADS : TC_MAIN_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ CUtensorMap mapO, TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* stg = smem + TC_STAGES * TC_STAGE_BYTES;                 // 2 x 16 KB, 1024-byte aligned
+  // PAIR: a CTA pair (cluster of 2 on one TPC) computes a 256 x BN tile with tcgen05.mma.cta_group::2.  Each CTA stages
+  // its own 128 rows of A and HALF of the B tile, so a k-block costs 32 KB of L2 -> SM traffic per CTA instead of 48 KB
+  // for the same 4.2 MFLOP (the single-CTA kernel sits at the L2 -> SM throughput cap: ~620 clk per k-block against 512
+  // for the tensor pipe), and the smaller stage leaves room for 6 pipeline stages.  Rank 0 issues the MMAs; both CTAs
+  // run TMA producers (signalling rank 0's full barriers) and epilogues (own 128 TMEM lanes); commits are multicast.
+  constexpr int NST = PAIR ? 6 : TC_STAGES;
+  constexpr uint32_t STB = PAIR ? (TC_A_BYTES + TC_B_BYTES / 2) : TC_STAGE_BYTES;
+  static_assert(NST * STB == TC_STAGES * TC_STAGE_BYTES, "both layouts use the same 192 KB ring");
+  static_assert(!(PAIR && XFORM), "the fused pooling adjoint is a single-CTA variant");
+  uint8_t* stg = smem + NST * STB;                                   // 2 x 16 KB, 1024-byte aligned
   uint64_t* bars = (uint64_t*)(stg + 2 * TC_STG_BYTES);
-  uint64_t* full = bars;                       // [TC_STAGES]
-  uint64_t* empty = bars + TC_STAGES;          // [TC_STAGES]
-  uint64_t* tfull = bars + 2 * TC_STAGES;      // [2]
-  uint64_t* tempty = bars + 2 * TC_STAGES + 2; // [2]
-  uint64_t* xfull = bars + 2 * TC_STAGES + 4;  // [TC_STAGES] (XFORM: tile transformed, ready for the MMA)
-  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * TC_STAGES + 4);
+  uint64_t* full = bars;                       // [NST]   (PAIR: rank 0's copy is the live one)
+  uint64_t* empty = bars + NST;                // [NST]   per CTA
+  uint64_t* tfull = bars + 2 * NST;            // [2]     per CTA
+  uint64_t* tempty = bars + 2 * NST + 2;       // [2]     (PAIR: rank 0's copy is the live one)
+  uint64_t* xfull = bars + 2 * NST + 4;        // [NST] (XFORM: tile transformed, ready for the MMA)
+  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * NST + 4);
   float* bias_s = (float*)(bars + 32);         // [2 epilogue groups][128]: the bias of the current tile's columns
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = a.taps * a.kchunks;
   const int ntiles = a.m_tiles * a.n_tiles;
   constexpr int KB_ELEMS = KIND_BF16 ? 64 : 32;     // elements per 128-byte k-block
+  const uint32_t rank = PAIR ? cluster_rank() : 0u;
+  const int cta0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // first tile of this CTA (pair)
+  const int tstep = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  constexpr int TILE_ROWS = PAIR ? 2 * TC_BM : TC_BM;
+  const int rbase = (int)rank * TC_BM;                                   // this CTA's rows inside a pair tile
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&xfull[s], 8); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
+    for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&xfull[s], 8); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], PAIR ? 16 : 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();                  // barriers of both CTAs initialised before any remote arrive / TMA signal
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -195,18 +256,45 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // ===== TMA producer =====
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      const uint32_t tx = TC_A_BYTES + (uint32_t)a.bn * TC_BK * 4;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int bh = PAIR ? (a.bn >> 1) : a.bn;                       // B rows staged by this CTA
+      const uint32_t tx = (PAIR ? 2u : 1u) * (TC_A_BYTES + (uint32_t)bh * TC_BK * 4);
+      // L2 prefetch cursor for the A operand, a.pf_dist k-blocks ahead of the load cursor.  A single-tap layer streams A
+      // from HBM exactly once, and with only TC_STAGES - 1 boxes in flight per SM the ring cannot cover the HBM latency
+      // (Little: 3 x 16 KB x 148 SMs / ~2 us = 3.5 TB/s); the prefetch moves that wait out of the ring, so the ring
+      // only sees L2 latency.  B (weights) is L2-resident anyway.
+      int ptile = cta0, pkb = 0;
+      auto prefetch_next = [&]() {
+        if (ptile < ntiles) {
+          const int ptap = pkb / a.kchunks, pkc = pkb - ptap * a.kchunks;
+          tma_prefetch_2d(&mapA, pkc * KB_ELEMS, (ptile / a.n_tiles) * TILE_ROWS + rbase + ptap * a.tap_step);
+          if (++pkb == nkb) { pkb = 0; ptile += tstep; }
+        }
+      };
+      for (int i = 0; i < a.pf_dist; ++i) prefetch_next();
+      for (int tile = cta0; tile < ntiles; tile += tstep) {
         const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
-        const int p0 = mt * TC_BM, n0 = nt * a.bn;
+        const int p0 = mt * TILE_ROWS + rbase, n0 = nt * a.bn + (int)rank * (PAIR ? bh : 0);
         for (int kb = 0; kb < nkb; ++kb) {
           const int tap = kb / a.kchunks, kc = kb - tap * a.kchunks;
+          if (a.pf_dist > 0) prefetch_next();
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], tx);
-          uint8_t* sa = smem + stage * TC_STAGE_BYTES;
-          tma_load_2d(sa, &mapA, &full[stage], kc * KB_ELEMS, p0 + tap * a.tap_step);
-          tma_load_2d(sa + TC_A_BYTES, &mapB, &full[stage], kb * KB_ELEMS, n0);
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          uint8_t* sa = smem + stage * STB;
+          if (PAIR) {
+            const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
+            // only the leader arms the barrier (count 1, transaction bytes of BOTH CTAs' boxes).  The peer's bytes may land
+            // first: the transaction count then goes negative while the phase's single arrival is still pending, so the
+            // phase cannot complete early, and the peer cannot run a whole ring phase ahead because its empty[stage] is
+            // released by the commit that follows the leader's MMAs.  (A per-k-block remote mbarrier.arrive.release.cluster
+            // from the peer costs a GPU-scope membar each time and throttled the pair to ~1700 clk per k-block.)
+            if (rank == 0) mbar_expect_tx(&full[stage], tx);
+            tma_load_2d_2sm(sa, &mapA, lead_full, kc * KB_ELEMS, p0 + tap * a.tap_step);
+            tma_load_2d_2sm(sa + TC_A_BYTES, &mapB, lead_full, kb * KB_ELEMS, n0);
+          } else {
+            mbar_expect_tx(&full[stage], tx);
+            tma_load_2d(sa, &mapA, &full[stage], kc * KB_ELEMS, p0 + tap * a.tap_step);
+            tma_load_2d(sa + TC_A_BYTES, &mapB, &full[stage], kb * KB_ELEMS, n0);
+          }
+          if (++stage == NST) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -214,29 +302,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // ===== MMA issuer =====
     // (a warp-convergent loop with an elected issuing lane was measured: fewer uniform-datapath instructions per k-block,
     // but no faster - the issue loop is not what limits the tensor pipe here)
-    if (lane == 0) {
+    if (lane == 0 && rank == 0) {
       // instruction descriptor: D=f32 [4,6)=1, A/B format [7,10)/[10,13) (tf32=2, bf16=1), K-major both,
       // N>>3 in [17,23), M>>4 in [24,29)
       const uint32_t fmt = KIND_BF16 ? 1u : 2u;
-      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(a.bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(a.bn >> 3) << 17) | ((uint32_t)(TILE_ROWS >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int tile = cta0; tile < ntiles; tile += tstep) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)acc * TC_MAX_BN;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(XFORM ? &xfull[stage] : &full[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * TC_STAGE_BYTES);
+          const uint32_t sa = smem_u32(smem + stage * STB);
           const uint64_t da = make_desc(sa), db = make_desc(sa + TC_A_BYTES);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)   // 4 x (K = 32 bytes) per 128-byte swizzle span: +2 in 16-byte units
-            tc_mma<KIND_BF16>(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-          tc_commit(&empty[stage]);      // frees the smem slot when these MMAs retire
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          for (int k = 0; k < 4; ++k) {  // 4 x (K = 32 bytes) per 128-byte swizzle span: +2 in 16-byte units
+            if (PAIR) tc_mma_2sm<KIND_BF16>(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            else tc_mma<KIND_BF16>(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          }
+          if (PAIR) tc_commit_2sm(&empty[stage]); else tc_commit(&empty[stage]);   // frees the smem slot when these MMAs retire
+          if (++stage == NST) { stage = 0; phase ^= 1; }
         }
-        tc_commit(&tfull[acc]);          // accumulator complete
+        if (PAIR) tc_commit_2sm(&tfull[acc]); else tc_commit(&tfull[acc]);          // accumulator complete
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -251,7 +341,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const uint32_t off = (uint32_t)g * 128u + (uint32_t)((j ^ (g & 7)) << 4);
     const int nutt = a.rows / a.T;
     int stage = 0; uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int tile = cta0; tile < ntiles; tile += tstep) {
       const int mt = tile / a.n_tiles;
       const int row0 = mt * TC_BM + g;
       const int b0 = row0 / a.T;
@@ -272,7 +362,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
         for (int k = 0; k < 2; ++k) { P[k] = __ldg(q0 + kb * 16 + k); Q[k] = __ldg(q1 + kb * 16 + k); }
         mbar_wait(&full[stage], phase);
-        uint8_t* sa = smem + stage * TC_STAGE_BYTES + off;
+        uint8_t* sa = smem + stage * STB + off;
         uint4 w[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) w[i] = *reinterpret_cast<const uint4*>(sa + i * 4096);
@@ -284,7 +374,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
         __syncwarp();
         if (lane == 0) mbar_arrive(&xfull[stage]);
-        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == NST) { stage = 0; phase ^= 1; }
       }
     }
   } else {
@@ -303,9 +393,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     float* bias_g = bias_s + grp * 128;
     int acc = 0; uint32_t acc_phase = 0;
     uint32_t nstore = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int tile = cta0; tile < ntiles; tile += tstep) {
       const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
-      const int row = mt * TC_BM + r_in;
+      const int row = mt * TILE_ROWS + rbase + r_in;
       const int n0 = nt * a.bn;
       if (has_bias) {
         // this group's 128 columns of the bias (chunk k, column i -> bias_g[k * CW + i]); the last named barrier of the
@@ -422,19 +512,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int j = 0; j < 8; ++j) srow[j ^ (r_in & 7)] = packed[j];
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         epi_bar(1 + grp);
-        if (issuer) tma_store_2d(buf, &mapO, n0 + c, mt * TC_BM);   // rows / columns beyond the tensor are clipped by TMA
+        if (issuer) tma_store_2d(buf, &mapO, n0 + c, mt * TILE_ROWS + rbase);   // rows / columns beyond the tensor are clipped by TMA
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0));
+        else mbar_arrive(&tempty[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();                  // the peer may still be reading its TMEM / signalling our barriers
+  else __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
   }
 }
 
@@ -451,41 +546,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #define TC2_BH_BYTES (128 * TC_BK * 4)          // half B tile: up to 128 rows
 #define TC2_STAGE_BYTES (TC_A_BYTES + TC2_BH_BYTES)
 #define TC2_SMEM_BYTES (TC2_STAGES * TC2_STAGE_BYTES + 1024 + 256)
-
-__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tc_commit_2sm(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
-}
-template <int KIND_BF16>
-__device__ __forceinline__ void tc_mma_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  if (KIND_BF16) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-  } else {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-  }
-}
 
 template <int KIND_BF16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
@@ -776,6 +836,9 @@ typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void
                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeFn g_encode = nullptr;
 static int g_num_sms = 0;
+static int g_pf_dist = 0;        // L2 prefetch distance (k-blocks) of the A operand; SGB200_TC_PREFETCH overrides, 0 = off
+static int g_pf_all = 0;         // SGB200_TC_PREFETCH_ALL=1: also for multi-tap layers (their A re-reads hit L2 anyway)
+static int g_pair_bf16 = 0;      // SGB200_TC_PAIR_BF16: bf16 contractions on CTA pairs (cta_group::2): 1 long-K only, 2 all
 static int g_use_256 = 0;        // 1: 256 x 256 tiles for long-K contractions (measured: no gain, kept for experiments)
 static int g_use_pair = 0;       // 1: 2-CTA (cta_group::2) kernel for tiles with BN >= 64
 
@@ -796,6 +859,7 @@ static int tc_init() {
   SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+  SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<1, 1, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES));
   SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc256_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC3_SMEM_BYTES));
   {
@@ -806,6 +870,9 @@ static int tc_init() {
     const char* e = getenv("SGB200_TC_PAIR");
     g_use_pair = e ? atoi(e) : 0;
   }
+  if (const char* e = getenv("SGB200_TC_PAIR_BF16")) g_pair_bf16 = atoi(e);
+  if (const char* e = getenv("SGB200_TC_PREFETCH")) { g_pf_dist = atoi(e); if (g_pf_dist < 0 || g_pf_dist > 64) g_pf_dist = 0; }
+  if (const char* e = getenv("SGB200_TC_PREFETCH_ALL")) g_pf_all = atoi(e) != 0;
   g_encode = (EncodeFn)fn;
   return SG_OK;
 }
@@ -852,6 +919,7 @@ int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
   t.epilogue = a.epilogue; t.T = a.T > 0 ? a.T : 1; t.t_valid = a.t_valid;
   t.m_tiles = (a.rows + TC_BM - 1) / TC_BM; t.n_tiles = a.N / bn;
   t.xf_ab = reinterpret_cast<const uint4*>(a.xf_ab); t.xf_ld = a.xf_ld; t.xf_tv = a.xf_tv;
+  t.pf_dist = (a.taps == 1 || g_pf_all) ? g_pf_dist : 0;
   if (a.xf_ab && !(a.op_bf16 && a.out_bf16 && a.taps == 1 && a.T >= TC_BM && a.rows % a.T == 0 && a.xf_ld % 8 == 0 && a.cin <= a.xf_ld &&
                    !g_use_256 && !g_use_pair)) {
     sg_set_error("sg_conv_tc: the fused pooling adjoint needs bf16 operands/output, one tap, T >= 128 (T=%d taps=%d)", a.T, a.taps);
@@ -883,6 +951,25 @@ int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
   CUtensorMap mapO;
   r = make_map(&mapO, a.out, a.out_bf16, (uint64_t)a.rows, (uint64_t)a.N, (uint64_t)a.ldo, TC_BM);
   if (r != SG_OK) return r;
+  // bf16 CTA-pair variant (cta_group::2): mode 1 = contractions with >= 16 k-blocks, 2 = every eligible one
+  if (g_pair_bf16 && a.op_bf16 && a.out_bf16 && !a.xf_ab && bn % 32 == 0 && bn >= 64 && a.rows > 256 &&
+      (g_pair_bf16 >= 2 || a.taps * t.kchunks >= 16)) {
+    CUtensorMap mapBh;
+    r = make_map(&mapBh, a.Wk, 1, (uint64_t)a.N, (uint64_t)a.taps * a.cin, (uint64_t)a.taps * a.cin, (uint32_t)(bn / 2));
+    if (r != SG_OK) return r;
+    t.m_tiles = (a.rows + 2 * TC_BM - 1) / (2 * TC_BM);
+    int pairs = t.m_tiles * t.n_tiles;
+    if (pairs > g_num_sms / 2) pairs = g_num_sms / 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(TC_MAIN_THREADS); cfg.dynamicSmemBytes = TC_SMEM_BYTES; cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    SG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, 1, 0, 1>, mapA, mapBh, mapO, t));
+    return SG_OK;
+  }
   int grid = t.m_tiles * t.n_tiles;
   if (grid > g_num_sms) grid = g_num_sms;
   if (a.xf_ab) conv_tc_kernel<1, 1, 1><<<grid, TC_XF_THREADS, TC_SMEM_BYTES, st>>>(mapA, mapB, mapO, t);
