@@ -105,6 +105,11 @@ __device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
   asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 // split form: several loads in flight, one wait (the registers must not be read before tc_ld_wait)
 __device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, float (&v)[32]) {
   asm volatile(
@@ -140,6 +145,7 @@ struct TcArgs {
   // reads it.  xf_ab: [rows / T][xf_ld / 2] x {alpha' pair, beta pair} (bf16x2 each) per utterance and channel pair.
   const uint4* xf_ab; int xf_ld, xf_tv;
   int pf_dist;                     // L2 prefetch distance of the A operand in k-blocks (0 = off)
+  int issue_mode;                  // MMA issuer: 0 single-lane region, 1 warp-convergent loop with an elected lane
 };
 
 // ---- cluster / cta_group::2 helpers ------------------------------------------------------------
@@ -300,8 +306,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    // (a warp-convergent loop with an elected issuing lane was measured: fewer uniform-datapath instructions per k-block,
-    // but no faster - the issue loop is not what limits the tensor pipe here)
+    // issue_mode 1: the whole warp runs the loop convergently (descriptors and counters stay in uniform registers, the
+    // four tcgen05.mma of a k-block issue back to back) and one elected lane issues; issue_mode 0: a single-lane region, where
+    // ptxas re-derives uniformity for every tcgen05.mma operand (ELECT + R2UR.BROADCAST per instruction, ~70 dependent
+    // instructions per k-block).
+    if (a.issue_mode != 0 && rank == 0) {
+      const uint32_t fmt = KIND_BF16 ? 1u : 2u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(a.bn >> 3) << 17) | ((uint32_t)(TILE_ROWS >> 4) << 24);
+      const uint32_t smem_base = smem_u32(smem);
+      const bool leader = elect_one();
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = cta0; tile < ntiles; tile += tstep) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)acc * TC_MAX_BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          const uint32_t sa = smem_base + (uint32_t)stage * STB;
+          const uint64_t da = make_desc(sa), db = make_desc(sa + TC_A_BYTES);
+          mbar_wait(XFORM ? &xfull[stage] : &full[stage], phase);
+          tc_fence_after();
+          if (leader) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (PAIR) tc_mma_2sm<KIND_BF16>(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+              else tc_mma<KIND_BF16>(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            }
+            if (PAIR) tc_commit_2sm(&empty[stage]); else tc_commit(&empty[stage]);
+          }
+          __syncwarp();
+          if (++stage == NST) { stage = 0; phase ^= 1; }
+        }
+        if (leader) { if (PAIR) tc_commit_2sm(&tfull[acc]); else tc_commit(&tfull[acc]); }
+        __syncwarp();
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    } else
     if (lane == 0 && rank == 0) {
       // instruction descriptor: D=f32 [4,6)=1, A/B format [7,10)/[10,13) (tf32=2, bf16=1), K-major both,
       // N>>3 in [17,23), M>>4 in [24,29)
@@ -838,7 +878,8 @@ static EncodeFn g_encode = nullptr;
 static int g_num_sms = 0;
 static int g_pf_dist = 0;        // L2 prefetch distance (k-blocks) of the A operand; SGB200_TC_PREFETCH overrides, 0 = off
 static int g_pf_all = 0;         // SGB200_TC_PREFETCH_ALL=1: also for multi-tap layers (their A re-reads hit L2 anyway)
-static int g_pair_bf16 = 0;      // SGB200_TC_PAIR_BF16: bf16 contractions on CTA pairs (cta_group::2): 1 long-K only, 2 all
+static int g_issue_mode = 1;     // SGB200_TC_ISSUE: see TcArgs::issue_mode
+static int g_pair_bf16 = 1;      // SGB200_TC_PAIR_BF16: bf16 contractions on CTA pairs (cta_group::2): 1 long-K only, 2 all
 static int g_use_256 = 0;        // 1: 256 x 256 tiles for long-K contractions (measured: no gain, kept for experiments)
 static int g_use_pair = 0;       // 1: 2-CTA (cta_group::2) kernel for tiles with BN >= 64
 
@@ -871,6 +912,7 @@ static int tc_init() {
     g_use_pair = e ? atoi(e) : 0;
   }
   if (const char* e = getenv("SGB200_TC_PAIR_BF16")) g_pair_bf16 = atoi(e);
+  if (const char* e = getenv("SGB200_TC_ISSUE")) g_issue_mode = atoi(e);
   if (const char* e = getenv("SGB200_TC_PREFETCH")) { g_pf_dist = atoi(e); if (g_pf_dist < 0 || g_pf_dist > 64) g_pf_dist = 0; }
   if (const char* e = getenv("SGB200_TC_PREFETCH_ALL")) g_pf_all = atoi(e) != 0;
   g_encode = (EncodeFn)fn;
@@ -920,6 +962,7 @@ int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
   t.m_tiles = (a.rows + TC_BM - 1) / TC_BM; t.n_tiles = a.N / bn;
   t.xf_ab = reinterpret_cast<const uint4*>(a.xf_ab); t.xf_ld = a.xf_ld; t.xf_tv = a.xf_tv;
   t.pf_dist = (a.taps == 1 || g_pf_all) ? g_pf_dist : 0;
+  t.issue_mode = g_issue_mode;
   if (a.xf_ab && !(a.op_bf16 && a.out_bf16 && a.taps == 1 && a.T >= TC_BM && a.rows % a.T == 0 && a.xf_ld % 8 == 0 && a.cin <= a.xf_ld &&
                    !g_use_256 && !g_use_pair)) {
     sg_set_error("sg_conv_tc: the fused pooling adjoint needs bf16 operands/output, one tap, T >= 128 (T=%d taps=%d)", a.T, a.taps);
