@@ -45,6 +45,18 @@ PRECISION_NOTE = {
 TDNN = [(30, 512, 5, 1), (512, 512, 5, 2), (512, 512, 7, 3), (512, 512, 1, 1), (512, 1500, 1, 1)]
 
 
+def tdnn_valid_frames(m: int):
+    t, out = m, []
+    for _, _, k, d in TDNN:
+        t -= (k - 1) * d
+        out.append(t)
+    return out
+
+
+def peaks_hbm_gbs() -> float:
+    return measured_peaks()[0].get("hbm_gbs", 6548.5)
+
+
 def tdnn_flops_per_utt(m: int) -> float:
     """Algorithmic FLOPs of the TDNN forward + dgrad for one utterance-iteration:
     2 * sum_l 2*C_in*k*C_out*T_l (valid frames only, no wgrad, unpadded channels)."""
@@ -504,11 +516,26 @@ def main():
     prof = eng.profile_read()
     eng.profile(False)
     tot_prof = sum(v[0] for v in prof.values())
+    # The roofline kernel is the plain contraction (conv_tc_kernel: 5 forward + 4 or 5 dgrad launches per pass).  With
+    # SG_OPT_POOL_FUSION the layer-5 dgrad launch also applies the statistics-pooling adjoint to its A tiles (HBM-side
+    # work of the former pool_bwd pass); it is timed in its own category and reported beside the plain launches.
+    fused_ms, fused_launches = prof.get("tdnn_dgrad5_pool", (0.0, 0))
     tdnn_ms = prof["tdnn_fwd"][0] + prof["tdnn_dgrad"][0]
     tdnn_launches = prof["tdnn_fwd"][1] + prof["tdnn_dgrad"][1]
     passes = iters + 1
-    flops = tdnn_flops_per_utt(m) * B * iters + 0.5 * tdnn_flops_per_utt(m) * B     # + forward of the evaluation pass
+    flops_all = tdnn_flops_per_utt(m) * B * iters + 0.5 * tdnn_flops_per_utt(m) * B   # + forward of the evaluation pass
+    flops_l5d = 2.0 * TDNN[4][0] * TDNN[4][1] * TDNN[4][2] * tdnn_valid_frames(m)[4] * B * iters if fused_launches else 0.0
+    flops = flops_all - flops_l5d
     achieved = flops / (tdnn_ms / 1000.0) / 1e12
+    fused = None
+    if fused_launches:
+        hbm = peaks_hbm_gbs()
+        fused_bytes = (m * B * 1536 * 2 + m * B * 512 * 2) * iters                # r5 read once + dA4 written, bf16
+        fused = {"kernel": "conv_tc_kernel<XFORM>: layer-5 dgrad + statistics-pooling adjoint on the staged tiles",
+                 "launches": fused_launches, "avg_launch_ms": fused_ms / fused_launches,
+                 "tflops": flops_l5d / (fused_ms / 1000.0) / 1e12,
+                 "hbm_gbs": fused_bytes / (fused_ms / 1000.0) / 1e9, "hbm_frac": fused_bytes / (fused_ms / 1000.0) / 1e9 / hbm,
+                 "note": "replaces pool_bwd (read r5, write dA5: 1.9 GB) + the plain layer-5 dgrad (read dA5): -0.09 ms per pass net"}
     peaks, peak_src = measured_peaks()
     if args.precision == "bf16":
         peak, peak_note = peaks["bf16_tflops_sustained"], f"bf16 sustained, {peak_src}"
@@ -541,13 +568,17 @@ def main():
         "e2e": {"value": e2e_value, "unit": "utt-iter/s", "h2d_bytes_per_step": B * N * 4 + B * 8,
                 "d2h_bytes_per_step": B * N * 4 + B * 8, "ms_per_step": e2e_s * 1000.0,
                 "api": "speakerguard_b200.attack.PGD(model).attack(x, y) with pinned host buffers"},
-        "roofline": {"bound": "tensor", "kernel": "TDNN conv-as-GEMM (forward + dgrad launches)", "achieved": achieved,
+        "roofline": {"bound": "tensor", "kernel": "TDNN conv-as-GEMM, conv_tc_kernel (plain forward + dgrad launches; the layer-5 dgrad with the fused pooling adjoint is listed under fused_l5_dgrad and included in all_tdnn_launches)", "achieved": achieved,
                      "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                      "traffic_note": "dram__bytes_read+write per launch, mean over the TDNN launches of one pass (ncu, profiles/conv_tc_traffic.json)",
                      "peak_source": peak_note,
                      "launches": tdnn_launches, "avg_launch_ms": tdnn_ms / max(tdnn_launches, 1),
                      "algorithmic_flops_per_utt_iter": tdnn_flops_per_utt(m),
-                     "share_of_step": tdnn_ms / tot_prof if tot_prof else None},
+                     "share_of_step": tdnn_ms / tot_prof if tot_prof else None,
+                     "all_tdnn_launches": {"tflops": flops_all / ((tdnn_ms + fused_ms) / 1000.0) / 1e12,
+                                           "frac": flops_all / ((tdnn_ms + fused_ms) / 1000.0) / 1e12 / peak,
+                                           "share_of_step": (tdnn_ms + fused_ms) / tot_prof if tot_prof else None},
+                     "fused_l5_dgrad": fused},
         "kernel_ms_per_step": {k: round(v[0], 3) for k, v in prof.items()},
         "attack_metrics": metrics,
     }

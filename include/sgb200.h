@@ -356,7 +356,8 @@ int sg_debug_conv(sg_handle* h, int precision, const float* A, int lda, const fl
  * uses this for the per-kernel share of a step and for the roofline of the dominant kernel. */
 enum { SG_PROF_MFCC_FWD = 0, SG_PROF_MFCC_BWD, SG_PROF_CMVN, SG_PROF_TDNN_FWD, SG_PROF_TDNN_BWD,
        SG_PROF_POOL, SG_PROF_HEAD_GEMM, SG_PROF_HEAD, SG_PROF_LOSS, SG_PROF_STEP, SG_PROF_AUDIONET,
-       SG_PROF_CW2, SG_PROF_IV_GEMM, SG_PROF_IV, SG_PROF_COUNT };
+       SG_PROF_CW2, SG_PROF_IV_GEMM, SG_PROF_IV,
+       SG_PROF_TDNN_BWD_POOL /* layer-5 dgrad with the pooling adjoint fused in (SG_OPT_POOL_FUSION) */, SG_PROF_COUNT };
 int sg_profile_enable(sg_handle* h, int enable);
 int sg_profile_read(sg_handle* h, int category, double* total_ms, long long* launches);
 const char* sg_profile_name(int category);

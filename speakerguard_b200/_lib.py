@@ -17,7 +17,7 @@ PREC_FP32, PREC_TF32, PREC_BF16 = 0, 1, 2
 DITHER_OFF, DITHER_TENSOR, DITHER_PHILOX = 0, 1, 2
 OPT_POOL_FUSION, OPT_FEAT_STASH = 1, 2
 LOSS_CE, LOSS_MARGIN = 0, 1
-PROF_COUNT = 14
+PROF_COUNT = 15
 IV_STAGE_POST, IV_STAGE_STATS, IV_STAGE_IVECTOR = 0, 1, 2
 TASK_CSI, TASK_SV, TASK_OSI = 0, 1, 2
 TASKS = {"CSI": TASK_CSI, "SV": TASK_SV, "OSI": TASK_OSI}

@@ -34,7 +34,7 @@ static const int kCout[5] = {512, 512, 512, 512, 1500};
 static const int kCoutP[5] = {512, 512, 512, 512, SG_C5P};
 
 static const char* kProfNames[SG_PROF_COUNT] = {
-    "mfcc_fwd", "mfcc_bwd", "cmvn", "tdnn_fwd", "tdnn_dgrad", "pool", "head_gemm", "head", "loss", "step", "audionet", "cw2", "iv_gemm", "iv"};
+    "mfcc_fwd", "mfcc_bwd", "cmvn", "tdnn_fwd", "tdnn_dgrad", "pool", "head_gemm", "head", "loss", "step", "audionet", "cw2", "iv_gemm", "iv", "tdnn_dgrad5_pool"};
 
 int sg_dev_upload(sg_handle* h, float** dst, const std::vector<float>& src) {
   SG_CUDA_CHECK(cudaMalloc((void**)dst, src.size() * sizeof(float)));
@@ -465,7 +465,7 @@ static int embed_bwd(sg_handle* h, const float* demb, int B, int T, const XvWs& 
       a.out = out; a.ldo = kCinP[l]; a.N = kCinP[l];
       a.epilogue = SG_EPI_MASK; a.mask = w.r[l - 1]; a.ldmask = kCoutP[l - 1]; a.t_valid = tv[l - 1];
       if (h->precision != SG_PREC_FP32) { a.bits_in = w.bits[l - 1]; a.ldbits = SG_C1 / 32; }
-      SG_TRY(sg_run_conv(h, a, true, SG_PROF_TDNN_BWD, st));
+      SG_TRY(sg_run_conv(h, a, true, (l == 4 && fuse_pool) ? SG_PROF_TDNN_BWD_POOL : SG_PROF_TDNN_BWD, st));
       gin = out;
     } else {
       a.out = dfeat; a.ldo = SG_FLD; a.N = SG_FLD; a.epilogue = SG_EPI_NONE;
