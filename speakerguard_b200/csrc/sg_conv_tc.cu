@@ -23,7 +23,8 @@
 #define TC_B_BYTES (TC_MAX_BN * TC_BK * 4)      // 32 KB
 #define TC_STAGE_BYTES (TC_A_BYTES + TC_B_BYTES)
 #define TC_STG_BYTES (TC_BM * 32 * 4)            // 16 KB epilogue staging box (128 rows x 32 fp32), x2
-#define TC_SMEM_BYTES (TC_STAGES * TC_STAGE_BYTES + 2 * TC_STG_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*bias*/)
+#define TC_MAX_STAGES 12
+#define TC_SMEM_BYTES (TC_STAGES * TC_STAGE_BYTES + 2 * TC_STG_BYTES + 1024 /*align*/ + 384 /*barriers*/ + 1024 /*bias*/)
 #define TC_THREADS 192                // experimental variants: TMA warp, MMA warp, 4 epilogue warps
 #define TC_MAIN_THREADS 320           // main kernel: TMA warp, MMA warp, 2 x 4 epilogue warps
 #define TC_XF_THREADS (TC_MAIN_THREADS + 256)   // XFORM variant: + 8 warps that rewrite the staged A tile in place
@@ -146,6 +147,7 @@ struct TcArgs {
   const uint4* xf_ab; int xf_ld, xf_tv;
   int pf_dist;                     // L2 prefetch distance of the A operand in k-blocks (0 = off)
   int issue_mode;                  // MMA issuer: 0 single-lane region, 1 warp-convergent loop with an elected lane
+  int nst, stb;                    // pipeline ring: stages and bytes per stage (main kernel)
 };
 
 // ---- cluster / cta_group::2 helpers ------------------------------------------------------------
@@ -215,19 +217,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   // for the same 4.2 MFLOP (the single-CTA kernel sits at the L2 -> SM throughput cap: ~620 clk per k-block against 512
   // for the tensor pipe), and the smaller stage leaves room for 6 pipeline stages.  Rank 0 issues the MMAs; both CTAs
   // run TMA producers (signalling rank 0's full barriers) and epilogues (own 128 TMEM lanes); commits are multicast.
-  constexpr int NST = PAIR ? 6 : TC_STAGES;
-  constexpr uint32_t STB = PAIR ? (TC_A_BYTES + TC_B_BYTES / 2) : TC_STAGE_BYTES;
-  static_assert(NST * STB == TC_STAGES * TC_STAGE_BYTES, "both layouts use the same 192 KB ring");
+  // The ring geometry is chosen by the host from the B box: stage = 16 KB of A + this CTA's B rows x 128 B, as many
+  // stages as fit in the 192 KB ring (4 for a 256-row B box, 6 for a pair's 128 rows, 9 for the 32-column layer-1 dgrad,
+  // whose short k-blocks are otherwise bound by the TMA round trip).
   static_assert(!(PAIR && XFORM), "the fused pooling adjoint is a single-CTA variant");
-  uint8_t* stg = smem + NST * STB;                                   // 2 x 16 KB, 1024-byte aligned
+  const int NST = a.nst;
+  const uint32_t STB = (uint32_t)a.stb;
+  uint8_t* stg = smem + TC_STAGES * TC_STAGE_BYTES;                  // 2 x 16 KB, 1024-byte aligned
   uint64_t* bars = (uint64_t*)(stg + 2 * TC_STG_BYTES);
-  uint64_t* full = bars;                       // [NST]   (PAIR: rank 0's copy is the live one)
-  uint64_t* empty = bars + NST;                // [NST]   per CTA
-  uint64_t* tfull = bars + 2 * NST;            // [2]     per CTA
-  uint64_t* tempty = bars + 2 * NST + 2;       // [2]     (PAIR: rank 0's copy is the live one)
-  uint64_t* xfull = bars + 2 * NST + 4;        // [NST] (XFORM: tile transformed, ready for the MMA)
-  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * NST + 4);
-  float* bias_s = (float*)(bars + 32);         // [2 epilogue groups][128]: the bias of the current tile's columns
+  uint64_t* full = bars;                                // [TC_MAX_STAGES]   (PAIR: rank 0's copy is the live one)
+  uint64_t* empty = bars + TC_MAX_STAGES;               // [TC_MAX_STAGES]   per CTA
+  uint64_t* tfull = bars + 2 * TC_MAX_STAGES;           // [2]     per CTA
+  uint64_t* tempty = bars + 2 * TC_MAX_STAGES + 2;      // [2]     (PAIR: rank 0's copy is the live one)
+  uint64_t* xfull = bars + 2 * TC_MAX_STAGES + 4;       // [TC_MAX_STAGES] (XFORM: tile transformed, ready for the MMA)
+  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * TC_MAX_STAGES + 4);
+  float* bias_s = (float*)(bars + 48);                  // [2 epilogue groups][128]: the bias of the current tile's columns
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = a.taps * a.kchunks;
@@ -880,6 +884,7 @@ static EncodeFn g_encode = nullptr;
 static int g_num_sms = 0;
 static int g_pf_dist = 0;        // L2 prefetch distance (k-blocks) of the A operand; SGB200_TC_PREFETCH overrides, 0 = off
 static int g_pf_all = 0;         // SGB200_TC_PREFETCH_ALL=1: also for multi-tap layers (their A re-reads hit L2 anyway)
+static int g_deep_ring = 0;      // SGB200_TC_DEEP_RING=1: as many stages as fit when the B box is small (measured: no gain)
 static int g_issue_mode = 1;     // SGB200_TC_ISSUE: see TcArgs::issue_mode
 static int g_pair_bf16 = 2;      // SGB200_TC_PAIR_BF16: bf16 contractions on CTA pairs (cta_group::2): 1 long-K only, 2 all
 static int g_use_256 = 0;        // 1: 256 x 256 tiles for long-K contractions (measured: no gain, kept for experiments)
@@ -915,6 +920,7 @@ static int tc_init() {
   }
   if (const char* e = getenv("SGB200_TC_PAIR_BF16")) g_pair_bf16 = atoi(e);
   if (const char* e = getenv("SGB200_TC_ISSUE")) g_issue_mode = atoi(e);
+  if (const char* e = getenv("SGB200_TC_DEEP_RING")) g_deep_ring = atoi(e);
   if (const char* e = getenv("SGB200_TC_PREFETCH")) { g_pf_dist = atoi(e); if (g_pf_dist < 0 || g_pf_dist > 64) g_pf_dist = 0; }
   if (const char* e = getenv("SGB200_TC_PREFETCH_ALL")) g_pf_all = atoi(e) != 0;
   g_encode = (EncodeFn)fn;
@@ -965,6 +971,9 @@ int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
   t.xf_ab = reinterpret_cast<const uint4*>(a.xf_ab); t.xf_ld = a.xf_ld; t.xf_tv = a.xf_tv;
   t.pf_dist = (a.taps == 1 || g_pf_all) ? g_pf_dist : 0;
   t.issue_mode = g_issue_mode;
+  t.stb = TC_A_BYTES + bn * TC_BK * 4; t.nst = (TC_STAGES * TC_STAGE_BYTES) / t.stb;
+  if (t.nst > TC_MAX_STAGES) t.nst = TC_MAX_STAGES;
+  if (!g_deep_ring && t.nst > TC_STAGES) t.nst = TC_STAGES;
   if (a.xf_ab && !(a.op_bf16 && a.out_bf16 && a.taps == 1 && a.T >= TC_BM && a.rows % a.T == 0 && a.xf_ld % 8 == 0 && a.cin <= a.xf_ld &&
                    !g_use_256 && !g_use_pair)) {
     sg_set_error("sg_conv_tc: the fused pooling adjoint needs bf16 operands/output, one tap, T >= 128 (T=%d taps=%d)", a.T, a.taps);
@@ -1003,6 +1012,9 @@ int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
     r = make_map(&mapBh, a.Wk, 1, (uint64_t)a.N, (uint64_t)a.taps * a.cin, (uint64_t)a.taps * a.cin, (uint32_t)(bn / 2));
     if (r != SG_OK) return r;
     t.m_tiles = (a.rows + 2 * TC_BM - 1) / (2 * TC_BM);
+    t.stb = TC_A_BYTES + (bn / 2) * TC_BK * 4; t.nst = (TC_STAGES * TC_STAGE_BYTES) / t.stb;
+    if (t.nst > TC_MAX_STAGES) t.nst = TC_MAX_STAGES;
+    if (!g_deep_ring && t.nst > 6) t.nst = 6;
     int pairs = t.m_tiles * t.n_tiles;
     if (pairs > g_num_sms / 2) pairs = g_num_sms / 2;
     cudaLaunchConfig_t cfg;
