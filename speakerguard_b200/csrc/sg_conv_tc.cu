@@ -25,7 +25,6 @@
 #define TC_STG_BYTES (TC_BM * 32 * 4)            // 16 KB epilogue staging box (128 rows x 32 fp32), x2
 #define TC_MAX_STAGES 12
 #define TC_SMEM_BYTES (TC_STAGES * TC_STAGE_BYTES + 2 * TC_STG_BYTES + 1024 /*align*/ + 384 /*barriers*/ + 1024 /*bias*/)
-#define TC_THREADS 192                // experimental variants: TMA warp, MMA warp, 4 epilogue warps
 #define TC_MAIN_THREADS 320           // main kernel: TMA warp, MMA warp, 2 x 4 epilogue warps
 #define TC_XF_THREADS (TC_MAIN_THREADS + 256)   // XFORM variant: + 8 warps that rewrite the staged A tile in place
 
@@ -334,7 +333,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           tc_fence_after();
           if (leader) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < 4; ++k) {      // (two N/2 MMAs per k-step on alternating column halves were measured: no gain)
               if (PAIR) tc_mma_2sm<KIND_BF16>(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
               else tc_mma<KIND_BF16>(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
             }
@@ -580,301 +579,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 }
 
 
-// =================================================================================================
-// 2-CTA variant (cta_group::2): a CTA pair on one TPC computes a 256 x BN tile.  Each CTA stages its own
-// 128 rows of A and HALF of the B tile (BN/2 weight rows), so per k-block a pair moves 64 KB from L2
-// for 4.2 MFLOP instead of 96 KB: the fp32-operand kernel above is L2-bandwidth bound
-// (43.7 FLOP/B x ~12 TB/s ~ 520 TFLOP/s), the pair raises the intensity to 65.5 FLOP/B.
-// Rank 0 issues tcgen05.mma.cta_group::2 (M = 256); both CTAs run TMA producers (signalling rank 0's
-// full barrier) and epilogues (each drains its own 128 TMEM lanes); commits are multicast to both.
-// =================================================================================================
-#define TC2_STAGES 6
-#define TC2_BH_BYTES (128 * TC_BK * 4)          // half B tile: up to 128 rows
-#define TC2_STAGE_BYTES (TC_A_BYTES + TC2_BH_BYTES)
-#define TC2_SMEM_BYTES (TC2_STAGES * TC2_STAGE_BYTES + 1024 + 256)
-
-template <int KIND_BF16>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
-conv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = (uint64_t*)(smem + TC2_STAGES * TC2_STAGE_BYTES);
-  uint64_t* full = bars;                          // [S]  (rank 0's copy is the live one)
-  uint64_t* empty = bars + TC2_STAGES;            // [S]  per CTA
-  uint64_t* tfull = bars + 2 * TC2_STAGES;        // [2]  per CTA
-  uint64_t* tempty = bars + 2 * TC2_STAGES + 2;   // [2]  (rank 0's copy is the live one)
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TC2_STAGES + 4);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_rank();
-  const int nkb = a.taps * a.kchunks;
-  const int ntiles = a.m_tiles * a.n_tiles;        // m_tiles counts 256-row pair tiles here
-  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-  const int bh = a.bn >> 1;                        // B rows staged by each CTA
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < TC2_STAGES; ++s) { mbar_init(&full[s], 2); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  cluster_sync_all();                              // barriers of both CTAs initialised before any remote arrive / TMA signal
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      const uint32_t tx_pair = 2u * (TC_A_BYTES + (uint32_t)bh * TC_BK * 4);
-      for (int tile = pair; tile < ntiles; tile += npairs) {
-        const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
-        const int p0 = mt * 256 + (int)rank * TC_BM, n0 = nt * a.bn + (int)rank * bh;
-        for (int kb = 0; kb < nkb; ++kb) {
-          const int tap = kb / a.kchunks, kc = kb - tap * a.kchunks;
-          mbar_wait(&empty[stage], phase ^ 1);
-          const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
-          if (rank == 0) mbar_expect_tx(&full[stage], tx_pair);
-          else mbar_arrive_cluster(lead_full);
-          uint8_t* sa = smem + stage * TC2_STAGE_BYTES;
-          tma_load_2d_2sm(sa, &mapA, lead_full, kc * TC_BK, p0 + tap * a.tap_step);
-          tma_load_2d_2sm(sa + TC_A_BYTES, &mapB, lead_full, kb * TC_BK, n0);
-          if (++stage == TC2_STAGES) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
-      const uint32_t fmt = KIND_BF16 ? 1u : 2u;
-      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(a.bn >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-      int stage = 0; uint32_t phase = 0;
-      int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = pair; tile < ntiles; tile += npairs) {
-        mbar_wait(&tempty[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)acc * TC_MAX_BN;
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * TC2_STAGE_BYTES);
-          const uint64_t da = make_desc(sa), db = make_desc(sa + TC_A_BYTES);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) tc_mma_2sm<KIND_BF16>(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-          tc_commit_2sm(&empty[stage]);
-          if (++stage == TC2_STAGES) { stage = 0; phase ^= 1; }
-        }
-        tc_commit_2sm(&tfull[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      }
-    }
-  } else {
-    const int q = warp & 3;
-    int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = pair; tile < ntiles; tile += npairs) {
-      const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
-      const int row = mt * 256 + (int)rank * TC_BM + q * 32 + lane;
-      const int n0 = nt * a.bn;
-      mbar_wait(&tfull[acc], acc_phase);
-      tc_fence_after();
-      const bool row_in = row < a.rows;
-      bool row_ok = row_in;
-      if (a.epilogue == SG_EPI_MASK) row_ok = row_in && ((row % a.T) < a.t_valid);
-      for (int c = 0; c < a.bn; c += 32) {
-        float v[32];
-        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TC_MAX_BN + c), v);
-        const int col = n0 + c;
-        if (a.epilogue == SG_EPI_BIAS || a.epilogue == SG_EPI_BIAS_RELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += __ldg(a.bias + col + j);
-          if (a.epilogue == SG_EPI_BIAS_RELU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-          }
-        } else if (a.epilogue == SG_EPI_MASK) {
-          if (row_ok) {
-            const float4* mp = reinterpret_cast<const float4*>(a.mask + (size_t)row * a.ldmask + col);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 m4 = __ldg(mp + j);
-              v[4 * j + 0] = m4.x > 0.f ? v[4 * j + 0] : 0.f;
-              v[4 * j + 1] = m4.y > 0.f ? v[4 * j + 1] : 0.f;
-              v[4 * j + 2] = m4.z > 0.f ? v[4 * j + 2] : 0.f;
-              v[4 * j + 3] = m4.w > 0.f ? v[4 * j + 3] : 0.f;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0.f;
-          }
-        }
-        if (row_in) {
-          float4* op = reinterpret_cast<float4*>(a.out + (size_t)row * a.ldo + col);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0));
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
-  }
-  tc_fence_before();
-  cluster_sync_all();                              // the peer may still be reading its TMEM / signalling our barriers
-  if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
-  }
-}
-
-
-// =================================================================================================
-// 256 x 256 tile variant for the long-K layers.  ncu on the 128 x 256 kernel shows nothing saturated
-// except the shared-memory operand path (84 %) with the tensor pipe at 53 %: with fp32 operands a
-// k-block is 48 KB for 2.1 MFLOP and only 4 stages (192 KB) fit, so TMA latency (~3000 cycles under
-// load) is not covered (Little: 96 B/clk x 3000 clk = 288 KB in flight needed).  Two M = 128 MMAs that
-// share one B tile move 64 KB per 4.2 MFLOP: 1.5x fewer bytes per FLOP from L2 and through the
-// pipeline.  The two accumulators fill TMEM (2 x 256 columns), so the epilogue (8 warps, one group
-// of 4 per accumulator) is not overlapped with the next tile's MMAs: used only when K is long enough
-// (>= 24 k-blocks) for that to cost < 15 %.
-// =================================================================================================
-#define TC3_STAGES 3
-#define TC3_STAGE_BYTES (2 * TC_A_BYTES + TC_B_BYTES)          // 64 KB
-#define TC3_SMEM_BYTES (TC3_STAGES * TC3_STAGE_BYTES + 1024 + 256)
-#define TC3_THREADS 320
-
-template <int KIND_BF16>
-__global__ void __launch_bounds__(TC3_THREADS, 1)
-conv_tc256_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, TcArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = (uint64_t*)(smem + TC3_STAGES * TC3_STAGE_BYTES);
-  uint64_t* full = bars;                       // [3]
-  uint64_t* empty = bars + TC3_STAGES;         // [3]
-  uint64_t* tfull = bars + 2 * TC3_STAGES;     // [1]
-  uint64_t* tempty = tfull + 1;                // [1]
-  uint32_t* tmem_slot = (uint32_t*)(tempty + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nkb = a.taps * a.kchunks;
-  const int ntiles = a.m_tiles * a.n_tiles;    // m_tiles counts 256-row tiles
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < TC3_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(tfull, 1); mbar_init(tempty, 8);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
-        const int p0 = mt * 256, n0 = nt * TC_MAX_BN;
-        for (int kb = 0; kb < nkb; ++kb) {
-          const int tap = kb / a.kchunks, kc = kb - tap * a.kchunks;
-          mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], TC3_STAGE_BYTES);
-          uint8_t* sa = smem + stage * TC3_STAGE_BYTES;
-          tma_load_2d(sa, &mapA, &full[stage], kc * TC_BK, p0 + tap * a.tap_step);              // 256 rows: A0 | A1
-          tma_load_2d(sa + 2 * TC_A_BYTES, &mapB, &full[stage], kb * TC_BK, n0);
-          if (++stage == TC3_STAGES) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t fmt = KIND_BF16 ? 1u : 2u;
-      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(TC_MAX_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      int stage = 0; uint32_t phase = 0, tphase = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        mbar_wait(tempty, tphase ^ 1);
-        tc_fence_after();
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * TC3_STAGE_BYTES);
-          const uint64_t da0 = make_desc(sa), da1 = make_desc(sa + TC_A_BYTES), db = make_desc(sa + 2 * TC_A_BYTES);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            tc_mma<KIND_BF16>(tmem_base, da0 + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-            tc_mma<KIND_BF16>(tmem_base + TC_MAX_BN, da1 + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-          }
-          tc_commit(&empty[stage]);
-          if (++stage == TC3_STAGES) { stage = 0; phase ^= 1; }
-        }
-        tc_commit(tfull);
-        tphase ^= 1;
-      }
-    }
-  } else {
-    const int q = warp & 3, g = (warp - 2) >> 2;           // TMEM lane quarter, accumulator (row half)
-    uint32_t tphase = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
-      const int row = mt * 256 + g * TC_BM + q * 32 + lane;
-      const int n0 = nt * TC_MAX_BN;
-      mbar_wait(tfull, tphase);
-      tc_fence_after();
-      const bool row_in = row < a.rows;
-      bool row_ok = row_in;
-      if (a.epilogue == SG_EPI_MASK) row_ok = row_in && ((row % a.T) < a.t_valid);
-      for (int c = 0; c < TC_MAX_BN; c += 32) {
-        float v[32];
-        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * TC_MAX_BN + c), v);
-        const int col = n0 + c;
-        if (a.epilogue == SG_EPI_BIAS || a.epilogue == SG_EPI_BIAS_RELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += __ldg(a.bias + col + j);
-          if (a.epilogue == SG_EPI_BIAS_RELU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-          }
-        } else if (a.epilogue == SG_EPI_MASK) {
-          if (row_ok) {
-            const float4* mp = reinterpret_cast<const float4*>(a.mask + (size_t)row * a.ldmask + col);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 m4 = __ldg(mp + j);
-              v[4 * j + 0] = m4.x > 0.f ? v[4 * j + 0] : 0.f;
-              v[4 * j + 1] = m4.y > 0.f ? v[4 * j + 1] : 0.f;
-              v[4 * j + 2] = m4.z > 0.f ? v[4 * j + 2] : 0.f;
-              v[4 * j + 3] = m4.w > 0.f ? v[4 * j + 3] : 0.f;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0.f;
-          }
-        }
-        if (row_in) {
-          float4* op = reinterpret_cast<float4*>(a.out + (size_t)row * a.ldo + col);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty);
-      tphase ^= 1;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
-  }
-}
+// (Two earlier experimental kernels lived here and were removed after the CTA-pair template variant above superseded them:
+// a TF32-only cta_group::2 kernel whose per-k-block remote mbarrier arrive cost a GPU-scope membar each time (-40 %), and a
+// single-CTA 256 x 256 tile kernel whose two accumulators filled TMEM so that the epilogue could not overlap the next
+// tile's MMAs (+-0 %).  DESIGN.md section 3 keeps the measurements.)
 
 // ---- host ---------------------------------------------------------------------------------------
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -887,8 +595,6 @@ static int g_pf_all = 0;         // SGB200_TC_PREFETCH_ALL=1: also for multi-tap
 static int g_deep_ring = 0;      // SGB200_TC_DEEP_RING=1: as many stages as fit when the B box is small (measured: no gain)
 static int g_issue_mode = 1;     // SGB200_TC_ISSUE: see TcArgs::issue_mode
 static int g_pair_bf16 = 2;      // SGB200_TC_PAIR_BF16: bf16 contractions on CTA pairs (cta_group::2): 1 long-K only, 2 all
-static int g_use_256 = 0;        // 1: 256 x 256 tiles for long-K contractions (measured: no gain, kept for experiments)
-static int g_use_pair = 0;       // 1: 2-CTA (cta_group::2) kernel for tiles with BN >= 64
 
 static int tc_init() {
   if (g_encode) return SG_OK;
@@ -908,16 +614,6 @@ static int tc_init() {
   SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<1, 1, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-  SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES));
-  SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc256_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC3_SMEM_BYTES));
-  {
-    const char* e = getenv("SGB200_TC_256");
-    g_use_256 = e ? atoi(e) : 0;
-  }
-  {
-    const char* e = getenv("SGB200_TC_PAIR");
-    g_use_pair = e ? atoi(e) : 0;
-  }
   if (const char* e = getenv("SGB200_TC_PAIR_BF16")) g_pair_bf16 = atoi(e);
   if (const char* e = getenv("SGB200_TC_ISSUE")) g_issue_mode = atoi(e);
   if (const char* e = getenv("SGB200_TC_DEEP_RING")) g_deep_ring = atoi(e);
@@ -963,7 +659,6 @@ int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
   if (r != SG_OK) return r;
   TcArgs t;
   t.bits_out = a.bits_out; t.bits_in = a.bits_in; t.ldbits = a.ldbits;
-  if (g_use_256 || g_use_pair) { t.bits_out = nullptr; t.bits_in = nullptr; }   // experimental tile variants keep fp32 masks
   t.bias = a.bias; t.out = a.out; t.ldo = a.ldo; t.mask = a.mask; t.ldmask = a.ldmask;
   t.rows = a.rows; t.N = a.N; t.bn = bn; t.kchunks = a.cin / kbe; t.taps = a.taps; t.tap_step = a.tap_step;
   t.epilogue = a.epilogue; t.T = a.T > 0 ? a.T : 1; t.t_valid = a.t_valid;
@@ -974,34 +669,11 @@ int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
   t.stb = TC_A_BYTES + bn * TC_BK * 4; t.nst = (TC_STAGES * TC_STAGE_BYTES) / t.stb;
   if (t.nst > TC_MAX_STAGES) t.nst = TC_MAX_STAGES;
   if (!g_deep_ring && t.nst > TC_STAGES) t.nst = TC_STAGES;
-  if (a.xf_ab && !(a.op_bf16 && a.out_bf16 && a.taps == 1 && a.T >= TC_BM && a.rows % a.T == 0 && a.xf_ld % 8 == 0 && a.cin <= a.xf_ld &&
-                   !g_use_256 && !g_use_pair)) {
+  if (a.xf_ab && !(a.op_bf16 && a.out_bf16 && a.taps == 1 && a.T >= TC_BM && a.rows % a.T == 0 && a.xf_ld % 8 == 0 && a.cin <= a.xf_ld)) {
     sg_set_error("sg_conv_tc: the fused pooling adjoint needs bf16 operands/output, one tap, T >= 128 (T=%d taps=%d)", a.T, a.taps);
     return SG_EINVAL;
   }
   if ((a.epilogue == SG_EPI_BIAS || a.epilogue == SG_EPI_BIAS_RELU) && !a.bias) { sg_set_error("sg_conv_tc: bias epilogue without bias"); return SG_EINVAL; }
-  if (g_use_256 && !a.op_bf16 && !a.out_bf16 && bn == TC_MAX_BN && a.taps * (a.cin / TC_BK) >= 24 && a.rows >= 256 * 64) {
-    CUtensorMap mapA2;
-    r = make_map(&mapA2, a.A, 0, (uint64_t)a.rows, (uint64_t)a.cin, (uint64_t)a.lda, 256);
-    if (r != SG_OK) return r;
-    t.m_tiles = (a.rows + 255) / 256;
-    int grid3 = t.m_tiles * t.n_tiles;
-    if (grid3 > g_num_sms) grid3 = g_num_sms;
-    conv_tc256_kernel<0><<<grid3, TC3_THREADS, TC3_SMEM_BYTES, st>>>(mapA2, mapB, t);
-    SG_LAUNCH_CHECK();
-    return SG_OK;
-  }
-  if (g_use_pair && !a.op_bf16 && !a.out_bf16 && bn >= 64 && bn % 64 == 0 && a.rows > 256) {
-    CUtensorMap mapBh;
-    r = make_map(&mapBh, a.Wk, 0, (uint64_t)a.N, (uint64_t)a.taps * a.cin, (uint64_t)a.taps * a.cin, (uint32_t)(bn / 2));
-    if (r != SG_OK) return r;
-    t.m_tiles = (a.rows + 255) / 256;
-    int pairs = t.m_tiles * t.n_tiles;
-    if (pairs > g_num_sms / 2) pairs = g_num_sms / 2;
-    conv_tc2_kernel<0><<<2 * pairs, TC_THREADS, TC2_SMEM_BYTES, st>>>(mapA, mapBh, t);
-    SG_LAUNCH_CHECK();
-    return SG_OK;
-  }
   CUtensorMap mapO;
   r = make_map(&mapO, a.out, a.out_bf16, (uint64_t)a.rows, (uint64_t)a.N, (uint64_t)a.ldo, TC_BM);
   if (r != SG_OK) return r;
