@@ -5,10 +5,17 @@
 // outside the tensor are zero-filled by TMA: no im2col, no halo copies).  Both operands are K-major,
 // SWIZZLE_128B: A box = 128 rows x 32 fp32, B box = BN rows x 32 fp32 per pipeline stage.
 //
-// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one elected
-// lane) and TMEM owner, warps 2..5 = epilogue (tcgen05.ld -> bias/ReLU or ReLU-mask -> st.global).
-// The fp32 accumulator (128 lanes x BN columns) is double-buffered in TMEM (2 x 256 columns) so
-// the epilogue of tile i overlaps the MMAs of tile i+1.
+// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (warp-convergent loop, one elected
+// lane issues) and TMEM owner, warps 2..9 = two epilogue groups of four (tcgen05.ld -> bias / ReLU + 1-bit ReLU mask, or
+// mask + row validity -> swizzled smem staging box -> TMA store).  The fp32 accumulator (128 lanes x BN columns) is
+// double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Template variants of the one kernel: KIND_BF16 (kind::f16 on bf16 operands, else kind::tf32 on fp32), OUT_BF16,
+// XFORM (the statistics-pooling adjoint applied to the staged A tiles of the layer-5 dgrad by 8 extra warps), and PAIR:
+// a 2-CTA cluster computes a 256 x BN tile with tcgen05.mma.cta_group::2, each CTA staging its 128 rows of A and half
+// of B (32 KB instead of 48 KB of L2 -> SM traffic per k-block and CTA, 6 pipeline stages instead of 4).  PAIR is the
+// default for every bf16 contraction with a bf16 output (+5 % on the PGD step, mostly through the lower power draw:
+// the step runs under the 1 kW cap).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdlib.h>
