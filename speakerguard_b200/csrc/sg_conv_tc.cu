@@ -621,6 +621,7 @@ static int tc_init() {
   SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<1, 1, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+  SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<0, 1, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   if (const char* e = getenv("SGB200_TC_PAIR_BF16")) g_pair_bf16 = atoi(e);
   if (const char* e = getenv("SGB200_TC_ISSUE")) g_issue_mode = atoi(e);
   if (const char* e = getenv("SGB200_TC_DEEP_RING")) g_deep_ring = atoi(e);
@@ -685,10 +686,10 @@ int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
   r = make_map(&mapO, a.out, a.out_bf16, (uint64_t)a.rows, (uint64_t)a.N, (uint64_t)a.ldo, TC_BM);
   if (r != SG_OK) return r;
   // bf16 CTA-pair variant (cta_group::2): mode 1 = contractions with >= 16 k-blocks, 2 = every eligible one
-  if (g_pair_bf16 && a.op_bf16 && a.out_bf16 && !a.xf_ab && bn % 32 == 0 && bn >= 64 && a.rows > 256 &&
+  if (g_pair_bf16 && (a.op_bf16 || g_pair_bf16 >= 3) && a.out_bf16 && !a.xf_ab && bn % 32 == 0 && bn >= 64 && a.rows > 256 &&
       (g_pair_bf16 >= 2 || a.taps * t.kchunks >= 16)) {
     CUtensorMap mapBh;
-    r = make_map(&mapBh, a.Wk, 1, (uint64_t)a.N, (uint64_t)a.taps * a.cin, (uint64_t)a.taps * a.cin, (uint32_t)(bn / 2));
+    r = make_map(&mapBh, a.Wk, a.op_bf16, (uint64_t)a.N, (uint64_t)a.taps * a.cin, (uint64_t)a.taps * a.cin, (uint32_t)(bn / 2));
     if (r != SG_OK) return r;
     t.m_tiles = (a.rows + 2 * TC_BM - 1) / (2 * TC_BM);
     t.stb = TC_A_BYTES + (bn / 2) * TC_BK * 4; t.nst = (TC_STAGES * TC_STAGE_BYTES) / t.stb;
@@ -703,7 +704,8 @@ int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
     attr.id = cudaLaunchAttributeClusterDimension;
     attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr; cfg.numAttrs = 1;
-    SG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, 1, 0, 1>, mapA, mapBh, mapO, t));
+    if (a.op_bf16) SG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, 1, 0, 1>, mapA, mapBh, mapO, t));
+    else SG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<0, 1, 0, 1>, mapA, mapBh, mapO, t));
     return SG_OK;
   }
   int grid = t.m_tiles * t.n_tiles;
