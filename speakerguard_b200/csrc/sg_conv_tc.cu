@@ -31,7 +31,7 @@
 #define TC_STAGE_BYTES (TC_A_BYTES + TC_B_BYTES)
 #define TC_STG_BYTES (TC_BM * 32 * 4)            // 16 KB epilogue staging box (128 rows x 32 fp32), x2
 #define TC_MAX_STAGES 12
-#define TC_SMEM_BYTES (TC_STAGES * TC_STAGE_BYTES + 2 * TC_STG_BYTES + 1024 /*align*/ + 384 /*barriers*/ + 1024 /*bias*/)
+#define TC_SMEM_BYTES (TC_STAGES * TC_STAGE_BYTES + 2 * TC_STG_BYTES + 1024 /*align*/ + 512 /*barriers*/ + 1024 /*bias*/)
 #define TC_MAIN_THREADS 320           // main kernel: TMA warp, MMA warp, 2 x 4 epilogue warps
 #define TC_XF_THREADS (TC_MAIN_THREADS + 256)   // XFORM variant: + 8 warps that rewrite the staged A tile in place
 
@@ -226,7 +226,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   // The ring geometry is chosen by the host from the B box: stage = 16 KB of A + this CTA's B rows x 128 B, as many
   // stages as fit in the 192 KB ring (4 for a 256-row B box, 6 for a pair's 128 rows, 9 for the 32-column layer-1 dgrad,
   // whose short k-blocks are otherwise bound by the TMA round trip).
-  static_assert(!(PAIR && XFORM), "the fused pooling adjoint is a single-CTA variant");
   const int NST = a.nst;
   const uint32_t STB = (uint32_t)a.stb;
   uint8_t* stg = smem + TC_STAGES * TC_STAGE_BYTES;                  // 2 x 16 KB, 1024-byte aligned
@@ -236,8 +235,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   uint64_t* tfull = bars + 2 * TC_MAX_STAGES;           // [2]     per CTA
   uint64_t* tempty = bars + 2 * TC_MAX_STAGES + 2;      // [2]     (PAIR: rank 0's copy is the live one)
   uint64_t* xfull = bars + 2 * TC_MAX_STAGES + 4;       // [TC_MAX_STAGES] (XFORM: tile transformed, ready for the MMA)
-  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * TC_MAX_STAGES + 4);
-  float* bias_s = (float*)(bars + 48);                  // [2 epilogue groups][128]: the bias of the current tile's columns
+  uint64_t* xpeer = bars + 3 * TC_MAX_STAGES + 4;       // [TC_MAX_STAGES] (XFORM + PAIR, rank 0's copy: the peer's tile is transformed)
+  uint32_t* tmem_slot = (uint32_t*)(bars + 4 * TC_MAX_STAGES + 4);
+  float* bias_s = (float*)(bars + 64);                  // [2 epilogue groups][128]: the bias of the current tile's columns
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = a.taps * a.kchunks;
@@ -250,7 +250,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const int rbase = (int)rank * TC_BM;                                   // this CTA's rows inside a pair tile
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&xfull[s], 8); }
+    for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&xfull[s], 8); mbar_init(&xpeer[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], PAIR ? 16 : 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -275,7 +275,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       const int bh = PAIR ? (a.bn >> 1) : a.bn;                       // B rows staged by this CTA
-      const uint32_t tx = (PAIR ? 2u : 1u) * (TC_A_BYTES + (uint32_t)bh * TC_BK * 4);
+      // XFORM + PAIR: every CTA's boxes signal its OWN full barrier (its transform warps wait on it); plain PAIR: the leader's
+      const uint32_t tx = ((PAIR && !XFORM) ? 2u : 1u) * (TC_A_BYTES + (uint32_t)bh * TC_BK * 4);
       // L2 prefetch cursor for the A operand, a.pf_dist k-blocks ahead of the load cursor.  A single-tap layer streams A
       // from HBM exactly once, and with only TC_STAGES - 1 boxes in flight per SM the ring cannot cover the HBM latency
       // (Little: 3 x 16 KB x 148 SMs / ~2 us = 3.5 TB/s); the prefetch moves that wait out of the ring, so the ring
@@ -297,7 +298,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           if (a.pf_dist > 0) prefetch_next();
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STB;
-          if (PAIR) {
+          if (PAIR && !XFORM) {
             const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
             // only the leader arms the barrier (count 1, transaction bytes of BOTH CTAs' boxes).  The peer's bytes may land
             // first: the transaction count then goes negative while the phase's single arrival is still pending, so the
@@ -322,7 +323,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // four tcgen05.mma of a k-block issue back to back) and one elected lane issues; issue_mode 0: a single-lane region, where
     // ptxas re-derives uniformity for every tcgen05.mma operand (ELECT + R2UR.BROADCAST per instruction, ~70 dependent
     // instructions per k-block).
-    if (a.issue_mode != 0 && rank == 0) {
+    if (PAIR && XFORM && rank != 0) {
+      // the peer's otherwise idle MMA warp forwards "my A tile is transformed" to the leader, one remote arrive per k-block
+      if (lane == 0) {
+        int stage = 0; uint32_t phase = 0;
+        for (int tile = cta0; tile < ntiles; tile += tstep)
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(&xfull[stage], phase);
+            mbar_arrive_cluster(mapa_u32(smem_u32(&xpeer[stage]), 0));
+            if (++stage == NST) { stage = 0; phase ^= 1; }
+          }
+      }
+    } else if (a.issue_mode != 0 && rank == 0) {
       const uint32_t fmt = KIND_BF16 ? 1u : 2u;
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(a.bn >> 3) << 17) | ((uint32_t)(TILE_ROWS >> 4) << 24);
       const uint32_t smem_base = smem_u32(smem);
@@ -337,6 +349,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           const uint32_t sa = smem_base + (uint32_t)stage * STB;
           const uint64_t da = make_desc(sa), db = make_desc(sa + TC_A_BYTES);
           mbar_wait(XFORM ? &xfull[stage] : &full[stage], phase);
+          if (PAIR && XFORM) mbar_wait(&xpeer[stage], phase);
           tc_fence_after();
           if (leader) {
 #pragma unroll
@@ -367,6 +380,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const uint32_t tmem_d = tmem_base + (uint32_t)acc * TC_MAX_BN;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(XFORM ? &xfull[stage] : &full[stage], phase);
+          if (PAIR && XFORM) mbar_wait(&xpeer[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STB);
           const uint64_t da = make_desc(sa), db = make_desc(sa + TC_A_BYTES);
@@ -395,7 +409,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     int stage = 0; uint32_t phase = 0;
     for (int tile = cta0; tile < ntiles; tile += tstep) {
       const int mt = tile / a.n_tiles;
-      const int row0 = mt * TC_BM + g;
+      const int row0 = mt * TILE_ROWS + rbase + g;
       const int b0 = row0 / a.T;
       const int tt0 = row0 - b0 * a.T;
       int isplit = (a.T - tt0 + 31) >> 5;
@@ -599,6 +613,7 @@ static EncodeFn g_encode = nullptr;
 static int g_num_sms = 0;
 static int g_pf_dist = 0;        // L2 prefetch distance (k-blocks) of the A operand; SGB200_TC_PREFETCH overrides, 0 = off
 static int g_pf_all = 0;         // SGB200_TC_PREFETCH_ALL=1: also for multi-tap layers (their A re-reads hit L2 anyway)
+static int g_pair_xf = 1;        // SGB200_TC_PAIR_XF=0: keep the fused layer-5 dgrad on the single-CTA kernel
 static int g_deep_ring = 0;      // SGB200_TC_DEEP_RING=1: as many stages as fit when the B box is small (measured: no gain)
 static int g_issue_mode = 1;     // SGB200_TC_ISSUE: see TcArgs::issue_mode
 static int g_pair_bf16 = 2;      // SGB200_TC_PAIR_BF16: bf16 contractions on CTA pairs (cta_group::2): 1 long-K only, 2 all
@@ -622,9 +637,11 @@ static int tc_init() {
   SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<1, 1, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<0, 1, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+  SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<1, 1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   if (const char* e = getenv("SGB200_TC_PAIR_BF16")) g_pair_bf16 = atoi(e);
   if (const char* e = getenv("SGB200_TC_ISSUE")) g_issue_mode = atoi(e);
   if (const char* e = getenv("SGB200_TC_DEEP_RING")) g_deep_ring = atoi(e);
+  if (const char* e = getenv("SGB200_TC_PAIR_XF")) g_pair_xf = atoi(e);
   if (const char* e = getenv("SGB200_TC_PREFETCH")) { g_pf_dist = atoi(e); if (g_pf_dist < 0 || g_pf_dist > 64) g_pf_dist = 0; }
   if (const char* e = getenv("SGB200_TC_PREFETCH_ALL")) g_pf_all = atoi(e) != 0;
   g_encode = (EncodeFn)fn;
@@ -686,7 +703,7 @@ int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
   r = make_map(&mapO, a.out, a.out_bf16, (uint64_t)a.rows, (uint64_t)a.N, (uint64_t)a.ldo, TC_BM);
   if (r != SG_OK) return r;
   // bf16 CTA-pair variant (cta_group::2): mode 1 = contractions with >= 16 k-blocks, 2 = every eligible one
-  if (g_pair_bf16 && (a.op_bf16 || g_pair_bf16 >= 3) && a.out_bf16 && !a.xf_ab && bn % 32 == 0 && bn >= 64 && a.rows > 256 &&
+  if (g_pair_bf16 && (a.op_bf16 || g_pair_bf16 >= 3) && a.out_bf16 && (!a.xf_ab || g_pair_xf) && bn % 32 == 0 && bn >= 64 && a.rows > 256 &&
       (g_pair_bf16 >= 2 || a.taps * t.kchunks >= 16)) {
     CUtensorMap mapBh;
     r = make_map(&mapBh, a.Wk, a.op_bf16, (uint64_t)a.N, (uint64_t)a.taps * a.cin, (uint64_t)a.taps * a.cin, (uint32_t)(bn / 2));
@@ -704,7 +721,8 @@ int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
     attr.id = cudaLaunchAttributeClusterDimension;
     attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr; cfg.numAttrs = 1;
-    if (a.op_bf16) SG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, 1, 0, 1>, mapA, mapBh, mapO, t));
+    if (a.xf_ab) { cfg.blockDim = dim3(TC_XF_THREADS); SG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, 1, 1, 1>, mapA, mapBh, mapO, t)); }
+    else if (a.op_bf16) SG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, 1, 0, 1>, mapA, mapBh, mapO, t));
     else SG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<0, 1, 0, 1>, mapA, mapBh, mapO, t));
     return SG_OK;
   }
