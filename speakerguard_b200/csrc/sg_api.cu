@@ -67,6 +67,7 @@ extern "C" int sg_create(sg_handle** out, int device) {
   h->device = device;
   if (const char* e = getenv("SGB200_POOL_FUSION")) h->pool_fusion = atoi(e) != 0;   // A/B switches for bench.py runs
   if (const char* e = getenv("SGB200_FEAT_STASH")) h->feat_stash = atoi(e) != 0;
+  if (const char* e = getenv("SGB200_L1_TAP_FORM")) h->l1_tap_form = atoi(e) != 0;
   SgFeatTables* host = new SgFeatTables();
   int r = sg_feat_tables_build(host);
   if (r != SG_OK) { delete host; delete h; sg_set_error("sg_create: feature table construction failed"); return r; }
@@ -102,6 +103,7 @@ extern "C" int sg_set_option(sg_handle* h, int option, int value) {
   if (!h) { sg_set_error("null handle"); return SG_EINVAL; }
   if (option == SG_OPT_POOL_FUSION) { h->pool_fusion = value != 0; return SG_OK; }
   if (option == SG_OPT_FEAT_STASH) { h->feat_stash = value != 0; return SG_OK; }
+  if (option == SG_OPT_L1_TAP_FORM) { h->l1_tap_form = value != 0; return SG_OK; }
   sg_set_error("unknown option %d", option);
   return SG_EINVAL;
 }
@@ -213,6 +215,14 @@ extern "C" int sg_load_xv(sg_handle* h, const sg_xv_weights* w) {
     SG_TRY(sg_dev_upload(h, &h->Wbk[l], Wbk));
     SG_TRY(upload_bf16(h, &h->Wfk_h[l], Wfk));
     SG_TRY(upload_bf16(h, &h->Wbk_h[l], Wbk));
+    if (l == 0) {
+      // per-tap form of the layer-1 dgrad (embed_bwd): G[t, k*32 + c] = sum_o dA1[t, o] w[o][c][k], dx[s, c] = sum_k G[s - k*d, k*32 + c]
+      std::vector<float> Wg((size_t)K * cip * cop, 0.f);
+      for (int o = 0; o < co; ++o)
+        for (int c = 0; c < ci; ++c)
+          for (int k = 0; k < K; ++k) Wg[((size_t)k * cip + c) * cop + o] = w->tdnn_w[l][((size_t)o * ci + c) * K + k];
+      SG_TRY(upload_bf16(h, &h->Wg1_h, Wg));
+    }
     SG_TRY(sg_dev_upload(h, &h->bias[l], bias));
   }
   {
@@ -467,6 +477,15 @@ static int embed_bwd(sg_handle* h, const float* demb, int B, int T, const XvWs& 
       if (h->precision != SG_PREC_FP32) { a.bits_in = w.bits[l - 1]; a.ldbits = SG_C1 / 32; }
       SG_TRY(sg_run_conv(h, a, true, (l == 4 && fuse_pool) ? SG_PROF_TDNN_BWD_POOL : SG_PROF_TDNN_BWD, st));
       gin = out;
+    } else if (h->precision == SG_PREC_BF16 && h->l1_tap_form) {
+      // layer-1 dgrad in per-tap form: one K = 512 contraction into G [R, taps * 32] (8 k-blocks per tile instead of 40:
+      // the N = 32 contraction pays the same ~650 cycles per k-block as a 256-column one), then the shifted sum over taps
+      float* G = w.G0;                                   // free here: dA5 (or nothing, with the pooling fusion) was consumed
+      a.Wk = (const float*)h->Wg1_h; a.W = nullptr; a.taps = 1; a.tap_step = 0;
+      a.out = G; a.ldo = kTaps[0] * SG_FLD; a.N = kTaps[0] * SG_FLD; a.epilogue = SG_EPI_NONE;
+      SG_TRY(sg_run_conv(h, a, true, SG_PROF_TDNN_BWD, st));
+      h->launches += 1;
+      PROF(h, SG_PROF_TDNN_BWD, st, sg_tap_gather_launch(G, kTaps[0] * SG_FLD, dfeat, SG_FLD, R, kTaps[0], kDil[0], st));
     } else {
       a.out = dfeat; a.ldo = SG_FLD; a.N = SG_FLD; a.epilogue = SG_EPI_NONE;
       SG_TRY(sg_run_conv(h, a, true, SG_PROF_TDNN_BWD, st));

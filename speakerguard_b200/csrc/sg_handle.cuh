@@ -35,6 +35,7 @@ struct sg_handle {
   int device = 0;
   int precision = SG_PREC_FP32;
   long long launches = 0;
+  int l1_tap_form = 0;              // SG_OPT_L1_TAP_FORM: bf16 mode computes the layer-1 dgrad per tap (K = 512) + a shifted sum
   int feat_stash = 1;               // SG_OPT_FEAT_STASH: the fused attack loop hands the per-frame forward state to the MFCC adjoint
   int pool_fusion = 1;              // SG_OPT_POOL_FUSION: bf16 mode contracts the pooling adjoint inside the layer-5 dgrad
   SgFeatTables* d_tables = nullptr;
@@ -48,6 +49,7 @@ struct sg_handle {
   float* Wbk[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [cinP, taps*coutP]
   void* Wfk_h[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; // bf16 copies of Wfk / Wbk (SG_PREC_BF16)
   void* Wbk_h[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  void* Wg1_h = nullptr;            // layer-1 dgrad in per-tap form: bf16 [taps * 32, 512], row k*32 + c = w[:, c, k]
   float* bias[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; // [coutP] (BN of the previous layer folded)
   float* bn5_mean = nullptr; float* bn5_istd = nullptr;           // [C5P]
   float* Wfc = nullptr; float* Wfc_b = nullptr; float* bfc = nullptr;     // fc1: [3072,512], [512,3072], [512]

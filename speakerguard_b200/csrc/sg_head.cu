@@ -197,6 +197,24 @@ __global__ void pool_bwd_params_kernel(int Tv, int npair, const float* __restric
   ab[p] = make_uint2(*reinterpret_cast<const uint32_t*>(&a2), *reinterpret_cast<const uint32_t*>(&b2));
 }
 
+// Shifted sum over the taps of the per-tap layer-1 dgrad: out[r, f] = sum_k G[r - k * dil, k * 32 + f] (rows before the
+// first one contribute nothing, exactly like the zero-filled TMA rows of the K = taps * 512 form; rows of the previous
+// utterance hold zeros there because the layer-2 dgrad epilogue zeroes its invalid frames).  One float4 per thread.
+__global__ void tap_gather_kernel(const float* __restrict__ G, int ldg, float* __restrict__ out, int ldo, size_t rows, int taps, int dil) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t r = i >> 3;
+  const int j = (int)(i & 7);
+  if (r >= rows) return;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < taps; ++k) {
+    const long long rr = (long long)r - (long long)k * dil;
+    if (rr < 0) break;
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(G + (size_t)rr * ldg + k * 32) + j);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  *(reinterpret_cast<float4*>(out + r * ldo) + j) = acc;
+}
+
 // ---------------------------------------------------------------------------------------------
 // block helpers (blockDim.x == 256)
 // ---------------------------------------------------------------------------------------------
@@ -463,6 +481,12 @@ int sg_pool_bwd_params_launch(int B, int Tv, const float* bn_istd, const float* 
                               const float* save_std, float* ab, cudaStream_t st) {
   const int n = B * SG_C5P / 2;
   pool_bwd_params_kernel<<<(n + 255) / 256, 256, 0, st>>>(Tv, n, bn_istd, dstats, save_mean, save_std, reinterpret_cast<uint2*>(ab));
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+int sg_tap_gather_launch(const float* G, int ldg, float* out, int ldo, size_t rows, int taps, int dil, cudaStream_t st) {
+  const size_t n = rows * 8;
+  tap_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(G, ldg, out, ldo, rows, taps, dil);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }

@@ -24,6 +24,7 @@ int sg_feat_bwd_step_launch(const SgFeatTables* dT, const float* x, int B, int N
                             const float* x0, float* x_out, float step, float eps, cudaStream_t st, const float* stash = nullptr);
 size_t sg_feat_stash_floats(int B, int m);   // per-frame forward stash consumed by the adjoint (attack loop only)
 int sg_dither_fill_launch(int B, int m, uint64_t seed, uint64_t pass, float* out, cudaStream_t st);
+int sg_tap_gather_launch(const float* G, int ldg, float* out, int ldo, size_t rows, int taps, int dil, cudaStream_t st);
 int sg_step_linf_launch(float* x, const float* x0, const float* grad, size_t n, float step, float eps, cudaStream_t st);
 int sg_cmvn_launch(const float* in, int ld_in, float* out, int ld_out, int B, int T, int backward, cudaStream_t st);
 
