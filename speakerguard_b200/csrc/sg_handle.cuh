@@ -35,7 +35,7 @@ struct sg_handle {
   int device = 0;
   int precision = SG_PREC_FP32;
   long long launches = 0;
-  int l1_tap_form = 0;              // SG_OPT_L1_TAP_FORM: bf16 mode computes the layer-1 dgrad per tap (K = 512) + a shifted sum
+  int l1_tap_form = 1;              // SG_OPT_L1_TAP_FORM: bf16 mode computes the layer-1 dgrad per tap (K = 512) + a shifted sum
   int feat_stash = 1;               // SG_OPT_FEAT_STASH: the fused attack loop hands the per-frame forward state to the MFCC adjoint
   int pool_fusion = 1;              // SG_OPT_POOL_FUSION: bf16 mode contracts the pooling adjoint inside the layer-5 dgrad
   SgFeatTables* d_tables = nullptr;
