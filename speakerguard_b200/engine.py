@@ -460,7 +460,17 @@ class Engine:
         return scores, dec, emb
 
     def pgd_ws(self, B: int, N: int) -> torch.Tensor:
-        return self.alloc_ws(self.lib.sg_pgd_ws_bytes(self._h, B, N))
+        """Scratch for one fused attack / forward call.  It only lives inside that call (the handle is not re-entrant and its
+        work is stream-ordered), so the engine keeps the largest one it has handed out instead of asking the allocator for
+        ~10 KB per frame on every ``attack()``."""
+        n = int(self.lib.sg_pgd_ws_bytes(self._h, B, N))
+        sid = torch.cuda.current_stream(self.device).cuda_stream    # like the caching allocator: never shared across streams
+        cached = getattr(self, "_pgd_ws_cache", None)
+        if cached is None or cached[0] != sid or cached[1].numel() < n:
+            self._pgd_ws_cache = None                      # release the old block before asking for a larger one
+            cached = (sid, self.alloc_ws(n))
+            self._pgd_ws_cache = cached
+        return cached[1][:n]
 
     def pgd_run(self, x_adv: torch.Tensor, x0: torch.Tensor, y: torch.Tensor, *, max_iter: int, epsilon: float,
                 step_size: float, lp: LossParams, dither_mode: int = _lib.DITHER_PHILOX,
