@@ -62,3 +62,16 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "oracle" not in txt.replace("sg_oracle-free", ""), f"{f} mentions the oracle"
+
+
+def test_python_constants_mirror_the_header():
+    """The ctypes layer restates a few enums of include/sgb200.h; they must not drift."""
+    from speakerguard_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "sgb200.h")).read()
+    defs = {k: int(v) for k, v in re.findall(r"#define\s+(SG_OPT_[A-Z0-9_]+)\s+(\d+)", src)}
+    assert defs == {"SG_OPT_POOL_FUSION": _lib.OPT_POOL_FUSION, "SG_OPT_FEAT_STASH": _lib.OPT_FEAT_STASH,
+                    "SG_OPT_L1_TAP_FORM": _lib.OPT_L1_TAP_FORM}
+    body = re.search(r"enum\s*\{\s*SG_PROF_MFCC_FWD\s*=\s*0(.*?)SG_PROF_COUNT\s*\}", re.sub(r"/\*.*?\*/", "", src, flags=re.S), re.S)
+    assert body is not None
+    n_prof = 1 + len(re.findall(r"SG_PROF_[A-Z0-9_]+", body.group(1)))
+    assert n_prof == _lib.PROF_COUNT
