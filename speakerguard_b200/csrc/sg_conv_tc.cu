@@ -220,12 +220,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   // PAIR: a CTA pair (cluster of 2 on one TPC) computes a 256 x BN tile with tcgen05.mma.cta_group::2.  Each CTA stages
   // its own 128 rows of A and HALF of the B tile, so a k-block costs 32 KB of L2 -> SM traffic per CTA instead of 48 KB
-  // for the same 4.2 MFLOP (the single-CTA kernel sits at the L2 -> SM throughput cap: ~620 clk per k-block against 512
-  // for the tensor pipe), and the smaller stage leaves room for 6 pipeline stages.  Rank 0 issues the MMAs; both CTAs
-  // run TMA producers (signalling rank 0's full barriers) and epilogues (own 128 TMEM lanes); commits are multicast.
-  // The ring geometry is chosen by the host from the B box: stage = 16 KB of A + this CTA's B rows x 128 B, as many
-  // stages as fit in the 192 KB ring (4 for a 256-row B box, 6 for a pair's 128 rows, 9 for the 32-column layer-1 dgrad,
-  // whose short k-blocks are otherwise bound by the TMA round trip).
+  // for the same 4.2 MFLOP, and the smaller stage leaves room for 6 pipeline stages.  Measured: the cycles per k-block
+  // stay at ~650 (512 for the tensor pipe alone; cuBLAS ~590), but the pair draws less power and the step runs under
+  // the 1 kW cap: +10 % SM clock, +5 % on the PGD step.  Rank 0 issues the MMAs; both CTAs run TMA producers
+  // (signalling rank 0's full barriers) and epilogues (own 128 TMEM lanes); commits are multicast.
+  // The ring geometry is chosen by the host from the B box: stage = 16 KB of A + this CTA's B rows x 128 B; 4 stages
+  // for a 256-row B box, 6 for a pair's 128 rows (SGB200_TC_DEEP_RING=1 allows up to 12 for small boxes: no gain measured).
   const int NST = a.nst;
   const uint32_t STB = (uint32_t)a.stb;
   uint8_t* stg = smem + TC_STAGES * TC_STAGE_BYTES;                  // 2 x 16 KB, 1024-byte aligned
