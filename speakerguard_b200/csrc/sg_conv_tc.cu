@@ -616,7 +616,7 @@ static int g_pf_all = 0;         // SGB200_TC_PREFETCH_ALL=1: also for multi-tap
 static int g_pair_xf = 1;        // SGB200_TC_PAIR_XF=0: keep the fused layer-5 dgrad on the single-CTA kernel
 static int g_deep_ring = 0;      // SGB200_TC_DEEP_RING=1: as many stages as fit when the B box is small (measured: no gain)
 static int g_issue_mode = 1;     // SGB200_TC_ISSUE: see TcArgs::issue_mode
-static int g_pair_bf16 = 2;      // SGB200_TC_PAIR_BF16: bf16 contractions on CTA pairs (cta_group::2): 1 long-K only, 2 all
+static int g_pair_bf16 = 2;      // SGB200_TC_PAIR_BF16: contractions on CTA pairs (cta_group::2): 1 bf16 long-K only, 2 all bf16 -> bf16, 3 / 4 see sg_conv_tc()
 
 static int tc_init() {
   if (g_encode) return SG_OK;
@@ -638,6 +638,7 @@ static int tc_init() {
   SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<1, 1, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<0, 1, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<1, 1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+  SG_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<0, 0, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   if (const char* e = getenv("SGB200_TC_PAIR_BF16")) g_pair_bf16 = atoi(e);
   if (const char* e = getenv("SGB200_TC_ISSUE")) g_issue_mode = atoi(e);
   if (const char* e = getenv("SGB200_TC_DEEP_RING")) g_deep_ring = atoi(e);
@@ -703,7 +704,10 @@ int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
   r = make_map(&mapO, a.out, a.out_bf16, (uint64_t)a.rows, (uint64_t)a.N, (uint64_t)a.ldo, TC_BM);
   if (r != SG_OK) return r;
   // bf16 CTA-pair variant (cta_group::2): mode 1 = contractions with >= 16 k-blocks, 2 = every eligible one
-  if (g_pair_bf16 && (a.op_bf16 || g_pair_bf16 >= 3) && a.out_bf16 && (!a.xf_ab || g_pair_xf) && bn % 32 == 0 && bn >= 64 && a.rows > 256 &&
+  // (modes 3 and 4 are not validated defaults: 3 adds the tf32-operand / bf16-output layer-1 forward (measured: no gain),
+  //  4 adds fp32-output contractions - the tf32 mode and the i-vector UBM contraction: tests/test_gpu_tc.py and
+  //  tests/test_gpu_iv.py pass with it, its throughput has not been measured yet)
+  if (g_pair_bf16 && (a.op_bf16 || g_pair_bf16 >= 3) && (a.out_bf16 || (g_pair_bf16 >= 4 && !a.op_bf16)) && (!a.xf_ab || g_pair_xf) && bn % 32 == 0 && bn >= 64 && a.rows > 256 &&
       (g_pair_bf16 >= 2 || a.taps * t.kchunks >= 16)) {
     CUtensorMap mapBh;
     r = make_map(&mapBh, a.Wk, a.op_bf16, (uint64_t)a.N, (uint64_t)a.taps * a.cin, (uint64_t)a.taps * a.cin, (uint32_t)(bn / 2));
@@ -723,7 +727,8 @@ int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
     cfg.attrs = &attr; cfg.numAttrs = 1;
     if (a.xf_ab) { cfg.blockDim = dim3(TC_XF_THREADS); SG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, 1, 1, 1>, mapA, mapBh, mapO, t)); }
     else if (a.op_bf16) SG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, 1, 0, 1>, mapA, mapBh, mapO, t));
-    else SG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<0, 1, 0, 1>, mapA, mapBh, mapO, t));
+    else if (a.out_bf16) SG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<0, 1, 0, 1>, mapA, mapBh, mapO, t));
+    else SG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<0, 0, 0, 1>, mapA, mapBh, mapO, t));
     return SG_OK;
   }
   int grid = t.m_tiles * t.n_tiles;
