@@ -8,7 +8,8 @@
  *   - every function returns 0 (SG_OK) or a negative SG_E* code; the message is read with
  *     sg_last_error() (thread-local); no C++ exception crosses the boundary;
  *   - functions enqueue work on `stream` (a cudaStream_t passed as void*) and do not synchronise;
- *   - a handle is bound to one device, holds the packed weights/tables, is not re-entrant;
+ *   - a handle is bound to one device, holds the packed weights/tables, is not re-entrant; every entry point
+ *     that takes a handle makes that device current (cudaSetDevice) and leaves it current;
  *   - the library never allocates per-call memory: workspaces are sized by sg_*_ws_bytes() and
  *     passed in by the caller.
  * There is no CPU fallback: without a CUDA device every compute entry point fails with SG_ECUDA.
@@ -23,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SGB200_VERSION 100
+#define SGB200_VERSION 200
 
 typedef struct sg_handle sg_handle;
 typedef void* sg_stream; /* cudaStream_t */
@@ -60,6 +61,11 @@ int sg_get_precision(const sg_handle* h);
  * channels, 5 taps) is computed as one K = 512 contraction into per-tap partial sums followed by the shifted sum over the
  * taps, instead of a K = 2560 contraction with 32 output columns; same arithmetic, fp32 summation order differs. */
 #define SG_OPT_L1_TAP_FORM 3
+/* SG_OPT_UTT_OFFSET (default 0): global index of the first utterance of the batches given to this handle.  The
+ * SG_DITHER_PHILOX noise of sample j of frame f of utterance b in pass p is philox(seed; p, value + b, f, j), so when the
+ * utterance axis is split contiguously over G handles (x[r*B/G:(r+1)*B/G] on GPU r) and handle r sets
+ * value = r*B/G, the sharded attack reproduces the unsharded one bit for bit. */
+#define SG_OPT_UTT_OFFSET 4
 int sg_set_option(sg_handle* h, int option, int value);
 
 /* ---- x-vector / PLDA system: weights ---------------------------------------------------------
@@ -163,6 +169,10 @@ typedef struct {
   uint64_t seed;
   sg_loss_params loss;
   float decision_threshold; /* model.threshold; -inf for CSI */
+  float grad_sign;    /* +1 / -1: the sign resolve_loss returns (attack/utils.py:114).  It follows the loss NAME the caller
+                         asked for, not the loss that is finally used: task SV / OSI with loss='Entropy' runs the margin
+                         loss but keeps the cross-entropy sign (+1 untargeted, -1 targeted).  0 = derive it from `loss`
+                         (CE: +1 / -1 by `targeted`; margin: -1), which is only right when name and loss agree. */
 } sg_pgd_params;
 size_t sg_pgd_ws_bytes(const sg_handle* h, int B, int N);
 int sg_pgd_run(sg_handle* h, float* x_adv, const float* x0, const int64_t* y, const float* dither,
@@ -222,6 +232,13 @@ int sg_audionet_cnn_fwd(sg_handle* h, const float* feat, int B, int N, void* ws,
                         sg_stream stream);
 int sg_audionet_cnn_bwd(sg_handle* h, const float* dlogits, int B, int N, void* ws, float* dfeat,
                         sg_stream stream);
+/* The same CNN split at the embedding (forward(..., return_emb=True), embedding(), predict_from_embeddings:
+ * audionet_csine.py:176-229): sg_audionet_emb_fwd/bwd = extract_emb, feat [B,T,32] <-> emb [B,32] (max over time of conv8);
+ * sg_audionet_fc_fwd/bwd = the final fc, emb [B,32] <-> logits [B,Cp]. */
+int sg_audionet_emb_fwd(sg_handle* h, const float* feat, int B, int N, void* ws, float* emb, sg_stream stream);
+int sg_audionet_emb_bwd(sg_handle* h, const float* demb, int B, int N, void* ws, float* dfeat, sg_stream stream);
+int sg_audionet_fc_fwd(sg_handle* h, const float* emb, int B, float* logits, sg_stream stream);
+int sg_audionet_fc_bwd(sg_handle* h, const float* dlogits, int B, float* demb, sg_stream stream);
 int sg_argmax_decide(sg_handle* h, const float* scores, int B, int S, int ld, float threshold,
                      int64_t* decisions, sg_stream stream);
 int sg_cw2_audionet_run(sg_handle* h, const float* x, const int64_t* y, int B, int N,
@@ -252,8 +269,10 @@ int sg_feco_means_bwd(sg_handle* h, const float* dout, const int32_t* ids, const
  *   gmm_gconsts [C], gmm_means_invcovars [C,F], gmm_invcovars [C,F,F]      (gmm.py:73-118)
  *   ive_T [C,F,D], ive_sigma_inv [C,F,F], ive_offset                       (ivector_extract.py:25-92)
  *   emb_mean [D], lda [L,D+1] (offset in the last column), plda_* and enroll [S,L] as sg_xv_weights.
- * C must be a multiple of 16.  All contractions of this path run in fp32 (FFMA) whatever the
- * handle's precision; the per-utterance SPD solve is an fp64 Cholesky.
+ * C must be a multiple of 16.  Handle precision SG_PREC_FP32: every contraction of this path is fp32 FFMA.
+ * SG_PREC_TF32 (the host class's 'tf32x3'): the UBM log-likelihood contraction, its adjoint and the L = N x U assembly run
+ * on tcgen05 as split-TF32 (operands split hi + lo, three products per algorithmic product, fp32 accumulate: posteriors
+ * within 5e-5 of fp64); the remaining small GEMMs stay FFMA.  The per-utterance SPD solve is always an fp64 Cholesky.
  * sg_iv_embed_fwd: feat [B,T,ld] CMVN'd features -> emb [B,L] (extract_emb, model/iv_plda.py:380-396).
  * sg_iv_embed_bwd: adjoint, using what the forward left in `ws` (sg_iv_ws_bytes(h,B,T) bytes);
  *   dfeat [B,T,ld], columns >= F written as zero.
@@ -365,6 +384,9 @@ enum { SG_PROF_MFCC_FWD = 0, SG_PROF_MFCC_BWD, SG_PROF_CMVN, SG_PROF_TDNN_FWD, S
 int sg_profile_enable(sg_handle* h, int enable);
 int sg_profile_read(sg_handle* h, int category, double* total_ms, long long* launches);
 const char* sg_profile_name(int category);
+/* every launch recorded since sg_profile_enable(), in launch order: category, tag (TDNN layer 1..5 for the contraction
+ * launches, else 0) and duration in ms; at most `capacity` entries are written, *count receives the number recorded. */
+int sg_profile_dump(sg_handle* h, int* categories, int* tags, float* ms, int capacity, int* count);
 
 /* kernel-launch counter (bench.py's gpu_launches): kernels launched by this library since the
  * last sg_reset_launch_count() on the calling thread's handle. */

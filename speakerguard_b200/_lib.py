@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libsgb200.so")
 SG_OK, SG_EINVAL, SG_ECUDA, SG_ESTATE, SG_EUNSUPPORTED = 0, -1, -2, -3, -4
 PREC_FP32, PREC_TF32, PREC_BF16 = 0, 1, 2
 DITHER_OFF, DITHER_TENSOR, DITHER_PHILOX = 0, 1, 2
-OPT_POOL_FUSION, OPT_FEAT_STASH, OPT_L1_TAP_FORM = 1, 2, 3
+OPT_POOL_FUSION, OPT_FEAT_STASH, OPT_L1_TAP_FORM, OPT_UTT_OFFSET = 1, 2, 3, 4
 LOSS_CE, LOSS_MARGIN = 0, 1
 PROF_COUNT = 15
 IV_STAGE_POST, IV_STAGE_STATS, IV_STAGE_IVECTOR = 0, 1, 2
@@ -67,7 +67,7 @@ class Cw2Params(C.Structure):
 class PgdParams(C.Structure):
     _fields_ = [("max_iter", C.c_int), ("epsilon", C.c_float), ("step_size", C.c_float), ("eot_size", C.c_int),
                 ("dither_mode", C.c_int), ("seed", C.c_uint64), ("loss", LossParams),
-                ("decision_threshold", C.c_float)]
+                ("decision_threshold", C.c_float), ("grad_sign", C.c_float)]
 
 
 # name -> (restype, argtypes); must list every symbol include/sgb200.h declares
@@ -106,6 +106,10 @@ PROTOTYPES = {
     "sg_audionet_logmel_bwd": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_float, C.c_int, _vp]),
     "sg_audionet_cnn_fwd": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
     "sg_audionet_cnn_bwd": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "sg_audionet_emb_fwd": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "sg_audionet_emb_bwd": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "sg_audionet_fc_fwd": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
+    "sg_audionet_fc_bwd": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
     "sg_argmax_decide": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_float, _vp, _vp]),
     "sg_cw2_audionet_run": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.POINTER(Cw2Params), _vp, _vp, _vp, _vp, _vp]),
     "sg_feco_kmeans": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_float, _vp, _vp]),
@@ -134,6 +138,7 @@ PROTOTYPES = {
     "sg_profile_enable": (C.c_int, [_vp, C.c_int]),
     "sg_profile_read": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "sg_profile_name": (C.c_char_p, [C.c_int]),
+    "sg_profile_dump": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.POINTER(C.c_int)]),
     "sg_launch_count": (C.c_longlong, [_vp]),
     "sg_reset_launch_count": (None, [_vp]),
 }

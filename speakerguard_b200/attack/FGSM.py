@@ -17,7 +17,7 @@ import torch
 
 from ..adaptive_attack.EOT import EOT
 from ..model.utils import known_input_range
-from ..engine import default_engine, make_loss_params
+from ..engine import default_engine, grad_sign_of, make_loss_params
 from .Attack import Attack
 from .utils import resolve_loss, resolve_prediction
 
@@ -28,7 +28,7 @@ def fused_target(model):
     from ..model.xv_plda import xv_plda
     if isinstance(model, defended_model) and model.defense is None:
         model = model.base_model
-    return model if isinstance(model, xv_plda) and hasattr(model, "enroll_embs") else None
+    return model if isinstance(model, xv_plda) and model.engine_enroll_current() else None
 
 
 class FGSM(Attack):
@@ -59,6 +59,7 @@ class FGSM(Attack):
                                                  threshold=self.threshold, clip_max=False)
         self.EOT_wrapper = EOT(self.model, self.loss, self.EOT_size, self.EOT_batch_size, True)
         self.use_fused = True                   # set False to force the generic autograd path
+        self.utt_offset = 0                     # global index of x[0] when the utterance axis is sharded over GPUs (dist.py)
 
     # ---- generic path (reference attack/FGSM.py:38-70) -----------------------------------------
     def attack_batch(self, x_batch, y_batch, lower, upper, batch_id, x0_batch=None, epsilon=None):
@@ -94,7 +95,7 @@ class FGSM(Attack):
         return x_batch, success
 
     # ---- fused path -----------------------------------------------------------------------------
-    def _fused_batch(self, xv, x_batch, x0_batch, y_batch, epsilon, batch_id):
+    def _fused_batch(self, xv, x_batch, x0_batch, y_batch, epsilon, batch_id, batch_offset=0):
         eng = xv.engine
         B, _, N = x_batch.shape
         xa = x_batch[:, 0, :].detach().to(torch.float32).contiguous().clone()
@@ -105,7 +106,8 @@ class FGSM(Attack):
         dec, scores, hist = eng.pgd_run(xa, x0, y_batch, max_iter=self.max_iter, epsilon=epsilon,
                                         step_size=self.step_size, lp=lp, dither_mode=mode, dither=dither, seed=seed,
                                         eot_size=E, decision_threshold=xv.decision_threshold,
-                                        want_loss_hist=bool(self.verbose))
+                                        want_loss_hist=bool(self.verbose), grad_sign=float(self.grad_sign),
+                                        utt_offset=self.utt_offset + batch_offset)
         predict = dec.cpu().numpy()                              # the only host sync of the attack
         target = y_batch.detach().cpu().numpy()
         if self.verbose:
@@ -121,6 +123,16 @@ class FGSM(Attack):
         n_audios, n_channels, _ = x.size()
         assert n_channels == 1, 'Only Support Mono Audio'
         assert y.shape[0] == n_audios, 'The number of x and y should be equal'
+        # what the reference's losses raise on (IndexError for a label >= num_spks, the SV assert of attack/utils.py:50);
+        # the device loss kernel cannot raise, it would return NaN losses and leave those utterances unchanged
+        if y.numel():
+            y_lo, y_hi = int(y.min()), int(y.max())
+            if self.task == 'SV':
+                assert y_lo >= -1 and y_hi <= 0, 'SV task should not have labels out of 0 and -1'
+            else:
+                n_spk = getattr(self.model, 'num_spks', None) or getattr(getattr(self.model, 'base_model', None), 'num_spks', None)
+                assert y_lo >= -1 and (n_spk is None or y_hi < n_spk), \
+                    'labels must be -1 (imposter) or an enrolled speaker index < {}'.format(n_spk)
         return n_audios
 
     def _run(self, x, x0, y, lower, upper, epsilon, tag=""):
@@ -134,7 +146,7 @@ class FGSM(Attack):
             sl = slice(b * batch_size, (b + 1) * batch_size)
             bid = '{}{}'.format(tag, b)
             if xv is not None:
-                a, s = self._fused_batch(xv, x[sl], x0[sl], y[sl], epsilon, bid)
+                a, s = self._fused_batch(xv, x[sl], x0[sl], y[sl], epsilon, bid, batch_offset=b * batch_size)
             else:
                 a, s = self.attack_batch(x[sl], y[sl], lower[sl], upper[sl], bid, x0_batch=x0[sl].detach().contiguous(),
                                          epsilon=epsilon)

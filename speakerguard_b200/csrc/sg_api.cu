@@ -104,6 +104,10 @@ extern "C" int sg_set_option(sg_handle* h, int option, int value) {
   if (option == SG_OPT_POOL_FUSION) { h->pool_fusion = value != 0; return SG_OK; }
   if (option == SG_OPT_FEAT_STASH) { h->feat_stash = value != 0; return SG_OK; }
   if (option == SG_OPT_L1_TAP_FORM) { h->l1_tap_form = value != 0; return SG_OK; }
+  if (option == SG_OPT_UTT_OFFSET) {
+    if (value < 0) { sg_set_error("SG_OPT_UTT_OFFSET must be >= 0"); return SG_EINVAL; }
+    h->utt_offset = value; return SG_OK;
+  }
   sg_set_error("unknown option %d", option);
   return SG_EINVAL;
 }
@@ -124,6 +128,20 @@ extern "C" int sg_profile_read(sg_handle* h, int category, double* total_ms, lon
     tot += ms; ++n;
   }
   *total_ms = tot; *launches = n;
+  return SG_OK;
+}
+extern "C" int sg_profile_dump(sg_handle* h, int* categories, int* tags, float* ms, int capacity, int* count) {
+  if (!h || !count || capacity < 0) { sg_set_error("sg_profile_dump: bad argument"); return SG_EINVAL; }
+  const size_t n = h->prof.used < (size_t)capacity ? h->prof.used : (size_t)capacity;
+  for (size_t i = 0; i < n; ++i) {
+    SG_CUDA_CHECK(cudaEventSynchronize(h->prof.ev[2 * i + 1]));
+    float t = 0.f;
+    SG_CUDA_CHECK(cudaEventElapsedTime(&t, h->prof.ev[2 * i], h->prof.ev[2 * i + 1]));
+    if (categories) categories[i] = h->prof.cat[i];
+    if (tags) tags[i] = h->prof.tag[i];
+    if (ms) ms[i] = t;
+  }
+  *count = (int)h->prof.used;
   return SG_OK;
 }
 extern "C" const char* sg_profile_name(int category) {
@@ -328,6 +346,9 @@ extern "C" size_t sg_pgd_ws_bytes(const sg_handle* h, int B, int N) {
 // ---------------------------------------------------------------------------------------------
 int sg_check_handle(sg_handle* h, bool need_xv) {
   if (!h) { sg_set_error("null handle"); return SG_EINVAL; }
+  // a handle is bound to one device: make it current so that launches, events and per-device kernel attributes of this call
+  // land there even when the caller's current device is another one (free when it already is)
+  SG_CUDA_CHECK(cudaSetDevice(h->device));
   if (need_xv && !h->xv_loaded) { sg_set_error("x-vector weights not loaded (call sg_load_xv first)"); return SG_ESTATE; }
   return SG_OK;
 }
@@ -342,6 +363,11 @@ static int check_dither(int mode, const float* dither) {
   return SG_OK;
 }
 
+// pass counter (low 32 bits) + the handle's global utterance offset (high 32 bits), as sg_feat.cu's make_dither() expects
+static inline uint64_t dither_pass(const sg_handle* h, uint64_t pass) {
+  return (pass & 0xffffffffull) | ((uint64_t)(uint32_t)h->utt_offset << 32);
+}
+
 extern "C" int sg_num_frames(int N) { return (N + SG_SHIFT / 2) / SG_SHIFT; }
 
 // ---------------------------------------------------------------------------------------------
@@ -352,7 +378,7 @@ extern "C" int sg_mfcc_fwd(sg_handle* h, const float* x, int B, int N, int dithe
   SG_TRY(sg_check_handle(h, false)); SG_TRY(check_wave(B, N)); SG_TRY(check_dither(dither_mode, dither));
   if (!x || !raw || ld < SG_NCEP || ld > 32) { sg_set_error("sg_mfcc_fwd: bad pointer or ld (%d not in [30,32])", ld); return SG_EINVAL; }
   h->launches += 1;
-  PROF(h, SG_PROF_MFCC_FWD, (cudaStream_t)stream, sg_feat_fwd_launch(h->d_tables, x, B, N, sg_num_frames(N), dither_mode, dither, seed, pass, raw, ld, (cudaStream_t)stream));
+  PROF(h, SG_PROF_MFCC_FWD, (cudaStream_t)stream, sg_feat_fwd_launch(h->d_tables, x, B, N, sg_num_frames(N), dither_mode, dither, seed, dither_pass(h, pass), raw, ld, (cudaStream_t)stream));
   return SG_OK;
 }
 
@@ -362,7 +388,7 @@ extern "C" int sg_mfcc_bwd(sg_handle* h, const float* x, int B, int N, int dithe
   SG_TRY(sg_check_handle(h, false)); SG_TRY(check_wave(B, N)); SG_TRY(check_dither(dither_mode, dither));
   if (!x || !draw || !grad || ld < SG_NCEP || ld > 32) { sg_set_error("sg_mfcc_bwd: bad pointer or ld (%d)", ld); return SG_EINVAL; }
   h->launches += 1;
-  PROF(h, SG_PROF_MFCC_BWD, (cudaStream_t)stream, sg_feat_bwd_launch(h->d_tables, x, B, N, sg_num_frames(N), dither_mode, dither, seed, pass, draw, ld, grad,
+  PROF(h, SG_PROF_MFCC_BWD, (cudaStream_t)stream, sg_feat_bwd_launch(h->d_tables, x, B, N, sg_num_frames(N), dither_mode, dither, seed, dither_pass(h, pass), draw, ld, grad,
                             scale, accumulate, (cudaStream_t)stream));
   return SG_OK;
 }
@@ -371,7 +397,7 @@ extern "C" int sg_dither_fill(sg_handle* h, int B, int N, uint64_t seed, uint64_
   SG_TRY(sg_check_handle(h, false)); SG_TRY(check_wave(B, N));
   if (!out) { sg_set_error("sg_dither_fill: null output"); return SG_EINVAL; }
   h->launches += 1;
-  return sg_dither_fill_launch(B, sg_num_frames(N), seed, pass, out, (cudaStream_t)stream);
+  return sg_dither_fill_launch(B, sg_num_frames(N), seed, dither_pass(h, pass), out, (cudaStream_t)stream);
 }
 
 extern "C" int sg_cmvn_fwd(sg_handle* h, const float* raw, int ld_in, float* out, int ld_out, int B, int T, sg_stream stream) {
@@ -420,6 +446,7 @@ static int embed_fwd(sg_handle* h, const float* feat, int B, int T, const XvWs& 
       a.out_bf16 = 1;
       if (l > 0) { a.op_bf16 = 1; a.Wk = (const float*)h->Wfk_h[l]; }
     }
+    h->prof.next_tag = l + 1;
     SG_TRY(sg_run_conv(h, a, true, SG_PROF_TDNN_FWD, st));
     in = w.r[l]; lda = kCoutP[l];
   }
@@ -470,6 +497,7 @@ static int embed_bwd(sg_handle* h, const float* demb, int B, int T, const XvWs& 
     a.tap_step = -kDil[l]; a.T = T;
     if (h->precision == SG_PREC_BF16) { a.op_bf16 = 1; a.out_bf16 = l > 0; a.Wk = (const float*)h->Wbk_h[l]; }
     if (l == 4 && fuse_pool) { a.A = w.r[4]; a.xf_ab = w.ab; a.xf_ld = SG_C5P; a.xf_tv = tv[4]; }
+    h->prof.next_tag = l + 1;
     if (l > 0) {
       float* out = bufs[(4 - l) & 1];
       a.out = out; a.ldo = kCinP[l]; a.N = kCinP[l];
@@ -485,6 +513,7 @@ static int embed_bwd(sg_handle* h, const float* demb, int B, int T, const XvWs& 
       a.out = G; a.ldo = kTaps[0] * SG_FLD; a.N = kTaps[0] * SG_FLD; a.epilogue = SG_EPI_NONE;
       SG_TRY(sg_run_conv(h, a, true, SG_PROF_TDNN_BWD, st));
       h->launches += 1;
+      h->prof.next_tag = 1;
       PROF(h, SG_PROF_TDNN_BWD, st, sg_tap_gather_launch(G, kTaps[0] * SG_FLD, dfeat, SG_FLD, R, kTaps[0], kDil[0], st));
     } else {
       a.out = dfeat; a.ldo = SG_FLD; a.N = SG_FLD; a.epilogue = SG_EPI_NONE;
@@ -577,7 +606,7 @@ static int forward_pass(sg_handle* h, const float* x, int B, int N, int m, int m
                         uint64_t pass, float thr, const XvWs& w, float* emb, float* scores, long long* dec, cudaStream_t st,
                         float* stash = nullptr) {
   h->launches += 3;
-  PROF(h, SG_PROF_MFCC_FWD, st, sg_feat_fwd_launch(h->d_tables, x, B, N, m, mode, dither, seed, pass, w.raw, SG_FLD, st, stash));
+  PROF(h, SG_PROF_MFCC_FWD, st, sg_feat_fwd_launch(h->d_tables, x, B, N, m, mode, dither, seed, dither_pass(h, pass), w.raw, SG_FLD, st, stash));
   PROF(h, SG_PROF_CMVN, st, sg_cmvn_launch(w.raw, SG_FLD, w.feat, SG_FLD, B, m, 0, st));
   SG_TRY(embed_fwd(h, w.feat, B, m, w, emb, st));
   PROF(h, SG_PROF_HEAD, st, sg_score_fwd_launch(h->H, emb, B, h->enroll, h->S, thr, scores, dec, st));
@@ -606,8 +635,10 @@ extern "C" int sg_pgd_run(sg_handle* h, float* x_adv, const float* x0, const int
   const int m = sg_num_frames(N), E = p->eot_size;
   XvWs w = xv_ws_layout(ws, B, m, h->Lp, h->L, h->S, true, N);
   const size_t dstride = (size_t)B * m * SG_WIN;
-  // grad_sign of attack/utils.py:114
-  const float grad_sign = (p->loss.loss == SG_LOSS_CE) ? (p->loss.targeted ? -1.f : 1.f) : -1.f;
+  // grad_sign of attack/utils.py:114 follows the requested loss NAME (SV / OSI with loss='Entropy' run the margin loss with
+  // the cross-entropy sign), so the caller passes it; 0 derives it from the effective loss
+  if (p->grad_sign != 0.f && p->grad_sign != 1.f && p->grad_sign != -1.f) { sg_set_error("sg_pgd_run: grad_sign must be +1, -1 or 0 (derive), got %g", p->grad_sign); return SG_EINVAL; }
+  const float grad_sign = p->grad_sign != 0.f ? p->grad_sign : ((p->loss.loss == SG_LOSS_CE) ? (p->loss.targeted ? -1.f : 1.f) : -1.f);
   float* cur = x_adv;
   float* other = w.xbuf;
   float* const stash = h->feat_stash ? w.stash : nullptr;
@@ -626,11 +657,11 @@ extern "C" int sg_pgd_run(sg_handle* h, float* x_adv, const float* x0, const int
       PROF(h, SG_PROF_CMVN, st, sg_cmvn_launch(w.dfeat, SG_FLD, w.draw, SG_FLD, B, m, 1, st));
       h->launches += 1;
       if (E == 1) {
-        PROF(h, SG_PROF_MFCC_BWD, st, sg_feat_bwd_step_launch(h->d_tables, cur, B, N, m, p->dither_mode, dth, p->seed, pass, w.draw, SG_FLD, x0,
+        PROF(h, SG_PROF_MFCC_BWD, st, sg_feat_bwd_step_launch(h->d_tables, cur, B, N, m, p->dither_mode, dth, p->seed, dither_pass(h, pass), w.draw, SG_FLD, x0,
                                        other, p->step_size * grad_sign, p->epsilon, st, stash));
         float* t = cur; cur = other; other = t;
       } else {
-        PROF(h, SG_PROF_MFCC_BWD, st, sg_feat_bwd_launch(h->d_tables, cur, B, N, m, p->dither_mode, dth, p->seed, pass, w.draw, SG_FLD, w.grad,
+        PROF(h, SG_PROF_MFCC_BWD, st, sg_feat_bwd_launch(h->d_tables, cur, B, N, m, p->dither_mode, dth, p->seed, dither_pass(h, pass), w.draw, SG_FLD, w.grad,
                                   1.0f / (float)E, e > 0, st, stash));
       }
     }

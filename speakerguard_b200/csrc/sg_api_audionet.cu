@@ -144,7 +144,8 @@ static void an_conv_args(SgConvArgs& a, const float* A, int cin, const float* W,
   a.mask = mask; a.ldmask = ldmask;
 }
 
-static int an_cnn_fwd(sg_handle* h, const float* feat, int B, const AnWs& w, float* logits, cudaStream_t st) {
+// extract_emb (audionet_csine.py:176-207): conv1 .. conv8 + max over time -> emb [B,32] (also left in w.emb / w.arg)
+static int an_emb_fwd(sg_handle* h, const float* feat, int B, const AnWs& w, float* emb, cudaStream_t st) {
   SgAudioNet* an = h->an;
   SgConvArgs a;
   an_conv_args(a, feat, 32, an->W1, an->b1, w.c1, 32, B * w.T[0], 5, -2, 1, w.T[0], SG_EPI_BIAS, nullptr, 0);
@@ -161,22 +162,41 @@ static int an_cnn_fwd(sg_handle* h, const float* feat, int B, const AnWs& w, flo
     in = w.p[l];
   }
   h->launches += 1;
-  PROF(h, SG_PROF_AUDIONET, st, sg_globalmax_fwd_launch(w.a[6], w.emb, w.arg, B, w.T[6], w.T[7], 32, st));   // valid conv8 outputs only
-  memset(&a, 0, sizeof(a));
-  a.A = w.emb; a.lda = 32; a.W = an->Wfc; a.bias = an->bfc; a.out = logits; a.ldo = an->Cp; a.rows = B; a.N = an->Cp; a.cin = 32;
-  a.taps = 1; a.epilogue = SG_EPI_BIAS; a.T = 1;
-  return sg_run_conv(h, a, false, SG_PROF_AUDIONET, st);
+  PROF(h, SG_PROF_AUDIONET, st, sg_globalmax_fwd_launch(w.a[6], emb, w.arg, B, w.T[6], w.T[7], 32, st));   // valid conv8 outputs only
+  return SG_OK;
 }
-
-static int an_cnn_bwd(sg_handle* h, const float* dlogits, int B, const AnWs& w, float* dfeat, cudaStream_t st) {
+// predict_from_embeddings (audionet_csine.py:210-211): logits = fc(emb)
+static int an_fc_fwd(sg_handle* h, const float* emb, int B, float* logits, cudaStream_t st) {
   SgAudioNet* an = h->an;
   SgConvArgs a;
   memset(&a, 0, sizeof(a));
-  a.A = dlogits; a.lda = an->Cp; a.W = an->Wfcb; a.out = w.demb; a.ldo = 32; a.rows = B; a.N = 32; a.cin = an->Cp;
+  a.A = emb; a.lda = 32; a.W = an->Wfc; a.bias = an->bfc; a.out = logits; a.ldo = an->Cp; a.rows = B; a.N = an->Cp; a.cin = 32;
+  a.taps = 1; a.epilogue = SG_EPI_BIAS; a.T = 1;
+  return sg_run_conv(h, a, false, SG_PROF_AUDIONET, st);
+}
+static int an_fc_bwd(sg_handle* h, const float* dlogits, int B, float* demb, cudaStream_t st) {
+  SgAudioNet* an = h->an;
+  SgConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.A = dlogits; a.lda = an->Cp; a.W = an->Wfcb; a.out = demb; a.ldo = 32; a.rows = B; a.N = 32; a.cin = an->Cp;
   a.taps = 1; a.epilogue = SG_EPI_NONE; a.T = 1;
-  SG_TRY(sg_run_conv(h, a, false, SG_PROF_AUDIONET, st));
+  return sg_run_conv(h, a, false, SG_PROF_AUDIONET, st);
+}
+static int an_cnn_fwd(sg_handle* h, const float* feat, int B, const AnWs& w, float* logits, cudaStream_t st) {
+  SG_TRY(an_emb_fwd(h, feat, B, w, w.emb, st));
+  return an_fc_fwd(h, w.emb, B, logits, st);
+}
+
+static int an_emb_bwd(sg_handle* h, const float* demb, int B, const AnWs& w, float* dfeat, cudaStream_t st);
+static int an_cnn_bwd(sg_handle* h, const float* dlogits, int B, const AnWs& w, float* dfeat, cudaStream_t st) {
+  SG_TRY(an_fc_bwd(h, dlogits, B, w.demb, st));
+  return an_emb_bwd(h, w.demb, B, w, dfeat, st);
+}
+static int an_emb_bwd(sg_handle* h, const float* demb, int B, const AnWs& w, float* dfeat, cudaStream_t st) {
+  SgAudioNet* an = h->an;
+  SgConvArgs a;
   h->launches += 1;
-  PROF(h, SG_PROF_AUDIONET, st, sg_globalmax_bwd_launch(w.a[6], w.demb, w.arg, w.g0, B, w.T[6], 32, st));   // dA8 (ReLU-masked)
+  PROF(h, SG_PROF_AUDIONET, st, sg_globalmax_bwd_launch(w.a[6], demb, w.arg, w.g0, B, w.T[6], 32, st));   // dA8 (ReLU-masked)
   float* gin = w.g0;
   float* gout = w.g1;
   for (int l = 6; l >= 0; --l) {
@@ -228,6 +248,29 @@ extern "C" int sg_audionet_cnn_bwd(sg_handle* h, const float* dlogits, int B, in
   if (!dlogits || !ws || !dfeat) { sg_set_error("sg_audionet_cnn_bwd: null pointer"); return SG_EINVAL; }
   AnWs w = an_ws_layout(ws, B, N, h->an->Cp, false);
   return an_cnn_bwd(h, dlogits, B, w, dfeat, (cudaStream_t)stream);
+}
+extern "C" int sg_audionet_emb_fwd(sg_handle* h, const float* feat, int B, int N, void* ws, float* emb, sg_stream stream) {
+  SG_TRY(an_check(h, B, N));
+  if (!feat || !ws || !emb) { sg_set_error("sg_audionet_emb_fwd: null pointer"); return SG_EINVAL; }
+  AnWs w = an_ws_layout(ws, B, N, h->an->Cp, false);
+  if (w.T[7] < 1) { sg_set_error("utterance too short for AudioNet's conv8 (N=%d)", N); return SG_EINVAL; }
+  return an_emb_fwd(h, feat, B, w, emb, (cudaStream_t)stream);
+}
+extern "C" int sg_audionet_emb_bwd(sg_handle* h, const float* demb, int B, int N, void* ws, float* dfeat, sg_stream stream) {
+  SG_TRY(an_check(h, B, N));
+  if (!demb || !ws || !dfeat) { sg_set_error("sg_audionet_emb_bwd: null pointer"); return SG_EINVAL; }
+  AnWs w = an_ws_layout(ws, B, N, h->an->Cp, false);
+  return an_emb_bwd(h, demb, B, w, dfeat, (cudaStream_t)stream);
+}
+extern "C" int sg_audionet_fc_fwd(sg_handle* h, const float* emb, int B, float* logits, sg_stream stream) {
+  SG_TRY(sg_check_handle(h, false));
+  if (!h->an || !emb || !logits || B < 1) { sg_set_error("sg_audionet_fc_fwd: AudioNet not loaded or bad argument"); return SG_EINVAL; }
+  return an_fc_fwd(h, emb, B, logits, (cudaStream_t)stream);
+}
+extern "C" int sg_audionet_fc_bwd(sg_handle* h, const float* dlogits, int B, float* demb, sg_stream stream) {
+  SG_TRY(sg_check_handle(h, false));
+  if (!h->an || !dlogits || !demb || B < 1) { sg_set_error("sg_audionet_fc_bwd: AudioNet not loaded or bad argument"); return SG_EINVAL; }
+  return an_fc_bwd(h, dlogits, B, demb, (cudaStream_t)stream);
 }
 extern "C" int sg_audionet_num_class_padded(const sg_handle* h) { return (h && h->an) ? h->an->Cp : 0; }
 extern "C" int sg_argmax_decide(sg_handle* h, const float* scores, int B, int S, int ld, float threshold, int64_t* decisions,

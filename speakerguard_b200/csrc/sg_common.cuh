@@ -24,6 +24,17 @@
 
 void sg_set_error(const char* fmt, ...);
 
+// One-time per-DEVICE setup (cudaFuncSetAttribute opt-ins and __constant__ uploads belong to a device's context, so a
+// process-global "done" flag would leave every device after the first one unconfigured).  Returns true the first time
+// it is called with `mask` while `device` is current; thread-safe.
+#include <atomic>
+static inline bool sg_first_on_device(std::atomic<unsigned long long>* mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return true;
+  const unsigned long long bit = 1ull << (dev & 63);
+  return (mask->fetch_or(bit) & bit) == 0;
+}
+
 #define SG_CUDA_CHECK(expr)                                                          \
   do {                                                                               \
     cudaError_t _e = (expr);                                                         \

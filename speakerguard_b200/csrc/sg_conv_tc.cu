@@ -618,8 +618,9 @@ static int g_deep_ring = 0;      // SGB200_TC_DEEP_RING=1: as many stages as fit
 static int g_issue_mode = 1;     // SGB200_TC_ISSUE: see TcArgs::issue_mode
 static int g_pair_bf16 = 2;      // SGB200_TC_PAIR_BF16: contractions on CTA pairs (cta_group::2): 1 bf16 long-K only, 2 all bf16 -> bf16, 3 / 4 see sg_conv_tc()
 
+static std::atomic<unsigned long long> g_tc_dev_init{0};
 static int tc_init() {
-  if (g_encode) return SG_OK;
+  if (!sg_first_on_device(&g_tc_dev_init)) return SG_OK;   // shared-memory opt-ins are per device
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);

@@ -214,6 +214,7 @@ struct DitherSpec {
   const float* tensor;   // [B, m, 400] for this pass
   uint32_t seed_lo, seed_hi;
   uint32_t pass;
+  uint32_t b_off;        // global index of utterance 0 (SG_OPT_UTT_OFFSET): the philox counter uses b + b_off
 };
 
 // Per-lane ownership of a frame: sample j = 64*n0 + 2*lane + e, n0 in [0,7), e in {0,1};
@@ -242,7 +243,7 @@ __device__ __forceinline__ void load_frame(Frame& F, const float* __restrict__ x
   } else if (D.mode == SG_DITHER_PHILOX) {
 #pragma unroll
     for (int h = 0; h < 4; ++h) {
-      uint4 r = philox4x32_10(make_uint4(h * 32 + lane, (uint32_t)fr, (uint32_t)b, D.pass),
+      uint4 r = philox4x32_10(make_uint4(h * 32 + lane, (uint32_t)fr, (uint32_t)b + D.b_off, D.pass),
                               make_uint2(D.seed_lo, D.seed_hi));
       float2 a = box_muller(r.x, r.y), c = box_muller(r.z, r.w);
       nz[4 * h] = a.x; nz[4 * h + 1] = a.y;
@@ -634,7 +635,7 @@ __global__ void dither_fill_kernel(int m, DitherSpec D, float* __restrict__ out)
   float* o = out + ((size_t)b * m + fr) * SG_WIN;
 #pragma unroll
   for (int h = 0; h < 4; ++h) {
-    uint4 r = philox4x32_10(make_uint4(h * 32 + lane, (uint32_t)fr, (uint32_t)b, D.pass),
+    uint4 r = philox4x32_10(make_uint4(h * 32 + lane, (uint32_t)fr, (uint32_t)b + D.b_off, D.pass),
                             make_uint2(D.seed_lo, D.seed_hi));
     float2 a = box_muller(r.x, r.y), c = box_muller(r.z, r.w);
     int j0 = 64 * (2 * h) + 2 * lane, j1 = 64 * (2 * h + 1) + 2 * lane;
@@ -779,10 +780,12 @@ static size_t feat_bwd_smem() {
   return sizeof(SgFeatTables) + (FEAT_WARPS * WARP_SCRATCH + FEAT_WARPS * SG_WIN + ACC_LEN) * sizeof(float);
 }
 
+// `pass` carries the pass counter in its low 32 bits and the handle's utterance offset in the high 32 (packed by
+// sg_api.cu: dither_pass())
 static DitherSpec make_dither(int mode, const float* tensor, uint64_t seed, uint64_t pass) {
   DitherSpec D;
   D.mode = mode; D.tensor = tensor;
-  D.seed_lo = (uint32_t)seed; D.seed_hi = (uint32_t)(seed >> 32); D.pass = (uint32_t)pass;
+  D.seed_lo = (uint32_t)seed; D.seed_hi = (uint32_t)(seed >> 32); D.pass = (uint32_t)pass; D.b_off = (uint32_t)(pass >> 32);
   return D;
 }
 
@@ -865,12 +868,10 @@ int sg_step_linf_launch(float* x, const float* x0, const float* grad, size_t n, 
 static int cmvn_dispatch(const float* in, int ld_in, float* out, int ld_out, int B, int T, int ncol, int backward, dim3 grid,
                          cudaStream_t st) {
   if (T > CMN_WIN && T <= CMN_PREFIX_MAX_T) {
-    static bool attr = false;
-    if (!attr) {
+    static std::atomic<unsigned long long> configured{0};
+    if (sg_first_on_device(&configured))
       SG_CUDA_CHECK(cudaFuncSetAttribute(cmvn_prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (CMN_PREFIX_MAX_T + 1) * 32 * (int)sizeof(double)));
-      attr = true;
-    }
     cmvn_prefix_kernel<<<grid, dim3(32, 8), (size_t)(T + 1) * 32 * sizeof(double), st>>>(in, ld_in, out, ld_out, T, ncol, backward);
   } else {
     cmvn_kernel<<<grid, dim3(32, 8), 0, st>>>(in, ld_in, out, ld_out, T, ncol, backward);

@@ -11,15 +11,17 @@ struct SgProf {
   bool on = false;
   std::vector<cudaEvent_t> ev;      // pairs (start, stop)
   std::vector<int> cat;             // category of pair i
+  std::vector<int> tag;             // caller-defined label of pair i (TDNN layer 1..5; 0 = none)
+  int next_tag = 0;                 // label of the next recorded launch (reset to 0 after each one)
   size_t used = 0;                  // pairs recorded since the last reset
   cudaEvent_t* begin(int c, cudaStream_t st) {
     if (!on) return nullptr;
     if (used == cat.size()) {
       cudaEvent_t a, b;
       if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return nullptr;
-      ev.push_back(a); ev.push_back(b); cat.push_back(c);
+      ev.push_back(a); ev.push_back(b); cat.push_back(c); tag.push_back(0);
     }
-    cat[used] = c;
+    cat[used] = c; tag[used] = next_tag; next_tag = 0;
     cudaEventRecord(ev[2 * used], st);
     return &ev[2 * used + 1];
   }
@@ -37,6 +39,7 @@ struct sg_handle {
   long long launches = 0;
   int l1_tap_form = 1;              // SG_OPT_L1_TAP_FORM: bf16 mode computes the layer-1 dgrad per tap (K = 512) + a shifted sum
   int feat_stash = 1;               // SG_OPT_FEAT_STASH: the fused attack loop hands the per-frame forward state to the MFCC adjoint
+  int utt_offset = 0;               // SG_OPT_UTT_OFFSET: global index of utterance 0 (philox dither key)
   int pool_fusion = 1;              // SG_OPT_POOL_FUSION: bf16 mode contracts the pooling adjoint inside the layer-5 dgrad
   SgFeatTables* d_tables = nullptr;
   bool xv_loaded = false;

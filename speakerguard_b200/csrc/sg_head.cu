@@ -383,6 +383,12 @@ __global__ void loss_kernel(const float* __restrict__ scores, const long long* _
   const int lab = (int)y[b];
   if (ds) for (int n = lane; n < S; n += 32) ds[n] = 0.f;
   __syncwarp();
+  // Labels the reference rejects (an index error for label >= S, the SV assert at attack/utils.py:50 for labels outside
+  // {0, -1}) cannot raise from a kernel: they give a NaN loss and a zero gradient instead of an out-of-bounds read.
+  if (lab < -1 || lab >= S || (lp.task == SG_TASK_SV && lab > 0)) {
+    if (lane == 0) loss[b] = __int_as_float(0x7fc00000);
+    return;
+  }
   float L = 0.f;
   if (lp.loss == SG_LOSS_CE && lp.task == SG_TASK_CSI) {
     if (lab >= 0) {

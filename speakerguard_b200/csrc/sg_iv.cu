@@ -455,9 +455,9 @@ __global__ void transpose_batched_kernel(const float* __restrict__ in, float* __
 // ---------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------
-static bool g_delta_init = false;
+static std::atomic<unsigned long long> g_delta_init{0};   // per device: __constant__ memory belongs to a device's context
 static int delta_init() {
-  if (g_delta_init) return SG_OK;
+  if (!sg_first_on_device(&g_delta_init)) return SG_OK;
   // get_scales(window 3, order 2): first filter j/28 for j=-3..3, second = first convolved with itself
   float d1[7], d2[13];
   for (int j = -3; j <= 3; ++j) d1[j + 3] = (float)j / 28.f;
@@ -467,7 +467,6 @@ static int delta_init() {
   for (int i = 0; i < 13; ++i) d2[i] *= 1.f / 28.f;
   SG_CUDA_CHECK(cudaMemcpyToSymbol(c_delta1, d1, sizeof(d1)));
   SG_CUDA_CHECK(cudaMemcpyToSymbol(c_delta2, d2, sizeof(d2)));
-  g_delta_init = true;
   return SG_OK;
 }
 static int iv_blocks(size_t n) { size_t b = (n + 255) / 256; return (int)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b)); }
@@ -505,13 +504,15 @@ int sg_softmax_rows_launch(const float* a, const float* b, float* out, int rows,
 }
 static size_t chol_smem(int D) { return ((size_t)D + 8 * CH_NB + (size_t)D * CH_LD) * sizeof(double); }
 static int chol_init(int D) {
-  static int configured = 0;
+  static int configured[64] = {0};                         // per device (function attributes are per context)
   const int need = (int)chol_smem(D);
   if (need > 227 * 1024) { sg_set_error("i-vector dimension %d too large for the shared-memory panel (max 800)", D); return SG_EINVAL; }
-  if (need > configured) {
+  int dev = 0;
+  SG_CUDA_CHECK(cudaGetDevice(&dev));
+  if (need > configured[dev & 63]) {
     SG_CUDA_CHECK(cudaFuncSetAttribute(chol_factor_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
     SG_CUDA_CHECK(cudaFuncSetAttribute(chol_solve_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
-    configured = need;
+    configured[dev & 63] = need;
   }
   return SG_OK;
 }

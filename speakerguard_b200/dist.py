@@ -37,6 +37,24 @@ def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def sharded_attack(attacker, x: torch.Tensor, y: torch.Tensor, rank: int, world: int, device=None):
+    """Strong-scaling form of ``attacker.attack(x, y)``: rank r attacks x[lo:hi] of the *global* batch on its
+    own GPU, no data-path collective.  The attacker's ``utt_offset`` is set to ``lo`` so the in-kernel philox dither is keyed
+    on the global utterance index: concatenating the ranks' results reproduces the single-GPU attack bit for bit.
+    -> (adv [hi-lo,1,N], success list, (lo, hi))"""
+    lo, hi = shard_bounds(x.shape[0], rank, world)
+    xs, ys = x[lo:hi], y[lo:hi]
+    if device is not None:
+        xs, ys = xs.to(device, non_blocking=True), ys.to(device, non_blocking=True)
+    prev = getattr(attacker, "utt_offset", 0)
+    attacker.utt_offset = lo
+    try:
+        adv, success = attacker.attack(xs, ys)
+    finally:
+        attacker.utt_offset = prev
+    return adv, success, (lo, hi)
+
+
 def attack_metrics(x: torch.Tensor, adv: torch.Tensor, success) -> torch.Tensor:
     """Local sums [n, n_success, sum SNR(dB), sum L2, sum Linf] as one fp64 vector on x's device."""
     x2, a2 = x.flatten(1).double(), adv.detach().flatten(1).double()

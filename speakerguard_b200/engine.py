@@ -37,23 +37,60 @@ def make_loss_params(loss_name: str = "Entropy", targeted: bool = False, task: s
     if loss_name not in ("Entropy", "Margin"):
         raise ValueError("loss must be 'Entropy' or 'Margin'")
     margin = task in ("SV", "OSI") or loss_name == "Margin"
-    thr = 0.0 if threshold is None or not math.isfinite(threshold) else float(threshold)
+    if threshold is None:
+        # the reference's margin loss does arithmetic on the threshold for SV / OSI (attack/utils.py:48-61, :73-91) and would
+        # raise a TypeError on None; CSI never reads it
+        if margin and task in ("SV", "OSI"):
+            raise ValueError(f"task {task} needs the model's threshold for the margin loss (got None)")
+        thr = 0.0
+    else:
+        thr = float(threshold)                       # -inf (a model built without a threshold) is passed through as is
+        if math.isnan(thr):
+            raise ValueError("threshold is NaN")
     return LossParams(_lib.LOSS_MARGIN if margin else _lib.LOSS_CE, _lib.TASKS[task], int(bool(targeted)),
                       int(bool(clip_max)), float(confidence), thr)
 
 
+def grad_sign_of(loss_name: str, targeted: bool) -> float:
+    """The update direction resolve_loss pairs with a loss (attack/utils.py:114).  It follows the loss *name*: SV / OSI with
+    loss='Entropy' run the margin loss but keep the cross-entropy sign."""
+    return float(1 - 2 * int(bool(targeted))) if loss_name == "Entropy" else -1.0
+
+
+class _BoundLib:
+    """libsgb200's entry points, called with the engine's device current: a handle is bound to one device and its kernels,
+    events and per-device function attributes must land there whatever ``torch.cuda.current_device()`` is."""
+
+    def __init__(self, lib, device: torch.device):
+        self._lib, self._device = lib, device
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        dev = self._device
+
+        def call(*args):
+            if torch.cuda.current_device() == dev.index:
+                return fn(*args)
+            with torch.cuda.device(dev):
+                return fn(*args)
+
+        call.__name__ = name
+        setattr(self, name, call)
+        return call
+
+
 class Engine:
     def __init__(self, device="cuda:0", precision: str = "fp32"):
-        self.lib = _lib.load()
+        lib = _lib.load()
         dev = torch.device(device)
         if dev.type != "cuda":
             raise _lib.SgError(f"speakerguard_b200 runs on CUDA devices only (got '{device}'); there is no CPU fallback")
         if dev.index is None:
             dev = torch.device("cuda", torch.cuda.current_device())
         self.device = dev
+        self.lib = _BoundLib(lib, dev)
         self._h = C.c_void_p()
-        with torch.cuda.device(dev):
-            check(self.lib.sg_create(C.byref(self._h), dev.index), "sg_create")
+        check(self.lib.sg_create(C.byref(self._h), dev.index), "sg_create")
         self.L = self.S = 0
         self.set_precision(precision)
 
@@ -71,6 +108,14 @@ class Engine:
     def set_option(self, option: int, value: int) -> None:
         """Engine options of include/sgb200.h (SG_OPT_*)."""
         check(self.lib.sg_set_option(self._h, int(option), int(value)), "sg_set_option")
+
+    def set_utt_offset(self, offset: int) -> None:
+        """Global index of the first utterance of the batches this engine is given (SG_OPT_UTT_OFFSET): the philox dither is
+        keyed on (seed, pass, global utterance, frame, sample), so rank r of a G-way contiguous split that sets r * B / G
+        draws exactly the noise the unsharded run draws for those utterances."""
+        if offset != getattr(self, "_utt_offset", 0):
+            self.set_option(_lib.OPT_UTT_OFFSET, offset)
+            self._utt_offset = int(offset)
 
     @property
     def stream(self):
@@ -93,6 +138,15 @@ class Engine:
             check(self.lib.sg_profile_read(self._h, c, C.byref(ms), C.byref(n)), "sg_profile_read")
             out[self.lib.sg_profile_name(c).decode()] = (ms.value, n.value)
         return out
+
+    def profile_dump(self):
+        """[(category name, tag, ms)] for every launch recorded since profile(True), in launch order; synchronises."""
+        n = C.c_int()
+        check(self.lib.sg_profile_dump(self._h, None, None, None, 0, C.byref(n)), "sg_profile_dump")
+        cats, tags, ms = (C.c_int * n.value)(), (C.c_int * n.value)(), (C.c_float * n.value)()
+        check(self.lib.sg_profile_dump(self._h, cats, tags, ms, n.value, C.byref(n)), "sg_profile_dump")
+        names = [self.lib.sg_profile_name(c).decode() for c in range(_lib.PROF_COUNT)]
+        return [(names[cats[i]], int(tags[i]), float(ms[i])) for i in range(n.value)]
 
     def load_xv(self, p: Dict[str, torch.Tensor], bn_eps: float = 1e-5) -> None:
         """p: 'tdnn{1..5}.weight/.bias', 'bn{1..5}.mean/.var', 'fc1.weight/.bias', 'emb_mean',
@@ -302,6 +356,35 @@ class Engine:
         check(self.lib.sg_audionet_cnn_bwd(self._h, _ptr(dl), B, N, _ptr(ws), _ptr(dfeat), self.stream), "sg_audionet_cnn_bwd")
         return dfeat
 
+    def an_emb_fwd(self, feat: torch.Tensor, N: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """feat [B,T,32] -> (emb [B,32] = extract_emb, workspace for an_emb_bwd)."""
+        feat = _f32c(feat, self.device)
+        B = feat.shape[0]
+        ws = self.an_ws(B, N)
+        emb = torch.empty(B, 32, device=self.device, dtype=torch.float32)
+        check(self.lib.sg_audionet_emb_fwd(self._h, _ptr(feat), B, N, _ptr(ws), _ptr(emb), self.stream), "sg_audionet_emb_fwd")
+        return emb, ws
+
+    def an_emb_bwd(self, demb: torch.Tensor, ws: torch.Tensor, B: int, N: int) -> torch.Tensor:
+        demb = _f32c(demb, self.device)
+        dfeat = torch.empty(B, self.an_num_frames(N), 32, device=self.device, dtype=torch.float32)
+        check(self.lib.sg_audionet_emb_bwd(self._h, _ptr(demb), B, N, _ptr(ws), _ptr(dfeat), self.stream), "sg_audionet_emb_bwd")
+        return dfeat
+
+    def an_fc_fwd(self, emb: torch.Tensor) -> torch.Tensor:
+        emb = _f32c(emb, self.device)
+        logits = torch.empty(emb.shape[0], self.an_cp, device=self.device, dtype=torch.float32)
+        check(self.lib.sg_audionet_fc_fwd(self._h, _ptr(emb), emb.shape[0], _ptr(logits), self.stream), "sg_audionet_fc_fwd")
+        return logits[:, :self.an_classes]
+
+    def an_fc_bwd(self, dlogits: torch.Tensor) -> torch.Tensor:
+        B = dlogits.shape[0]
+        dl = torch.zeros(B, self.an_cp, device=self.device, dtype=torch.float32)
+        dl[:, :self.an_classes] = dlogits
+        demb = torch.empty(B, 32, device=self.device, dtype=torch.float32)
+        check(self.lib.sg_audionet_fc_bwd(self._h, _ptr(dl), B, _ptr(demb), self.stream), "sg_audionet_fc_bwd")
+        return demb
+
     def cw2_audionet_run(self, x: torch.Tensor, y: torch.Tensor, *, lp: LossParams, binary_search_steps: int, max_iter: int,
                          stop_early: bool, stop_early_iter: int, lr: float, initial_const: float,
                          decision_threshold: float = -math.inf):
@@ -475,8 +558,11 @@ class Engine:
     def pgd_run(self, x_adv: torch.Tensor, x0: torch.Tensor, y: torch.Tensor, *, max_iter: int, epsilon: float,
                 step_size: float, lp: LossParams, dither_mode: int = _lib.DITHER_PHILOX,
                 dither: Optional[torch.Tensor] = None, seed: int = 0, eot_size: int = 1,
-                decision_threshold: float = -math.inf, ws: Optional[torch.Tensor] = None, want_loss_hist: bool = False):
-        """x_adv [B,N] is updated in place.  Returns (decisions [B] i64, scores [B,S], loss_hist or None)."""
+                decision_threshold: float = -math.inf, ws: Optional[torch.Tensor] = None, want_loss_hist: bool = False,
+                grad_sign: float = 0.0, utt_offset: int = 0):
+        """x_adv [B,N] is updated in place.  Returns (decisions [B] i64, scores [B,S], loss_hist or None).
+        grad_sign: the sign resolve_loss returned (0 derives it from ``lp``); utt_offset: global index of this shard's first
+        utterance (keys the philox dither so that a sharded run reproduces the unsharded one bit for bit)."""
         assert x_adv.is_contiguous() and x_adv.dtype == torch.float32 and x_adv.device == self.device
         x0 = _f32c(x0, self.device)
         y = y.to(device=self.device, dtype=torch.int64).contiguous()
@@ -488,7 +574,8 @@ class Engine:
         hist = torch.empty(max_iter + 1, B, device=self.device, dtype=torch.float32) if want_loss_hist else None
         d = None if dither is None else _f32c(dither, self.device)
         pp = PgdParams(int(max_iter), float(epsilon), float(step_size), int(eot_size), int(dither_mode), int(seed), lp,
-                       float(decision_threshold))
+                       float(decision_threshold), float(grad_sign))
+        self.set_utt_offset(utt_offset)
         check(self.lib.sg_pgd_run(self._h, _ptr(x_adv), _ptr(x0), _ptr(y), _ptr(d), B, N, C.byref(pp), _ptr(ws), _ptr(dec),
                                   _ptr(scores), _ptr(hist), self.stream), "sg_pgd_run")
         return dec, scores, hist

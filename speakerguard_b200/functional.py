@@ -117,6 +117,34 @@ class AnCnnFn(torch.autograd.Function):
         return ctx.eng.an_cnn_bwd(g.contiguous(), ctx.ws, B, N), None, None
 
 
+class AnEmbFn(torch.autograd.Function):
+    """log-mel [B,T,32] -> AudioNet embedding [B,32]  (sg_audionet_emb_fwd / _bwd; extract_emb of the reference)."""
+
+    @staticmethod
+    def forward(ctx, feat, eng: Engine, N: int):
+        emb, ws = eng.an_emb_fwd(feat.contiguous(), N)
+        ctx.eng, ctx.ws, ctx.dims = eng, ws, (feat.shape[0], N)
+        return emb
+
+    @staticmethod
+    def backward(ctx, g):
+        B, N = ctx.dims
+        return ctx.eng.an_emb_bwd(g.contiguous(), ctx.ws, B, N), None, None
+
+
+class AnFcFn(torch.autograd.Function):
+    """AudioNet embedding [B,32] -> logits [B,C]  (sg_audionet_fc_fwd / _bwd; predict_from_embeddings)."""
+
+    @staticmethod
+    def forward(ctx, emb, eng: Engine):
+        ctx.eng = eng
+        return eng.an_fc_fwd(emb.contiguous()).contiguous()
+
+    @staticmethod
+    def backward(ctx, g):
+        return ctx.eng.an_fc_bwd(g.contiguous()), None
+
+
 class Mfcc24Fn(torch.autograd.Function):
     """x [B,N] -> the first ``num_ceps`` MFCCs [B,m,num_ceps] (iv_plda.raw asks kaldi.mfcc for 24 of the
     30 cepstra, model/iv_plda.py:203-237; lifter and DCT columns do not depend on num_ceps)."""

@@ -20,7 +20,7 @@ import torch.nn as nn
 
 from .. import _lib
 from ..engine import Engine
-from ..functional import AnCnnFn, AnCnnTrainFn, AnLogMelFn
+from ..functional import AnCnnFn, AnCnnTrainFn, AnEmbFn, AnFcFn, AnLogMelFn
 from .utils import check_input_range
 
 _CONVS = ["conv2", "conv3", "conv4", "conv5", "conv6", "conv7", "conv8"]
@@ -140,16 +140,32 @@ class audionet_csine(nn.Module):
         """x: (B, 1, T) in [-1,1] -> log-mel (B, frames, 32)."""
         return AnLogMelFn.apply(x[:, 0, :], self.engine)
 
+    def _eval_only(self, what):
+        if self.training:
+            raise NotImplementedError(f"{what} is built for eval() mode (running-statistics BatchNorm); the train-mode kernels "
+                                      "fuse the CNN with the final fc")
+        self._sync_engine()
+
     def extract_emb(self, x):
-        raise NotImplementedError("the engine fuses extract_emb and the final fc; use forward()/score()")
+        """x: (B, T, F) log-mel -> (B, 32) embedding (audionet_csine.py:176-207)."""
+        self._eval_only("extract_emb")
+        return AnEmbFn.apply(x, self.engine, (x.shape[1] - 1) * 160 + 1)
 
     def embedding(self, x, flag=0):
-        raise NotImplementedError("the engine fuses extract_emb and the final fc; use forward()/score()")
+        """x: wav (flag 0) or log-mel (flag 1) -> (B, 32) (audionet_csine.py:159-173)."""
+        assert flag in self.allowed_flags
+        feats = self.compute_feat(x, flag=1) if flag == 0 else x
+        return self.extract_emb(feats)
+
+    def predict_from_embeddings(self, x):
+        self._eval_only("predict_from_embeddings")
+        return AnFcFn.apply(x, self.engine)
 
     def forward(self, x, flag=0, return_emb=False, enroll_embs=None):
         assert flag in self.allowed_flags
         if return_emb:
-            raise NotImplementedError("return_emb is not supported by the fused AudioNet CNN")
+            embedding = self.embedding(x, flag=flag)
+            return self.predict_from_embeddings(embedding), embedding
         if flag == 0:
             n = x.shape[2]
             feats = self.compute_feat(x, flag=1)

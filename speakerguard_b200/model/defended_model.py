@@ -60,15 +60,25 @@ class defended_model(nn.Module):
         return xx
 
     def _averaged(self, x, fn):
-        """mean over all defenses of fn(defended input, flag) (tuple outputs are averaged member-wise)."""
+        """mean over all defenses of fn(defended input, flag) (tuple outputs are averaged member-wise).
+
+        Like the reference (model/defended_model.py:79-91, :108-124, :143-153) the members after the first are added through
+        ``.data`` and the division is done on ``.data``: the returned *values* are the mean, but autograd only sees the first
+        member's graph, with weight 1.  An adaptive attack through an 'average' ensemble therefore follows the first
+        defense's gradient - kept as is, because sign steps would differ otherwise."""
         acc = None
         for flag in self._levels():
             xx = x.clone() if flag == 0 else self.base_model.compute_feat(x, flag=flag)
             for d in self.flag2defense[flag]:
                 out = fn(d(xx), flag)
                 out = out if isinstance(out, tuple) else (out,)
-                acc = list(out) if acc is None else [a + o for a, o in zip(acc, out)]
-        acc = [a / len(self.defense) for a in acc]
+                if acc is None:
+                    acc = list(out)
+                else:
+                    for a, o in zip(acc, out):
+                        a.data += o.data
+        for a in acc:
+            a.data /= len(self.defense)
         return acc[0] if len(acc) == 1 else tuple(acc)
 
     def embedding(self, x):

@@ -68,6 +68,9 @@ class xv_plda(nn.Module):
             self.num_spks, self.spk_ids, self.z_norm_means, self.z_norm_stds, self.enroll_embs = \
                 parse_enroll_model_file(model_file, self.device)
             p["enroll"] = self.enroll_embs
+            # the fused paths score against the copy the engine took here: remember which tensor (and which version of it)
+            # that was, so a later assignment to / in-place edit of model.enroll_embs falls back to the stage-wise path
+            self._engine_enroll = (self.enroll_embs, self.enroll_embs._version)
         else:
             p["enroll"] = torch.zeros(1, mean.shape[0])     # placeholder; forward() then requires enroll_embs
         self.engine.load_xv(p)
@@ -146,15 +149,20 @@ class xv_plda(nn.Module):
         x2 = (x[:, 0, :] / float(2 ** 15)).contiguous()
         B, N = x2.shape
         mode, d = self._draw_dither(B, self.engine.num_frames(N))
-        key = (B, N)
-        if getattr(self, "_fwd_ws_key", None) != key:
-            self._fwd_ws, self._fwd_ws_key = self.engine.pgd_ws(B, N), key
-        out = self.engine.xv_forward(x2, mode, d, self.seed, self._pass, self.decision_threshold, ws=self._fwd_ws)
+        # the engine keeps (and grows) one scratch block per stream; asking each time never pins a stale block
+        out = self.engine.xv_forward(x2, mode, d, self.seed, self._pass, self.decision_threshold,
+                                     ws=self.engine.pgd_ws(B, N))
         self._pass += 1
         return out
 
+    def engine_enroll_current(self) -> bool:
+        """True while ``self.enroll_embs`` is still the tensor (same object, unmodified) the engine copied at construction."""
+        held = getattr(self, "_engine_enroll", None)
+        cur = getattr(self, "enroll_embs", None)
+        return held is not None and cur is held[0] and cur._version == held[1]
+
     def _can_fuse(self, x, flag, enroll_embs):
-        return (flag == 0 and enroll_embs is None and hasattr(self, "enroll_embs")
+        return (flag == 0 and enroll_embs is None and self.engine_enroll_current()
                 and not (torch.is_grad_enabled() and x.requires_grad))
 
     def forward(self, x, flag=0, return_emb=False, enroll_embs=None):

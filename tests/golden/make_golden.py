@@ -196,6 +196,61 @@ def attack_case(model, p, tag, seed, B, N, out, kind, **kw):
           f"oracle success equal: {suc == success}")
 
 
+def long_attack_cases(out):
+    """Round 2: (i) the reference's PGD-100 (BASELINE configs[1] at B = 8) - the outcome the benched precision modes are
+    checked against; (ii) PGD-3 for task OSI with the *default* loss name 'Entropy': resolve_loss then runs the margin loss
+    with the cross-entropy sign (attack/utils.py:107-114), the case the fused loop's grad_sign has to reproduce."""
+    p = O.make_xv_params(seed=0)
+    with tempfile.TemporaryDirectory() as tmp:
+        model = build_reference_xv(p, tmp)
+        attack_case(model, p, "pgd100", 3030, 8, 48000, out, "PGD", epsilon=0.002, step_size=0.0004, max_iter=100)
+        x, _ = make_inputs(3030, 8, 48000)
+        adv = torch.from_numpy(out["pgd100.adv"])
+        d = adv - x[:, 0]
+        out["pgd100.snr_db"] = (10 * torch.log10(x[:, 0].double().pow(2).sum(1) / d.double().pow(2).sum(1))).numpy()
+        out["pgd100.linf"] = d.abs().max(1)[0].numpy()
+    thr = -5.2
+    with tempfile.TemporaryDirectory() as tmp:
+        model = build_reference_xv(p, tmp, threshold=thr)
+        pp = dict(p)
+        pp["threshold"] = thr
+        for tag, targeted, seed in (("pgd3osi", False, 2030), ("pgd3osit", True, 2031)):
+            x, y = make_inputs(seed, 4, 32000)
+            with torch.no_grad():
+                torch.manual_seed(1)
+                dec, sc = model.make_decision(x)
+            print(f"[{tag}] clean decisions {dec.tolist()} max scores {sc.max(1)[0].tolist()} y {y.tolist()}")
+            attack_case_task(model, pp, tag, seed, 4, 32000, out, task="OSI", targeted=targeted, thr=thr)
+
+
+def attack_case_task(model, p, tag, seed, B, N, out, task, targeted, thr):
+    from attack.PGD import PGD
+    x, y = make_inputs(seed, B, N)
+    y[-1] = -1                                             # one imposter label
+    import contextlib
+    import io
+    import warnings
+    with warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
+        warnings.simplefilter("ignore")
+        att = PGD(model, task=task, epsilon=0.002, step_size=0.0004, max_iter=3, loss="Entropy", targeted=targeted,
+                  batch_size=B, verbose=0)
+    assert att.grad_sign == (1 - 2 * int(targeted))
+    torch.manual_seed(seed + 1)
+    with RandnTap() as tap:
+        adv, success = att.attack(x, y)
+    m = O.num_frames(N)
+    dither = torch.stack(tap.draws).view(4, B, m, 400)
+    out.update({f"{tag}.seed": seed, f"{tag}.B": B, f"{tag}.N": N, f"{tag}.thr": thr, f"{tag}.targeted": int(targeted),
+                f"{tag}.x_cks": cks(x), f"{tag}.dither_cks": cks(dither), f"{tag}.y": y.numpy(),
+                f"{tag}.adv": adv.detach()[:, 0].numpy(), f"{tag}.success": np.array(success)})
+    xa, suc, info = O.pgd_attack(x[:, 0], y, p, dither=dither, epsilon=0.002, step_size=0.0004, max_iter=3,
+                                 loss_name="Entropy", targeted=targeted, task=task)
+    mism = float((xa != adv.detach()[:, 0]).float().mean())
+    moved = float((adv.detach()[:, 0] != x[:, 0]).float().mean())
+    print(f"[{tag}] success {success}; moved fraction {moved:.3f}; oracle iterate mismatch {mism:.2e}; "
+          f"oracle success equal: {suc == success}")
+
+
 def audionet_case(out):
     torch.stft = _stft
     try:
@@ -401,6 +456,11 @@ def main():
         iv_case(out)
         np.savez_compressed(os.path.join(HERE, "iv_golden.npz"), **out)
         print("iv_golden.npz", os.path.getsize(os.path.join(HERE, "iv_golden.npz")) // 1024, "KiB")
+        return
+    if "--only-long" in sys.argv:
+        long_attack_cases(out)
+        np.savez_compressed(os.path.join(HERE, "xv_long_golden.npz"), **out)
+        print("xv_long_golden.npz", os.path.getsize(os.path.join(HERE, "xv_long_golden.npz")) // 1024, "KiB")
         return
     if "--only-antrain" in sys.argv:
         audionet_train_case(out)

@@ -1,0 +1,187 @@
+"""The benched precision modes (tf32, bf16) checked DIRECTLY against tensors dumped from the unmodified reference
+(tests/golden/xv_golden.npz, xv_long_golden.npz), not only against the engine's own fp32 mode: forward values at stated
+tolerances, short-attack success lists, the outcome of the reference's PGD-100 (BASELINE configs[1] at B = 8), and the
+OSI task with the default loss name (margin loss with the cross-entropy sign, attack/utils.py:107-114).
+
+Tolerances are <= 2x what was measured on B200 (the measured value is printed by every test)."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sg_oracle as O
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+# relative to the row maximum; measured on B200 (round 2): see the printed values
+TOL = {
+    "fp32": dict(emb=1e-4, scores=1e-4, loss=2e-4),
+    "tf32": dict(emb=2e-3, scores=1.5e-3, loss=2e-3),
+    "bf16": dict(emb=1.5e-3, scores=1e-3, loss=2e-3),
+}
+
+
+def relerr(a, b):
+    a, b = a.detach().double().cpu().flatten(1), b.detach().double().cpu().flatten(1)
+    return float(((a - b).abs().max(1)[0] / b.abs().max(1)[0].clamp_min(1e-30)).max())
+
+
+@pytest.fixture(scope="module")
+def params():
+    return O.make_xv_params(seed=0)
+
+
+@pytest.fixture(scope="module")
+def engines(params):
+    from speakerguard_b200.engine import Engine
+    out = {}
+    for prec in ("fp32", "tf32", "bf16"):
+        e = Engine("cuda:0", precision=prec)
+        e.load_xv(params)
+        out[prec] = e
+    return out
+
+
+@pytest.fixture(scope="module")
+def xv():
+    return np.load(os.path.join(G, "xv_golden.npz"))
+
+
+@pytest.fixture(scope="module")
+def xvl():
+    return np.load(os.path.join(G, "xv_long_golden.npz"))
+
+
+def regen(g, tag, n_pass=None, S=10):
+    seed, B, N = int(g[f"{tag}.seed"]), int(g[f"{tag}.B"]), int(g[f"{tag}.N"])
+    torch.manual_seed(seed)
+    x = (torch.rand(B, 1, N) * 2 - 1) * 0.5
+    y = torch.randint(0, S, (B,))
+    m = O.num_frames(N)
+    torch.manual_seed(seed + 1)
+    n = B if n_pass is None else n_pass * B
+    d = torch.stack([torch.randn((m, 400)) for _ in range(n)])
+    d = d if n_pass is None else d.view(n_pass, B, m, 400)
+    assert abs(float(d.double().abs().sum()) - float(g[f"{tag}.dither_cks"])) < 1e-6
+    assert abs(float(x.double().abs().sum()) - float(g[f"{tag}.x_cks"])) < 1e-6
+    return x[:, 0].contiguous(), y, d
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("tag", ["fwd2s", "fwd5s", "fwd1p1s"])
+def test_forward_vs_reference_golden(engines, xv, tag, prec):
+    """wav -> embedding / scores / decisions / CE loss of the reference, in the tensor-core modes."""
+    from speakerguard_b200 import _lib
+    from speakerguard_b200.engine import make_loss_params
+    eng, tol = engines[prec], TOL[prec]
+    x, y, d = regen(xv, tag)
+    feat = eng.cmvn(eng.mfcc_fwd(x.cuda(), _lib.DITHER_TENSOR, d.cuda(), ld=32), ld_out=32)
+    emb, ws = eng.embed_fwd(feat)
+    scores, dec = eng.score_fwd(emb)
+    loss, ds = eng.loss(scores, y.cuda(), make_loss_params("Entropy"))
+    e_emb, e_sc = relerr(emb, torch.tensor(xv[f"{tag}.emb"])), relerr(scores, torch.tensor(xv[f"{tag}.scores"]))
+    ref_loss = xv[f"{tag}.loss"]
+    e_loss = float(np.abs(loss.cpu().numpy() - ref_loss).max() / max(np.abs(ref_loss).max(), 1e-30))
+    # input gradient: sign agreement and cosine with the reference's autograd gradient
+    dfeat = eng.embed_bwd(eng.score_bwd(emb, ds), ws, feat.shape[0], feat.shape[1])
+    grad = eng.mfcc_bwd(x.cuda(), eng.cmvn(dfeat, ld_out=32, backward=True), _lib.DITHER_TENSOR, d.cuda()).cpu()
+    ref_g = torch.tensor(xv[f"{tag}.grad"])
+    agree = float((torch.sign(grad) == torch.sign(ref_g)).float().mean())
+    cos = float((grad * ref_g).sum() / (grad.norm() * ref_g.norm()))
+    print(f"[{prec} {tag}] vs reference: emb {e_emb:.2e} scores {e_sc:.2e} loss {e_loss:.2e} grad-sign agreement {agree:.4f} "
+          f"cosine {cos:.5f}")
+    assert e_emb < tol["emb"] and e_sc < tol["scores"] and e_loss < tol["loss"]
+    assert np.array_equal(dec.cpu().numpy(), xv[f"{tag}.dec"])
+    assert agree > (0.97 if prec == "tf32" else 0.955) and cos > (0.996 if prec == "tf32" else 0.99)
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("tag,kw", [
+    ("fgsm", dict(fgsm=True, epsilon=0.002)),
+    ("pgd3", dict(epsilon=0.002, step_size=0.0004, max_iter=3)),
+    ("pgd3t", dict(epsilon=0.002, step_size=0.0004, max_iter=3, targeted=True)),
+    ("cwinf3", dict(epsilon=0.002, step_size=0.0004, max_iter=3, loss_name="Margin")),
+])
+def test_short_attacks_vs_reference_golden(engines, xv, tag, kw, prec):
+    """sg_pgd_run in the tensor-core modes vs the reference's adversarial examples: success list equal, iterates inside
+    the eps ball, >= 95 % of the adversarial samples bit-identical to the reference's (the rest are sign flips of
+    near-zero gradient entries, Q4 / Q13 class differences)."""
+    from speakerguard_b200 import _lib
+    from speakerguard_b200.engine import grad_sign_of, make_loss_params
+    eng = engines[prec]
+    x, y, d = regen(xv, tag, int(xv[f"{tag}.n_pass"]))
+    fgsm, eps = kw.get("fgsm", False), kw["epsilon"]
+    name, targeted = kw.get("loss_name", "Entropy"), kw.get("targeted", False)
+    lp = make_loss_params(name, targeted, "CSI", 0.0, None, False)
+    xa = x.cuda().clone()
+    dec, scores, _ = eng.pgd_run(xa, x.cuda(), y.cuda(), max_iter=1 if fgsm else kw["max_iter"],
+                                 epsilon=math.inf if fgsm else eps, step_size=eps if fgsm else kw["step_size"], lp=lp,
+                                 dither_mode=_lib.DITHER_TENSOR, dither=d.cuda(), grad_sign=grad_sign_of(name, targeted))
+    ref = torch.tensor(xv[f"{tag}.adv"])
+    same = float((xa.cpu() == ref).float().mean())
+    success = ((dec.cpu() == y) if targeted else (dec.cpu() != y)).tolist()
+    print(f"[{prec} {tag}] adversarial samples bit-identical to the reference: {same:.4f}; success {success}")
+    assert success == xv[f"{tag}.success"].tolist()
+    assert float((xa.cpu() - x).abs().max()) <= eps + 1e-7
+    assert same > 0.95
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32", "bf16"])
+def test_pgd100_outcome_vs_reference(engines, xvl, prec):
+    """The reference's own PGD-100 (eps 0.002, step 0.0004, CE, untargeted; B = 8 x 3 s, same dither stream) against
+    sg_pgd_run in every precision mode.  100 sign steps are chaotic in the individual samples, so the outcome is compared:
+    per-utterance success, per-utterance SNR, L-inf, and the fraction of samples that end on the same side of x0."""
+    from speakerguard_b200 import _lib
+    from speakerguard_b200.engine import make_loss_params
+    eng = engines[prec]
+    tag = "pgd100"
+    x, y, d = regen(xvl, tag, int(xvl[f"{tag}.n_pass"]))
+    xa = x.cuda().clone()
+    dec, scores, _ = eng.pgd_run(xa, x.cuda(), y.cuda(), max_iter=100, epsilon=0.002, step_size=0.0004,
+                                 lp=make_loss_params("Entropy"), dither_mode=_lib.DITHER_TENSOR, dither=d.cuda(), grad_sign=1.0)
+    adv, ref = xa.cpu(), torch.tensor(xvl[f"{tag}.adv"])
+    success = (dec.cpu() != y).tolist()
+    delta = (adv - x).double()
+    snr = (10 * torch.log10(x.double().pow(2).sum(1) / delta.pow(2).sum(1))).numpy()
+    side = float((torch.sign(adv - x) == torch.sign(ref - x)).float().mean())
+    print(f"[{prec}] PGD-100: success {success} (reference {xvl[f'{tag}.success'].tolist()}); SNR max |d| "
+          f"{np.abs(snr - xvl[f'{tag}.snr_db']).max():.3f} dB; same side of x0 as the reference: {side:.4f}")
+    assert success == xvl[f"{tag}.success"].tolist()
+    assert np.abs(snr - xvl[f"{tag}.snr_db"]).max() < 0.1
+    assert float(delta.abs().max()) <= 0.002 + 1e-7
+    assert side > 0.80
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("tag", ["pgd3osi", "pgd3osit"])
+@pytest.mark.parametrize("fused", [True, False])
+def test_osi_with_default_loss_name_steps_like_the_reference(params, xvl, tag, prec, fused):
+    """PGD(task='OSI') with the default loss='Entropy': the reference runs the margin loss but keeps the cross-entropy
+    sign (+1 untargeted, -1 targeted; attack/utils.py:107-114).  Fused device loop and generic autograd path, through the
+    public classes, against the reference's adversarial examples."""
+    import tempfile
+    from speakerguard_b200.attack.PGD import PGD
+    from speakerguard_b200.model.xv_plda import xv_plda
+    from speakerguard_b200.synthetic import state_dict_of, write_xv_model_files
+    x, y, d = regen(xvl, tag, 4)
+    y[-1] = -1
+    assert np.array_equal(y.numpy(), xvl[f"{tag}.y"])
+    targeted, thr = bool(int(xvl[f"{tag}.targeted"])), float(xvl[f"{tag}.thr"])
+    it = iter(d.cuda())
+    with tempfile.TemporaryDirectory() as tmp:
+        f = write_xv_model_files(params, tmp)
+        model = xv_plda(state_dict_of(params), f["plda.txt"], f["mean.vec"], f["transform.txt"], model_file=f["speaker_model"],
+                        threshold=thr, device="cuda:0", precision=prec, dither=lambda B, m: next(it))
+    att = PGD(model, task="OSI", epsilon=0.002, step_size=0.0004, max_iter=3, loss="Entropy", targeted=targeted, batch_size=4,
+              verbose=0)
+    assert att.grad_sign == (1 - 2 * int(targeted))
+    att.use_fused = fused
+    adv, success = att.attack(x.unsqueeze(1).cuda(), y.cuda())
+    ref = torch.tensor(xvl[f"{tag}.adv"])
+    same = float((adv[:, 0].cpu() == ref).float().mean())
+    print(f"[{prec} {tag} fused={fused}] bit-identical to the reference: {same:.4f}; success {success}")
+    assert [bool(s) for s in success] == xvl[f"{tag}.success"].tolist()
+    assert same > (0.98 if prec == "fp32" else 0.95)

@@ -65,8 +65,9 @@ def test_tc_conv_matches_ffma_and_fp64(rows, cin, N, taps, step, epi):
 
 def test_tf32_network_vs_fp32_network():
     """Whole x-vector pass in TF32 tensor-core mode vs the fp32 parity mode (same kernels otherwise).
-    Stated tolerances for TF32 mode: embeddings / scores 5e-3 relative (row max), decisions equal on
-    this data, >= 97 % of input-gradient signs equal, gradient cosine >= 0.995."""
+    Stated tolerances for TF32 mode (<= 2x what was measured on B200: 9e-4 / 6e-4 / 98.6 % / 0.9989): embeddings 2e-3,
+    scores 1.5e-3 relative (row max), decisions equal on this data, >= 97.5 % of input-gradient signs equal, gradient
+    cosine >= 0.997."""
     from oracle import sg_oracle as O
     from speakerguard_b200 import _lib
     from speakerguard_b200.engine import Engine, make_loss_params
@@ -91,9 +92,9 @@ def test_tf32_network_vs_fp32_network():
     sign_agree = float((torch.sign(g1) == torch.sign(g0)).float().mean())
     cos = float((g1 * g0).sum() / (g1.norm() * g0.norm()))
     print(f"tf32 vs fp32: emb {e_emb:.2e} scores {e_sc:.2e} grad sign agreement {sign_agree:.4f} cosine {cos:.5f}")
-    assert e_emb < 5e-3 and e_sc < 5e-3
+    assert e_emb < 2e-3 and e_sc < 1.5e-3
     assert torch.equal(res["tf32"][2], res["fp32"][2])
-    assert sign_agree > 0.97 and cos > 0.995
+    assert sign_agree > 0.975 and cos > 0.997
 
 
 BF16_SHAPES = [  # rows, cin, N, taps, step, epilogue, op_bf16, out_bf16
@@ -128,8 +129,9 @@ def test_tc_conv_bf16(rows, cin, N, taps, step, epi, opb, outb):
 
 
 def test_bf16_network_vs_fp32_network():
-    """Whole x-vector pass in BF16 mode vs fp32 parity mode.  Stated tolerances for BF16 mode: embeddings /
-    scores 3e-2 relative (row max), >= 90 % of input-gradient signs equal, gradient cosine >= 0.97."""
+    """Whole x-vector pass in BF16 mode vs fp32 parity mode.  Stated tolerances for BF16 mode (<= 2x what was measured
+    on B200: 6e-4 / 4e-4 / 97.3 % / 0.996): embeddings 1.2e-3, scores 8e-4 relative (row max), decisions equal on this data,
+    >= 96 % of input-gradient signs equal, gradient cosine >= 0.992."""
     from oracle import sg_oracle as O
     from speakerguard_b200 import _lib
     from speakerguard_b200.engine import Engine, make_loss_params
@@ -154,8 +156,9 @@ def test_bf16_network_vs_fp32_network():
     sign_agree = float((torch.sign(g1) == torch.sign(g0)).float().mean())
     cos = float((g1 * g0).sum() / (g1.norm() * g0.norm()))
     print(f"bf16 vs fp32: emb {e_emb:.2e} scores {e_sc:.2e} grad sign agreement {sign_agree:.4f} cosine {cos:.5f}")
-    assert e_emb < 3e-2 and e_sc < 3e-2
-    assert sign_agree > 0.90 and cos > 0.97
+    assert e_emb < 1.2e-3 and e_sc < 8e-4
+    assert torch.equal(res["bf16"][2], res["fp32"][2])
+    assert sign_agree > 0.96 and cos > 0.992
 
 
 @pytest.mark.parametrize("prec", ["tf32", "bf16"])
