@@ -245,6 +245,10 @@ int sg_cw2_audionet_run(sg_handle* h, const float* x, const int64_t* y, int B, i
                         const sg_cw2_params* p, void* ws, float* best_x, int64_t* success,
                         float* final_const, sg_stream stream);
 
+/* gradient iterations executed by the last sg_cw2_audionet_run on this handle, summed over the binary-search steps (early
+ * stop, attack/CW2.py:96-100, can end a search step before max_iter) */
+long long sg_cw2_last_iterations(const sg_handle* h);
+
 /* ---- FeCo feature compression (replaces libKMCUDA) ----------------------------------------------
  * sg_feco_kmeans: per-utterance Lloyd k-means over the frames (defense/feature_level.py:192-193:
  *   kmeans_cuda(x, k, yinyang_t=0, metric='L2'); k-means++ seeding, stops when <= tol*n frames

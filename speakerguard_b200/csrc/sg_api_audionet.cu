@@ -333,6 +333,7 @@ extern "C" int sg_cw2_audionet_run(sg_handle* h, const float* x, const int64_t* 
   SG_CUDA_CHECK(cudaMemcpyAsync(best_x, x, BN * sizeof(float), cudaMemcpyDeviceToDevice, st));   // global_best_adver_x = x.clone()
   cw2_init_kernel<<<nb, 128, 0, st>>>(w.cst, w.lower, w.upper, w.gbest_l2, w.gbest_score, p->initial_const, B);
   SG_LAUNCH_CHECK();
+  h->cw2_iters = 0;
   for (int bs = 0; bs < p->binary_search_steps; ++bs) {
     SG_CUDA_CHECK(cudaMemsetAsync(w.w, 0, BN * sizeof(float), st));
     SG_CUDA_CHECK(cudaMemsetAsync(w.m, 0, BN * sizeof(float), st));
@@ -354,6 +355,7 @@ extern "C" int sg_cw2_audionet_run(sg_handle* h, const float* x, const int64_t* 
       const bool grad = it < p->max_iter;
       PROF(h, SG_PROF_LOSS, st, sg_loss_launch(scores, (const long long*)y, B, C, p->loss, w.loss1, grad ? w.dscores : nullptr, st));
       if (grad) {
+        h->cw2_iters += 1;
         expand_rows_kernel<<<(B * Cp + 255) / 256, 256, 0, st>>>(w.dscores, C, w.dlogits, Cp, B);
         SG_LAUNCH_CHECK();
         SG_TRY(an_cnn_bwd(h, w.dlogits, B, w, w.dfeat, st));
@@ -382,6 +384,8 @@ extern "C" int sg_cw2_audionet_run(sg_handle* h, const float* x, const int64_t* 
   if (final_const) SG_CUDA_CHECK(cudaMemcpyAsync(final_const, w.cst, (size_t)B * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return SG_OK;
 }
+
+extern "C" long long sg_cw2_last_iterations(const sg_handle* h) { return h ? h->cw2_iters : 0; }
 
 // ---------------------------------------------------------------------------------------------
 // FeCo (defense/feature_level.py:18-50, :168-217)

@@ -37,6 +37,7 @@ struct sg_handle {
   int device = 0;
   int precision = SG_PREC_FP32;
   long long launches = 0;
+  long long cw2_iters = 0;          // gradient iterations executed by the last sg_cw2_audionet_run
   int l1_tap_form = 1;              // SG_OPT_L1_TAP_FORM: bf16 mode computes the layer-1 dgrad per tap (K = 512) + a shifted sum
   int feat_stash = 1;               // SG_OPT_FEAT_STASH: the fused attack loop hands the per-frame forward state to the MFCC adjoint
   int utt_offset = 0;               // SG_OPT_UTT_OFFSET: global index of utterance 0 (philox dither key)

@@ -402,6 +402,11 @@ class Engine:
                                            _ptr(cst), self.stream), "sg_cw2_audionet_run")
         return best, suc, cst
 
+    def cw2_iterations(self) -> int:
+        """Gradient iterations executed by the last cw2_audionet_run (summed over the binary-search steps; early stop
+        shortens a search step).  Synchronises."""
+        return int(self.lib.sg_cw2_last_iterations(self._h))
+
     # ---- FeCo ------------------------------------------------------------------------------------
     def feco_kmeans(self, feat: torch.Tensor, k: int, seed: int = 0, max_iter: int = 100, tol: float = 0.01) -> torch.Tensor:
         """feat [B,n,dim] -> cluster ids [B,n] int32."""

@@ -126,3 +126,52 @@ def test_cw2_kernels_one_iteration_exact(model, params):
     np.testing.assert_allclose(cst.cpu().numpy(), info["const"].numpy(), rtol=1e-6)
     if any(suc_o):
         assert float((best.cpu() - xa).abs().max()) < 2e-2
+
+
+def test_return_emb_and_embedding_split():
+    """forward(return_emb=True) / embedding() / predict_from_embeddings (audionet_csine.py:159-229): the CNN split at the
+    32-dim embedding gives the same logits as the fused path and the same input gradient; emb == the oracle's."""
+    from speakerguard_b200.model.audionet_csine import audionet_csine
+    p = O.make_audionet_params(seed=0, num_class=251)
+    model = audionet_csine(params=p, device="cuda:0")
+    torch.manual_seed(4321)
+    x = ((torch.rand(4, 1, 16000) * 2 - 1) * 0.5).cuda()
+    xr = x.clone().requires_grad_(True)
+    logits, emb = model(xr, return_emb=True)
+    assert emb.shape == (4, 32) and logits.shape == (4, 251)
+    o = O.audionet_forward(x[:, 0].cpu(), p, return_all=True)
+    np.testing.assert_allclose(logits.detach().cpu().numpy(), o["logits"].numpy(), atol=2e-4, rtol=1e-4)
+    if "emb" in o:
+        np.testing.assert_allclose(emb.detach().cpu().numpy(), o["emb"].numpy(), atol=1e-4, rtol=1e-4)
+    w = torch.randn(4, 251, generator=torch.Generator().manual_seed(1)).cuda()
+    (logits * w).sum().backward()
+    xf = x.clone().requires_grad_(True)
+    lf = model(xf)
+    (lf * w).sum().backward()
+    assert torch.equal(lf.detach(), logits.detach())
+    assert float((xr.grad - xf.grad).abs().max()) <= 1e-6 * float(xf.grad.abs().max())
+    assert torch.equal(model.embedding(x).detach(), emb.detach())
+
+
+def test_defended_model_average_follows_the_reference_data_semantics():
+    """order='average' (model/defended_model.py:108-124): values are the mean over the defenses, autograd only sees the first
+    member's graph with weight 1 (`.data +=` / `.data /=`) - and it runs against AudioNet now that return_emb exists."""
+    from speakerguard_b200.model.audionet_csine import audionet_csine
+    from speakerguard_b200.model.defended_model import defended_model
+    p = O.make_audionet_params(seed=0, num_class=251)
+    model = audionet_csine(params=p, device="cuda:0")
+    d1 = lambda z: z * 0.5
+    d2 = lambda z: z * 0.25
+    dm = defended_model(model, defense=[[0, d1], [0, d2]], order="average")
+    torch.manual_seed(7)
+    x = ((torch.rand(2, 1, 16000) * 2 - 1) * 0.5).cuda()
+    xr = x.clone().requires_grad_(True)
+    logits, emb = dm(xr, return_emb=True)
+    l1, l2 = model(d1(x)), model(d2(x))
+    np.testing.assert_allclose(logits.detach().cpu().numpy(), ((l1 + l2) / 2).detach().cpu().numpy(), atol=1e-5, rtol=1e-5)
+    logits.sum().backward()
+    x1 = x.clone().requires_grad_(True)
+    model(d1(x1)).sum().backward()
+    assert torch.allclose(xr.grad, x1.grad, rtol=1e-5, atol=1e-8)             # first member only, unscaled
+    dec, sc = dm.make_decision(x)
+    assert dec.shape == (2,)
