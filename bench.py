@@ -681,7 +681,10 @@ def xv_leg(args, precision, steps, warmup, e2e_steps, rank, world, local, want_m
         adv, success = e2e_step()
     e2e_s = dist.max_over_ranks(time.perf_counter() - t0, dev) / max(e2e_steps, 1)
     e2e_value = global_B * iters / e2e_s if e2e_steps else None
-    metrics = dist.reduce_metrics(dist.attack_metrics(x_dev, adv, success)) if want_metrics else None   # NCCL: metric scalars only
+    if want_metrics and world > 1:
+        dist.engine_comm_init(eng)                                   # libsgb200's own NCCL communicator (sg_comm_init)
+    # the path's only collective: five metric scalars, summed over NVLink by sg_allreduce_metrics
+    metrics = dist.reduce_metrics(dist.attack_metrics(x_dev, adv, success), engine=eng) if want_metrics else None
 
     # ---- per-kernel device time of one profiled step, roofline of the TDNN contraction -------------
     eng.profile(True)

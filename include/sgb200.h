@@ -66,6 +66,11 @@ int sg_get_precision(const sg_handle* h);
  * utterance axis is split contiguously over G handles (x[r*B/G:(r+1)*B/G] on GPU r) and handle r sets
  * value = r*B/G, the sharded attack reproduces the unsharded one bit for bit. */
 #define SG_OPT_UTT_OFFSET 4
+/* SG_OPT_CUDA_GRAPH (default 1): sg_pgd_run captures one PGD iteration (forward, backward, fused sign step: ~26 kernels) per
+ * ping-pong parity into a CUDA graph and replays it max_iter times; seed and pass counter are read from a device control
+ * block so the same graphs serve every later attack with the same shapes / workspace / parameters.  Iterates are
+ * bit-identical to the launch-by-launch path (0).  Not used with a dither tensor, a loss history or profiling on. */
+#define SG_OPT_CUDA_GRAPH 5
 int sg_set_option(sg_handle* h, int option, int value);
 
 /* ---- x-vector / PLDA system: weights ---------------------------------------------------------
@@ -364,6 +369,19 @@ int sg_pcm16_quantize(sg_handle* h, const float* adv, int B, int N, int16_t* pcm
 int sg_wav_write_batch(const char* const* paths, const int16_t* pcm, int B, int N, int fs, int nthreads);
 int sg_wav_read_batch(const char* const* paths, int B, int wav_length, const int64_t* starts,
                       int normalize, float* out, int32_t* lens, int nthreads);
+
+/* ---- the path's one collective ----------------------------------------------------
+ * Utterances shard independently over the GPUs (no data-path collective); what is reduced over NVLink / NVSwitch is a
+ * handful of metric scalars at the end of an attack (success count, sums of SNR / L2 / Linf, utterance count: reference
+ * metric/metric.py:10-42 semantics).  NCCL is bound with dlopen at run time (inside PyTorch: the copy torch loaded).
+ * sg_comm_unique_id: rank 0 fills 128 bytes (ncclUniqueId) and ships them to the other ranks by any host channel.
+ * sg_comm_init: one communicator per handle (= per GPU / process).
+ * sg_allreduce_metrics: in-place sum over the ranks of a DEVICE fp64 vector, asynchronous on `stream`. */
+int sg_comm_unique_id(void* id128);
+int sg_comm_init(sg_handle* h, const void* id128, int rank, int world);
+int sg_allreduce_metrics(sg_handle* h, double* v, int n, sg_stream stream);
+int sg_comm_destroy(sg_handle* h);
+int sg_comm_nccl_version(void);
 
 /* ---- test hook: one conv-as-GEMM launch on either arithmetic path -----------------------------
  * out[p,n] = epi(sum_{tap,c} A[p + tap*tap_step, c] * W[tap*cin + c, n]); W is [taps*cin, N]

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libsgb200.so")
 SG_OK, SG_EINVAL, SG_ECUDA, SG_ESTATE, SG_EUNSUPPORTED = 0, -1, -2, -3, -4
 PREC_FP32, PREC_TF32, PREC_BF16 = 0, 1, 2
 DITHER_OFF, DITHER_TENSOR, DITHER_PHILOX = 0, 1, 2
-OPT_POOL_FUSION, OPT_FEAT_STASH, OPT_L1_TAP_FORM, OPT_UTT_OFFSET = 1, 2, 3, 4
+OPT_POOL_FUSION, OPT_FEAT_STASH, OPT_L1_TAP_FORM, OPT_UTT_OFFSET, OPT_CUDA_GRAPH = 1, 2, 3, 4, 5
 LOSS_CE, LOSS_MARGIN = 0, 1
 PROF_COUNT = 15
 IV_STAGE_POST, IV_STAGE_STATS, IV_STAGE_IVECTOR = 0, 1, 2
@@ -134,6 +134,11 @@ PROTOTYPES = {
     "sg_pcm16_quantize": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
     "sg_wav_write_batch": (C.c_int, [C.POINTER(C.c_char_p), _vp, C.c_int, C.c_int, C.c_int, C.c_int]),
     "sg_wav_read_batch": (C.c_int, [C.POINTER(C.c_char_p), C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, C.c_int]),
+    "sg_comm_unique_id": (C.c_int, [_vp]),
+    "sg_comm_init": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
+    "sg_allreduce_metrics": (C.c_int, [_vp, _vp, C.c_int, _vp]),
+    "sg_comm_destroy": (C.c_int, [_vp]),
+    "sg_comm_nccl_version": (C.c_int, []),
     "sg_debug_conv": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.c_int, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     "sg_profile_enable": (C.c_int, [_vp, C.c_int]),

@@ -68,6 +68,7 @@ extern "C" int sg_create(sg_handle** out, int device) {
   if (const char* e = getenv("SGB200_POOL_FUSION")) h->pool_fusion = atoi(e) != 0;   // A/B switches for bench.py runs
   if (const char* e = getenv("SGB200_FEAT_STASH")) h->feat_stash = atoi(e) != 0;
   if (const char* e = getenv("SGB200_L1_TAP_FORM")) h->l1_tap_form = atoi(e) != 0;
+  if (const char* e = getenv("SGB200_CUDA_GRAPH")) h->use_graph = atoi(e) != 0;
   SgFeatTables* host = new SgFeatTables();
   int r = sg_feat_tables_build(host);
   if (r != SG_OK) { delete host; delete h; sg_set_error("sg_create: feature table construction failed"); return r; }
@@ -77,6 +78,7 @@ extern "C" int sg_create(sg_handle** out, int device) {
   if (ce != cudaSuccess) { sg_set_error("sg_create: table upload failed: %s", cudaGetErrorString(ce)); delete h; return SG_ECUDA; }
   h->allocs.push_back(h->d_tables);
   r = sg_feat_init();
+  if (r == SG_OK) r = sg_conv_tc_warm();
   if (r != SG_OK) { sg_destroy(h); return r; }
   *out = h;
   return SG_OK;
@@ -86,6 +88,9 @@ extern "C" void sg_destroy(sg_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   for (cudaEvent_t e : h->prof.ev) cudaEventDestroy(e);
+  for (int i = 0; i < 2; ++i) if (h->pgd_graph.exec[i]) cudaGraphExecDestroy(h->pgd_graph.exec[i]);
+  if (h->pgd_graph.cap_stream) cudaStreamDestroy(h->pgd_graph.cap_stream);
+  sg_comm_destroy(h);
   sg_audionet_free(h);
   sg_iv_free(h);
   for (void* p : h->allocs) cudaFree(p);
@@ -104,6 +109,7 @@ extern "C" int sg_set_option(sg_handle* h, int option, int value) {
   if (option == SG_OPT_POOL_FUSION) { h->pool_fusion = value != 0; return SG_OK; }
   if (option == SG_OPT_FEAT_STASH) { h->feat_stash = value != 0; return SG_OK; }
   if (option == SG_OPT_L1_TAP_FORM) { h->l1_tap_form = value != 0; return SG_OK; }
+  if (option == SG_OPT_CUDA_GRAPH) { h->use_graph = value != 0; return SG_OK; }
   if (option == SG_OPT_UTT_OFFSET) {
     if (value < 0) { sg_set_error("SG_OPT_UTT_OFFSET must be >= 0"); return SG_EINVAL; }
     h->utt_offset = value; return SG_OK;
@@ -295,7 +301,9 @@ struct XvWs {
   float *r[5], *G0, *G1, *G2, *stats, *dstats, *save_mean, *save_std, *ab, *e1, *de1, *e2, *de2, *tsave, *scal;
   // attack-loop extras
   float *raw, *draw, *feat, *dfeat, *emb, *demb, *scores, *dscores, *loss, *xbuf, *grad, *stash;
-  long long* dec;
+  float *xbuf2, *x0c;               // graph replay: the iterate ping-pongs between xbuf / xbuf2, x0 and y are copied in so that
+  long long *dec, *yc;              // the captured kernels only reference workspace addresses
+  uint32_t* ctl;                    // {pass, seed_lo, seed_hi} read by the MFCC kernels
   size_t bytes;
 };
 
@@ -319,7 +327,7 @@ static XvWs xv_ws_layout(void* base, int B, int T, int Lp, int L, int S, bool at
   w.e2 = take((size_t)B * Lp); w.de2 = take((size_t)B * Lp); w.tsave = take((size_t)B * Lp);
   w.scal = take((size_t)B * 4);
   w.raw = w.draw = w.feat = w.dfeat = w.emb = w.demb = w.scores = w.dscores = w.loss = w.xbuf = w.grad = w.stash = nullptr;
-  w.dec = nullptr;
+  w.dec = w.yc = nullptr; w.xbuf2 = w.x0c = nullptr; w.ctl = nullptr;
   if (attack) {
     w.raw = take(R * SG_FLD); w.draw = take(R * SG_FLD); w.feat = take(R * SG_FLD); w.dfeat = take(R * SG_FLD);
     w.emb = take((size_t)B * L); w.demb = take((size_t)B * L);
@@ -327,6 +335,8 @@ static XvWs xv_ws_layout(void* base, int B, int T, int Lp, int L, int S, bool at
     w.dec = (long long*)take((size_t)B * 2);
     w.xbuf = take((size_t)B * N); w.grad = take((size_t)B * N);
     w.stash = take(sg_feat_stash_floats(B, T));      // forward -> adjoint hand-over of the MFCC kernels
+    w.xbuf2 = take((size_t)B * N); w.x0c = take((size_t)B * N);
+    w.yc = (long long*)take((size_t)B * 2); w.ctl = (uint32_t*)take(64);
   }
   w.bytes = off;
   return w;
@@ -624,6 +634,76 @@ extern "C" int sg_xv_forward(sg_handle* h, const float* x, int B, int N, int dit
                       (long long*)decisions, (cudaStream_t)stream);
 }
 
+// One PGD iteration (attack/FGSM.py:44-68 for iter < max_iter): E gradient passes (EOT) and the sign step, reading the iterate
+// from `cur` and writing the next one to `other` (E == 1: fused into the MFCC adjoint) or back into `cur` (E > 1).
+// `it` only selects the dither slice / loss-history row of the launch-by-launch path; with a device control block (ctl) the
+// pass counter comes from there and the function is iteration-independent, which is what makes it capturable.
+static int pgd_iteration(sg_handle* h, float* cur, float* other, const float* x0, const long long* y, const float* dither, int B,
+                         int N, int m, const sg_pgd_params* p, float grad_sign, const XvWs& w, float* sc, long long* dec,
+                         float* loss_hist, int it, uint32_t* ctl, cudaStream_t st) {
+  const int E = p->eot_size;
+  const size_t dstride = (size_t)B * m * SG_WIN;
+  float* const stash = h->feat_stash ? w.stash : nullptr;
+  for (int e = 0; e < E; ++e) {
+    const uint64_t pass = ctl ? (uint64_t)e : (uint64_t)it * E + e;
+    const float* dth = dither ? dither + ((uint64_t)it * E + e) * dstride : nullptr;
+    SG_TRY(forward_pass(h, cur, B, N, m, p->dither_mode, dth, p->seed, pass, p->decision_threshold, w, w.emb, sc, dec, st, stash));
+    float* lossp = (loss_hist && e == 0) ? loss_hist + (size_t)it * B : w.loss;
+    h->launches += 3;
+    PROF(h, SG_PROF_LOSS, st, sg_loss_launch(sc, y, B, h->S, p->loss, lossp, w.dscores, st));
+    PROF(h, SG_PROF_HEAD, st, sg_score_bwd_launch(h->H, w.emb, w.dscores, B, h->enroll, h->S, w.demb, st));
+    SG_TRY(embed_bwd(h, w.demb, B, m, w, w.dfeat, st));
+    PROF(h, SG_PROF_CMVN, st, sg_cmvn_launch(w.dfeat, SG_FLD, w.draw, SG_FLD, B, m, 1, st));
+    h->launches += 1;
+    if (E == 1) {
+      PROF(h, SG_PROF_MFCC_BWD, st, sg_feat_bwd_step_launch(h->d_tables, cur, B, N, m, p->dither_mode, dth, p->seed, dither_pass(h, pass), w.draw, SG_FLD, x0,
+                                     other, p->step_size * grad_sign, p->epsilon, st, stash));
+    } else {
+      PROF(h, SG_PROF_MFCC_BWD, st, sg_feat_bwd_launch(h->d_tables, cur, B, N, m, p->dither_mode, dth, p->seed, dither_pass(h, pass), w.draw, SG_FLD, w.grad,
+                                1.0f / (float)E, e > 0, st, stash));
+    }
+  }
+  if (E > 1) {
+    h->launches += 1;
+    PROF(h, SG_PROF_STEP, st, sg_step_linf_launch(cur, x0, w.grad, (size_t)B * N, p->step_size * grad_sign, p->epsilon, st));
+  }
+  if (ctl) { h->launches += 1; SG_TRY(sg_feat_ctl_tick_launch(ctl, (uint32_t)E, st)); }
+  return SG_OK;
+}
+
+// capture pgd_iteration for both ping-pong parities; on any failure the capture is abandoned and the caller falls back
+static int pgd_capture(sg_handle* h, int B, int N, int m, const sg_pgd_params* p, float grad_sign, const XvWs& w,
+                       const unsigned long long* key, cudaStream_t st) {
+  SgPgdGraph& g = h->pgd_graph;
+  for (int i = 0; i < 2; ++i) if (g.exec[i]) { cudaGraphExecDestroy(g.exec[i]); g.exec[i] = nullptr; }
+  g.valid = false;
+  const long long launches0 = h->launches;
+  // capture on a private stream: the caller's stream may be the legacy default stream, which cannot be captured; captured
+  // work does not execute, so no ordering with the caller's stream is needed here
+  if (!g.cap_stream && cudaStreamCreateWithFlags(&g.cap_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return SG_ECUDA; }
+  st = g.cap_stream;
+  for (int par = 0; par < 2; ++par) {
+    float* cur = par == 0 ? w.xbuf : w.xbuf2;
+    float* other = par == 0 ? w.xbuf2 : w.xbuf;
+    if (p->eot_size > 1) { cur = w.xbuf; other = w.xbuf2; }              // E > 1 steps in place: one parity only
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); return SG_ECUDA; }
+    sg_feat_set_ctl(w.ctl);
+    int r = pgd_iteration(h, cur, other, w.x0c, w.yc, nullptr, B, N, m, p, grad_sign, w, w.scores, w.dec, nullptr, 0, w.ctl, st);
+    sg_feat_set_ctl(nullptr);
+    cudaError_t e = cudaStreamEndCapture(st, &graph);
+    if (r != SG_OK || e != cudaSuccess || !graph) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return SG_ECUDA; }
+    e = cudaGraphInstantiate(&g.exec[par], graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { g.exec[par] = nullptr; cudaGetLastError(); return SG_ECUDA; }
+  }
+  g.kernels = (int)((h->launches - launches0) / 2);
+  h->launches = launches0;                                               // captured, not launched
+  memcpy(g.key, key, sizeof(g.key));
+  g.valid = true;
+  return SG_OK;
+}
+
 extern "C" int sg_pgd_run(sg_handle* h, float* x_adv, const float* x0, const int64_t* y, const float* dither, int B, int N,
                           const sg_pgd_params* p, void* ws, int64_t* decisions, float* scores, float* loss_hist,
                           sg_stream stream) {
@@ -639,36 +719,55 @@ extern "C" int sg_pgd_run(sg_handle* h, float* x_adv, const float* x0, const int
   // the cross-entropy sign), so the caller passes it; 0 derives it from the effective loss
   if (p->grad_sign != 0.f && p->grad_sign != 1.f && p->grad_sign != -1.f) { sg_set_error("sg_pgd_run: grad_sign must be +1, -1 or 0 (derive), got %g", p->grad_sign); return SG_EINVAL; }
   const float grad_sign = p->grad_sign != 0.f ? p->grad_sign : ((p->loss.loss == SG_LOSS_CE) ? (p->loss.targeted ? -1.f : 1.f) : -1.f);
-  float* cur = x_adv;
-  float* other = w.xbuf;
-  float* const stash = h->feat_stash ? w.stash : nullptr;
   float* sc = scores ? scores : w.scores;
   long long* dec = decisions ? (long long*)decisions : w.dec;
-  for (int it = 0; it < p->max_iter; ++it) {
-    for (int e = 0; e < E; ++e) {
-      const uint64_t pass = (uint64_t)it * E + e;
-      const float* dth = dither ? dither + pass * dstride : nullptr;
-      SG_TRY(forward_pass(h, cur, B, N, m, p->dither_mode, dth, p->seed, pass, p->decision_threshold, w, w.emb, sc, dec, st, stash));
-      float* lossp = (loss_hist && e == 0) ? loss_hist + (size_t)it * B : w.loss;
-      h->launches += 3;
-      PROF(h, SG_PROF_LOSS, st, sg_loss_launch(sc, (const long long*)y, B, h->S, p->loss, lossp, w.dscores, st));
-      PROF(h, SG_PROF_HEAD, st, sg_score_bwd_launch(h->H, w.emb, w.dscores, B, h->enroll, h->S, w.demb, st));
-      SG_TRY(embed_bwd(h, w.demb, B, m, w, w.dfeat, st));
-      PROF(h, SG_PROF_CMVN, st, sg_cmvn_launch(w.dfeat, SG_FLD, w.draw, SG_FLD, B, m, 1, st));
+  const size_t xbytes = (size_t)B * N * sizeof(float);
+
+  // ---- graph replay: every iteration is the same kernel sequence on workspace addresses ------------------------------
+  bool graphed = false;
+  if (h->use_graph && !h->prof.on && !loss_hist && p->dither_mode != SG_DITHER_TENSOR && p->max_iter >= 2) {
+    unsigned long long key[12] = {(unsigned long long)(uintptr_t)ws, (unsigned long long)B, (unsigned long long)N,
+                                  (unsigned long long)E, (unsigned long long)p->dither_mode, 0, 0, 0, 0, 0, 0, 0};
+    static_assert(sizeof(sg_loss_params) == 24, "sg_loss_params fills key[7..9]");
+    memcpy(&key[5], &p->epsilon, sizeof(float)); memcpy(&key[6], &p->step_size, sizeof(float));
+    memcpy(&key[7], &p->loss, sizeof(sg_loss_params));
+    memcpy(&key[10], &p->decision_threshold, sizeof(float));
+    key[11] = (unsigned long long)(grad_sign > 0.f) | ((unsigned long long)h->precision << 1) | ((unsigned long long)h->pool_fusion << 3) |
+              ((unsigned long long)h->feat_stash << 4) | ((unsigned long long)h->l1_tap_form << 5) |
+              ((unsigned long long)(uint32_t)h->utt_offset << 8);
+    if (!h->pgd_graph.valid || memcmp(h->pgd_graph.key, key, sizeof(key)) != 0) {
+      if (pgd_capture(h, B, N, m, p, grad_sign, w, key, st) != SG_OK) h->use_graph = 0;    // capture unavailable: launch-by-launch from now on
+    }
+    if (h->pgd_graph.valid && h->use_graph) {
+      SG_CUDA_CHECK(cudaMemcpyAsync(w.xbuf, x_adv, xbytes, cudaMemcpyDeviceToDevice, st));
+      SG_CUDA_CHECK(cudaMemcpyAsync(w.x0c, x0, xbytes, cudaMemcpyDeviceToDevice, st));
+      SG_CUDA_CHECK(cudaMemcpyAsync(w.yc, y, (size_t)B * sizeof(long long), cudaMemcpyDeviceToDevice, st));
       h->launches += 1;
-      if (E == 1) {
-        PROF(h, SG_PROF_MFCC_BWD, st, sg_feat_bwd_step_launch(h->d_tables, cur, B, N, m, p->dither_mode, dth, p->seed, dither_pass(h, pass), w.draw, SG_FLD, x0,
-                                       other, p->step_size * grad_sign, p->epsilon, st, stash));
-        float* t = cur; cur = other; other = t;
-      } else {
-        PROF(h, SG_PROF_MFCC_BWD, st, sg_feat_bwd_launch(h->d_tables, cur, B, N, m, p->dither_mode, dth, p->seed, dither_pass(h, pass), w.draw, SG_FLD, w.grad,
-                                  1.0f / (float)E, e > 0, st, stash));
+      SG_TRY(sg_feat_ctl_init_launch(w.ctl, p->seed, 0u, st));
+      for (int it = 0; it < p->max_iter; ++it) {
+        SG_CUDA_CHECK(cudaGraphLaunch(h->pgd_graph.exec[E > 1 ? 0 : (it & 1)], st));
+        h->launches += h->pgd_graph.kernels;                               // kernels inside one replayed iteration
       }
-    }
-    if (E > 1) {
+      float* cur = (E > 1 || (p->max_iter & 1) == 0) ? w.xbuf : w.xbuf2;
+      // final evaluation pass (attack/FGSM.py:44-57 with iter == max_iter): pass counter max_iter * E from the control block
+      sg_feat_set_ctl(w.ctl);
+      int r = forward_pass(h, cur, B, N, m, p->dither_mode, nullptr, p->seed, 0, p->decision_threshold, w, w.emb, sc, dec, st);
+      sg_feat_set_ctl(nullptr);
+      SG_TRY(r);
       h->launches += 1;
-      PROF(h, SG_PROF_STEP, st, sg_step_linf_launch(cur, x0, w.grad, (size_t)B * N, p->step_size * grad_sign, p->epsilon, st));
+      PROF(h, SG_PROF_LOSS, st, sg_loss_launch(sc, (const long long*)y, B, h->S, p->loss, w.loss, nullptr, st));
+      SG_CUDA_CHECK(cudaMemcpyAsync(x_adv, cur, xbytes, cudaMemcpyDeviceToDevice, st));
+      graphed = true;
     }
+  }
+  if (graphed) return SG_OK;
+
+  // ---- launch by launch -------------------------------------------------------------------------------------------------
+  float* cur = x_adv;
+  float* other = w.xbuf;
+  for (int it = 0; it < p->max_iter; ++it) {
+    SG_TRY(pgd_iteration(h, cur, other, x0, (const long long*)y, dither, B, N, m, p, grad_sign, w, sc, dec, loss_hist, it, nullptr, st));
+    if (E == 1) { float* t = cur; cur = other; other = t; }
   }
   // final evaluation pass (attack/FGSM.py:44-57 with iter == max_iter)
   {
@@ -679,6 +778,6 @@ extern "C" int sg_pgd_run(sg_handle* h, float* x_adv, const float* x0, const int
     h->launches += 1;
     PROF(h, SG_PROF_LOSS, st, sg_loss_launch(sc, (const long long*)y, B, h->S, p->loss, lossp, nullptr, st));
   }
-  if (cur != x_adv) SG_CUDA_CHECK(cudaMemcpyAsync(x_adv, cur, (size_t)B * N * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (cur != x_adv) SG_CUDA_CHECK(cudaMemcpyAsync(x_adv, cur, xbytes, cudaMemcpyDeviceToDevice, st));
   return SG_OK;
 }

@@ -151,6 +151,7 @@ struct TcArgs {
   // the transform warps turn each staged tile into dA5 = (t < xf_tv && r > 0) ? alpha' + beta * r : 0 before the MMA
   // reads it.  xf_ab: [rows / T][xf_ld / 2] x {alpha' pair, beta pair} (bf16x2 each) per utterance and channel pair.
   const uint4* xf_ab; int xf_ld, xf_tv;
+  const uint8_t* xf_A; int xf_lda;   // XFORM: r5 itself (bf16, row stride xf_lda elements): loaded by the transform warps, not by TMA
   int pf_dist;                     // L2 prefetch distance of the A operand in k-blocks (0 = off)
   int issue_mode;                  // MMA issuer: 0 single-lane region, 1 warp-convergent loop with an elected lane
   int nst, stb;                    // pipeline ring: stages and bytes per stage (main kernel)
@@ -276,7 +277,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       int stage = 0; uint32_t phase = 0;
       const int bh = PAIR ? (a.bn >> 1) : a.bn;                       // B rows staged by this CTA
       // XFORM + PAIR: every CTA's boxes signal its OWN full barrier (its transform warps wait on it); plain PAIR: the leader's
-      const uint32_t tx = ((PAIR && !XFORM) ? 2u : 1u) * (TC_A_BYTES + (uint32_t)bh * TC_BK * 4);
+      // XFORM: A never goes through TMA (the transform warps load r5 from global memory, transform it in registers and store
+      // the swizzled tile themselves), so a stage's transaction is the B box only
+      const uint32_t tx = XFORM ? (uint32_t)bh * TC_BK * 4 : ((PAIR ? 2u : 1u) * (TC_A_BYTES + (uint32_t)bh * TC_BK * 4));
       // L2 prefetch cursor for the A operand, a.pf_dist k-blocks ahead of the load cursor.  A single-tap layer streams A
       // from HBM exactly once, and with only TC_STAGES - 1 boxes in flight per SM the ring cannot cover the HBM latency
       // (Little: 3 x 16 KB x 148 SMs / ~2 us = 3.5 TB/s); the prefetch moves that wait out of the ring, so the ring
@@ -310,7 +313,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             tma_load_2d_2sm(sa + TC_A_BYTES, &mapB, lead_full, kb * KB_ELEMS, n0);
           } else {
             mbar_expect_tx(&full[stage], tx);
-            tma_load_2d(sa, &mapA, &full[stage], kc * KB_ELEMS, p0 + tap * a.tap_step);
+            if (!XFORM) tma_load_2d(sa, &mapA, &full[stage], kc * KB_ELEMS, p0 + tap * a.tap_step);
             tma_load_2d(sa + TC_A_BYTES, &mapB, &full[stage], kb * KB_ELEMS, n0);
           }
           if (++stage == NST) { stage = 0; phase ^= 1; }
@@ -329,7 +332,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         int stage = 0; uint32_t phase = 0;
         for (int tile = cta0; tile < ntiles; tile += tstep)
           for (int kb = 0; kb < nkb; ++kb) {
-            mbar_wait(&xfull[stage], phase);
+            mbar_wait(&full[stage], phase);                       // this CTA's half of B has landed
+            mbar_wait(&xfull[stage], phase);                      // and its 128 rows of A are transformed and stored
             mbar_arrive_cluster(mapa_u32(smem_u32(&xpeer[stage]), 0));
             if (++stage == NST) { stage = 0; phase ^= 1; }
           }
@@ -348,7 +352,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int kb = 0; kb < nkb; ++kb) {
           const uint32_t sa = smem_base + (uint32_t)stage * STB;
           const uint64_t da = make_desc(sa), db = make_desc(sa + TC_A_BYTES);
-          mbar_wait(XFORM ? &xfull[stage] : &full[stage], phase);
+          mbar_wait(&full[stage], phase);
+          if (XFORM) mbar_wait(&xfull[stage], phase);
           if (PAIR && XFORM) mbar_wait(&xpeer[stage], phase);
           tc_fence_after();
           if (leader) {
@@ -379,7 +384,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)acc * TC_MAX_BN;
         for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(XFORM ? &xfull[stage] : &full[stage], phase);
+          mbar_wait(&full[stage], phase);
+          if (XFORM) mbar_wait(&xfull[stage], phase);
           if (PAIR && XFORM) mbar_wait(&xpeer[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STB);
@@ -397,50 +403,80 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
     }
   } else if (XFORM && warp >= TC_MAIN_THREADS / 32) {
-    // ===== A-operand transform: warps 10..17 (bf16 tiles: 128 rows x 64 channels, SWIZZLE_128B) =====
+    // ===== A-operand producer + transform: warps 10..17 (bf16 tiles: 128 rows x 64 channels, SWIZZLE_128B) =====
+    // The in-place form (TMA lands r5, these warps rewrite the tile) moved every A byte through shared memory three times
+    // (TMA write, transform read, transform write) on top of the MMA's own operand reads: ~770 cycles of the 128 B/clk
+    // shared-memory port per k-block against 512 cycles of tensor work.  Here the warps load r5 straight from global memory
+    // (16 bytes per thread and row, XF_PF k-blocks ahead in registers to cover the HBM latency), apply the pooling adjoint in
+    // registers and store the swizzled tile once.
     // thread -> logical 16-byte chunk j (8 channels) of rows g, g+32, g+64, g+96; (g + 32 i) & 7 == g & 7, so the
     // physical chunk position j ^ (row & 7) is the same for all four rows.  A tile spans at most two utterances
     // (the host only selects this variant for T >= 128): rows before `isplit` use the parameters of utterance b0,
     // the others those of b0 + 1.
+    constexpr int XF_PF = 3;
     const int t = (int)threadIdx.x - TC_MAIN_THREADS;
     const int j = t & 7, g = t >> 3;
     const uint32_t off = (uint32_t)g * 128u + (uint32_t)((j ^ (g & 7)) << 4);
     const int nutt = a.rows / a.T;
+    const int my_tiles = cta0 < ntiles ? (ntiles - cta0 + tstep - 1) / tstep : 0;
+    const int S = my_tiles * nkb;                                   // k-blocks this CTA produces, in ring order
+    uint4 w[XF_PF][4];
+    // prefetch cursor
+    int ptile = cta0, pkb = 0;
+    auto issue = [&](uint4 (&dst)[4]) {
+      const int prow0 = (ptile / a.n_tiles) * TILE_ROWS + rbase + g;
+      const uint8_t* src = a.xf_A + ((size_t)prow0 * a.xf_lda + (size_t)pkb * 64 + j * 8) * 2;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        dst[i] = (prow0 + 32 * i < a.rows) ? __ldg(reinterpret_cast<const uint4*>(src + (size_t)32 * i * a.xf_lda * 2)) : make_uint4(0u, 0u, 0u, 0u);
+      if (++pkb == nkb) { pkb = 0; ptile += tstep; }
+    };
+#pragma unroll
+    for (int u = 0; u < XF_PF; ++u) if (u < S) issue(w[u]);
     int stage = 0; uint32_t phase = 0;
-    for (int tile = cta0; tile < ntiles; tile += tstep) {
-      const int mt = tile / a.n_tiles;
-      const int row0 = mt * TILE_ROWS + rbase + g;
-      const int b0 = row0 / a.T;
-      const int tt0 = row0 - b0 * a.T;
-      int isplit = (a.T - tt0 + 31) >> 5;
-      if (isplit > 4) isplit = 4;
-      uint32_t okm[4];
+    int tile = cta0, kb = 0;
+    int isplit = 4;
+    uint32_t okm[4] = {0u, 0u, 0u, 0u};
+    const uint4* q0 = a.xf_ab;
+    const uint4* q1 = a.xf_ab;
+    for (int s0 = 0; s0 < S; s0 += XF_PF) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int tt = tt0 + 32 * i - (i >= isplit ? a.T : 0);
-        okm[i] = ((row0 + 32 * i < a.rows) && (tt < a.xf_tv)) ? 0xffffffffu : 0u;
-      }
-      const bool second = (isplit < 4) && (b0 + 1 < nutt);
-      const uint4* q0 = a.xf_ab + (((size_t)(b0 < nutt ? b0 : 0) * a.xf_ld + j * 8) >> 2);   // one uint4 = 4 channels
-      const uint4* q1 = q0 + (second ? (a.xf_ld >> 2) : 0);
-      for (int kb = 0; kb < nkb; ++kb) {
-        uint4 P[2], Q[2];
+      for (int u = 0; u < XF_PF; ++u) {
+        if (s0 + u < S) {
+          if (kb == 0) {                                            // new tile: utterance split and row validity
+            const int mt = tile / a.n_tiles;
+            const int row0 = mt * TILE_ROWS + rbase + g;
+            const int b0 = row0 / a.T;
+            const int tt0 = row0 - b0 * a.T;
+            isplit = (a.T - tt0 + 31) >> 5;
+            if (isplit > 4) isplit = 4;
 #pragma unroll
-        for (int k = 0; k < 2; ++k) { P[k] = __ldg(q0 + kb * 16 + k); Q[k] = __ldg(q1 + kb * 16 + k); }
-        mbar_wait(&full[stage], phase);
-        uint8_t* sa = smem + stage * STB + off;
-        uint4 w[4];
+            for (int i = 0; i < 4; ++i) {
+              const int tt = tt0 + 32 * i - (i >= isplit ? a.T : 0);
+              okm[i] = ((row0 + 32 * i < a.rows) && (tt < a.xf_tv)) ? 0xffffffffu : 0u;
+            }
+            const bool second = (isplit < 4) && (b0 + 1 < nutt);
+            q0 = a.xf_ab + (((size_t)(b0 < nutt ? b0 : 0) * a.xf_ld + j * 8) >> 2);   // one uint4 = 4 channels
+            q1 = q0 + (second ? (a.xf_ld >> 2) : 0);
+          }
+          uint4 P[2], Q[2];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) w[i] = *reinterpret_cast<const uint4*>(sa + i * 4096);
+          for (int k = 0; k < 2; ++k) { P[k] = __ldg(q0 + kb * 16 + k); Q[k] = __ldg(q1 + kb * 16 + k); }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (i < isplit) xf8(w[i], P, okm[i]); else xf8(w[i], Q, okm[i]);
-          *reinterpret_cast<uint4*>(sa + i * 4096) = w[i];
+          for (int i = 0; i < 4; ++i) {
+            if (i < isplit) xf8(w[u][i], P, okm[i]); else xf8(w[u][i], Q, okm[i]);
+          }
+          mbar_wait(&empty[stage], phase ^ 1);                      // the MMAs that read this slot one lap ago have retired
+          uint8_t* sa = smem + stage * STB + off;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(sa + i * 4096) = w[u][i];
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&xfull[stage]);
+          if (++stage == NST) { stage = 0; phase ^= 1; }
+          if (++kb == nkb) { kb = 0; tile += tstep; }
+          if (s0 + u + XF_PF < S) issue(w[u]);                      // refill this register slot
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&xfull[stage]);
-        if (++stage == NST) { stage = 0; phase ^= 1; }
       }
     }
   } else {
@@ -650,6 +686,8 @@ static int tc_init() {
   return SG_OK;
 }
 
+int sg_conv_tc_warm() { return tc_init(); }
+
 static int make_map(CUtensorMap* m, const void* base, int bf16, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {ld * (bf16 ? 2 : 4)};
@@ -691,6 +729,7 @@ int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
   t.epilogue = a.epilogue; t.T = a.T > 0 ? a.T : 1; t.t_valid = a.t_valid;
   t.m_tiles = (a.rows + TC_BM - 1) / TC_BM; t.n_tiles = a.N / bn;
   t.xf_ab = reinterpret_cast<const uint4*>(a.xf_ab); t.xf_ld = a.xf_ld; t.xf_tv = a.xf_tv;
+  t.xf_A = reinterpret_cast<const uint8_t*>(a.A); t.xf_lda = a.lda;
   t.pf_dist = (a.taps == 1 || g_pf_all) ? g_pf_dist : 0;
   t.issue_mode = g_issue_mode;
   t.stb = TC_A_BYTES + bn * TC_BK * 4; t.nst = (TC_STAGES * TC_STAGE_BYTES) / t.stb;

@@ -102,7 +102,7 @@ int sg_feat_tables_build(SgFeatTables* t) {
 #define FEAT_WARPS 8
 #define WARP_SCRATCH 832                  // floats per warp: re[288] + im[288] + P[256]
 #define ACC_LEN 1520                      // 7*160 + 400: padded span of 8 consecutive frames
-#define ACC_FIN 1280                      // 8*160: positions no later group touches
+#define ACC_RING 2048                     // circular accumulator of the adjoint (>= ACC_LEN, power of two)
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -184,6 +184,22 @@ __device__ __forceinline__ void fft_out_to_smem(const float2 (&z)[8], float* sre
     }
 }
 
+// ---- split CTA barrier (mbarrier): arrive now, wait later -------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(a), "r"(parity) : "memory");
+  }
+}
+
 // ---- Philox4x32-7 (counter-based dither; 7 rounds pass BigCrush, Salmon et al. 2011) -----------------------------------------------------
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 #pragma unroll
@@ -215,7 +231,15 @@ struct DitherSpec {
   uint32_t seed_lo, seed_hi;
   uint32_t pass;
   uint32_t b_off;        // global index of utterance 0 (SG_OPT_UTT_OFFSET): the philox counter uses b + b_off
+  // CUDA-graph replay (sg_pgd_run): seed and pass counter live in device memory so that one captured iteration can be
+  // replayed for every iteration of every attack; ctl = {pass, seed_lo, seed_hi}, `pass` above is then added to ctl[0]
+  const uint32_t* ctl;
 };
+
+// resolve the device-resident part of a DitherSpec (warp-uniform loads, once per kernel)
+__device__ __forceinline__ void dither_resolve(DitherSpec& D) {
+  if (D.ctl != nullptr) { D.pass += __ldg(D.ctl); D.seed_lo = __ldg(D.ctl + 1); D.seed_hi = __ldg(D.ctl + 2); }
+}
 
 // Per-lane ownership of a frame: sample j = 64*n0 + 2*lane + e, n0 in [0,7), e in {0,1};
 // valid iff j < 400 (n0 == 6 only for lane < 8).  The FFT packs z[n] = g[2n] + i g[2n+1], so
@@ -382,6 +406,7 @@ mfcc_fwd_kernel(const float* __restrict__ x, int N, int m, int frames_per_cta, D
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SgFeatTables* T = reinterpret_cast<SgFeatTables*>(smem_raw);
   copy_tables(T, gT);
+  dither_resolve(D);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* scratch = reinterpret_cast<float*>(smem_raw + sizeof(SgFeatTables)) + warp * WARP_SCRATCH;
@@ -440,15 +465,17 @@ mfcc_bwd_kernel(const float* __restrict__ x, int N, int m, int own_frames, Dithe
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SgFeatTables* T = reinterpret_cast<SgFeatTables*>(smem_raw);
   float* fbase = reinterpret_cast<float*>(smem_raw + sizeof(SgFeatTables));
-  float* framebuf = fbase + FEAT_WARPS * WARP_SCRATCH;             // [8][400]
-  float* acc = framebuf + FEAT_WARPS * SG_WIN;                     // [ACC_LEN]
+  float* framebuf = fbase + FEAT_WARPS * WARP_SCRATCH;             // [8][400]: frame gradients of the current group
+  float* acc = framebuf + FEAT_WARPS * SG_WIN;                     // [ACC_RING]: circular overlap-add accumulator, index = padded position & (ACC_RING - 1)
+  __shared__ __align__(8) uint64_t ola_done;                       // split barrier: "group g's frame gradients have been consumed"
   copy_tables(T, gT);
-  for (int i = threadIdx.x; i < ACC_LEN; i += FEAT_THREADS) acc[i] = 0.f;
+  dither_resolve(D);
+  for (int i = threadIdx.x; i < ACC_RING; i += FEAT_THREADS) acc[i] = 0.f;
+  if (threadIdx.x == 0) mbar_init(&ola_done, FEAT_THREADS);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* scratch = fbase + warp * WARP_SCRATCH;
   float *sre = scratch, *sim = scratch + 288, *P = scratch + 576;
-  float* mybuf = framebuf + warp * SG_WIN;
   const int b = blockIdx.y;
   const float* xb = x + (size_t)b * N;
   const int f0 = blockIdx.x * own_frames;
@@ -458,8 +485,19 @@ mfcc_bwd_kernel(const float* __restrict__ x, int N, int m, int own_frames, Dithe
   const int own_lo = SG_SHIFT * f0 - SG_HALO;
   const int own_hi = (f1 == m) ? pmax + 1 : SG_SHIFT * f1 - SG_HALO;
 
-  for (int gf = fs; gf < f1; gf += FEAT_WARPS) {
-    const int fr = gf + warp;
+  // Frame groups of up to FEAT_WARPS frames.  The remainder goes FIRST so that the last group is full (or the only one):
+  // every sample whose right-reflected partner exists is then finalised in the last group, where the partner's sum is
+  // complete.  The first group keeps >= 2 frames so that it finalises all samples n < 120, whose left-reflected partners
+  // only need frame 0 (a remainder of 1 is split 5 + 4 with the following group).
+  const int nfrm = f1 - fs, rem = nfrm % FEAT_WARPS;
+  const int gs0 = nfrm <= FEAT_WARPS ? nfrm : (rem == 0 ? FEAT_WARPS : (rem == 1 ? 5 : rem));
+  const int gs1 = (nfrm > FEAT_WARPS && rem == 1) ? 4 : FEAT_WARPS;
+  int gi = 0;
+  int gsz = gs0;
+  for (int gf = fs; gf < f1; gf += gsz, gsz = (gi == 0 ? gs1 : FEAT_WARPS), ++gi) {
+    const int fr = (warp < gsz) ? gf + warp : f1;                  // warps beyond the group idle (fr >= f1)
+    float* const gbuf = framebuf;
+    float* const mybuf = gbuf + warp * SG_WIN;
     // prefetch the iterate / clean waveform of the samples this thread will finalise after the group's frames
     // (the loads then complete under the FFT work instead of stalling the whole CTA in the finalise phase)
     float pre_x[6], pre_x0[6];
@@ -563,6 +601,9 @@ mfcc_bwd_kernel(const float* __restrict__ x, int N, int m, int own_frames, Dithe
         s += dfe[n0] + dfo[n0];
       }
       const float mean = warp_sum(s) * (1.0f / SG_WIN);            // DC-removal adjoint
+      // the previous group's frame gradients must have been summed by every thread before they are overwritten; the
+      // arrivals happened right after that group's overlap-add, a whole frame computation ago: this wait is normally free
+      if (gi > 0) mbar_wait(&ola_done, (uint32_t)((gi - 1) & 1));
 #pragma unroll
       for (int n0 = 0; n0 < 7; ++n0)
         if ((n0 < 6) || (lane < 8))
@@ -570,36 +611,50 @@ mfcc_bwd_kernel(const float* __restrict__ x, int N, int m, int own_frames, Dithe
               make_float2((dfe[n0] - mean) * 32768.0f, (dfo[n0] - mean) * 32768.0f);
     }
     __syncthreads();
-    // ---- deterministic overlap-add of this group's frames -----------------------------------
-    const int base = SG_SHIFT * gf - SG_HALO;                      // padded position of acc[0]
-    const int nfr = min(FEAT_WARPS, f1 - gf);
-    for (int q = threadIdx.x; q < ACC_LEN; q += FEAT_THREADS) {
-      float a = acc[q];
+    // ---- deterministic overlap-add of this group's frames ------------------------------------
+    // One full barrier per group (frame gradients complete) plus a split mbarrier (frame gradients consumed, waited for
+    // just before the next group's gradients are stored).  The accumulator is a ring indexed by the padded sample
+    // position, so a position is summed, finalised and cleared by one thread in one visit.  Positions >= base + fin stay in the ring
+    // for the next group (its barrier orders the hand-over).  Only the utterance edges, whose reflected positions are summed
+    // by other threads, need the two-phase form.
+    const int base = SG_SHIFT * gf - SG_HALO;                      // padded position of ring slot q = 0 of this group
+    const int nfr = gsz;
+    const bool last = (gf + gsz >= f1);
+    const int fin = last ? ACC_LEN : SG_SHIFT * gsz;               // positions no later group touches
+    const bool edge = (gf == 0) || (last && f1 == m);              // CTA-uniform: left / right reflection partners in range
+    float asum[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const int q = threadIdx.x + i * FEAT_THREADS;
+      asum[i] = 0.f;
+      if (q >= ACC_LEN) continue;
+      float a = acc[(base + q) & (ACC_RING - 1)];
       // frames w with 0 <= q - 160 w < 400 (at most 3), in increasing w: fixed summation order
       const int w_hi = min(nfr - 1, q / SG_SHIFT);
       int w_lo = (q - SG_WIN + SG_SHIFT) / SG_SHIFT;               // ceil((q - 399) / 160) for q >= 240
       if (q < SG_WIN) w_lo = 0;
-      for (int w = w_lo; w <= w_hi; ++w) a += framebuf[w * SG_WIN + q - SG_SHIFT * w];
-      acc[q] = a;
+      for (int w = w_lo; w <= w_hi; ++w) a += gbuf[w * SG_WIN + q - SG_SHIFT * w];
+      asum[i] = a;
+      acc[(base + q) & (ACC_RING - 1)] = (edge || q >= fin) ? a : 0.f;   // finalised slots are released for the ring's next lap
     }
-    __syncthreads();
-    const bool last = (gf + FEAT_WARPS >= f1);
-    const int fin = last ? ACC_LEN : ACC_FIN;
+    if (edge) __syncthreads();                                     // reflected partners are complete
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
       const int q = threadIdx.x + i * FEAT_THREADS;
       if (q >= fin) continue;
       const int n = base + q;
       if (n < own_lo || n >= own_hi || n < 0 || n >= N) continue;
-      float g = acc[q];
-      if (n < SG_HALO) {                                           // left reflection: p = -n-1
-        const int qm = (-n - 1) - base;
-        if (qm >= 0 && qm < ACC_LEN) g += acc[qm];
-      }
-      const int pr = 2 * N - 1 - n;                                // right reflection
-      if (pr <= pmax) {
-        const int qm = pr - base;
-        if (qm >= 0 && qm < ACC_LEN) g += acc[qm];
+      float g = asum[i];
+      if (edge) {
+        if (n < SG_HALO) {                                         // left reflection: p = -n-1
+          const int qm = (-n - 1) - base;
+          if (qm >= 0 && qm < ACC_LEN) g += acc[(base + qm) & (ACC_RING - 1)];
+        }
+        const int pr = 2 * N - 1 - n;                              // right reflection
+        if (pr <= pmax) {
+          const int qm = pr - base;
+          if (qm >= 0 && qm < ACC_LEN) g += acc[(base + qm) & (ACC_RING - 1)];
+        }
       }
       const size_t gi = (size_t)b * N + n;
       if (O.mode == 0) {
@@ -613,15 +668,15 @@ mfcc_bwd_kernel(const float* __restrict__ x, int N, int m, int own_frames, Dithe
         O.x_out[gi] = fminf(fmaxf(xn, lo), hi);                    // attack/FGSM.py:68
       }
     }
-    __syncthreads();
-    if (!last) {
-      // shift the 240-sample overlap to the front, clear the rest
-      float keep = 0.f;
-      if (threadIdx.x < ACC_LEN - ACC_FIN) keep = acc[threadIdx.x + ACC_FIN];
-      __syncthreads();
-      for (int q = threadIdx.x; q < ACC_LEN; q += FEAT_THREADS) acc[q] = (q < ACC_LEN - ACC_FIN) ? keep : 0.f;
-      __syncthreads();
+    if (edge) {
+      __syncthreads();                                             // every reflected read is done: release the finalised slots
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const int q = threadIdx.x + i * FEAT_THREADS;
+        if (q < fin) acc[(base + q) & (ACC_RING - 1)] = 0.f;
+      }
     }
+    mbar_arrive(&ola_done);                                        // this thread is done with the group's frame gradients
   }
 }
 
@@ -629,6 +684,7 @@ mfcc_bwd_kernel(const float* __restrict__ x, int N, int m, int own_frames, Dithe
 // dither materialisation, sign step
 // =============================================================================================
 __global__ void dither_fill_kernel(int m, DitherSpec D, float* __restrict__ out) {
+  dither_resolve(D);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int fr = blockIdx.x * (blockDim.x >> 5) + warp, b = blockIdx.y;
   if (fr >= m) return;
@@ -777,8 +833,13 @@ __global__ void cmvn_prefix_kernel(const float* __restrict__ in, int ld_in, floa
 // =============================================================================================
 static size_t feat_fwd_smem() { return sizeof(SgFeatTables) + FEAT_WARPS * WARP_SCRATCH * sizeof(float); }
 static size_t feat_bwd_smem() {
-  return sizeof(SgFeatTables) + (FEAT_WARPS * WARP_SCRATCH + FEAT_WARPS * SG_WIN + ACC_LEN) * sizeof(float);
+  return sizeof(SgFeatTables) + (FEAT_WARPS * WARP_SCRATCH + FEAT_WARPS * SG_WIN + ACC_RING) * sizeof(float);
 }
+
+// Device control block {pass, seed_lo, seed_hi} for the launches that follow on this thread (set around the captured /
+// replayed PGD iteration by sg_api.cu; null = use the immediate seed / pass arguments).
+static thread_local const uint32_t* g_feat_ctl = nullptr;
+void sg_feat_set_ctl(const uint32_t* ctl) { g_feat_ctl = ctl; }
 
 // `pass` carries the pass counter in its low 32 bits and the handle's utterance offset in the high 32 (packed by
 // sg_api.cu: dither_pass())
@@ -786,7 +847,22 @@ static DitherSpec make_dither(int mode, const float* tensor, uint64_t seed, uint
   DitherSpec D;
   D.mode = mode; D.tensor = tensor;
   D.seed_lo = (uint32_t)seed; D.seed_hi = (uint32_t)(seed >> 32); D.pass = (uint32_t)pass; D.b_off = (uint32_t)(pass >> 32);
+  D.ctl = g_feat_ctl;
   return D;
+}
+__global__ void feat_ctl_init_kernel(uint32_t* ctl, uint32_t pass, uint32_t seed_lo, uint32_t seed_hi) {
+  ctl[0] = pass; ctl[1] = seed_lo; ctl[2] = seed_hi;
+}
+__global__ void feat_ctl_tick_kernel(uint32_t* ctl, uint32_t n) { ctl[0] += n; }
+int sg_feat_ctl_init_launch(uint32_t* ctl, uint64_t seed, uint32_t pass, cudaStream_t st) {
+  feat_ctl_init_kernel<<<1, 1, 0, st>>>(ctl, pass, (uint32_t)seed, (uint32_t)(seed >> 32));
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+int sg_feat_ctl_tick_launch(uint32_t* ctl, uint32_t n, cudaStream_t st) {
+  feat_ctl_tick_kernel<<<1, 1, 0, st>>>(ctl, n);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
 }
 
 int sg_feat_init() {

@@ -32,6 +32,16 @@ struct SgProf {
   }
 };
 
+// One captured PGD iteration per ping-pong parity (sg_pgd_run): replayed for every iteration of every attack whose shapes,
+// workspace and parameters match `key`.
+struct SgPgdGraph {
+  cudaGraphExec_t exec[2] = {nullptr, nullptr};
+  unsigned long long key[12] = {0};
+  cudaStream_t cap_stream = nullptr;   // private capture stream (the caller's may be the legacy default stream)
+  int kernels = 0;                     // kernels per captured iteration (launch accounting)
+  bool valid = false;
+};
+
 struct sg_handle {
   SgProf prof;
   int device = 0;
@@ -41,6 +51,8 @@ struct sg_handle {
   int l1_tap_form = 1;              // SG_OPT_L1_TAP_FORM: bf16 mode computes the layer-1 dgrad per tap (K = 512) + a shifted sum
   int feat_stash = 1;               // SG_OPT_FEAT_STASH: the fused attack loop hands the per-frame forward state to the MFCC adjoint
   int utt_offset = 0;               // SG_OPT_UTT_OFFSET: global index of utterance 0 (philox dither key)
+  int use_graph = 1;                // SG_OPT_CUDA_GRAPH: sg_pgd_run replays one captured iteration instead of ~26 launches per pass
+  SgPgdGraph pgd_graph;
   int pool_fusion = 1;              // SG_OPT_POOL_FUSION: bf16 mode contracts the pooling adjoint inside the layer-5 dgrad
   SgFeatTables* d_tables = nullptr;
   bool xv_loaded = false;
@@ -65,6 +77,7 @@ struct sg_handle {
   float* enroll = nullptr;
   SgHeadConst H;
   std::vector<void*> allocs;
+  void* comm = nullptr; int comm_rank = 0, comm_world = 0;   // NCCL communicator of the metric all-reduce (sg_comm.cu)
   struct SgAudioNet* an = nullptr;   // AudioNet state (sg_api_audionet.cu)
   struct SgIv* iv = nullptr;         // i-vector system state (sg_api_iv.cu)
 };
@@ -80,3 +93,4 @@ void sg_audionet_free(sg_handle* h);
 void sg_iv_free(sg_handle* h);
 int sg_load_backend(sg_handle* h, const float* plda_mean, const float* plda_transform, const float* plda_psi,
                     const float* enroll, int L, int S);
+extern "C" int sg_comm_destroy(sg_handle* h);

@@ -22,12 +22,16 @@ int sg_feat_bwd_launch(const SgFeatTables* dT, const float* x, int B, int N, int
 int sg_feat_bwd_step_launch(const SgFeatTables* dT, const float* x, int B, int N, int m, int mode,
                             const float* dither, uint64_t seed, uint64_t pass, const float* draw, int ld,
                             const float* x0, float* x_out, float step, float eps, cudaStream_t st, const float* stash = nullptr);
+void sg_feat_set_ctl(const uint32_t* ctl);                     // device {pass, seed_lo, seed_hi} for the following launches (null: immediates)
+int sg_feat_ctl_init_launch(uint32_t* ctl, uint64_t seed, uint32_t pass, cudaStream_t st);
+int sg_feat_ctl_tick_launch(uint32_t* ctl, uint32_t n, cudaStream_t st);
 size_t sg_feat_stash_floats(int B, int m);   // per-frame forward stash consumed by the adjoint (attack loop only)
 int sg_dither_fill_launch(int B, int m, uint64_t seed, uint64_t pass, float* out, cudaStream_t st);
 int sg_tap_gather_launch(const float* G, int ldg, float* out, int ldo, size_t rows, int taps, int dil, cudaStream_t st);
 int sg_step_linf_launch(float* x, const float* x0, const float* grad, size_t n, float step, float eps, cudaStream_t st);
 int sg_cmvn_launch(const float* in, int ld_in, float* out, int ld_out, int B, int T, int backward, cudaStream_t st);
 
+int sg_conv_tc_warm();                                         // per-device one-time setup of the tcgen05 kernels (outside any capture)
 int sg_pool_fwd_launch(const void* r5, int bf16, int B, int T, int Tv, const float* bn_mean, const float* bn_istd,
                        float* stats, float* save_mean, float* save_std, cudaStream_t st);
 int sg_pool_bwd_launch(const void* r5, int bf16, int B, int T, int Tv, const float* bn_istd, const float* dstats,

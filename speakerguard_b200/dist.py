@@ -67,10 +67,27 @@ def attack_metrics(x: torch.Tensor, adv: torch.Tensor, success) -> torch.Tensor:
                         noise.sqrt().sum(), delta.abs().max(1)[0].sum()])
 
 
-def reduce_metrics(local: torch.Tensor) -> Dict[str, float]:
-    """All-reduce (sum) of the metric vector over the job; a no-op without a process group."""
+def engine_comm_init(engine) -> None:
+    """Give ``engine`` its own NCCL communicator (sg_comm_init) for the metric all-reduce: rank 0's unique id travels over
+    the already-initialised torch.distributed group (host side, once per process)."""
+    if getattr(engine, "comm_world", 0) or not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return
+
+    def exchange(ident):
+        box = [ident]
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
+
+    engine.comm_init(dist.get_rank(), dist.get_world_size(), exchange)
+
+
+def reduce_metrics(local: torch.Tensor, engine=None) -> Dict[str, float]:
+    """All-reduce (sum) of the metric vector over the job; a no-op without a process group.  With an ``engine`` that has a
+    communicator (engine_comm_init) the reduction is libsgb200's own sg_allreduce_metrics; otherwise torch.distributed's."""
     v = local.clone()
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+    if engine is not None and getattr(engine, "comm_world", 0) > 1 and v.is_cuda:
+        engine.allreduce_metrics(v)
+    elif dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(v, op=dist.ReduceOp.SUM)
     n = max(float(v[0]), 1.0)
     return {"n": float(v[0]), "success_rate": float(v[1]) / n, "snr_db": float(v[2]) / n, "l2": float(v[3]) / n,

@@ -148,6 +148,25 @@ class Engine:
         names = [self.lib.sg_profile_name(c).decode() for c in range(_lib.PROF_COUNT)]
         return [(names[cats[i]], int(tags[i]), float(ms[i])) for i in range(n.value)]
 
+    # ---- the metric all-reduce (sg_comm.cu) -----------------------------------------------------------
+    def comm_init(self, rank: int, world: int, exchange) -> None:
+        """One NCCL communicator for this engine's GPU.  ``exchange(bytes_or_None) -> bytes``: a host channel that returns
+        rank 0's 128-byte id on every rank (dist.py uses torch.distributed's object broadcast)."""
+        buf = (C.c_char * 128)()
+        if rank == 0:
+            check(self.lib.sg_comm_unique_id(buf), "sg_comm_unique_id")
+        ident = exchange(bytes(buf) if rank == 0 else None)
+        assert len(ident) == 128
+        ibuf = (C.c_char * 128).from_buffer_copy(ident)
+        check(self.lib.sg_comm_init(self._h, ibuf, int(rank), int(world)), "sg_comm_init")
+        self.comm_world = world
+
+    def allreduce_metrics(self, v: torch.Tensor) -> torch.Tensor:
+        """In-place sum over the ranks of a device fp64 vector (NCCL over NVLink / NVSwitch)."""
+        assert v.is_cuda and v.dtype == torch.float64 and v.is_contiguous() and v.device == self.device
+        check(self.lib.sg_allreduce_metrics(self._h, _ptr(v), v.numel(), self.stream), "sg_allreduce_metrics")
+        return v
+
     def load_xv(self, p: Dict[str, torch.Tensor], bn_eps: float = 1e-5) -> None:
         """p: 'tdnn{1..5}.weight/.bias', 'bn{1..5}.mean/.var', 'fc1.weight/.bias', 'emb_mean',
         'lda' [L,513], 'plda.mean/.transform/.psi', 'enroll' [S,L] (any device; copied to host)."""

@@ -74,3 +74,36 @@ def test_sharded_attack_helper_through_the_public_classes():
         got_suc += suc
     assert torch.equal(torch.cat(got_adv), ref_adv)
     assert got_suc == ref_suc
+
+
+@pytest.mark.parametrize("prec,iters,eot", [("fp32", 3, 1), ("bf16", 4, 1), ("bf16", 5, 1), ("bf16", 2, 3)])
+def test_graph_replay_is_bit_identical_to_launch_by_launch(prec, iters, eot):
+    """SG_OPT_CUDA_GRAPH: the captured-iteration replay of sg_pgd_run (seed / pass counter read from the device control
+    block) gives exactly the iterates, scores and decisions of the launch-by-launch loop - odd and even iteration counts
+    (ping-pong parity), EOT > 1 (in-place step), and a second attack with another seed on the same captured graphs."""
+    from speakerguard_b200 import _lib
+    from speakerguard_b200.engine import Engine, make_loss_params
+    p = O.make_xv_params(seed=0)
+    B, N = 4, 32000
+    torch.manual_seed(9)
+    x = ((torch.rand(B, 1, N) * 2 - 1) * 0.5)[:, 0].contiguous().cuda()
+    y = torch.randint(0, 10, (B,)).cuda()
+    lp = make_loss_params("Entropy")
+    eng = Engine("cuda:0", precision=prec)
+    eng.load_xv(p)
+    ws = eng.pgd_ws(B, N)
+    out = {}
+    for graph in (0, 1):
+        eng.set_option(_lib.OPT_CUDA_GRAPH, graph)
+        for seed in (21, 22):
+            xa = x.clone()
+            n0 = eng.launch_count()
+            dec, sc, _ = eng.pgd_run(xa, x, y, max_iter=iters, epsilon=0.002, step_size=0.0004, lp=lp, eot_size=eot,
+                                     dither_mode=_lib.DITHER_PHILOX, seed=seed, ws=ws, grad_sign=1.0)
+            torch.cuda.synchronize()
+            out[(graph, seed)] = (xa.cpu(), dec.cpu(), sc.cpu(), eng.launch_count() - n0)
+    for seed in (21, 22):
+        a, b = out[(0, seed)], out[(1, seed)]
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+        assert abs(a[3] - b[3]) <= 8 + iters, (a[3], b[3])          # same kernels (+ control-block ticks / copies)
+    assert not torch.equal(out[(1, 21)][0], out[(1, 22)][0])
