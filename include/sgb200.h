@@ -71,6 +71,11 @@ int sg_get_precision(const sg_handle* h);
  * block so the same graphs serve every later attack with the same shapes / workspace / parameters.  Iterates are
  * bit-identical to the launch-by-launch path (0).  Not used with a dither tensor, a loss history or profiling on. */
 #define SG_OPT_CUDA_GRAPH 5
+/* SG_OPT_CMVN_FUSION (default 1): in sg_pgd_run / sg_xv_forward, utterances of <= 300 frames (every CMVN window is the whole
+ * utterance, model/iv_plda.py:321-337) get their CMVN inside the MFCC kernel (one thread-block cluster per utterance, column
+ * sums exchanged through distributed shared memory) and its adjoint inside the MFCC adjoint: two launches and the raw-feature
+ * round trip less per pass.  Bit-identical to the separate sg_cmvn_fwd / sg_cmvn_bwd stages (same summation order). */
+#define SG_OPT_CMVN_FUSION 6
 int sg_set_option(sg_handle* h, int option, int value);
 
 /* ---- x-vector / PLDA system: weights ---------------------------------------------------------

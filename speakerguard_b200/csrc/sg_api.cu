@@ -69,6 +69,7 @@ extern "C" int sg_create(sg_handle** out, int device) {
   if (const char* e = getenv("SGB200_FEAT_STASH")) h->feat_stash = atoi(e) != 0;
   if (const char* e = getenv("SGB200_L1_TAP_FORM")) h->l1_tap_form = atoi(e) != 0;
   if (const char* e = getenv("SGB200_CUDA_GRAPH")) h->use_graph = atoi(e) != 0;
+  if (const char* e = getenv("SGB200_CMVN_FUSION")) h->cmvn_fusion = atoi(e) != 0;
   SgFeatTables* host = new SgFeatTables();
   int r = sg_feat_tables_build(host);
   if (r != SG_OK) { delete host; delete h; sg_set_error("sg_create: feature table construction failed"); return r; }
@@ -110,6 +111,7 @@ extern "C" int sg_set_option(sg_handle* h, int option, int value) {
   if (option == SG_OPT_FEAT_STASH) { h->feat_stash = value != 0; return SG_OK; }
   if (option == SG_OPT_L1_TAP_FORM) { h->l1_tap_form = value != 0; return SG_OK; }
   if (option == SG_OPT_CUDA_GRAPH) { h->use_graph = value != 0; return SG_OK; }
+  if (option == SG_OPT_CMVN_FUSION) { h->cmvn_fusion = value != 0; return SG_OK; }
   if (option == SG_OPT_UTT_OFFSET) {
     if (value < 0) { sg_set_error("SG_OPT_UTT_OFFSET must be >= 0"); return SG_EINVAL; }
     h->utt_offset = value; return SG_OK;
@@ -615,9 +617,15 @@ extern "C" int sg_step_linf(sg_handle* h, float* x, const float* x0, const float
 static int forward_pass(sg_handle* h, const float* x, int B, int N, int m, int mode, const float* dither, uint64_t seed,
                         uint64_t pass, float thr, const XvWs& w, float* emb, float* scores, long long* dec, cudaStream_t st,
                         float* stash = nullptr) {
-  h->launches += 3;
-  PROF(h, SG_PROF_MFCC_FWD, st, sg_feat_fwd_launch(h->d_tables, x, B, N, m, mode, dither, seed, dither_pass(h, pass), w.raw, SG_FLD, st, stash));
-  PROF(h, SG_PROF_CMVN, st, sg_cmvn_launch(w.raw, SG_FLD, w.feat, SG_FLD, B, m, 0, st));
+  if (h->cmvn_fusion && sg_feat_cmvn_fusable(m)) {
+    // CMVN inside the MFCC kernel (one CTA cluster per utterance): no raw-feature round trip, one launch less
+    h->launches += 2;
+    PROF(h, SG_PROF_MFCC_FWD, st, sg_feat_fwd_launch(h->d_tables, x, B, N, m, mode, dither, seed, dither_pass(h, pass), w.feat, SG_FLD, st, stash, 1));
+  } else {
+    h->launches += 3;
+    PROF(h, SG_PROF_MFCC_FWD, st, sg_feat_fwd_launch(h->d_tables, x, B, N, m, mode, dither, seed, dither_pass(h, pass), w.raw, SG_FLD, st, stash));
+    PROF(h, SG_PROF_CMVN, st, sg_cmvn_launch(w.raw, SG_FLD, w.feat, SG_FLD, B, m, 0, st));
+  }
   SG_TRY(embed_fwd(h, w.feat, B, m, w, emb, st));
   PROF(h, SG_PROF_HEAD, st, sg_score_fwd_launch(h->H, emb, B, h->enroll, h->S, thr, scores, dec, st));
   return SG_OK;
@@ -653,14 +661,21 @@ static int pgd_iteration(sg_handle* h, float* cur, float* other, const float* x0
     PROF(h, SG_PROF_LOSS, st, sg_loss_launch(sc, y, B, h->S, p->loss, lossp, w.dscores, st));
     PROF(h, SG_PROF_HEAD, st, sg_score_bwd_launch(h->H, w.emb, w.dscores, B, h->enroll, h->S, w.demb, st));
     SG_TRY(embed_bwd(h, w.demb, B, m, w, w.dfeat, st));
-    PROF(h, SG_PROF_CMVN, st, sg_cmvn_launch(w.dfeat, SG_FLD, w.draw, SG_FLD, B, m, 1, st));
+    const int fuse_cmvn = h->cmvn_fusion && sg_feat_cmvn_fusable(m);
+    const float* dr = w.dfeat;                                     // fused: the MFCC adjoint applies dx = dy - mean(dy) itself
+    if (!fuse_cmvn) {
+      PROF(h, SG_PROF_CMVN, st, sg_cmvn_launch(w.dfeat, SG_FLD, w.draw, SG_FLD, B, m, 1, st));
+      dr = w.draw;
+    } else {
+      h->launches -= 1;
+    }
     h->launches += 1;
     if (E == 1) {
-      PROF(h, SG_PROF_MFCC_BWD, st, sg_feat_bwd_step_launch(h->d_tables, cur, B, N, m, p->dither_mode, dth, p->seed, dither_pass(h, pass), w.draw, SG_FLD, x0,
-                                     other, p->step_size * grad_sign, p->epsilon, st, stash));
+      PROF(h, SG_PROF_MFCC_BWD, st, sg_feat_bwd_step_launch(h->d_tables, cur, B, N, m, p->dither_mode, dth, p->seed, dither_pass(h, pass), dr, SG_FLD, x0,
+                                     other, p->step_size * grad_sign, p->epsilon, st, stash, fuse_cmvn));
     } else {
-      PROF(h, SG_PROF_MFCC_BWD, st, sg_feat_bwd_launch(h->d_tables, cur, B, N, m, p->dither_mode, dth, p->seed, dither_pass(h, pass), w.draw, SG_FLD, w.grad,
-                                1.0f / (float)E, e > 0, st, stash));
+      PROF(h, SG_PROF_MFCC_BWD, st, sg_feat_bwd_launch(h->d_tables, cur, B, N, m, p->dither_mode, dth, p->seed, dither_pass(h, pass), dr, SG_FLD, w.grad,
+                                1.0f / (float)E, e > 0, st, stash, fuse_cmvn));
     }
   }
   if (E > 1) {
@@ -733,7 +748,7 @@ extern "C" int sg_pgd_run(sg_handle* h, float* x_adv, const float* x0, const int
     memcpy(&key[7], &p->loss, sizeof(sg_loss_params));
     memcpy(&key[10], &p->decision_threshold, sizeof(float));
     key[11] = (unsigned long long)(grad_sign > 0.f) | ((unsigned long long)h->precision << 1) | ((unsigned long long)h->pool_fusion << 3) |
-              ((unsigned long long)h->feat_stash << 4) | ((unsigned long long)h->l1_tap_form << 5) |
+              ((unsigned long long)h->feat_stash << 4) | ((unsigned long long)h->l1_tap_form << 5) | ((unsigned long long)h->cmvn_fusion << 6) |
               ((unsigned long long)(uint32_t)h->utt_offset << 8);
     if (!h->pgd_graph.valid || memcmp(h->pgd_graph.key, key, sizeof(key)) != 0) {
       if (pgd_capture(h, B, N, m, p, grad_sign, w, key, st) != SG_OK) h->use_graph = 0;    // capture unavailable: launch-by-launch from now on

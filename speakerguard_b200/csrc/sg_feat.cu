@@ -12,6 +12,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <cooperative_groups.h>
+
 #include "sg_common.cuh"
 
 // =============================================================================================
@@ -103,6 +105,12 @@ int sg_feat_tables_build(SgFeatTables* t) {
 #define WARP_SCRATCH 832                  // floats per warp: re[288] + im[288] + P[256]
 #define ACC_LEN 1520                      // 7*160 + 400: padded span of 8 consecutive frames
 #define ACC_RING 2048                     // circular accumulator of the adjoint (>= ACC_LEN, power of two)
+// cmvn_colsum_order: column sums over the frames of an utterance of T <= CMN_WIN frames are formed as
+//   sum over chunks c of CMVN_CHUNK frames ( sum over r < 8 ( sum over i < 8 of x[64 c + r + 8 i] ) ), every sum left to right from 0.f,
+// by all three implementations (cmvn_kernel, the cluster epilogue of mfcc_fwd_kernel<true>, the prologue of mfcc_bwd_kernel),
+// so the fused attack loop and the stage-by-stage API produce identical bits.
+#define CMVN_CHUNK 64
+#define CMN_WIN 300
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -400,10 +408,18 @@ __device__ __forceinline__ float stash_load(const float* __restrict__ sp, Frame&
 // =============================================================================================
 // F1: waveform -> raw MFCC
 // =============================================================================================
-__global__ void __launch_bounds__(FEAT_THREADS)
+// CMVN = true (utterances of <= CMN_WIN frames, where every CMVN window is the whole utterance: model/iv_plda.py:321-337):
+// the CTAs of one utterance form a thread-block cluster (CMVN_CHUNK frames each); every warp keeps the running column sum
+// of the cepstra it produced, the CTA's column sums are exchanged through distributed shared memory, and the mean is
+// subtracted before the kernel ends, so `raw` receives the CMVN output and no separate CMVN launch (and no raw-feature
+// round trip through HBM) is needed.  The summation order (cmvn_colsum_order below) is the one the stand-alone cmvn_kernel
+// uses, so both routes give identical bits.
+template <bool CMVN, int MINB>
+__global__ void __launch_bounds__(FEAT_THREADS, MINB)
 mfcc_fwd_kernel(const float* __restrict__ x, int N, int m, int frames_per_cta, DitherSpec D,
                 float* __restrict__ raw, int ld, const SgFeatTables* __restrict__ gT, float* __restrict__ stash) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ float cm_chunk[32];                                   // CMVN: this CTA's column sums (read by the cluster)
   SgFeatTables* T = reinterpret_cast<SgFeatTables*>(smem_raw);
   copy_tables(T, gT);
   dither_resolve(D);
@@ -415,6 +431,7 @@ mfcc_fwd_kernel(const float* __restrict__ x, int N, int m, int frames_per_cta, D
   const float* xb = x + (size_t)b * N;
   const int f0 = blockIdx.x * frames_per_cta;
   const int f1 = min(f0 + frames_per_cta, m);
+  float colsum = 0.f;                                              // CMVN: sum of column `lane` over this warp's frames, in frame order
   for (int fr = f0 + warp; fr < f1; fr += FEAT_WARPS) {
     Frame F;
     load_frame(F, xb, N, b, m, fr, D, lane);
@@ -439,7 +456,35 @@ mfcc_fwd_kernel(const float* __restrict__ x, int N, int m, int frames_per_cta, D
     if (lane == 0) c = logE;                                       // kaldi.py:799-800
     if (lane >= SG_NCEP) c = 0.f;
     if (lane < ld) raw[((size_t)b * m + fr) * ld + lane] = c;
+    if (CMVN) colsum += c;
     __syncwarp();
+  }
+  if (CMVN) {
+    // model/iv_plda.py:296-377 with T <= 300: y[t] = x[t] - mean_t(x)
+    namespace cg = cooperative_groups;
+    cg::cluster_group cl = cg::this_cluster();
+    __syncthreads();                                               // every warp is done with its scratch
+    sre[lane] = colsum;                                            // warp partial (scratch of warp w starts at fbase + w * WARP_SCRATCH)
+    __syncthreads();
+    if (warp == 0) {
+      const float* fb = reinterpret_cast<const float*>(smem_raw + sizeof(SgFeatTables));
+      float a = 0.f;
+#pragma unroll
+      for (int w = 0; w < FEAT_WARPS; ++w) a += fb[w * WARP_SCRATCH + lane];
+      cm_chunk[lane] = a;
+    }
+    cl.sync();                                                     // all chunk sums of the utterance are published
+    float tot = 0.f;
+    const unsigned nr = cl.num_blocks();
+    for (unsigned r = 0; r < nr; ++r) tot += *cl.map_shared_rank(&cm_chunk[lane], r);   // rank order = chunk order
+    const float mu = tot / (float)m;
+    // each lane re-reads exactly the elements it wrote above (same thread: no fence needed) and subtracts the mean
+    if (lane < ld)
+      for (int fr = f0 + warp; fr < f1; fr += FEAT_WARPS) {
+        float* q = raw + ((size_t)b * m + fr) * ld + lane;
+        *q = (lane < SG_NCEP) ? *q - mu : 0.f;
+      }
+    cl.sync();                                                     // nobody leaves while a peer may still read its cm_chunk
   }
 }
 
@@ -455,6 +500,8 @@ struct BwdOut {
   float* x_out;           // mode 1: updated iterate (must not alias the input waveform)
   float step;             // mode 1: step_size * grad_sign
   float eps;              // mode 1
+  int cmvn;               // `draw` is d(CMVN output) of an utterance of <= CMN_WIN frames: the kernel applies the CMVN adjoint
+                          // dx = dy - mean_t(dy) itself (model/iv_plda.py:296-377 is self-adjoint when every window is [0, T))
 };
 
 template <bool STASH>
@@ -484,6 +531,34 @@ mfcc_bwd_kernel(const float* __restrict__ x, int N, int m, int own_frames, Dithe
   const int pmax = SG_SHIFT * (m - 1) + (SG_WIN - SG_HALO) - 1;    // last padded position touched
   const int own_lo = SG_SHIFT * f0 - SG_HALO;
   const int own_hi = (f1 == m) ? pmax + 1 : SG_SHIFT * f1 - SG_HALO;
+
+  // fused CMVN adjoint: column means of the utterance's d(feat), summed in cmvn_colsum_order (identical bits to cmvn_kernel);
+  // every CTA of the utterance recomputes them (m x 32 floats from L2) instead of a separate launch and a dRaw round trip
+  float cm_mu = 0.f;
+  if (O.cmvn) {
+    const float* db = draw + (size_t)b * m * ld;
+    const int nch = (m + CMVN_CHUNK - 1) / CMVN_CHUNK;
+    const bool cin = lane < SG_NCEP && lane < ld;
+    for (int c = 0; c < nch; ++c) {
+      float s0 = 0.f;
+#pragma unroll
+      for (int i = 0; i < CMVN_CHUNK / FEAT_WARPS; ++i) {
+        const int t = c * CMVN_CHUNK + warp + FEAT_WARPS * i;
+        if (t < m) s0 += cin ? __ldg(db + (size_t)t * ld + lane) : 0.f;
+      }
+      scratch[c * 32 + lane] = s0;
+    }
+    __syncthreads();
+    float tot = 0.f;
+    for (int c = 0; c < nch; ++c) {
+      float a = 0.f;
+#pragma unroll
+      for (int w = 0; w < FEAT_WARPS; ++w) a += fbase[w * WARP_SCRATCH + c * 32 + lane];
+      tot += a;
+    }
+    cm_mu = tot / (float)m;
+    __syncthreads();                                               // the scratch is reused by the frame computation
+  }
 
   // Frame groups of up to FEAT_WARPS frames.  The remainder goes FIRST so that the last group is full (or the only one):
   // every sample whose right-reflected partner exists is then finalised in the last group, where the partner's sum is
@@ -523,7 +598,7 @@ mfcc_bwd_kernel(const float* __restrict__ x, int N, int m, int own_frames, Dithe
         me = mel_energy(T, P, lane);
       }
       // ---- backward: cepstra -> log-mel -> mel -> power -> spectrum -----------------------
-      const float dC = (lane < SG_NCEP) ? __ldg(draw + ((size_t)b * m + fr) * ld + lane) : 0.f;
+      const float dC = (lane < SG_NCEP) ? __ldg(draw + ((size_t)b * m + fr) * ld + lane) - cm_mu : 0.f;
       const float dE = __shfl_sync(0xffffffffu, dC, 0);            // C0 <- log-energy
       __syncwarp();
       P[lane] = dC;                                                // P is free after mel_energy: dC[32] (k >= 30 zero)
@@ -713,7 +788,6 @@ __global__ void step_linf_kernel(float* __restrict__ x, const float* __restrict_
 // =============================================================================================
 // CMVN (model/iv_plda.py:296-377): y[t] = x[t] - mean(x[ws(t):we(t)]), window 300 centred
 // =============================================================================================
-#define CMN_WIN 300
 __device__ __forceinline__ void cmvn_window(int t, int T, int& ws, int& we) {
   ws = t - CMN_WIN / 2; we = ws + CMN_WIN;
   if (ws < 0) { we -= ws; ws = 0; }
@@ -723,7 +797,7 @@ __device__ __forceinline__ void cmvn_window(int t, int T, int& ws, int& we) {
 // one CTA per utterance, blockDim = (32 columns, 8 row lanes)
 __global__ void cmvn_kernel(const float* __restrict__ in, int ld_in, float* __restrict__ out, int ld_out,
                             int T, int ncol, int backward) {
-  __shared__ float part[8][33];
+  __shared__ float part[(CMN_WIN + CMVN_CHUNK - 1) / CMVN_CHUNK][8][33];
   __shared__ float tot[32];
   const int lc = threadIdx.x, c = blockIdx.y * 32 + lc, r = threadIdx.y, b = blockIdx.x;
   const float* ib = in + (size_t)b * T * ld_in;
@@ -731,15 +805,26 @@ __global__ void cmvn_kernel(const float* __restrict__ in, int ld_in, float* __re
   const bool cin = c < ncol && c < ld_in;
   if (T <= CMN_WIN) {
     // every window is [0,T): global mean.  Self-adjoint: dx = dy - mean(dy).
-    float s = 0.f;
-    for (int t = r; t < T; t += 8) s += cin ? ib[(size_t)t * ld_in + c] : 0.f;
-    part[r][lc] = s;
+    const int nch = (T + CMVN_CHUNK - 1) / CMVN_CHUNK;             // cmvn_colsum_order
+    for (int ch = 0; ch < nch; ++ch) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < CMVN_CHUNK / 8; ++i) {
+        const int t = ch * CMVN_CHUNK + r + 8 * i;
+        if (t < T) s += cin ? ib[(size_t)t * ld_in + c] : 0.f;
+      }
+      part[ch][r][lc] = s;
+    }
     __syncthreads();
     if (r == 0) {
-      float a = 0.f;
+      float sum = 0.f;
+      for (int ch = 0; ch < nch; ++ch) {
+        float a = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) a += part[i][lc];
-      tot[lc] = a / (float)T;
+        for (int i = 0; i < 8; ++i) a += part[ch][i][lc];
+        sum += a;
+      }
+      tot[lc] = sum / (float)T;
     }
     __syncthreads();
     const float mu = tot[lc];
@@ -865,20 +950,51 @@ int sg_feat_ctl_tick_launch(uint32_t* ctl, uint32_t n, cudaStream_t st) {
   return SG_OK;
 }
 
+// resident CTAs per SM the forward kernel is compiled for: 4 (64 registers, a few spilled words) or 3 (80 registers);
+// SGB200_FEAT_OCC selects (A/B switch)
+static int g_fwd_occ = 4;
+
 int sg_feat_init() {
-  SG_CUDA_CHECK(cudaFuncSetAttribute(mfcc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)feat_fwd_smem()));
+  if (const char* e = getenv("SGB200_FEAT_OCC")) g_fwd_occ = atoi(e) == 3 ? 3 : 4;
+  SG_CUDA_CHECK(cudaFuncSetAttribute(mfcc_fwd_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)feat_fwd_smem()));
+  SG_CUDA_CHECK(cudaFuncSetAttribute(mfcc_fwd_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)feat_fwd_smem()));
+  SG_CUDA_CHECK(cudaFuncSetAttribute(mfcc_fwd_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)feat_fwd_smem()));
+  SG_CUDA_CHECK(cudaFuncSetAttribute(mfcc_fwd_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)feat_fwd_smem()));
   SG_CUDA_CHECK(cudaFuncSetAttribute(mfcc_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)feat_bwd_smem()));
   SG_CUDA_CHECK(cudaFuncSetAttribute(mfcc_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)feat_bwd_smem()));
   return SG_OK;
 }
 
+int sg_feat_cmvn_fusable(int m) { return m >= 1 && m <= CMN_WIN; }
+
+// cmvn != 0 (requires sg_feat_cmvn_fusable(m)): `raw` receives the CMVN output (one cluster of ceil(m / 64) CTAs per utterance)
 int sg_feat_fwd_launch(const SgFeatTables* dT, const float* x, int B, int N, int m, int mode, const float* dither,
-                       uint64_t seed, uint64_t pass, float* raw, int ld, cudaStream_t st, float* stash) {
+                       uint64_t seed, uint64_t pass, float* raw, int ld, cudaStream_t st, float* stash, int cmvn) {
+  if (cmvn) {
+    if (!sg_feat_cmvn_fusable(m)) { sg_set_error("sg_feat_fwd_launch: fused CMVN needs m <= %d frames (got %d)", CMN_WIN, m); return SG_EINVAL; }
+    const int nch = (m + CMVN_CHUNK - 1) / CMVN_CHUNK;            // <= 5: a portable cluster size
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(nch, B); cfg.blockDim = dim3(FEAT_THREADS); cfg.dynamicSmemBytes = feat_fwd_smem(); cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = nch; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (g_fwd_occ == 4)
+      SG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mfcc_fwd_kernel<true, 4>, x, N, m, (int)CMVN_CHUNK, make_dither(mode, dither, seed, pass), raw, ld,
+                                       dT, stash));
+    else
+      SG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mfcc_fwd_kernel<true, 3>, x, N, m, (int)CMVN_CHUNK, make_dither(mode, dither, seed, pass), raw, ld,
+                                       dT, stash));
+    return SG_OK;
+  }
   int fpc = 64;
   while (fpc > 8 && (long long)B * ((m + fpc - 1) / fpc) < 592) fpc >>= 1;   // >= 4 CTAs per SM when possible
   dim3 grid((m + fpc - 1) / fpc, B);
-  mfcc_fwd_kernel<<<grid, FEAT_THREADS, feat_fwd_smem(), st>>>(x, N, m, fpc, make_dither(mode, dither, seed, pass),
-                                                              raw, ld, dT, stash);
+  if (g_fwd_occ == 4)
+    mfcc_fwd_kernel<false, 4><<<grid, FEAT_THREADS, feat_fwd_smem(), st>>>(x, N, m, fpc, make_dither(mode, dither, seed, pass), raw, ld, dT, stash);
+  else
+    mfcc_fwd_kernel<false, 3><<<grid, FEAT_THREADS, feat_fwd_smem(), st>>>(x, N, m, fpc, make_dither(mode, dither, seed, pass), raw, ld, dT, stash);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }
@@ -893,10 +1009,11 @@ static int bwd_own_frames(int B, int m) {
 
 int sg_feat_bwd_launch(const SgFeatTables* dT, const float* x, int B, int N, int m, int mode, const float* dither,
                        uint64_t seed, uint64_t pass, const float* draw, int ld, float* grad, float scale,
-                       int accumulate, cudaStream_t st, const float* stash) {
+                       int accumulate, cudaStream_t st, const float* stash, int cmvn) {
+  if (cmvn && !sg_feat_cmvn_fusable(m)) { sg_set_error("sg_feat_bwd_launch: fused CMVN needs m <= %d frames (got %d)", CMN_WIN, m); return SG_EINVAL; }
   BwdOut O;
   memset(&O, 0, sizeof(O));
-  O.mode = 0; O.grad = grad; O.scale = scale; O.accumulate = accumulate;
+  O.mode = 0; O.grad = grad; O.scale = scale; O.accumulate = accumulate; O.cmvn = cmvn;
   int own = bwd_own_frames(B, m);
   dim3 grid((m + own - 1) / own, B);
   if (stash) mfcc_bwd_kernel<true><<<grid, FEAT_THREADS, feat_bwd_smem(), st>>>(x, N, m, own, make_dither(mode, dither, seed, pass),
@@ -909,10 +1026,11 @@ int sg_feat_bwd_launch(const SgFeatTables* dT, const float* x, int B, int N, int
 
 int sg_feat_bwd_step_launch(const SgFeatTables* dT, const float* x, int B, int N, int m, int mode,
                             const float* dither, uint64_t seed, uint64_t pass, const float* draw, int ld,
-                            const float* x0, float* x_out, float step, float eps, cudaStream_t st, const float* stash) {
+                            const float* x0, float* x_out, float step, float eps, cudaStream_t st, const float* stash, int cmvn) {
+  if (cmvn && !sg_feat_cmvn_fusable(m)) { sg_set_error("sg_feat_bwd_step_launch: fused CMVN needs m <= %d frames (got %d)", CMN_WIN, m); return SG_EINVAL; }
   BwdOut O;
   memset(&O, 0, sizeof(O));
-  O.mode = 1; O.x0 = x0; O.x_out = x_out; O.step = step; O.eps = eps;
+  O.mode = 1; O.x0 = x0; O.x_out = x_out; O.step = step; O.eps = eps; O.cmvn = cmvn;
   int own = bwd_own_frames(B, m);
   dim3 grid((m + own - 1) / own, B);
   if (stash) mfcc_bwd_kernel<true><<<grid, FEAT_THREADS, feat_bwd_smem(), st>>>(x, N, m, own, make_dither(mode, dither, seed, pass),

@@ -53,6 +53,7 @@ struct sg_handle {
   int utt_offset = 0;               // SG_OPT_UTT_OFFSET: global index of utterance 0 (philox dither key)
   int use_graph = 1;                // SG_OPT_CUDA_GRAPH: sg_pgd_run replays one captured iteration instead of ~26 launches per pass
   SgPgdGraph pgd_graph;
+  int cmvn_fusion = 1;              // SG_OPT_CMVN_FUSION: utterances of <= 300 frames run CMVN (and its adjoint) inside the MFCC kernels
   int pool_fusion = 1;              // SG_OPT_POOL_FUSION: bf16 mode contracts the pooling adjoint inside the layer-5 dgrad
   SgFeatTables* d_tables = nullptr;
   bool xv_loaded = false;

@@ -15,13 +15,15 @@ struct SgHeadConst {           // device pointers + scalars describing the PLDA 
 
 int sg_feat_init();
 int sg_feat_fwd_launch(const SgFeatTables* dT, const float* x, int B, int N, int m, int mode, const float* dither,
-                       uint64_t seed, uint64_t pass, float* raw, int ld, cudaStream_t st, float* stash = nullptr);
+                       uint64_t seed, uint64_t pass, float* raw, int ld, cudaStream_t st, float* stash = nullptr, int cmvn = 0);
+int sg_feat_cmvn_fusable(int m);                               // m <= 300 frames: CMVN can run inside the MFCC kernels (cmvn = 1 below)
 int sg_feat_bwd_launch(const SgFeatTables* dT, const float* x, int B, int N, int m, int mode, const float* dither,
                        uint64_t seed, uint64_t pass, const float* draw, int ld, float* grad, float scale,
-                       int accumulate, cudaStream_t st, const float* stash = nullptr);
+                       int accumulate, cudaStream_t st, const float* stash = nullptr, int cmvn = 0);
 int sg_feat_bwd_step_launch(const SgFeatTables* dT, const float* x, int B, int N, int m, int mode,
                             const float* dither, uint64_t seed, uint64_t pass, const float* draw, int ld,
-                            const float* x0, float* x_out, float step, float eps, cudaStream_t st, const float* stash = nullptr);
+                            const float* x0, float* x_out, float step, float eps, cudaStream_t st, const float* stash = nullptr,
+                            int cmvn = 0);
 void sg_feat_set_ctl(const uint32_t* ctl);                     // device {pass, seed_lo, seed_hi} for the following launches (null: immediates)
 int sg_feat_ctl_init_launch(uint32_t* ctl, uint64_t seed, uint32_t pass, cudaStream_t st);
 int sg_feat_ctl_tick_launch(uint32_t* ctl, uint32_t n, cudaStream_t st);

@@ -150,3 +150,63 @@ class WavBatchLoader:
             if th is not None:
                 th.join()
                 th = None
+
+
+def attack_stream(attacker, batches, device=None, out: Optional[List[torch.Tensor]] = None):
+    """Run ``attacker.attack`` over an iterable of HOST batches ``(x [B,1,N] float32, y [B] int64)`` with the copies off
+    the critical path (the attackMain.py:306-333 loop: load batch -> attack -> save).
+
+    The host->device copy of batch k+1 and the device->host copy of the adversarial batch k-1 run on a side stream while
+    batch k is attacked on the current stream; pinned host tensors make both copies asynchronous (pageable ones still
+    work, they just serialise).  Yields ``(adv_host [B,1,N], success list)`` per batch, in order.  ``out``: optional list
+    of pinned host tensors to receive the adversarial batches (cycled; at least 2), else pinned buffers are allocated.
+    """
+    it = iter(batches)
+    first = next(it, None)
+    if first is None:
+        return
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    side = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
+
+    def upload(b):
+        x, y = b
+        with torch.cuda.stream(side):
+            xd, yd = x.to(dev, non_blocking=True), y.to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        return xd, yd, ev
+
+    nxt = upload(first)
+    pending = None                                  # (adv_host, success, event) of the previous batch
+    k = 0
+    while nxt is not None:
+        xd, yd, ev = nxt
+        b = next(it, None)
+        nxt = upload(b) if b is not None else None  # overlaps the attack below
+        main.wait_event(ev)
+        xd.record_stream(main); yd.record_stream(main)
+        adv, success = attacker.attack(xd, yd)      # synchronises on the decisions at its end
+        if out is not None:
+            host = out[k % len(out)]
+        else:
+            host = torch.empty(adv.shape, dtype=adv.dtype, pin_memory=True)
+        done = torch.cuda.Event()
+        with torch.cuda.stream(side):
+            side.wait_event(_record(main))
+            adv.record_stream(side)
+            host.copy_(adv, non_blocking=True)
+            done.record(side)
+        if pending is not None:
+            pending[2].synchronize()
+            yield pending[0], pending[1]
+        pending = (host, success, done)
+        k += 1
+    pending[2].synchronize()
+    yield pending[0], pending[1]
+
+
+def _record(stream):
+    ev = torch.cuda.Event()
+    ev.record(stream)
+    return ev

@@ -247,7 +247,8 @@ def test_end_to_end_against_reference_golden(eng, xv, tag):
     ref_g = torch.tensor(xv[f"{tag}.grad"])
     err = (grad - ref_g).abs() / ref_g.abs().max(1, keepdim=True)[0]
     print(f"[{tag}] input-gradient vs reference: max rel {float(err.max()):.3e} median rel {float(err.median()):.3e}")
-    assert float(err.median()) < 1e-4 and float(err.max()) < 0.2     # raw comparison: ReLU-kink flips allowed
+    # raw comparison, ReLU-kink flips allowed: measured on B200 median 1.5e-6 .. 6.7e-6, max 2.9e-3 .. 2.1e-2 (one flipped unit)
+    assert float(err.median()) < 2e-5 and float(err.max()) < 5e-2
     params = O.make_xv_params(seed=0)
     for b in range(x.shape[0]):                                     # strict, kink-resolved
         fn = kink.xv_input_grad_fn(x[b:b + 1], y[b:b + 1], params, O.loss_ce, d[b:b + 1])
