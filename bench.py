@@ -32,6 +32,17 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
+# The ONE JSON line goes to the real stdout; everything else the run prints (the attack classes keep the reference's
+# progress prints, attack/FGSM.py:30-34) goes to stderr so that stdout stays machine-readable.
+_STDOUT = sys.stdout
+sys.stdout = sys.stderr
+
+
+def _emit(line):
+    _STDOUT.write(line + "\n")
+    _STDOUT.flush()
+
+
 WORKLOAD = "PGD-100 Linf eps=0.002 step=0.0004 CE-untargeted vs xv_plda CSI-E (random-init TDNN+PLDA, L=200, S=10), " \
            "synthetic 3 s 16 kHz utterances, batch 1024 per GPU"
 PRECISION_NOTE = {
@@ -206,7 +217,7 @@ def run_reference(args):
            "config": {"workload": WORKLOAD, "note": note},
            "cpu_baseline": {"value": value, "unit": "utt-iter/s", "cores": cores, "kind": kind, "sample": sample},
            "e2e": {"value": value, "unit": "utt-iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    _emit(json.dumps(out))
 
 
 def measure_matmul_peak(dev, dtype: str, seconds: float = 2.0):
@@ -368,7 +379,7 @@ def run_iv(args):
     if not args.no_cpu_baseline and world == 1:
         v, sample, cores = iv_cpu_throughput(p, N)
         out["cpu_baseline"] = {"value": v, "unit": "utt-iter/s", "cores": cores, "kind": "port", "sample": sample}
-    print(json.dumps(out))
+    _emit(json.dumps(out))
     sys.stdout.flush()
 
 
@@ -479,7 +490,7 @@ def run_antrain(args):
     if not args.no_cpu_baseline and world == 1:
         v, sample, cores = antrain_cpu_throughput(N, pgd_iters=iters)
         out["cpu_baseline"] = {"value": v, "unit": "utt/s", "cores": cores, "kind": "port", "sample": sample}
-    print(json.dumps(out))
+    _emit(json.dumps(out))
     sys.stdout.flush()
 
 
@@ -592,7 +603,7 @@ def run_cw2(args):
     if not args.no_cpu_baseline and world == 1:
         v, sample, cores = cw2_cpu_throughput(N)
         out["cpu_baseline"] = {"value": v, "unit": "utt-iter/s", "cores": cores, "kind": "port", "sample": sample}
-    print(json.dumps(out))
+    _emit(json.dumps(out))
     sys.stdout.flush()
 
 
@@ -681,7 +692,11 @@ def xv_leg(args, precision, steps, warmup, e2e_steps, rank, world, local, want_m
     # with the attack on a side stream; pipeline fill and drain are inside the timed region)
     from speakerguard_b200.io import attack_stream
     adv_hosts = [adv_host, torch.empty(B, 1, N).pin_memory()]
+    if e2e_steps:                                                    # warm the side stream's allocator pool and the pipeline
+        for _adv_h, _succ in attack_stream(attacker, ((x_host, y_host) for _ in range(2)), device=dev, out=adv_hosts):
+            pass
     torch.cuda.synchronize()
+    dist.barrier()
     t0 = time.perf_counter()
     for _adv_h, _succ in attack_stream(attacker, ((x_host, y_host) for _ in range(e2e_steps)), device=dev, out=adv_hosts):
         pass
@@ -800,7 +815,7 @@ def run_torch_gpu(args):
         tdist.destroy_process_group()
     if rank != 0:
         return
-    print(json.dumps({"impl": "torch_gpu", "metric": "PGD utterance-iterations/s vs xv_plda", "value": world * B * iters / (ms_step / 1e3),
+    _emit(json.dumps({"impl": "torch_gpu", "metric": "PGD utterance-iterations/s vs xv_plda", "value": world * B * iters / (ms_step / 1e3),
                       "unit": "utt-iter/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
                       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
                       "config": {"workload": WORKLOAD, "batch_per_gpu": B, "samples": N, "pgd_iters": iters,
@@ -900,7 +915,7 @@ def main():
         out["cpu_baseline"] = cpu_reference_baseline(leg["params"], N)
         v, sample, cores = cpu_port_throughput(leg["params"], N, budget_s=6.0)
         out["cpu_baseline_port"] = {"value": v, "unit": "utt-iter/s", "cores": cores, "kind": "port", "sample": sample}
-    print(json.dumps(out))
+    _emit(json.dumps(out))
     sys.stdout.flush()
 
 

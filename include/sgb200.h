@@ -71,10 +71,14 @@ int sg_get_precision(const sg_handle* h);
  * block so the same graphs serve every later attack with the same shapes / workspace / parameters.  Iterates are
  * bit-identical to the launch-by-launch path (0).  Not used with a dither tensor, a loss history or profiling on. */
 #define SG_OPT_CUDA_GRAPH 5
-/* SG_OPT_CMVN_FUSION (default 1): in sg_pgd_run / sg_xv_forward, utterances of <= 300 frames (every CMVN window is the whole
- * utterance, model/iv_plda.py:321-337) get their CMVN inside the MFCC kernel (one thread-block cluster per utterance, column
- * sums exchanged through distributed shared memory) and its adjoint inside the MFCC adjoint: two launches and the raw-feature
- * round trip less per pass.  Bit-identical to the separate sg_cmvn_fwd / sg_cmvn_bwd stages (same summation order). */
+/* SG_OPT_CMVN_FUSION (default 0): in sg_pgd_run / sg_xv_forward, utterances of <= 300 frames (every CMVN window is the whole
+ * utterance, model/iv_plda.py:321-337) get their CMVN inside the MFCC kernel (every CTA publishes the column sums of its 64
+ * frames, the CTA that finishes the utterance last subtracts the mean from rows that are still in L2) and its adjoint inside
+ * the MFCC adjoint (a prologue that forms the column means of d feat): two launches and the raw-feature round trip less per
+ * pass, bit-identical to the separate sg_cmvn_fwd / sg_cmvn_bwd stages (same summation order).  Measured on B200 (PGD-100,
+ * B = 1024, 3 s): MFCC forward +4.8 ms, adjoint +1.8 ms, CMVN launches -4.6 ms per step, i.e. 2 ms slower than the separate
+ * kernels once those issue all their loads up front (10.8 -> 4.6 ms per step); a thread-block-cluster variant with a DSMEM
+ * exchange was slower still (+19 ms: every CTA waits for its cluster at the barrier).  Kept as an option, off by default. */
 #define SG_OPT_CMVN_FUSION 6
 int sg_set_option(sg_handle* h, int option, int value);
 

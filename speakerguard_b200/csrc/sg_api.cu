@@ -614,13 +614,26 @@ extern "C" int sg_step_linf(sg_handle* h, float* x, const float* x0, const float
 // ---------------------------------------------------------------------------------------------
 // fused passes
 // ---------------------------------------------------------------------------------------------
+// fused-CMVN scratch of the handle (grown outside any stream capture: called at the top of the entry points)
+static int cmvn_scratch_reserve(sg_handle* h, int B) {
+  if (!h->cmvn_fusion || B <= h->cm_cap) return SG_OK;
+  float* part = nullptr; unsigned int* cnt = nullptr;
+  SG_CUDA_CHECK(cudaMalloc(&part, sg_feat_cmvn_part_floats(B) * sizeof(float)));
+  SG_CUDA_CHECK(cudaMalloc(&cnt, (size_t)B * sizeof(unsigned int)));
+  SG_CUDA_CHECK(cudaMemset(cnt, 0, (size_t)B * sizeof(unsigned int)));
+  h->allocs.push_back(part); h->allocs.push_back(cnt);            // an outgrown pair stays allocated until sg_destroy
+  h->cm_part = part; h->cm_count = cnt; h->cm_cap = B;
+  return SG_OK;
+}
+
 static int forward_pass(sg_handle* h, const float* x, int B, int N, int m, int mode, const float* dither, uint64_t seed,
                         uint64_t pass, float thr, const XvWs& w, float* emb, float* scores, long long* dec, cudaStream_t st,
                         float* stash = nullptr) {
   if (h->cmvn_fusion && sg_feat_cmvn_fusable(m)) {
     // CMVN inside the MFCC kernel (one CTA cluster per utterance): no raw-feature round trip, one launch less
     h->launches += 2;
-    PROF(h, SG_PROF_MFCC_FWD, st, sg_feat_fwd_launch(h->d_tables, x, B, N, m, mode, dither, seed, dither_pass(h, pass), w.feat, SG_FLD, st, stash, 1));
+    PROF(h, SG_PROF_MFCC_FWD, st, sg_feat_fwd_launch(h->d_tables, x, B, N, m, mode, dither, seed, dither_pass(h, pass), w.feat, SG_FLD, st, stash, 1,
+                                                     h->cm_part, h->cm_count));
   } else {
     h->launches += 3;
     PROF(h, SG_PROF_MFCC_FWD, st, sg_feat_fwd_launch(h->d_tables, x, B, N, m, mode, dither, seed, dither_pass(h, pass), w.raw, SG_FLD, st, stash));
@@ -638,6 +651,7 @@ extern "C" int sg_xv_forward(sg_handle* h, const float* x, int B, int N, int dit
   if (!x || !ws || !scores) { sg_set_error("sg_xv_forward: bad argument"); return SG_EINVAL; }
   const int m = sg_num_frames(N);
   XvWs w = xv_ws_layout(ws, B, m, h->Lp, h->L, h->S, true, N);
+  SG_TRY(cmvn_scratch_reserve(h, B));
   return forward_pass(h, x, B, N, m, dither_mode, dither, seed, pass, decision_threshold, w, emb ? emb : w.emb, scores,
                       (long long*)decisions, (cudaStream_t)stream);
 }
@@ -729,6 +743,7 @@ extern "C" int sg_pgd_run(sg_handle* h, float* x_adv, const float* x0, const int
   cudaStream_t st = (cudaStream_t)stream;
   const int m = sg_num_frames(N), E = p->eot_size;
   XvWs w = xv_ws_layout(ws, B, m, h->Lp, h->L, h->S, true, N);
+  SG_TRY(cmvn_scratch_reserve(h, B));
   const size_t dstride = (size_t)B * m * SG_WIN;
   // grad_sign of attack/utils.py:114 follows the requested loss NAME (SV / OSI with loss='Entropy' run the margin loss with
   // the cross-entropy sign), so the caller passes it; 0 derives it from the effective loss
@@ -741,8 +756,9 @@ extern "C" int sg_pgd_run(sg_handle* h, float* x_adv, const float* x0, const int
   // ---- graph replay: every iteration is the same kernel sequence on workspace addresses ------------------------------
   bool graphed = false;
   if (h->use_graph && !h->prof.on && !loss_hist && p->dither_mode != SG_DITHER_TENSOR && p->max_iter >= 2) {
-    unsigned long long key[12] = {(unsigned long long)(uintptr_t)ws, (unsigned long long)B, (unsigned long long)N,
-                                  (unsigned long long)E, (unsigned long long)p->dither_mode, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long key[13] = {(unsigned long long)(uintptr_t)ws, (unsigned long long)B, (unsigned long long)N,
+                                  (unsigned long long)E, (unsigned long long)p->dither_mode, 0, 0, 0, 0, 0, 0, 0,
+                                  (unsigned long long)(uintptr_t)h->cm_part};
     static_assert(sizeof(sg_loss_params) == 24, "sg_loss_params fills key[7..9]");
     memcpy(&key[5], &p->epsilon, sizeof(float)); memcpy(&key[6], &p->step_size, sizeof(float));
     memcpy(&key[7], &p->loss, sizeof(sg_loss_params));

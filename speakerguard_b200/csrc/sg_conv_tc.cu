@@ -151,7 +151,6 @@ struct TcArgs {
   // the transform warps turn each staged tile into dA5 = (t < xf_tv && r > 0) ? alpha' + beta * r : 0 before the MMA
   // reads it.  xf_ab: [rows / T][xf_ld / 2] x {alpha' pair, beta pair} (bf16x2 each) per utterance and channel pair.
   const uint4* xf_ab; int xf_ld, xf_tv;
-  const uint8_t* xf_A; int xf_lda;   // XFORM: r5 itself (bf16, row stride xf_lda elements): loaded by the transform warps, not by TMA
   int pf_dist;                     // L2 prefetch distance of the A operand in k-blocks (0 = off)
   int issue_mode;                  // MMA issuer: 0 single-lane region, 1 warp-convergent loop with an elected lane
   int nst, stb;                    // pipeline ring: stages and bytes per stage (main kernel)
@@ -251,7 +250,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const int rbase = (int)rank * TC_BM;                                   // this CTA's rows inside a pair tile
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&xfull[s], 8); mbar_init(&xpeer[s], 1); }
+    for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&xfull[s], 4); mbar_init(&xpeer[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], PAIR ? 16 : 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -277,9 +276,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       int stage = 0; uint32_t phase = 0;
       const int bh = PAIR ? (a.bn >> 1) : a.bn;                       // B rows staged by this CTA
       // XFORM + PAIR: every CTA's boxes signal its OWN full barrier (its transform warps wait on it); plain PAIR: the leader's
-      // XFORM: A never goes through TMA (the transform warps load r5 from global memory, transform it in registers and store
-      // the swizzled tile themselves), so a stage's transaction is the B box only
-      const uint32_t tx = XFORM ? (uint32_t)bh * TC_BK * 4 : ((PAIR ? 2u : 1u) * (TC_A_BYTES + (uint32_t)bh * TC_BK * 4));
+      const uint32_t tx = ((PAIR && !XFORM) ? 2u : 1u) * (TC_A_BYTES + (uint32_t)bh * TC_BK * 4);
       // L2 prefetch cursor for the A operand, a.pf_dist k-blocks ahead of the load cursor.  A single-tap layer streams A
       // from HBM exactly once, and with only TC_STAGES - 1 boxes in flight per SM the ring cannot cover the HBM latency
       // (Little: 3 x 16 KB x 148 SMs / ~2 us = 3.5 TB/s); the prefetch moves that wait out of the ring, so the ring
@@ -313,7 +310,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             tma_load_2d_2sm(sa + TC_A_BYTES, &mapB, lead_full, kb * KB_ELEMS, n0);
           } else {
             mbar_expect_tx(&full[stage], tx);
-            if (!XFORM) tma_load_2d(sa, &mapA, &full[stage], kc * KB_ELEMS, p0 + tap * a.tap_step);
+            tma_load_2d(sa, &mapA, &full[stage], kc * KB_ELEMS, p0 + tap * a.tap_step);
             tma_load_2d(sa + TC_A_BYTES, &mapB, &full[stage], kb * KB_ELEMS, n0);
           }
           if (++stage == NST) { stage = 0; phase ^= 1; }
@@ -332,8 +329,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         int stage = 0; uint32_t phase = 0;
         for (int tile = cta0; tile < ntiles; tile += tstep)
           for (int kb = 0; kb < nkb; ++kb) {
-            mbar_wait(&full[stage], phase);                       // this CTA's half of B has landed
-            mbar_wait(&xfull[stage], phase);                      // and its 128 rows of A are transformed and stored
+            mbar_wait(&xfull[stage], phase);
             mbar_arrive_cluster(mapa_u32(smem_u32(&xpeer[stage]), 0));
             if (++stage == NST) { stage = 0; phase ^= 1; }
           }
@@ -352,8 +348,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int kb = 0; kb < nkb; ++kb) {
           const uint32_t sa = smem_base + (uint32_t)stage * STB;
           const uint64_t da = make_desc(sa), db = make_desc(sa + TC_A_BYTES);
-          mbar_wait(&full[stage], phase);
-          if (XFORM) mbar_wait(&xfull[stage], phase);
+          mbar_wait(XFORM ? &xfull[stage] : &full[stage], phase);
           if (PAIR && XFORM) mbar_wait(&xpeer[stage], phase);
           tc_fence_after();
           if (leader) {
@@ -384,8 +379,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)acc * TC_MAX_BN;
         for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&full[stage], phase);
-          if (XFORM) mbar_wait(&xfull[stage], phase);
+          mbar_wait(XFORM ? &xfull[stage] : &full[stage], phase);
           if (PAIR && XFORM) mbar_wait(&xpeer[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STB);
@@ -403,81 +397,80 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
     }
   } else if (XFORM && warp >= TC_MAIN_THREADS / 32) {
-    // ===== A-operand producer + transform: warps 10..17 (bf16 tiles: 128 rows x 64 channels, SWIZZLE_128B) =====
-    // The in-place form (TMA lands r5, these warps rewrite the tile) moved every A byte through shared memory three times
-    // (TMA write, transform read, transform write) on top of the MMA's own operand reads: ~770 cycles of the 128 B/clk
-    // shared-memory port per k-block against 512 cycles of tensor work.  Here the warps load r5 straight from global memory
-    // (16 bytes per thread and row, XF_PF k-blocks ahead in registers to cover the HBM latency), apply the pooling adjoint in
-    // registers and store the swizzled tile once.
-    // thread -> logical 16-byte chunk j (8 channels) of rows g, g+32, g+64, g+96; (g + 32 i) & 7 == g & 7, so the
-    // physical chunk position j ^ (row & 7) is the same for all four rows.  A tile spans at most two utterances
-    // (the host only selects this variant for T >= 128): rows before `isplit` use the parameters of utterance b0,
-    // the others those of b0 + 1.
-    constexpr int XF_PF = 3;
+    // ===== A-operand transform: warps 10..17 (bf16 tiles: 128 rows x 64 channels, SWIZZLE_128B) =====
+    // Two groups of four warps take ALTERNATE k-blocks of the ring, so that one group's latencies (barrier wait, shared-memory
+    // round trip, the generic->async proxy fence: 16 % of all samples as `membar` in the one-group form, and the parameter
+    // loads: another 16 % as long-scoreboard) overlap the other group's arithmetic; the parameters of a group's next k-block
+    // are requested before it waits for the current one.
+    // thread -> logical 16-byte chunk j (8 channels) of rows g, g+16, ..., g+112; (g + 16 i) & 7 == g & 7, so the physical
+    // chunk position j ^ (row & 7) is the same for all eight rows.  A tile spans at most two utterances (the host only
+    // selects this variant for T >= 128): rows before `isplit` use the parameters of utterance b0, the others those of b0 + 1.
     const int t = (int)threadIdx.x - TC_MAIN_THREADS;
-    const int j = t & 7, g = t >> 3;
+    const int xg = t >> 7, tg = t & 127;                            // transform group, thread within the group
+    const int j = tg & 7, g = tg >> 3;                              // g in [0, 16)
     const uint32_t off = (uint32_t)g * 128u + (uint32_t)((j ^ (g & 7)) << 4);
     const int nutt = a.rows / a.T;
-    const int my_tiles = cta0 < ntiles ? (ntiles - cta0 + tstep - 1) / tstep : 0;
-    const int S = my_tiles * nkb;                                   // k-blocks this CTA produces, in ring order
-    uint4 w[XF_PF][4];
-    // prefetch cursor
-    int ptile = cta0, pkb = 0;
-    auto issue = [&](uint4 (&dst)[4]) {
-      const int prow0 = (ptile / a.n_tiles) * TILE_ROWS + rbase + g;
-      const uint8_t* src = a.xf_A + ((size_t)prow0 * a.xf_lda + (size_t)pkb * 64 + j * 8) * 2;
+    struct XfTile { const uint4* q0; const uint4* q1; int isplit; uint32_t okbits; };
+    auto tile_info = [&](int tile) {
+      XfTile ti;
+      const int mt = tile / a.n_tiles;
+      const int row0 = mt * TILE_ROWS + rbase + g;
+      const int b0 = row0 / a.T;
+      const int tt0 = row0 - b0 * a.T;
+      int isplit = (a.T - tt0 + 15) >> 4;
+      if (isplit > 8) isplit = 8;
+      uint32_t ok = 0u;
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-        dst[i] = (prow0 + 32 * i < a.rows) ? __ldg(reinterpret_cast<const uint4*>(src + (size_t)32 * i * a.xf_lda * 2)) : make_uint4(0u, 0u, 0u, 0u);
-      if (++pkb == nkb) { pkb = 0; ptile += tstep; }
-    };
-#pragma unroll
-    for (int u = 0; u < XF_PF; ++u) if (u < S) issue(w[u]);
-    int stage = 0; uint32_t phase = 0;
-    int tile = cta0, kb = 0;
-    int isplit = 4;
-    uint32_t okm[4] = {0u, 0u, 0u, 0u};
-    const uint4* q0 = a.xf_ab;
-    const uint4* q1 = a.xf_ab;
-    for (int s0 = 0; s0 < S; s0 += XF_PF) {
-#pragma unroll
-      for (int u = 0; u < XF_PF; ++u) {
-        if (s0 + u < S) {
-          if (kb == 0) {                                            // new tile: utterance split and row validity
-            const int mt = tile / a.n_tiles;
-            const int row0 = mt * TILE_ROWS + rbase + g;
-            const int b0 = row0 / a.T;
-            const int tt0 = row0 - b0 * a.T;
-            isplit = (a.T - tt0 + 31) >> 5;
-            if (isplit > 4) isplit = 4;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int tt = tt0 + 32 * i - (i >= isplit ? a.T : 0);
-              okm[i] = ((row0 + 32 * i < a.rows) && (tt < a.xf_tv)) ? 0xffffffffu : 0u;
-            }
-            const bool second = (isplit < 4) && (b0 + 1 < nutt);
-            q0 = a.xf_ab + (((size_t)(b0 < nutt ? b0 : 0) * a.xf_ld + j * 8) >> 2);   // one uint4 = 4 channels
-            q1 = q0 + (second ? (a.xf_ld >> 2) : 0);
-          }
-          uint4 P[2], Q[2];
-#pragma unroll
-          for (int k = 0; k < 2; ++k) { P[k] = __ldg(q0 + kb * 16 + k); Q[k] = __ldg(q1 + kb * 16 + k); }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (i < isplit) xf8(w[u][i], P, okm[i]); else xf8(w[u][i], Q, okm[i]);
-          }
-          mbar_wait(&empty[stage], phase ^ 1);                      // the MMAs that read this slot one lap ago have retired
-          uint8_t* sa = smem + stage * STB + off;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(sa + i * 4096) = w[u][i];
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&xfull[stage]);
-          if (++stage == NST) { stage = 0; phase ^= 1; }
-          if (++kb == nkb) { kb = 0; tile += tstep; }
-          if (s0 + u + XF_PF < S) issue(w[u]);                      // refill this register slot
-        }
+      for (int i = 0; i < 8; ++i) {
+        const int tt = tt0 + 16 * i - (i >= isplit ? a.T : 0);
+        ok |= ((row0 + 16 * i < a.rows) && (tt < a.xf_tv)) ? (1u << i) : 0u;
       }
+      const bool second = (isplit < 8) && (b0 + 1 < nutt);
+      ti.q0 = a.xf_ab + (((size_t)(b0 < nutt ? b0 : 0) * a.xf_ld + j * 8) >> 2);   // one uint4 = 4 channels
+      ti.q1 = ti.q0 + (second ? (a.xf_ld >> 2) : 0);
+      ti.isplit = isplit; ti.okbits = ok;
+      return ti;
+    };
+    // ring position of this group's first k-block: s = xg
+    int stage = xg % NST; uint32_t phase = (uint32_t)((xg / NST) & 1);
+    int tile = cta0, kb = xg;
+    while (kb >= nkb) { kb -= nkb; tile += tstep; }
+    XfTile cur = tile_info(tile < ntiles ? tile : 0);
+    uint4 P[2], Q[2];
+    if (tile < ntiles) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) { P[k] = __ldg(cur.q0 + kb * 16 + k); Q[k] = __ldg(cur.q1 + kb * 16 + k); }
+    }
+    while (tile < ntiles) {
+      // this group's next k-block: two ring positions on
+      int ntile = tile, nkbk = kb + 2;
+      while (nkbk >= nkb) { nkbk -= nkb; ntile += tstep; }
+      XfTile nxt = cur;
+      if (ntile != tile && ntile < ntiles) nxt = tile_info(ntile);
+      uint4 Pn[2] = {P[0], P[1]}, Qn[2] = {Q[0], Q[1]};
+      if (ntile < ntiles) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) { Pn[k] = __ldg(nxt.q0 + nkbk * 16 + k); Qn[k] = __ldg(nxt.q1 + nkbk * 16 + k); }
+      }
+      mbar_wait(&full[stage], phase);
+      uint8_t* sa = smem + stage * STB + off;
+      uint4 w[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) w[i] = *reinterpret_cast<const uint4*>(sa + i * 2048);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t okm = 0u - ((cur.okbits >> i) & 1u);
+        if (i < cur.isplit) xf8(w[i], P, okm); else xf8(w[i], Q, okm);
+        *reinterpret_cast<uint4*>(sa + i * 2048) = w[i];
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&xfull[stage]);
+      stage += 2;
+      if (stage >= NST) { stage -= NST; phase ^= 1; }
+      cur = nxt; tile = ntile; kb = nkbk;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) { P[k] = Pn[k]; Q[k] = Qn[k]; }
     }
   } else {
     // ===== epilogue: warps 2..9 = two groups of four; a warp may only touch TMEM lanes 32*(warp%4) .. +31 =====
@@ -729,7 +722,6 @@ int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
   t.epilogue = a.epilogue; t.T = a.T > 0 ? a.T : 1; t.t_valid = a.t_valid;
   t.m_tiles = (a.rows + TC_BM - 1) / TC_BM; t.n_tiles = a.N / bn;
   t.xf_ab = reinterpret_cast<const uint4*>(a.xf_ab); t.xf_ld = a.xf_ld; t.xf_tv = a.xf_tv;
-  t.xf_A = reinterpret_cast<const uint8_t*>(a.A); t.xf_lda = a.lda;
   t.pf_dist = (a.taps == 1 || g_pf_all) ? g_pf_dist : 0;
   t.issue_mode = g_issue_mode;
   t.stb = TC_A_BYTES + bn * TC_BK * 4; t.nst = (TC_STAGES * TC_STAGE_BYTES) / t.stb;

@@ -12,8 +12,6 @@
 #include <math.h>
 #include <string.h>
 
-#include <cooperative_groups.h>
-
 #include "sg_common.cuh"
 
 // =============================================================================================
@@ -110,6 +108,7 @@ int sg_feat_tables_build(SgFeatTables* t) {
 // by all three implementations (cmvn_kernel, the cluster epilogue of mfcc_fwd_kernel<true>, the prologue of mfcc_bwd_kernel),
 // so the fused attack loop and the stage-by-stage API produce identical bits.
 #define CMVN_CHUNK 64
+#define CMVN_MAX_CHUNKS 8                 // (CMN_WIN + CMVN_CHUNK - 1) / CMVN_CHUNK = 5, padded
 #define CMN_WIN 300
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
@@ -191,6 +190,11 @@ __device__ __forceinline__ void fft_out_to_smem(const float2 (&z)[8], float* sre
       sim[k] = z[4 * j + k2].y;
     }
 }
+
+// ---- cache prefetch hints: the per-frame working set of the NEXT frame a warp will process is requested while the current
+// one is computed (one 128-byte line per lane), so the dependent loads at the top of the next iteration hit L1 / L2
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ---- split CTA barrier (mbarrier): arrive now, wait later -------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -409,17 +413,22 @@ __device__ __forceinline__ float stash_load(const float* __restrict__ sp, Frame&
 // F1: waveform -> raw MFCC
 // =============================================================================================
 // CMVN = true (utterances of <= CMN_WIN frames, where every CMVN window is the whole utterance: model/iv_plda.py:321-337):
-// the CTAs of one utterance form a thread-block cluster (CMVN_CHUNK frames each); every warp keeps the running column sum
-// of the cepstra it produced, the CTA's column sums are exchanged through distributed shared memory, and the mean is
-// subtracted before the kernel ends, so `raw` receives the CMVN output and no separate CMVN launch (and no raw-feature
-// round trip through HBM) is needed.  The summation order (cmvn_colsum_order below) is the one the stand-alone cmvn_kernel
-// uses, so both routes give identical bits.
+// every warp keeps the running column sum of the cepstra it produced; each CTA (CMVN_CHUNK frames) publishes its column sums
+// in `cm.part`, and the CTA that finishes an utterance LAST (a counter per utterance) forms the mean in chunk order and
+// subtracts it from all rows of the utterance, which are still in L2.  `raw` therefore receives the CMVN output: no separate
+// CMVN launch, no raw-feature round trip through HBM and - unlike a cluster barrier - no CTA ever waits for another.
+// The summation order (cmvn_colsum_order) is the one the stand-alone cmvn_kernel uses, so both routes give identical bits,
+// and it does not depend on which CTA happens to be last.
+struct CmvnScratch {
+  float* part;            // [B][CMVN_MAX_CHUNKS][32] column sums per chunk
+  unsigned int* count;    // [B] CTAs finished per utterance; zero between launches (the last CTA resets it)
+};
 template <bool CMVN, int MINB>
 __global__ void __launch_bounds__(FEAT_THREADS, MINB)
 mfcc_fwd_kernel(const float* __restrict__ x, int N, int m, int frames_per_cta, DitherSpec D,
-                float* __restrict__ raw, int ld, const SgFeatTables* __restrict__ gT, float* __restrict__ stash) {
+                float* __restrict__ raw, int ld, const SgFeatTables* __restrict__ gT, float* __restrict__ stash, CmvnScratch cm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ float cm_chunk[32];                                   // CMVN: this CTA's column sums (read by the cluster)
+  __shared__ int cm_last;                                          // CMVN: this CTA finished its utterance last
   SgFeatTables* T = reinterpret_cast<SgFeatTables*>(smem_raw);
   copy_tables(T, gT);
   dither_resolve(D);
@@ -434,6 +443,11 @@ mfcc_fwd_kernel(const float* __restrict__ x, int N, int m, int frames_per_cta, D
   float colsum = 0.f;                                              // CMVN: sum of column `lane` over this warp's frames, in frame order
   for (int fr = f0 + warp; fr < f1; fr += FEAT_WARPS) {
     Frame F;
+    if (fr + FEAT_WARPS < f1 && lane < 14) {                       // next frame's 400 samples: <= 14 lines of 128 bytes
+      int p = (fr + FEAT_WARPS) * SG_SHIFT - SG_HALO + 32 * lane;
+      p = p < 0 ? 0 : (p >= N ? N - 1 : p);                        // (edge frames read reflected samples: nearby lines anyway)
+      prefetch_l1(xb + p);
+    }
     load_frame(F, xb, N, b, m, fr, D, lane);
     const float logE = logf(fmaxf(F.sumsq, SG_EPS));               // kaldi.py:119
     frame_spectrum(F, T, sre, sim, P, lane);
@@ -461,30 +475,39 @@ mfcc_fwd_kernel(const float* __restrict__ x, int N, int m, int frames_per_cta, D
   }
   if (CMVN) {
     // model/iv_plda.py:296-377 with T <= 300: y[t] = x[t] - mean_t(x)
-    namespace cg = cooperative_groups;
-    cg::cluster_group cl = cg::this_cluster();
+    const float* fb = reinterpret_cast<const float*>(smem_raw + sizeof(SgFeatTables));
+    const int nch = gridDim.x;
     __syncthreads();                                               // every warp is done with its scratch
-    sre[lane] = colsum;                                            // warp partial (scratch of warp w starts at fbase + w * WARP_SCRATCH)
+    sre[lane] = colsum;                                            // warp partial (scratch of warp w starts at fb + w * WARP_SCRATCH)
     __syncthreads();
     if (warp == 0) {
-      const float* fb = reinterpret_cast<const float*>(smem_raw + sizeof(SgFeatTables));
       float a = 0.f;
 #pragma unroll
       for (int w = 0; w < FEAT_WARPS; ++w) a += fb[w * WARP_SCRATCH + lane];
-      cm_chunk[lane] = a;
+      __stcg(cm.part + ((size_t)b * CMVN_MAX_CHUNKS + blockIdx.x) * 32 + lane, a);
     }
-    cl.sync();                                                     // all chunk sums of the utterance are published
-    float tot = 0.f;
-    const unsigned nr = cl.num_blocks();
-    for (unsigned r = 0; r < nr; ++r) tot += *cl.map_shared_rank(&cm_chunk[lane], r);   // rank order = chunk order
-    const float mu = tot / (float)m;
-    // each lane re-reads exactly the elements it wrote above (same thread: no fence needed) and subtracts the mean
-    if (lane < ld)
-      for (int fr = f0 + warp; fr < f1; fr += FEAT_WARPS) {
-        float* q = raw + ((size_t)b * m + fr) * ld + lane;
-        *q = (lane < SG_NCEP) ? *q - mu : 0.f;
+    __threadfence();                                               // this CTA's rows and chunk sums are visible device-wide ...
+    __syncthreads();
+    if (threadIdx.x == 0) cm_last = (atomicAdd(cm.count + b, 1u) == (unsigned)nch - 1u);   // ... before it is counted
+    __syncthreads();
+    if (cm_last) {
+      __threadfence();
+      float tot = 0.f;
+      for (int c = 0; c < nch; ++c) tot += __ldcg(cm.part + ((size_t)b * CMVN_MAX_CHUNKS + c) * 32 + lane);   // chunk order
+      const float mu = tot / (float)m;
+      // rows written by the other CTAs are read past L1 (they are in L2); 8 rows per warp in flight
+      if (lane < ld) {
+        float* q0 = raw + (size_t)b * m * ld + lane;
+        for (int t0 = warp; t0 < m; t0 += 8 * FEAT_WARPS) {
+          float v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { const int t = t0 + u * FEAT_WARPS; v[u] = t < m ? __ldcg(q0 + (size_t)t * ld) : 0.f; }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { const int t = t0 + u * FEAT_WARPS; if (t < m) q0[(size_t)t * ld] = (lane < SG_NCEP) ? v[u] - mu : 0.f; }
+        }
       }
-    cl.sync();                                                     // nobody leaves while a peer may still read its cm_chunk
+      if (threadIdx.x == 0) cm.count[b] = 0u;                      // ready for the next launch on this stream
+    }
   }
 }
 
@@ -539,14 +562,21 @@ mfcc_bwd_kernel(const float* __restrict__ x, int N, int m, int own_frames, Dithe
     const float* db = draw + (size_t)b * m * ld;
     const int nch = (m + CMVN_CHUNK - 1) / CMVN_CHUNK;
     const bool cin = lane < SG_NCEP && lane < ld;
-    for (int c = 0; c < nch; ++c) {
-      float s0 = 0.f;
+    // all loads first (d(feat) was just written: L2 hits), then the sums in the fixed order
+    float v[(CMN_WIN + CMVN_CHUNK - 1) / CMVN_CHUNK][CMVN_CHUNK / FEAT_WARPS];
+#pragma unroll
+    for (int c = 0; c < (CMN_WIN + CMVN_CHUNK - 1) / CMVN_CHUNK; ++c)
 #pragma unroll
       for (int i = 0; i < CMVN_CHUNK / FEAT_WARPS; ++i) {
         const int t = c * CMVN_CHUNK + warp + FEAT_WARPS * i;
-        if (t < m) s0 += cin ? __ldg(db + (size_t)t * ld + lane) : 0.f;
+        v[c][i] = (cin && t < m) ? __ldg(db + (size_t)t * ld + lane) : 0.f;
       }
-      scratch[c * 32 + lane] = s0;
+#pragma unroll
+    for (int c = 0; c < (CMN_WIN + CMVN_CHUNK - 1) / CMVN_CHUNK; ++c) {
+      float s0 = 0.f;
+#pragma unroll
+      for (int i = 0; i < CMVN_CHUNK / FEAT_WARPS; ++i) s0 += v[c][i];   // frames beyond m contribute +0.f (exact)
+      if (c < nch) scratch[c * 32 + lane] = s0;
     }
     __syncthreads();
     float tot = 0.f;
@@ -584,6 +614,13 @@ mfcc_bwd_kernel(const float* __restrict__ x, int N, int m, int own_frames, Dithe
         const bool ok = (threadIdx.x + i * FEAT_THREADS < ACC_LEN) && n >= own_lo && n < own_hi && n >= 0 && n < N;
         pre_x[i] = ok ? __ldg(xb + n) : 0.f;
         pre_x0[i] = ok ? __ldg(O.x0 + (size_t)b * N + n) : 0.f;
+      }
+    }
+    if (STASH) {                                                   // the frame this warp takes in the NEXT group: 4 KB of stash (HBM) -> L2
+      const int nf = gf + gsz + warp;
+      if (nf < f1) {
+        prefetch_l2(stash + ((size_t)b * m + nf) * SG_STASH_FLOATS + 32 * lane);
+        if (lane == 0) prefetch_l2(draw + ((size_t)b * m + nf) * ld);
       }
     }
     if (fr < f1) {
@@ -704,11 +741,13 @@ mfcc_bwd_kernel(const float* __restrict__ x, int N, int m, int own_frames, Dithe
       asum[i] = 0.f;
       if (q >= ACC_LEN) continue;
       float a = acc[(base + q) & (ACC_RING - 1)];
-      // frames w with 0 <= q - 160 w < 400 (at most 3), in increasing w: fixed summation order
-      const int w_hi = min(nfr - 1, q / SG_SHIFT);
-      int w_lo = (q - SG_WIN + SG_SHIFT) / SG_SHIFT;               // ceil((q - 399) / 160) for q >= 240
-      if (q < SG_WIN) w_lo = 0;
-      for (int w = w_lo; w <= w_hi; ++w) a += gbuf[w * SG_WIN + q - SG_SHIFT * w];
+      // frames w with 0 <= q - 160 w < 400 (at most 3: w0 - 2, w0 - 1, w0 = q / 160), added in increasing w (fixed
+      // summation order); the three loads are independent, absent terms add +0.f (exact)
+      const int w0 = q / SG_SHIFT, o0 = q - SG_SHIFT * w0;         // o0 in [0, 160)
+      const float t2 = (w0 >= 2 && w0 - 2 < nfr && o0 + 2 * SG_SHIFT < SG_WIN) ? gbuf[(w0 - 2) * SG_WIN + o0 + 2 * SG_SHIFT] : 0.f;
+      const float t1 = (w0 >= 1 && w0 - 1 < nfr) ? gbuf[(w0 - 1) * SG_WIN + o0 + SG_SHIFT] : 0.f;
+      const float t0 = (w0 < nfr) ? gbuf[w0 * SG_WIN + o0] : 0.f;
+      a += t2; a += t1; a += t0;
       asum[i] = a;
       acc[(base + q) & (ACC_RING - 1)] = (edge || q >= fin) ? a : 0.f;   // finalised slots are released for the ring's next lap
     }
@@ -806,14 +845,20 @@ __global__ void cmvn_kernel(const float* __restrict__ in, int ld_in, float* __re
   if (T <= CMN_WIN) {
     // every window is [0,T): global mean.  Self-adjoint: dx = dy - mean(dy).
     const int nch = (T + CMVN_CHUNK - 1) / CMVN_CHUNK;             // cmvn_colsum_order
-    for (int ch = 0; ch < nch; ++ch) {
-      float s = 0.f;
+    float v[(CMN_WIN + CMVN_CHUNK - 1) / CMVN_CHUNK][CMVN_CHUNK / 8];   // this thread's rows, all loads in flight together
+#pragma unroll
+    for (int ch = 0; ch < (CMN_WIN + CMVN_CHUNK - 1) / CMVN_CHUNK; ++ch)
 #pragma unroll
       for (int i = 0; i < CMVN_CHUNK / 8; ++i) {
         const int t = ch * CMVN_CHUNK + r + 8 * i;
-        if (t < T) s += cin ? ib[(size_t)t * ld_in + c] : 0.f;
+        v[ch][i] = (cin && t < T) ? ib[(size_t)t * ld_in + c] : 0.f;
       }
-      part[ch][r][lc] = s;
+#pragma unroll
+    for (int ch = 0; ch < (CMN_WIN + CMVN_CHUNK - 1) / CMVN_CHUNK; ++ch) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < CMVN_CHUNK / 8; ++i) s += v[ch][i];         // rows beyond T contribute +0.f (exact)
+      if (ch < nch) part[ch][r][lc] = s;
     }
     __syncthreads();
     if (r == 0) {
@@ -828,8 +873,15 @@ __global__ void cmvn_kernel(const float* __restrict__ in, int ld_in, float* __re
     }
     __syncthreads();
     const float mu = tot[lc];
-    for (int t = r; t < T; t += 8)
-      if (c < ld_out) ob[(size_t)t * ld_out + c] = cin ? ib[(size_t)t * ld_in + c] - mu : 0.f;
+    if (c < ld_out) {
+#pragma unroll
+      for (int ch = 0; ch < (CMN_WIN + CMVN_CHUNK - 1) / CMVN_CHUNK; ++ch)
+#pragma unroll
+        for (int i = 0; i < CMVN_CHUNK / 8; ++i) {
+          const int t = ch * CMVN_CHUNK + r + 8 * i;
+          if (t < T) ob[(size_t)t * ld_out + c] = cin ? v[ch][i] - mu : 0.f;
+        }
+    }
     return;
   }
   // T > 300: sliding window.  Serial per column (rare path: > 3 s utterances), r == 0 only.
@@ -950,12 +1002,13 @@ int sg_feat_ctl_tick_launch(uint32_t* ctl, uint32_t n, cudaStream_t st) {
   return SG_OK;
 }
 
-// resident CTAs per SM the forward kernel is compiled for: 4 (64 registers, a few spilled words) or 3 (80 registers);
+// resident CTAs per SM the forward kernel is compiled for: 3 (80 registers, the default: measured 60.8 vs 61.5 ms per step)
+// or 4 (64 registers, a few spilled words);
 // SGB200_FEAT_OCC selects (A/B switch)
-static int g_fwd_occ = 4;
+static int g_fwd_occ = 3;
 
 int sg_feat_init() {
-  if (const char* e = getenv("SGB200_FEAT_OCC")) g_fwd_occ = atoi(e) == 3 ? 3 : 4;
+  if (const char* e = getenv("SGB200_FEAT_OCC")) g_fwd_occ = atoi(e) == 4 ? 4 : 3;
   SG_CUDA_CHECK(cudaFuncSetAttribute(mfcc_fwd_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)feat_fwd_smem()));
   SG_CUDA_CHECK(cudaFuncSetAttribute(mfcc_fwd_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)feat_fwd_smem()));
   SG_CUDA_CHECK(cudaFuncSetAttribute(mfcc_fwd_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)feat_fwd_smem()));
@@ -967,34 +1020,34 @@ int sg_feat_init() {
 
 int sg_feat_cmvn_fusable(int m) { return m >= 1 && m <= CMN_WIN; }
 
-// cmvn != 0 (requires sg_feat_cmvn_fusable(m)): `raw` receives the CMVN output (one cluster of ceil(m / 64) CTAs per utterance)
+// fused-CMVN scratch for B utterances: [B][CMVN_MAX_CHUNKS][32] floats, then [B] counters that must be ZERO before the first launch
+size_t sg_feat_cmvn_part_floats(int B) { return (size_t)B * CMVN_MAX_CHUNKS * 32; }
+
+// cmvn != 0 (requires sg_feat_cmvn_fusable(m)): `raw` receives the CMVN output
 int sg_feat_fwd_launch(const SgFeatTables* dT, const float* x, int B, int N, int m, int mode, const float* dither,
-                       uint64_t seed, uint64_t pass, float* raw, int ld, cudaStream_t st, float* stash, int cmvn) {
+                       uint64_t seed, uint64_t pass, float* raw, int ld, cudaStream_t st, float* stash, int cmvn,
+                       float* cmvn_part, unsigned int* cmvn_count) {
   if (cmvn) {
     if (!sg_feat_cmvn_fusable(m)) { sg_set_error("sg_feat_fwd_launch: fused CMVN needs m <= %d frames (got %d)", CMN_WIN, m); return SG_EINVAL; }
-    const int nch = (m + CMVN_CHUNK - 1) / CMVN_CHUNK;            // <= 5: a portable cluster size
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(nch, B); cfg.blockDim = dim3(FEAT_THREADS); cfg.dynamicSmemBytes = feat_fwd_smem(); cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = nch; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (!cmvn_part || !cmvn_count) { sg_set_error("sg_feat_fwd_launch: fused CMVN needs its scratch (sg_feat_cmvn_scratch_bytes)"); return SG_EINVAL; }
+    const int nch = (m + CMVN_CHUNK - 1) / CMVN_CHUNK;            // <= 5
+    CmvnScratch cm; cm.part = cmvn_part; cm.count = cmvn_count;
+    dim3 grid(nch, B);
     if (g_fwd_occ == 4)
-      SG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mfcc_fwd_kernel<true, 4>, x, N, m, (int)CMVN_CHUNK, make_dither(mode, dither, seed, pass), raw, ld,
-                                       dT, stash));
+      mfcc_fwd_kernel<true, 4><<<grid, FEAT_THREADS, feat_fwd_smem(), st>>>(x, N, m, (int)CMVN_CHUNK, make_dither(mode, dither, seed, pass), raw, ld, dT, stash, cm);
     else
-      SG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mfcc_fwd_kernel<true, 3>, x, N, m, (int)CMVN_CHUNK, make_dither(mode, dither, seed, pass), raw, ld,
-                                       dT, stash));
+      mfcc_fwd_kernel<true, 3><<<grid, FEAT_THREADS, feat_fwd_smem(), st>>>(x, N, m, (int)CMVN_CHUNK, make_dither(mode, dither, seed, pass), raw, ld, dT, stash, cm);
+    SG_LAUNCH_CHECK();
     return SG_OK;
   }
+  CmvnScratch cm; cm.part = nullptr; cm.count = nullptr;
   int fpc = 64;
   while (fpc > 8 && (long long)B * ((m + fpc - 1) / fpc) < 592) fpc >>= 1;   // >= 4 CTAs per SM when possible
   dim3 grid((m + fpc - 1) / fpc, B);
   if (g_fwd_occ == 4)
-    mfcc_fwd_kernel<false, 4><<<grid, FEAT_THREADS, feat_fwd_smem(), st>>>(x, N, m, fpc, make_dither(mode, dither, seed, pass), raw, ld, dT, stash);
+    mfcc_fwd_kernel<false, 4><<<grid, FEAT_THREADS, feat_fwd_smem(), st>>>(x, N, m, fpc, make_dither(mode, dither, seed, pass), raw, ld, dT, stash, cm);
   else
-    mfcc_fwd_kernel<false, 3><<<grid, FEAT_THREADS, feat_fwd_smem(), st>>>(x, N, m, fpc, make_dither(mode, dither, seed, pass), raw, ld, dT, stash);
+    mfcc_fwd_kernel<false, 3><<<grid, FEAT_THREADS, feat_fwd_smem(), st>>>(x, N, m, fpc, make_dither(mode, dither, seed, pass), raw, ld, dT, stash, cm);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }

@@ -36,7 +36,7 @@ struct SgProf {
 // workspace and parameters match `key`.
 struct SgPgdGraph {
   cudaGraphExec_t exec[2] = {nullptr, nullptr};
-  unsigned long long key[12] = {0};
+  unsigned long long key[13] = {0};
   cudaStream_t cap_stream = nullptr;   // private capture stream (the caller's may be the legacy default stream)
   int kernels = 0;                     // kernels per captured iteration (launch accounting)
   bool valid = false;
@@ -53,7 +53,9 @@ struct sg_handle {
   int utt_offset = 0;               // SG_OPT_UTT_OFFSET: global index of utterance 0 (philox dither key)
   int use_graph = 1;                // SG_OPT_CUDA_GRAPH: sg_pgd_run replays one captured iteration instead of ~26 launches per pass
   SgPgdGraph pgd_graph;
-  int cmvn_fusion = 1;              // SG_OPT_CMVN_FUSION: utterances of <= 300 frames run CMVN (and its adjoint) inside the MFCC kernels
+  float* cm_part = nullptr; unsigned int* cm_count = nullptr; int cm_cap = 0;   // fused-CMVN scratch (chunk sums, counters) for cm_cap utterances
+  int cmvn_fusion = 0;              // SG_OPT_CMVN_FUSION: utterances of <= 300 frames run CMVN (and its adjoint) inside the MFCC kernels
+                                    // (off: measured 2 ms per PGD-100 step SLOWER than the two 23 us cmvn launches, see sgb200.h)
   int pool_fusion = 1;              // SG_OPT_POOL_FUSION: bf16 mode contracts the pooling adjoint inside the layer-5 dgrad
   SgFeatTables* d_tables = nullptr;
   bool xv_loaded = false;

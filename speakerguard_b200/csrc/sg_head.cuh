@@ -15,7 +15,9 @@ struct SgHeadConst {           // device pointers + scalars describing the PLDA 
 
 int sg_feat_init();
 int sg_feat_fwd_launch(const SgFeatTables* dT, const float* x, int B, int N, int m, int mode, const float* dither,
-                       uint64_t seed, uint64_t pass, float* raw, int ld, cudaStream_t st, float* stash = nullptr, int cmvn = 0);
+                       uint64_t seed, uint64_t pass, float* raw, int ld, cudaStream_t st, float* stash = nullptr, int cmvn = 0,
+                       float* cmvn_part = nullptr, unsigned int* cmvn_count = nullptr);
+size_t sg_feat_cmvn_part_floats(int B);                        // fused-CMVN scratch: this many floats + B zeroed counters
 int sg_feat_cmvn_fusable(int m);                               // m <= 300 frames: CMVN can run inside the MFCC kernels (cmvn = 1 below)
 int sg_feat_bwd_launch(const SgFeatTables* dT, const float* x, int B, int N, int m, int mode, const float* dither,
                        uint64_t seed, uint64_t pass, const float* draw, int ld, float* grad, float scale,
