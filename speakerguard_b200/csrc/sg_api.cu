@@ -301,6 +301,7 @@ extern "C" int sg_load_xv(sg_handle* h, const sg_xv_weights* w) {
 struct XvWs {
   uint32_t* bits[4];
   float *r[5], *G0, *G1, *G2, *stats, *dstats, *save_mean, *save_std, *ab, *e1, *de1, *e2, *de2, *tsave, *scal;
+  float* splitk; size_t splitk_floats;   // fp32 partials of the head's split-K contractions (8 slices x B rows padded to 128 x 512)
   // attack-loop extras
   float *raw, *draw, *feat, *dfeat, *emb, *demb, *scores, *dscores, *loss, *xbuf, *grad, *stash;
   float *xbuf2, *x0c;               // graph replay: the iterate ping-pongs between xbuf / xbuf2, x0 and y are copied in so that
@@ -328,6 +329,8 @@ static XvWs xv_ws_layout(void* base, int B, int T, int Lp, int L, int S, bool at
   w.e1 = take((size_t)B * SG_EMB); w.de1 = take((size_t)B * SG_EMB);
   w.e2 = take((size_t)B * Lp); w.de2 = take((size_t)B * Lp); w.tsave = take((size_t)B * Lp);
   w.scal = take((size_t)B * 4);
+  w.splitk_floats = (size_t)8 * ((B + 127) / 128) * 128 * SG_EMB;
+  w.splitk = take(w.splitk_floats);
   w.raw = w.draw = w.feat = w.dfeat = w.emb = w.demb = w.scores = w.dscores = w.loss = w.xbuf = w.grad = w.stash = nullptr;
   w.dec = w.yc = nullptr; w.xbuf2 = w.x0c = nullptr; w.ctl = nullptr;
   if (attack) {
@@ -430,7 +433,11 @@ extern "C" int sg_cmvn_bwd(sg_handle* h, const float* dout, int ld_in, float* dr
 // ---- TDNN -------------------------------------------------------------------------------------
 int sg_run_conv(sg_handle* h, const SgConvArgs& a, bool tensor_ok, int cat, cudaStream_t st) {
   h->launches += 1;
-  if (h->precision != SG_PREC_FP32 && tensor_ok) { PROF(h, cat, st, sg_conv_tc(a, h->precision, st)); return SG_OK; }
+  if (h->precision != SG_PREC_FP32 && tensor_ok) {
+    PROF(h, cat, st, sg_conv_tc(a, h->precision, st));
+    h->launches += sg_conv_tc_extra_launches();                  // the split-K reduction, when one was launched
+    return SG_OK;
+  }
   PROF(h, cat, st, sg_conv_simt(a, st));
   return SG_OK;
 }
@@ -469,6 +476,7 @@ static int embed_fwd(sg_handle* h, const float* feat, int B, int T, const XvWs& 
     memset(&a, 0, sizeof(a));
     a.A = w.stats; a.lda = SG_STATS; a.W = h->Wfc; a.Wk = h->Wfc_k; a.bias = h->bfc; a.out = w.e1; a.ldo = SG_EMB;
     a.rows = B; a.N = SG_EMB; a.cin = SG_STATS; a.taps = 1; a.tap_step = 0; a.epilogue = SG_EPI_BIAS; a.T = 1;
+    a.splitk_ws = w.splitk; a.splitk_floats = w.splitk_floats;
     SG_TRY(sg_run_conv(h, a, true, SG_PROF_HEAD_GEMM, st));
     a.A = w.e1; a.lda = SG_EMB; a.W = h->Wlda; a.Wk = h->Wlda_k; a.bias = h->blda; a.out = w.e2; a.ldo = h->Lp;
     a.N = h->Lp; a.cin = SG_EMB;
@@ -490,6 +498,7 @@ static int embed_bwd(sg_handle* h, const float* demb, int B, int T, const XvWs& 
     memset(&a, 0, sizeof(a));
     a.A = w.de2; a.lda = h->Lp; a.W = h->Wlda_b; a.Wk = h->Wlda_bk; a.out = w.de1; a.ldo = SG_EMB;
     a.rows = B; a.N = SG_EMB; a.cin = h->Lp; a.taps = 1; a.epilogue = SG_EPI_NONE; a.T = 1;
+    a.splitk_ws = w.splitk; a.splitk_floats = w.splitk_floats;
     SG_TRY(sg_run_conv(h, a, true, SG_PROF_HEAD_GEMM, st));
     a.A = w.de1; a.lda = SG_EMB; a.W = h->Wfc_b; a.Wk = h->Wfc_bk; a.out = w.dstats; a.ldo = SG_STATS; a.N = SG_STATS; a.cin = SG_EMB;
     SG_TRY(sg_run_conv(h, a, true, SG_PROF_HEAD_GEMM, st));

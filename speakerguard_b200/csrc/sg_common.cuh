@@ -103,12 +103,15 @@ struct SgConvArgs {
   // tensor-core path, bf16 only: fuse the statistics-pooling adjoint into this (layer-5 dgrad) contraction.  A is then the
   // stored activation r5 and xf_ab [rows / T][xf_ld] holds (alpha', beta) pairs: dA5 = (t < xf_tv && r > 0) ? alpha' + beta r : 0
   const float* xf_ab; int xf_ld; int xf_tv;
+  // tensor-core path, small problems: scratch for split-K partials (fp32, splitk_floats elements); null = no split
+  float* splitk_ws; size_t splitk_floats;
   // batched GEMM (SIMT path only): blockIdx.z selects an item; element strides, 0 = shared operand
   int nbatch; long long strideA, strideW, strideO;
 };
 
 int sg_conv_simt(const SgConvArgs& a, cudaStream_t st);
 int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st);   // tcgen05 path (sg_tdnn_tc.cu)
+int sg_conv_tc_extra_launches();                                       // kernels the last sg_conv_tc on this thread launched beyond the contraction
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

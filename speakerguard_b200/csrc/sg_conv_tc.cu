@@ -154,6 +154,9 @@ struct TcArgs {
   int pf_dist;                     // L2 prefetch distance of the A operand in k-blocks (0 = off)
   int issue_mode;                  // MMA issuer: 0 single-lane region, 1 warp-convergent loop with an elected lane
   int nst, stb;                    // pipeline ring: stages and bytes per stage (main kernel)
+  // split-K (small problems): tile index = (m-tile, n-tile, k-slice); slice ks contracts k-blocks [ks * kb_per, (ks+1) * kb_per)
+  // and stores its fp32 partial at row offset ks * rows_pad of the partial buffer (the output map then covers that buffer)
+  int ksplit, kb_per, rows_pad;
 };
 
 // ---- cluster / cta_group::2 helpers ------------------------------------------------------------
@@ -241,7 +244,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = a.taps * a.kchunks;
-  const int ntiles = a.m_tiles * a.n_tiles;
+  const int ntiles = a.m_tiles * a.n_tiles * a.ksplit;
   constexpr int KB_ELEMS = KIND_BF16 ? 64 : 32;     // elements per 128-byte k-block
   const uint32_t rank = PAIR ? cluster_rank() : 0u;
   const int cta0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // first tile of this CTA (pair)
@@ -291,9 +294,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       };
       for (int i = 0; i < a.pf_dist; ++i) prefetch_next();
       for (int tile = cta0; tile < ntiles; tile += tstep) {
-        const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
+        const int t2 = tile / a.ksplit, ks = tile - t2 * a.ksplit;
+        const int mt = t2 / a.n_tiles, nt = t2 - mt * a.n_tiles;
         const int p0 = mt * TILE_ROWS + rbase, n0 = nt * a.bn + (int)rank * (PAIR ? bh : 0);
-        for (int kb = 0; kb < nkb; ++kb) {
+        const int kb0 = ks * a.kb_per, kb1 = min(nkb, kb0 + a.kb_per);
+        for (int kb = kb0; kb < kb1; ++kb) {
           const int tap = kb / a.kchunks, kc = kb - tap * a.kchunks;
           if (a.pf_dist > 0) prefetch_next();
           mbar_wait(&empty[stage], phase ^ 1);
@@ -345,7 +350,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)acc * TC_MAX_BN;
-        for (int kb = 0; kb < nkb; ++kb) {
+        const int nk = min(nkb, (tile % a.ksplit) * a.kb_per + a.kb_per) - (tile % a.ksplit) * a.kb_per;   // k-blocks of this slice
+        for (int kb = 0; kb < nk; ++kb) {
           const uint32_t sa = smem_base + (uint32_t)stage * STB;
           const uint64_t da = make_desc(sa), db = make_desc(sa + TC_A_BYTES);
           mbar_wait(XFORM ? &xfull[stage] : &full[stage], phase);
@@ -378,7 +384,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)acc * TC_MAX_BN;
-        for (int kb = 0; kb < nkb; ++kb) {
+        const int nk = min(nkb, (tile % a.ksplit) * a.kb_per + a.kb_per) - (tile % a.ksplit) * a.kb_per;   // k-blocks of this slice
+        for (int kb = 0; kb < nk; ++kb) {
           mbar_wait(XFORM ? &xfull[stage] : &full[stage], phase);
           if (PAIR && XFORM) mbar_wait(&xpeer[stage], phase);
           tc_fence_after();
@@ -489,7 +496,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     int acc = 0; uint32_t acc_phase = 0;
     uint32_t nstore = 0;
     for (int tile = cta0; tile < ntiles; tile += tstep) {
-      const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
+      const int t2 = tile / a.ksplit, ks = tile - t2 * a.ksplit;
+      const int mt = t2 / a.n_tiles, nt = t2 - mt * a.n_tiles;
       const int row = mt * TILE_ROWS + rbase + r_in;
       const int n0 = nt * a.bn;
       if (has_bias) {
@@ -607,7 +615,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int j = 0; j < 8; ++j) srow[j ^ (r_in & 7)] = packed[j];
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         epi_bar(1 + grp);
-        if (issuer) tma_store_2d(buf, &mapO, n0 + c, mt * TILE_ROWS + rbase);   // rows / columns beyond the tensor are clipped by TMA
+        if (issuer) tma_store_2d(buf, &mapO, n0 + c, ks * a.rows_pad + mt * TILE_ROWS + rbase);   // rows / columns beyond the tensor are clipped by TMA
       }
       tc_fence_before();
       __syncwarp();
@@ -643,6 +651,8 @@ static int g_num_sms = 0;
 static int g_pf_dist = 0;        // L2 prefetch distance (k-blocks) of the A operand; SGB200_TC_PREFETCH overrides, 0 = off
 static int g_pf_all = 0;         // SGB200_TC_PREFETCH_ALL=1: also for multi-tap layers (their A re-reads hit L2 anyway)
 static int g_pair_xf = 1;        // SGB200_TC_PAIR_XF=0: keep the fused layer-5 dgrad on the single-CTA kernel
+static int g_max_bn = TC_MAX_BN;  // SGB200_TC_BN: cap of the N-tile width (A/B switch)
+static int g_small_bn = 1;       // SGB200_TC_SMALL_BN=0: keep 256-column tiles for problems that do not fill the GPU
 static int g_deep_ring = 0;      // SGB200_TC_DEEP_RING=1: as many stages as fit when the B box is small (measured: no gain)
 static int g_issue_mode = 1;     // SGB200_TC_ISSUE: see TcArgs::issue_mode
 static int g_pair_bf16 = 2;      // SGB200_TC_PAIR_BF16: contractions on CTA pairs (cta_group::2): 1 bf16 long-K only, 2 all bf16 -> bf16, 3 / 4 see sg_conv_tc()
@@ -672,6 +682,8 @@ static int tc_init() {
   if (const char* e = getenv("SGB200_TC_PAIR_BF16")) g_pair_bf16 = atoi(e);
   if (const char* e = getenv("SGB200_TC_ISSUE")) g_issue_mode = atoi(e);
   if (const char* e = getenv("SGB200_TC_DEEP_RING")) g_deep_ring = atoi(e);
+  if (const char* e = getenv("SGB200_TC_SMALL_BN")) g_small_bn = atoi(e) != 0;
+  if (const char* e = getenv("SGB200_TC_BN")) { const int v = atoi(e); if (v >= 32 && v <= TC_MAX_BN && v % 32 == 0) g_max_bn = v; }
   if (const char* e = getenv("SGB200_TC_PAIR_XF")) g_pair_xf = atoi(e);
   if (const char* e = getenv("SGB200_TC_PREFETCH")) { g_pf_dist = atoi(e); if (g_pf_dist < 0 || g_pf_dist > 64) g_pf_dist = 0; }
   if (const char* e = getenv("SGB200_TC_PREFETCH_ALL")) g_pf_all = atoi(e) != 0;
@@ -694,8 +706,28 @@ static int make_map(CUtensorMap* m, const void* base, int bf16, uint64_t rows, u
   return SG_OK;
 }
 
+// split-K epilogue: out[r][c] = bias[c] + sum over slices s (in order) of part[s][r][c]; float4 per thread
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, int S, size_t slice_floats, int rows, int N, const float* __restrict__ bias,
+                                     float* __restrict__ out, int ldo) {
+  const int n4 = N >> 2;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)rows * n4) return;
+  const int r = (int)(i / n4), c = (int)(i - (size_t)r * n4) * 4;
+  float4 a = bias ? __ldg(reinterpret_cast<const float4*>(bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* p = part + (size_t)r * N + c;
+  for (int s = 0; s < S; ++s) {
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(p + (size_t)s * slice_floats));
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  }
+  *reinterpret_cast<float4*>(out + (size_t)r * ldo + c) = a;
+}
+
+static thread_local int g_tc_extra = 0;
+int sg_conv_tc_extra_launches() { return g_tc_extra; }
+
 // uses a.Wk, the K-major copy of the weights: [N][taps*cin]
 int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
+  g_tc_extra = 0;
   if (precision == SG_PREC_FP32) { sg_set_error("sg_conv_tc called in fp32 mode"); return SG_EINVAL; }
   const int kbe = a.op_bf16 ? 64 : 32;
   if (a.same_utt || a.tap_base != 0) { sg_set_error("sg_conv_tc: 'same' padding is only built for the FFMA path"); return SG_EUNSUPPORTED; }
@@ -706,9 +738,38 @@ int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
     sg_set_error("sg_conv_tc: cin %% 32, N %% 32, lda/ldo %% 4 required (cin=%d N=%d)", a.cin, a.N);
     return SG_EINVAL;
   }
-  int bn = TC_MAX_BN;
+  int bn = g_max_bn;
   while (bn > 32 && a.N % bn != 0) bn -= 32;     // largest N-tile (multiple of 32, <= 256) dividing N
+  // (Narrower tiles against wave quantisation - B = 128 x 300 frames is 300 pair tiles on 74 pairs = 4.05 -> 5 rounds - were
+  // measured and rejected: 128-column tiles run the 512-channel layers 55 % slower (A is re-read once more per output column
+  // and the tensor pipe waits on shared memory), 112.8 k vs 143.2 k utt-iter/s at B = 128.  SGB200_TC_BN caps the width for A/B runs.)
   if (a.N % bn != 0) { sg_set_error("sg_conv_tc: N=%d is not a multiple of 32", a.N); return SG_EINVAL; }
+  // Small problems (the head's fc1 / LDA contractions: B rows): with 256-column tiles only m_tiles x N/256 SMs work, and each
+  // pulls its whole A + B stream through one SM's L2 port (the B = 1024 fc1 forward ran 16 CTAs for 41 us).  Narrower tiles
+  // spread the same stream over more SMs; the tensor pipe is nowhere near busy in this regime.
+  // Split-K first: the head's fc1 forward (K = 3000: 94 k-blocks in sequence on 16 CTAs, each k-block a full L2 round trip
+  // behind a 4-deep ring) becomes 8 x fewer k-blocks per CTA on 8 x more CTAs; the fp32 partials are summed in slice order by
+  // splitk_reduce_kernel (deterministic), which also applies the bias.
+  int ksplit = 1;
+  const int nkb_all = a.taps * (a.cin / kbe);
+  // The slice count is a function of the contraction's K and N only, never of the row count: the summation order of an
+  // output element must not depend on the batch size, or a sharded run would differ from the unsharded one in the last bit
+  // (tests/test_gpu_shard.py).
+  if (g_small_bn && !a.xf_ab && a.splitk_ws && !a.out_bf16 && !a.bits_out && a.N % 4 == 0 && a.ldo % 4 == 0 && a.N <= 512 &&
+      (a.epilogue == SG_EPI_BIAS || a.epilogue == SG_EPI_NONE)) {
+    const int S = nkb_all >= 64 ? 8 : (nkb_all >= 16 ? 4 : 1);
+    const size_t need = (size_t)S * ((a.rows + TC_BM - 1) / TC_BM) * TC_BM * a.N;
+    if (S > 1 && (S - 1) * ((nkb_all + S - 1) / S) < nkb_all) {
+      if (need > a.splitk_floats) { sg_set_error("sg_conv_tc: split-K scratch too small (%zu floats needed, %zu given)", need, a.splitk_floats); return SG_EINVAL; }
+      ksplit = S;
+    }
+  }
+  if (g_small_bn && !a.xf_ab) {
+    const int mt = ((a.rows + TC_BM - 1) / TC_BM) * ksplit;
+    while (bn >= 128 && (bn / 2) % 32 == 0 && a.N % (bn / 2) == 0 && (!a.out_bf16 || (bn / 2) % 64 == 0) &&
+           2 * mt * (a.N / bn) <= g_num_sms)
+      bn /= 2;
+  }
   CUtensorMap mapA, mapB;
   r = make_map(&mapA, a.A, a.op_bf16, (uint64_t)a.rows, (uint64_t)a.cin, (uint64_t)a.lda, TC_BM);
   if (r != SG_OK) return r;
@@ -726,20 +787,25 @@ int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
   t.issue_mode = g_issue_mode;
   t.stb = TC_A_BYTES + bn * TC_BK * 4; t.nst = (TC_STAGES * TC_STAGE_BYTES) / t.stb;
   if (t.nst > TC_MAX_STAGES) t.nst = TC_MAX_STAGES;
-  if (!g_deep_ring && t.nst > TC_STAGES) t.nst = TC_STAGES;
+  // a problem that does not fill the GPU is latency-bound per CTA: use every stage that fits (a narrow B box leaves room for 8)
+  const bool small_problem = g_small_bn && t.m_tiles * t.n_tiles * ksplit < g_num_sms;
+  if (!g_deep_ring && !small_problem && t.nst > TC_STAGES) t.nst = TC_STAGES;
+  t.ksplit = ksplit; t.kb_per = (nkb_all + ksplit - 1) / ksplit; t.rows_pad = t.m_tiles * TC_BM;
+  if (ksplit > 1) { t.bias = nullptr; t.epilogue = SG_EPI_NONE; t.out = a.splitk_ws; t.ldo = a.N; }
   if (a.xf_ab && !(a.op_bf16 && a.out_bf16 && a.taps == 1 && a.T >= TC_BM && a.rows % a.T == 0 && a.xf_ld % 8 == 0 && a.cin <= a.xf_ld)) {
     sg_set_error("sg_conv_tc: the fused pooling adjoint needs bf16 operands/output, one tap, T >= 128 (T=%d taps=%d)", a.T, a.taps);
     return SG_EINVAL;
   }
   if ((a.epilogue == SG_EPI_BIAS || a.epilogue == SG_EPI_BIAS_RELU) && !a.bias) { sg_set_error("sg_conv_tc: bias epilogue without bias"); return SG_EINVAL; }
   CUtensorMap mapO;
-  r = make_map(&mapO, a.out, a.out_bf16, (uint64_t)a.rows, (uint64_t)a.N, (uint64_t)a.ldo, TC_BM);
+  if (ksplit > 1) r = make_map(&mapO, a.splitk_ws, 0, (uint64_t)ksplit * t.rows_pad, (uint64_t)a.N, (uint64_t)a.N, TC_BM);
+  else r = make_map(&mapO, a.out, a.out_bf16, (uint64_t)a.rows, (uint64_t)a.N, (uint64_t)a.ldo, TC_BM);
   if (r != SG_OK) return r;
   // bf16 CTA-pair variant (cta_group::2): mode 1 = contractions with >= 16 k-blocks, 2 = every eligible one
   // (modes 3 and 4 are not validated defaults: 3 adds the tf32-operand / bf16-output layer-1 forward (measured: no gain),
   //  4 adds fp32-output contractions - the tf32 mode and the i-vector UBM contraction: tests/test_gpu_tc.py and
   //  tests/test_gpu_iv.py pass with it, its throughput has not been measured yet)
-  if (g_pair_bf16 && (a.op_bf16 || g_pair_bf16 >= 3) && (a.out_bf16 || (g_pair_bf16 >= 4 && !a.op_bf16)) && (!a.xf_ab || g_pair_xf) && bn % 32 == 0 && bn >= 64 && a.rows > 256 &&
+  if (ksplit == 1 && g_pair_bf16 && (a.op_bf16 || g_pair_bf16 >= 3) && (a.out_bf16 || (g_pair_bf16 >= 4 && !a.op_bf16)) && (!a.xf_ab || g_pair_xf) && bn % 32 == 0 && bn >= 64 && a.rows > 256 &&
       (g_pair_bf16 >= 2 || a.taps * t.kchunks >= 16)) {
     CUtensorMap mapBh;
     r = make_map(&mapBh, a.Wk, a.op_bf16, (uint64_t)a.N, (uint64_t)a.taps * a.cin, (uint64_t)a.taps * a.cin, (uint32_t)(bn / 2));
@@ -763,7 +829,7 @@ int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
     else SG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<0, 0, 0, 1>, mapA, mapBh, mapO, t));
     return SG_OK;
   }
-  int grid = t.m_tiles * t.n_tiles;
+  int grid = t.m_tiles * t.n_tiles * ksplit;
   if (grid > g_num_sms) grid = g_num_sms;
   if (a.xf_ab) conv_tc_kernel<1, 1, 1><<<grid, TC_XF_THREADS, TC_SMEM_BYTES, st>>>(mapA, mapB, mapO, t);
   else if (a.op_bf16 && a.out_bf16) conv_tc_kernel<1, 1><<<grid, TC_MAIN_THREADS, TC_SMEM_BYTES, st>>>(mapA, mapB, mapO, t);
@@ -771,5 +837,12 @@ int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
   else if (a.out_bf16) conv_tc_kernel<0, 1><<<grid, TC_MAIN_THREADS, TC_SMEM_BYTES, st>>>(mapA, mapB, mapO, t);
   else conv_tc_kernel<0, 0><<<grid, TC_MAIN_THREADS, TC_SMEM_BYTES, st>>>(mapA, mapB, mapO, t);
   SG_LAUNCH_CHECK();
+  if (ksplit > 1) {
+    const size_t n = (size_t)a.rows * (a.N / 4);
+    splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a.splitk_ws, ksplit, (size_t)t.rows_pad * a.N, a.rows, a.N,
+                                                                    a.epilogue == SG_EPI_BIAS ? a.bias : nullptr, a.out, a.ldo);
+    SG_LAUNCH_CHECK();
+    g_tc_extra = 1;
+  }
   return SG_OK;
 }

@@ -7,6 +7,8 @@
 #include <cuda_bf16.h>
 #include <math.h>
 
+#include <stdlib.h>
+
 #include "sg_common.cuh"
 #include "sg_head.cuh"
 
@@ -296,6 +298,212 @@ head_bwd_kernel(SgHeadConst H, const float* __restrict__ dq, const float* __rest
 }
 
 // ---------------------------------------------------------------------------------------------
+// The same two stages with HEAD_U utterances per CTA and the L x L transform staged in shared memory.  One utterance per
+// CTA streams the 160 KB matrix (L = 200) from L2 once per utterance: 164 MB of L2 reads per launch at B = 1024 (33 us),
+// and at small B a chain of dependent L2 round trips (the head was 18 % of the B = 128 step).  Here the matrix is read once
+// per 8 utterances and every weight fetched from shared memory feeds 8 accumulators.  Per utterance the arithmetic and its
+// order are those of head_fwd_kernel / head_bwd_kernel (the fallbacks for L*L beyond the shared-memory budget): same bits.
+// ---------------------------------------------------------------------------------------------
+// U block sums with two barriers in total; per value the reduction tree is block_sum's (warp butterfly, then the eight warp
+// partials in order), so the results are bit-identical to U separate block_sum calls.  red: [U][8]
+template <int U>
+__device__ __forceinline__ void block_sum_multi(float (&v)[U], float* red) {
+#pragma unroll
+  for (int u = 0; u < U; ++u) v[u] = warp_sum(v[u]);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) red[u * 8 + (threadIdx.x >> 5)] = v[u];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    float a = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a += red[u * 8 + i];
+    v[u] = a;
+  }
+}
+
+// The matrix arrives by bulk asynchronous copies (cp.async.bulk, one thread issues, an mbarrier counts the bytes) while the
+// CTA computes the length norms; U = 8 utterances per CTA for large batches, 2 for small ones (more CTAs, shorter chains).
+__device__ __forceinline__ void head_stage_matrix(float* Ts, const float* __restrict__ src, int nfloat, uint64_t* bar) {
+  const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(bar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t bytes = (uint32_t)nfloat * 4u;                     // multiple of 16 (checked by the host)
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+    for (uint32_t off = 0; off < bytes; off += 32768u) {
+      const uint32_t n = min(32768u, bytes - off);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"((uint32_t)__cvta_generic_to_shared(Ts) + off), "l"(reinterpret_cast<const char*>(src) + off), "r"(n), "r"(bar_a) : "memory");
+    }
+  }
+}
+__device__ __forceinline__ void head_wait_matrix(uint64_t* bar) {
+  const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(bar);
+  uint32_t done = 0;
+  while (!done)
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar_a) : "memory");
+}
+
+template <int U>
+__global__ void __launch_bounds__(256)
+head_fwd_multi_kernel(SgHeadConst H, const float* __restrict__ e2, int B, float* __restrict__ tsave,
+                      float* __restrict__ scal, float* __restrict__ emb) {
+  extern __shared__ __align__(16) float sm[];
+  __shared__ __align__(8) uint64_t mbar;
+  const int L = H.L, Lp = H.Lp, tid = threadIdx.x;
+  float* Ts = sm;                              // [L][L]  plda_Tt: row j, column i
+  float* v = Ts + (size_t)L * L;               // [U][Lp]
+  float* red = v + U * Lp;                     // [U][8]
+  const int b0 = blockIdx.x * U, nu = min(U, B - b0);
+  head_stage_matrix(Ts, H.plda_Tt, L * L, &mbar);
+  float ratio[U], norm[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {                                      // all loads in flight together, one multi-value reduction
+    float x = 0.f;
+    if (u < nu)
+      for (int j = tid; j < L; j += 256) { float e = e2[(size_t)(b0 + u) * Lp + j]; x = fmaf(e, e, x); }
+    norm[u] = x;
+  }
+  block_sum_multi<U>(norm, red);
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    ratio[u] = 0.f;
+    if (u < nu) {                                                    // CTA-uniform
+      norm[u] = sqrtf(norm[u]);
+      ratio[u] = sqrtf((float)L) / norm[u];                          // xvector_extract.py:31-38
+      for (int j = tid; j < Lp; j += 256) v[u * Lp + j] = j < L ? e2[(size_t)(b0 + u) * Lp + j] * ratio[u] - H.plda_mean[j] : 0.f;
+    } else {
+      for (int j = tid; j < Lp; j += 256) v[u * Lp + j] = 0.f;
+    }
+  }
+  __syncthreads();                                                   // v[] complete (and the mbarrier initialised long ago)
+  head_wait_matrix(&mbar);
+  float tloc[2][U];                                                  // L <= 512
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int i = tid + 256 * h;
+#pragma unroll
+    for (int u = 0; u < U; ++u) tloc[h][u] = 0.f;
+    if (i < L) {
+      int j = 0;
+      for (; j + 4 <= L; j += 4) {                                   // plda.py:75; per utterance: the same j order as head_fwd_kernel
+        const float w0 = Ts[(size_t)j * L + i], w1 = Ts[(size_t)(j + 1) * L + i], w2 = Ts[(size_t)(j + 2) * L + i], w3 = Ts[(size_t)(j + 3) * L + i];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const float4 x = *reinterpret_cast<const float4*>(v + u * Lp + j);   // broadcast read
+          float a = tloc[h][u];
+          a = fmaf(w0, x.x, a); a = fmaf(w1, x.y, a); a = fmaf(w2, x.z, a); a = fmaf(w3, x.w, a);
+          tloc[h][u] = a;
+        }
+      }
+      for (; j < L; ++j) {
+        const float w = Ts[(size_t)j * L + i];
+#pragma unroll
+        for (int u = 0; u < U; ++u) tloc[h][u] = fmaf(w, v[u * Lp + j], tloc[h][u]);
+      }
+    }
+  }
+  float ssum[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    float s = 0.f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i = tid + 256 * h;
+      if (i < L) s = fmaf(tloc[h][u] * tloc[h][u], H.inv_psi1[i], s);
+    }
+    ssum[u] = s;
+  }
+  block_sum_multi<U>(ssum, red);
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (u < nu) {
+      const int b = b0 + u;
+      const float s = ssum[u];
+      const float factor = sqrtf((float)L / s);                      // plda.py:92-97
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = tid + 256 * h;
+        if (i < L) {
+          tsave[(size_t)b * Lp + i] = tloc[h][u];
+          emb[(size_t)b * L + i] = tloc[h][u] * factor;
+        }
+      }
+      if (tid == 0) { scal[b * 4 + 0] = ratio[u]; scal[b * 4 + 1] = factor; scal[b * 4 + 2] = s; scal[b * 4 + 3] = norm[u]; }
+    }
+  }
+}
+
+template <int U>
+__global__ void __launch_bounds__(256)
+head_bwd_multi_kernel(SgHeadConst H, const float* __restrict__ dq, int B, const float* __restrict__ tsave,
+                      const float* __restrict__ scal, float* __restrict__ de2) {
+  extern __shared__ __align__(16) float sm[];
+  __shared__ __align__(8) uint64_t mbar;
+  const int L = H.L, Lp = H.Lp, tid = threadIdx.x;
+  float* Ts = sm;                              // [L][L]  plda_T: row i, column j
+  float* dt = Ts + (size_t)L * L;              // [U][Lp]
+  float* red = dt + U * Lp;                    // [U][8]
+  const int b0 = blockIdx.x * U, nu = min(U, B - b0);
+  head_stage_matrix(Ts, H.plda_T, L * L, &mbar);
+  float ratio[U], dots[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    float dot = 0.f;
+    if (u < nu)
+      for (int i = tid; i < L; i += 256) dot = fmaf(dq[(size_t)(b0 + u) * L + i], tsave[(size_t)(b0 + u) * Lp + i], dot);
+    dots[u] = dot;
+  }
+  block_sum_multi<U>(dots, red);
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    ratio[u] = 0.f;
+    if (u < nu) {
+      const int b = b0 + u;
+      ratio[u] = scal[b * 4 + 0];
+      const float factor = scal[b * 4 + 1], s = scal[b * 4 + 2];
+      const float k = factor / s * dots[u];
+      for (int i = tid; i < Lp; i += 256)
+        dt[u * Lp + i] = i < L ? factor * dq[(size_t)b * L + i] - k * H.inv_psi1[i] * tsave[(size_t)b * Lp + i] : 0.f;
+    } else {
+      for (int i = tid; i < Lp; i += 256) dt[u * Lp + i] = 0.f;
+    }
+  }
+  __syncthreads();
+  head_wait_matrix(&mbar);
+  for (int j = tid; j < Lp; j += 256) {
+    float a[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) a[u] = 0.f;
+    if (j < L) {
+      int i = 0;
+      for (; i + 4 <= L; i += 4) {
+        const float w0 = Ts[(size_t)i * L + j], w1 = Ts[(size_t)(i + 1) * L + j], w2 = Ts[(size_t)(i + 2) * L + j], w3 = Ts[(size_t)(i + 3) * L + j];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const float4 x = *reinterpret_cast<const float4*>(dt + u * Lp + i);
+          float c = a[u];
+          c = fmaf(w0, x.x, c); c = fmaf(w1, x.y, c); c = fmaf(w2, x.z, c); c = fmaf(w3, x.w, c);
+          a[u] = c;
+        }
+      }
+      for (; i < L; ++i) {
+        const float w = Ts[(size_t)i * L + j];
+#pragma unroll
+        for (int u = 0; u < U; ++u) a[u] = fmaf(w, dt[u * Lp + i], a[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (u < nu) de2[(size_t)(b0 + u) * Lp + j] = a[u] * ratio[u];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // PLDA log-likelihood-ratio scoring + decision (plda.py:140-190, defended_model.py:167-170)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -496,13 +704,36 @@ int sg_tap_gather_launch(const float* G, int ldg, float* out, int ldo, size_t ro
   SG_LAUNCH_CHECK();
   return SG_OK;
 }
+static size_t head_multi_smem(const SgHeadConst& H, int U) { return ((size_t)H.L * H.L + (size_t)U * H.Lp + 8 * U) * sizeof(float); }
+static bool head_multi_ok(const SgHeadConst& H) {
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("SGB200_HEAD_MULTI"); enabled = e ? (atoi(e) != 0) : 1; }
+  if (!enabled || head_multi_smem(H, 8) > 200 * 1024 || (H.L * H.L) % 4 != 0 || H.Lp % 4 != 0) return false;
+  static std::atomic<unsigned long long> configured{0};
+  if (sg_first_on_device(&configured)) {
+    if (cudaFuncSetAttribute(head_fwd_multi_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(head_bwd_multi_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(head_fwd_multi_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(head_bwd_multi_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+  }
+  return true;
+}
 int sg_head_fwd_launch(const SgHeadConst& H, const float* e2, int B, float* tsave, float* scal, float* emb, cudaStream_t st) {
-  head_fwd_kernel<<<B, 256, (H.Lp + 8) * sizeof(float), st>>>(H, e2, tsave, scal, emb);
+  if (head_multi_ok(H)) {
+    if (B >= 512) head_fwd_multi_kernel<8><<<(B + 7) / 8, 256, head_multi_smem(H, 8), st>>>(H, e2, B, tsave, scal, emb);
+    else head_fwd_multi_kernel<2><<<(B + 1) / 2, 256, head_multi_smem(H, 2), st>>>(H, e2, B, tsave, scal, emb);
+  } else head_fwd_kernel<<<B, 256, (H.Lp + 8) * sizeof(float), st>>>(H, e2, tsave, scal, emb);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }
 int sg_head_bwd_launch(const SgHeadConst& H, const float* dq, int B, const float* tsave, const float* scal, float* de2, cudaStream_t st) {
-  head_bwd_kernel<<<B, 256, (H.Lp + 8) * sizeof(float), st>>>(H, dq, tsave, scal, de2);
+  if (head_multi_ok(H)) {
+    if (B >= 512) head_bwd_multi_kernel<8><<<(B + 7) / 8, 256, head_multi_smem(H, 8), st>>>(H, dq, B, tsave, scal, de2);
+    else head_bwd_multi_kernel<2><<<(B + 1) / 2, 256, head_multi_smem(H, 2), st>>>(H, dq, B, tsave, scal, de2);
+  } else head_bwd_kernel<<<B, 256, (H.Lp + 8) * sizeof(float), st>>>(H, dq, tsave, scal, de2);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }

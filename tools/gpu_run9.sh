@@ -1,0 +1,12 @@
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q --no-header -p no:cacheprovider > gpurun_out/r2i_pytest.log 2>&1
+grep -E "passed|failed" gpurun_out/r2i_pytest.log | tail -3; grep -E "^(FAILED|E  )" gpurun_out/r2i_pytest.log | head -20
+b() { tag=$1; shift; env "$@" > gpurun_out/r2i_bench_$tag.json 2>> gpurun_out/r2i_bench.err; python -c "
+import json; d=json.load(open('gpurun_out/r2i_bench_$tag.json')); print('$tag', round(d['value']), round(d['e2e']['value'] or 0), d['gpu_launches'], d['kernel_ms_per_step'])"; }
+b b1024 timeout 300 python bench.py --steps 4 --warmup 3 --no-ladder --no-cpu-baseline --e2e-steps 0 --no-peak
+b b128 timeout 300 python bench.py --steps 5 --warmup 3 --no-ladder --no-cpu-baseline --batch 128 --e2e-steps 0 --no-peak
+b b128_nowave SGB200_TC_WAVE_BN=0 timeout 300 python bench.py --steps 5 --warmup 3 --no-ladder --no-cpu-baseline --batch 128 --e2e-steps 0 --no-peak
+b b128_bn128 SGB200_TC_BN=128 timeout 300 python bench.py --steps 5 --warmup 3 --no-ladder --no-cpu-baseline --batch 128 --e2e-steps 0 --no-peak
+b b1024_bn128 SGB200_TC_BN=128 timeout 300 python bench.py --steps 3 --warmup 3 --no-ladder --no-cpu-baseline --e2e-steps 0 --no-peak
+tail -3 gpurun_out/r2i_bench.err
