@@ -80,6 +80,11 @@ int sg_get_precision(const sg_handle* h);
  * kernels once those issue all their loads up front (10.8 -> 4.6 ms per step); a thread-block-cluster variant with a DSMEM
  * exchange was slower still (+19 ms: every CTA waits for its cluster at the barrier).  Kept as an option, off by default. */
 #define SG_OPT_CMVN_FUSION 6
+/* SG_OPT_ROW_COMPACTION (default 1, tensor-core precisions): layer 3 of the TDNN stores only the frames that are still valid
+ * after its dilated taps (T - 30: 270 of 300 at 3 s), so the two 1 x 1 layers, the statistics pooling and their adjoints
+ * contract 10 % fewer rows; layer 4's adjoint spreads its result back into layer 3's row space.  Values are unchanged (the
+ * dropped frames were masked before). */
+#define SG_OPT_ROW_COMPACTION 7
 int sg_set_option(sg_handle* h, int option, int value);
 
 /* ---- x-vector / PLDA system: weights ---------------------------------------------------------

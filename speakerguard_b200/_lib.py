@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libsgb200.so")
 SG_OK, SG_EINVAL, SG_ECUDA, SG_ESTATE, SG_EUNSUPPORTED = 0, -1, -2, -3, -4
 PREC_FP32, PREC_TF32, PREC_BF16 = 0, 1, 2
 DITHER_OFF, DITHER_TENSOR, DITHER_PHILOX = 0, 1, 2
-OPT_POOL_FUSION, OPT_FEAT_STASH, OPT_L1_TAP_FORM, OPT_UTT_OFFSET, OPT_CUDA_GRAPH, OPT_CMVN_FUSION = 1, 2, 3, 4, 5, 6
+OPT_POOL_FUSION, OPT_FEAT_STASH, OPT_L1_TAP_FORM, OPT_UTT_OFFSET, OPT_CUDA_GRAPH, OPT_CMVN_FUSION, OPT_ROW_COMPACTION = 1, 2, 3, 4, 5, 6, 7
 LOSS_CE, LOSS_MARGIN = 0, 1
 PROF_COUNT = 15
 IV_STAGE_POST, IV_STAGE_STATS, IV_STAGE_IVECTOR = 0, 1, 2

@@ -70,6 +70,7 @@ extern "C" int sg_create(sg_handle** out, int device) {
   if (const char* e = getenv("SGB200_L1_TAP_FORM")) h->l1_tap_form = atoi(e) != 0;
   if (const char* e = getenv("SGB200_CUDA_GRAPH")) h->use_graph = atoi(e) != 0;
   if (const char* e = getenv("SGB200_CMVN_FUSION")) h->cmvn_fusion = atoi(e) != 0;
+  if (const char* e = getenv("SGB200_ROW_COMPACTION")) h->row_compaction = atoi(e) != 0;
   SgFeatTables* host = new SgFeatTables();
   int r = sg_feat_tables_build(host);
   if (r != SG_OK) { delete host; delete h; sg_set_error("sg_create: feature table construction failed"); return r; }
@@ -112,6 +113,7 @@ extern "C" int sg_set_option(sg_handle* h, int option, int value) {
   if (option == SG_OPT_L1_TAP_FORM) { h->l1_tap_form = value != 0; return SG_OK; }
   if (option == SG_OPT_CUDA_GRAPH) { h->use_graph = value != 0; return SG_OK; }
   if (option == SG_OPT_CMVN_FUSION) { h->cmvn_fusion = value != 0; return SG_OK; }
+  if (option == SG_OPT_ROW_COMPACTION) { h->row_compaction = value != 0; return SG_OK; }
   if (option == SG_OPT_UTT_OFFSET) {
     if (value < 0) { sg_set_error("SG_OPT_UTT_OFFSET must be >= 0"); return SG_EINVAL; }
     h->utt_offset = value; return SG_OK;
@@ -447,11 +449,23 @@ static void tdnn_valid(int T, int tv[5]) {
   for (int l = 0; l < 5; ++l) { t -= (kTaps[l] - 1) * kDil[l]; tv[l] = t; }
 }
 
+// frames per utterance kept from layer 3's output on (0: no compaction).  Needs the tensor-core path (3-D TMA stores) and
+// >= 128 rows per utterance on both sides, so that a 128-row box touches at most two utterances.
+static int xv_compact_T(const sg_handle* h, int T) {
+  if (h->precision == SG_PREC_FP32 || !h->row_compaction) return 0;
+  const int tc = T - (kTaps[0] - 1) * kDil[0] - (kTaps[1] - 1) * kDil[1] - (kTaps[2] - 1) * kDil[2];
+  return (tc >= 128 && tc < T) ? tc : 0;
+}
+
 static int embed_fwd(sg_handle* h, const float* feat, int B, int T, const XvWs& w, float* emb, cudaStream_t st) {
   int tv[5];
   tdnn_valid(T, tv);
   if (tv[4] < 2) { sg_set_error("need at least 32 frames for the TDNN + unbiased std (T=%d)", T); return SG_EINVAL; }
   const int R = B * T;
+  // Row compaction (tensor-core modes): layers 4 and 5 are 1 x 1, so from layer 3's output on only the tv[2] valid frames of
+  // every utterance need to exist.  Layer 3's epilogue stores them as [B][Tc] rows, and layers 4, 5, the pooling and their
+  // adjoints run on B * Tc instead of B * T rows (270 / 300 at 3 s).
+  const int Tc = xv_compact_T(h, T);
   const float* in = feat;
   int lda = SG_FLD;
   for (int l = 0; l < 5; ++l) {
@@ -460,6 +474,8 @@ static int embed_fwd(sg_handle* h, const float* feat, int B, int T, const XvWs& 
     a.A = in; a.lda = lda; a.W = h->Wf[l]; a.Wk = h->Wfk[l]; a.bias = h->bias[l]; a.out = w.r[l]; a.ldo = kCoutP[l];
     a.rows = R; a.N = kCoutP[l]; a.cin = kCinP[l]; a.taps = kTaps[l]; a.tap_step = kDil[l];
     a.epilogue = SG_EPI_BIAS_RELU; a.T = T; a.t_valid = tv[l];
+    if (Tc && l == 2) { a.out_T = Tc; a.out_Tstride = Tc; a.bits_T = Tc; }
+    if (Tc && l >= 3) { a.rows = B * Tc; a.T = Tc; }
     if (l < 4 && h->precision != SG_PREC_FP32) { a.bits_out = w.bits[l]; a.ldbits = SG_C1 / 32; }
     if (h->precision == SG_PREC_BF16) {                  // bf16 activations; layer 1 still reads the fp32 features
       a.out_bf16 = 1;
@@ -470,7 +486,7 @@ static int embed_fwd(sg_handle* h, const float* feat, int B, int T, const XvWs& 
     in = w.r[l]; lda = kCoutP[l];
   }
   h->launches += 1;
-  PROF(h, SG_PROF_POOL, st, sg_pool_fwd_launch(w.r[4], h->precision == SG_PREC_BF16, B, T, tv[4], h->bn5_mean, h->bn5_istd, w.stats, w.save_mean, w.save_std, st));
+  PROF(h, SG_PROF_POOL, st, sg_pool_fwd_launch(w.r[4], h->precision == SG_PREC_BF16, B, Tc ? Tc : T, tv[4], h->bn5_mean, h->bn5_istd, w.stats, w.save_mean, w.save_std, st));
   {
     SgConvArgs a;
     memset(&a, 0, sizeof(a));
@@ -504,10 +520,11 @@ static int embed_bwd(sg_handle* h, const float* demb, int B, int T, const XvWs& 
     SG_TRY(sg_run_conv(h, a, true, SG_PROF_HEAD_GEMM, st));
   }
   // bf16 mode: the pooling adjoint is applied to the staged r5 tiles inside the layer-5 dgrad (no dA5 round trip through HBM)
+  const int Tc = xv_compact_T(h, T);
   const bool fuse_pool = h->precision == SG_PREC_BF16 && h->pool_fusion && T >= 128;
   h->launches += 1;
   if (fuse_pool) PROF(h, SG_PROF_POOL, st, sg_pool_bwd_params_launch(B, tv[4], h->bn5_istd, w.dstats, w.save_mean, w.save_std, w.ab, st));
-  else PROF(h, SG_PROF_POOL, st, sg_pool_bwd_launch(w.r[4], h->precision == SG_PREC_BF16, B, T, tv[4], h->bn5_istd, w.dstats, w.save_mean, w.save_std, w.G0, st));
+  else PROF(h, SG_PROF_POOL, st, sg_pool_bwd_launch(w.r[4], h->precision == SG_PREC_BF16, B, Tc ? Tc : T, tv[4], h->bn5_istd, w.dstats, w.save_mean, w.save_std, w.G0, st));
   // dgrad chain: dA_l (pre-ReLU grad of layer l) -> dA_{l-1}
   const float* gin = w.G0;
   float* bufs[2] = {w.G1, w.G2};
@@ -516,6 +533,7 @@ static int embed_bwd(sg_handle* h, const float* demb, int B, int T, const XvWs& 
     memset(&a, 0, sizeof(a));
     a.A = gin; a.lda = kCoutP[l]; a.W = h->Wb[l]; a.Wk = h->Wbk[l]; a.rows = R; a.cin = kCoutP[l]; a.taps = kTaps[l];
     a.tap_step = -kDil[l]; a.T = T;
+    if (Tc && l >= 3) { a.rows = B * Tc; a.T = Tc; }                // compact rows: the adjoints of the 1 x 1 layers
     if (h->precision == SG_PREC_BF16) { a.op_bf16 = 1; a.out_bf16 = l > 0; a.Wk = (const float*)h->Wbk_h[l]; }
     if (l == 4 && fuse_pool) { a.A = w.r[4]; a.xf_ab = w.ab; a.xf_ld = SG_C5P; a.xf_tv = tv[4]; }
     h->prof.next_tag = l + 1;
@@ -524,6 +542,13 @@ static int embed_bwd(sg_handle* h, const float* demb, int B, int T, const XvWs& 
       a.out = out; a.ldo = kCinP[l]; a.N = kCinP[l];
       a.epilogue = SG_EPI_MASK; a.mask = w.r[l - 1]; a.ldmask = kCoutP[l - 1]; a.t_valid = tv[l - 1];
       if (h->precision != SG_PREC_FP32) { a.bits_in = w.bits[l - 1]; a.ldbits = SG_C1 / 32; }
+      if (Tc && l == 3) {
+        // layer 4's adjoint hands dA3 back in layer 3's row space ([B][T] rows): its epilogue spreads the compact rows out
+        // again, and the T - Tc tail rows of every utterance, which layer 3's adjoint reads as taps, are cleared first
+        const size_t es = a.out_bf16 ? 2 : 4, rowb = (size_t)kCinP[l] * es;
+        SG_CUDA_CHECK(cudaMemset2DAsync((char*)out + (size_t)Tc * rowb, (size_t)T * rowb, 0, (size_t)(T - Tc) * rowb, (size_t)B, st));
+        a.out_T = Tc; a.out_Tstride = T;
+      }
       SG_TRY(sg_run_conv(h, a, true, (l == 4 && fuse_pool) ? SG_PROF_TDNN_BWD_POOL : SG_PROF_TDNN_BWD, st));
       gin = out;
     } else if (h->precision == SG_PREC_BF16 && h->l1_tap_form) {
@@ -773,7 +798,7 @@ extern "C" int sg_pgd_run(sg_handle* h, float* x_adv, const float* x0, const int
     memcpy(&key[7], &p->loss, sizeof(sg_loss_params));
     memcpy(&key[10], &p->decision_threshold, sizeof(float));
     key[11] = (unsigned long long)(grad_sign > 0.f) | ((unsigned long long)h->precision << 1) | ((unsigned long long)h->pool_fusion << 3) |
-              ((unsigned long long)h->feat_stash << 4) | ((unsigned long long)h->l1_tap_form << 5) | ((unsigned long long)h->cmvn_fusion << 6) |
+              ((unsigned long long)h->feat_stash << 4) | ((unsigned long long)h->l1_tap_form << 5) | ((unsigned long long)h->cmvn_fusion << 6) | ((unsigned long long)h->row_compaction << 7) |
               ((unsigned long long)(uint32_t)h->utt_offset << 8);
     if (!h->pgd_graph.valid || memcmp(h->pgd_graph.key, key, sizeof(key)) != 0) {
       if (pgd_capture(h, B, N, m, p, grad_sign, w, key, st) != SG_OK) h->use_graph = 0;    // capture unavailable: launch-by-launch from now on

@@ -103,6 +103,11 @@ struct SgConvArgs {
   // tensor-core path, bf16 only: fuse the statistics-pooling adjoint into this (layer-5 dgrad) contraction.  A is then the
   // stored activation r5 and xf_ab [rows / T][xf_ld] holds (alpha', beta) pairs: dA5 = (t < xf_tv && r > 0) ? alpha' + beta r : 0
   const float* xf_ab; int xf_ld; int xf_tv;
+  // tensor-core path: re-strided output.  The rows are frames of utterances with T rows each; with out_T > 0 the output is
+  // [rows / T][out_T frames][N] with out_Tstride rows per utterance in memory: out_T < T drops the frames >= out_T of every
+  // utterance (compaction to the valid frames), out_T == T with a larger out_Tstride spreads a compact tensor out again.
+  // bits_T > 0: the ReLU-bit rows written by the forward epilogue use the same compact indexing (frame < bits_T kept).
+  int out_T, out_Tstride, bits_T;
   // tensor-core path, small problems: scratch for split-K partials (fp32, splitk_floats elements); null = no split
   float* splitk_ws; size_t splitk_floats;
   // batched GEMM (SIMT path only): blockIdx.z selects an item; element strides, 0 = shared operand

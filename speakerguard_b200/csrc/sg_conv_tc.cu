@@ -72,6 +72,13 @@ __device__ __forceinline__ void tma_store_2d(const void* smem_src, const CUtenso
                ::"l"((uint64_t)map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+// 3-D store: elements whose coordinates fall beyond the tensor's extents are not written.  (Only the UPPER bound clips: a
+// store with a negative coordinate raises an illegal-instruction fault on sm_100, unlike a load, which zero-fills.)
+__device__ __forceinline__ void tma_store_3d(const void* smem_src, const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"((uint64_t)map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
 __device__ __forceinline__ void epi_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -157,6 +164,11 @@ struct TcArgs {
   // split-K (small problems): tile index = (m-tile, n-tile, k-slice); slice ks contracts k-blocks [ks * kb_per, (ks+1) * kb_per)
   // and stores its fp32 partial at row offset ks * rows_pad of the partial buffer (the output map then covers that buffer)
   int ksplit, kb_per, rows_pad;
+  // re-strided output: the tile rows are frames of utterances with a.T rows each; the output tensor is [utterance][st_T frames]
+  // (st_T <= a.T when compacting to the valid frames, or a.T when expanding a compact tensor into a wider row stride) and a
+  // staged box is stored once per utterance it touches (3-D map, out-of-range frames clipped).  bits_T: row stride of the
+  // ReLU-bit words written by the forward epilogue (0: a.T)
+  int st_dual, bits_T, st_nutt, st_stride;
 };
 
 // ---- cluster / cta_group::2 helpers ------------------------------------------------------------
@@ -218,7 +230,7 @@ __device__ __forceinline__ void xf8(uint4& w, const uint4 (&P)[2], uint32_t okm)
 template <int KIND_BF16, int OUT_BF16, int XFORM = 0, int PAIR = 0>
 __global__ void __launch_bounds__(XFORM ? TC_XF_THREADS : TC_MAIN_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-               const __grid_constant__ CUtensorMap mapO, TcArgs a) {
+               const __grid_constant__ CUtensorMap mapO, const __grid_constant__ CUtensorMap mapO2, TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   // PAIR: a CTA pair (cluster of 2 on one TPC) computes a 256 x BN tile with tcgen05.mma.cta_group::2.  Each CTA stages
@@ -231,8 +243,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   // for a 256-row B box, 6 for a pair's 128 rows (SGB200_TC_DEEP_RING=1 allows up to 12 for small boxes: no gain measured).
   const int NST = a.nst;
   const uint32_t STB = (uint32_t)a.stb;
-  uint8_t* stg = smem + TC_STAGES * TC_STAGE_BYTES;                  // 2 x 16 KB, 1024-byte aligned
-  uint64_t* bars = (uint64_t*)(stg + 2 * TC_STG_BYTES);
+  // layout: [2 epilogue staging boxes][pipeline ring][barriers, bias].  The staging boxes come first so that the shifted
+  // source window of a re-strided store (st_dual, below) stays inside the CTA's shared memory.
+  uint8_t* stg = smem;                                                 // 2 x 16 KB, 1024-byte aligned
+  smem += 2 * TC_STG_BYTES;                                            // from here on `smem` is the ring
+  uint64_t* bars = (uint64_t*)(smem + TC_STAGES * TC_STAGE_BYTES);
   uint64_t* full = bars;                                // [TC_MAX_STAGES]   (PAIR: rank 0's copy is the live one)
   uint64_t* empty = bars + TC_MAX_STAGES;               // [TC_MAX_STAGES]   per CTA
   uint64_t* tfull = bars + 2 * TC_MAX_STAGES;           // [2]     per CTA
@@ -538,7 +553,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               uint32_t ob = 0;
 #pragma unroll
               for (int j = 31; j >= 0; --j) ob = __funnelshift_l(__float_as_uint(0.f - v[j]), ob, 1);
-              a.bits_out[(size_t)row * a.ldbits + (col >> 5)] = ob;
+              if (a.bits_T == 0) {
+                a.bits_out[(size_t)row * a.ldbits + (col >> 5)] = ob;
+              } else {                                              // compacted output: the bit rows follow it
+                const int ub = row / a.T, ut = row - ub * a.T;
+                if (ut < a.bits_T) a.bits_out[((size_t)ub * a.bits_T + ut) * a.ldbits + (col >> 5)] = ob;
+              }
             }
           }
         } else if (a.epilogue == SG_EPI_MASK) {
@@ -615,7 +635,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int j = 0; j < 8; ++j) srow[j ^ (r_in & 7)] = packed[j];
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         epi_bar(1 + grp);
-        if (issuer) tma_store_2d(buf, &mapO, n0 + c, ks * a.rows_pad + mt * TILE_ROWS + rbase);   // rows / columns beyond the tensor are clipped by TMA
+        if (issuer) {
+          if (!a.st_dual) {
+            tma_store_2d(buf, &mapO, n0 + c, ks * a.rows_pad + mt * TILE_ROWS + rbase);   // rows / columns beyond the tensor are clipped by TMA
+          } else {
+            const int R0 = mt * TILE_ROWS + rbase, ub = R0 / a.T, ut = R0 - ub * a.T;      // first row of the box: utterance, frame
+            tma_store_3d(buf, &mapO, n0 + c, ut, ub);                                       // frames >= the map's extent are dropped
+            // The box's rows [k, 128) belong to the next utterance (frames 0 ...).  They are stored through the "sliding" map
+            // (element (c, i, s) = row s + i, i < 128): source window shifted down by k rows - the 128-byte swizzle is a function
+            // of the shared-memory address, so a row-shifted window reads what was staged - and i-coordinate k, so that the
+            // window's rows beyond the box (i >= 128) are clipped.
+            const int k = a.T - ut;
+            if (k < TC_BM && ub + 1 < a.st_nutt) tma_store_3d(buf + k * 128, &mapO2, n0 + c, k, (ub + 1) * a.st_stride - k);
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -703,6 +736,35 @@ static int make_map(CUtensorMap* m, const void* base, int bf16, uint64_t rows, u
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { sg_set_error("cuTensorMapEncodeTiled failed (%d): rows=%llu cols=%llu ld=%llu box=%u", (int)r,
                                         (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows); return SG_ECUDA; }
+  return SG_OK;
+}
+
+// sliding view of a [rows][cols] tensor: element (c, i, s) = row s + i for i < 128 (overlapping strides), box = 128 x 128 bytes
+static int make_map_slide(CUtensorMap* m, const void* base, int bf16, uint64_t rows, uint64_t cols, uint64_t ld) {
+  const uint64_t es = bf16 ? 2 : 4;
+  cuuint64_t dims[3] = {cols, TC_BM, rows};
+  cuuint64_t strides[2] = {ld * es, ld * es};
+  cuuint32_t box[3] = {(cuuint32_t)(bf16 ? 64 : 32), TC_BM, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { sg_set_error("cuTensorMapEncodeTiled (sliding) failed (%d): rows=%llu cols=%llu", (int)r, (unsigned long long)rows, (unsigned long long)cols); return SG_ECUDA; }
+  return SG_OK;
+}
+
+// [utterance][frames][cols] output with `frames` <= `tstride` rows per utterance in memory; box = 128 frames x 128 bytes
+static int make_map3(CUtensorMap* m, const void* base, int bf16, uint64_t nutt, uint64_t frames, uint64_t tstride, uint64_t cols, uint64_t ld) {
+  const uint64_t es = bf16 ? 2 : 4;
+  cuuint64_t dims[3] = {cols, frames, nutt};
+  cuuint64_t strides[2] = {ld * es, tstride * ld * es};
+  cuuint32_t box[3] = {(cuuint32_t)(bf16 ? 64 : 32), TC_BM, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { sg_set_error("cuTensorMapEncodeTiled (3-D) failed (%d): utt=%llu frames=%llu stride=%llu cols=%llu", (int)r,
+                                        (unsigned long long)nutt, (unsigned long long)frames, (unsigned long long)tstride, (unsigned long long)cols); return SG_ECUDA; }
   return SG_OK;
 }
 
@@ -797,7 +859,19 @@ int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
     return SG_EINVAL;
   }
   if ((a.epilogue == SG_EPI_BIAS || a.epilogue == SG_EPI_BIAS_RELU) && !a.bias) { sg_set_error("sg_conv_tc: bias epilogue without bias"); return SG_EINVAL; }
-  CUtensorMap mapO;
+  CUtensorMap mapO, mapO2;
+  memset(&mapO2, 0, sizeof(mapO2));
+  t.st_dual = 0; t.bits_T = a.bits_T; t.st_nutt = 0; t.st_stride = 0;
+  if (a.out_T > 0) {
+    if (ksplit > 1 || a.T < TC_BM || a.rows % a.T != 0 || a.out_T > a.out_Tstride || a.out_T > a.T) {
+      sg_set_error("sg_conv_tc: re-strided output needs T >= 128 rows per utterance and rows %% T == 0 (T=%d rows=%d)", a.T, a.rows);
+      return SG_EINVAL;
+    }
+    t.st_dual = 1; t.st_nutt = a.rows / a.T; t.st_stride = a.out_Tstride;
+    r = make_map_slide(&mapO2, a.out, a.out_bf16, (uint64_t)(a.rows / a.T) * a.out_Tstride, (uint64_t)a.N, (uint64_t)a.ldo);
+    if (r != SG_OK) return r;
+    r = make_map3(&mapO, a.out, a.out_bf16, (uint64_t)(a.rows / a.T), (uint64_t)a.out_T, (uint64_t)a.out_Tstride, (uint64_t)a.N, (uint64_t)a.ldo);
+  } else
   if (ksplit > 1) r = make_map(&mapO, a.splitk_ws, 0, (uint64_t)ksplit * t.rows_pad, (uint64_t)a.N, (uint64_t)a.N, TC_BM);
   else r = make_map(&mapO, a.out, a.out_bf16, (uint64_t)a.rows, (uint64_t)a.N, (uint64_t)a.ldo, TC_BM);
   if (r != SG_OK) return r;
@@ -823,19 +897,19 @@ int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
     attr.id = cudaLaunchAttributeClusterDimension;
     attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr; cfg.numAttrs = 1;
-    if (a.xf_ab) { cfg.blockDim = dim3(TC_XF_THREADS); SG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, 1, 1, 1>, mapA, mapBh, mapO, t)); }
-    else if (a.op_bf16) SG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, 1, 0, 1>, mapA, mapBh, mapO, t));
-    else if (a.out_bf16) SG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<0, 1, 0, 1>, mapA, mapBh, mapO, t));
-    else SG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<0, 0, 0, 1>, mapA, mapBh, mapO, t));
+    if (a.xf_ab) { cfg.blockDim = dim3(TC_XF_THREADS); SG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, 1, 1, 1>, mapA, mapBh, mapO, mapO2, t)); }
+    else if (a.op_bf16) SG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<1, 1, 0, 1>, mapA, mapBh, mapO, mapO2, t));
+    else if (a.out_bf16) SG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<0, 1, 0, 1>, mapA, mapBh, mapO, mapO2, t));
+    else SG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<0, 0, 0, 1>, mapA, mapBh, mapO, mapO2, t));
     return SG_OK;
   }
   int grid = t.m_tiles * t.n_tiles * ksplit;
   if (grid > g_num_sms) grid = g_num_sms;
-  if (a.xf_ab) conv_tc_kernel<1, 1, 1><<<grid, TC_XF_THREADS, TC_SMEM_BYTES, st>>>(mapA, mapB, mapO, t);
-  else if (a.op_bf16 && a.out_bf16) conv_tc_kernel<1, 1><<<grid, TC_MAIN_THREADS, TC_SMEM_BYTES, st>>>(mapA, mapB, mapO, t);
-  else if (a.op_bf16) conv_tc_kernel<1, 0><<<grid, TC_MAIN_THREADS, TC_SMEM_BYTES, st>>>(mapA, mapB, mapO, t);
-  else if (a.out_bf16) conv_tc_kernel<0, 1><<<grid, TC_MAIN_THREADS, TC_SMEM_BYTES, st>>>(mapA, mapB, mapO, t);
-  else conv_tc_kernel<0, 0><<<grid, TC_MAIN_THREADS, TC_SMEM_BYTES, st>>>(mapA, mapB, mapO, t);
+  if (a.xf_ab) conv_tc_kernel<1, 1, 1><<<grid, TC_XF_THREADS, TC_SMEM_BYTES, st>>>(mapA, mapB, mapO, mapO2, t);
+  else if (a.op_bf16 && a.out_bf16) conv_tc_kernel<1, 1><<<grid, TC_MAIN_THREADS, TC_SMEM_BYTES, st>>>(mapA, mapB, mapO, mapO2, t);
+  else if (a.op_bf16) conv_tc_kernel<1, 0><<<grid, TC_MAIN_THREADS, TC_SMEM_BYTES, st>>>(mapA, mapB, mapO, mapO2, t);
+  else if (a.out_bf16) conv_tc_kernel<0, 1><<<grid, TC_MAIN_THREADS, TC_SMEM_BYTES, st>>>(mapA, mapB, mapO, mapO2, t);
+  else conv_tc_kernel<0, 0><<<grid, TC_MAIN_THREADS, TC_SMEM_BYTES, st>>>(mapA, mapB, mapO, mapO2, t);
   SG_LAUNCH_CHECK();
   if (ksplit > 1) {
     const size_t n = (size_t)a.rows * (a.N / 4);

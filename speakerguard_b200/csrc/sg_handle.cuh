@@ -54,6 +54,7 @@ struct sg_handle {
   int use_graph = 1;                // SG_OPT_CUDA_GRAPH: sg_pgd_run replays one captured iteration instead of ~26 launches per pass
   SgPgdGraph pgd_graph;
   float* cm_part = nullptr; unsigned int* cm_count = nullptr; int cm_cap = 0;   // fused-CMVN scratch (chunk sums, counters) for cm_cap utterances
+  int row_compaction = 1;           // SG_OPT_ROW_COMPACTION: layers 4 / 5, pooling and their adjoints on the valid frames only (tensor-core modes)
   int cmvn_fusion = 0;              // SG_OPT_CMVN_FUSION: utterances of <= 300 frames run CMVN (and its adjoint) inside the MFCC kernels
                                     // (off: measured 2 ms per PGD-100 step SLOWER than the two 23 us cmvn launches, see sgb200.h)
   int pool_fusion = 1;              // SG_OPT_POOL_FUSION: bf16 mode contracts the pooling adjoint inside the layer-5 dgrad

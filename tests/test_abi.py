@@ -71,7 +71,7 @@ def test_python_constants_mirror_the_header():
     defs = {k: int(v) for k, v in re.findall(r"#define\s+(SG_OPT_[A-Z0-9_]+)\s+(\d+)", src)}
     assert defs == {"SG_OPT_POOL_FUSION": _lib.OPT_POOL_FUSION, "SG_OPT_FEAT_STASH": _lib.OPT_FEAT_STASH,
                     "SG_OPT_L1_TAP_FORM": _lib.OPT_L1_TAP_FORM, "SG_OPT_UTT_OFFSET": _lib.OPT_UTT_OFFSET,
-                    "SG_OPT_CUDA_GRAPH": _lib.OPT_CUDA_GRAPH, "SG_OPT_CMVN_FUSION": _lib.OPT_CMVN_FUSION}
+                    "SG_OPT_CUDA_GRAPH": _lib.OPT_CUDA_GRAPH, "SG_OPT_CMVN_FUSION": _lib.OPT_CMVN_FUSION, "SG_OPT_ROW_COMPACTION": _lib.OPT_ROW_COMPACTION}
     body = re.search(r"enum\s*\{\s*SG_PROF_MFCC_FWD\s*=\s*0(.*?)SG_PROF_COUNT\s*\}", re.sub(r"/\*.*?\*/", "", src, flags=re.S), re.S)
     assert body is not None
     n_prof = 1 + len(re.findall(r"SG_PROF_[A-Z0-9_]+", body.group(1)))

@@ -271,3 +271,34 @@ def test_layer1_dgrad_tap_form_matches_long_k_form():
     print(f"layer-1 dgrad tap form vs long-K form: max rel diff {err:.2e}")
     assert torch.isfinite(g1).all() and err < 1e-5
     assert float(g1[:, :, 30:].abs().max()) == 0.0          # padding columns stay zero
+
+
+@pytest.mark.parametrize("prec,pool_fusion", [("bf16", 1), ("bf16", 0), ("tf32", 1)])
+@pytest.mark.parametrize("B,N", [(7, 48000), (3, 32000), (5, 22400)])
+def test_row_compaction_is_bit_identical(prec, pool_fusion, B, N):
+    """SG_OPT_ROW_COMPACTION: layer 3 stores only the T - 30 frames that are still valid, layers 4 / 5, the pooling and their
+    adjoints run on the compact rows and layer 4's adjoint spreads its result back out.  Every kept value is computed from
+    the same operands in the same order, so embeddings and feature gradients must be equal bit for bit (3 s: boxes straddle
+    utterance boundaries at changing offsets, ragged last tile; 2 s; 1.4 s: T - 30 = 108 < 128 frames, compaction declines)."""
+    from oracle import sg_oracle as O
+    from speakerguard_b200 import _lib
+    from speakerguard_b200.engine import Engine, make_loss_params
+    p = O.make_xv_params(seed=0)
+    torch.manual_seed(31)
+    x = ((torch.rand(B, 1, N) * 2 - 1) * 0.5)[:, 0].cuda()
+    y = (torch.arange(B) % 10).cuda()
+    res = {}
+    for rc in (0, 1):
+        eng = Engine("cuda:0", precision=prec)
+        eng.load_xv(p)
+        eng.set_option(_lib.OPT_ROW_COMPACTION, rc)
+        eng.set_option(_lib.OPT_POOL_FUSION, pool_fusion)
+        feat = eng.cmvn(eng.mfcc_fwd(x, _lib.DITHER_PHILOX, None, seed=3, pass_=0, ld=32), ld_out=32)
+        emb, ws = eng.embed_fwd(feat)
+        scores, _ = eng.score_fwd(emb)
+        _, ds = eng.loss(scores, y, make_loss_params("Entropy"))
+        g = eng.embed_bwd(eng.score_bwd(emb, ds), ws, B, feat.shape[1])
+        res[rc] = (emb.cpu(), g.float().cpu())
+    assert torch.isfinite(res[1][1]).all()
+    assert torch.equal(res[0][0], res[1][0])
+    assert torch.equal(res[0][1], res[1][1])
