@@ -1,5 +1,6 @@
 // Shared declarations for libsgb200 (internal; the public C-ABI is include/sgb200.h).
 #pragma once
+#include <stddef.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -56,6 +57,28 @@ static inline bool sg_first_on_device(std::atomic<unsigned long long>* mask) {
   } while (0)
 
 // ---- feature tables (device resident, built once per handle by sg_feat_tables_build) --------
+// tables of the half-warp-per-frame MFCC kernels (sg_feat.cu, "V2"): 16 lanes own a frame, lane l holds the FFT elements
+// 16 a + l and, after the transform, the bins l + 16 i
+#define SG_M2_ITERS 16
+struct alignas(16) SgFeatTables2 {
+  // common
+  float window[SG_WIN];          // Povey window
+  float2 tw16[16][16];           // [k1][b] = exp(-2 pi i b k1 / 256): twiddles between the two radix-16 passes
+  float2 untw[16][16];           // [i][l] = (cos, sin)(2 pi (l + 16 i) / 512): real-FFT untangle
+  // forward only (the forward kernel copies the struct up to `binw`)
+  float4 m2_w[SG_M2_ITERS][16];  // mel weights: lane l runs through the float4 groups of filter l, then of filter 29 - l
+  int m2_len0[16], m2_lo0[16], m2_lo1s[16];   // groups of the first filter, its first bin, first bin of the second minus 4 * len0
+  int m2_iters;                  // max over lanes of the two filters' groups
+  int pad_[3];
+  float dct_kn[32][36];          // as below
+  // adjoint only
+  float2 binw[256];              // per FFT bin: weights towards the (<= 2) filters it feeds
+  int binc[256];                 // their indices c0 | c1 << 8 (31 = none)
+  float dct_nk[32][36];
+};
+#define SG_T2_FWD_BYTES (offsetof(SgFeatTables2, binw))
+#define SG_T2_COMMON_BYTES (offsetof(SgFeatTables2, m2_w))
+
 struct alignas(16) SgFeatTables {
   float window[SG_WIN];          // Povey window
   float2 tw[24][32];             // per-lane FFT twiddles: [0..7] pass A, [8..15] pass B, [16..23] untangle
@@ -68,7 +91,10 @@ struct alignas(16) SgFeatTables {
   float dct_kn[32][36];          // [k][n] = D[n][k] * lifter[k]: forward, lane k reads float4 over n (stride 36: conflict-free)
   float dct_nk[32][36];          // [n][k] (k >= 1; column 0 zero: C0 is the log-energy): adjoint, lane n reads float4 over k
   int mel_maxlen;                // max number of float4 groups
+  int pad_[3];
+  SgFeatTables2 v2;              // LAST member: the V1 kernels copy only the bytes before it into shared memory
 };
+#define SG_FEAT_V1_BYTES (offsetof(SgFeatTables, v2))
 
 int sg_feat_tables_build(SgFeatTables* host_out);
 

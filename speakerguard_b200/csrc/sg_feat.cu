@@ -92,6 +92,38 @@ int sg_feat_tables_build(SgFeatTables* t) {
       t->dct_kn[k][n] = (float)(d * lift);
       t->dct_nk[n][k] = (k == 0) ? 0.f : (float)(d * lift);
     }
+  // ---- V2 (half-warp per frame): the same values, re-indexed -------------------------------------
+  SgFeatTables2& u = t->v2;
+  memcpy(u.window, t->window, sizeof(u.window));
+  memcpy(u.dct_kn, t->dct_kn, sizeof(u.dct_kn));
+  memcpy(u.dct_nk, t->dct_nk, sizeof(u.dct_nk));
+  for (int k1 = 0; k1 < 16; ++k1)
+    for (int b = 0; b < 16; ++b) {
+      const double a = -2.0 * PI * (b * k1) / 256.0;
+      u.tw16[k1][b] = make_float2((float)cos(a), (float)sin(a));
+    }
+  for (int i = 0; i < 16; ++i)
+    for (int l = 0; l < 16; ++l) {
+      const double a = 2.0 * PI * (l + 16 * i) / 512.0;
+      u.untw[i][l] = make_float2((float)cos(a), (float)sin(a));
+    }
+  int iters = 0;
+  for (int l = 0; l < 16; ++l) {
+    const int c0 = l, c1 = SG_NMEL - 1 - l;
+    const int g0 = l < 15 ? t->mel_len[c0] : 0, g1 = l < 15 ? t->mel_len[c1] : 0;
+    if (g0 + g1 > SG_M2_ITERS) return SG_EINVAL;
+    u.m2_len0[l] = g0; u.m2_lo0[l] = l < 15 ? t->mel_lo[c0] : 0; u.m2_lo1s[l] = l < 15 ? t->mel_lo[c1] - 4 * g0 : 0;
+    for (int i = 0; i < g0 + g1; ++i) {
+      const float* w4 = i < g0 ? &t->mel_w[t->mel_off[c0] + 4 * i] : &t->mel_w[t->mel_off[c1] + 4 * (i - g0)];
+      u.m2_w[i][l] = make_float4(w4[0], w4[1], w4[2], w4[3]);
+    }
+    if (g0 + g1 > iters) iters = g0 + g1;
+  }
+  u.m2_iters = iters;
+  for (int k = 0; k < 256; ++k) {
+    u.binw[k] = make_float2(t->bin_w0[k], t->bin_w1[k]);
+    u.binc[k] = t->bin_c0[k] | (t->bin_c1[k] << 8);
+  }
   return SG_OK;
 }
 
@@ -227,14 +259,22 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 // The philox dither is a statistically-equivalent stand-in for torch.randn (SG_DITHER_TENSOR is the
 // bit-parity mode), so the fast intrinsics are fine here; forward, adjoint and sg_dither_fill share
 // this function and therefore see identical noise.
-__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
-  float u1 = __uint2float_rn(a) * 2.3283064365386963e-10f + 1.1641532182693481e-10f;
-  float u2 = __uint2float_rn(b) * 2.3283064365386963e-10f + 1.1641532182693481e-10f;
-  const float t2 = -2.0f * __logf(u1);
-  float r = t2 * rsqrtf(fmaxf(t2, 1e-30f));                      // sqrt(t2) without the IEEE sqrt sequence
-  float s, c;
-  __sincosf(6.283185307179586f * u2, &s, &c);
-  return make_float2(r * c, r * s);
+// N(0,1) pairs from 16-bit uniforms: one philox call (4 words) feeds four sample pairs.  The dither is one quantisation
+// step of the int16-range waveform; its distribution, not its resolution, is what the features see (radius: 65536 levels up
+// to 4.8 sigma, angle: 65536 directions).
+__device__ __forceinline__ float2 box_muller16(uint32_t w) {
+  const float u1 = __uint_as_float(0x3f800000u | ((w & 0xffffu) << 7)) - 0.99999237060546875f;    // (lo16 + 0.5) / 65536 in (0, 1)
+  const float u2 = __uint_as_float(0x3f800000u | ((w >> 16) << 7)) - 1.0f;                       // hi16 / 65536 in [0, 1)
+  // the bare MUFU forms (u1 is a normal number well inside the range of lg2.approx, the angle lies in [0, 2 pi))
+  float lg, rs, sn, cs;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(u1));
+  const float t2 = -1.3862943611198906f * lg;                                                     // -2 ln u1 > 0
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(t2));
+  const float r = t2 * rs;
+  const float ang = 6.283185307179586f * u2;
+  asm("sin.approx.ftz.f32 %0, %1;" : "=f"(sn) : "f"(ang));
+  asm("cos.approx.ftz.f32 %0, %1;" : "=f"(cs) : "f"(ang));
+  return make_float2(r * cs, r * sn);
 }
 
 struct DitherSpec {
@@ -277,13 +317,15 @@ __device__ __forceinline__ void load_frame(Frame& F, const float* __restrict__ x
         nz[2 * n0] = d.x; nz[2 * n0 + 1] = d.y;
       }
   } else if (D.mode == SG_DITHER_PHILOX) {
+    // one dither stream for both kernel generations (defined by the V2 ownership: call q, lane l = lane & 15, word u -> sample
+    // pair a = 4 q + u, samples 32 a + 2 l, +1): this lane's pair n0 is a = 2 n0 + (lane >> 4)
+    const int hi = lane >> 4;
 #pragma unroll
-    for (int h = 0; h < 4; ++h) {
-      uint4 r = philox4x32_10(make_uint4(h * 32 + lane, (uint32_t)fr, (uint32_t)b + D.b_off, D.pass),
-                              make_uint2(D.seed_lo, D.seed_hi));
-      float2 a = box_muller(r.x, r.y), c = box_muller(r.z, r.w);
-      nz[4 * h] = a.x; nz[4 * h + 1] = a.y;
-      if (h < 3) { nz[4 * h + 2] = c.x; nz[4 * h + 3] = c.y; }
+    for (int q = 0; q < 4; ++q) {
+      const uint4 r = philox4x32_10(make_uint4(q * 16 + (lane & 15), (uint32_t)fr, (uint32_t)b + D.b_off, D.pass), make_uint2(D.seed_lo, D.seed_hi));
+      const float2 a = box_muller16(hi ? r.y : r.x);
+      nz[4 * q] = a.x; nz[4 * q + 1] = a.y;
+      if (q < 3) { const float2 c = box_muller16(hi ? r.w : r.z); nz[4 * q + 2] = c.x; nz[4 * q + 3] = c.y; }
     }
   }
   float s = 0.f;
@@ -380,9 +422,9 @@ __device__ __forceinline__ float mel_energy(const SgFeatTables* T, const float* 
 __device__ __forceinline__ void copy_tables(SgFeatTables* dst, const SgFeatTables* __restrict__ src) {
   const int4* s = reinterpret_cast<const int4*>(src);
   int4* d = reinterpret_cast<int4*>(dst);
-  for (int i = threadIdx.x; i < (int)(sizeof(SgFeatTables) / 16); i += blockDim.x) d[i] = s[i];
+  for (int i = threadIdx.x; i < (int)(SG_FEAT_V1_BYTES / 16); i += blockDim.x) d[i] = s[i];
 }
-static_assert(sizeof(SgFeatTables) % 16 == 0, "SgFeatTables must be int4-copyable");
+static_assert(SG_FEAT_V1_BYTES % 16 == 0 && sizeof(SgFeatTables2) % 16 == 0, "feature tables must be int4-copyable");
 
 // ---- per-frame stash: what the adjoint needs from the forward (spectrum, DC-removed dithered frame, mel energies,
 // raw energy).  Written by mfcc_fwd_kernel when the attack loop asks for it, so that mfcc_bwd_kernel neither regenerates
@@ -434,7 +476,7 @@ mfcc_fwd_kernel(const float* __restrict__ x, int N, int m, int frames_per_cta, D
   dither_resolve(D);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* scratch = reinterpret_cast<float*>(smem_raw + sizeof(SgFeatTables)) + warp * WARP_SCRATCH;
+  float* scratch = reinterpret_cast<float*>(smem_raw + SG_FEAT_V1_BYTES) + warp * WARP_SCRATCH;
   float *sre = scratch, *sim = scratch + 288, *P = scratch + 576;
   const int b = blockIdx.y;
   const float* xb = x + (size_t)b * N;
@@ -475,7 +517,7 @@ mfcc_fwd_kernel(const float* __restrict__ x, int N, int m, int frames_per_cta, D
   }
   if (CMVN) {
     // model/iv_plda.py:296-377 with T <= 300: y[t] = x[t] - mean_t(x)
-    const float* fb = reinterpret_cast<const float*>(smem_raw + sizeof(SgFeatTables));
+    const float* fb = reinterpret_cast<const float*>(smem_raw + SG_FEAT_V1_BYTES);
     const int nch = gridDim.x;
     __syncthreads();                                               // every warp is done with its scratch
     sre[lane] = colsum;                                            // warp partial (scratch of warp w starts at fb + w * WARP_SCRATCH)
@@ -534,7 +576,7 @@ mfcc_bwd_kernel(const float* __restrict__ x, int N, int m, int own_frames, Dithe
                 const float* __restrict__ stash) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SgFeatTables* T = reinterpret_cast<SgFeatTables*>(smem_raw);
-  float* fbase = reinterpret_cast<float*>(smem_raw + sizeof(SgFeatTables));
+  float* fbase = reinterpret_cast<float*>(smem_raw + SG_FEAT_V1_BYTES);
   float* framebuf = fbase + FEAT_WARPS * WARP_SCRATCH;             // [8][400]: frame gradients of the current group
   float* acc = framebuf + FEAT_WARPS * SG_WIN;                     // [ACC_RING]: circular overlap-add accumulator, index = padded position & (ACC_RING - 1)
   __shared__ __align__(8) uint64_t ola_done;                       // split barrier: "group g's frame gradients have been consumed"
@@ -797,23 +839,6 @@ mfcc_bwd_kernel(const float* __restrict__ x, int N, int m, int own_frames, Dithe
 // =============================================================================================
 // dither materialisation, sign step
 // =============================================================================================
-__global__ void dither_fill_kernel(int m, DitherSpec D, float* __restrict__ out) {
-  dither_resolve(D);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int fr = blockIdx.x * (blockDim.x >> 5) + warp, b = blockIdx.y;
-  if (fr >= m) return;
-  float* o = out + ((size_t)b * m + fr) * SG_WIN;
-#pragma unroll
-  for (int h = 0; h < 4; ++h) {
-    uint4 r = philox4x32_10(make_uint4(h * 32 + lane, (uint32_t)fr, (uint32_t)b + D.b_off, D.pass),
-                            make_uint2(D.seed_lo, D.seed_hi));
-    float2 a = box_muller(r.x, r.y), c = box_muller(r.z, r.w);
-    int j0 = 64 * (2 * h) + 2 * lane, j1 = 64 * (2 * h + 1) + 2 * lane;
-    if (j0 < SG_WIN) { o[j0] = a.x; o[j0 + 1] = a.y; }
-    if (h < 3 && j1 < SG_WIN) { o[j1] = c.x; o[j1 + 1] = c.y; }
-  }
-}
-
 __global__ void step_linf_kernel(float* __restrict__ x, const float* __restrict__ x0,
                                  const float* __restrict__ grad, size_t n, float step, float eps) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -966,11 +991,637 @@ __global__ void cmvn_prefix_kernel(const float* __restrict__ in, int ld_in, floa
 }
 
 // =============================================================================================
+// V2: one HALF-warp per frame (two frames per warp)
+// =============================================================================================
+// The V1 kernels above give a frame to a whole warp: 8 FFT elements per lane, a 256-point complex FFT as 8 x 8 x 4 with two
+// shared-memory exchanges, and every table (twiddles, window, mel weights, DCT) read from shared memory once per frame.
+// ncu (profiles/r2_mfcc_ncu_summary.json) puts them at 91 % of the L1/shared-memory pipe and 68 % issue utilisation at once:
+// ~370 shared-memory wavefronts and ~1300 warp instructions per frame.  Here 16 lanes own a frame and hold 16 FFT elements
+// each: 256 = 16 x 16 needs ONE exchange, the real-FFT untangle finds its mirror bin 256 - k in the partner lane 16 - l
+// (a shuffle, no shared memory), and every table load is shared by the two frames of the warp (same address in both halves:
+// a broadcast).  Ownership inside a half-warp, lane l = lane & 15:
+//   samples      pair a in [0, 13): j = 32 a + 2 l (+1); a = 12 only for l < 8 (j < 400)        = FFT input element 16 a + l
+//   spectrum     slot i in [0, 16): bin k = l + 16 i
+//   mel filters  l and 29 - l (lane 15 idles), cepstra l and l + 16
+#define F2_GROUP 16                        // frames per CTA iteration
+#define F2_EX 272                          // floats per exchange plane: 16 rows x 17
+#define F2_SMALL (4 * F2_EX)               // offset of the small per-frame rows: lm / dC [2][48], dmel [2][48]
+#define F2_ROW 48                          // row stride of the small rows (32 used): the two half-warps land in different banks
+#define F2_WARP_SCRATCH (4 * F2_EX + 4 * F2_ROW)
+// plane order [re 0][re 1][im 0][im 1]: the two half-warps of an access are 272 = 16 (mod 32) floats apart, i.e. in disjoint
+// banks; the power spectrum P (256 floats) reuses this half-warp's re plane once the FFT is done
+#define F2_RE(scratch, hf) ((scratch) + (hf) * F2_EX)
+#define F2_IM(scratch, hf) ((scratch) + (2 + (hf)) * F2_EX)
+#define F2_ACC_LEN ((F2_GROUP - 1) * SG_SHIFT + SG_WIN)   // 2800: padded span of 16 consecutive frames
+#define F2_ACC_RING 4096
+#define F2_NQ ((F2_ACC_LEN + FEAT_THREADS - 1) / FEAT_THREADS)   // 11 positions per thread (scalar form)
+#define F2_NQ4 ((F2_ACC_LEN / 4 + FEAT_THREADS - 1) / FEAT_THREADS)   // 3 float4 of positions per thread
+
+__device__ __forceinline__ float2 cmulc(float2 a, float cr, float ci) { return make_float2(a.x * cr - a.y * ci, a.x * ci + a.y * cr); }
+
+// natural-order in, natural-order out: v[k] = sum_n v[n] W_16^(nk); radix 4 x 4, constant twiddles
+__device__ __forceinline__ void fft16(float2 (&v)[16]) {
+#pragma unroll
+  for (int n0 = 0; n0 < 4; ++n0) fft4(v[n0], v[n0 + 4], v[n0 + 8], v[n0 + 12]);
+  const float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, h = 0.70710678118654752f;
+  v[5] = cmulc(v[5], c1, -s1);                                               // W^1
+  v[9] = make_float2(h * (v[9].x + v[9].y), h * (v[9].y - v[9].x));          // W^2
+  v[13] = cmulc(v[13], s1, -c1);                                             // W^3
+  v[6] = make_float2(h * (v[6].x + v[6].y), h * (v[6].y - v[6].x));          // W^2
+  v[10] = make_float2(v[10].y, -v[10].x);                                    // W^4 = -i
+  v[14] = make_float2(h * (v[14].y - v[14].x), -h * (v[14].x + v[14].y));    // W^6
+  v[7] = cmulc(v[7], s1, -c1);                                               // W^3
+  v[11] = make_float2(h * (v[11].y - v[11].x), -h * (v[11].x + v[11].y));    // W^6
+  v[15] = cmulc(v[15], -c1, s1);                                             // W^9
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1) fft4(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);
+  float2 t[16];                                                              // v[4 k1 + k2] = X[k1 + 4 k2]: register renaming
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1)
+#pragma unroll
+    for (int k2 = 0; k2 < 4; ++k2) t[k1 + 4 * k2] = v[4 * k1 + k2];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) v[k] = t[k];
+}
+
+// 256-point complex FFT on 16 lanes.  In: z[a] = element 16 a + l.  Out: z[i] = Z[l + 16 i].  re / im: this half-warp's
+// exchange planes (F2_EX floats each).  (index maps checked against numpy: tools/fft16_proto.py)
+__device__ __forceinline__ void hw_fft256(float2 (&z)[16], const SgFeatTables2* T, float* re, float* im, int l) {
+  // the two passes share one copy of fft16 in the instruction stream (the forward kernel's loop body is ~35 KB of code and
+  // stalls on instruction fetch otherwise)
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    fft16(z);
+    if (pass == 0) {
+#pragma unroll
+      for (int k1 = 1; k1 < 16; ++k1) z[k1] = cmul(z[k1], T->tw16[k1][l]);
+#pragma unroll
+      for (int k1 = 0; k1 < 16; ++k1) { re[k1 * 17 + l] = z[k1].x; im[k1 * 17 + l] = z[k1].y; }
+      __syncwarp();
+#pragma unroll
+      for (int b = 0; b < 16; ++b) z[b] = make_float2(re[l * 17 + b], im[l * 17 + b]);
+      __syncwarp();
+    }
+  }
+}
+
+struct Frame2 {
+  float fe[13], fo[13];  // DC-removed samples of pair a (even / odd)
+  float sumsq;
+};
+
+__device__ __forceinline__ float half_sum(float v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void load_frame2(Frame2& F, const float* __restrict__ xb, int N, int b, int m, int fr, const DitherSpec& D, int l) {
+  const int p0 = fr * SG_SHIFT - SG_HALO + 2 * l;
+  // the waveform loads go first: the dither arithmetic below covers their latency
+  const int w0 = fr * SG_SHIFT - SG_HALO;
+  const bool interior = (w0 >= 0) && (w0 + SG_WIN <= N);
+  const bool vec = interior && ((reinterpret_cast<uintptr_t>(xb + w0) & 7) == 0);
+#pragma unroll
+  for (int a = 0; a < 13; ++a) {
+    const bool valid = (a < 12) || (l < 8);
+    float ve = 0.f, vo = 0.f;
+    if (valid) {
+      if (vec) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(xb + p0 + 32 * a));
+        ve = v.x; vo = v.y;
+      } else {
+        int pe = p0 + 32 * a, po = pe + 1;
+        pe = pe < 0 ? -pe - 1 : (pe >= N ? 2 * N - 1 - pe : pe);       // kaldi.py:69-77 reflect pad
+        po = po < 0 ? -po - 1 : (po >= N ? 2 * N - 1 - po : po);
+        ve = __ldg(xb + pe); vo = __ldg(xb + po);
+      }
+    }
+    F.fe[a] = ve; F.fo[a] = vo;
+  }
+  float nz[26];
+#pragma unroll
+  for (int i = 0; i < 26; ++i) nz[i] = 0.f;
+  if (D.mode == SG_DITHER_TENSOR) {
+    const float* dp = D.tensor + ((size_t)b * m + fr) * SG_WIN + 2 * l;
+#pragma unroll
+    for (int a = 0; a < 13; ++a)
+      if (a < 12 || l < 8) {
+        const float2 d = *reinterpret_cast<const float2*>(dp + 32 * a);
+        nz[2 * a] = d.x; nz[2 * a + 1] = d.y;
+      }
+  } else if (D.mode == SG_DITHER_PHILOX) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 r = philox4x32_10(make_uint4(q * 16 + l, (uint32_t)fr, (uint32_t)b + D.b_off, D.pass), make_uint2(D.seed_lo, D.seed_hi));
+      const float2 n0 = box_muller16(r.x);
+      nz[8 * q] = n0.x; nz[8 * q + 1] = n0.y;
+      if (q < 3) {
+        const float2 n1 = box_muller16(r.y), n2 = box_muller16(r.z), n3 = box_muller16(r.w);
+        nz[8 * q + 2] = n1.x; nz[8 * q + 3] = n1.y; nz[8 * q + 4] = n2.x; nz[8 * q + 5] = n2.y; nz[8 * q + 6] = n3.x; nz[8 * q + 7] = n3.y;
+      }
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int a = 0; a < 13; ++a) {
+    const bool valid = (a < 12) || (l < 8);
+    const float ve = valid ? fmaf(F.fe[a], 32768.0f, nz[2 * a]) : 0.f;      // model/utils.py:14, kaldi.py:181 (x * 2^15 is exact)
+    const float vo = valid ? fmaf(F.fo[a], 32768.0f, nz[2 * a + 1]) : 0.f;
+    F.fe[a] = ve; F.fo[a] = vo;
+    s += ve + vo;
+  }
+  const float mean = half_sum(s) * (1.0f / SG_WIN);                    // kaldi.py:183-186
+  float q = 0.f;
+#pragma unroll
+  for (int a = 0; a < 13; ++a) {
+    const bool valid = (a < 12) || (l < 8);
+    F.fe[a] = valid ? F.fe[a] - mean : 0.f;
+    F.fo[a] = valid ? F.fo[a] - mean : 0.f;
+    q += F.fe[a] * F.fe[a] + F.fo[a] * F.fo[a];
+  }
+  F.sumsq = half_sum(q);
+}
+
+// pre-emphasis + window + real FFT: spectrum bins l + 16 i in X, |X|^2 in P[0..255] (this half-warp's row, shared memory)
+__device__ __forceinline__ void frame_spectrum2(const Frame2& F, float2 (&X)[16], const SgFeatTables2* T, float* re, float* im, float* P, int l) {
+  float2 z[16];
+#pragma unroll
+  for (int a = 0; a < 13; ++a) {
+    // previous sample of the even element: odd element of lane l-1 (same pair row), or of lane 15 of the previous row;
+    // j == 0 replicates itself (kaldi.py:193-198)
+    const float up = __shfl_up_sync(0xffffffffu, F.fo[a], 1, 16);
+    const float wrap = __shfl_sync(0xffffffffu, a > 0 ? F.fo[a > 0 ? a - 1 : 0] : F.fe[0], 15, 16);
+    const float prev = l > 0 ? up : (a > 0 ? wrap : F.fe[0]);
+    const bool valid = (a < 12) || (l < 8);
+    const float2 w2 = valid ? *reinterpret_cast<const float2*>(&T->window[32 * a + 2 * l]) : make_float2(0.f, 0.f);
+    z[a] = make_float2((F.fe[a] - 0.97f * prev) * w2.x, (F.fo[a] - 0.97f * F.fe[a]) * w2.y);
+  }
+  z[13] = z[14] = z[15] = make_float2(0.f, 0.f);
+  hw_fft256(z, T, re, im, l);
+  // untangle: X[k] = a_k Z[k] + b_k conj(Z[256-k]),  a_k = ((1-s) - i c)/2, b_k = ((1+s) + i c)/2; the mirror bin
+  // 256 - (l + 16 i) = (16 - l) + 16 (15 - i) lives in lane 16 - l, slot 15 - i (lane 0: own slot (16 - i) & 15)
+  const int partner = (16 - l) & 15;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float mx = __shfl_sync(0xffffffffu, z[15 - i].x, partner, 16);
+    float my = __shfl_sync(0xffffffffu, z[15 - i].y, partner, 16);
+    if (l == 0) { mx = z[(16 - i) & 15].x; my = z[(16 - i) & 15].y; }
+    const float2 zm = make_float2(mx, -my);
+    const float2 cs = T->untw[i][l];
+    const float2 a = make_float2(0.5f * (1.f - cs.y), -0.5f * cs.x);
+    const float2 bq = make_float2(0.5f * (1.f + cs.y), 0.5f * cs.x);
+    X[i] = cadd(cmul(a, z[i]), cmul(bq, zm));
+    P[l + 16 * i] = X[i].x * X[i].x + X[i].y * X[i].y;                  // kaldi.py:616-618
+  }
+  __syncwarp();
+}
+
+// mel energies (before the log; kaldi.py:621-630) of filters l (me0) and 29 - l (me1); each filter is summed in the same
+// order as in the V1 kernel (float4 groups left to right, one fma chain)
+__device__ __forceinline__ void mel_energy2(const SgFeatTables2* T, const float* P, int l, float& me0, float& me1) {
+  const int len0 = T->m2_len0[l], lo0 = T->m2_lo0[l], lo1s = T->m2_lo1s[l];
+  float a0 = 0.f, a1 = 0.f;
+  const int iters = T->m2_iters;
+  for (int i = 0; i < iters; ++i) {
+    const bool first = i < len0;
+    const int off = min((first ? lo0 : lo1s) + 4 * i, 252);          // padding groups (zero weights) must still read finite values
+    const float4 w = T->m2_w[i][l];
+    const float4 p = *reinterpret_cast<const float4*>(&P[off]);
+    float acc = first ? a0 : a1;
+    acc = fmaf(w.x, p.x, acc); acc = fmaf(w.y, p.y, acc); acc = fmaf(w.z, p.z, acc); acc = fmaf(w.w, p.w, acc);
+    if (first) a0 = acc; else a1 = acc;
+  }
+  me0 = a0; me1 = a1;
+}
+
+// ---- per-frame stash, V2 layout (floats): X as float4 {X[2j], X[2j+1]} [8][16] | f as float2 [13][16] | mel[32] | sumsq
+#define S2_F 512
+#define S2_MEL 928
+#define S2_SUMSQ 960
+__device__ __forceinline__ void stash2_store_f(float* __restrict__ sp, const Frame2& F, int l) {
+  float2* s2 = reinterpret_cast<float2*>(sp + S2_F);
+#pragma unroll
+  for (int a = 0; a < 13; ++a) __stcs(s2 + a * 16 + l, make_float2(F.fe[a], F.fo[a]));
+  if (l == 0) __stcs(sp + S2_SUMSQ, F.sumsq);
+}
+__device__ __forceinline__ void stash2_store_x(float* __restrict__ sp, const float2 (&X)[16], int l) {
+  float4* s4 = reinterpret_cast<float4*>(sp);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) __stcs(s4 + j * 16 + l, make_float4(X[2 * j].x, X[2 * j].y, X[2 * j + 1].x, X[2 * j + 1].y));
+}
+__device__ __forceinline__ void stash2_load_x(const float* __restrict__ sp, float2 (&X)[16], int l) {
+  const float4* s4 = reinterpret_cast<const float4*>(sp);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 v = __ldcs(s4 + j * 16 + l);
+    X[2 * j] = make_float2(v.x, v.y); X[2 * j + 1] = make_float2(v.z, v.w);
+  }
+}
+__device__ __forceinline__ void stash2_load_f(const float* __restrict__ sp, Frame2& F, int l) {
+  const float2* s2 = reinterpret_cast<const float2*>(sp + S2_F);
+#pragma unroll
+  for (int a = 0; a < 13; ++a) { const float2 v = __ldcs(s2 + a * 16 + l); F.fe[a] = v.x; F.fo[a] = v.y; }
+  F.sumsq = __ldcs(sp + S2_SUMSQ);
+}
+
+// PART 0: the forward's tables (a prefix of the struct), 1: the adjoint's (common part + tail), 2: everything
+template <int PART>
+__device__ __forceinline__ void copy_tables2(SgFeatTables2* dst, const SgFeatTables* __restrict__ src) {
+  const int4* s = reinterpret_cast<const int4*>(&src->v2);
+  int4* d = reinterpret_cast<int4*>(dst);
+  const int n0 = (int)((PART == 0 ? SG_T2_FWD_BYTES : (PART == 1 ? SG_T2_COMMON_BYTES : sizeof(SgFeatTables2))) / 16);
+  for (int i = threadIdx.x; i < n0; i += blockDim.x) d[i] = s[i];
+  if (PART == 1)
+    for (int i = (int)(SG_T2_FWD_BYTES / 16) + threadIdx.x; i < (int)(sizeof(SgFeatTables2) / 16); i += blockDim.x) d[i] = s[i];
+}
+static_assert(SG_T2_FWD_BYTES % 16 == 0 && SG_T2_COMMON_BYTES % 16 == 0, "table sections must be int4-copyable");
+
+// F1 (V2): waveform -> raw MFCC
+template <int MINB>
+__global__ void __launch_bounds__(FEAT_THREADS, MINB)
+mfcc2_fwd_kernel(const float* __restrict__ x, int N, int m, int frames_per_cta, DitherSpec D, float* __restrict__ raw, int ld,
+                 const SgFeatTables* __restrict__ gT, float* __restrict__ stash) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SgFeatTables2* T = reinterpret_cast<SgFeatTables2*>(smem_raw);       // only the forward's prefix of the struct is resident
+  copy_tables2<0>(T, gT);
+  dither_resolve(D);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, hf = lane >> 4, l = lane & 15;
+  float* scratch = reinterpret_cast<float*>(smem_raw + SG_T2_FWD_BYTES) + warp * F2_WARP_SCRATCH;
+  float *re = F2_RE(scratch, hf), *im = F2_IM(scratch, hf), *P = re;
+  float* lm = scratch + F2_SMALL + F2_ROW * hf;
+  const int b = blockIdx.y;
+  const float* xb = x + (size_t)b * N;
+  const int f0 = blockIdx.x * frames_per_cta;
+  const int f1 = min(f0 + frames_per_cta, m);
+  for (int fb = f0 + 2 * warp; fb < f1; fb += F2_GROUP) {
+    const bool active = fb + hf < f1;                                 // an odd tail: the upper half-warp recomputes the last frame
+    const int fr = active ? fb + hf : f1 - 1;
+    if (fb + F2_GROUP + hf < f1 && l < 14) {                           // next frame's 400 samples: <= 14 lines of 128 bytes
+      int p = (fb + F2_GROUP + hf) * SG_SHIFT - SG_HALO + 32 * l;
+      p = p < 0 ? 0 : (p >= N ? N - 1 : p);
+      prefetch_l1(xb + p);
+    }
+    float* sp = stash != nullptr ? stash + ((size_t)b * m + fr) * SG_STASH_FLOATS : nullptr;
+    float logE;
+    float2 X[16];
+    {
+      Frame2 F;
+      load_frame2(F, xb, N, b, m, fr, D, l);
+      if (sp != nullptr && active) stash2_store_f(sp, F, l);
+      logE = logf(fmaxf(F.sumsq, SG_EPS));                             // kaldi.py:119
+      frame_spectrum2(F, X, T, re, im, P, l);
+    }
+    if (sp != nullptr && active) stash2_store_x(sp, X, l);
+    float me0, me1;
+    mel_energy2(T, P, l, me0, me1);
+    if (sp != nullptr && active) {
+      if (l < 15) { __stcs(sp + S2_MEL + l, me0); __stcs(sp + S2_MEL + SG_NMEL - 1 - l, me1); }
+      else { __stcs(sp + S2_MEL + 30, 0.f); __stcs(sp + S2_MEL + 31, 0.f); }
+    }
+    if (l < 15) { lm[l] = logf(fmaxf(me0, SG_EPS)); lm[SG_NMEL - 1 - l] = logf(fmaxf(me1, SG_EPS)); }   // kaldi.py:631-633
+    else { lm[30] = 0.f; lm[31] = 0.f; }
+    __syncwarp();
+    float c0 = 0.f, c1 = 0.f;
+    {
+      const float4* d0 = reinterpret_cast<const float4*>(&T->dct_kn[l][0]);
+      const float4* d1 = reinterpret_cast<const float4*>(&T->dct_kn[l + 16][0]);
+      const float4* l4 = reinterpret_cast<const float4*>(lm);
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const float4 v = l4[g], a = d0[g], bb = d1[g];
+        c0 = fmaf(v.x, a.x, c0); c0 = fmaf(v.y, a.y, c0); c0 = fmaf(v.z, a.z, c0); c0 = fmaf(v.w, a.w, c0);
+        c1 = fmaf(v.x, bb.x, c1); c1 = fmaf(v.y, bb.y, c1); c1 = fmaf(v.z, bb.z, c1); c1 = fmaf(v.w, bb.w, c1);
+      }
+    }
+    if (l == 0) c0 = logE;                                             // kaldi.py:799-800
+    if (l + 16 >= SG_NCEP) c1 = 0.f;
+    if (active) {
+      float* o = raw + ((size_t)b * m + fr) * ld;
+      o[l] = c0;
+      if (l + 16 < ld) o[l + 16] = c1;
+    }
+    __syncwarp();
+  }
+}
+
+// F2 (V2): d(raw MFCC) -> d(waveform), optionally fused with the L-inf sign step.  Frame groups of up to 16 frames (one per
+// half-warp); overlap-add, finalisation and the split barrier as in mfcc_bwd_kernel, with the ring sized for 16 frames.
+template <bool STASH>
+__global__ void __launch_bounds__(FEAT_THREADS, 2)
+mfcc2_bwd_kernel(const float* __restrict__ x, int N, int m, int own_frames, DitherSpec D, const float* __restrict__ draw, int ld, BwdOut O,
+                 const SgFeatTables* __restrict__ gT, const float* __restrict__ stash) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SgFeatTables2* T = reinterpret_cast<SgFeatTables2*>(smem_raw);
+  float* fbase = reinterpret_cast<float*>(smem_raw + sizeof(SgFeatTables2));
+  float* framebuf = fbase + FEAT_WARPS * F2_WARP_SCRATCH;          // [16][400]: frame gradients of the current group
+  float* acc = framebuf + F2_GROUP * SG_WIN;                       // [F2_ACC_RING]: circular overlap-add accumulator
+  __shared__ __align__(8) uint64_t ola_done;
+  copy_tables2<STASH ? 1 : 2>(T, gT);
+  dither_resolve(D);
+  for (int i = threadIdx.x; i < F2_ACC_RING; i += FEAT_THREADS) acc[i] = 0.f;
+  if (threadIdx.x == 0) mbar_init(&ola_done, FEAT_THREADS);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, hf = lane >> 4, l = lane & 15;
+  float* scratch = fbase + warp * F2_WARP_SCRATCH;
+  float *re = F2_RE(scratch, hf), *im = F2_IM(scratch, hf), *P = re;
+  float* rowc = scratch + F2_SMALL + F2_ROW * hf;                  // dC[32]
+  float* rowm = scratch + F2_SMALL + F2_ROW * (2 + hf);            // dmel[32]
+  const int b = blockIdx.y;
+  const float* xb = x + (size_t)b * N;
+  const int f0 = blockIdx.x * own_frames;
+  const int f1 = min(f0 + own_frames, m);
+  const int fs = max(f0 - 2, 0);                                   // 2 halo frames on the left
+  const int pmax = SG_SHIFT * (m - 1) + (SG_WIN - SG_HALO) - 1;    // last padded position touched
+  const int own_lo = SG_SHIFT * f0 - SG_HALO;
+  const int own_hi = (f1 == m) ? pmax + 1 : SG_SHIFT * f1 - SG_HALO;
+  // four samples per thread in the overlap-add / finalise phase when every row of the waveform tensors is 16-byte aligned
+  const bool al4 = ((N & 3) == 0) && (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(O.x0) | reinterpret_cast<uintptr_t>(O.x_out) |
+                                        reinterpret_cast<uintptr_t>(O.grad)) & 15) == 0);
+
+  // (the fused CMVN adjoint of mfcc_bwd_kernel is not built here: the host keeps the V1 kernels when SG_OPT_CMVN_FUSION is on)
+  const float mu0 = 0.f, mu1 = 0.f;
+
+  // Frame groups of up to 16 frames; remainder first, first group >= 2 frames (see mfcc_bwd_kernel)
+  const int nfrm = f1 - fs, rem = nfrm % F2_GROUP;
+  const int gs0 = nfrm <= F2_GROUP ? nfrm : (rem == 0 ? F2_GROUP : (rem == 1 ? F2_GROUP / 2 + 1 : rem));
+  const int gs1 = (nfrm > F2_GROUP && rem == 1) ? F2_GROUP / 2 : F2_GROUP;
+  int gi = 0;
+  int gsz = gs0;
+  for (int gf = fs; gf < f1; gf += gsz, gsz = (gi == 0 ? gs1 : F2_GROUP), ++gi) {
+    const int slot = 2 * warp + hf;
+    const bool active = slot < gsz;
+    const int base = SG_SHIFT * gf - SG_HALO;                      // padded position of ring slot q = 0 of this group
+    const bool last = (gf + gsz >= f1);
+    const int fin = last ? F2_ACC_LEN : SG_SHIFT * gsz;            // positions no later group touches
+    const bool edge = (gf == 0) || (last && f1 == m);              // CTA-uniform: left / right reflection partners in range
+    const bool vec = al4 && !edge;
+    const int fr = active ? gf + slot : gf + gsz - 1;              // idle half-warps shadow the group's last frame (results dropped)
+    float* const mybuf = framebuf + slot * SG_WIN;
+    if (STASH) {                                                   // the frame this half-warp takes in the NEXT group: stash (HBM) -> L2
+      const int nf = gf + gsz + slot;
+      if (nf < f1) {
+        prefetch_l2(stash + ((size_t)b * m + nf) * SG_STASH_FLOATS + 32 * l);
+        prefetch_l2(stash + ((size_t)b * m + nf) * SG_STASH_FLOATS + 512 + 32 * l);
+        if (l == 0) prefetch_l2(draw + ((size_t)b * m + nf) * ld);
+      }
+    }
+    const bool work = 2 * warp < gsz;                              // warp-uniform: at least the lower half-warp has a frame
+    const float* sp = STASH ? stash + ((size_t)b * m + fr) * SG_STASH_FLOATS : nullptr;
+    float2 z[16];
+    Frame2 F;
+    float dE = 0.f;
+    if (work) {
+      float2 X[16];
+      float me0, me1;
+      if (STASH) {
+        stash2_load_x(sp, X, l);
+        me0 = __ldcs(sp + S2_MEL + l); me1 = __ldcs(sp + S2_MEL + l + 16);   // filters l, l + 16
+      } else {
+        load_frame2(F, xb, N, b, m, fr, D, l);
+        frame_spectrum2(F, X, T, re, im, P, l);
+        float ma, mb;
+        mel_energy2(T, P, l, ma, mb);                               // filters l and 29 - l
+        __syncwarp();
+        if (l < 15) { rowm[l] = ma; rowm[SG_NMEL - 1 - l] = mb; } else { rowm[30] = 0.f; rowm[31] = 0.f; }
+        __syncwarp();
+        me0 = rowm[l]; me1 = rowm[l + 16];
+        __syncwarp();
+      }
+      // ---- backward: cepstra -> log-mel -> mel -> power -> spectrum -----------------------
+      const float* dr = draw + ((size_t)b * m + fr) * ld;
+      const float dC0 = __ldg(dr + l) - mu0;
+      const float dC1 = (l + 16 < SG_NCEP) ? __ldg(dr + l + 16) - mu1 : 0.f;
+      dE = __shfl_sync(0xffffffffu, dC0, 0, 16);                    // C0 <- log-energy
+      rowc[l] = dC0; rowc[l + 16] = dC1;
+      __syncwarp();
+      float dM0 = 0.f, dM1 = 0.f;
+      {
+        const float4* d0 = reinterpret_cast<const float4*>(&T->dct_nk[l][0]);        // column 0 is zero (C0 <- log-energy)
+        const float4* d1 = reinterpret_cast<const float4*>(&T->dct_nk[l + 16][0]);
+        const float4* c4 = reinterpret_cast<const float4*>(rowc);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 cc = c4[g], a = d0[g], bb = d1[g];
+          dM0 = fmaf(cc.x, a.x, dM0); dM0 = fmaf(cc.y, a.y, dM0); dM0 = fmaf(cc.z, a.z, dM0); dM0 = fmaf(cc.w, a.w, dM0);
+          dM1 = fmaf(cc.x, bb.x, dM1); dM1 = fmaf(cc.y, bb.y, dM1); dM1 = fmaf(cc.z, bb.z, dM1); dM1 = fmaf(cc.w, bb.w, dM1);
+        }
+      }
+      rowm[l] = (me0 > SG_EPS) ? dM0 / me0 : 0.f;
+      rowm[l + 16] = (l + 16 < SG_NMEL && me1 > SG_EPS) ? dM1 / me1 : 0.f;
+      __syncwarp();
+      float2 dX[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int k = l + 16 * i;
+        const float2 w = T->binw[k];
+        const int c = T->binc[k];
+        const float dP = w.x * rowm[c & 255] + w.y * rowm[c >> 8];
+        dX[i] = make_float2(2.f * dP * X[i].x, 2.f * dP * X[i].y);
+      }
+      // adjoint of the untangle step: dZ[k] = ((1-s) + i c)/2 * dX[k] + ((1+s) - i c)/2 * conj(dX[256-k]),  dZ[0] = 0
+      const int partner = (16 - l) & 15;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float mx = __shfl_sync(0xffffffffu, dX[15 - i].x, partner, 16);
+        float my = __shfl_sync(0xffffffffu, dX[15 - i].y, partner, 16);
+        if (l == 0) { mx = dX[(16 - i) & 15].x; my = dX[(16 - i) & 15].y; }
+        const float2 xm = make_float2(mx, -my);
+        const float2 cs = T->untw[i][l];
+        const float2 ca = make_float2(0.5f * (1.f - cs.y), 0.5f * cs.x);
+        const float2 cb = make_float2(0.5f * (1.f + cs.y), -0.5f * cs.x);
+        float2 dz = cadd(cmul(ca, dX[i]), cmul(cb, xm));
+        if (i == 0 && l == 0) dz = make_float2(0.f, 0.f);
+        z[i] = make_float2(dz.x, -dz.y);                            // conj -> forward FFT -> conj = inverse
+      }
+      __syncwarp();
+      if (STASH) stash2_load_f(sp, F, l);                           // needed after the FFT: in flight during it
+      hw_fft256(z, T, re, im, l);
+    }
+    // the iterate / clean waveform of the samples this thread finalises after the group's frames: requested now, so that
+    // the loads complete under the window / pre-emphasis work and the barrier instead of stalling the finalise phase
+    float4 px[F2_NQ4], px0[F2_NQ4];
+#pragma unroll
+    for (int i = 0; i < F2_NQ4; ++i) px[i] = px0[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (O.mode == 1 && vec) {
+#pragma unroll
+      for (int i = 0; i < F2_NQ4; ++i) {
+        const int q = 4 * (threadIdx.x + i * FEAT_THREADS), n = base + q;
+        if (q < fin && n >= own_lo && n < own_hi && n < N) {           // (n >= 0: interior groups start at a positive position)
+          px[i] = __ldg(reinterpret_cast<const float4*>(xb + n));
+          px0[i] = __ldg(reinterpret_cast<const float4*>(O.x0 + (size_t)b * N + n));
+        }
+      }
+    }
+    if (work) {
+      // back in sample ownership: pair a = element 16 a + l: dg[2n] = Re, dg[2n+1] = -Im of the transform
+      float dge[13], dgo[13];
+#pragma unroll
+      for (int a = 0; a < 13; ++a) {
+        const bool valid = (a < 12) || (l < 8);
+        const float2 w2 = valid ? *reinterpret_cast<const float2*>(&T->window[32 * a + 2 * l]) : make_float2(0.f, 0.f);
+        dge[a] = z[a].x * w2.x;
+        dgo[a] = -z[a].y * w2.y;
+      }
+      // pre-emphasis adjoint: g[j] = f[j] - 0.97 f[max(j-1,0)]
+      float s = 0.f;
+      const float esc = (F.sumsq > SG_EPS) ? 2.f * dE / F.sumsq : 0.f;    // d log(sum f^2)
+      float dfe[13], dfo[13];
+#pragma unroll
+      for (int a = 0; a < 13; ++a) {
+        const bool valid = (a < 12) || (l < 8);
+        const float dn = __shfl_down_sync(0xffffffffu, dge[a], 1, 16);   // even sample of lane l+1
+        const float wrap = __shfl_sync(0xffffffffu, dge[a < 12 ? a + 1 : 12], 0, 16);
+        float next = l < 15 ? dn : (a < 12 ? wrap : 0.f);           // dg of sample j+1 for the odd element
+        if (a == 12 && l == 7) next = 0.f;                          // j = 399 is the last sample
+        float de = dge[a] - 0.97f * dgo[a];
+        float dd = dgo[a] - 0.97f * next;
+        if (a == 0 && l == 0) de -= 0.97f * dge[0];                 // replicate pad at j = 0
+        de = fmaf(esc, F.fe[a], de);
+        dd = fmaf(esc, F.fo[a], dd);
+        dfe[a] = valid ? de : 0.f;
+        dfo[a] = valid ? dd : 0.f;
+        s += dfe[a] + dfo[a];
+      }
+      const float mean = half_sum(s) * (1.0f / SG_WIN);            // DC-removal adjoint
+      if (gi > 0) mbar_wait(&ola_done, (uint32_t)((gi - 1) & 1));  // the previous group's frame gradients have been consumed
+      if (active) {
+#pragma unroll
+        for (int a = 0; a < 13; ++a)
+          if ((a < 12) || (l < 8))
+            *reinterpret_cast<float2*>(&mybuf[32 * a + 2 * l]) = make_float2((dfe[a] - mean) * 32768.0f, (dfo[a] - mean) * 32768.0f);
+      }
+    }
+    __syncthreads();
+    // ---- deterministic overlap-add of this group's frames (see mfcc_bwd_kernel) ---------------
+    const int nfr = gsz;
+    if (vec) {
+      // interior group, aligned rows: every quantity of the scalar form below is constant over 4 consecutive positions
+      // (SG_SHIFT, SG_WIN, SG_HALO, the group bounds and N are multiples of 4), so a thread takes a float4 of positions; each
+      // position still receives its (up to) three terms in increasing frame order: identical sums.
+      const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < F2_NQ4; ++i) {
+        const int q = 4 * (threadIdx.x + i * FEAT_THREADS);
+        if (q >= F2_ACC_LEN) continue;
+        float4* ap = reinterpret_cast<float4*>(&acc[(base + q) & (F2_ACC_RING - 1)]);
+        float4 a4 = *ap;
+        const int w0 = q / SG_SHIFT, o0 = q - SG_SHIFT * w0;
+        const float4 t2 = (w0 >= 2 && w0 - 2 < nfr && o0 + 2 * SG_SHIFT < SG_WIN) ? *reinterpret_cast<const float4*>(&framebuf[(w0 - 2) * SG_WIN + o0 + 2 * SG_SHIFT]) : zero4;
+        const float4 t1 = (w0 >= 1 && w0 - 1 < nfr) ? *reinterpret_cast<const float4*>(&framebuf[(w0 - 1) * SG_WIN + o0 + SG_SHIFT]) : zero4;
+        const float4 t0 = (w0 < nfr) ? *reinterpret_cast<const float4*>(&framebuf[w0 * SG_WIN + o0]) : zero4;
+        a4.x += t2.x; a4.x += t1.x; a4.x += t0.x;
+        a4.y += t2.y; a4.y += t1.y; a4.y += t0.y;
+        a4.z += t2.z; a4.z += t1.z; a4.z += t0.z;
+        a4.w += t2.w; a4.w += t1.w; a4.w += t0.w;
+        *ap = (q >= fin) ? a4 : zero4;
+        const int n = base + q;
+        if (q >= fin || n < own_lo || n >= own_hi || n >= N) continue;
+        const size_t gidx = (size_t)b * N + n;
+        if (O.mode == 0) {
+          float4 v = make_float4(O.scale * a4.x, O.scale * a4.y, O.scale * a4.z, O.scale * a4.w);
+          float4* gp = reinterpret_cast<float4*>(O.grad + gidx);
+          if (O.accumulate) { const float4 o = *gp; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+          *gp = v;
+        } else {
+          const float g[4] = {a4.x, a4.y, a4.z, a4.w};
+          const float xc[4] = {px[i].x, px[i].y, px[i].z, px[i].w}, xz[4] = {px0[i].x, px0[i].y, px0[i].z, px0[i].w};
+          float r[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float sg = (g[e] > 0.f) ? 1.f : ((g[e] < 0.f) ? -1.f : 0.f);
+            const float xn = xc[e] + O.step * sg;                     // attack/FGSM.py:65
+            const float lo = fmaxf(xz[e] - O.eps, -1.f), hi = fminf(xz[e] + O.eps, 1.f);   // attack/PGD.py:48-49
+            r[e] = fminf(fmaxf(xn, lo), hi);                          // attack/FGSM.py:68
+          }
+          *reinterpret_cast<float4*>(O.x_out + gidx) = make_float4(r[0], r[1], r[2], r[3]);
+        }
+      }
+    } else {
+    float asum[F2_NQ];
+#pragma unroll
+    for (int i = 0; i < F2_NQ; ++i) {
+      const int q = threadIdx.x + i * FEAT_THREADS;
+      asum[i] = 0.f;
+      if (q >= F2_ACC_LEN) continue;
+      float a = acc[(base + q) & (F2_ACC_RING - 1)];
+      const int w0 = q / SG_SHIFT, o0 = q - SG_SHIFT * w0;
+      const float t2 = (w0 >= 2 && w0 - 2 < nfr && o0 + 2 * SG_SHIFT < SG_WIN) ? framebuf[(w0 - 2) * SG_WIN + o0 + 2 * SG_SHIFT] : 0.f;
+      const float t1 = (w0 >= 1 && w0 - 1 < nfr) ? framebuf[(w0 - 1) * SG_WIN + o0 + SG_SHIFT] : 0.f;
+      const float t0 = (w0 < nfr) ? framebuf[w0 * SG_WIN + o0] : 0.f;
+      a += t2; a += t1; a += t0;
+      asum[i] = a;
+      acc[(base + q) & (F2_ACC_RING - 1)] = (edge || q >= fin) ? a : 0.f;
+    }
+    if (edge) __syncthreads();
+#pragma unroll
+    for (int i = 0; i < F2_NQ; ++i) {
+      const int q = threadIdx.x + i * FEAT_THREADS;
+      if (q >= fin) continue;
+      const int n = base + q;
+      if (n < own_lo || n >= own_hi || n < 0 || n >= N) continue;
+      float g = asum[i];
+      if (edge) {
+        if (n < SG_HALO) {
+          const int qm = (-n - 1) - base;
+          if (qm >= 0 && qm < F2_ACC_LEN) g += acc[(base + qm) & (F2_ACC_RING - 1)];
+        }
+        const int pr = 2 * N - 1 - n;
+        if (pr <= pmax) {
+          const int qm = pr - base;
+          if (qm >= 0 && qm < F2_ACC_LEN) g += acc[(base + qm) & (F2_ACC_RING - 1)];
+        }
+      }
+      const size_t gidx = (size_t)b * N + n;
+      if (O.mode == 0) {
+        const float v = O.scale * g;
+        O.grad[gidx] = O.accumulate ? O.grad[gidx] + v : v;
+      } else {
+        const float xc = __ldg(xb + n), x0 = __ldg(O.x0 + gidx);
+        const float sg = (g > 0.f) ? 1.f : ((g < 0.f) ? -1.f : 0.f);
+        const float xn = xc + O.step * sg;                          // attack/FGSM.py:65
+        const float lo = fmaxf(x0 - O.eps, -1.f), hi = fminf(x0 + O.eps, 1.f);   // attack/PGD.py:48-49
+        O.x_out[gidx] = fminf(fmaxf(xn, lo), hi);                   // attack/FGSM.py:68
+      }
+    }
+    if (edge) {
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < F2_NQ; ++i) {
+        const int q = threadIdx.x + i * FEAT_THREADS;
+        if (q < fin) acc[(base + q) & (F2_ACC_RING - 1)] = 0.f;
+      }
+    }
+    }
+    mbar_arrive(&ola_done);
+  }
+}
+
+__global__ void dither_fill2_kernel(int m, DitherSpec D, float* __restrict__ out) {
+  dither_resolve(D);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, l = lane & 15;
+  const int fr = (blockIdx.x * (blockDim.x >> 5) + warp) * 2 + (lane >> 4), b = blockIdx.y;
+  if (fr >= m) return;
+  float* o = out + ((size_t)b * m + fr) * SG_WIN;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint4 r = philox4x32_10(make_uint4(q * 16 + l, (uint32_t)fr, (uint32_t)b + D.b_off, D.pass), make_uint2(D.seed_lo, D.seed_hi));
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = 32 * (4 * q + u) + 2 * l;
+      if (j < SG_WIN) { const float2 n = box_muller16(w[u]); o[j] = n.x; o[j + 1] = n.y; }
+    }
+  }
+}
+
+// =============================================================================================
 // host launchers (called from sg_api.cu)
 // =============================================================================================
-static size_t feat_fwd_smem() { return sizeof(SgFeatTables) + FEAT_WARPS * WARP_SCRATCH * sizeof(float); }
+static size_t feat_fwd_smem() { return SG_FEAT_V1_BYTES + FEAT_WARPS * WARP_SCRATCH * sizeof(float); }
 static size_t feat_bwd_smem() {
-  return sizeof(SgFeatTables) + (FEAT_WARPS * WARP_SCRATCH + FEAT_WARPS * SG_WIN + ACC_RING) * sizeof(float);
+  return SG_FEAT_V1_BYTES + (FEAT_WARPS * WARP_SCRATCH + FEAT_WARPS * SG_WIN + ACC_RING) * sizeof(float);
 }
 
 // Device control block {pass, seed_lo, seed_hi} for the launches that follow on this thread (set around the captured /
@@ -1006,6 +1657,13 @@ int sg_feat_ctl_tick_launch(uint32_t* ctl, uint32_t n, cudaStream_t st) {
 // or 4 (64 registers, a few spilled words);
 // SGB200_FEAT_OCC selects (A/B switch)
 static int g_fwd_occ = 3;
+// SGB200_FEAT_V2 (default 1): the half-warp-per-frame kernels (mfcc2_*); 0 keeps the warp-per-frame ones.  The forward ->
+// adjoint stash layout belongs to the kernel generation, so forward and adjoint always come from the same one; launches with
+// the fused CMVN (SG_OPT_CMVN_FUSION) use the V1 kernels.
+static int g_feat_v2 = 1;
+static int g_fwd2_occ = 3;       // SGB200_FEAT2_OCC: resident CTAs per SM the V2 forward is compiled for (2: 128 registers, 3: 80)
+static size_t feat2_fwd_smem() { return SG_T2_FWD_BYTES + FEAT_WARPS * F2_WARP_SCRATCH * sizeof(float); }
+static size_t feat2_bwd_smem() { return sizeof(SgFeatTables2) + (FEAT_WARPS * F2_WARP_SCRATCH + F2_GROUP * SG_WIN + F2_ACC_RING) * sizeof(float); }
 
 int sg_feat_init() {
   if (const char* e = getenv("SGB200_FEAT_OCC")) g_fwd_occ = atoi(e) == 4 ? 4 : 3;
@@ -1015,6 +1673,12 @@ int sg_feat_init() {
   SG_CUDA_CHECK(cudaFuncSetAttribute(mfcc_fwd_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)feat_fwd_smem()));
   SG_CUDA_CHECK(cudaFuncSetAttribute(mfcc_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)feat_bwd_smem()));
   SG_CUDA_CHECK(cudaFuncSetAttribute(mfcc_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)feat_bwd_smem()));
+  if (const char* e = getenv("SGB200_FEAT_V2")) g_feat_v2 = atoi(e) != 0;
+  if (const char* e = getenv("SGB200_FEAT2_OCC")) g_fwd2_occ = atoi(e) == 2 ? 2 : 3;
+  SG_CUDA_CHECK(cudaFuncSetAttribute(mfcc2_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)feat2_fwd_smem()));
+  SG_CUDA_CHECK(cudaFuncSetAttribute(mfcc2_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)feat2_fwd_smem()));
+  SG_CUDA_CHECK(cudaFuncSetAttribute(mfcc2_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)feat2_bwd_smem()));
+  SG_CUDA_CHECK(cudaFuncSetAttribute(mfcc2_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)feat2_bwd_smem()));
   return SG_OK;
 }
 
@@ -1040,6 +1704,15 @@ int sg_feat_fwd_launch(const SgFeatTables* dT, const float* x, int B, int N, int
     SG_LAUNCH_CHECK();
     return SG_OK;
   }
+  if (g_feat_v2) {
+    int fpc = 64;
+    while (fpc > 16 && (long long)B * ((m + fpc - 1) / fpc) < 592) fpc >>= 1;
+    dim3 grid((m + fpc - 1) / fpc, B);
+    if (g_fwd2_occ == 2) mfcc2_fwd_kernel<2><<<grid, FEAT_THREADS, feat2_fwd_smem(), st>>>(x, N, m, fpc, make_dither(mode, dither, seed, pass), raw, ld, dT, stash);
+    else mfcc2_fwd_kernel<3><<<grid, FEAT_THREADS, feat2_fwd_smem(), st>>>(x, N, m, fpc, make_dither(mode, dither, seed, pass), raw, ld, dT, stash);
+    SG_LAUNCH_CHECK();
+    return SG_OK;
+  }
   CmvnScratch cm; cm.part = nullptr; cm.count = nullptr;
   int fpc = 64;
   while (fpc > 8 && (long long)B * ((m + fpc - 1) / fpc) < 592) fpc >>= 1;   // >= 4 CTAs per SM when possible
@@ -1060,6 +1733,21 @@ static int bwd_own_frames(int B, int m) {
   return (m + chunks - 1) / chunks;
 }
 
+static int bwd_dispatch(const SgFeatTables* dT, const float* x, int B, int N, int m, DitherSpec D, const float* draw, int ld, const BwdOut& O,
+                        const float* stash, cudaStream_t st) {
+  const int own = bwd_own_frames(B, m);
+  dim3 grid((m + own - 1) / own, B);
+  if (g_feat_v2 && !O.cmvn) {
+    if (stash) mfcc2_bwd_kernel<true><<<grid, FEAT_THREADS, feat2_bwd_smem(), st>>>(x, N, m, own, D, draw, ld, O, dT, stash);
+    else mfcc2_bwd_kernel<false><<<grid, FEAT_THREADS, feat2_bwd_smem(), st>>>(x, N, m, own, D, draw, ld, O, dT, nullptr);
+  } else {
+    if (stash) mfcc_bwd_kernel<true><<<grid, FEAT_THREADS, feat_bwd_smem(), st>>>(x, N, m, own, D, draw, ld, O, dT, stash);
+    else mfcc_bwd_kernel<false><<<grid, FEAT_THREADS, feat_bwd_smem(), st>>>(x, N, m, own, D, draw, ld, O, dT, nullptr);
+  }
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+
 int sg_feat_bwd_launch(const SgFeatTables* dT, const float* x, int B, int N, int m, int mode, const float* dither,
                        uint64_t seed, uint64_t pass, const float* draw, int ld, float* grad, float scale,
                        int accumulate, cudaStream_t st, const float* stash, int cmvn) {
@@ -1067,14 +1755,7 @@ int sg_feat_bwd_launch(const SgFeatTables* dT, const float* x, int B, int N, int
   BwdOut O;
   memset(&O, 0, sizeof(O));
   O.mode = 0; O.grad = grad; O.scale = scale; O.accumulate = accumulate; O.cmvn = cmvn;
-  int own = bwd_own_frames(B, m);
-  dim3 grid((m + own - 1) / own, B);
-  if (stash) mfcc_bwd_kernel<true><<<grid, FEAT_THREADS, feat_bwd_smem(), st>>>(x, N, m, own, make_dither(mode, dither, seed, pass),
-                                                                            draw, ld, O, dT, stash);
-  else mfcc_bwd_kernel<false><<<grid, FEAT_THREADS, feat_bwd_smem(), st>>>(x, N, m, own, make_dither(mode, dither, seed, pass),
-                                                                         draw, ld, O, dT, nullptr);
-  SG_LAUNCH_CHECK();
-  return SG_OK;
+  return bwd_dispatch(dT, x, B, N, m, make_dither(mode, dither, seed, pass), draw, ld, O, stash, st);
 }
 
 int sg_feat_bwd_step_launch(const SgFeatTables* dT, const float* x, int B, int N, int m, int mode,
@@ -1084,19 +1765,12 @@ int sg_feat_bwd_step_launch(const SgFeatTables* dT, const float* x, int B, int N
   BwdOut O;
   memset(&O, 0, sizeof(O));
   O.mode = 1; O.x0 = x0; O.x_out = x_out; O.step = step; O.eps = eps; O.cmvn = cmvn;
-  int own = bwd_own_frames(B, m);
-  dim3 grid((m + own - 1) / own, B);
-  if (stash) mfcc_bwd_kernel<true><<<grid, FEAT_THREADS, feat_bwd_smem(), st>>>(x, N, m, own, make_dither(mode, dither, seed, pass),
-                                                                            draw, ld, O, dT, stash);
-  else mfcc_bwd_kernel<false><<<grid, FEAT_THREADS, feat_bwd_smem(), st>>>(x, N, m, own, make_dither(mode, dither, seed, pass),
-                                                                         draw, ld, O, dT, nullptr);
-  SG_LAUNCH_CHECK();
-  return SG_OK;
+  return bwd_dispatch(dT, x, B, N, m, make_dither(mode, dither, seed, pass), draw, ld, O, stash, st);
 }
 
 int sg_dither_fill_launch(int B, int m, uint64_t seed, uint64_t pass, float* out, cudaStream_t st) {
-  dim3 grid((m + 7) / 8, B);
-  dither_fill_kernel<<<grid, 256, 0, st>>>(m, make_dither(SG_DITHER_PHILOX, nullptr, seed, pass), out);
+  dim3 grid((m + 15) / 16, B);
+  dither_fill2_kernel<<<grid, 256, 0, st>>>(m, make_dither(SG_DITHER_PHILOX, nullptr, seed, pass), out);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }

@@ -19,11 +19,16 @@ def rel_rows(a, b):
     return (a - b).abs().max(1)[0] / b.abs().max(1)[0].clamp_min(1e-30)
 
 
-def resolve(grad_fn, target, tau=1e-5, max_units=48, return_grad=False):
+def resolve(grad_fn, target, tau=1e-4, max_units=96, return_grad=False):
     """grad_fn(flips) -> (grad [1,...], preacts list) for ONE utterance; target: candidate gradient.
     Greedy over the units with |pre-activation| < tau (closest to zero first): a flip is kept when it
     lowers the L2 distance to the candidate.  Returns (max-norm relative error of the best match,
-    number of near-kink units, number of flipped units[, matched gradient])."""
+    number of near-kink units, number of flipped units[, matched gradient]).
+
+    tau: the MFCC of two correct fp32 implementations (different FFT factorisations) differs by ~1e-5 of the
+    feature magnitude (C0 ~ 20..70), i.e. up to ~1e-4 in a first-layer pre-activation; units are tried closest
+    to zero first and the search stops as soon as the match is within 2e-5, so the wider band only matters
+    when a unit between 1e-5 and 1e-4 really flipped."""
     g0, pre = grad_fn(None)
     near = []
     for l, a in enumerate(pre):
