@@ -1225,16 +1225,29 @@ __device__ __forceinline__ void stash2_load_f(const float* __restrict__ sp, Fram
   F.sumsq = __ldcs(sp + S2_SUMSQ);
 }
 
-// PART 0: the forward's tables (a prefix of the struct), 1: the adjoint's (common part + tail), 2: everything
+// PART 0: the forward's tables (a prefix of the struct), 1: the adjoint's (common part + tail), 2: everything.
+// Thread 0 starts bulk asynchronous copies (cp.async.bulk, bytes counted by an mbarrier); the CTA goes on with its own
+// set-up and calls wait_tables2 after its next __syncthreads().  (A load / store loop over 13 - 22 KB per CTA was 7 % of the
+// adjoint's stall samples: four dependent L2 round trips per thread before the first frame.)
 template <int PART>
-__device__ __forceinline__ void copy_tables2(SgFeatTables2* dst, const SgFeatTables* __restrict__ src) {
-  const int4* s = reinterpret_cast<const int4*>(&src->v2);
-  int4* d = reinterpret_cast<int4*>(dst);
-  const int n0 = (int)((PART == 0 ? SG_T2_FWD_BYTES : (PART == 1 ? SG_T2_COMMON_BYTES : sizeof(SgFeatTables2))) / 16);
-  for (int i = threadIdx.x; i < n0; i += blockDim.x) d[i] = s[i];
-  if (PART == 1)
-    for (int i = (int)(SG_T2_FWD_BYTES / 16) + threadIdx.x; i < (int)(sizeof(SgFeatTables2) / 16); i += blockDim.x) d[i] = s[i];
+__device__ __forceinline__ void stage_tables2(SgFeatTables2* dst, const SgFeatTables* __restrict__ src, uint64_t* bar) {
+  if (threadIdx.x == 0) {
+    const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(bar);
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+    const char* g = reinterpret_cast<const char*>(&src->v2);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t n0 = (uint32_t)(PART == 0 ? SG_T2_FWD_BYTES : (PART == 1 ? SG_T2_COMMON_BYTES : sizeof(SgFeatTables2)));
+    const uint32_t n1 = PART == 1 ? (uint32_t)(sizeof(SgFeatTables2) - SG_T2_FWD_BYTES) : 0u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(n0 + n1) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(d), "l"(g), "r"(n0), "r"(bar_a) : "memory");
+    if (PART == 1)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(d + (uint32_t)SG_T2_FWD_BYTES), "l"(g + SG_T2_FWD_BYTES), "r"(n1), "r"(bar_a) : "memory");
+  }
 }
+__device__ __forceinline__ void wait_tables2(uint64_t* bar) { mbar_wait(bar, 0); }
 static_assert(SG_T2_FWD_BYTES % 16 == 0 && SG_T2_COMMON_BYTES % 16 == 0, "table sections must be int4-copyable");
 
 // F1 (V2): waveform -> raw MFCC
@@ -1244,9 +1257,11 @@ mfcc2_fwd_kernel(const float* __restrict__ x, int N, int m, int frames_per_cta, 
                  const SgFeatTables* __restrict__ gT, float* __restrict__ stash) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SgFeatTables2* T = reinterpret_cast<SgFeatTables2*>(smem_raw);       // only the forward's prefix of the struct is resident
-  copy_tables2<0>(T, gT);
+  __shared__ __align__(8) uint64_t tbar;
+  stage_tables2<0>(T, gT, &tbar);
   dither_resolve(D);
   __syncthreads();
+  wait_tables2(&tbar);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, hf = lane >> 4, l = lane & 15;
   float* scratch = reinterpret_cast<float*>(smem_raw + SG_T2_FWD_BYTES) + warp * F2_WARP_SCRATCH;
   float *re = F2_RE(scratch, hf), *im = F2_IM(scratch, hf), *P = re;
@@ -1318,11 +1333,13 @@ mfcc2_bwd_kernel(const float* __restrict__ x, int N, int m, int own_frames, Dith
   float* framebuf = fbase + FEAT_WARPS * F2_WARP_SCRATCH;          // [16][400]: frame gradients of the current group
   float* acc = framebuf + F2_GROUP * SG_WIN;                       // [F2_ACC_RING]: circular overlap-add accumulator
   __shared__ __align__(8) uint64_t ola_done;
-  copy_tables2<STASH ? 1 : 2>(T, gT);
+  __shared__ __align__(8) uint64_t tbar;
+  stage_tables2<STASH ? 1 : 2>(T, gT, &tbar);
   dither_resolve(D);
   for (int i = threadIdx.x; i < F2_ACC_RING; i += FEAT_THREADS) acc[i] = 0.f;
   if (threadIdx.x == 0) mbar_init(&ola_done, FEAT_THREADS);
   __syncthreads();
+  wait_tables2(&tbar);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, hf = lane >> 4, l = lane & 15;
   float* scratch = fbase + warp * F2_WARP_SCRATCH;
   float *re = F2_RE(scratch, hf), *im = F2_IM(scratch, hf), *P = re;
@@ -1661,6 +1678,8 @@ static int g_fwd_occ = 3;
 // adjoint stash layout belongs to the kernel generation, so forward and adjoint always come from the same one; launches with
 // the fused CMVN (SG_OPT_CMVN_FUSION) use the V1 kernels.
 static int g_feat_v2 = 1;
+static int g_fwd2_fpc = 64;      // SGB200_FEAT2_FPC: frames per CTA of the V2 forward (multiple of 16)
+static int g_bwd2_chunks = 0;    // SGB200_FEAT2_CHUNKS: CTAs per utterance of the V2 adjoint (0 = heuristic)
 static int g_fwd2_occ = 3;       // SGB200_FEAT2_OCC: resident CTAs per SM the V2 forward is compiled for (2: 128 registers, 3: 80)
 static size_t feat2_fwd_smem() { return SG_T2_FWD_BYTES + FEAT_WARPS * F2_WARP_SCRATCH * sizeof(float); }
 static size_t feat2_bwd_smem() { return sizeof(SgFeatTables2) + (FEAT_WARPS * F2_WARP_SCRATCH + F2_GROUP * SG_WIN + F2_ACC_RING) * sizeof(float); }
@@ -1675,6 +1694,8 @@ int sg_feat_init() {
   SG_CUDA_CHECK(cudaFuncSetAttribute(mfcc_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)feat_bwd_smem()));
   if (const char* e = getenv("SGB200_FEAT_V2")) g_feat_v2 = atoi(e) != 0;
   if (const char* e = getenv("SGB200_FEAT2_OCC")) g_fwd2_occ = atoi(e) == 2 ? 2 : 3;
+  if (const char* e = getenv("SGB200_FEAT2_FPC")) { const int v = atoi(e); if (v >= 16 && v % 16 == 0) g_fwd2_fpc = v; }
+  if (const char* e = getenv("SGB200_FEAT2_CHUNKS")) { const int v = atoi(e); if (v >= 0 && v <= 16) g_bwd2_chunks = v; }
   SG_CUDA_CHECK(cudaFuncSetAttribute(mfcc2_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)feat2_fwd_smem()));
   SG_CUDA_CHECK(cudaFuncSetAttribute(mfcc2_fwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)feat2_fwd_smem()));
   SG_CUDA_CHECK(cudaFuncSetAttribute(mfcc2_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)feat2_bwd_smem()));
@@ -1705,7 +1726,7 @@ int sg_feat_fwd_launch(const SgFeatTables* dT, const float* x, int B, int N, int
     return SG_OK;
   }
   if (g_feat_v2) {
-    int fpc = 64;
+    int fpc = g_fwd2_fpc;
     while (fpc > 16 && (long long)B * ((m + fpc - 1) / fpc) < 592) fpc >>= 1;
     dim3 grid((m + fpc - 1) / fpc, B);
     if (g_fwd2_occ == 2) mfcc2_fwd_kernel<2><<<grid, FEAT_THREADS, feat2_fwd_smem(), st>>>(x, N, m, fpc, make_dither(mode, dither, seed, pass), raw, ld, dT, stash);
@@ -1735,7 +1756,8 @@ static int bwd_own_frames(int B, int m) {
 
 static int bwd_dispatch(const SgFeatTables* dT, const float* x, int B, int N, int m, DitherSpec D, const float* draw, int ld, const BwdOut& O,
                         const float* stash, cudaStream_t st) {
-  const int own = bwd_own_frames(B, m);
+  int own = bwd_own_frames(B, m);
+  if (g_feat_v2 && !O.cmvn && g_bwd2_chunks > 0 && m / g_bwd2_chunks >= 32) own = (m + g_bwd2_chunks - 1) / g_bwd2_chunks;
   dim3 grid((m + own - 1) / own, B);
   if (g_feat_v2 && !O.cmvn) {
     if (stash) mfcc2_bwd_kernel<true><<<grid, FEAT_THREADS, feat2_bwd_smem(), st>>>(x, N, m, own, D, draw, ld, O, dT, stash);
