@@ -392,7 +392,7 @@ extern "C" long long sg_cw2_last_iterations(const sg_handle* h) { return h ? h->
 // ---------------------------------------------------------------------------------------------
 size_t sg_kmeans_smem(int n, int dim, int k);
 int sg_feco_kmeans_launch(const float* feat, int ld, int B, int n, int dim, int k, uint64_t seed, int max_iter, float tol,
-                          int* ids, cudaStream_t st);
+                          int* ids, cudaStream_t st, const uint32_t* ctl);
 int sg_feco_means_fwd_launch(const float* feat, int ld_in, const int* ids, int B, int n, int dim, int k, int force,
                              float* out, int ld_out, int* counts, cudaStream_t st);
 int sg_feco_means_bwd_launch(const float* dout, int ld_out, const int* ids, const int* counts, int B, int n, int dim, int k,
@@ -408,7 +408,7 @@ extern "C" int sg_feco_kmeans(sg_handle* h, const float* feat, int ld, int B, in
   SG_TRY(feco_check(h, B, n, dim, k));
   if (!feat || !ids || ld < dim || max_iter < 1) { sg_set_error("sg_feco_kmeans: bad argument"); return SG_EINVAL; }
   h->launches += 1;
-  return sg_feco_kmeans_launch(feat, ld, B, n, dim, k, seed, max_iter, tol, (int*)ids, (cudaStream_t)stream);
+  return sg_feco_kmeans_launch(feat, ld, B, n, dim, k, seed, max_iter, tol, (int*)ids, (cudaStream_t)stream, nullptr);
 }
 extern "C" int sg_feco_means_fwd(sg_handle* h, const float* feat, int ld, const int32_t* ids, int B, int n, int dim, int k,
                                  int force, float* out, int32_t* counts, sg_stream stream) {

@@ -6,6 +6,7 @@
 // One CTA per utterance: frames and centroids live in shared memory for the whole run (n x dim and
 // k x dim floats), so HBM traffic is one read of the features and one write of ids / means.
 #include <math.h>
+#include <stdlib.h>
 
 #include "sg_common.cuh"
 
@@ -115,6 +116,220 @@ feco_kmeans_kernel(const float* __restrict__ feat, int ld, int n, int dim, int k
   for (int j = tid; j < n; j += KM_THREADS) ids_out[(size_t)b * n + j] = ids[j];
 }
 
+
+// ---- second version: the same algorithm with the serial parts removed -----------------------------------------------------
+// (the kernel above is kept for utterances whose padded working set does not fit: it needs 120 bytes per frame, this one 152)
+//  * assignment step on the tensor cores: the n x k matrix of ||c||^2 - 2 x.c is formed 16 frames x 8 centroids at a time
+//    with mma.sync m16n8k8 in error-compensated TF32 (x = hi + lo, c = hi + lo, products lo.hi + hi.lo + hi.hi accumulated
+//    in fp32: ~2^-21 relative, so the arg-min is the fp32 one up to exact ties, which go to the lower index as before);
+//    frames / centroids are padded to 32 floats with a row stride of 36 (fragment loads are bank-conflict free);
+//  * k-means++ sampling by a warp prefix scan instead of thread 0 walking the n distances (k = n / 2 rounds of it);
+//  * centroid update through per-cluster member lists (members in increasing frame order: deterministic sums):
+//    k x n id comparisons + k x 32 short sums, where thread c used to scan all n frames once per dimension.
+#define KM_DP 36
+__device__ __forceinline__ uint32_t km_tf32(float x) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return r; }
+__device__ __forceinline__ void km_mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__global__ void __launch_bounds__(KM_THREADS)
+feco_kmeans2_kernel(const float* __restrict__ feat, int ld, int n, int dim, int k, uint32_t seed_lo, uint32_t seed_hi,
+                    const uint32_t* __restrict__ ctl, int max_iter, float tol, int* __restrict__ ids_out) {
+  extern __shared__ __align__(16) float sm[];
+  float* X = sm;                                         // [n][36]
+  float* Cn = X + (size_t)n * KM_DP;                     // [k8][36], k8 = k rounded up to 8 (padding rows zero)
+  const int k8 = (k + 7) & ~7;
+  float* mind = Cn + (size_t)k8 * KM_DP;                 // [n]
+  float* cn2 = mind + n;                                 // [k8]: ||c||^2, +inf for the padding centroids
+  uint32_t* Ch = reinterpret_cast<uint32_t*>(cn2 + k8);  // [k8][36]: tf32(c)
+  uint32_t* Cl = Ch + (size_t)k8 * KM_DP;                // [k8][36]: tf32(c - tf32(c))
+  int* ids = reinterpret_cast<int*>(Cl + (size_t)k8 * KM_DP);   // [n]
+  int* cnt = ids + n;                                    // [k]
+  int* off = cnt + k;                                    // [k + 1]
+  int* list = off + k + 1;                               // [n]
+  __shared__ int s_pick;
+  __shared__ int s_changed;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (ctl != nullptr) { seed_lo ^= __ldg(ctl) * 0x9E3779B9u; seed_hi += __ldg(ctl + 1) ^ __ldg(ctl + 2); }   // per-pass clustering (graph replay)
+  const float* fb = feat + (size_t)b * n * ld;
+  for (int i = tid; i < n * KM_DP; i += KM_THREADS) {
+    const int j = i / KM_DP, d = i - j * KM_DP;
+    X[i] = d < dim ? fb[(size_t)j * ld + d] : 0.f;
+  }
+  for (int i = tid; i < k8 * KM_DP; i += KM_THREADS) Cn[i] = 0.f;
+  if (tid == 0) s_pick = (int)(km_hash(seed_lo, seed_hi, (uint32_t)b, 0u) % (uint32_t)n);
+  __syncthreads();
+
+  // ---- k-means++ seeding ----
+  const int chunk = (n + 31) / 32;                       // sampling: lane l owns frames [l * chunk, (l + 1) * chunk)
+  for (int c = 0; c < k; ++c) {
+    const float4* cp = reinterpret_cast<const float4*>(X + (size_t)s_pick * KM_DP);
+    float4 cv[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) cv[g] = cp[g];
+    if (warp == 1 && lane < 8) reinterpret_cast<float4*>(Cn + (size_t)c * KM_DP)[lane] = cv[lane];
+    for (int j = tid; j < n; j += KM_THREADS) {
+      const float4* xp = reinterpret_cast<const float4*>(X + (size_t)j * KM_DP);
+      float s = 0.f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const float4 x = xp[g];
+        float t = x.x - cv[g].x; s = fmaf(t, t, s);
+        t = x.y - cv[g].y; s = fmaf(t, t, s);
+        t = x.z - cv[g].z; s = fmaf(t, t, s);
+        t = x.w - cv[g].w; s = fmaf(t, t, s);
+      }
+      mind[j] = (c == 0) ? s : fminf(mind[j], s);
+    }
+    __syncthreads();
+    if (c + 1 < k && warp == 0) {
+      // frame j with probability mind[j] / total: lane sums of consecutive chunks, warp prefix, then a walk inside one chunk
+      const int j0 = lane * chunk, j1 = min(n, j0 + chunk);
+      float part = 0.f;
+      for (int j = j0; j < j1; ++j) part += mind[j];
+      float incl = part;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const float v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+      const float total = __shfl_sync(0xffffffffu, incl, 31);
+      const float u = (km_hash(seed_lo, seed_hi, (uint32_t)b, (uint32_t)(c + 1)) >> 8) * (1.0f / 16777216.0f);
+      const float r = u * total;
+      const unsigned hit = __ballot_sync(0xffffffffu, incl > r);
+      const int owner = hit ? __ffs(hit) - 1 : 31;
+      if (lane == owner) {
+        float acc = incl - part;
+        int sel = j1 - 1;
+        for (int j = j0; j < j1; ++j) { acc += mind[j]; if (acc > r) { sel = j; break; } }
+        s_pick = max(0, min(sel, n - 1));
+      }
+    }
+    __syncthreads();
+  }
+  for (int j = tid; j < n; j += KM_THREADS) ids[j] = -1;
+  __syncthreads();
+
+  // ---- Lloyd iterations ----
+  const int g8 = lane >> 2, t4 = lane & 3;
+  const int m_tiles = (n + 15) >> 4, n_tiles = k8 >> 3;
+  for (int it = 0; it < max_iter; ++it) {
+    if (tid == 0) s_changed = 0;
+    for (int c = tid; c < k; c += KM_THREADS) cnt[c] = 0;
+    for (int c = tid; c < k8; c += KM_THREADS) {
+      float s = INFINITY;
+      if (c < k) {
+        const float4* cp = reinterpret_cast<const float4*>(Cn + (size_t)c * KM_DP);
+        s = 0.f;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) { const float4 v = cp[g]; s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s); s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s); }
+      }
+      cn2[c] = s;
+    }
+    for (int i = tid; i < k8 * KM_DP; i += KM_THREADS) {              // the split is the same for every frame tile: once per iteration
+      const float v = Cn[i];
+      const uint32_t h = km_tf32(v);
+      Ch[i] = h; Cl[i] = km_tf32(v - __uint_as_float(h));
+    }
+    __syncthreads();
+    // assignment: warp w takes the 16-frame tiles w, w + 8, ...
+    int changed = 0;
+    for (int mt = warp; mt < m_tiles; mt += KM_THREADS / 32) {
+      const int r0 = min(mt * 16 + g8, n - 1), r1 = min(mt * 16 + g8 + 8, n - 1);      // rows beyond n repeat the last frame (results dropped)
+      uint32_t ah[4][4], al[4][4];
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const float v[4] = {X[r0 * KM_DP + 8 * ks + t4], X[r1 * KM_DP + 8 * ks + t4], X[r0 * KM_DP + 8 * ks + t4 + 4], X[r1 * KM_DP + 8 * ks + t4 + 4]};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { ah[ks][e] = km_tf32(v[e]); al[ks][e] = km_tf32(v[e] - __uint_as_float(ah[ks][e])); }
+      }
+      float bv0 = INFINITY, bv1 = INFINITY;
+      int bi0 = 0, bi1 = 0;
+      for (int nt = 0; nt < n_tiles; ++nt) {
+        const size_t co = (size_t)(nt * 8 + g8) * KM_DP + t4;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint32_t h0 = Ch[co + 8 * ks], h1 = Ch[co + 8 * ks + 4], l0 = Cl[co + 8 * ks], l1 = Cl[co + 8 * ks + 4];
+          km_mma(acc, al[ks], h0, h1);
+          km_mma(acc, ah[ks], l0, l1);
+          km_mma(acc, ah[ks], h0, h1);
+        }
+        const int cA = nt * 8 + 2 * t4;
+        const float n0 = cn2[cA], n1 = cn2[cA + 1];
+        const float d00 = fmaf(-2.f, acc[0], n0), d01 = fmaf(-2.f, acc[1], n1), d10 = fmaf(-2.f, acc[2], n0), d11 = fmaf(-2.f, acc[3], n1);
+        if (d00 < bv0) { bv0 = d00; bi0 = cA; }
+        if (d01 < bv0) { bv0 = d01; bi0 = cA + 1; }
+        if (d10 < bv1) { bv1 = d10; bi1 = cA; }
+        if (d11 < bv1) { bv1 = d11; bi1 = cA + 1; }
+      }
+#pragma unroll
+      for (int o = 1; o <= 2; o <<= 1) {                 // the four lanes of a quad hold the row's other columns
+        const float ov0 = __shfl_xor_sync(0xffffffffu, bv0, o), ov1 = __shfl_xor_sync(0xffffffffu, bv1, o);
+        const int oi0 = __shfl_xor_sync(0xffffffffu, bi0, o), oi1 = __shfl_xor_sync(0xffffffffu, bi1, o);
+        if (ov0 < bv0 || (ov0 == bv0 && oi0 < bi0)) { bv0 = ov0; bi0 = oi0; }
+        if (ov1 < bv1 || (ov1 == bv1 && oi1 < bi1)) { bv1 = ov1; bi1 = oi1; }
+      }
+      if (t4 == 0) {
+        const int j0 = mt * 16 + g8, j1 = j0 + 8;
+        if (j0 < n) { if (ids[j0] != bi0) { ids[j0] = bi0; ++changed; } atomicAdd(&cnt[bi0], 1); }   // counts only: order-free
+        if (j1 < n) { if (ids[j1] != bi1) { ids[j1] = bi1; ++changed; } atomicAdd(&cnt[bi1], 1); }
+      }
+    }
+    if (changed) atomicAdd(&s_changed, changed);
+    __syncthreads();
+    // member lists (members in increasing frame order): warp 0 forms the exclusive prefix of the counts, then walks the frames
+    // 32 at a time; lanes with the same cluster id find each other with match.any, take consecutive slots behind the
+    // cluster's cursor (cnt is reused as the cursor), and the lowest of them advances it
+    if (warp == 0) {
+      const int per = (k + 31) / 32, c0 = lane * per, c1 = min(k, c0 + per);
+      int part = 0;
+      for (int c = c0; c < c1; ++c) part += cnt[c];
+      int incl = part;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+      int run = incl - part;
+      for (int c = c0; c < c1; ++c) { const int m = cnt[c]; off[c] = run; cnt[c] = run; run += m; }
+      if (lane == 31) off[k] = incl;
+      __syncwarp();
+      for (int j0 = 0; j0 < n; j0 += 32) {
+        const int j = j0 + lane;
+        const int id = j < n ? ids[j] : -1 - lane;                  // idle lanes: unique ids, no partners
+        const unsigned peers = __match_any_sync(0xffffffffu, id);
+        const int rank = __popc(peers & ((1u << lane) - 1u));
+        const int base = j < n ? cnt[id] : 0;
+        __syncwarp();                                               // every cursor read before any cursor update
+        if (j < n) {
+          list[base + rank] = j;
+          if (rank == 0) cnt[id] = base + __popc(peers);
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    // centroid = mean of the members, summed in list (= frame) order; an empty cluster keeps its centroid
+    for (int w = tid; w < k * 8; w += KM_THREADS) {
+      const int c = w >> 3, g = w & 7;
+      const int o0 = off[c], m = off[c + 1] - o0;
+      if (m > 0) {
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < m; ++i) {
+          const float4 x = reinterpret_cast<const float4*>(X + (size_t)list[o0 + i] * KM_DP)[g];
+          s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
+        }
+        const float inv = (float)m;
+        reinterpret_cast<float4*>(Cn + (size_t)c * KM_DP)[g] = make_float4(s.x / inv, s.y / inv, s.z / inv, s.w / inv);
+      }
+    }
+    __syncthreads();
+    if ((float)s_changed <= tol * (float)n) break;                  // uniform: s_changed is shared
+    __syncthreads();
+  }
+  for (int j = tid; j < n; j += KM_THREADS) ids_out[(size_t)b * n + j] = ids[j];
+}
+
+static size_t kmeans2_smem(int n, int k) {
+  const size_t k8 = ((size_t)k + 7) & ~(size_t)7;
+  return ((size_t)n * KM_DP + 3 * k8 * KM_DP + n + k8) * sizeof(float) + ((size_t)n + k + k + 1 + n) * sizeof(int);
+}
+
 // out[b,i,:] = mean of feat[b, ids==i, :]; empty cluster -> feat[b,i,:] when force (feature_level.py:205-216)
 __global__ void feco_means_fwd_kernel(const float* __restrict__ feat, int ld_in, const int* __restrict__ ids, int n, int dim,
                                       int k, int force, float* __restrict__ out, int ld_out, int* __restrict__ counts) {
@@ -149,8 +364,19 @@ size_t sg_kmeans_smem(int n, int dim, int k) {
   return ((size_t)n * dim + (size_t)k * dim + n) * sizeof(float) + ((size_t)n + k) * sizeof(int) + 40 * sizeof(float);
 }
 
+// ctl: optional device control block {pass, seed_lo, seed_hi} mixed into the seed (CUDA-graph replay of the fused attack loop)
 int sg_feco_kmeans_launch(const float* feat, int ld, int B, int n, int dim, int k, uint64_t seed, int max_iter, float tol,
-                          int* ids, cudaStream_t st) {
+                          int* ids, cudaStream_t st, const uint32_t* ctl) {
+  static int use_v2 = -1;
+  if (use_v2 < 0) { const char* e = getenv("SGB200_KMEANS_V2"); use_v2 = e ? atoi(e) != 0 : 1; }
+  const size_t smem2 = kmeans2_smem(n, k);
+  if (use_v2 && dim <= 32 && smem2 <= 220 * 1024) {
+    SG_CUDA_CHECK(cudaFuncSetAttribute(feco_kmeans2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    feco_kmeans2_kernel<<<B, KM_THREADS, smem2, st>>>(feat, ld, n, dim, k, (uint32_t)seed, (uint32_t)(seed >> 32), ctl, max_iter, tol, ids);
+    SG_LAUNCH_CHECK();
+    return SG_OK;
+  }
+  if (ctl) { sg_set_error("FeCo k-means inside the fused loop needs the shared-memory kernel (n=%d k=%d)", n, k); return SG_EUNSUPPORTED; }
   const size_t smem = sg_kmeans_smem(n, dim, k);
   if (smem > 200 * 1024) { sg_set_error("FeCo k-means: utterance too long for the shared-memory kernel (n=%d dim=%d k=%d)", n, dim, k); return SG_EUNSUPPORTED; }
   SG_CUDA_CHECK(cudaFuncSetAttribute(feco_kmeans_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
