@@ -192,6 +192,18 @@ typedef struct {
                          asked for, not the loss that is finally used: task SV / OSI with loss='Entropy' runs the margin
                          loss but keeps the cross-entropy sign (+1 untargeted, -1 targeted).  0 = derive it from `loss`
                          (CE: +1 / -1 by `targeted`; margin: -1), which is only right when name and loss agree. */
+  /* EOT samples as batch rows (adaptive_attack/EOT.py:30-42: x_batch.repeat(EOT_batch_size, 1, 1)): eot_batch copies of the
+   * batch run through one pass as B * eot_batch rows, row e * B + b = copy e of utterance b, each with its own dither and its
+   * own FeCo clustering; eot_size / eot_batch passes per iteration.  0 or 1 = one copy per pass.  The workspace must then be
+   * sized by sg_pgd_ws_bytes(h, B * eot_batch, N).  Needs dither_mode OFF or PHILOX. */
+  int eot_batch;
+  /* FeCo feature compression between the raw MFCC and CMVN (model/defended_model.py:46-65 with defense = [[1, FeCo]],
+   * defense/feature_level.py:18-50): k = (int)(frames * feco_ratio) cluster means per utterance, clustering re-drawn for
+   * every pass (the randomness EOT averages over).  feco_ratio 0 = no defense.  Needs >= 2 rows per pass (the reference
+   * drops empty clusters for a batch of one, which changes the frame count). */
+  float feco_ratio;
+  int feco_max_iter;  /* Lloyd iteration cap (kmeans_ids default: 100) */
+  float feco_tol;     /* stop when <= feco_tol * frames change cluster (libKMCUDA default: 0.01) */
 } sg_pgd_params;
 size_t sg_pgd_ws_bytes(const sg_handle* h, int B, int N);
 int sg_pgd_run(sg_handle* h, float* x_adv, const float* x0, const int64_t* y, const float* dither,
@@ -416,7 +428,8 @@ int sg_debug_conv(sg_handle* h, int precision, const float* A, int lda, const fl
 enum { SG_PROF_MFCC_FWD = 0, SG_PROF_MFCC_BWD, SG_PROF_CMVN, SG_PROF_TDNN_FWD, SG_PROF_TDNN_BWD,
        SG_PROF_POOL, SG_PROF_HEAD_GEMM, SG_PROF_HEAD, SG_PROF_LOSS, SG_PROF_STEP, SG_PROF_AUDIONET,
        SG_PROF_CW2, SG_PROF_IV_GEMM, SG_PROF_IV,
-       SG_PROF_TDNN_BWD_POOL /* layer-5 dgrad with the pooling adjoint fused in (SG_OPT_POOL_FUSION) */, SG_PROF_COUNT };
+       SG_PROF_TDNN_BWD_POOL /* layer-5 dgrad with the pooling adjoint fused in (SG_OPT_POOL_FUSION) */,
+       SG_PROF_FECO /* FeCo k-means, cluster means and their adjoint inside sg_pgd_run */, SG_PROF_COUNT };
 int sg_profile_enable(sg_handle* h, int enable);
 int sg_profile_read(sg_handle* h, int category, double* total_ms, long long* launches);
 const char* sg_profile_name(int category);

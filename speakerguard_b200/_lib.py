@@ -17,7 +17,7 @@ PREC_FP32, PREC_TF32, PREC_BF16 = 0, 1, 2
 DITHER_OFF, DITHER_TENSOR, DITHER_PHILOX = 0, 1, 2
 OPT_POOL_FUSION, OPT_FEAT_STASH, OPT_L1_TAP_FORM, OPT_UTT_OFFSET, OPT_CUDA_GRAPH, OPT_CMVN_FUSION, OPT_ROW_COMPACTION = 1, 2, 3, 4, 5, 6, 7
 LOSS_CE, LOSS_MARGIN = 0, 1
-PROF_COUNT = 15
+PROF_COUNT = 16
 IV_STAGE_POST, IV_STAGE_STATS, IV_STAGE_IVECTOR = 0, 1, 2
 TASK_CSI, TASK_SV, TASK_OSI = 0, 1, 2
 TASKS = {"CSI": TASK_CSI, "SV": TASK_SV, "OSI": TASK_OSI}
@@ -67,7 +67,8 @@ class Cw2Params(C.Structure):
 class PgdParams(C.Structure):
     _fields_ = [("max_iter", C.c_int), ("epsilon", C.c_float), ("step_size", C.c_float), ("eot_size", C.c_int),
                 ("dither_mode", C.c_int), ("seed", C.c_uint64), ("loss", LossParams),
-                ("decision_threshold", C.c_float), ("grad_sign", C.c_float)]
+                ("decision_threshold", C.c_float), ("grad_sign", C.c_float), ("eot_batch", C.c_int),
+                ("feco_ratio", C.c_float), ("feco_max_iter", C.c_int), ("feco_tol", C.c_float)]
 
 
 # name -> (restype, argtypes); must list every symbol include/sgb200.h declares

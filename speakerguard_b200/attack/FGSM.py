@@ -19,16 +19,29 @@ from ..adaptive_attack.EOT import EOT
 from ..model.utils import known_input_range
 from ..engine import default_engine, grad_sign_of, make_loss_params
 from .Attack import Attack
+from .. import _lib
 from .utils import resolve_loss, resolve_prediction
 
 
 def fused_target(model):
-    """The engine-backed xv_plda behind ``model`` if the fused loop applies, else None."""
-    from ..model.defended_model import defended_model
+    """(xv, feco): the engine-backed xv_plda behind ``model`` if the fused loop applies (else None), and the FeCoDefense the
+    loop has to run between the raw MFCC and CMVN (None for an undefended model).  Fusable defended models: no defense, or
+    exactly one FeCoDefense (k-means, L2) at the raw-feature level, combined sequentially."""
+    from ..defense.feature_level import FeCoDefense
+    from ..model.defended_model import defended_model, sequential
     from ..model.xv_plda import xv_plda
-    if isinstance(model, defended_model) and model.defense is None:
+    feco = None
+    if isinstance(model, defended_model):
+        if model.defense is not None:
+            d = model.defense
+            if not (len(d) == 1 and d[0][0] == 1 and isinstance(d[0][1], FeCoDefense) and d[0][1].fusable()
+                    and getattr(model, "order", sequential) == sequential):
+                return None, None
+            feco = d[0][1]
         model = model.base_model
-    return model if isinstance(model, xv_plda) and model.engine_enroll_current() else None
+    if isinstance(model, xv_plda) and model.engine_enroll_current():
+        return model, feco
+    return None, None
 
 
 class FGSM(Attack):
@@ -95,7 +108,7 @@ class FGSM(Attack):
         return x_batch, success
 
     # ---- fused path -----------------------------------------------------------------------------
-    def _fused_batch(self, xv, x_batch, x0_batch, y_batch, epsilon, batch_id, batch_offset=0):
+    def _fused_batch(self, xv, x_batch, x0_batch, y_batch, epsilon, batch_id, batch_offset=0, feco=None):
         eng = xv.engine
         B, _, N = x_batch.shape
         xa = x_batch[:, 0, :].detach().to(torch.float32).contiguous().clone()
@@ -103,11 +116,17 @@ class FGSM(Attack):
         E = self.EOT_size
         mode, dither, seed = xv.fused_dither(self.max_iter * E + 1, B, N)
         lp = make_loss_params(self.loss_name, self.targeted, self.task, 0.0, self.threshold, False)
+        # EOT copies as batch rows (EOT.py:30-42): the largest divisor of E that is <= EOT_batch_size and keeps a pass at
+        # <= 2048 rows (the workspace is ~25 KB per frame and row); one copy per pass with a dither tensor or a loss history
+        eb = 1
+        if E > 1 and mode != _lib.DITHER_TENSOR and not self.verbose:
+            eb = max(d for d in range(1, self.EOT_batch_size + 1) if E % d == 0 and (d == 1 or B * d <= 2048))
+        fk = {} if feco is None else dict(feco_ratio=feco.param, feco_max_iter=feco.max_iter, feco_tol=feco.tol)
         dec, scores, hist = eng.pgd_run(xa, x0, y_batch, max_iter=self.max_iter, epsilon=epsilon,
                                         step_size=self.step_size, lp=lp, dither_mode=mode, dither=dither, seed=seed,
-                                        eot_size=E, decision_threshold=xv.decision_threshold,
+                                        eot_size=E, eot_batch=eb, decision_threshold=xv.decision_threshold,
                                         want_loss_hist=bool(self.verbose), grad_sign=float(self.grad_sign),
-                                        utt_offset=self.utt_offset + batch_offset)
+                                        utt_offset=self.utt_offset + batch_offset, **fk)
         predict = dec.cpu().numpy()                              # the only host sync of the attack
         target = y_batch.detach().cpu().numpy()
         if self.verbose:
@@ -140,13 +159,13 @@ class FGSM(Attack):
         n_audios = x.shape[0]
         batch_size = min(self.batch_size, n_audios)
         n_batches = int(np.ceil(n_audios / float(batch_size)))
-        xv = fused_target(self.model) if self.use_fused else None
+        xv, feco = fused_target(self.model) if self.use_fused else (None, None)
         adver, success = [], []
         for b in range(n_batches):
             sl = slice(b * batch_size, (b + 1) * batch_size)
             bid = '{}{}'.format(tag, b)
-            if xv is not None:
-                a, s = self._fused_batch(xv, x[sl], x0[sl], y[sl], epsilon, bid, batch_offset=b * batch_size)
+            if xv is not None and (feco is None or x[sl].shape[0] >= 2):      # FeCo on a batch of one drops empty clusters: generic path
+                a, s = self._fused_batch(xv, x[sl], x0[sl], y[sl], epsilon, bid, batch_offset=b * batch_size, feco=feco)
             else:
                 a, s = self.attack_batch(x[sl], y[sl], lower[sl], upper[sl], bid, x0_batch=x0[sl].detach().contiguous(),
                                          epsilon=epsilon)

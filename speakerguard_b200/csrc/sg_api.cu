@@ -34,7 +34,7 @@ static const int kCout[5] = {512, 512, 512, 512, 1500};
 static const int kCoutP[5] = {512, 512, 512, 512, SG_C5P};
 
 static const char* kProfNames[SG_PROF_COUNT] = {
-    "mfcc_fwd", "mfcc_bwd", "cmvn", "tdnn_fwd", "tdnn_dgrad", "pool", "head_gemm", "head", "loss", "step", "audionet", "cw2", "iv_gemm", "iv", "tdnn_dgrad5_pool"};
+    "mfcc_fwd", "mfcc_bwd", "cmvn", "tdnn_fwd", "tdnn_dgrad", "pool", "head_gemm", "head", "loss", "step", "audionet", "cw2", "iv_gemm", "iv", "tdnn_dgrad5_pool", "feco"};
 
 int sg_dev_upload(sg_handle* h, float** dst, const std::vector<float>& src) {
   SG_CUDA_CHECK(cudaMalloc((void**)dst, src.size() * sizeof(float)));
@@ -80,6 +80,7 @@ extern "C" int sg_create(sg_handle** out, int device) {
   if (ce != cudaSuccess) { sg_set_error("sg_create: table upload failed: %s", cudaGetErrorString(ce)); delete h; return SG_ECUDA; }
   h->allocs.push_back(h->d_tables);
   r = sg_feat_init();
+  if (r == SG_OK) r = sg_kmeans_init();
   if (r == SG_OK) r = sg_conv_tc_warm();
   if (r != SG_OK) { sg_destroy(h); return r; }
   *out = h;
@@ -309,6 +310,8 @@ struct XvWs {
   float *xbuf2, *x0c;               // graph replay: the iterate ping-pongs between xbuf / xbuf2, x0 and y are copied in so that
   long long *dec, *yc;              // the captured kernels only reference workspace addresses
   uint32_t* ctl;                    // {pass, seed_lo, seed_hi} read by the MFCC kernels
+  float* xtile;                     // EOT samples as batch rows: the iterate repeated eot_batch times
+  int *km_ids, *km_cnt;             // FeCo inside the loop: cluster ids [B][m], member counts [B][k]
   size_t bytes;
 };
 
@@ -334,7 +337,7 @@ static XvWs xv_ws_layout(void* base, int B, int T, int Lp, int L, int S, bool at
   w.splitk_floats = (size_t)8 * ((B + 127) / 128) * 128 * SG_EMB;
   w.splitk = take(w.splitk_floats);
   w.raw = w.draw = w.feat = w.dfeat = w.emb = w.demb = w.scores = w.dscores = w.loss = w.xbuf = w.grad = w.stash = nullptr;
-  w.dec = w.yc = nullptr; w.xbuf2 = w.x0c = nullptr; w.ctl = nullptr;
+  w.dec = w.yc = nullptr; w.xbuf2 = w.x0c = nullptr; w.ctl = nullptr; w.xtile = nullptr; w.km_ids = w.km_cnt = nullptr;
   if (attack) {
     w.raw = take(R * SG_FLD); w.draw = take(R * SG_FLD); w.feat = take(R * SG_FLD); w.dfeat = take(R * SG_FLD);
     w.emb = take((size_t)B * L); w.demb = take((size_t)B * L);
@@ -344,6 +347,8 @@ static XvWs xv_ws_layout(void* base, int B, int T, int Lp, int L, int S, bool at
     w.stash = take(sg_feat_stash_floats(B, T));      // forward -> adjoint hand-over of the MFCC kernels
     w.xbuf2 = take((size_t)B * N); w.x0c = take((size_t)B * N);
     w.yc = (long long*)take((size_t)B * 2); w.ctl = (uint32_t*)take(64);
+    w.xtile = take((size_t)B * N);
+    w.km_ids = (int*)take(R); w.km_cnt = (int*)take(R);
   }
   w.bytes = off;
   return w;
@@ -660,10 +665,29 @@ static int cmvn_scratch_reserve(sg_handle* h, int B) {
   return SG_OK;
 }
 
+// FeCo inside the loop (sg_pgd_params::feco_ratio): k cluster means per utterance replace the m raw frames
+struct FecoSpec {
+  int k;                  // 0: no defense
+  int max_iter; float tol;
+  uint64_t seed;
+  uint32_t pass;          // pass index of the run (graph replay: the round inside the iteration, the control block adds the rest):
+  const uint32_t* ctl;    // the kernel draws a fresh clustering per pass
+};
+static const FecoSpec kNoFeco = {0, 0, 0.f, 0, 0, nullptr};
+
 static int forward_pass(sg_handle* h, const float* x, int B, int N, int m, int mode, const float* dither, uint64_t seed,
                         uint64_t pass, float thr, const XvWs& w, float* emb, float* scores, long long* dec, cudaStream_t st,
-                        float* stash = nullptr) {
-  if (h->cmvn_fusion && sg_feat_cmvn_fusable(m)) {
+                        float* stash = nullptr, const FecoSpec& fc = kNoFeco) {
+  int T = m;                                                       // frames the TDNN sees
+  if (fc.k > 0) {
+    // raw MFCC -> k-means ids -> cluster means (w.draw as the staging tensor: free in the forward) -> CMVN over the k means
+    h->launches += 5;
+    PROF(h, SG_PROF_MFCC_FWD, st, sg_feat_fwd_launch(h->d_tables, x, B, N, m, mode, dither, seed, dither_pass(h, pass), w.raw, SG_FLD, st, stash));
+    PROF(h, SG_PROF_FECO, st, sg_feco_kmeans_launch(w.raw, SG_FLD, B, m, SG_NCEP, fc.k, fc.seed, fc.max_iter, fc.tol, w.km_ids, st, fc.ctl, fc.pass));
+    PROF(h, SG_PROF_FECO, st, sg_feco_means_fwd_launch(w.raw, SG_FLD, w.km_ids, B, m, SG_NCEP, fc.k, 1, w.draw, SG_FLD, w.km_cnt, st));
+    PROF(h, SG_PROF_CMVN, st, sg_cmvn_launch(w.draw, SG_FLD, w.feat, SG_FLD, B, fc.k, 0, st));
+    T = fc.k;
+  } else if (h->cmvn_fusion && sg_feat_cmvn_fusable(m)) {
     // CMVN inside the MFCC kernel (one CTA cluster per utterance): no raw-feature round trip, one launch less
     h->launches += 2;
     PROF(h, SG_PROF_MFCC_FWD, st, sg_feat_fwd_launch(h->d_tables, x, B, N, m, mode, dither, seed, dither_pass(h, pass), w.feat, SG_FLD, st, stash, 1,
@@ -673,7 +697,7 @@ static int forward_pass(sg_handle* h, const float* x, int B, int N, int m, int m
     PROF(h, SG_PROF_MFCC_FWD, st, sg_feat_fwd_launch(h->d_tables, x, B, N, m, mode, dither, seed, dither_pass(h, pass), w.raw, SG_FLD, st, stash));
     PROF(h, SG_PROF_CMVN, st, sg_cmvn_launch(w.raw, SG_FLD, w.feat, SG_FLD, B, m, 0, st));
   }
-  SG_TRY(embed_fwd(h, w.feat, B, m, w, emb, st));
+  SG_TRY(embed_fwd(h, w.feat, B, T, w, emb, st));
   PROF(h, SG_PROF_HEAD, st, sg_score_fwd_launch(h->H, emb, B, h->enroll, h->S, thr, scores, dec, st));
   return SG_OK;
 }
@@ -690,29 +714,57 @@ extern "C" int sg_xv_forward(sg_handle* h, const float* x, int B, int N, int dit
                       (long long*)decisions, (cudaStream_t)stream);
 }
 
-// One PGD iteration (attack/FGSM.py:44-68 for iter < max_iter): E gradient passes (EOT) and the sign step, reading the iterate
+// FeCo geometry of a run: k cluster means for m frames (0: no defense)
+static int feco_k(const sg_pgd_params* p, int m) { return p->feco_ratio > 0.f ? (int)((float)m * p->feco_ratio) : 0; }
+static FecoSpec feco_spec(const sg_pgd_params* p, int m, uint64_t pass, const uint32_t* ctl) {
+  FecoSpec fc;
+  fc.k = feco_k(p, m); fc.max_iter = p->feco_max_iter > 0 ? p->feco_max_iter : 100; fc.tol = p->feco_tol > 0.f ? p->feco_tol : 0.01f;
+  fc.seed = p->seed; fc.pass = (uint32_t)pass;
+  fc.ctl = ctl;
+  return fc;
+}
+
+// One PGD iteration (attack/FGSM.py:44-68 for iter < max_iter): E gradient samples (EOT) and the sign step, reading the iterate
 // from `cur` and writing the next one to `other` (E == 1: fused into the MFCC adjoint) or back into `cur` (E > 1).
+// The E samples run as E / Eb passes of B * Eb rows (Eb = eot_batch copies of the batch per pass, adaptive_attack/EOT.py:30-42).
 // `it` only selects the dither slice / loss-history row of the launch-by-launch path; with a device control block (ctl) the
 // pass counter comes from there and the function is iteration-independent, which is what makes it capturable.
 static int pgd_iteration(sg_handle* h, float* cur, float* other, const float* x0, const long long* y, const float* dither, int B,
                          int N, int m, const sg_pgd_params* p, float grad_sign, const XvWs& w, float* sc, long long* dec,
                          float* loss_hist, int it, uint32_t* ctl, cudaStream_t st) {
-  const int E = p->eot_size;
+  const int E = p->eot_size, Eb = p->eot_batch > 1 ? p->eot_batch : 1, rounds = E / Eb, Bv = B * Eb;
   const size_t dstride = (size_t)B * m * SG_WIN;
   float* const stash = h->feat_stash ? w.stash : nullptr;
-  for (int e = 0; e < E; ++e) {
-    const uint64_t pass = ctl ? (uint64_t)e : (uint64_t)it * E + e;
+  const int k = feco_k(p, m), T = k > 0 ? k : m;
+  for (int e = 0; e < rounds; ++e) {
+    const uint64_t pass = ctl ? (uint64_t)e : (uint64_t)it * rounds + e;
     const float* dth = dither ? dither + ((uint64_t)it * E + e) * dstride : nullptr;
-    SG_TRY(forward_pass(h, cur, B, N, m, p->dither_mode, dth, p->seed, pass, p->decision_threshold, w, w.emb, sc, dec, st, stash));
+    const float* xin = cur;
+    const long long* yin = y;
+    float* scb = sc;
+    long long* decb = dec;
+    if (Eb > 1) {
+      h->launches += 1;
+      PROF(h, SG_PROF_STEP, st, sg_tile_rows_launch(cur, w.xtile, (size_t)N, B, Eb, y, w.yc, st));
+      xin = w.xtile; yin = w.yc; scb = w.scores; decb = w.dec;
+    }
+    SG_TRY(forward_pass(h, xin, Bv, N, m, p->dither_mode, dth, p->seed, pass, p->decision_threshold, w, w.emb, scb, decb, st, stash,
+                        feco_spec(p, m, pass, ctl)));
     float* lossp = (loss_hist && e == 0) ? loss_hist + (size_t)it * B : w.loss;
     h->launches += 3;
-    PROF(h, SG_PROF_LOSS, st, sg_loss_launch(sc, y, B, h->S, p->loss, lossp, w.dscores, st));
-    PROF(h, SG_PROF_HEAD, st, sg_score_bwd_launch(h->H, w.emb, w.dscores, B, h->enroll, h->S, w.demb, st));
-    SG_TRY(embed_bwd(h, w.demb, B, m, w, w.dfeat, st));
-    const int fuse_cmvn = h->cmvn_fusion && sg_feat_cmvn_fusable(m);
+    PROF(h, SG_PROF_LOSS, st, sg_loss_launch(scb, yin, Bv, h->S, p->loss, lossp, w.dscores, st));
+    PROF(h, SG_PROF_HEAD, st, sg_score_bwd_launch(h->H, w.emb, w.dscores, Bv, h->enroll, h->S, w.demb, st));
+    SG_TRY(embed_bwd(h, w.demb, Bv, T, w, w.dfeat, st));
+    const int fuse_cmvn = k == 0 && h->cmvn_fusion && sg_feat_cmvn_fusable(m);
     const float* dr = w.dfeat;                                     // fused: the MFCC adjoint applies dx = dy - mean(dy) itself
-    if (!fuse_cmvn) {
-      PROF(h, SG_PROF_CMVN, st, sg_cmvn_launch(w.dfeat, SG_FLD, w.draw, SG_FLD, B, m, 1, st));
+    if (k > 0) {
+      // CMVN adjoint over the k means (w.feat is free in the backward), then the cluster-mean adjoint back to the m frames
+      h->launches += 1;
+      PROF(h, SG_PROF_CMVN, st, sg_cmvn_launch(w.dfeat, SG_FLD, w.feat, SG_FLD, Bv, k, 1, st));
+      PROF(h, SG_PROF_FECO, st, sg_feco_means_bwd_launch(w.feat, SG_FLD, w.km_ids, w.km_cnt, Bv, m, SG_NCEP, k, 1, w.draw, SG_FLD, st));
+      dr = w.draw;
+    } else if (!fuse_cmvn) {
+      PROF(h, SG_PROF_CMVN, st, sg_cmvn_launch(w.dfeat, SG_FLD, w.draw, SG_FLD, Bv, m, 1, st));
       dr = w.draw;
     } else {
       h->launches -= 1;
@@ -721,16 +773,22 @@ static int pgd_iteration(sg_handle* h, float* cur, float* other, const float* x0
     if (E == 1) {
       PROF(h, SG_PROF_MFCC_BWD, st, sg_feat_bwd_step_launch(h->d_tables, cur, B, N, m, p->dither_mode, dth, p->seed, dither_pass(h, pass), dr, SG_FLD, x0,
                                      other, p->step_size * grad_sign, p->epsilon, st, stash, fuse_cmvn));
-    } else {
+    } else if (Eb == 1) {
       PROF(h, SG_PROF_MFCC_BWD, st, sg_feat_bwd_launch(h->d_tables, cur, B, N, m, p->dither_mode, dth, p->seed, dither_pass(h, pass), dr, SG_FLD, w.grad,
                                 1.0f / (float)E, e > 0, st, stash, fuse_cmvn));
+    } else {
+      // one gradient row per copy, then the copies of an utterance are summed in copy order into the [B, N] accumulator
+      h->launches += 1;
+      PROF(h, SG_PROF_MFCC_BWD, st, sg_feat_bwd_launch(h->d_tables, xin, Bv, N, m, p->dither_mode, dth, p->seed, dither_pass(h, pass), dr, SG_FLD, w.grad,
+                                1.0f / (float)E, 0, st, stash, 0));
+      PROF(h, SG_PROF_STEP, st, sg_reduce_rows_launch(w.grad, w.xbuf2, (size_t)N, B, Eb, e > 0, st));
     }
   }
   if (E > 1) {
     h->launches += 1;
-    PROF(h, SG_PROF_STEP, st, sg_step_linf_launch(cur, x0, w.grad, (size_t)B * N, p->step_size * grad_sign, p->epsilon, st));
+    PROF(h, SG_PROF_STEP, st, sg_step_linf_launch(cur, x0, Eb > 1 ? w.xbuf2 : w.grad, (size_t)B * N, p->step_size * grad_sign, p->epsilon, st));
   }
-  if (ctl) { h->launches += 1; SG_TRY(sg_feat_ctl_tick_launch(ctl, (uint32_t)E, st)); }
+  if (ctl) { h->launches += 1; SG_TRY(sg_feat_ctl_tick_launch(ctl, (uint32_t)rounds, st)); }
   return SG_OK;
 }
 
@@ -776,7 +834,17 @@ extern "C" int sg_pgd_run(sg_handle* h, float* x_adv, const float* x0, const int
   if (p->max_iter < 0 || p->eot_size < 1) { sg_set_error("sg_pgd_run: max_iter >= 0 and eot_size >= 1 required"); return SG_EINVAL; }
   cudaStream_t st = (cudaStream_t)stream;
   const int m = sg_num_frames(N), E = p->eot_size;
-  XvWs w = xv_ws_layout(ws, B, m, h->Lp, h->L, h->S, true, N);
+  const int Eb = p->eot_batch > 1 ? p->eot_batch : 1, rounds = E / Eb;
+  if (E % Eb != 0) { sg_set_error("sg_pgd_run: eot_batch (%d) must divide eot_size (%d)", Eb, E); return SG_EINVAL; }
+  if (Eb > 1 && (p->dither_mode == SG_DITHER_TENSOR || loss_hist)) {
+    sg_set_error("sg_pgd_run: eot_batch > 1 needs dither OFF / PHILOX and no loss history"); return SG_EUNSUPPORTED;
+  }
+  const int fk = feco_k(p, m);
+  if (p->feco_ratio < 0.f || p->feco_ratio > 1.f || (p->feco_ratio > 0.f && (fk < 1 || B < 2))) {
+    sg_set_error("sg_pgd_run: FeCo needs 0 < feco_ratio <= 1, >= 1 cluster and a batch of >= 2 (ratio %g, frames %d, B %d)", p->feco_ratio, m, B);
+    return SG_EINVAL;
+  }
+  XvWs w = xv_ws_layout(ws, B * Eb, m, h->Lp, h->L, h->S, true, N);
   SG_TRY(cmvn_scratch_reserve(h, B));
   const size_t dstride = (size_t)B * m * SG_WIN;
   // grad_sign of attack/utils.py:114 follows the requested loss NAME (SV / OSI with loss='Entropy' run the margin loss with
@@ -790,9 +858,11 @@ extern "C" int sg_pgd_run(sg_handle* h, float* x_adv, const float* x0, const int
   // ---- graph replay: every iteration is the same kernel sequence on workspace addresses ------------------------------
   bool graphed = false;
   if (h->use_graph && !h->prof.on && !loss_hist && p->dither_mode != SG_DITHER_TENSOR && p->max_iter >= 2) {
-    unsigned long long key[13] = {(unsigned long long)(uintptr_t)ws, (unsigned long long)B, (unsigned long long)N,
+    unsigned long long key[16] = {(unsigned long long)(uintptr_t)ws, (unsigned long long)B, (unsigned long long)N,
                                   (unsigned long long)E, (unsigned long long)p->dither_mode, 0, 0, 0, 0, 0, 0, 0,
-                                  (unsigned long long)(uintptr_t)h->cm_part};
+                                  (unsigned long long)(uintptr_t)h->cm_part, (unsigned long long)Eb, 0, 0};
+    memcpy(&key[14], &p->feco_ratio, sizeof(float)); memcpy(&key[15], &p->feco_tol, sizeof(float));
+    key[15] |= (unsigned long long)(uint32_t)p->feco_max_iter << 32;
     static_assert(sizeof(sg_loss_params) == 24, "sg_loss_params fills key[7..9]");
     memcpy(&key[5], &p->epsilon, sizeof(float)); memcpy(&key[6], &p->step_size, sizeof(float));
     memcpy(&key[7], &p->loss, sizeof(sg_loss_params));
@@ -816,7 +886,8 @@ extern "C" int sg_pgd_run(sg_handle* h, float* x_adv, const float* x0, const int
       float* cur = (E > 1 || (p->max_iter & 1) == 0) ? w.xbuf : w.xbuf2;
       // final evaluation pass (attack/FGSM.py:44-57 with iter == max_iter): pass counter max_iter * E from the control block
       sg_feat_set_ctl(w.ctl);
-      int r = forward_pass(h, cur, B, N, m, p->dither_mode, nullptr, p->seed, 0, p->decision_threshold, w, w.emb, sc, dec, st);
+      int r = forward_pass(h, cur, B, N, m, p->dither_mode, nullptr, p->seed, 0, p->decision_threshold, w, w.emb, sc, dec, st, nullptr,
+                           feco_spec(p, m, 0, w.ctl));
       sg_feat_set_ctl(nullptr);
       SG_TRY(r);
       h->launches += 1;
@@ -836,9 +907,10 @@ extern "C" int sg_pgd_run(sg_handle* h, float* x_adv, const float* x0, const int
   }
   // final evaluation pass (attack/FGSM.py:44-57 with iter == max_iter)
   {
-    const uint64_t pass = (uint64_t)p->max_iter * E;
-    const float* dth = dither ? dither + pass * dstride : nullptr;
-    SG_TRY(forward_pass(h, cur, B, N, m, p->dither_mode, dth, p->seed, pass, p->decision_threshold, w, w.emb, sc, dec, st));
+    const uint64_t pass = (uint64_t)p->max_iter * rounds;
+    const float* dth = dither ? dither + (uint64_t)p->max_iter * E * dstride : nullptr;
+    SG_TRY(forward_pass(h, cur, B, N, m, p->dither_mode, dth, p->seed, pass, p->decision_threshold, w, w.emb, sc, dec, st, nullptr,
+                        feco_spec(p, m, pass, nullptr)));
     float* lossp = loss_hist ? loss_hist + (size_t)p->max_iter * B : w.loss;
     h->launches += 1;
     PROF(h, SG_PROF_LOSS, st, sg_loss_launch(sc, (const long long*)y, B, h->S, p->loss, lossp, nullptr, st));

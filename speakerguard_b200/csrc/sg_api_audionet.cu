@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include "sg_handle.cuh"
+#include "sg_head.cuh"
 
 void sg_audionet_free(sg_handle* h) {
   if (h && h->an) { delete h->an; h->an = nullptr; }            // device buffers are in h->allocs
@@ -390,14 +391,7 @@ extern "C" long long sg_cw2_last_iterations(const sg_handle* h) { return h ? h->
 // ---------------------------------------------------------------------------------------------
 // FeCo (defense/feature_level.py:18-50, :168-217)
 // ---------------------------------------------------------------------------------------------
-size_t sg_kmeans_smem(int n, int dim, int k);
-int sg_feco_kmeans_launch(const float* feat, int ld, int B, int n, int dim, int k, uint64_t seed, int max_iter, float tol,
-                          int* ids, cudaStream_t st, const uint32_t* ctl);
-int sg_feco_means_fwd_launch(const float* feat, int ld_in, const int* ids, int B, int n, int dim, int k, int force,
-                             float* out, int ld_out, int* counts, cudaStream_t st);
-int sg_feco_means_bwd_launch(const float* dout, int ld_out, const int* ids, const int* counts, int B, int n, int dim, int k,
-                             int force, float* dfeat, int ld_in, cudaStream_t st);
-
+// (launchers of sg_kmeans.cu: declared in sg_head.cuh)
 static int feco_check(sg_handle* h, int B, int n, int dim, int k) {
   SG_TRY(sg_check_handle(h, false));
   if (B < 1 || n < 1 || dim < 1 || dim > 32 || k < 1 || k > n) { sg_set_error("FeCo: need B >= 1, 1 <= k <= n, 1 <= dim <= 32 (B=%d n=%d dim=%d k=%d)", B, n, dim, k); return SG_EINVAL; }

@@ -1797,6 +1797,39 @@ int sg_dither_fill_launch(int B, int m, uint64_t seed, uint64_t pass, float* out
   return SG_OK;
 }
 
+// EOT samples as batch rows: out[e * B + b] = in[b] for e < copies (float4 rows when N % 4 == 0), labels alike
+__global__ void tile_rows_kernel(const float* __restrict__ in, float* __restrict__ out, size_t row_floats, int B, int copies,
+                                 const long long* __restrict__ yin, long long* __restrict__ yout) {
+  const size_t total = row_floats * B;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = in[i];
+    for (int e = 0; e < copies; ++e) out[(size_t)e * total + i] = v;
+  }
+  if (yin != nullptr && blockIdx.x == 0)
+    for (int i = threadIdx.x; i < B * copies; i += blockDim.x) yout[i] = yin[i % B];
+}
+// acc[b] (+)= sum over copies e of rows[e * B + b], summed in copy order
+__global__ void reduce_rows_kernel(const float* __restrict__ rows, float* __restrict__ acc, size_t row_floats, int B, int copies,
+                                   int accumulate) {
+  const size_t total = row_floats * B;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    float a = accumulate ? acc[i] : 0.f;
+    for (int e = 0; e < copies; ++e) a += rows[(size_t)e * total + i];
+    acc[i] = a;
+  }
+}
+int sg_tile_rows_launch(const float* in, float* out, size_t row_floats, int B, int copies, const long long* yin, long long* yout,
+                        cudaStream_t st) {
+  tile_rows_kernel<<<148 * 8, 256, 0, st>>>(in, out, row_floats, B, copies, yin, yout);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+int sg_reduce_rows_launch(const float* rows, float* acc, size_t row_floats, int B, int copies, int accumulate, cudaStream_t st) {
+  reduce_rows_kernel<<<148 * 8, 256, 0, st>>>(rows, acc, row_floats, B, copies, accumulate);
+  SG_LAUNCH_CHECK();
+  return SG_OK;
+}
+
 int sg_step_linf_launch(float* x, const float* x0, const float* grad, size_t n, float step, float eps,
                         cudaStream_t st) {
   int blocks = (int)((n + 255) / 256);

@@ -36,7 +36,7 @@ struct SgProf {
 // workspace and parameters match `key`.
 struct SgPgdGraph {
   cudaGraphExec_t exec[2] = {nullptr, nullptr};
-  unsigned long long key[13] = {0};
+  unsigned long long key[16] = {0};
   cudaStream_t cap_stream = nullptr;   // private capture stream (the caller's may be the legacy default stream)
   int kernels = 0;                     // kernels per captured iteration (launch accounting)
   bool valid = false;

@@ -33,6 +33,17 @@ size_t sg_feat_stash_floats(int B, int m);   // per-frame forward stash consumed
 int sg_dither_fill_launch(int B, int m, uint64_t seed, uint64_t pass, float* out, cudaStream_t st);
 int sg_tap_gather_launch(const float* G, int ldg, float* out, int ldo, size_t rows, int taps, int dil, cudaStream_t st);
 int sg_step_linf_launch(float* x, const float* x0, const float* grad, size_t n, float step, float eps, cudaStream_t st);
+int sg_tile_rows_launch(const float* in, float* out, size_t row_floats, int B, int copies, const long long* yin, long long* yout,
+                        cudaStream_t st);
+int sg_reduce_rows_launch(const float* rows, float* acc, size_t row_floats, int B, int copies, int accumulate, cudaStream_t st);
+// FeCo (sg_kmeans.cu); ctl: device {pass, seed_lo, seed_hi} mixed into the k-means seed (graph replay), or null
+int sg_kmeans_init();
+int sg_feco_kmeans_launch(const float* feat, int ld, int B, int n, int dim, int k, uint64_t seed, int max_iter, float tol,
+                          int* ids, cudaStream_t st, const uint32_t* ctl, uint32_t pass = 0);
+int sg_feco_means_fwd_launch(const float* feat, int ld_in, const int* ids, int B, int n, int dim, int k, int force,
+                             float* out, int ld_out, int* counts, cudaStream_t st);
+int sg_feco_means_bwd_launch(const float* dout, int ld_out, const int* ids, const int* counts, int B, int n, int dim, int k,
+                             int force, float* dfeat, int ld_in, cudaStream_t st);
 int sg_cmvn_launch(const float* in, int ld_in, float* out, int ld_out, int B, int T, int backward, cudaStream_t st);
 
 int sg_conv_tc_warm();                                         // per-device one-time setup of the tcgen05 kernels (outside any capture)

@@ -134,7 +134,7 @@ __device__ __forceinline__ void km_mma(float (&c)[4], const uint32_t (&a)[4], ui
 }
 __global__ void __launch_bounds__(KM_THREADS)
 feco_kmeans2_kernel(const float* __restrict__ feat, int ld, int n, int dim, int k, uint32_t seed_lo, uint32_t seed_hi,
-                    const uint32_t* __restrict__ ctl, int max_iter, float tol, int* __restrict__ ids_out) {
+                    uint32_t pass, const uint32_t* __restrict__ ctl, int max_iter, float tol, int* __restrict__ ids_out) {
   extern __shared__ __align__(16) float sm[];
   float* X = sm;                                         // [n][36]
   float* Cn = X + (size_t)n * KM_DP;                     // [k8][36], k8 = k rounded up to 8 (padding rows zero)
@@ -150,7 +150,10 @@ feco_kmeans2_kernel(const float* __restrict__ feat, int ld, int n, int dim, int 
   __shared__ int s_pick;
   __shared__ int s_changed;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (ctl != nullptr) { seed_lo ^= __ldg(ctl) * 0x9E3779B9u; seed_hi += __ldg(ctl + 1) ^ __ldg(ctl + 2); }   // per-pass clustering (graph replay)
+  // a fresh clustering per pass of the attack loop: pass index = immediate + the device counter (graph replay); pass 0 leaves
+  // the seed as given (stand-alone calls)
+  if (ctl != nullptr) pass += __ldg(ctl);
+  seed_lo ^= pass * 0x9E3779B9u; seed_hi += pass * 0x85EBCA77u;
   const float* fb = feat + (size_t)b * n * ld;
   for (int i = tid; i < n * KM_DP; i += KM_THREADS) {
     const int j = i / KM_DP, d = i - j * KM_DP;
@@ -364,19 +367,25 @@ size_t sg_kmeans_smem(int n, int dim, int k) {
   return ((size_t)n * dim + (size_t)k * dim + n) * sizeof(float) + ((size_t)n + k) * sizeof(int) + 40 * sizeof(float);
 }
 
+// shared-memory opt-in of the second kernel, per device, outside any stream capture (called by sg_create)
+#define KM2_MAX_SMEM (220 * 1024)
+int sg_kmeans_init() {
+  SG_CUDA_CHECK(cudaFuncSetAttribute(feco_kmeans2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KM2_MAX_SMEM));
+  return SG_OK;
+}
+
 // ctl: optional device control block {pass, seed_lo, seed_hi} mixed into the seed (CUDA-graph replay of the fused attack loop)
 int sg_feco_kmeans_launch(const float* feat, int ld, int B, int n, int dim, int k, uint64_t seed, int max_iter, float tol,
-                          int* ids, cudaStream_t st, const uint32_t* ctl) {
+                          int* ids, cudaStream_t st, const uint32_t* ctl, uint32_t pass) {
   static int use_v2 = -1;
   if (use_v2 < 0) { const char* e = getenv("SGB200_KMEANS_V2"); use_v2 = e ? atoi(e) != 0 : 1; }
   const size_t smem2 = kmeans2_smem(n, k);
-  if (use_v2 && dim <= 32 && smem2 <= 220 * 1024) {
-    SG_CUDA_CHECK(cudaFuncSetAttribute(feco_kmeans2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    feco_kmeans2_kernel<<<B, KM_THREADS, smem2, st>>>(feat, ld, n, dim, k, (uint32_t)seed, (uint32_t)(seed >> 32), ctl, max_iter, tol, ids);
+  if (use_v2 && dim <= 32 && smem2 <= KM2_MAX_SMEM) {
+    feco_kmeans2_kernel<<<B, KM_THREADS, smem2, st>>>(feat, ld, n, dim, k, (uint32_t)seed, (uint32_t)(seed >> 32), pass, ctl, max_iter, tol, ids);
     SG_LAUNCH_CHECK();
     return SG_OK;
   }
-  if (ctl) { sg_set_error("FeCo k-means inside the fused loop needs the shared-memory kernel (n=%d k=%d)", n, k); return SG_EUNSUPPORTED; }
+  if (ctl || pass) { sg_set_error("FeCo k-means inside the fused loop needs the shared-memory kernel (n=%d k=%d)", n, k); return SG_EUNSUPPORTED; }
   const size_t smem = sg_kmeans_smem(n, dim, k);
   if (smem > 200 * 1024) { sg_set_error("FeCo k-means: utterance too long for the shared-memory kernel (n=%d dim=%d k=%d)", n, dim, k); return SG_EUNSUPPORTED; }
   SG_CUDA_CHECK(cudaFuncSetAttribute(feco_kmeans_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

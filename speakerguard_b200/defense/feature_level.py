@@ -61,3 +61,20 @@ def FEATURE_COMPRESSION(feat, method='kmeans', param=0.5, other_param='L2', seed
 
 def FeCo(feat, method='kmeans', param=0.5, other_param='L2', seed=None, ids=None):
     return FEATURE_COMPRESSION(feat, method, param, other_param, seed=seed, ids=ids)
+
+
+class FeCoDefense:
+    """``lambda feat: FeCo(feat, method, param, other_param)`` as an object (what defense.parser_defense builds for 'FeCo',
+    reference defense/defense.py:72-77), so that the attack classes can see which defense a ``defended_model`` carries:
+    ``defended_model(xv, defense=[[1, FeCoDefense('kmeans', 0.5, 'L2')]])`` runs FeCo + EOT inside the fused device loop
+    (sg_pgd_run, sg_pgd_params::feco_ratio); a plain lambda keeps working through the generic autograd path."""
+
+    def __init__(self, method='kmeans', param=0.5, other_param='L2', max_iter=100, tol=0.01):
+        self.method, self.param, self.other_param = method, float(param), other_param
+        self.max_iter, self.tol = int(max_iter), float(tol)
+
+    def __call__(self, feat):
+        return FeCo(feat, self.method, self.param, self.other_param)
+
+    def fusable(self):
+        return self.method == 'kmeans' and self.other_param == 'L2' and 0.0 < self.param <= 1.0

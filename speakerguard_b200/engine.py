@@ -583,22 +583,27 @@ class Engine:
                 step_size: float, lp: LossParams, dither_mode: int = _lib.DITHER_PHILOX,
                 dither: Optional[torch.Tensor] = None, seed: int = 0, eot_size: int = 1,
                 decision_threshold: float = -math.inf, ws: Optional[torch.Tensor] = None, want_loss_hist: bool = False,
-                grad_sign: float = 0.0, utt_offset: int = 0):
+                grad_sign: float = 0.0, utt_offset: int = 0, eot_batch: int = 1, feco_ratio: float = 0.0,
+                feco_max_iter: int = 100, feco_tol: float = 0.01):
         """x_adv [B,N] is updated in place.  Returns (decisions [B] i64, scores [B,S], loss_hist or None).
         grad_sign: the sign resolve_loss returned (0 derives it from ``lp``); utt_offset: global index of this shard's first
-        utterance (keys the philox dither so that a sharded run reproduces the unsharded one bit for bit)."""
+        utterance (keys the philox dither so that a sharded run reproduces the unsharded one bit for bit).
+        eot_batch: EOT copies run as batch rows (B * eot_batch rows per pass); feco_ratio > 0: FeCo k-means compression of
+        the raw features inside the loop (sg_pgd_params)."""
         assert x_adv.is_contiguous() and x_adv.dtype == torch.float32 and x_adv.device == self.device
         x0 = _f32c(x0, self.device)
         y = y.to(device=self.device, dtype=torch.int64).contiguous()
         B, N = x_adv.shape
+        eot_batch = max(1, int(eot_batch))
         if ws is None:
-            ws = self.pgd_ws(B, N)
+            ws = self.pgd_ws(B * eot_batch, N)
         scores = torch.empty(B, self.S, device=self.device, dtype=torch.float32)
         dec = torch.empty(B, device=self.device, dtype=torch.int64)
         hist = torch.empty(max_iter + 1, B, device=self.device, dtype=torch.float32) if want_loss_hist else None
         d = None if dither is None else _f32c(dither, self.device)
         pp = PgdParams(int(max_iter), float(epsilon), float(step_size), int(eot_size), int(dither_mode), int(seed), lp,
-                       float(decision_threshold), float(grad_sign))
+                       float(decision_threshold), float(grad_sign), eot_batch, float(feco_ratio), int(feco_max_iter),
+                       float(feco_tol))
         self.set_utt_offset(utt_offset)
         check(self.lib.sg_pgd_run(self._h, _ptr(x_adv), _ptr(x0), _ptr(y), _ptr(d), B, N, C.byref(pp), _ptr(ws), _ptr(dec),
                                   _ptr(scores), _ptr(hist), self.stream), "sg_pgd_run")

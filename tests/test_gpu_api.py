@@ -163,7 +163,7 @@ def test_eot_wrapper_and_defended_model(model):
     # no defense: defended_model is transparent and the fused path is taken
     from speakerguard_b200.attack.FGSM import fused_target
     plain = defended_model(model)
-    assert fused_target(plain) is model and fused_target(dm) is None
+    assert fused_target(plain) == (model, None) and fused_target(dm) == (None, None)
     d1, s1 = plain.make_decision(x)
     d2, s2 = model.make_decision(x)
     assert torch.equal(d1, d2) and torch.equal(s1, s2)

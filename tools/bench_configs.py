@@ -70,17 +70,21 @@ def main():
     t, _ = timed(lambda: att.attack(x, y), reps=10)
     print(json.dumps({"config": "1: FGSM B=8 2 s vs xv_plda", "precision": prec, "s_per_attack": t, "utt_iter_per_s": 8 / t}))
 
-    # config 4: PGD-10, EOT_size 50 (batch 50), FeCo kmeans 0.5 at the raw-feature level, generic (autograd) path
+    # config 4: PGD-10, EOT_size 50 (batch 50), FeCo kmeans 0.5 at the raw-feature level: the fused device loop (FeCoDefense
+    # object: FeCo + EOT inside sg_pgd_run, EOT copies as batch rows) and the generic autograd path (plain lambda)
+    from speakerguard_b200.defense.feature_level import FeCoDefense
     exact = bool(os.environ.get("SGB200_EXACT"))       # BASELINE.json sizes: C4 B=256 / PGD-10, C3 targeted 9 x 1000
     B4 = int(os.environ.get("SGB200_CFG4_B", "256" if exact else "32"))
-    dm = defended_model(model, defense=[[1, lambda f: FeCo(f, "kmeans", 0.5, "L2")]], order="sequential")
     x4, y4 = synthetic_batch(B4, 48000)
     x4, y4 = x4.cuda(), y4.cuda()
     it4 = 10 if exact else 2
-    att4 = PGD(dm, epsilon=0.002, step_size=0.0004, max_iter=it4, batch_size=B4, EOT_size=50, EOT_batch_size=50, verbose=0)
-    t, _ = timed(lambda: att4.attack(x4, y4), reps=1)
-    print(json.dumps({"config": f"4: EOT-PGD-{it4} (EOT 50) vs FeCo(kmeans 0.5)-defended xv_plda, B={B4}, 3 s", "precision": prec,
-                      "s_per_iteration": t / it4, "utt_iter_per_s": B4 * it4 / t, "eot_utt_passes_per_s": B4 * it4 * 50 / t}))
+    for path, defense in (("fused", FeCoDefense("kmeans", 0.5, "L2")), ("generic", lambda f: FeCo(f, "kmeans", 0.5, "L2"))):
+        dm = defended_model(model, defense=[[1, defense]], order="sequential")
+        att4 = PGD(dm, epsilon=0.002, step_size=0.0004, max_iter=it4, batch_size=B4, EOT_size=50, EOT_batch_size=50, verbose=0)
+        t, _ = timed(lambda: att4.attack(x4, y4), reps=2 if path == "fused" else 1)
+        print(json.dumps({"config": f"4: EOT-PGD-{it4} (EOT 50) vs FeCo(kmeans 0.5)-defended xv_plda, B={B4}, 3 s", "path": path,
+                          "precision": prec, "s_per_iteration": t / it4, "utt_iter_per_s": B4 * it4 / t,
+                          "eot_utt_passes_per_s": B4 * it4 * 50 / t}), flush=True)
     del att4, dm, model
     torch.cuda.empty_cache()
 
