@@ -530,7 +530,8 @@ def run_cw2(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     B, N, iters, bs = args.batch, int(args.seconds * 16000), args.iters, args.search_steps
-    an = audionet_csine(params=audionet_params(), device=dev)
+    an_prec = "fp32" if args.precision == "fp32" else "tf32"    # AudioNet's convolutions: FFMA parity mode or tcgen05 / TF32
+    an = audionet_csine(params=audionet_params(), device=dev, precision=an_prec)
     eng = an.engine
     x_host, _ = synthetic_batch(B, N, 10, seed=1234 + rank)
     x_host = x_host.pin_memory()
@@ -585,8 +586,9 @@ def run_cw2(args):
     per_it = 1.4e6 * N / 48000.0
     out = {"metric": "CW2 utterance-iterations/s vs AudioNet", "value": value, "unit": "utt-iter/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "CW2 targeted (%d binary-search steps x %d iterations, c0 1e-3, lr 1e-2, stop_early_iter 1000) vs AudioNet "
+           "vs_baseline": None, "dtype": "f32" if an_prec == "fp32" else "tf32", "data": "synthetic",
+           "config": {"precision": an_prec,
+                      "workload": "CW2 targeted (%d binary-search steps x %d iterations, c0 1e-3, lr 1e-2, stop_early_iter 1000) vs AudioNet "
                                   "CSI-NE (251 classes, random init, eval), synthetic %g s utterances, batch %d per GPU (BASELINE configs[2])"
                                   % (bs, iters, args.seconds, B), "batch_per_gpu": B, "samples": N, "iterations_executed": done_iters,
                       "cache": "inputs larger than L2 (iterate + Adam state 0.5 GB, activations 1.3 GB per pass)"},

@@ -12,6 +12,13 @@ void sg_audionet_free(sg_handle* h) {
 }
 
 static int an_up(sg_handle* h, float** dst, const std::vector<float>& v) { return sg_dev_upload(h, dst, v); }
+// K-major copy of a packed [K, N] matrix: [N, K]
+static int an_up_t(sg_handle* h, float** dst, const std::vector<float>& v, size_t K, size_t N) {
+  std::vector<float> t(v.size());
+  for (size_t k = 0; k < K; ++k)
+    for (size_t n = 0; n < N; ++n) t[n * K + k] = v[k * N + n];
+  return sg_dev_upload(h, dst, t);
+}
 
 extern "C" int sg_load_audionet(sg_handle* h, const sg_audionet_weights* w) {
   SG_TRY(sg_check_handle(h, false));
@@ -46,6 +53,7 @@ extern "C" int sg_load_audionet(sg_handle* h, const sg_audionet_weights* w) {
         }
     for (int fo = 0; fo < 32; ++fo) b1[fo] = (float)(((double)w->conv1_b[0] - w->bn_mean[0][0]) * sc + w->bn_beta[0][0]);
     SG_TRY(an_up(h, &an->W1, W1)); SG_TRY(an_up(h, &an->W1b, W1b)); SG_TRY(an_up(h, &an->b1, b1));
+    SG_TRY(an_up_t(h, &an->W1k, W1, 5 * 32, 32)); SG_TRY(an_up_t(h, &an->W1bk, W1b, 5 * 32, 32));
   }
   for (int l = 0; l < 7; ++l) {   // Conv1d k=3 + BatchNorm1d (affine) folded: BN directly follows the conv
     const int ci = kAnCin[l], co = kAnCout[l];
@@ -61,6 +69,7 @@ extern "C" int sg_load_audionet(sg_handle* h, const sg_audionet_weights* w) {
       b[o] = (float)(((double)w->conv_b[l][o] - w->bn_mean[l + 1][o]) * sc + w->bn_beta[l + 1][o]);
     }
     SG_TRY(an_up(h, &an->W[l], W)); SG_TRY(an_up(h, &an->Wb[l], Wb)); SG_TRY(an_up(h, &an->bias[l], b));
+    SG_TRY(an_up_t(h, &an->Wk[l], W, (size_t)3 * ci, co)); SG_TRY(an_up_t(h, &an->Wbk[l], Wb, (size_t)3 * co, ci));
   }
   {
     const int C = w->num_class, Cp = (C + 15) / 16 * 16;
@@ -137,10 +146,12 @@ static int an_check(sg_handle* h, int B, int N) {
   return SG_OK;
 }
 
-static void an_conv_args(SgConvArgs& a, const float* A, int cin, const float* W, const float* bias, float* out, int cout, int rows,
+// The convolutions run on the tensor cores (conv_tc_kernel's utterance-tiled mode, TF32 operands, fp32 storage) when the
+// handle's precision is not fp32; fp32 is the FFMA parity mode.
+static void an_conv_args(SgConvArgs& a, const float* A, int cin, const float* W, const float* Wk, const float* bias, float* out, int cout, int rows,
                          int taps, int tap_base, int tap_step, int T, int epi, const float* mask, int ldmask) {
   memset(&a, 0, sizeof(a));
-  a.A = A; a.lda = cin; a.W = W; a.bias = bias; a.out = out; a.ldo = cout; a.rows = rows; a.N = cout; a.cin = cin;
+  a.A = A; a.lda = cin; a.W = W; a.Wk = Wk; a.bias = bias; a.out = out; a.ldo = cout; a.rows = rows; a.N = cout; a.cin = cin;
   a.taps = taps; a.tap_base = tap_base; a.tap_step = tap_step; a.same_utt = 1; a.T = T; a.t_valid = T; a.epilogue = epi;
   a.mask = mask; a.ldmask = ldmask;
 }
@@ -149,13 +160,13 @@ static void an_conv_args(SgConvArgs& a, const float* A, int cin, const float* W,
 static int an_emb_fwd(sg_handle* h, const float* feat, int B, const AnWs& w, float* emb, cudaStream_t st) {
   SgAudioNet* an = h->an;
   SgConvArgs a;
-  an_conv_args(a, feat, 32, an->W1, an->b1, w.c1, 32, B * w.T[0], 5, -2, 1, w.T[0], SG_EPI_BIAS, nullptr, 0);
-  SG_TRY(sg_run_conv(h, a, false, SG_PROF_AUDIONET, st));
+  an_conv_args(a, feat, 32, an->W1, an->W1k, an->b1, w.c1, 32, B * w.T[0], 5, -2, 1, w.T[0], SG_EPI_BIAS, nullptr, 0);
+  SG_TRY(sg_run_conv(h, a, true, SG_PROF_AUDIONET, st));
   const float* in = w.c1;
   for (int l = 0; l < 7; ++l) {
-    an_conv_args(a, in, kAnCin[l], an->W[l], an->bias[l], w.a[l], kAnCout[l], B * w.T[l], 3, -kAnPad[l], 1, w.T[l],
+    an_conv_args(a, in, kAnCin[l], an->W[l], an->Wk[l], an->bias[l], w.a[l], kAnCout[l], B * w.T[l], 3, -kAnPad[l], 1, w.T[l],
                  SG_EPI_BIAS_RELU, nullptr, 0);
-    SG_TRY(sg_run_conv(h, a, false, SG_PROF_AUDIONET, st));
+    SG_TRY(sg_run_conv(h, a, true, SG_PROF_AUDIONET, st));
     if (kAnPool[l]) {
       h->launches += 1;
       PROF(h, SG_PROF_AUDIONET, st, sg_maxpool2_fwd_launch(w.a[l], w.p[l], B, w.T[l], kAnCout[l], st));
@@ -204,9 +215,9 @@ static int an_emb_bwd(sg_handle* h, const float* demb, int B, const AnWs& w, flo
     // dgrad of conv stage l: dIn[s] = sum_k W_k^T dOut[s - k + pad]; output = gradient wrt p[l-1] (or c1)
     const bool prev_pooled = l > 0 && kAnPool[l - 1];
     const bool mask_here = l > 0 && !prev_pooled;       // ReLU of stage l-1 sits directly under this conv
-    an_conv_args(a, gin, kAnCout[l], an->Wb[l], nullptr, gout, kAnCin[l], B * w.T[l], 3, kAnPad[l], -1, w.T[l],
+    an_conv_args(a, gin, kAnCout[l], an->Wb[l], an->Wbk[l], nullptr, gout, kAnCin[l], B * w.T[l], 3, kAnPad[l], -1, w.T[l],
                  mask_here ? SG_EPI_MASK : SG_EPI_NONE, mask_here ? w.a[l - 1] : nullptr, mask_here ? kAnCout[l - 1] : 0);
-    SG_TRY(sg_run_conv(h, a, false, SG_PROF_AUDIONET, st));
+    SG_TRY(sg_run_conv(h, a, true, SG_PROF_AUDIONET, st));
     float* t = gin; gin = gout; gout = t;
     if (prev_pooled) {                                  // un-pool into stage l-1's resolution + its ReLU mask
       h->launches += 1;
@@ -214,8 +225,8 @@ static int an_emb_bwd(sg_handle* h, const float* demb, int B, const AnWs& w, flo
       t = gin; gin = gout; gout = t;
     }
   }
-  an_conv_args(a, gin, 32, an->W1b, nullptr, dfeat, 32, B * w.T[0], 5, 2, -1, w.T[0], SG_EPI_NONE, nullptr, 0);
-  return sg_run_conv(h, a, false, SG_PROF_AUDIONET, st);
+  an_conv_args(a, gin, 32, an->W1b, an->W1bk, nullptr, dfeat, 32, B * w.T[0], 5, 2, -1, w.T[0], SG_EPI_NONE, nullptr, 0);
+  return sg_run_conv(h, a, true, SG_PROF_AUDIONET, st);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -52,5 +52,7 @@ struct SgAudioNet {
   float *W1 = nullptr, *W1b = nullptr, *b1 = nullptr;         // banded 5x5 pre-filter as a 5-tap 32->32 conv
   float *W[7] = {}, *Wb[7] = {}, *bias[7] = {};               // [3*cin, cout], [3*cout, cin], [cout]
   float *Wfc = nullptr, *Wfcb = nullptr, *bfc = nullptr;      // [32, Cp], [Cp, 32], [Cp]
+  // K-major copies for the tensor-core path (tf32 / bf16 precision modes): [cout, taps*cin] and [cin, taps*cout]
+  float *W1k = nullptr, *W1bk = nullptr, *Wk[7] = {}, *Wbk[7] = {};
 };
 

@@ -64,6 +64,13 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// 3-D load (channel, frame, utterance): frames outside [0, T) - negative ones included - are zero-filled, which is exactly the
+// 'same' padding of a convolution that must not read across utterances
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"((uint64_t)map), "r"(c0), "r"(c1) : "memory");
 }
@@ -169,6 +176,10 @@ struct TcArgs {
   // staged box is stored once per utterance it touches (3-D map, out-of-range frames clipped).  bits_T: row stride of the
   // ReLU-bit words written by the forward epilogue (0: a.T)
   int st_dual, bits_T, st_nutt, st_stride;
+  // utterance-tiled mode ('same' padding, AudioNet): an M tile is 128 frames of ONE utterance (utt_tpu tiles per utterance of
+  // utt_T frames); A and the output are addressed through 3-D maps (channel, frame, utterance), taps read frame
+  // f + tap_base + tap * tap_step and frames outside the utterance read zero
+  int utt_T, utt_tpu, tap_base;
 };
 
 // ---- cluster / cta_group::2 helpers ------------------------------------------------------------
@@ -328,6 +339,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             if (rank == 0) mbar_expect_tx(&full[stage], tx);
             tma_load_2d_2sm(sa, &mapA, lead_full, kc * KB_ELEMS, p0 + tap * a.tap_step);
             tma_load_2d_2sm(sa + TC_A_BYTES, &mapB, lead_full, kb * KB_ELEMS, n0);
+          } else if (!PAIR && a.utt_T > 0) {
+            const int ub = mt / a.utt_tpu, f0 = (mt - ub * a.utt_tpu) * TC_BM;
+            mbar_expect_tx(&full[stage], tx);
+            tma_load_3d(sa, &mapA, &full[stage], kc * KB_ELEMS, f0 + a.tap_base + tap * a.tap_step, ub);
+            tma_load_2d(sa + TC_A_BYTES, &mapB, &full[stage], kb * KB_ELEMS, n0);
           } else {
             mbar_expect_tx(&full[stage], tx);
             tma_load_2d(sa, &mapA, &full[stage], kc * KB_ELEMS, p0 + tap * a.tap_step);
@@ -513,7 +529,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     for (int tile = cta0; tile < ntiles; tile += tstep) {
       const int t2 = tile / a.ksplit, ks = tile - t2 * a.ksplit;
       const int mt = t2 / a.n_tiles, nt = t2 - mt * a.n_tiles;
-      const int row = mt * TILE_ROWS + rbase + r_in;
+      // utterance-tiled mode: the tile is frames f0 .. f0 + 127 of utterance ub; rows beyond the utterance are not stored
+      const int u_ub = a.utt_T > 0 ? mt / a.utt_tpu : 0, u_f0 = a.utt_T > 0 ? (mt - u_ub * a.utt_tpu) * TC_BM : 0;
+      const int row = a.utt_T > 0 ? u_ub * a.utt_T + u_f0 + r_in : mt * TILE_ROWS + rbase + r_in;
+      const bool row_in = a.utt_T > 0 ? (u_f0 + r_in < a.utt_T) : (row < a.rows);
       const int n0 = nt * a.bn;
       if (has_bias) {
         // this group's 128 columns of the bias (chunk k, column i -> bias_g[k * CW + i]); the last named barrier of the
@@ -525,7 +544,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      bool row_ok = row < a.rows;
+      bool row_ok = row_in;
       if (a.epilogue == SG_EPI_MASK) row_ok = row_ok && ((row % a.T) < a.t_valid);
       // One chunk = NG groups of 32 columns.  The operands of the epilogue op (bias / ReLU bits) are requested first,
       // then all TMEM loads of the chunk are issued with a single wait, so that their latencies overlap instead of
@@ -547,7 +566,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
             }
-            if (a.bits_out != nullptr && row < a.rows) {
+            if (a.bits_out != nullptr && row_in) {
               // bit j = (x_j > 0): 0 - x has its sign bit set exactly then (0 - (+-0) = +0), and a funnel shift moves that
               // sign into the word: two FADDs on the wide FMA pipe + one SHF per element instead of FSETP + SEL + IADD3
               uint32_t ob = 0;
@@ -636,7 +655,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         epi_bar(1 + grp);
         if (issuer) {
-          if (!a.st_dual) {
+          if (a.utt_T > 0) {
+            tma_store_3d(buf, &mapO, n0 + c, u_f0, u_ub);                                   // frames >= T are clipped
+          } else if (!a.st_dual) {
             tma_store_2d(buf, &mapO, n0 + c, ks * a.rows_pad + mt * TILE_ROWS + rbase);   // rows / columns beyond the tensor are clipped by TMA
           } else {
             const int R0 = mt * TILE_ROWS + rbase, ub = R0 / a.T, ut = R0 - ub * a.T;      // first row of the box: utterance, frame
@@ -792,7 +813,11 @@ int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
   g_tc_extra = 0;
   if (precision == SG_PREC_FP32) { sg_set_error("sg_conv_tc called in fp32 mode"); return SG_EINVAL; }
   const int kbe = a.op_bf16 ? 64 : 32;
-  if (a.same_utt || a.tap_base != 0) { sg_set_error("sg_conv_tc: 'same' padding is only built for the FFMA path"); return SG_EUNSUPPORTED; }
+  const bool utt = a.same_utt != 0;
+  if (utt && (a.op_bf16 || a.out_bf16 || a.xf_ab || a.out_T > 0 || a.bits_out || a.bits_in || a.T < 1 || a.rows % a.T != 0)) {
+    sg_set_error("sg_conv_tc: 'same' padding is built for fp32 tensors with TF32 operands (rows %d, T %d)", a.rows, a.T); return SG_EUNSUPPORTED;
+  }
+  if (!utt && a.tap_base != 0) { sg_set_error("sg_conv_tc: tap_base needs the utterance-tiled ('same' padding) mode"); return SG_EUNSUPPORTED; }
   int r = tc_init();
   if (r != SG_OK) return r;
   if (a.cin % kbe != 0 || a.N % 32 != 0 || a.lda % 8 != 0 || a.ldo % 8 != 0 || (a.out_bf16 && a.N % 64 != 0) ||
@@ -817,7 +842,7 @@ int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
   // The slice count is a function of the contraction's K and N only, never of the row count: the summation order of an
   // output element must not depend on the batch size, or a sharded run would differ from the unsharded one in the last bit
   // (tests/test_gpu_shard.py).
-  if (g_small_bn && !a.xf_ab && a.splitk_ws && !a.out_bf16 && !a.bits_out && a.N % 4 == 0 && a.ldo % 4 == 0 && a.N <= 512 &&
+  if (g_small_bn && !utt && !a.xf_ab && a.splitk_ws && !a.out_bf16 && !a.bits_out && a.N % 4 == 0 && a.ldo % 4 == 0 && a.N <= 512 &&
       (a.epilogue == SG_EPI_BIAS || a.epilogue == SG_EPI_NONE)) {
     const int S = nkb_all >= 64 ? 8 : (nkb_all >= 16 ? 4 : 1);
     const size_t need = (size_t)S * ((a.rows + TC_BM - 1) / TC_BM) * TC_BM * a.N;
@@ -827,13 +852,14 @@ int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
     }
   }
   if (g_small_bn && !a.xf_ab) {
-    const int mt = ((a.rows + TC_BM - 1) / TC_BM) * ksplit;
+    const int mt = utt ? (a.rows / a.T) * ((a.T + TC_BM - 1) / TC_BM) : ((a.rows + TC_BM - 1) / TC_BM) * ksplit;
     while (bn >= 128 && (bn / 2) % 32 == 0 && a.N % (bn / 2) == 0 && (!a.out_bf16 || (bn / 2) % 64 == 0) &&
            2 * mt * (a.N / bn) <= g_num_sms)
       bn /= 2;
   }
   CUtensorMap mapA, mapB;
-  r = make_map(&mapA, a.A, a.op_bf16, (uint64_t)a.rows, (uint64_t)a.cin, (uint64_t)a.lda, TC_BM);
+  if (utt) r = make_map3(&mapA, a.A, 0, (uint64_t)(a.rows / a.T), (uint64_t)a.T, (uint64_t)a.T, (uint64_t)a.cin, (uint64_t)a.lda);
+  else r = make_map(&mapA, a.A, a.op_bf16, (uint64_t)a.rows, (uint64_t)a.cin, (uint64_t)a.lda, TC_BM);
   if (r != SG_OK) return r;
   if (!a.Wk) { sg_set_error("sg_conv_tc: K-major weights missing"); return SG_EINVAL; }
   r = make_map(&mapB, a.Wk, a.op_bf16, (uint64_t)a.N, (uint64_t)a.taps * a.cin, (uint64_t)a.taps * a.cin, (uint32_t)bn);
@@ -844,8 +870,10 @@ int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
   t.rows = a.rows; t.N = a.N; t.bn = bn; t.kchunks = a.cin / kbe; t.taps = a.taps; t.tap_step = a.tap_step;
   t.epilogue = a.epilogue; t.T = a.T > 0 ? a.T : 1; t.t_valid = a.t_valid;
   t.m_tiles = (a.rows + TC_BM - 1) / TC_BM; t.n_tiles = a.N / bn;
+  t.utt_T = 0; t.utt_tpu = 1; t.tap_base = 0;
+  if (utt) { t.utt_T = a.T; t.utt_tpu = (a.T + TC_BM - 1) / TC_BM; t.m_tiles = (a.rows / a.T) * t.utt_tpu; t.tap_base = a.tap_base; }
   t.xf_ab = reinterpret_cast<const uint4*>(a.xf_ab); t.xf_ld = a.xf_ld; t.xf_tv = a.xf_tv;
-  t.pf_dist = (a.taps == 1 || g_pf_all) ? g_pf_dist : 0;
+  t.pf_dist = (!utt && (a.taps == 1 || g_pf_all)) ? g_pf_dist : 0;
   t.issue_mode = g_issue_mode;
   t.stb = TC_A_BYTES + bn * TC_BK * 4; t.nst = (TC_STAGES * TC_STAGE_BYTES) / t.stb;
   if (t.nst > TC_MAX_STAGES) t.nst = TC_MAX_STAGES;
@@ -862,6 +890,9 @@ int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
   CUtensorMap mapO, mapO2;
   memset(&mapO2, 0, sizeof(mapO2));
   t.st_dual = 0; t.bits_T = a.bits_T; t.st_nutt = 0; t.st_stride = 0;
+  if (utt) {
+    r = make_map3(&mapO, a.out, 0, (uint64_t)(a.rows / a.T), (uint64_t)a.T, (uint64_t)a.T, (uint64_t)a.N, (uint64_t)a.ldo);
+  } else
   if (a.out_T > 0) {
     if (ksplit > 1 || a.T < TC_BM || a.rows % a.T != 0 || a.out_T > a.out_Tstride || a.out_T > a.T) {
       sg_set_error("sg_conv_tc: re-strided output needs T >= 128 rows per utterance and rows %% T == 0 (T=%d rows=%d)", a.T, a.rows);
@@ -879,7 +910,7 @@ int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
   // (modes 3 and 4 are not validated defaults: 3 adds the tf32-operand / bf16-output layer-1 forward (measured: no gain),
   //  4 adds fp32-output contractions - the tf32 mode and the i-vector UBM contraction: tests/test_gpu_tc.py and
   //  tests/test_gpu_iv.py pass with it, its throughput has not been measured yet)
-  if (ksplit == 1 && g_pair_bf16 && (a.op_bf16 || g_pair_bf16 >= 3) && (a.out_bf16 || (g_pair_bf16 >= 4 && !a.op_bf16)) && (!a.xf_ab || g_pair_xf) && bn % 32 == 0 && bn >= 64 && a.rows > 256 &&
+  if (!utt && ksplit == 1 && g_pair_bf16 && (a.op_bf16 || g_pair_bf16 >= 3) && (a.out_bf16 || (g_pair_bf16 >= 4 && !a.op_bf16)) && (!a.xf_ab || g_pair_xf) && bn % 32 == 0 && bn >= 64 && a.rows > 256 &&
       (g_pair_bf16 >= 2 || a.taps * t.kchunks >= 16)) {
     CUtensorMap mapBh;
     r = make_map(&mapBh, a.Wk, a.op_bf16, (uint64_t)a.N, (uint64_t)a.taps * a.cin, (uint64_t)a.taps * a.cin, (uint32_t)(bn / 2));

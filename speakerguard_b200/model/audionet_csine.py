@@ -51,11 +51,16 @@ def state_dict_from_params(p: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor
 
 class audionet_csine(nn.Module):
 
-    def __init__(self, extractor_file=None, num_class=None, label_encoder=None, device="cuda", params=None):
+    def __init__(self, extractor_file=None, num_class=None, label_encoder=None, device="cuda", params=None,
+                 precision="fp32"):
         """extractor_file: checkpoint path / state dict of the reference model (-> eval mode); without it the model is
         freshly initialised for training and ``num_class`` (or ``label_encoder``) is required, as in the reference.
-        ``params`` (engine naming, see Engine.load_audionet) may be given instead of a checkpoint for synthetic models."""
+        ``params`` (engine naming, see Engine.load_audionet) may be given instead of a checkpoint for synthetic models.
+        ``precision``: "fp32" (FFMA convolutions, the parity mode) or "tf32" (the eval-mode convolutions and their adjoints on
+        tcgen05 tiles with TF32 operands and fp32 storage - the precision class of the reference's own GPU default)."""
         super().__init__()
+        assert precision in ("fp32", "tf32")
+        self.precision = precision
         dev = torch.device(device)
         if dev.type != "cuda":
             raise _lib.SgError("speakerguard_b200.audionet_csine needs a CUDA device (no CPU fallback); got '%s'" % device)
@@ -120,7 +125,7 @@ class audionet_csine(nn.Module):
         v = self._version()
         if self.engine is not None and v == self._engine_version:
             return
-        eng = Engine(self.device)
+        eng = Engine(self.device, precision=self.precision)
         eng.load_audionet(params_from_state_dict({k: t.detach() for k, t in self.state_dict().items()}))
         self.engine, self._engine_version = eng, v
 
