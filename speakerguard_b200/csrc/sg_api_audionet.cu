@@ -93,6 +93,7 @@ struct AnWs {
   int* arg;
   // CW2 state
   float *inp, *w, *m, *v, *gmodel, *l2part, *loss1, *loss2, *dscores, *cst, *lower, *upper, *best_l2, *gbest_l2, *lossmean;
+  float* anstash;           // log-mel forward -> adjoint hand-over (spectrum + mel energies per frame)
   long long *dec, *best_score, *gbest_score;
   size_t bytes;
 };
@@ -128,6 +129,7 @@ static AnWs an_ws_layout(void* base, int B, int N, int Cp, bool cw2) {
     w.l2part = take((size_t)B * SG_CW2_CHUNKS); w.loss1 = take(B); w.loss2 = take(B); w.dscores = take((size_t)B * Cp);
     w.cst = take(B); w.lower = take(B); w.upper = take(B); w.best_l2 = take(B); w.gbest_l2 = take(B); w.lossmean = take(4);
     w.dec = (long long*)take((size_t)B * 2); w.best_score = (long long*)take((size_t)B * 2); w.gbest_score = (long long*)take((size_t)B * 2);
+    w.anstash = take((size_t)B * T0 * AN_STASH_FLOATS);
   }
   w.bytes = off;
   return w;
@@ -358,13 +360,13 @@ extern "C" int sg_cw2_audionet_run(sg_handle* h, const float* x, const int64_t* 
       h->launches += 2;
       PROF(h, SG_PROF_CW2, st, sg_cw2_prepare_launch(x, w.w, w.inp, w.l2part, w.loss2, B, N, st));
       h->launches += 1;
-      PROF(h, SG_PROF_AUDIONET, st, sg_an_logmel_fwd_launch(an->d_tables, w.inp, B, N, T0, w.feat, st));
+      const bool grad = it < p->max_iter;
+      PROF(h, SG_PROF_AUDIONET, st, sg_an_logmel_fwd_launch(an->d_tables, w.inp, B, N, T0, w.feat, st, grad ? w.anstash : nullptr));
       SG_TRY(an_cnn_fwd(h, w.feat, B, w, w.logits, st));
       compact_rows_kernel<<<(B * C + 255) / 256, 256, 0, st>>>(w.logits, Cp, scores, B, C);
       SG_LAUNCH_CHECK();
       h->launches += 3;
       SG_TRY(sg_argmax_rows_launch(scores, w.dec, B, C, p->decision_threshold, st));
-      const bool grad = it < p->max_iter;
       PROF(h, SG_PROF_LOSS, st, sg_loss_launch(scores, (const long long*)y, B, C, p->loss, w.loss1, grad ? w.dscores : nullptr, st));
       if (grad) {
         h->cw2_iters += 1;
@@ -372,7 +374,7 @@ extern "C" int sg_cw2_audionet_run(sg_handle* h, const float* x, const int64_t* 
         SG_LAUNCH_CHECK();
         SG_TRY(an_cnn_bwd(h, w.dlogits, B, w, w.dfeat, st));
         h->launches += 3;
-        PROF(h, SG_PROF_AUDIONET, st, sg_an_logmel_bwd_launch(an->d_tables, w.inp, B, N, T0, w.dfeat, w.dgw, w.gmodel, 1.0f, 0, st));
+        PROF(h, SG_PROF_AUDIONET, st, sg_an_logmel_bwd_launch(an->d_tables, w.inp, B, N, T0, w.dfeat, w.dgw, w.gmodel, 1.0f, 0, st, w.anstash));
         PROF(h, SG_PROF_CW2, st, sg_cw2_adam_launch(w.w, w.m, w.v, x, w.inp, w.gmodel, w.cst, B, N, p->lr, it + 1, st));
       }
       if (p->stop_early && p->stop_early_iter > 0 && it % p->stop_early_iter == 0) {   // attack/CW2.py:96-100

@@ -216,7 +216,7 @@ __device__ __forceinline__ float an_mel(const SgAnTables* T, const float* P, int
 // =============================================================================================
 __global__ void __launch_bounds__(AN_THREADS)
 an_logmel_fwd_kernel(const float* __restrict__ x, int N, int T_frames, int frames_per_cta, float* __restrict__ feat,
-                     const SgAnTables* __restrict__ gT) {
+                     const SgAnTables* __restrict__ gT, float* __restrict__ stash) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SgAnTables* T = reinterpret_cast<SgAnTables*>(smem_raw);
   an_copy_tables(T, gT);
@@ -235,6 +235,15 @@ an_logmel_fwd_kernel(const float* __restrict__ x, int N, int T_frames, int frame
     __syncwarp();
     const float me = an_mel(T, sre, lane);
     feat[((size_t)b * T_frames + t) * AN_MELS + lane] = AN_LOGSCALE * logf(fmaxf(me, 1e-16f));   // Preprocessor.py:111
+    if (stash != nullptr) {
+      // forward -> adjoint hand-over inside the CW2 loop: the spectrum and the mel energies of this frame (4.1 KB), so that
+      // the adjoint neither reloads the frame nor repeats the forward FFT
+      float* sp = stash + ((size_t)b * T_frames + t) * AN_STASH_FLOATS;
+      float4* s4 = reinterpret_cast<float4*>(sp);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) __stcs(s4 + r * 32 + lane, make_float4(X[2 * r].x, X[2 * r].y, X[2 * r + 1].x, X[2 * r + 1].y));
+      __stcs(sp + 1024 + lane, me);
+    }
     __syncwarp();
   }
 }
@@ -244,7 +253,8 @@ an_logmel_fwd_kernel(const float* __restrict__ x, int N, int T_frames, int frame
 // =============================================================================================
 __global__ void __launch_bounds__(AN_THREADS)
 an_logmel_bwd_frames_kernel(const float* __restrict__ x, int N, int T_frames, int frames_per_cta,
-                            const float* __restrict__ dfeat, float* __restrict__ dgw, const SgAnTables* __restrict__ gT) {
+                            const float* __restrict__ dfeat, float* __restrict__ dgw, const SgAnTables* __restrict__ gT,
+                            const float* __restrict__ stash) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SgAnTables* T = reinterpret_cast<SgAnTables*>(smem_raw);
   an_copy_tables(T, gT);
@@ -257,11 +267,23 @@ an_logmel_bwd_frames_kernel(const float* __restrict__ x, int N, int T_frames, in
   const int f0 = blockIdx.x * frames_per_cta, f1 = min(f0 + frames_per_cta, T_frames);
   for (int t = f0 + warp; t < f1; t += AN_WARPS) {
     float2 X[16];
-    an_frame_spectrum(X, xb, M, t, T, sre, sim, lane);
+    float me;
+    if (stash != nullptr) {
+      const float* sp = stash + ((size_t)b * T_frames + t) * AN_STASH_FLOATS;
+      const float4* s4 = reinterpret_cast<const float4*>(sp);
 #pragma unroll
-    for (int r = 0; r < 16; ++r) sre[lane + 32 * r] = X[r].x * X[r].x + X[r].y * X[r].y;
-    __syncwarp();
-    const float me = an_mel(T, sre, lane);
+      for (int r = 0; r < 8; ++r) {
+        const float4 v = __ldcs(s4 + r * 32 + lane);
+        X[2 * r] = make_float2(v.x, v.y); X[2 * r + 1] = make_float2(v.z, v.w);
+      }
+      me = __ldcs(sp + 1024 + lane);
+    } else {
+      an_frame_spectrum(X, xb, M, t, T, sre, sim, lane);
+#pragma unroll
+      for (int r = 0; r < 16; ++r) sre[lane + 32 * r] = X[r].x * X[r].x + X[r].y * X[r].y;
+      __syncwarp();
+      me = an_mel(T, sre, lane);
+    }
     const float dF = __ldg(dfeat + ((size_t)b * T_frames + t) * AN_MELS + lane);
     const float dmel = (me > 1e-16f) ? AN_LOGSCALE * dF / me : 0.f;   // clamp passes gradient only above the floor
     __syncwarp();
@@ -331,14 +353,23 @@ __device__ __forceinline__ float an_dw(const float* __restrict__ g, int T_frames
 }
 __global__ void an_overlap_add_kernel(const float* __restrict__ dgw, int N, int T_frames, float* __restrict__ dx,
                                       float scale, int accumulate) {
-  const int b = blockIdx.y, M = N - 1;
+  const int b = blockIdx.y, M = N - 1, lane = threadIdx.x & 31;
   const float* g = dgw + (size_t)b * T_frames * AN_WIN;
-  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
-    float v = 0.f;
-    if (n >= 1) v += an_dw(g, T_frames, M, n - 1);                  // w[n-1] = x[n] - 0.97 x[n-1]
-    if (n <= M - 1) v -= 0.97f * an_dw(g, T_frames, M, n);
-    const size_t gi = (size_t)b * N + n;
-    dx[gi] = accumulate ? dx[gi] + scale * v : scale * v;
+  // x[n] feeds w[n-1] = x[n] - 0.97 x[n-1] and w[n]: dx[n] = dw[n-1] - 0.97 dw[n].  Every thread forms dw[n] once; dw[n-1] is
+  // the left neighbour's value (lane 0 computes it itself).  The loop bound is warp-uniform so the shuffle is always full.
+  const int nblk = (N + blockDim.x * gridDim.x - 1) / (blockDim.x * gridDim.x);
+  for (int i = 0; i < nblk; ++i) {
+    const int n = (i * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+    const float cur = (n <= M - 1) ? an_dw(g, T_frames, M, n) : 0.f;
+    float prev = __shfl_up_sync(0xffffffffu, cur, 1);
+    if (lane == 0) prev = (n >= 1 && n - 1 <= M - 1) ? an_dw(g, T_frames, M, n - 1) : 0.f;
+    if (n < N) {
+      float v = 0.f;
+      if (n >= 1) v += prev;                                          // w[n-1] = x[n] - 0.97 x[n-1]
+      if (n <= M - 1) v -= 0.97f * cur;
+      const size_t gi = (size_t)b * N + n;
+      dx[gi] = accumulate ? dx[gi] + scale * v : scale * v;
+    }
   }
 }
 
@@ -511,16 +542,16 @@ static int an_fpc(int B, int T) {
   while (fpc > 8 && (long long)B * ((T + fpc - 1) / fpc) < 444) fpc >>= 1;
   return fpc;
 }
-int sg_an_logmel_fwd_launch(const SgAnTables* dT, const float* x, int B, int N, int T, float* feat, cudaStream_t st) {
+int sg_an_logmel_fwd_launch(const SgAnTables* dT, const float* x, int B, int N, int T, float* feat, cudaStream_t st, float* stash) {
   const int fpc = an_fpc(B, T);
-  an_logmel_fwd_kernel<<<dim3((T + fpc - 1) / fpc, B), AN_THREADS, an_smem(), st>>>(x, N, T, fpc, feat, dT);
+  an_logmel_fwd_kernel<<<dim3((T + fpc - 1) / fpc, B), AN_THREADS, an_smem(), st>>>(x, N, T, fpc, feat, dT, stash);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }
 int sg_an_logmel_bwd_launch(const SgAnTables* dT, const float* x, int B, int N, int T, const float* dfeat, float* dgw,
-                            float* dx, float scale, int accumulate, cudaStream_t st) {
+                            float* dx, float scale, int accumulate, cudaStream_t st, const float* stash) {
   const int fpc = an_fpc(B, T);
-  an_logmel_bwd_frames_kernel<<<dim3((T + fpc - 1) / fpc, B), AN_THREADS, an_smem(), st>>>(x, N, T, fpc, dfeat, dgw, dT);
+  an_logmel_bwd_frames_kernel<<<dim3((T + fpc - 1) / fpc, B), AN_THREADS, an_smem(), st>>>(x, N, T, fpc, dfeat, dgw, dT, stash);
   SG_LAUNCH_CHECK();
   an_overlap_add_kernel<<<dim3((N + 1023) / 1024, B), 256, 0, st>>>(dgw, N, T, dx, scale, accumulate);
   SG_LAUNCH_CHECK();

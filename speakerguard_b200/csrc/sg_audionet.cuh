@@ -25,9 +25,11 @@ struct alignas(16) SgAnTables {
 
 int sg_an_tables_build(SgAnTables* host_out);
 int sg_an_init();
-int sg_an_logmel_fwd_launch(const SgAnTables* dT, const float* x, int B, int N, int T, float* feat, cudaStream_t st);
+#define AN_STASH_FLOATS 1056             // per frame: spectrum X[16][32] float2 (as float4 pairs) + mel energies [32]
+int sg_an_logmel_fwd_launch(const SgAnTables* dT, const float* x, int B, int N, int T, float* feat, cudaStream_t st,
+                            float* stash = nullptr);
 int sg_an_logmel_bwd_launch(const SgAnTables* dT, const float* x, int B, int N, int T, const float* dfeat, float* dgw,
-                            float* dx, float scale, int accumulate, cudaStream_t st);
+                            float* dx, float scale, int accumulate, cudaStream_t st, const float* stash = nullptr);
 int sg_maxpool2_fwd_launch(const float* in, float* out, int B, int T, int C, cudaStream_t st);
 int sg_maxpool2_bwd_launch(const float* in, const float* dout, float* din, int B, int T, int C, cudaStream_t st);
 int sg_globalmax_fwd_launch(const float* in, float* out, int* arg, int B, int T, int Tv, int C, cudaStream_t st);
