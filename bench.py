@@ -753,7 +753,8 @@ def xv_leg(args, precision, steps, warmup, e2e_steps, rank, world, local, want_m
     tpath = os.path.join(ROOT, "profiles", "conv_tc_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get(precision, {}).get("dram_bytes_per_launch_avg")
+            tj = json.load(f)
+            traffic = (tj.get(precision + "_round2") or tj.get(precision, {})).get("dram_bytes_per_launch_avg")
     roof = {"bound": "tensor",
             "kernel": "TDNN conv-as-GEMM: ALL forward + dgrad launches of the step (conv_tc_kernel incl. the layer-5 dgrad with the "
                       "fused pooling adjoint and layer 1's tap gather)" if precision != "fp32" else
