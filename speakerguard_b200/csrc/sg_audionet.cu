@@ -329,16 +329,19 @@ an_logmel_bwd_frames_kernel(const float* __restrict__ x, int N, int T_frames, in
 
 // backward, stage 2: gather overlap-add through the reflect padding and the pre-emphasis -> dx [B,N]
 __device__ __forceinline__ float an_dpad(const float* __restrict__ g, int T_frames, int q) {
-  // sum over frames t of dgw[t][q - 160 t], q = shifted padded position (frame t covers [160 t, 160 t + 800))
-  float s = 0.f;
-  int t_hi = q / AN_HOP;
-  if (t_hi > T_frames - 1) t_hi = T_frames - 1;
-  int t_lo = (q - AN_WIN + AN_HOP) / AN_HOP;                        // ceil((q - 799) / 160)
-  if (q - AN_WIN + 1 <= 0) t_lo = 0;
-  for (int t = t_lo; t <= t_hi; ++t) {
-    const int ii = q - AN_HOP * t;
-    if (ii >= 0 && ii < AN_WIN) s += __ldg(g + (size_t)t * AN_WIN + ii);
+  // sum over frames t of dgw[t][q - 160 t], q = shifted padded position (frame t covers [160 t, 160 t + 800)): exactly the five
+  // frames t_hi - 4 .. t_hi with t_hi = q / 160 (offsets (q % 160) + 160 k < 800), those inside [0, T) - five independent,
+  // predicated loads, added in increasing frame order
+  const int t_hi = q / AN_HOP, r = q - AN_HOP * t_hi;
+  float v[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const int t = t_hi - 4 + k;
+    v[k] = (t >= 0 && t < T_frames) ? __ldg(g + (size_t)t * AN_WIN + r + AN_HOP * (4 - k)) : 0.f;
   }
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) s += v[k];
   return s;
 }
 __device__ __forceinline__ float an_dw(const float* __restrict__ g, int T_frames, int M, int j) {
@@ -376,34 +379,37 @@ __global__ void an_overlap_add_kernel(const float* __restrict__ dgw, int N, int 
 // =============================================================================================
 // CNN helpers: MaxPool1d(2,2) over channels-last [B,T,C] and the global max over time
 // =============================================================================================
+// One thread per pooled position and 4 channels (C is a multiple of 4: 32 / 64 / 128), 32-bit index arithmetic: the scalar
+// forms with 64-bit div / mod per element ran at 1.4 TB/s.
 __global__ void maxpool2_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int T, int C) {
-  const int To = T / 2;
-  const size_t n = (size_t)B * To * C;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    const size_t bt = i / C;
-    const int t = (int)(bt % To), b = (int)(bt / To);
-    const float* p = in + ((size_t)b * T + 2 * t) * C + c;
-    out[i] = fmaxf(p[0], p[C]);
+  const int To = T / 2, C4 = C >> 2;
+  const unsigned n = (unsigned)B * To * C4;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned c4 = i % C4, bt = i / C4, t = bt % To, b = bt / To;
+    const float4* p = reinterpret_cast<const float4*>(in + ((size_t)b * T + 2 * t) * C) + c4;
+    const float4 u = p[0], v = p[C4];
+    reinterpret_cast<float4*>(out)[i] = make_float4(fmaxf(u.x, v.x), fmaxf(u.y, v.y), fmaxf(u.z, v.z), fmaxf(u.w, v.w));
   }
 }
-// routes the gradient to the arg-max (first element on ties, like torch) and applies the ReLU mask of `in`
+// routes the gradient to the arg-max (first element on ties, like torch) and applies the ReLU mask of `in`; a trailing odd
+// frame receives no gradient
 __global__ void maxpool2_bwd_kernel(const float* __restrict__ in, const float* __restrict__ dout, float* __restrict__ din,
                                     int B, int T, int C) {
-  const int To = T / 2;
-  const size_t n = (size_t)B * T * C;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    const size_t bt = i / C;
-    const int t = (int)(bt % T), b = (int)(bt / T);
-    float g = 0.f;
-    const int tp = t >> 1;
-    if (tp < To) {
-      const float* p = in + ((size_t)b * T + 2 * tp) * C + c;
-      const bool first = p[0] >= p[C];
-      if (((t & 1) == 0) == first) g = dout[((size_t)b * To + tp) * C + c];
-    }
-    din[i] = (in[i] > 0.f) ? g : 0.f;
+  const int To = T / 2, C4 = C >> 2, Th = (T + 1) / 2;
+  const unsigned n = (unsigned)B * Th * C4;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned c4 = i % C4, bt = i / C4, t = bt % Th, b = bt / Th;
+    float4* q = reinterpret_cast<float4*>(din + ((size_t)b * T + 2 * t) * C) + c4;
+    if ((int)t >= To) { q[0] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }     // the odd last frame
+    const float4* p = reinterpret_cast<const float4*>(in + ((size_t)b * T + 2 * t) * C) + c4;
+    const float4 u = p[0], v = p[C4];
+    const float4 g = reinterpret_cast<const float4*>(dout + ((size_t)b * To + t) * C)[c4];
+    float4 a, d;
+    a.x = (u.x >= v.x && u.x > 0.f) ? g.x : 0.f;  d.x = (!(u.x >= v.x) && v.x > 0.f) ? g.x : 0.f;
+    a.y = (u.y >= v.y && u.y > 0.f) ? g.y : 0.f;  d.y = (!(u.y >= v.y) && v.y > 0.f) ? g.y : 0.f;
+    a.z = (u.z >= v.z && u.z > 0.f) ? g.z : 0.f;  d.z = (!(u.z >= v.z) && v.z > 0.f) ? g.z : 0.f;
+    a.w = (u.w >= v.w && u.w > 0.f) ? g.w : 0.f;  d.w = (!(u.w >= v.w) && v.w > 0.f) ? g.w : 0.f;
+    q[0] = a; q[C4] = d;
   }
 }
 // global max over time (audionet_csine.py:203): out [B,C], arg [B,C]
