@@ -123,7 +123,12 @@ feco_kmeans_kernel(const float* __restrict__ feat, int ld, int n, int dim, int k
 //    with mma.sync m16n8k8 in error-compensated TF32 (x = hi + lo, c = hi + lo, products lo.hi + hi.lo + hi.hi accumulated
 //    in fp32: ~2^-21 relative, so the arg-min is the fp32 one up to exact ties, which go to the lower index as before);
 //    frames / centroids are padded to 32 floats with a row stride of 36 (fragment loads are bank-conflict free);
-//  * k-means++ sampling by a warp prefix scan instead of thread 0 walking the n distances (k = n / 2 rounds of it);
+//  * k-means++ sampling by a warp prefix scan instead of thread 0 walking the n distances (k = n / 2 rounds of it).  The
+//    seeding is what remains: ~80 % of the kernel, Lloyd converges in 3 - 4 iterations from it (the time does not change for
+//    max_iter >= 5), and it is a chain of k dependent rounds per utterance (pick -> distances -> prefix -> pick), so it is
+//    bound by per-round latency x resident CTAs (2 per SM: 122 registers, 92 KB), not by instructions: a block-wide
+//    prefix sampler, skipping empty slots, shorter FMA chains and a third CTA per SM (hi / lo split redone at every use)
+//    were each measured at +-0 or worse.  One warp per utterance (no block barriers, 4 - 5 utterances per SM) is the next step;
 //  * centroid update through per-cluster member lists (members in increasing frame order: deterministic sums):
 //    k x n id comparisons + k x 32 short sums, where thread c used to scan all n frames once per dimension.
 #define KM_DP 36
@@ -334,33 +339,58 @@ static size_t kmeans2_smem(int n, int k) {
 }
 
 // out[b,i,:] = mean of feat[b, ids==i, :]; empty cluster -> feat[b,i,:] when force (feature_level.py:205-216)
-__global__ void feco_means_fwd_kernel(const float* __restrict__ feat, int ld_in, const int* __restrict__ ids, int n, int dim,
+// One WARP per utterance (lane = feature dimension): the frames are walked once, in order, each added to its cluster's row
+// of a shared-memory accumulator - sums in increasing frame order, no atomics.  (The first version launched one 32-thread
+// block per (cluster, utterance), each scanning all n ids: 192 000 blocks for 1280 utterances, 0.4 ms.)
+__global__ void feco_means_fwd_kernel(const float* __restrict__ feat, int ld_in, const int* __restrict__ ids, int B, int n, int dim,
                                       int k, int force, float* __restrict__ out, int ld_out, int* __restrict__ counts) {
-  const int b = blockIdx.y, i = blockIdx.x, d = threadIdx.x;
+  extern __shared__ __align__(16) float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+  const int b = blockIdx.x * wpc + warp;
+  if (b >= B) return;
+  float* sums = sm + (size_t)warp * ((size_t)k * 32 + k);      // [k][32]
+  int* cnt = reinterpret_cast<int*>(sums + (size_t)k * 32);    // [k]
+  for (int i = lane; i < k * 32; i += 32) sums[i] = 0.f;
+  for (int i = lane; i < k; i += 32) cnt[i] = 0;
+  __syncwarp();
   const int* ib = ids + (size_t)b * n;
   const float* fb = feat + (size_t)b * n * ld_in;
-  float s = 0.f;
-  int m = 0;
-  for (int j = 0; j < n; ++j)
-    if (ib[j] == i) { ++m; if (d < dim) s += fb[(size_t)j * ld_in + d]; }
-  float v = 0.f;
-  if (d < dim) v = m > 0 ? s / (float)m : ((force && i < n) ? fb[(size_t)i * ld_in + d] : 0.f);
-  if (d < ld_out) out[((size_t)b * k + i) * ld_out + d] = v;
-  if (d == 0) counts[(size_t)b * k + i] = m;
-}
-// dfeat[b,j,:] = dout[b, ids[j], :] / count[ids[j]]  (+ dout[b,j,:] if cluster j is empty and force)
-__global__ void feco_means_bwd_kernel(const float* __restrict__ dout, int ld_out, const int* __restrict__ ids,
-                                      const int* __restrict__ counts, int n, int dim, int k, int force,
-                                      float* __restrict__ dfeat, int ld_in) {
-  const int b = blockIdx.y, j = blockIdx.x, d = threadIdx.x;
-  if (d >= ld_in) return;
-  const int id = ids[(size_t)b * n + j];
-  float g = 0.f;
-  if (d < dim) {
-    if (id >= 0 && id < k) g = dout[((size_t)b * k + id) * ld_out + d] / (float)counts[(size_t)b * k + id];
-    if (force && j < k && counts[(size_t)b * k + j] == 0) g += dout[((size_t)b * k + j) * ld_out + d];
+  for (int j0 = 0; j0 < n; j0 += 32) {
+    const int myid = (j0 + lane < n) ? ib[j0 + lane] : -1;
+    const int m = min(32, n - j0);
+    for (int u = 0; u < m; ++u) {
+      const int id = __shfl_sync(0xffffffffu, myid, u);
+      if (id >= 0 && id < k) {
+        if (lane < dim) sums[id * 32 + lane] += fb[(size_t)(j0 + u) * ld_in + lane];
+        if (lane == 0) cnt[id] += 1;
+      }
+    }
   }
-  dfeat[((size_t)b * n + j) * ld_in + d] = g;
+  __syncwarp();
+  for (int i = 0; i < k; ++i) {
+    const int m = cnt[i];
+    float v = 0.f;
+    if (lane < dim) v = m > 0 ? sums[i * 32 + lane] / (float)m : ((force && i < n) ? fb[(size_t)i * ld_in + lane] : 0.f);
+    if (lane < ld_out) out[((size_t)b * k + i) * ld_out + lane] = v;
+  }
+  for (int i = lane; i < k; i += 32) counts[(size_t)b * k + i] = cnt[i];
+}
+// dfeat[b,j,:] = dout[b, ids[j], :] / count[ids[j]]  (+ dout[b,j,:] if cluster j is empty and force): a warp per (b, j) row
+__global__ void feco_means_bwd_kernel(const float* __restrict__ dout, int ld_out, const int* __restrict__ ids,
+                                      const int* __restrict__ counts, int B, int n, int dim, int k, int force,
+                                      float* __restrict__ dfeat, int ld_in) {
+  const int lane = threadIdx.x & 31;
+  const unsigned rows = (unsigned)B * n, wpg = (gridDim.x * blockDim.x) >> 5;
+  for (unsigned r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += wpg) {
+    const unsigned b = r / n, j = r - b * n;
+    const int id = ids[r];
+    float g = 0.f;
+    if (lane < dim) {
+      if (id >= 0 && id < k) g = dout[((size_t)b * k + id) * ld_out + lane] / (float)counts[(size_t)b * k + id];
+      if (force && (int)j < k && counts[(size_t)b * k + j] == 0) g += dout[((size_t)b * k + j) * ld_out + lane];
+    }
+    if (lane < ld_in) dfeat[(size_t)r * ld_in + lane] = g;
+  }
 }
 
 size_t sg_kmeans_smem(int n, int dim, int k) {
@@ -371,6 +401,7 @@ size_t sg_kmeans_smem(int n, int dim, int k) {
 #define KM2_MAX_SMEM (220 * 1024)
 int sg_kmeans_init() {
   SG_CUDA_CHECK(cudaFuncSetAttribute(feco_kmeans2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KM2_MAX_SMEM));
+  SG_CUDA_CHECK(cudaFuncSetAttribute(feco_means_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   return SG_OK;
 }
 
@@ -395,13 +426,21 @@ int sg_feco_kmeans_launch(const float* feat, int ld, int B, int n, int dim, int 
 }
 int sg_feco_means_fwd_launch(const float* feat, int ld_in, const int* ids, int B, int n, int dim, int k, int force,
                              float* out, int ld_out, int* counts, cudaStream_t st) {
-  feco_means_fwd_kernel<<<dim3(k, B), 32, 0, st>>>(feat, ld_in, ids, n, dim, k, force, out, ld_out, counts);
+  const size_t per_warp = ((size_t)k * 32 + k) * sizeof(float);
+  if (per_warp > 200 * 1024) { sg_set_error("FeCo means: too many clusters for the shared-memory accumulator (k=%d)", k); return SG_EUNSUPPORTED; }
+  int wpc = (int)((96 * 1024) / per_warp);                       // warps (utterances) per CTA: <= 96 KB of accumulators
+  wpc = wpc < 1 ? 1 : (wpc > 8 ? 8 : wpc);
+  const size_t smem = per_warp * wpc;
+  feco_means_fwd_kernel<<<(B + wpc - 1) / wpc, wpc * 32, smem, st>>>(feat, ld_in, ids, B, n, dim, k, force, out, ld_out, counts);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }
 int sg_feco_means_bwd_launch(const float* dout, int ld_out, const int* ids, const int* counts, int B, int n, int dim, int k,
                              int force, float* dfeat, int ld_in, cudaStream_t st) {
-  feco_means_bwd_kernel<<<dim3(n, B), 32, 0, st>>>(dout, ld_out, ids, counts, n, dim, k, force, dfeat, ld_in);
+  const size_t rows = (size_t)B * n;
+  size_t blocks = (rows + 7) / 8;                                 // 8 warps per block, one row per warp and iteration
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  feco_means_bwd_kernel<<<(unsigned)blocks, 256, 0, st>>>(dout, ld_out, ids, counts, B, n, dim, k, force, dfeat, ld_in);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }
