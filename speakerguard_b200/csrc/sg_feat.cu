@@ -953,18 +953,31 @@ __global__ void cmvn_prefix_kernel(const float* __restrict__ in, int ld_in, floa
   const float* ib = in + (size_t)b * T * ld_in;
   float* ob = out + (size_t)b * T * ld_out;
   const bool cin = c < ncol && c < ld_in;
-  if (r == 0) {
+  // prefix sums in fp64, eight segments in parallel (warp r owns frames [r * seg, (r + 1) * seg)): a local running sum per
+  // segment, then the exclusive prefix of the eight segment totals is added in place.  (One warp walking all T frames was a
+  // chain of T dependent fp64 adds with the CTA - alone on its SM: 128 KB of prefixes - waiting for it: 0.55 ms at B = 256,
+  // T = 500, 72 columns.)
+  __shared__ double seg_tot[8][32];
+  const int seg = (T + 7) / 8, t0 = r * seg, t1 = min(T, t0 + seg);
+  if (r == 0) cm_prefix[lc] = 0.0;
+  {
     double acc = 0.0;
-    cm_prefix[lc] = 0.0;
-    int t = 0;
-    for (; t + 8 <= T; t += 8) {                                    // loads issued together, adds in order
+    int t = t0;
+    for (; t + 8 <= t1; t += 8) {                                   // loads issued together, adds in order
       float v[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) v[u] = cin ? ib[(size_t)(t + u) * ld_in + c] : 0.f;
 #pragma unroll
       for (int u = 0; u < 8; ++u) { acc += (double)v[u]; cm_prefix[(size_t)(t + u + 1) * 32 + lc] = acc; }
     }
-    for (; t < T; ++t) { acc += cin ? (double)ib[(size_t)t * ld_in + c] : 0.0; cm_prefix[(size_t)(t + 1) * 32 + lc] = acc; }
+    for (; t < t1; ++t) { acc += cin ? (double)ib[(size_t)t * ld_in + c] : 0.0; cm_prefix[(size_t)(t + 1) * 32 + lc] = acc; }
+    seg_tot[r][lc] = acc;
+  }
+  __syncthreads();
+  {
+    double off = 0.0;
+    for (int q = 0; q < r; ++q) off += seg_tot[q][lc];
+    if (r > 0) for (int t = t0; t < t1; ++t) cm_prefix[(size_t)(t + 1) * 32 + lc] += off;
   }
   __syncthreads();
   if (c >= ld_out) return;
