@@ -247,3 +247,28 @@ def test_cw2_in_tf32_mode_reaches_the_reference_outcome(model_tf32):
     assert suc == g["cw2.success"].tolist()
     # outcome parity as in the fp32 test; measured: the best distortions are within 24 % of the reference's (fp32 mode: 15 %)
     np.testing.assert_allclose(l2(adv).numpy(), l2(ref.unsqueeze(1)).numpy(), rtol=0.4)
+
+
+def test_cw2_at_baseline_hyperparameters_vs_oracle(model, params):
+    """BASELINE configs[2]'s setting - targeted, initial_const 1e-3, lr 1e-2, binary search over the constant, early-stop check
+    every `stop_early_iter` - on a small slice with the iteration counts cut so that the CPU oracle finishes in seconds
+    (B = 3, 8 search steps x 40 iterations instead of 9 x 1000; the constant climbs from 1e-3 by x 10 per failed step, so the
+    later steps succeed): the per-utterance outcome of the search (success flags, the best distortion) must match the oracle's."""
+    from speakerguard_b200.attack.CW2 import CW2
+    B, N = 3, 16000
+    x = wave(B, N, seed=99)
+    with torch.no_grad():
+        tgt = O.audionet_forward(x[:, 0], params).topk(2, dim=1)[1][:, 1]        # target = the runner-up class (!= prediction)
+    kw = dict(targeted=True, initial_const=1e-3, binary_search_steps=8, max_iter=40, stop_early=True, stop_early_iter=40, lr=1e-2)
+    adv, suc = CW2(model, batch_size=B, verbose=0, **kw).attack(x.cuda(), tgt.cuda())
+    xo, suc_o, info = O.cw2_attack(x[:, 0], tgt, lambda z: O.audionet_forward(z, params), **kw)
+    l2 = lambda a: (a.flatten(1) - x.flatten(1)).pow(2).sum(1)
+    l2_g, l2_o = l2(adv.cpu()), l2(xo.unsqueeze(1))
+    print("targeted CW2 (BASELINE hyper-parameters, reduced iterations): success", suc, "oracle", suc_o,
+          "L2", l2_g.tolist(), "oracle", l2_o.tolist(), "const", info["const"].tolist())
+    assert [bool(s) for s in suc] == [bool(s) for s in suc_o]
+    for b in range(B):
+        if suc_o[b]:
+            assert abs(float(l2_g[b]) - float(l2_o[b])) <= 0.05 * float(l2_o[b]) + 1e-6      # measured: equal to 7 digits
+        else:
+            assert torch.equal(adv[b].cpu(), x[b])                                # unsuccessful: the clean input is returned
