@@ -128,7 +128,9 @@ feco_kmeans_kernel(const float* __restrict__ feat, int ld, int n, int dim, int k
 //    max_iter >= 5), and it is a chain of k dependent rounds per utterance (pick -> distances -> prefix -> pick), so it is
 //    bound by per-round latency x resident CTAs (2 per SM: 122 registers, 92 KB), not by instructions: a block-wide
 //    prefix sampler, skipping empty slots, shorter FMA chains and a third CTA per SM (hi / lo split redone at every use)
-//    were each measured at +-0 or worse.  One warp per utterance (no block barriers, 4 - 5 utterances per SM) is the next step;
+//    were each measured at +-0 or worse, and so was running the seeding on a single warp without block barriers (1.24 -> 1.58 ms:
+//    the rounds also carry n x 32 x 2 flops each, 90 k warp instructions per utterance in total).  What is left is residency:
+//    92 KB and 122 registers allow two CTAs per SM, 27 % issue utilisation;
 //  * centroid update through per-cluster member lists (members in increasing frame order: deterministic sums):
 //    k x n id comparisons + k x 32 short sums, where thread c used to scan all n frames once per dimension.
 #define KM_DP 36
