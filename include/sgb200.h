@@ -227,7 +227,14 @@ int sg_xv_forward(sg_handle* h, const float* x, int B, int N, int dither_mode, c
  * sg_cw2_audionet_run: CW2.attack_batch (attack/CW2.py:41-132) entirely on the device: tanh-space
  *   iterate, clipped margin loss, L2 term, Adam (lr, betas 0.9/0.999, eps 1e-8), best-example
  *   tracking, per-utterance binary search on c; the only host syncs are the early-stop checks every
- *   stop_early_iter iterations.  best_x [B,N] out, success [B] (0/1) out. */
+ *   stop_early_iter iterations (one 4-byte read per check; at BASELINE's stop_early_iter = max_iter = 1000 that is two per
+ *   search step, which is why the check stays on the host).  best_x [B,N] out, success [B] (0/1) out.
+ * Precision: sg_set_precision(h, SG_PREC_FP32) runs the CNN's convolutions and their adjoints as fp32 FFMA (parity mode);
+ *   TF32 / BF16 run them on the tensor cores with TF32 operands and fp32 storage (conv_tc_kernel's utterance-tiled mode:
+ *   3-D TMA maps (channel, frame, utterance), frames outside the utterance zero-fill = the 'same' padding of
+ *   audionet_csine.py:66-118); the log-mel front end, pooling, fc layer and CW2 arithmetic are fp32 in every mode.
+ *   Inside sg_cw2_audionet_run the log-mel forward hands its spectrum and mel energies to the adjoint (4.2 KB per frame in
+ *   the workspace) instead of the adjoint repeating the FFT. */
 typedef struct {
   const float* conv1_w;
   const float* conv1_b;

@@ -164,7 +164,8 @@ def test_bf16_network_vs_fp32_network():
 @pytest.mark.parametrize("prec", ["tf32", "bf16"])
 def test_fused_pgd_loop_in_tensor_core_modes_matches_fp32_outcome(prec):
     """PGD-5 through sg_pgd_run in the tensor-core modes: same decisions / success as the fp32 parity mode on this
-    batch, iterates inside the epsilon ball, and >= 90 % of the perturbation signs equal after 5 steps."""
+    batch, iterates inside the epsilon ball, >= 95.4 % of the perturbation signs equal after 5 steps and the final loss within
+    1.4e-3 (<= 2x what was measured on B200: 97.7 % / 98.4 % and 2.7e-4 / 6.6e-4 for bf16 / tf32)."""
     from oracle import sg_oracle as O
     from speakerguard_b200 import _lib
     from speakerguard_b200.engine import Engine, make_loss_params
@@ -187,8 +188,8 @@ def test_fused_pgd_loop_in_tensor_core_modes_matches_fp32_outcome(prec):
     agree = float((torch.sign(xa1 - x.cpu()) == torch.sign(xa0 - x.cpu())).float().mean())
     print(f"{prec}: perturbation sign agreement after 5 PGD steps {agree:.4f}; final loss rel diff "
           f"{float((h1[-1] - h0[-1]).abs().max() / h0[-1].abs().max()):.3e}")
-    assert agree > 0.90
-    assert float((h1[-1] - h0[-1]).abs().max()) < 0.05 * float(h0[-1].abs().max())
+    assert agree > 0.954
+    assert float((h1[-1] - h0[-1]).abs().max()) < 1.4e-3 * float(h0[-1].abs().max())
 
 
 def test_pool_adjoint_fused_into_layer5_dgrad_matches_two_kernel_form():
