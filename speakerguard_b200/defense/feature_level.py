@@ -40,7 +40,7 @@ def kmeans_ids(feat, k, seed=None, max_iter=100, tol=0.01):
     return eng.feco_kmeans(feat.detach(), k, seed=seed, max_iter=max_iter, tol=tol)
 
 
-def FEATURE_COMPRESSION(feat, method='kmeans', param=0.5, other_param='L2', seed=None, ids=None):
+def FEATURE_COMPRESSION(feat, method='kmeans', param=0.5, other_param='L2', seed=None, ids=None, max_iter=100, tol=0.01):
     if method != 'kmeans':
         raise NotImplementedError('speakerguard_b200 FeCo supports method="kmeans" (warped_kmeans stays with the reference)')
     if other_param != 'L2':
@@ -50,7 +50,7 @@ def FEATURE_COMPRESSION(feat, method='kmeans', param=0.5, other_param='L2', seed
     k = int(n * param)
     force = B > 1                                   # feature_level.py:37
     if ids is None:
-        ids = kmeans_ids(feat, k, seed=seed)
+        ids = kmeans_ids(feat, k, seed=seed, max_iter=max_iter, tol=tol)
     out = _FeCoMeans.apply(feat, ids, k, True)
     if not force:                                   # batch of one: empty clusters are dropped, as in the reference
         counts = torch.bincount(ids[0].long(), minlength=k)
@@ -59,8 +59,8 @@ def FEATURE_COMPRESSION(feat, method='kmeans', param=0.5, other_param='L2', seed
     return out
 
 
-def FeCo(feat, method='kmeans', param=0.5, other_param='L2', seed=None, ids=None):
-    return FEATURE_COMPRESSION(feat, method, param, other_param, seed=seed, ids=ids)
+def FeCo(feat, method='kmeans', param=0.5, other_param='L2', seed=None, ids=None, max_iter=100, tol=0.01):
+    return FEATURE_COMPRESSION(feat, method, param, other_param, seed=seed, ids=ids, max_iter=max_iter, tol=tol)
 
 
 class FeCoDefense:
@@ -74,7 +74,7 @@ class FeCoDefense:
         self.max_iter, self.tol = int(max_iter), float(tol)
 
     def __call__(self, feat):
-        return FeCo(feat, self.method, self.param, self.other_param)
+        return FeCo(feat, self.method, self.param, self.other_param, max_iter=self.max_iter, tol=self.tol)
 
     def fusable(self):
         return self.method == 'kmeans' and self.other_param == 'L2' and 0.0 < self.param <= 1.0
