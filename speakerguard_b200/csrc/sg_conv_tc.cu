@@ -829,7 +829,10 @@ int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
   while (bn > 32 && a.N % bn != 0) bn -= 32;     // largest N-tile (multiple of 32, <= 256) dividing N
   // (Narrower tiles against wave quantisation - B = 128 x 300 frames is 300 pair tiles on 74 pairs = 4.05 -> 5 rounds - were
   // measured and rejected: 128-column tiles run the 512-channel layers 55 % slower (A is re-read once more per output column
-  // and the tensor pipe waits on shared memory), 112.8 k vs 143.2 k utt-iter/s at B = 128.  SGB200_TC_BN caps the width for A/B runs.)
+  // and the tensor pipe waits on shared memory), 112.8 k vs 143.2 k utt-iter/s at B = 128.  SGB200_TC_BN caps the width for A/B runs.
+  // Narrow tiles for the LAST wave only - the four full waves as one launch, the 4 leftover tiles as a second launch of sixteen
+  // 64-column tiles - were measured too: 150.4 k vs 152.0 k (a k-block costs ~650 cycles whatever its N, so a quarter-width
+  // tile is not a quarter of the time).)
   if (a.N % bn != 0) { sg_set_error("sg_conv_tc: N=%d is not a multiple of 32", a.N); return SG_EINVAL; }
   // Small problems (the head's fc1 / LDA contractions: B rows): with 256-column tiles only m_tiles x N/256 SMs work, and each
   // pulls its whole A + B stream through one SM's L2 port (the B = 1024 fc1 forward ran 16 CTAs for 41 us).  Narrower tiles

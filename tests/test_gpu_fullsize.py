@@ -45,8 +45,12 @@ def _attack(eng, x, y, iters=3, dither=None, **kw):
     return xa, dec, sc
 
 
-def test_full_batch_equals_its_slices_and_is_reproducible(eng, batch):
+@pytest.mark.parametrize("nb", [1024, 128])
+def test_full_batch_equals_its_slices_and_is_reproducible(eng, batch, nb):
+    """nb = 1024: the benched batch; nb = 128: the per-GPU batch of the 8-way strong-scaling split, where the long-K layers'
+    last wave of pair tiles runs as a separate launch on 64-column tiles (sg_conv_tc: tail split)."""
     x, y = batch
+    x, y = x[:nb].contiguous(), y[:nb].contiguous()
     xa, dec, sc = _attack(eng, x, y)
     # invariants of the iterate (attack/FGSM.py:65-68, attack/PGD.py:48-49)
     assert float((xa - x).abs().max()) <= 0.002 + 1e-7 and float(xa.abs().max()) <= 1.0
@@ -56,7 +60,7 @@ def test_full_batch_equals_its_slices_and_is_reproducible(eng, batch):
     cks = lambda t: t.double().sum(1)
     assert torch.equal(cks(xa), cks(xb)) and torch.equal(xa, xb) and torch.equal(dec, dec_b) and torch.equal(sc, sc_b)
     # slices at their global offsets (first / middle / last; 8 and 3 utterances: tile-straddling and ragged cases)
-    for lo, hi in ((0, 8), (509, 517), (1021, 1024)):
+    for lo, hi in ((0, 8), (nb // 2 - 3, nb // 2 + 5), (nb - 3, nb)):
         xs, ds, ss = _attack(eng, x[lo:hi].contiguous(), y[lo:hi].contiguous(), utt_offset=lo)
         assert torch.equal(xs, xa[lo:hi]), f"slice [{lo}:{hi}) differs from the full batch"
         assert torch.equal(ds, dec[lo:hi]) and torch.equal(ss, sc[lo:hi])
