@@ -11,5 +11,5 @@ export SGB200_CUDA_GRAPH=0
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 60 --csv --log-file gpurun_out/${T}_launches_b1024.csv python bench.py --steps 1 --warmup 0 --iters 20 --e2e-steps 0 --no-ladder --no-cpu-baseline --no-peak > /dev/null 2> gpurun_out/${T}_ncu_l.err
 python tools/launch_summary.py gpurun_out/${T}_launches_b1024.csv 60 | tail -32
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 16 -c 11 -f -o gpurun_out/${T}_conv_tc python bench.py --steps 1 --warmup 0 --iters 6 --e2e-steps 0 --no-ladder --no-cpu-baseline --no-peak > /dev/null 2> gpurun_out/${T}_ncu3.err
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:mfcc_ -s 6 -c 2 -f -o gpurun_out/${T}_mfcc python bench.py --steps 1 --warmup 0 --iters 6 --e2e-steps 0 --no-ladder --no-cpu-baseline --no-peak > /dev/null 2>> gpurun_out/${T}_ncu3.err
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:mfcc -s 6 -c 2 -f -o gpurun_out/${T}_mfcc python bench.py --steps 1 --warmup 0 --iters 6 --e2e-steps 0 --no-ladder --no-cpu-baseline --no-peak > /dev/null 2>> gpurun_out/${T}_ncu3.err
 ls -la gpurun_out/${T}*.ncu-rep | tail -5; tail -3 gpurun_out/${T}_ncu3.err
