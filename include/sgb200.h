@@ -295,6 +295,12 @@ long long sg_cw2_last_iterations(const sg_handle* h);
  *   empty cluster i -> feat[i] when force.  out [B,k,dim], counts [B,k], dfeat [B,n,dim]. */
 int sg_feco_kmeans(sg_handle* h, const float* feat, int ld, int B, int n, int dim, int k, uint64_t seed,
                    int max_iter, float tol, int32_t* ids, sg_stream stream);
+/* the same with the random stream of row r keyed as inside sg_pgd_run: rows are `copy_rows` utterances repeated (row r = copy
+ * r / copy_rows of utterance r % copy_rows; 0: rows are utterances), utterance indices are offset by `utt_offset` (a shard of
+ * a larger batch), and `pass` selects the clustering of that pass of an attack */
+int sg_feco_kmeans_keyed(sg_handle* h, const float* feat, int ld, int B, int n, int dim, int k, uint64_t seed,
+                         int max_iter, float tol, int32_t* ids, uint32_t pass, uint32_t utt_offset, uint32_t copy_rows,
+                         sg_stream stream);
 int sg_feco_means_fwd(sg_handle* h, const float* feat, int ld, const int32_t* ids, int B, int n, int dim,
                       int k, int force, float* out, int32_t* counts, sg_stream stream);
 int sg_feco_means_bwd(sg_handle* h, const float* dout, const int32_t* ids, const int32_t* counts, int B,

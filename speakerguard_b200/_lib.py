@@ -115,6 +115,8 @@ PROTOTYPES = {
     "sg_cw2_audionet_run": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.POINTER(Cw2Params), _vp, _vp, _vp, _vp, _vp]),
     "sg_cw2_last_iterations": (C.c_longlong, [_vp]),
     "sg_feco_kmeans": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_float, _vp, _vp]),
+    "sg_feco_kmeans_keyed": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_float, _vp,
+                                       C.c_uint32, C.c_uint32, C.c_uint32, _vp]),
     "sg_feco_means_fwd": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
     "sg_feco_means_bwd": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "sg_load_iv": (C.c_int, [_vp, C.POINTER(IvWeights)]),

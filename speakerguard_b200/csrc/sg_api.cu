@@ -672,8 +672,9 @@ struct FecoSpec {
   uint64_t seed;
   uint32_t pass;          // pass index of the run (graph replay: the round inside the iteration, the control block adds the rest):
   const uint32_t* ctl;    // the kernel draws a fresh clustering per pass
+  uint32_t copy_rows;     // EOT copies as batch rows: utterances per copy (0: rows are utterances)
 };
-static const FecoSpec kNoFeco = {0, 0, 0.f, 0, 0, nullptr};
+static const FecoSpec kNoFeco = {0, 0, 0.f, 0, 0, nullptr, 0};
 
 static int forward_pass(sg_handle* h, const float* x, int B, int N, int m, int mode, const float* dither, uint64_t seed,
                         uint64_t pass, float thr, const XvWs& w, float* emb, float* scores, long long* dec, cudaStream_t st,
@@ -683,7 +684,8 @@ static int forward_pass(sg_handle* h, const float* x, int B, int N, int m, int m
     // raw MFCC -> k-means ids -> cluster means (w.draw as the staging tensor: free in the forward) -> CMVN over the k means
     h->launches += 5;
     PROF(h, SG_PROF_MFCC_FWD, st, sg_feat_fwd_launch(h->d_tables, x, B, N, m, mode, dither, seed, dither_pass(h, pass), w.raw, SG_FLD, st, stash));
-    PROF(h, SG_PROF_FECO, st, sg_feco_kmeans_launch(w.raw, SG_FLD, B, m, SG_NCEP, fc.k, fc.seed, fc.max_iter, fc.tol, w.km_ids, st, fc.ctl, fc.pass));
+    PROF(h, SG_PROF_FECO, st, sg_feco_kmeans_launch(w.raw, SG_FLD, B, m, SG_NCEP, fc.k, fc.seed, fc.max_iter, fc.tol, w.km_ids, st, fc.ctl, fc.pass,
+                                                    (uint32_t)h->utt_offset, fc.copy_rows));
     PROF(h, SG_PROF_FECO, st, sg_feco_means_fwd_launch(w.raw, SG_FLD, w.km_ids, B, m, SG_NCEP, fc.k, 1, w.draw, SG_FLD, w.km_cnt, st));
     PROF(h, SG_PROF_CMVN, st, sg_cmvn_launch(w.draw, SG_FLD, w.feat, SG_FLD, B, fc.k, 0, st));
     T = fc.k;
@@ -719,7 +721,7 @@ static int feco_k(const sg_pgd_params* p, int m) { return p->feco_ratio > 0.f ? 
 static FecoSpec feco_spec(const sg_pgd_params* p, int m, uint64_t pass, const uint32_t* ctl) {
   FecoSpec fc;
   fc.k = feco_k(p, m); fc.max_iter = p->feco_max_iter > 0 ? p->feco_max_iter : 100; fc.tol = p->feco_tol > 0.f ? p->feco_tol : 0.01f;
-  fc.seed = p->seed; fc.pass = (uint32_t)pass;
+  fc.seed = p->seed; fc.pass = (uint32_t)pass; fc.copy_rows = 0;
   fc.ctl = ctl;
   return fc;
 }
@@ -733,6 +735,7 @@ static int pgd_iteration(sg_handle* h, float* cur, float* other, const float* x0
                          int N, int m, const sg_pgd_params* p, float grad_sign, const XvWs& w, float* sc, long long* dec,
                          float* loss_hist, int it, uint32_t* ctl, cudaStream_t st) {
   const int E = p->eot_size, Eb = p->eot_batch > 1 ? p->eot_batch : 1, rounds = E / Eb, Bv = B * Eb;
+  struct CopyRowsGuard { ~CopyRowsGuard() { sg_feat_set_copy_rows(0); } } copy_rows_guard;   // whatever path this function leaves by
   const size_t dstride = (size_t)B * m * SG_WIN;
   float* const stash = h->feat_stash ? w.stash : nullptr;
   const int k = feco_k(p, m), T = k > 0 ? k : m;
@@ -748,8 +751,9 @@ static int pgd_iteration(sg_handle* h, float* cur, float* other, const float* x0
       PROF(h, SG_PROF_STEP, st, sg_tile_rows_launch(cur, w.xtile, (size_t)N, B, Eb, y, w.yc, st));
       xin = w.xtile; yin = w.yc; scb = w.scores; decb = w.dec;
     }
-    SG_TRY(forward_pass(h, xin, Bv, N, m, p->dither_mode, dth, p->seed, pass, p->decision_threshold, w, w.emb, scb, decb, st, stash,
-                        feco_spec(p, m, pass, ctl)));
+    FecoSpec fc = feco_spec(p, m, pass, ctl);
+    if (Eb > 1) { fc.copy_rows = (uint32_t)B; sg_feat_set_copy_rows(B); }   // noise / clustering keyed by (copy, global utterance)
+    SG_TRY(forward_pass(h, xin, Bv, N, m, p->dither_mode, dth, p->seed, pass, p->decision_threshold, w, w.emb, scb, decb, st, stash, fc));
     float* lossp = (loss_hist && e == 0) ? loss_hist + (size_t)it * B : w.loss;
     h->launches += 3;
     PROF(h, SG_PROF_LOSS, st, sg_loss_launch(scb, yin, Bv, h->S, p->loss, lossp, w.dscores, st));
@@ -783,6 +787,7 @@ static int pgd_iteration(sg_handle* h, float* cur, float* other, const float* x0
                                 1.0f / (float)E, 0, st, stash, 0));
       PROF(h, SG_PROF_STEP, st, sg_reduce_rows_launch(w.grad, w.xbuf2, (size_t)N, B, Eb, e > 0, st));
     }
+    sg_feat_set_copy_rows(0);
   }
   if (E > 1) {
     h->launches += 1;

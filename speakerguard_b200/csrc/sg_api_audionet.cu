@@ -417,6 +417,14 @@ extern "C" int sg_feco_kmeans(sg_handle* h, const float* feat, int ld, int B, in
   h->launches += 1;
   return sg_feco_kmeans_launch(feat, ld, B, n, dim, k, seed, max_iter, tol, (int*)ids, (cudaStream_t)stream, nullptr);
 }
+extern "C" int sg_feco_kmeans_keyed(sg_handle* h, const float* feat, int ld, int B, int n, int dim, int k, uint64_t seed,
+                                    int max_iter, float tol, int32_t* ids, uint32_t pass, uint32_t utt_offset, uint32_t copy_rows,
+                                    sg_stream stream) {
+  SG_TRY(feco_check(h, B, n, dim, k));
+  if (!feat || !ids || ld < dim || max_iter < 1) { sg_set_error("sg_feco_kmeans_keyed: bad argument"); return SG_EINVAL; }
+  h->launches += 1;
+  return sg_feco_kmeans_launch(feat, ld, B, n, dim, k, seed, max_iter, tol, (int*)ids, (cudaStream_t)stream, nullptr, pass, utt_offset, copy_rows);
+}
 extern "C" int sg_feco_means_fwd(sg_handle* h, const float* feat, int ld, const int32_t* ids, int B, int n, int dim, int k,
                                  int force, float* out, int32_t* counts, sg_stream stream) {
   SG_TRY(feco_check(h, B, n, dim, k));

@@ -283,11 +283,18 @@ struct DitherSpec {
   uint32_t seed_lo, seed_hi;
   uint32_t pass;
   uint32_t b_off;        // global index of utterance 0 (SG_OPT_UTT_OFFSET): the philox counter uses b + b_off
+  uint32_t copy_rows;    // EOT copies as batch rows (sg_pgd_params::eot_batch): row r = copy r / copy_rows of utterance r % copy_rows,
+                         // keyed as (utterance + b_off) + (copy << 24) so that a sharded run draws the unsharded one's noise; 0 = off
   // CUDA-graph replay (sg_pgd_run): seed and pass counter live in device memory so that one captured iteration can be
   // replayed for every iteration of every attack; ctl = {pass, seed_lo, seed_hi}, `pass` above is then added to ctl[0]
   const uint32_t* ctl;
 };
 
+__device__ __forceinline__ uint32_t dither_key(const DitherSpec& D, int b) {
+  if (D.copy_rows == 0u) return (uint32_t)b + D.b_off;
+  const uint32_t e = (uint32_t)b / D.copy_rows;
+  return ((uint32_t)b - e * D.copy_rows) + D.b_off + (e << 24);
+}
 // resolve the device-resident part of a DitherSpec (warp-uniform loads, once per kernel)
 __device__ __forceinline__ void dither_resolve(DitherSpec& D) {
   if (D.ctl != nullptr) { D.pass += __ldg(D.ctl); D.seed_lo = __ldg(D.ctl + 1); D.seed_hi = __ldg(D.ctl + 2); }
@@ -322,7 +329,7 @@ __device__ __forceinline__ void load_frame(Frame& F, const float* __restrict__ x
     const int hi = lane >> 4;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const uint4 r = philox4x32_10(make_uint4(q * 16 + (lane & 15), (uint32_t)fr, (uint32_t)b + D.b_off, D.pass), make_uint2(D.seed_lo, D.seed_hi));
+      const uint4 r = philox4x32_10(make_uint4(q * 16 + (lane & 15), (uint32_t)fr, dither_key(D, b), D.pass), make_uint2(D.seed_lo, D.seed_hi));
       const float2 a = box_muller16(hi ? r.y : r.x);
       nz[4 * q] = a.x; nz[4 * q + 1] = a.y;
       if (q < 3) { const float2 c = box_muller16(hi ? r.w : r.z); nz[4 * q + 2] = c.x; nz[4 * q + 3] = c.y; }
@@ -1126,7 +1133,7 @@ __device__ __forceinline__ void load_frame2(Frame2& F, const float* __restrict__
   } else if (D.mode == SG_DITHER_PHILOX) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const uint4 r = philox4x32_10(make_uint4(q * 16 + l, (uint32_t)fr, (uint32_t)b + D.b_off, D.pass), make_uint2(D.seed_lo, D.seed_hi));
+      const uint4 r = philox4x32_10(make_uint4(q * 16 + l, (uint32_t)fr, dither_key(D, b), D.pass), make_uint2(D.seed_lo, D.seed_hi));
       const float2 n0 = box_muller16(r.x);
       nz[8 * q] = n0.x; nz[8 * q + 1] = n0.y;
       if (q < 3) {
@@ -1636,7 +1643,7 @@ __global__ void dither_fill2_kernel(int m, DitherSpec D, float* __restrict__ out
   float* o = out + ((size_t)b * m + fr) * SG_WIN;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    const uint4 r = philox4x32_10(make_uint4(q * 16 + l, (uint32_t)fr, (uint32_t)b + D.b_off, D.pass), make_uint2(D.seed_lo, D.seed_hi));
+    const uint4 r = philox4x32_10(make_uint4(q * 16 + l, (uint32_t)fr, dither_key(D, b), D.pass), make_uint2(D.seed_lo, D.seed_hi));
     const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -1658,6 +1665,8 @@ static size_t feat_bwd_smem() {
 // replayed PGD iteration by sg_api.cu; null = use the immediate seed / pass arguments).
 static thread_local const uint32_t* g_feat_ctl = nullptr;
 void sg_feat_set_ctl(const uint32_t* ctl) { g_feat_ctl = ctl; }
+static thread_local uint32_t g_feat_copy_rows = 0;    // DitherSpec::copy_rows for the launches that follow on this thread
+void sg_feat_set_copy_rows(int rows) { g_feat_copy_rows = rows > 0 ? (uint32_t)rows : 0u; }
 
 // `pass` carries the pass counter in its low 32 bits and the handle's utterance offset in the high 32 (packed by
 // sg_api.cu: dither_pass())
@@ -1665,7 +1674,7 @@ static DitherSpec make_dither(int mode, const float* tensor, uint64_t seed, uint
   DitherSpec D;
   D.mode = mode; D.tensor = tensor;
   D.seed_lo = (uint32_t)seed; D.seed_hi = (uint32_t)(seed >> 32); D.pass = (uint32_t)pass; D.b_off = (uint32_t)(pass >> 32);
-  D.ctl = g_feat_ctl;
+  D.ctl = g_feat_ctl; D.copy_rows = g_feat_copy_rows;
   return D;
 }
 __global__ void feat_ctl_init_kernel(uint32_t* ctl, uint32_t pass, uint32_t seed_lo, uint32_t seed_hi) {

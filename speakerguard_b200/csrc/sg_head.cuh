@@ -26,6 +26,7 @@ int sg_feat_bwd_step_launch(const SgFeatTables* dT, const float* x, int B, int N
                             const float* dither, uint64_t seed, uint64_t pass, const float* draw, int ld,
                             const float* x0, float* x_out, float step, float eps, cudaStream_t st, const float* stash = nullptr,
                             int cmvn = 0);
+void sg_feat_set_copy_rows(int rows);                          // EOT copies as batch rows: utterances per copy for the following launches (0: off)
 void sg_feat_set_ctl(const uint32_t* ctl);                     // device {pass, seed_lo, seed_hi} for the following launches (null: immediates)
 int sg_feat_ctl_init_launch(uint32_t* ctl, uint64_t seed, uint32_t pass, cudaStream_t st);
 int sg_feat_ctl_tick_launch(uint32_t* ctl, uint32_t n, cudaStream_t st);
@@ -39,7 +40,7 @@ int sg_reduce_rows_launch(const float* rows, float* acc, size_t row_floats, int 
 // FeCo (sg_kmeans.cu); ctl: device {pass, seed_lo, seed_hi} mixed into the k-means seed (graph replay), or null
 int sg_kmeans_init();
 int sg_feco_kmeans_launch(const float* feat, int ld, int B, int n, int dim, int k, uint64_t seed, int max_iter, float tol,
-                          int* ids, cudaStream_t st, const uint32_t* ctl, uint32_t pass = 0);
+                          int* ids, cudaStream_t st, const uint32_t* ctl, uint32_t pass = 0, uint32_t b_off = 0, uint32_t copy_rows = 0);
 int sg_feco_means_fwd_launch(const float* feat, int ld_in, const int* ids, int B, int n, int dim, int k, int force,
                              float* out, int ld_out, int* counts, cudaStream_t st);
 int sg_feco_means_bwd_launch(const float* dout, int ld_out, const int* ids, const int* counts, int B, int n, int dim, int k,

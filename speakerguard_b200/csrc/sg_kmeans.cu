@@ -141,7 +141,8 @@ __device__ __forceinline__ void km_mma(float (&c)[4], const uint32_t (&a)[4], ui
 }
 __global__ void __launch_bounds__(KM_THREADS)
 feco_kmeans2_kernel(const float* __restrict__ feat, int ld, int n, int dim, int k, uint32_t seed_lo, uint32_t seed_hi,
-                    uint32_t pass, const uint32_t* __restrict__ ctl, int max_iter, float tol, int* __restrict__ ids_out) {
+                    uint32_t pass, const uint32_t* __restrict__ ctl, uint32_t b_off, uint32_t copy_rows, int max_iter, float tol,
+                    int* __restrict__ ids_out) {
   extern __shared__ __align__(16) float sm[];
   float* X = sm;                                         // [n][36]
   float* Cn = X + (size_t)n * KM_DP;                     // [k8][36], k8 = k rounded up to 8 (padding rows zero)
@@ -161,13 +162,16 @@ feco_kmeans2_kernel(const float* __restrict__ feat, int ld, int n, int dim, int 
   // the seed as given (stand-alone calls)
   if (ctl != nullptr) pass += __ldg(ctl);
   seed_lo ^= pass * 0x9E3779B9u; seed_hi += pass * 0x85EBCA77u;
+  // the random stream of a row is keyed like the MFCC dither (dither_key): global utterance index + (EOT copy << 24)
+  const uint32_t cpy = copy_rows ? (uint32_t)b / copy_rows : 0u;
+  const uint32_t bkey = ((uint32_t)b - cpy * copy_rows) + b_off + (cpy << 24);
   const float* fb = feat + (size_t)b * n * ld;
   for (int i = tid; i < n * KM_DP; i += KM_THREADS) {
     const int j = i / KM_DP, d = i - j * KM_DP;
     X[i] = d < dim ? fb[(size_t)j * ld + d] : 0.f;
   }
   for (int i = tid; i < k8 * KM_DP; i += KM_THREADS) Cn[i] = 0.f;
-  if (tid == 0) s_pick = (int)(km_hash(seed_lo, seed_hi, (uint32_t)b, 0u) % (uint32_t)n);
+  if (tid == 0) s_pick = (int)(km_hash(seed_lo, seed_hi, bkey, 0u) % (uint32_t)n);
   __syncthreads();
 
   // ---- k-means++ seeding ----
@@ -201,7 +205,7 @@ feco_kmeans2_kernel(const float* __restrict__ feat, int ld, int n, int dim, int 
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { const float v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
       const float total = __shfl_sync(0xffffffffu, incl, 31);
-      const float u = (km_hash(seed_lo, seed_hi, (uint32_t)b, (uint32_t)(c + 1)) >> 8) * (1.0f / 16777216.0f);
+      const float u = (km_hash(seed_lo, seed_hi, bkey, (uint32_t)(c + 1)) >> 8) * (1.0f / 16777216.0f);
       const float r = u * total;
       const unsigned hit = __ballot_sync(0xffffffffu, incl > r);
       const int owner = hit ? __ffs(hit) - 1 : 31;
@@ -409,16 +413,16 @@ int sg_kmeans_init() {
 
 // ctl: optional device control block {pass, seed_lo, seed_hi} mixed into the seed (CUDA-graph replay of the fused attack loop)
 int sg_feco_kmeans_launch(const float* feat, int ld, int B, int n, int dim, int k, uint64_t seed, int max_iter, float tol,
-                          int* ids, cudaStream_t st, const uint32_t* ctl, uint32_t pass) {
+                          int* ids, cudaStream_t st, const uint32_t* ctl, uint32_t pass, uint32_t b_off, uint32_t copy_rows) {
   static int use_v2 = -1;
   if (use_v2 < 0) { const char* e = getenv("SGB200_KMEANS_V2"); use_v2 = e ? atoi(e) != 0 : 1; }
   const size_t smem2 = kmeans2_smem(n, k);
   if (use_v2 && dim <= 32 && smem2 <= KM2_MAX_SMEM) {
-    feco_kmeans2_kernel<<<B, KM_THREADS, smem2, st>>>(feat, ld, n, dim, k, (uint32_t)seed, (uint32_t)(seed >> 32), pass, ctl, max_iter, tol, ids);
+    feco_kmeans2_kernel<<<B, KM_THREADS, smem2, st>>>(feat, ld, n, dim, k, (uint32_t)seed, (uint32_t)(seed >> 32), pass, ctl, b_off, copy_rows, max_iter, tol, ids);
     SG_LAUNCH_CHECK();
     return SG_OK;
   }
-  if (ctl || pass) { sg_set_error("FeCo k-means inside the fused loop needs the shared-memory kernel (n=%d k=%d)", n, k); return SG_EUNSUPPORTED; }
+  if (ctl || pass || b_off || copy_rows) { sg_set_error("FeCo k-means inside the fused loop needs the shared-memory kernel (n=%d k=%d)", n, k); return SG_EUNSUPPORTED; }
   const size_t smem = sg_kmeans_smem(n, dim, k);
   if (smem > 200 * 1024) { sg_set_error("FeCo k-means: utterance too long for the shared-memory kernel (n=%d dim=%d k=%d)", n, dim, k); return SG_EUNSUPPORTED; }
   SG_CUDA_CHECK(cudaFuncSetAttribute(feco_kmeans_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -32,15 +32,16 @@ class _FeCoMeans(torch.autograd.Function):
         return ctx.eng.feco_means_bwd(g.contiguous(), ctx.ids, ctx.counts, ctx.n, ctx.force), None, None, None
 
 
-def kmeans_ids(feat, k, seed=None, max_iter=100, tol=0.01):
-    """Cluster ids [B, n] (int32) of every utterance's frames, L2 metric."""
+def kmeans_ids(feat, k, seed=None, max_iter=100, tol=0.01, **key):
+    """Cluster ids [B, n] (int32) of every utterance's frames, L2 metric.  ``key``: pass_ / utt_offset / copy_rows of
+    Engine.feco_kmeans (the stream keying of the fused attack loop)."""
     eng = default_engine(feat.device)
     if seed is None:
         seed = (int(torch.initial_seed()) * 0x9E3779B97F4A7C15 + next(_seed_counter)) & 0xFFFFFFFFFFFFFFFF
-    return eng.feco_kmeans(feat.detach(), k, seed=seed, max_iter=max_iter, tol=tol)
+    return eng.feco_kmeans(feat.detach(), k, seed=seed, max_iter=max_iter, tol=tol, **key)
 
 
-def FEATURE_COMPRESSION(feat, method='kmeans', param=0.5, other_param='L2', seed=None, ids=None, max_iter=100, tol=0.01):
+def FEATURE_COMPRESSION(feat, method='kmeans', param=0.5, other_param='L2', seed=None, ids=None, max_iter=100, tol=0.01, **key):
     if method != 'kmeans':
         raise NotImplementedError('speakerguard_b200 FeCo supports method="kmeans" (warped_kmeans stays with the reference)')
     if other_param != 'L2':
@@ -50,7 +51,7 @@ def FEATURE_COMPRESSION(feat, method='kmeans', param=0.5, other_param='L2', seed
     k = int(n * param)
     force = B > 1                                   # feature_level.py:37
     if ids is None:
-        ids = kmeans_ids(feat, k, seed=seed, max_iter=max_iter, tol=tol)
+        ids = kmeans_ids(feat, k, seed=seed, max_iter=max_iter, tol=tol, **key)
     out = _FeCoMeans.apply(feat, ids, k, True)
     if not force:                                   # batch of one: empty clusters are dropped, as in the reference
         counts = torch.bincount(ids[0].long(), minlength=k)
@@ -59,8 +60,8 @@ def FEATURE_COMPRESSION(feat, method='kmeans', param=0.5, other_param='L2', seed
     return out
 
 
-def FeCo(feat, method='kmeans', param=0.5, other_param='L2', seed=None, ids=None, max_iter=100, tol=0.01):
-    return FEATURE_COMPRESSION(feat, method, param, other_param, seed=seed, ids=ids, max_iter=max_iter, tol=tol)
+def FeCo(feat, method='kmeans', param=0.5, other_param='L2', seed=None, ids=None, max_iter=100, tol=0.01, **key):
+    return FEATURE_COMPRESSION(feat, method, param, other_param, seed=seed, ids=ids, max_iter=max_iter, tol=tol, **key)
 
 
 class FeCoDefense:

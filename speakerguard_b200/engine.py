@@ -427,13 +427,20 @@ class Engine:
         return int(self.lib.sg_cw2_last_iterations(self._h))
 
     # ---- FeCo ------------------------------------------------------------------------------------
-    def feco_kmeans(self, feat: torch.Tensor, k: int, seed: int = 0, max_iter: int = 100, tol: float = 0.01) -> torch.Tensor:
-        """feat [B,n,dim] -> cluster ids [B,n] int32."""
+    def feco_kmeans(self, feat: torch.Tensor, k: int, seed: int = 0, max_iter: int = 100, tol: float = 0.01,
+                    pass_: int = 0, utt_offset: int = 0, copy_rows: int = 0) -> torch.Tensor:
+        """feat [B,n,dim] -> cluster ids [B,n] int32.  pass_ / utt_offset / copy_rows key the random stream of a row the way
+        sg_pgd_run does (sg_feco_kmeans_keyed): the clustering of pass `pass_`, rows = `copy_rows` utterances repeated, utterance
+        indices offset by `utt_offset`; all zero: the plain per-row stream."""
         feat = _f32c(feat, self.device)
         B, n, dim = feat.shape
         ids = torch.empty(B, n, device=self.device, dtype=torch.int32)
-        check(self.lib.sg_feco_kmeans(self._h, _ptr(feat), dim, B, n, dim, k, seed, max_iter, tol, _ptr(ids), self.stream),
-              "sg_feco_kmeans")
+        if pass_ or utt_offset or copy_rows:
+            check(self.lib.sg_feco_kmeans_keyed(self._h, _ptr(feat), dim, B, n, dim, k, seed, max_iter, tol, _ptr(ids),
+                                                int(pass_), int(utt_offset), int(copy_rows), self.stream), "sg_feco_kmeans_keyed")
+        else:
+            check(self.lib.sg_feco_kmeans(self._h, _ptr(feat), dim, B, n, dim, k, seed, max_iter, tol, _ptr(ids), self.stream),
+                  "sg_feco_kmeans")
         return ids
 
     def feco_means_fwd(self, feat: torch.Tensor, ids: torch.Tensor, k: int, force: bool = True):

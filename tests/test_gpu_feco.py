@@ -93,15 +93,6 @@ def test_eot_pgd_against_feco_defended_xv_plda(tmp_path):
 
 
 # ---- FeCo + EOT inside the fused device loop (sg_pgd_params::feco_ratio / eot_batch) --------------------------------------
-def _kmeans_pass_seed(seed, pass_):
-    """The seed sg_pgd_run's k-means launch of pass `pass_` ends up with (feco_kmeans2_kernel: lo ^= pass * 0x9E3779B9,
-    hi += pass * 0x85EBCA77)."""
-    lo, hi = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
-    lo ^= (pass_ * 0x9E3779B9) & 0xFFFFFFFF
-    hi = (hi + pass_ * 0x85EBCA77) & 0xFFFFFFFF
-    return lo | (hi << 32)
-
-
 @pytest.fixture(scope="module")
 def eng_fp32():
     from speakerguard_b200.engine import Engine
@@ -130,7 +121,7 @@ def test_fused_feco_step_equals_stagewise_composition(eng_fp32):
 
     def defended_forward(xin, pass_):
         raw = eng.mfcc_fwd(xin, _lib.DITHER_OFF, None, ld=32)
-        ids = eng.feco_kmeans(raw[:, :, :30].contiguous(), k, seed=_kmeans_pass_seed(seed, pass_))
+        ids = eng.feco_kmeans(raw[:, :, :30].contiguous(), k, seed=seed, pass_=pass_)       # the loop's clustering of that pass
         means, counts = eng.feco_means_fwd(raw[:, :, :30].contiguous(), ids, k, True)
         feat = eng.cmvn(means, ld_out=32)
         emb, ws = eng.embed_fwd(feat)
@@ -222,8 +213,11 @@ def test_fused_feco_through_the_attack_classes(tmp_path):
     adv_f, suc_f = PGD(dm_fused, epsilon=0.002, step_size=0.0004, max_iter=iters, batch_size=4, EOT_size=E, EOT_batch_size=E,
                        verbose=0).attack(x, y)
     counter = itertools.count(0)
+    # the generic EOT wrapper tiles the batch like the fused loop does (copies outermost): rows = 4 utterances repeated in
+    # the E-copy passes, the plain batch in the final evaluation
     dm_seeded = defended_model(base, order="sequential",
-                               defense=[[1, lambda feat: FeCo(feat, "kmeans", 0.5, "L2", seed=_kmeans_pass_seed(seed, next(counter)))]])
+                               defense=[[1, lambda feat: FeCo(feat, "kmeans", 0.5, "L2", seed=seed, pass_=next(counter),
+                                                              copy_rows=4 if feat.shape[0] > 4 else 0)]])
     adv_g, suc_g = PGD(dm_seeded, epsilon=0.002, step_size=0.0004, max_iter=iters, batch_size=4, EOT_size=E, EOT_batch_size=E,
                        verbose=0).attack(x, y)
     assert next(counter) == iters + 1                                # one defended forward per iteration + the final evaluation

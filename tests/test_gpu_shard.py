@@ -107,3 +107,36 @@ def test_graph_replay_is_bit_identical_to_launch_by_launch(prec, iters, eot):
         assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
         assert abs(a[3] - b[3]) <= 8 + iters, (a[3], b[3])          # same kernels (+ control-block ticks / copies)
     assert not torch.equal(out[(1, 21)][0], out[(1, 22)][0])
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_sharded_feco_eot_loop_equals_unsharded(prec):
+    """FeCo + EOT inside the fused loop with EOT copies as batch rows: the philox dither and the k-means streams of a row are
+    keyed by (EOT copy, GLOBAL utterance index), not by the row's position in the pass, so a contiguous split of the batch
+    over two handles reproduces the unsharded attack bit for bit although the tiled rows sit at different positions."""
+    from speakerguard_b200 import _lib
+    from speakerguard_b200.engine import Engine, make_loss_params
+    p = O.make_xv_params(seed=0)
+    B, N = 6, 32000
+    torch.manual_seed(43)
+    x = ((torch.rand(B, 1, N) * 2 - 1) * 0.5)[:, 0].contiguous()
+    y = torch.randint(0, 10, (B,))
+    kw = dict(max_iter=3, epsilon=0.002, step_size=0.0004, lp=make_loss_params("Entropy"), dither_mode=_lib.DITHER_PHILOX, seed=78,
+              grad_sign=1.0, eot_size=4, eot_batch=2, feco_ratio=0.5)
+    full = Engine("cuda:0", precision=prec)
+    full.load_xv(p)
+    xa = x.cuda().clone()
+    dec, scores, _ = full.pgd_run(xa, x.cuda(), y.cuda(), **kw)
+    torch.cuda.synchronize()
+    parts = []
+    for lo, hi in ((0, 4), (4, 6)):
+        e = Engine("cuda:0", precision=prec)
+        e.load_xv(p)
+        xs = x[lo:hi].cuda()
+        xo = xs.clone()
+        d, s, _ = e.pgd_run(xo, xs, y[lo:hi].cuda(), utt_offset=lo, **kw)
+        torch.cuda.synchronize()
+        parts.append((xo.cpu(), d.cpu(), s.cpu()))
+    assert torch.equal(torch.cat([a for a, _, _ in parts]), xa.cpu())
+    assert torch.equal(torch.cat([d for _, d, _ in parts]), dec.cpu())
+    assert torch.equal(torch.cat([s for _, _, s in parts]), scores.cpu())
