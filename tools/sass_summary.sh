@@ -4,4 +4,4 @@
 # usage: tools/sass_summary.sh > profiles/r2_sass_conv_tc.txt
 cd "$(dirname "$0")/.."
 echo "# cuobjdump -sass speakerguard_b200/libsgb200.so: count, kernel, mnemonic (tools/sass_summary.sh)"
-cuobjdump -sass speakerguard_b200/libsgb200.so | awk '/Function :/{fn=$3} /UTCHMMA|UTCQMMA|UTCMMA|UTMALDG|UTMASTG|UTMAPF|LDTM|STTM|UTCBAR|UTCCP|UTCATOM|SYNCS|UTMACCTL|UTMACMDFLUSH|UBLKCP/{ m=$0; sub(/^[ \t]*\/\*[0-9a-f]+\*\/[ \t]*/,"",m); split(m,a," "); op=a[1]; if (op ~ /^@/) op=a[2]; gsub(/;/,"",op); c[fn" "op]++} END{for(k in c) print c[k], k}' | sort -k2,2 -k1,1nr
+cuobjdump -sass speakerguard_b200/libsgb200.so | awk '/Function :/{fn=$3} /UTCHMMA|UTCQMMA|UTCMMA|UTMALDG|UTMASTG|UTMAPF|LDTM|STTM|UTCBAR|UTCCP|UTCATOM|SYNCS|UTMACCTL|UTMACMDFLUSH|UBLKCP|HMMA|MATCH/{ m=$0; sub(/^[ \t]*\/\*[0-9a-f]+\*\/[ \t]*/,"",m); split(m,a," "); op=a[1]; if (op ~ /^@/) op=a[2]; gsub(/;/,"",op); c[fn" "op]++} END{for(k in c) print c[k], k}' | sort -k2,2 -k1,1nr
