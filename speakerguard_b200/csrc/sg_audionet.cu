@@ -65,21 +65,23 @@ int sg_an_tables_build(SgAnTables* t) {
     int lo = AN_BINS, hi = -1;
     for (int b = 0; b < 512; ++b)
       if (w[c][b] > 0.0) { if (b < lo) lo = b; hi = b; }
-    int len = hi >= lo ? hi - lo + 1 : 0;
-    if (len == 0) lo = 0;
-    t->mel_lo[c] = lo; t->mel_len[c] = len; t->mel_off[c] = off;
-    if (off + len > AN_MELW) return SG_EINVAL;
-    for (int i = 0; i < len; ++i) {
-      const int b = lo + i;
-      t->mel_w[off + i] = (float)w[c][b];
-      if (w[c][b] > 0.0) {
-        if (t->bin_w0[b] == 0.f) { t->bin_c0[b] = c; t->bin_w0[b] = (float)w[c][b]; }
-        else if (t->bin_w1[b] == 0.f) { t->bin_c1[b] = c; t->bin_w1[b] = (float)w[c][b]; }
+    // float4 groups: the window starts at a multiple of 4 and is zero-padded to whole groups (an_mel reads float4 pairs)
+    const int lo4 = hi >= lo ? (lo & ~3) : 0;
+    const int groups = hi >= lo ? (hi - lo4) / 4 + 1 : 0;
+    t->mel_lo[c] = lo4; t->mel_len[c] = groups; t->mel_off[c] = off;
+    if (off + 4 * groups > AN_MELW) return SG_EINVAL;
+    for (int i = 0; i < 4 * groups; ++i) {
+      const int b = lo4 + i;
+      const double wv = (b >= lo && b <= hi && b < 512) ? w[c][b] : 0.0;
+      t->mel_w[off + i] = (float)wv;
+      if (wv > 0.0) {
+        if (t->bin_w0[b] == 0.f) { t->bin_c0[b] = c; t->bin_w0[b] = (float)wv; }
+        else if (t->bin_w1[b] == 0.f) { t->bin_c1[b] = c; t->bin_w1[b] = (float)wv; }
         else return SG_EINVAL;
       }
     }
-    off += len;
-    if (len > maxlen) maxlen = len;
+    off += 4 * groups;
+    if (groups > maxlen) maxlen = groups;
   }
   t->mel_maxlen = maxlen;
   return SG_OK;
@@ -201,11 +203,17 @@ __device__ __forceinline__ void an_copy_tables(SgAnTables* dst, const SgAnTables
   for (int i = threadIdx.x; i < (int)(sizeof(SgAnTables) / 16); i += blockDim.x) d[i] = s[i];
 }
 
+// lane c: mel energy of filter c; windows are float4-aligned and zero-padded (P must be finite up to index 515)
 __device__ __forceinline__ float an_mel(const SgAnTables* T, const float* P, int lane) {
   const int lo = T->mel_lo[lane], len = T->mel_len[lane], off = T->mel_off[lane];
+  const float4* w4 = reinterpret_cast<const float4*>(&T->mel_w[off]);
+  const float4* p4 = reinterpret_cast<const float4*>(&P[lo]);
   float acc = 0.f;
   for (int i = 0; i < T->mel_maxlen; ++i)
-    if (i < len) acc = fmaf(T->mel_w[off + i], P[lo + i], acc);
+    if (i < len) {
+      const float4 w = w4[i], p = p4[i];
+      acc = fmaf(w.x, p.x, acc); acc = fmaf(w.y, p.y, acc); acc = fmaf(w.z, p.z, acc); acc = fmaf(w.w, p.w, acc);
+    }
   return acc;
 }
 
@@ -232,6 +240,7 @@ an_logmel_fwd_kernel(const float* __restrict__ x, int N, int T_frames, int frame
     an_frame_spectrum(X, xb, M, t, T, sre, sim, lane);
 #pragma unroll
     for (int r = 0; r < 16; ++r) sre[lane + 32 * r] = X[r].x * X[r].x + X[r].y * X[r].y;   // power, Preprocessor.py:28-37
+    if (lane < 4) sre[512 + lane] = 0.f;                           // the zero-weighted tail of the last float4 group
     __syncwarp();
     const float me = an_mel(T, sre, lane);
     feat[((size_t)b * T_frames + t) * AN_MELS + lane] = AN_LOGSCALE * logf(fmaxf(me, 1e-16f));   // Preprocessor.py:111
@@ -281,6 +290,7 @@ an_logmel_bwd_frames_kernel(const float* __restrict__ x, int N, int T_frames, in
       an_frame_spectrum(X, xb, M, t, T, sre, sim, lane);
 #pragma unroll
       for (int r = 0; r < 16; ++r) sre[lane + 32 * r] = X[r].x * X[r].x + X[r].y * X[r].y;
+      if (lane < 4) sre[512 + lane] = 0.f;
       __syncwarp();
       me = an_mel(T, sre, lane);
     }

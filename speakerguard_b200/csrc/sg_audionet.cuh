@@ -8,7 +8,7 @@
 #define AN_WOFF 112                 // (1024 - 800) / 2: the window is centred in the FFT frame
 #define AN_MELS 32
 #define AN_BINS 513
-#define AN_MELW 1152
+#define AN_MELW 1280              // packed mel weights, float4 groups (zero-padded)
 #define SG_CW2_CHUNKS 16
 
 struct alignas(16) SgAnTables {
