@@ -11,6 +11,7 @@
 // of the inner loop is one shared-memory wavefront (the 2 x 16 arrangement ran the data pipe at 68 % and the FMA pipe at 60 %).
 // The loop carries its tap / channel position and the weight pointer forward instead of dividing the chunk index each round.
 #include "sg_common.cuh"
+#include <cstdlib>
 
 #define BM 128
 #define BK 16
@@ -176,10 +177,17 @@ int sg_conv_simt(const SgConvArgs& a, cudaStream_t st) {
     sg_set_error("sg_conv_simt: batch strides must be multiples of 4 floats and nbatch <= 65535");
     return SG_EINVAL;
   }
-  // 128-column tiles unless more than a quarter of their columns would be padding; then the narrower tile with less padding
+  // Tile width: the one with the least padded columns per unit of measured throughput.  The 8 x 8 micro-tile of the 128-wide
+  // kernel does 64 FMAs per 4 fragment loads, the 8 x 4 and 8 x 2 ones 32 per 3 and 16 per 3; measured on the N = 80 statistics
+  // adjoint of the i-vector path (2048-deep contraction, 256 batches): 1.77 ms at 128 (48 padded columns), 2.00 ms at 64,
+  // 2.27 ms at 32 - i.e. 0.89 and 0.59 of the wide kernel's rate per computed column.
   auto padded = [&](int t) { return (a.N + t - 1) / t * t; };
-  int bn = 128;
-  if (4 * (padded(128) - a.N) > padded(128)) bn = padded(32) < padded(64) ? 32 : 64;
+  const float c128 = (float)padded(128), c64 = padded(64) / 0.89f, c32 = padded(32) / 0.59f;
+  int bn = 128;                                  // a narrow tile has to win by 10 % (N = 400 at 64: 1.22 ms against 1.01 ms at 128)
+  if (c64 < 0.9f * c128 && c64 <= c32) bn = 64;
+  else if (c32 < 0.9f * c128 && c32 < c64) bn = 32;
+  static const int force_bn = [] { const char* e = getenv("SGB200_SIMT_BN"); return e ? atoi(e) : 0; }();   // A/B switch
+  if (force_bn == 32 || force_bn == 64 || force_bn == 128) bn = force_bn;
   dim3 grid((a.N + bn - 1) / bn, (a.rows + BM - 1) / BM, a.nbatch > 1 ? a.nbatch : 1);
   if (bn == 32) conv_simt_kernel<32><<<grid, 256, 0, st>>>(a);
   else if (bn == 64) conv_simt_kernel<64><<<grid, 256, 0, st>>>(a);

@@ -211,13 +211,25 @@ __global__ void softmax_rows_bwd_kernel(const float* __restrict__ post, const fl
 #define CH_NB 32                 // panel width of the blocked factorisation
 #define CH_LD (CH_NB + 1)        // padded panel row stride (doubles)
 
-// rows k0..D-1 of the nb panel columns -> shared memory (upper part of the diagonal block zeroed)
+// rows k0..D-1 of the nb panel columns -> shared memory (upper part of the diagonal block zeroed).  One warp per row, one
+// 8-byte asynchronous copy per element, every copy of the panel in flight before the first wait: with plain loads staged through
+// registers the panel came in at ~4 loads in flight per thread and a quarter of the kernel's samples sat on this line.
 __device__ __forceinline__ void chol_load_panel(const double* __restrict__ A, int D, int k0, int nb, double* Pn) {
   const int rows = D - k0;
-  for (int e = threadIdx.x; e < rows * nb; e += blockDim.x) {
-    const int r = e / nb, c = e - r * nb;
-    Pn[r * CH_LD + c] = (r >= c) ? A[(size_t)(k0 + r) * D + k0 + c] : 0.0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (lane < nb) {
+    const double* src = reinterpret_cast<const double*>(__cvta_generic_to_global(A + (size_t)(k0 + warp) * D + k0 + lane));
+    uint32_t dst = (uint32_t)__cvta_generic_to_shared(Pn + warp * CH_LD + lane);
+    for (int r = warp; r < rows; r += nw) {
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+      src += (size_t)nw * D;
+      dst += (uint32_t)(nw * CH_LD * sizeof(double));
+    }
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  if (lane < nb)
+    for (int r = warp; r < nb; r += nw)
+      if (lane > r) Pn[r * CH_LD + lane] = 0.0;
 }
 
 // forward substitution L y = v, then back substitution L' w = y, panel by panel (L lower-triangular, row-major)
@@ -274,68 +286,105 @@ __device__ void chol_solve_with_factor(const double* __restrict__ A, int D, doub
   __syncthreads();
 }
 
-// blocked right-looking Cholesky, in place in the lower triangle of A (row-major [D, D], global memory):
-// the 32-column panel is factorised in shared memory, the trailing matrix gets one rank-32 update per panel
+// blocked right-looking Cholesky, in place in the lower triangle of A (row-major [D, D], global memory).  Per 32-column panel:
+// the 32 x 32 diagonal block is factorised by the whole CTA, the rows below it are then independent triangular solves
+// x L11' = a (one thread per row, the row in registers; the same sequence of fused multiply-adds and divisions per element as the
+// column-by-column right-looking form, without its 3 block barriers per column over the full panel height), and the trailing
+// matrix gets one rank-32 update.
 __device__ void chol_factor_blocked(double* __restrict__ A, int D, double* Pn) {
-  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nthr >> 5;
   for (int k0 = 0; k0 < D; k0 += CH_NB) {
     const int nb = min(CH_NB, D - k0), rows = D - k0;
     __syncthreads();
     chol_load_panel(A, D, k0, nb, Pn);
     __syncthreads();
+    // diagonal block: lane -> column, warp -> row
     for (int j = 0; j < nb; ++j) {
       const double d = sqrt(Pn[j * CH_LD + j]);
       __syncthreads();
-      for (int r = j + tid; r < rows; r += nthr) Pn[r * CH_LD + j] = (r == j) ? d : Pn[r * CH_LD + j] / d;
+      if (tid < nb - j) { const int r = j + tid; Pn[r * CH_LD + j] = (r == j) ? d : Pn[r * CH_LD + j] / d; }
       __syncthreads();
-      const int nc = nb - j - 1;
-      for (int e = tid; e < (rows - j - 1) * nc; e += nthr) {
-        const int q = e / nc, r = j + 1 + q, c = j + 1 + (e - q * nc);
-        if (r >= c) Pn[r * CH_LD + c] -= Pn[r * CH_LD + j] * Pn[c * CH_LD + j];
-      }
+      const int c = j + 1 + lane;
+      if (c < nb)
+        for (int r = j + 1 + warp; r < nb; r += nw)
+          if (r >= c) Pn[r * CH_LD + c] -= Pn[r * CH_LD + j] * Pn[c * CH_LD + j];
       __syncthreads();
     }
+    // rows below the block (nb == CH_NB whenever there are any)
+    for (int r = nb + tid; r < rows; r += nthr) {
+      double x[CH_NB];
+      double* pr = Pn + r * CH_LD;
+#pragma unroll
+      for (int c = 0; c < CH_NB; ++c) x[c] = pr[c];
+#pragma unroll
+      for (int c = 0; c < CH_NB; ++c) {
+        const double* lc = Pn + c * CH_LD;           // uniform address: broadcast reads
+        double acc = x[c];
+#pragma unroll
+        for (int k = 0; k < c; ++k) acc = fma(-x[k], lc[k], acc);
+        x[c] = acc / lc[c];
+      }
+#pragma unroll
+      for (int c = 0; c < CH_NB; ++c) pr[c] = x[c];
+    }
+    __syncthreads();
     for (int e = tid; e < rows * nb; e += nthr) {
       const int r = e / nb, c = e - r * nb;
       if (r >= c) A[(size_t)(k0 + r) * D + k0 + c] = Pn[r * CH_LD + c];
     }
-    // trailing update in 4x4 register tiles over the lower triangle of the (n2 x n2) block
+    // trailing update in 4x4 register tiles over the lower triangle of the (n2 x n2) block.  A warp takes a patch of 4 x 8
+    // tiles: its row operands are 4 distinct panel rows (one shared-memory wavefront), its column operands 8 (two) - with 32
+    // consecutive column tiles per warp the rows were 4 * 33 doubles apart on every lane, an 8-way bank conflict that made up
+    // 60 % of the kernel's shared-memory wavefronts.
     const int n2 = rows - nb, nt = (n2 + 3) / 4;
-    for (int t = tid; t < nt * (nt + 1) / 2; t += nthr) {
-      int ti = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
-      while (ti * (ti + 1) / 2 > t) --ti;
-      while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-      const int tj = t - ti * (ti + 1) / 2;
-      double acc[4][4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-#pragma unroll
-        for (int w = 0; w < 4; ++w) acc[u][w] = 0.0;
-      int ri[4], rj[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) { ri[u] = min(nb + ti * 4 + u, rows - 1) * CH_LD; rj[u] = min(nb + tj * 4 + u, rows - 1) * CH_LD; }
-      for (int c = 0; c < nb; ++c) {
-        double a[4], bq[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) { a[u] = Pn[ri[u] + c]; bq[u] = Pn[rj[u] + c]; }
+    int cnt = 0;
+    for (int si = 0; 4 * si < nt; ++si) {
+      const int sjmax = min((4 * si + 3) >> 3, (nt - 1) >> 3);
+      for (int sj = 0; sj <= sjmax; ++sj, ++cnt) {
+        if (cnt % nw != warp) continue;
+        const int ti = 4 * si + (lane >> 3), tj = 8 * sj + (lane & 7);
+        if (ti >= nt || tj > ti) continue;
+        double acc[4][4];
 #pragma unroll
         for (int u = 0; u < 4; ++u)
 #pragma unroll
-          for (int w = 0; w < 4; ++w) acc[u][w] = fma(a[u], bq[w], acc[u][w]);
-      }
+          for (int w = 0; w < 4; ++w) acc[u][w] = 0.0;
+        int ri[4], rj[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < 4; ++u) { ri[u] = min(nb + ti * 4 + u, rows - 1) * CH_LD; rj[u] = min(nb + tj * 4 + u, rows - 1) * CH_LD; }
+        for (int c = 0; c < nb; ++c) {
+          double a[4], bq[4];
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
-          const int gi = nb + ti * 4 + u, gj = nb + tj * 4 + w;
-          if (gi < rows && gj <= gi) A[(size_t)(k0 + gi) * D + k0 + gj] -= acc[u][w];
+          for (int u = 0; u < 4; ++u) { a[u] = Pn[ri[u] + c]; bq[u] = Pn[rj[u] + c]; }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int w = 0; w < 4; ++w) acc[u][w] = fma(a[u], bq[w], acc[u][w]);
         }
+        const int gj0 = nb + tj * 4;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int gi = nb + ti * 4 + u;
+          if (gi >= rows) continue;
+          double* arow = A + (size_t)(k0 + gi) * D + k0 + gj0;
+          if ((D & 1) == 0 && gj0 + 3 <= gi) {             // the tile's four columns of this row: two 16-byte updates
+            double2* a2 = reinterpret_cast<double2*>(arow);
+            double2 v0 = a2[0], v1 = a2[1];
+            v0.x -= acc[u][0]; v0.y -= acc[u][1]; v1.x -= acc[u][2]; v1.y -= acc[u][3];
+            a2[0] = v0; a2[1] = v1;
+          } else {
+#pragma unroll
+            for (int w = 0; w < 4; ++w)
+              if (gj0 + w <= gi) arow[w] -= acc[u][w];
+          }
+        }
+      }
     }
   }
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 chol_factor_solve_kernel(const float* __restrict__ Lp, int ldp, const float* __restrict__ rhs, int ldr, float offset,
                          const float* __restrict__ emb_mean, double* __restrict__ fac, float* __restrict__ wfull,
                          float* __restrict__ iv, int D) {
@@ -346,9 +395,27 @@ chol_factor_solve_kernel(const float* __restrict__ Lp, int ldp, const float* __r
   double* A = fac + (size_t)b * D * D;
   const float* lp = Lp + (size_t)b * ldp;
   // unpack (upper-triangle packing: p = i*D - i(i-1)/2 + (j-i), i <= j) into the lower triangle; L = I + sum_c N_c U_c
-  for (int i = 0; i < D; ++i)
-    for (int j = i + threadIdx.x; j < D; j += blockDim.x)
-      A[(size_t)j * D + i] = (double)lp[(size_t)i * D - (size_t)i * (i - 1) / 2 + (j - i)] + (i == j ? 1.0 : 0.0);
+  // through 32 x 32 tiles (one per warp at a time, in the panel buffer) so that both the packed rows and A's rows are read and
+  // written along their contiguous direction (writing A[j][i] with j across the lanes was 9 % of the kernel's samples)
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5, nbk = (D + 31) / 32;
+    float* tile = reinterpret_cast<float*>(Pn) + warp * (32 * 33);
+    int cnt = 0;
+    for (int bi = 0; bi < nbk; ++bi)
+      for (int bj = bi; bj < nbk; ++bj, ++cnt) {
+        if (cnt % nw != warp) continue;
+        for (int ii = 0; ii < 32; ++ii) {
+          const int i = 32 * bi + ii, j = 32 * bj + lane;
+          if (i < D && j < D && j >= i) tile[ii * 33 + lane] = lp[(size_t)i * D - (size_t)i * (i - 1) / 2 + (j - i)];
+        }
+        __syncwarp();
+        for (int jj = 0; jj < 32; ++jj) {
+          const int j = 32 * bj + jj, i = 32 * bi + lane;
+          if (j < D && i <= j) A[(size_t)j * D + i] = (double)tile[lane * 33 + jj] + (i == j ? 1.0 : 0.0);
+        }
+        __syncwarp();
+      }
+  }
   chol_factor_blocked(A, D, Pn);
   // linear[0] += prior_offset; ivector[0] -= prior_offset (ivector_extract.py:108-113); then the global mean is removed
   for (int i = threadIdx.x; i < D; i += blockDim.x) vs[i] = (double)rhs[(size_t)b * ldr + i] + (i == 0 ? (double)offset : 0.0);
@@ -502,7 +569,11 @@ int sg_softmax_rows_launch(const float* a, const float* b, float* out, int rows,
   SG_LAUNCH_CHECK();
   return SG_OK;
 }
-static size_t chol_smem(int D) { return ((size_t)D + 8 * CH_NB + (size_t)D * CH_LD) * sizeof(double); }
+// [D] right-hand side, [8 * 32] reduction scratch, panel [D * 33] - which also holds the eight 32 x 33 float tiles of the unpack
+static size_t chol_smem(int D) {
+  const size_t panel = (size_t)D * CH_LD, tiles = 8 * 32 * 33 / 2;
+  return ((size_t)D + 8 * CH_NB + (panel > tiles ? panel : tiles)) * sizeof(double);
+}
 static int chol_init(int D) {
   static int configured[64] = {0};                         // per device (function attributes are per context)
   const int need = (int)chol_smem(D);
