@@ -25,6 +25,7 @@ struct SgIv {
   int C, F, D, L, Lp, Fa, Dp, P, Pp, Kq;
   float offset;
   float *Wq, *WqT, *gconst;        // [Kq, C], [C, Kq], [C]
+  uint32_t* qidx;                  // [Kq]: factor pair of every column of the quadratic expansion (i | j << 16; see quad_expand_fwd_kernel)
   float *Wq3K, *WqT3K;             // 3xTF32 operands (K-major): [C, 3Kq] = [hi|lo|hi](WqT), [Kq, 3C] = [hi|lo|hi](Wq)
   float *U;                        // [C, Pp]: packed upper triangles of U_c = T_c' S_c^-1 T_c
   float *UT3;                      // 3xTF32 operand of the L assembly, K-major [Pp, 3C] = [hi|lo|hi](U^T); built on first use
@@ -102,6 +103,18 @@ extern "C" int sg_load_iv(sg_handle* h, const sg_iv_weights* w) {
         }
       SG_TRY(sg_dev_upload(h, &m->Wq3K, A3));
       SG_TRY(sg_dev_upload(h, &m->WqT3K, B3));
+    }
+    {
+      std::vector<uint32_t> qi((size_t)Kq, 0xffffu);                 // padding columns
+      for (int f = 0; f < F; ++f) qi[f] = (uint32_t)f | (0xffffu << 16);
+      int k = F;
+      for (int i = 0; i < F; ++i)
+        for (int j = i; j < F; ++j) qi[k++] = (uint32_t)i | ((uint32_t)j << 16);
+      std::vector<float> qf((size_t)Kq);
+      memcpy(qf.data(), qi.data(), (size_t)Kq * sizeof(float));
+      float* dq = nullptr;
+      SG_TRY(sg_dev_upload(h, &dq, qf));
+      m->qidx = reinterpret_cast<uint32_t*>(dq);
     }
     SG_TRY(sg_dev_upload(h, &m->gconst, std::vector<float>(w->gmm_gconsts, w->gmm_gconsts + C)));
   }
@@ -265,10 +278,10 @@ static int iv_embed_fwd(sg_handle* h, const float* feat, int ld, int B, int T, c
   IV_K(sg_transpose_batched_launch(w.Xa, w.XaT, Tp, Fa, Fa, Tp, (size_t)Tp * Fa, (size_t)Tp * Fa, B, st));
   const bool tc = h->precision != SG_PREC_FP32;
   if (tc) {
-    IV_K(sg_quad_expand_launch(w.Xa, Fa, w.Q, 3 * m->Kq, R, F, 1, m->Kq, st));
+    IV_K(sg_quad_expand_launch(w.Xa, Fa, w.Q, 3 * m->Kq, R, F, 1, m->Kq, m->qidx, st));
     SG_TRY(iv_gemm_tc3(h, w.Q, 3 * m->Kq, m->Wq3K, m->gconst, w.post, C, R, C, st));
   } else {
-    IV_K(sg_quad_expand_launch(w.Xa, Fa, w.Q, m->Kq, R, F, 0, 0, st));
+    IV_K(sg_quad_expand_launch(w.Xa, Fa, w.Q, m->Kq, R, F, 0, 0, nullptr, st));
     SG_TRY(iv_gemm(h, gemm_args(w.Q, m->Kq, m->Wq, m->WqT, m->gconst, w.post, C, R, C, m->Kq), st));
   }
   IV_K(sg_softmax_rows_launch(w.post, nullptr, w.post, R, C, T, Tp, 0, 0, st));

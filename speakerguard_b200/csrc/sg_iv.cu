@@ -8,6 +8,7 @@
 // and per-utterance pieces:
 //   delta filters, quadratic feature expansion, row softmax, and a batched SPD solve (fp64 Cholesky).
 #include <math.h>
+#include <stdint.h>
 
 #include "sg_common.cuh"
 
@@ -78,11 +79,26 @@ __global__ void delta_bwd_kernel(const float* __restrict__ dout, int ldo, float*
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
 // split3 != 0: the row holds three K-segments [lo | hi | hi] of width kseg (3xTF32 operand layout, see sg_api_iv.cu)
+// idx (optional, [kseg]): the factor pair of column k as i | j << 16, j = 0xffff for a linear column, i = 0xffff for padding -
+// with it the kernel is a table lookup, two shared-memory reads and three coalesced stores per column (1.11 -> see DESIGN)
 __global__ void quad_expand_fwd_kernel(const float* __restrict__ xa, int ldx, float* __restrict__ q, int ldq, int F,
-                                       int split3, int kseg) {
+                                       int split3, int kseg, const uint32_t* __restrict__ idx) {
   extern __shared__ float xs[];                                   // [F]
   const int row = blockIdx.x;
   float* qr = q + (size_t)row * ldq;
+  if (split3 && idx) {
+    for (int i = threadIdx.x; i < F; i += blockDim.x) xs[i] = xa[(size_t)row * ldx + i];
+    __syncthreads();
+    for (int k = threadIdx.x; k < kseg; k += blockDim.x) {
+      const uint32_t ij = __ldg(idx + k);
+      const uint32_t i = ij & 0xffffu, j = ij >> 16;
+      float v = 0.f;
+      if (i != 0xffffu) v = (j == 0xffffu) ? xs[i] : xs[i] * xs[j];
+      const float hi = tf32_hi(v);
+      qr[k] = v - hi; qr[kseg + k] = hi; qr[2 * kseg + k] = hi;
+    }
+    return;
+  }
   if (split3) {
     for (int i = threadIdx.x; i < F; i += blockDim.x) xs[i] = xa[(size_t)row * ldx + i];
     __syncthreads();
@@ -181,6 +197,77 @@ __global__ void softmax_rows_fwd_kernel(const float* ll, float* post, int C, int
   s = iv_block_reduce(s, red, false);
   const float inv = 1.f / s;
   for (int c = threadIdx.x; c < C; c += blockDim.x) pr[c] = expf(lr[c] - mx) * inv;
+}
+// One warp per row with the row in registers (C = 128 * NV: NV float4 per lane): one pass over memory, one exp per element,
+// shuffle reductions instead of block barriers.  The CTA-per-row form above read the row three times through L1 and ran at
+// 2.7 x the time of its HBM traffic at C = 2048.
+template <int NV>
+__global__ void __launch_bounds__(256)
+softmax_rows_fwd_warp_kernel(const float* ll, float* post, int rows, int T, int Tp) {
+  const int lane = threadIdx.x & 31, row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  constexpr int C = 128 * NV;
+  const float4* lr = reinterpret_cast<const float4*>(ll + (size_t)row * C);
+  float4* pr = reinterpret_cast<float4*>(post + (size_t)row * C);
+  if (row % Tp >= T) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) pr[i * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  float4 v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = lr[i * 32 + lane];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) mx = fmaxf(mx, fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w)));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i].x = expf(v[i].x - mx); v[i].y = expf(v[i].y - mx); v[i].z = expf(v[i].z - mx); v[i].w = expf(v[i].w - mx);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float inv = 1.f / s;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) pr[i * 32 + lane] = make_float4(v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv);
+}
+template <int NV>
+__global__ void __launch_bounds__(256)
+softmax_rows_bwd_warp_kernel(const float* __restrict__ post, const float* dpost, float* dll, int rows, int T, int Tp, int split3) {
+  const int lane = threadIdx.x & 31, row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  constexpr int C = 128 * NV;
+  const int nseg = split3 ? 3 : 1;
+  float4* o = reinterpret_cast<float4*>(dll + (size_t)row * C * nseg);
+  if (row % Tp >= T) {
+    for (int i = lane; i < NV * 32 * nseg; i += 32) o[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  const float4* pr = reinterpret_cast<const float4*>(post + (size_t)row * C);
+  const float4* dr = reinterpret_cast<const float4*>(dpost + (size_t)row * C);
+  float4 p[NV], d[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) { p[i] = __ldg(pr + i * 32 + lane); d[i] = dr[i * 32 + lane]; }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) { s = fmaf(d[i].x, p[i].x, s); s = fmaf(d[i].y, p[i].y, s); s = fmaf(d[i].z, p[i].z, s); s = fmaf(d[i].w, p[i].w, s); }
+#pragma unroll
+  for (int k = 16; k > 0; k >>= 1) s += __shfl_xor_sync(0xffffffffu, s, k);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 v = make_float4(p[i].x * (d[i].x - s), p[i].y * (d[i].y - s), p[i].z * (d[i].z - s), p[i].w * (d[i].w - s));
+    if (split3) {
+      const float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+      o[i * 32 + lane] = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+      o[NV * 32 + i * 32 + lane] = hi;
+      o[2 * NV * 32 + i * 32 + lane] = hi;
+    } else {
+      o[i * 32 + lane] = v;
+    }
+  }
 }
 // dll = post * (dpost - sum_c dpost_c post_c)
 // split3: dll is written as [lo | hi | hi] segments of width C into a row of 3C (operand of the 3xTF32 contraction)
@@ -551,8 +638,9 @@ int sg_pad_aug_launch(const float* feat, int ld, float* xa, int Fa, int B, int T
   SG_LAUNCH_CHECK();
   return SG_OK;
 }
-int sg_quad_expand_launch(const float* xa, int ldx, float* q, int ldq, int rows, int F, int split3, int kseg, cudaStream_t st) {
-  quad_expand_fwd_kernel<<<rows, 256, F * sizeof(float), st>>>(xa, ldx, q, ldq, F, split3, kseg);
+int sg_quad_expand_launch(const float* xa, int ldx, float* q, int ldq, int rows, int F, int split3, int kseg, const uint32_t* idx,
+                          cudaStream_t st) {
+  quad_expand_fwd_kernel<<<rows, 256, F * sizeof(float), st>>>(xa, ldx, q, ldq, F, split3, kseg, idx);
   SG_LAUNCH_CHECK();
   return SG_OK;
 }
@@ -564,6 +652,17 @@ int sg_quad_expand_bwd_launch(const float* dq, int ldq, const float* xa, int ldx
 }
 int sg_softmax_rows_launch(const float* a, const float* b, float* out, int rows, int C, int T, int Tp, int backward,
                            int split3, cudaStream_t st) {
+  const bool al = (((uintptr_t)a | (uintptr_t)b | (uintptr_t)out) & 15) == 0;
+  if (C == 2048 && al) {
+    if (!backward) softmax_rows_fwd_warp_kernel<16><<<(rows + 7) / 8, 256, 0, st>>>(a, out, rows, T, Tp);
+    else softmax_rows_bwd_warp_kernel<16><<<(rows + 7) / 8, 256, 0, st>>>(a, b, out, rows, T, Tp, split3);
+  } else if (C == 1024 && al) {
+    if (!backward) softmax_rows_fwd_warp_kernel<8><<<(rows + 7) / 8, 256, 0, st>>>(a, out, rows, T, Tp);
+    else softmax_rows_bwd_warp_kernel<8><<<(rows + 7) / 8, 256, 0, st>>>(a, b, out, rows, T, Tp, split3);
+  } else if (C == 256 && al) {
+    if (!backward) softmax_rows_fwd_warp_kernel<2><<<(rows + 7) / 8, 256, 0, st>>>(a, out, rows, T, Tp);
+    else softmax_rows_bwd_warp_kernel<2><<<(rows + 7) / 8, 256, 0, st>>>(a, b, out, rows, T, Tp, split3);
+  } else
   if (!backward) softmax_rows_fwd_kernel<<<rows, 256, 0, st>>>(a, out, C, T, Tp);
   else softmax_rows_bwd_kernel<<<rows, 256, 0, st>>>(a, b, out, C, T, Tp, split3);
   SG_LAUNCH_CHECK();
