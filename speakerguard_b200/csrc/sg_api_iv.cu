@@ -30,6 +30,8 @@ struct SgIv {
   float *U;                        // [C, Pp]: packed upper triangles of U_c = T_c' S_c^-1 T_c
   float *UT3;                      // 3xTF32 operand of the L assembly, K-major [Pp, 3C] = [hi|lo|hi](U^T); built on first use
   float *Tt;                       // [Dp, F*C]: Tt[d, f*C + c] = T_c[f, d]   (adjoint of the L assembly)
+  float *Wlin3K, *Tt3K;            // 3xTF32 operands of the two [B, Dp] x [Dp, F*C] adjoint contractions, K-major [F*C, K3p]; built on first use
+  int K3p;                         // 3 Dp rounded up to the tensor core's k-block
   float *Wlin, *WlinT;             // [F*C, Dp], [Dp, F*C]
   float *Wlda, *Wlda_b, *blda;     // [Dp, Lp], [Lp, Dp], [Lp]
   float* emb_mean;                 // [Dp]
@@ -183,7 +185,7 @@ extern "C" int sg_load_iv(sg_handle* h, const sg_iv_weights* w) {
 
 // ---------------------------------------------------------------------------------------------
 struct IvWs {
-  float *Xa, *XaT, *Q, *post, *dpost, *FsT, *dFsT, *dFs, *Lpk, *lin, *dlin, *wfull, *iv, *div, *e2, *de2, *tsave, *scal, *dXa, *part, *dll3, *N3;
+  float *Xa, *XaT, *Q, *post, *dpost, *FsT, *dFsT, *dFs, *Lpk, *lin, *dlin, *wfull, *iv, *div, *e2, *de2, *tsave, *scal, *dXa, *part, *dll3, *N3, *d3;
   double* fac;
   size_t bytes;
 };
@@ -199,6 +201,7 @@ static IvWs iv_ws_layout(void* base, const SgIv* m, int B, int T) {
   w.post = take(R * m->C); w.dpost = take(R * m->C);
   w.FsT = take((size_t)B * m->Fa * m->C); w.dFsT = take((size_t)B * m->Fa * m->C); w.dFs = take((size_t)B * m->Fa * m->C);
   w.Lpk = take((size_t)B * m->Pp); w.N3 = take((size_t)B * 3 * m->C);
+  w.d3 = take((size_t)B * ((3 * m->Dp + 31) / 32 * 32));
   w.lin = take((size_t)B * m->Dp); w.dlin = take((size_t)B * m->Dp);
   w.wfull = take((size_t)B * m->Dp); w.iv = take((size_t)B * m->Dp); w.div = take((size_t)B * m->Dp);
   w.e2 = take((size_t)B * m->Lp); w.de2 = take((size_t)B * m->Lp); w.tsave = take((size_t)B * m->Lp);
@@ -248,6 +251,20 @@ static int iv_build_ut3(sg_handle* h, cudaStream_t st) {
   SG_CUDA_CHECK(cudaMalloc((void**)&m->UT3, (size_t)m->Pp * 3 * m->C * sizeof(float)));
   h->allocs.push_back(m->UT3);
   return sg_build_ut3_launch(m->U, m->UT3, m->C, m->Pp, st);
+}
+// ~0.7 GB each at C = 2048, D = 400: only built when a tensor-core precision is set and the adjoint runs
+static int iv_build_w3(sg_handle* h, cudaStream_t st) {
+  SgIv* m = h->iv;
+  if (m->Wlin3K) return SG_OK;
+  const size_t N = (size_t)m->F * m->C;
+  m->K3p = (3 * m->Dp + 31) / 32 * 32;
+  SG_CUDA_CHECK(cudaMalloc((void**)&m->Wlin3K, N * m->K3p * sizeof(float)));
+  h->allocs.push_back(m->Wlin3K);
+  SG_CUDA_CHECK(cudaMalloc((void**)&m->Tt3K, N * m->K3p * sizeof(float)));
+  h->allocs.push_back(m->Tt3K);
+  SG_TRY(sg_build_w3_launch(m->Wlin, (size_t)m->Dp, 1, m->Wlin3K, (int)N, m->Dp, m->K3p, st));     // Wlin [F*C, Dp]
+  SG_TRY(sg_build_w3_launch(m->Tt, 1, N, m->Tt3K, (int)N, m->Dp, m->K3p, st));                     // Tt [Dp, F*C]
+  return SG_OK;
 }
 static int iv_gemm(sg_handle* h, const SgConvArgs& a, cudaStream_t st) {
   h->launches += 1;
@@ -313,9 +330,17 @@ static int iv_embed_bwd(sg_handle* h, const float* demb, int B, int T, const IvW
   SG_TRY(iv_gemm(h, gemm_args(w.de2, m->Lp, m->Wlda_b, m->Wlda, nullptr, w.div, m->Dp, B, m->Dp, m->Lp), st));
   IV_K(sg_chol_solve_bwd_launch(w.fac, w.wfull, w.div, m->Dp, w.dlin, nullptr, m->Pp, B, m->D, st));
   SG_CUDA_CHECK(cudaMemsetAsync(w.dFsT, 0, (size_t)B * Fa * C * sizeof(float), st));
-  SG_TRY(iv_gemm(h, gemm_args(w.dlin, m->Dp, m->WlinT, m->Wlin, nullptr, w.dFsT, Fa * C, B, F * C, m->Dp), st));
   // dL = -lambda w' contracts with U_c = G_c T_c without forming it: dN_c = -(G_c' lambda) . (T_c w) = -dF_c . (T_c w)
-  SG_TRY(iv_gemm(h, gemm_args(w.wfull, m->Dp, m->Tt, nullptr, nullptr, w.dFs, Fa * C, B, F * C, m->Dp), st));
+  if (h->precision != SG_PREC_FP32 && (F * C) % 32 == 0) {      // both as 3xTF32: [B, K3p] x [K3p, F*C]
+    SG_TRY(iv_build_w3(h, st));
+    IV_K(sg_split3_rows_ld_launch(w.dlin, m->Dp, w.d3, m->K3p, B, m->Dp, st));
+    SG_TRY(iv_gemm_tc3(h, w.d3, m->K3p, m->Wlin3K, nullptr, w.dFsT, Fa * C, B, F * C, st));
+    IV_K(sg_split3_rows_ld_launch(w.wfull, m->Dp, w.d3, m->K3p, B, m->Dp, st));
+    SG_TRY(iv_gemm_tc3(h, w.d3, m->K3p, m->Tt3K, nullptr, w.dFs, Fa * C, B, F * C, st));
+  } else {
+    SG_TRY(iv_gemm(h, gemm_args(w.dlin, m->Dp, m->WlinT, m->Wlin, nullptr, w.dFsT, Fa * C, B, F * C, m->Dp), st));
+    SG_TRY(iv_gemm(h, gemm_args(w.wfull, m->Dp, m->Tt, nullptr, nullptr, w.dFs, Fa * C, B, F * C, m->Dp), st));
+  }
   IV_K(sg_dn_from_df_launch(w.dFsT, w.dFs, B, F, Fa, C, st));
   {  // d post_b = Xa_b dFsT_b : [Tp, Fa] x [Fa, C]
     SgConvArgs a = gemm_args(w.Xa, Fa, w.dFsT, nullptr, nullptr, w.dpost, C, Tp, C, Fa);

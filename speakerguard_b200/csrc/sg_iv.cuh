@@ -20,4 +20,6 @@ int sg_transpose_batched_launch(const float* in, float* out, int R, int C, int l
 int sg_splitk_reduce_launch(const float* part, int splits, int rows, int N, float* out, int ldo, cudaStream_t st);
 int sg_split3_rows_launch(const float* in, int ld, float* out, int rows, int C, cudaStream_t st);
 int sg_build_ut3_launch(const float* U, float* UT3, int C, int Pp, cudaStream_t st);
+int sg_split3_rows_ld_launch(const float* in, int ld, float* out, int ldo, int rows, int C, cudaStream_t st);
+int sg_build_w3_launch(const float* src, size_t sn, size_t sd, float* W3, int N, int K, int K3p, cudaStream_t st);
 int sg_dn_from_df_launch(float* dFsT, const float* a, int B, int F, int Fa, int C, cudaStream_t st);
