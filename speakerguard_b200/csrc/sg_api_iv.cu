@@ -30,6 +30,7 @@ struct SgIv {
   float *U;                        // [C, Pp]: packed upper triangles of U_c = T_c' S_c^-1 T_c
   float *UT3;                      // 3xTF32 operand of the L assembly, K-major [Pp, 3C] = [hi|lo|hi](U^T); built on first use
   float *Tt;                       // [Dp, F*C]: Tt[d, f*C + c] = T_c[f, d]   (adjoint of the L assembly)
+  float* WlinT3;                   // 3xTF32 operand of the linear term computed transposed, K-major [Dp, 3 F C] = [hi | lo | hi](Wlin^T); built on first use
   float *Wlin3K, *Tt3K;            // 3xTF32 operands of the two [B, Dp] x [Dp, F*C] adjoint contractions, K-major [F*C, K3p]; built on first use
   int K3p;                         // 3 Dp rounded up to the tensor core's k-block
   float *Wlin, *WlinT;             // [F*C, Dp], [Dp, F*C]
@@ -189,6 +190,14 @@ struct IvWs {
   double* fac;
   size_t bytes;
 };
+// split-K scratch: the SIMT skinny contractions (IV_SPLITS slices of [B, max(C, Dp)]) or the tensor-core linear term
+// (32 slices of [Dp rounded to 128, B rounded to 32] plus its transposed result)
+static size_t iv_part_floats(const SgIv* m, int B) {
+  const size_t simt = (size_t)IV_SPLITS * B * (m->C > m->Dp ? m->C : m->Dp);
+  const size_t Bp = ((size_t)B + 31) / 32 * 32, mrows = ((size_t)m->Dp + 127) / 128 * 128;
+  const size_t tc = 32 * mrows * Bp + (size_t)m->Dp * Bp;
+  return simt > tc ? simt : tc;
+}
 static IvWs iv_ws_layout(void* base, const SgIv* m, int B, int T) {
   IvWs w;
   char* p = (char*)base;
@@ -207,7 +216,7 @@ static IvWs iv_ws_layout(void* base, const SgIv* m, int B, int T) {
   w.e2 = take((size_t)B * m->Lp); w.de2 = take((size_t)B * m->Lp); w.tsave = take((size_t)B * m->Lp);
   w.scal = take((size_t)B * 4);
   w.fac = (double*)take((size_t)B * m->D * m->D * 2);
-  w.part = take((size_t)IV_SPLITS * B * (m->C > m->Dp ? m->C : m->Dp));
+  w.part = take(iv_part_floats(m, B));
   w.bytes = off;
   return w;
 }
@@ -266,6 +275,14 @@ static int iv_build_w3(sg_handle* h, cudaStream_t st) {
   SG_TRY(sg_build_w3_launch(m->Tt, 1, N, m->Tt3K, (int)N, m->Dp, m->K3p, st));                     // Tt [Dp, F*C]
   return SG_OK;
 }
+static int iv_build_wlint3(sg_handle* h, cudaStream_t st) {
+  SgIv* m = h->iv;
+  if (m->WlinT3) return SG_OK;
+  const size_t K = (size_t)m->F * m->C;
+  SG_CUDA_CHECK(cudaMalloc((void**)&m->WlinT3, (size_t)m->Dp * 3 * K * sizeof(float)));
+  h->allocs.push_back(m->WlinT3);
+  return sg_build_w3_launch(m->WlinT, K, 1, m->WlinT3, m->Dp, (int)K, (int)(3 * K), st);              // WlinT [Dp, F*C]
+}
 static int iv_gemm(sg_handle* h, const SgConvArgs& a, cudaStream_t st) {
   h->launches += 1;
   PROF(h, SG_PROF_IV_GEMM, st, sg_conv_simt(a, st));
@@ -314,7 +331,30 @@ static int iv_embed_fwd(sg_handle* h, const float* feat, int ld, int B, int T, c
   } else {
     SG_TRY(iv_gemm(h, gemm_args(w.FsT + (size_t)F * C, Fa * C, m->U, nullptr, nullptr, w.Lpk, m->Pp, B, m->Pp, C), st));
   }
-  SG_TRY(iv_gemm_splitk(h, gemm_args(w.FsT, Fa * C, m->Wlin, m->WlinT, nullptr, w.lin, m->Dp, B, m->Dp, F * C), w.part, st));
+  {
+    // linear term vec(F) Wlin.  Tensor-core form: computed transposed, lin' [Dp, B] = Wlin' [Dp, 3 F C] x vec(F)' - the weights
+    // are the row operand (4 row tiles at D = 400), the B utterances the 32-padded column operand, K split 32 ways (128 CTAs
+    // stream the 0.7 GB split weights once); both split operands of the pass live in the expansion buffer, dead by now.
+    const size_t K = (size_t)F * C;
+    const int Bp = (B + 31) / 32 * 32, mrows = (m->Dp + 127) / 128 * 128;
+    const size_t need = (size_t)32 * mrows * Bp, part_floats = iv_part_floats(m, B);
+    if (tc && K % 32 == 0 && Bp <= 512 && need + (size_t)m->Dp * Bp <= part_floats && (size_t)Bp * 3 * K <= (size_t)R * m->Kq * 3) {
+      SG_TRY(iv_build_wlint3(h, st));
+      float* F3 = w.Q;
+      float* linT = w.part + need;
+      if (Bp > B) SG_CUDA_CHECK(cudaMemsetAsync(F3 + (size_t)B * 3 * K, 0, (size_t)(Bp - B) * 3 * K * sizeof(float), st));
+      IV_K(sg_split3_rows_ld_launch(w.FsT, Fa * C, F3, (int)(3 * K), B, (int)K, st));
+      SgConvArgs a;
+      memset(&a, 0, sizeof(a));
+      a.A = m->WlinT3; a.lda = (int)(3 * K); a.Wk = F3; a.out = linT; a.ldo = Bp; a.rows = m->Dp; a.N = Bp; a.cin = (int)(3 * K);
+      a.taps = 1; a.T = 1; a.epilogue = SG_EPI_NONE; a.splitk_ws = w.part; a.splitk_floats = need;
+      h->launches += 2;
+      PROF(h, SG_PROF_IV_GEMM, st, sg_conv_tc(a, SG_PREC_TF32, st));
+      IV_K(sg_transpose_batched_launch(linT, w.lin, m->Dp, B, Bp, m->Dp, 0, 0, 1, st));
+    } else {
+      SG_TRY(iv_gemm_splitk(h, gemm_args(w.FsT, Fa * C, m->Wlin, m->WlinT, nullptr, w.lin, m->Dp, B, m->Dp, F * C), w.part, st));
+    }
+  }
   IV_K(sg_chol_solve_launch(w.Lpk, m->Pp, w.lin, m->Dp, m->offset, m->emb_mean, w.fac, w.wfull, w.iv, B, m->D, st));
   SG_TRY(iv_gemm(h, gemm_args(w.iv, m->Dp, m->Wlda, m->Wlda_b, m->blda, w.e2, m->Lp, B, m->Lp, m->Dp), st));
   h->launches += 1;
@@ -342,6 +382,23 @@ static int iv_embed_bwd(sg_handle* h, const float* demb, int B, int T, const IvW
     SG_TRY(iv_gemm(h, gemm_args(w.wfull, m->Dp, m->Tt, nullptr, nullptr, w.dFs, Fa * C, B, F * C, m->Dp), st));
   }
   IV_K(sg_dn_from_df_launch(w.dFsT, w.dFs, B, F, Fa, C, st));
+  // dFs_b = dFsT_b^T  [C, Fa]: the K-major operand of d post, and the first-order statistics' direct path to x further down
+  IV_K(sg_transpose_batched_launch(w.dFsT, w.dFs, Fa, C, C, Fa, (size_t)Fa * C, (size_t)Fa * C, B, st));
+  const int K3a = (3 * Fa + 31) / 32 * 32;
+  if (h->precision != SG_PREC_FP32 && C % 32 == 0 && (size_t)(R + B * C) * K3a <= (size_t)R * m->Kq * 3) {
+    // d post_b = Xa_b dFs_b' as a batched 3xTF32 contraction on tcgen05: one [C, 3 Fa] operand per utterance, tiles of 128
+    // frames of one utterance.  Both split operands live in the (dead at this point) buffer of the quadratic expansion.
+    float* X3 = w.Q;
+    float* W3 = w.Q + (size_t)R * K3a;
+    IV_K(sg_split3_rows_ld_launch(w.Xa, Fa, X3, K3a, R, Fa, st));
+    IV_K(sg_build_w3_launch(w.dFs, (size_t)Fa, 1, W3, B * C, Fa, K3a, st));
+    SgConvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.A = X3; a.lda = K3a; a.Wk = W3; a.out = w.dpost; a.ldo = C; a.rows = R; a.N = C; a.cin = K3a;
+    a.taps = 1; a.T = Tp; a.same_utt = 1; a.w_per_utt = 1; a.epilogue = SG_EPI_NONE;
+    h->launches += 1;
+    PROF(h, SG_PROF_IV_GEMM, st, sg_conv_tc(a, SG_PREC_TF32, st));
+  } else
   {  // d post_b = Xa_b dFsT_b : [Tp, Fa] x [Fa, C]
     SgConvArgs a = gemm_args(w.Xa, Fa, w.dFsT, nullptr, nullptr, w.dpost, C, Tp, C, Fa);
     a.nbatch = B; a.strideA = (long long)Tp * Fa; a.strideW = (long long)Fa * C; a.strideO = (long long)Tp * C;
@@ -354,8 +411,7 @@ static int iv_embed_bwd(sg_handle* h, const float* demb, int B, int T, const IvW
     IV_K(sg_softmax_rows_launch(w.post, w.dpost, w.dpost, R, C, T, Tp, 1, 0, st));
     SG_TRY(iv_gemm(h, gemm_args(w.dpost, C, m->WqT, m->Wq, nullptr, w.Q, m->Kq, R, m->Kq, C), st));
   }
-  // the first-order statistics also depend on x directly: dXa_b = post_b dFs_b, dFs_b = dFsT_b^T  [C, Fa]
-  IV_K(sg_transpose_batched_launch(w.dFsT, w.dFs, Fa, C, C, Fa, (size_t)Fa * C, (size_t)Fa * C, B, st));
+  // the first-order statistics also depend on x directly: dXa_b = post_b dFs_b
   {
     SgConvArgs a = gemm_args(w.post, C, w.dFs, nullptr, nullptr, w.dXa, Fa, Tp, Fa, C);
     a.nbatch = B; a.strideA = (long long)Tp * C; a.strideW = (long long)C * Fa; a.strideO = (long long)Tp * Fa;

@@ -117,6 +117,7 @@ struct SgConvArgs {
   int cin;                          // K per tap (multiple of 16)
   int taps; int tap_step;           // source row of tap k = p + tap_base + k*tap_step (may be negative)
   int tap_base; int same_utt;       // same_utt: taps that leave the utterance (row / T changes) read zero ('same' padding)
+  int w_per_utt;                    // tensor-core path with same_utt: Wk holds one [N, taps*cin] K-major operand PER UTTERANCE (batched contraction)
   int epilogue;
   const float* mask; int ldmask;    // SG_EPI_MASK: post-ReLU activation of the producing layer
   int T; int t_valid;               // rows per utterance / valid rows (SG_EPI_MASK)

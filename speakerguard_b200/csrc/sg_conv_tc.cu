@@ -180,6 +180,7 @@ struct TcArgs {
   // utt_T frames); A and the output are addressed through 3-D maps (channel, frame, utterance), taps read frame
   // f + tap_base + tap * tap_step and frames outside the utterance read zero
   int utt_T, utt_tpu, tap_base;
+  int wb_rows;                     // rows of the B operand per utterance (0: one operand shared by all tiles)
 };
 
 // ---- cluster / cta_group::2 helpers ------------------------------------------------------------
@@ -343,7 +344,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const int ub = mt / a.utt_tpu, f0 = (mt - ub * a.utt_tpu) * TC_BM;
             mbar_expect_tx(&full[stage], tx);
             tma_load_3d(sa, &mapA, &full[stage], kc * KB_ELEMS, f0 + a.tap_base + tap * a.tap_step, ub);
-            tma_load_2d(sa + TC_A_BYTES, &mapB, &full[stage], kb * KB_ELEMS, n0);
+            tma_load_2d(sa + TC_A_BYTES, &mapB, &full[stage], kb * KB_ELEMS, n0 + ub * a.wb_rows);
           } else {
             mbar_expect_tx(&full[stage], tx);
             tma_load_2d(sa, &mapA, &full[stage], kc * KB_ELEMS, p0 + tap * a.tap_step);
@@ -847,7 +848,7 @@ int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
   // (tests/test_gpu_shard.py).
   if (g_small_bn && !utt && !a.xf_ab && a.splitk_ws && !a.out_bf16 && !a.bits_out && a.N % 4 == 0 && a.ldo % 4 == 0 && a.N <= 512 &&
       (a.epilogue == SG_EPI_BIAS || a.epilogue == SG_EPI_NONE)) {
-    const int S = nkb_all >= 64 ? 8 : (nkb_all >= 16 ? 4 : 1);
+    const int S = nkb_all >= 2048 ? 32 : (nkb_all >= 64 ? 8 : (nkb_all >= 16 ? 4 : 1));   // 32: the i-vector linear term, K = 3 F C
     const size_t need = (size_t)S * ((a.rows + TC_BM - 1) / TC_BM) * TC_BM * a.N;
     if (S > 1 && (S - 1) * ((nkb_all + S - 1) / S) < nkb_all) {
       if (need > a.splitk_floats) { sg_set_error("sg_conv_tc: split-K scratch too small (%zu floats needed, %zu given)", need, a.splitk_floats); return SG_EINVAL; }
@@ -865,7 +866,9 @@ int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
   else r = make_map(&mapA, a.A, a.op_bf16, (uint64_t)a.rows, (uint64_t)a.cin, (uint64_t)a.lda, TC_BM);
   if (r != SG_OK) return r;
   if (!a.Wk) { sg_set_error("sg_conv_tc: K-major weights missing"); return SG_EINVAL; }
-  r = make_map(&mapB, a.Wk, a.op_bf16, (uint64_t)a.N, (uint64_t)a.taps * a.cin, (uint64_t)a.taps * a.cin, (uint32_t)bn);
+  if (a.w_per_utt && !utt) { sg_set_error("sg_conv_tc: per-utterance weights need the utterance-tiled mode"); return SG_EUNSUPPORTED; }
+  r = make_map(&mapB, a.Wk, a.op_bf16, (uint64_t)a.N * (a.w_per_utt ? (uint64_t)(a.rows / a.T) : 1), (uint64_t)a.taps * a.cin,
+               (uint64_t)a.taps * a.cin, (uint32_t)bn);
   if (r != SG_OK) return r;
   TcArgs t;
   t.bits_out = a.bits_out; t.bits_in = a.bits_in; t.ldbits = a.ldbits;
@@ -873,7 +876,7 @@ int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
   t.rows = a.rows; t.N = a.N; t.bn = bn; t.kchunks = a.cin / kbe; t.taps = a.taps; t.tap_step = a.tap_step;
   t.epilogue = a.epilogue; t.T = a.T > 0 ? a.T : 1; t.t_valid = a.t_valid;
   t.m_tiles = (a.rows + TC_BM - 1) / TC_BM; t.n_tiles = a.N / bn;
-  t.utt_T = 0; t.utt_tpu = 1; t.tap_base = 0;
+  t.utt_T = 0; t.utt_tpu = 1; t.tap_base = 0; t.wb_rows = a.w_per_utt ? a.N : 0;
   if (utt) { t.utt_T = a.T; t.utt_tpu = (a.T + TC_BM - 1) / TC_BM; t.m_tiles = (a.rows / a.T) * t.utt_tpu; t.tap_base = a.tap_base; }
   t.xf_ab = reinterpret_cast<const uint4*>(a.xf_ab); t.xf_ld = a.xf_ld; t.xf_tv = a.xf_tv;
   t.pf_dist = (!utt && (a.taps == 1 || g_pf_all)) ? g_pf_dist : 0;
