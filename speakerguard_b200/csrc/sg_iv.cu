@@ -668,8 +668,9 @@ int sg_quad_expand_launch(const float* xa, int ldx, float* q, int ldq, int rows,
 }
 int sg_quad_expand_bwd_launch(const float* dq, int ldq, const float* xa, int ldx, const float* add, float* dx, int lddx,
                               int B, int T, int Tp, int F, cudaStream_t st) {
-  // (a warp-per-row form that reads each packed row once - warp sum for dx_i, per-lane accumulators for dx_j - was measured:
-  // 1.16 ms against 0.69 ms, its 72 dependent rounds of load + shuffle reduction are latency-bound)
+  // (measured without gain at 131 072 rows, 0.70 ms: a warp-per-row form that reads each packed row once - warp sum for dx_i,
+  // per-lane accumulators for dx_j: 1.16 ms, 72 dependent rounds of load + shuffle reduction; carried packed indices instead
+  // of min / max / multiply per term: 0.72 ms; the packed row staged in shared memory by float4 loads: 0.73 ms)
   quad_expand_bwd_kernel<<<B * Tp, 96, F * sizeof(float), st>>>(dq, ldq, xa, ldx, add, dx, lddx, T, Tp, F);
   SG_LAUNCH_CHECK();
   return SG_OK;

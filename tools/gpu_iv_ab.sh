@@ -8,4 +8,4 @@ python -c "
 import json; d=json.load(open('gpurun_out/${T}_iv.json')); print('iv', round(d['value']), d['ms_per_step'])"
 export SGB200_CUDA_GRAPH=0
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 150 -c 60 --csv --log-file gpurun_out/${T}_launches_iv.csv python bench.py --workload iv --steps 1 --warmup 0 --iters 5 --e2e-steps 0 --no-cpu-baseline --no-peak > /dev/null 2> gpurun_out/${T}_ncu_l.err
-python tools/launch_summary.py gpurun_out/${T}_launches_iv.csv 60 | grep -E "simt|conv_tc|split3|transpose|splitk"
+python tools/launch_summary.py gpurun_out/${T}_launches_iv.csv 60 | grep -E "quad|chol"
