@@ -848,7 +848,8 @@ int sg_conv_tc(const SgConvArgs& a, int precision, cudaStream_t st) {
   // (tests/test_gpu_shard.py).
   if (g_small_bn && !utt && !a.xf_ab && a.splitk_ws && !a.out_bf16 && !a.bits_out && a.N % 4 == 0 && a.ldo % 4 == 0 && a.N <= 512 &&
       (a.epilogue == SG_EPI_BIAS || a.epilogue == SG_EPI_NONE)) {
-    const int S = nkb_all >= 2048 ? 32 : (nkb_all >= 64 ? 8 : (nkb_all >= 16 ? 4 : 1));   // 32: the i-vector linear term, K = 3 F C
+    // 32 slices: the i-vector linear term, K = 3 F C (13 824 k-blocks at C = 2048; 1 728 at the C = 256 system of tests/test_gpu_iv.py)
+    const int S = nkb_all >= 1024 ? 32 : (nkb_all >= 64 ? 8 : (nkb_all >= 16 ? 4 : 1));
     const size_t need = (size_t)S * ((a.rows + TC_BM - 1) / TC_BM) * TC_BM * a.N;
     if (S > 1 && (S - 1) * ((nkb_all + S - 1) / S) < nkb_all) {
       if (need > a.splitk_floats) { sg_set_error("sg_conv_tc: split-K scratch too small (%zu floats needed, %zu given)", need, a.splitk_floats); return SG_EINVAL; }
