@@ -417,7 +417,7 @@ static int iv_embed_bwd(sg_handle* h, const float* demb, int B, int T, const IvW
     a.nbatch = B; a.strideA = (long long)Tp * C; a.strideW = (long long)C * Fa; a.strideO = (long long)Tp * Fa;
     SG_TRY(iv_gemm(h, a, st));
   }
-  IV_K(sg_quad_expand_bwd_launch(w.Q, m->Kq, w.Xa, Fa, w.dXa, dfeat, ld, B, T, Tp, F, st));
+  IV_K(sg_quad_expand_bwd_launch(w.Q, m->Kq, w.Xa, Fa, w.dXa, dfeat, ld, B, T, Tp, F, m->qidx, st));
   return SG_OK;
 }
 

@@ -155,6 +155,44 @@ __global__ void quad_expand_bwd_kernel(const float* __restrict__ dq, int ldq, co
     o[i] = g;
   }
 }
+// Same result (same terms, same order) from the symmetric matrix expanded in shared memory: the packed row is read once,
+// coalesced, and scattered to both (i, j) and (j, i) through the column -> factor-pair table of the forward kernel; every
+// output is then a float4 dot product of one padded matrix row with x.  The form above spends 22 instructions per term on the
+// packed index and the scattered load (635 M warp instructions at 131 072 rows: issue-bound at 0.70 ms; this one: 0.59 ms).
+__global__ void __launch_bounds__(128)
+quad_expand_bwd_sym_kernel(const float* __restrict__ dq, int ldq, const float* __restrict__ xa, int ldx,
+                           const float* __restrict__ add, float* __restrict__ dx, int lddx, int T, int Tp, int F,
+                           const uint32_t* __restrict__ idx) {
+  extern __shared__ float xs[];                                   // [F4] x, then M [F][LDM]
+  const int row = blockIdx.x, b = row / Tp, t = row - b * Tp;
+  if (t >= T) return;
+  const int F4 = (F + 3) & ~3, LDM = F4 + 4;                      // F = 72: rows 76 floats apart, conflict-free float4 reads
+  float* M = xs + F4;
+  const float* dr = dq + (size_t)row * ldq;
+  for (int i = threadIdx.x; i < F4; i += blockDim.x) xs[i] = i < F ? xa[(size_t)row * ldx + i] : 0.f;
+  for (int e = threadIdx.x; e < F * (F4 - F); e += blockDim.x) M[(e / (F4 - F)) * LDM + F + e % (F4 - F)] = 0.f;
+  const int P = F * (F + 1) / 2;
+  for (int p = threadIdx.x; p < P; p += blockDim.x) {
+    const uint32_t ij = __ldg(idx + F + p);
+    const int i = (int)(ij & 0xffffu), j = (int)(ij >> 16);
+    const float d = dr[F + p];
+    M[i * LDM + j] = (i == j) ? d * 2.f : d;
+    if (i != j) M[j * LDM + i] = d;
+  }
+  __syncthreads();
+  float* o = dx + ((size_t)b * T + t) * lddx;
+  for (int i = threadIdx.x; i < lddx; i += blockDim.x) {
+    if (i >= F) { o[i] = 0.f; continue; }
+    float g = dr[i] + add[(size_t)row * ldx + i];
+    const float4* mr = reinterpret_cast<const float4*>(M + i * LDM);
+    const float4* xv = reinterpret_cast<const float4*>(xs);
+    for (int q = 0; q < F4 / 4; ++q) {
+      const float4 m4 = mr[q], x4 = xv[q];
+      g = fmaf(m4.x, x4.x, g); g = fmaf(m4.y, x4.y, g); g = fmaf(m4.z, x4.z, g); g = fmaf(m4.w, x4.w, g);
+    }
+    o[i] = g;
+  }
+}
 // feat [B,T,ld] -> Xa [B*Tp, Fa] = [x, 1, 0...]; rows t >= T are zero
 __global__ void pad_aug_kernel(const float* __restrict__ feat, int ld, float* __restrict__ xa, int Fa, int B, int T, int Tp, int F) {
   const size_t n = (size_t)B * Tp * Fa;
@@ -667,7 +705,14 @@ int sg_quad_expand_launch(const float* xa, int ldx, float* q, int ldq, int rows,
   return SG_OK;
 }
 int sg_quad_expand_bwd_launch(const float* dq, int ldq, const float* xa, int ldx, const float* add, float* dx, int lddx,
-                              int B, int T, int Tp, int F, cudaStream_t st) {
+                              int B, int T, int Tp, int F, const uint32_t* idx, cudaStream_t st) {
+  const int F4 = (F + 3) & ~3;
+  const size_t sym = ((size_t)F4 + (size_t)F * (F4 + 4)) * sizeof(float);
+  if (idx && sym <= 48 * 1024) {
+    quad_expand_bwd_sym_kernel<<<B * Tp, 128, sym, st>>>(dq, ldq, xa, ldx, add, dx, lddx, T, Tp, F, idx);
+    SG_LAUNCH_CHECK();
+    return SG_OK;
+  }
   // (measured without gain at 131 072 rows, 0.70 ms: a warp-per-row form that reads each packed row once - warp sum for dx_i,
   // per-lane accumulators for dx_j: 1.16 ms, 72 dependent rounds of load + shuffle reduction; carried packed indices instead
   // of min / max / multiply per term: 0.72 ms; the packed row staged in shared memory by float4 loads: 0.73 ms)

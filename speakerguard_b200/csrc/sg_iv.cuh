@@ -8,7 +8,7 @@ int sg_pad_aug_launch(const float* feat, int ld, float* xa, int Fa, int B, int T
 int sg_quad_expand_launch(const float* xa, int ldx, float* q, int ldq, int rows, int F, int split3, int kseg, const uint32_t* idx,
                           cudaStream_t st);
 int sg_quad_expand_bwd_launch(const float* dq, int ldq, const float* xa, int ldx, const float* add, float* dx, int lddx,
-                              int B, int T, int Tp, int F, cudaStream_t st);
+                              int B, int T, int Tp, int F, const uint32_t* idx, cudaStream_t st);
 int sg_softmax_rows_launch(const float* a, const float* b, float* out, int rows, int C, int T, int Tp, int backward,
                            int split3, cudaStream_t st);
 int sg_chol_solve_launch(const float* Lp, int ldp, const float* rhs, int ldr, float offset, const float* emb_mean, double* fac,
